@@ -1,0 +1,371 @@
+// fp.cuh — 8x32-bit-limb Montgomery arithmetic for the two bn256 prime fields (Fr scalar field, Fq base field).
+//
+// Semantics contract (results are limb-identical to the reference because every value is kept fully reduced in
+// [0, p) and Montgomery multiplication has a unique canonical answer a*b*2^-256 mod p):
+//   add/sub/neg/double      -> reference arithmetic/curves/src/derive/field.rs:351-430, 488-500
+//   mul / square            -> reference derive/field.rs:502-562 (sparse CIOS) and :358-393 (square + montgomery_reduce :564-617)
+//   from_mont (to canonical)-> reference derive/field.rs:432-470 (montgomery_reduce_short), used by to_repr bn256/fr.rs:241-257
+// Constants                 -> reference bn256/fr.rs:29-118, bn256/fq.rs:28-90 (64-bit limbs split into 32-bit halves;
+//                              INV32 = INV mod 2^32).
+//
+// This is NOT a translation of the reference's 4x64 code: the limb width (32), the even/odd split carry chains and the
+// PTX mad.lo.cc/madc.hi.cc pairing (which ptxas fuses into IMAD.WIDE on sm_100a) are chosen for the B200 integer pipe.
+//
+// The same source compiles for the host (carry flag emulated in a thread-local) so the exact limb algorithm can be
+// unit-tested on a box without a GPU (tests/test_fp_host.py builds tools/fp_host_check.cu with nvcc -x cu host path).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CQB_HD __host__ __device__ __forceinline__
+#define CQB_D __device__ __forceinline__
+#else
+#define CQB_HD inline
+#define CQB_D inline
+#endif
+
+namespace cqb {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// carry-chain primitives: PTX on the device, emulation on the host
+// ---------------------------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define CQB_ASM_CC 1
+#else
+#define CQB_ASM_CC 0
+static thread_local uint32_t cqb_cf = 0;  // emulated carry/borrow flag (host only)
+#endif
+
+CQB_HD uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+CQB_HD uint32_t mul_hi(uint32_t a, uint32_t b) {
+#if CQB_ASM_CC
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+#if CQB_ASM_CC
+#define CQB_OP3(name, ptx)                                                                  \
+    CQB_D uint32_t name(uint32_t a, uint32_t b) {                                           \
+        uint32_t r;                                                                         \
+        asm volatile(ptx " %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));                        \
+        return r;                                                                           \
+    }
+#define CQB_OP4(name, ptx)                                                                  \
+    CQB_D uint32_t name(uint32_t a, uint32_t b, uint32_t c) {                               \
+        uint32_t r;                                                                         \
+        asm volatile(ptx " %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));            \
+        return r;                                                                           \
+    }
+CQB_OP3(add_cc, "add.cc.u32")
+CQB_OP3(addc_cc, "addc.cc.u32")
+CQB_OP3(addc, "addc.u32")
+CQB_OP3(sub_cc, "sub.cc.u32")
+CQB_OP3(subc_cc, "subc.cc.u32")
+CQB_OP3(subc, "subc.u32")
+CQB_OP4(mad_lo_cc, "mad.lo.cc.u32")
+CQB_OP4(madc_lo_cc, "madc.lo.cc.u32")
+CQB_OP4(mad_hi_cc, "mad.hi.cc.u32")
+CQB_OP4(madc_hi_cc, "madc.hi.cc.u32")
+CQB_OP4(madc_hi, "madc.hi.u32")
+CQB_OP4(madc_lo, "madc.lo.u32")
+#undef CQB_OP3
+#undef CQB_OP4
+#else
+inline uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b; cqb_cf = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b + cqb_cf; cqb_cf = (uint32_t)(s >> 32); return (uint32_t)s; }
+inline uint32_t addc(uint32_t a, uint32_t b) { return a + b + cqb_cf; }
+inline uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a - b; cqb_cf = (uint32_t)(s >> 63); return (uint32_t)s; }
+inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a - b - cqb_cf; cqb_cf = (uint32_t)(s >> 63); return (uint32_t)s; }
+inline uint32_t subc(uint32_t a, uint32_t b) { return a - b - cqb_cf; }
+inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc(a * b, c); }
+inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(a * b, c); }
+inline uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc(mul_hi(a, b), c); }
+inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(mul_hi(a, b), c); }
+inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return addc(mul_hi(a, b), c); }
+inline uint32_t madc_lo(uint32_t a, uint32_t b, uint32_t c) { return addc(a * b, c); }
+#endif
+
+// ---------------------------------------------------------------------------------------------------------------------
+// field parameters. mod(i)/r(i)/r2(i) are pure expressions of i so that, after full unrolling, they fold to immediates.
+// ---------------------------------------------------------------------------------------------------------------------
+#define CQB_SEL8(i, a0, a1, a2, a3, a4, a5, a6, a7) \
+    ((i) == 0 ? a0 : (i) == 1 ? a1 : (i) == 2 ? a2 : (i) == 3 ? a3 : (i) == 4 ? a4 : (i) == 5 ? a5 : (i) == 6 ? a6 : a7)
+
+// scalar field r (reference bn256/fr.rs:29-66)
+struct FrP {
+    static CQB_HD constexpr uint32_t mod(int i) {
+        return CQB_SEL8(i, 0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u);
+    }
+    static CQB_HD constexpr uint32_t inv() { return 0xefffffffu; }  // INV mod 2^32, fr.rs:39
+    static CQB_HD constexpr uint32_t r(int i) {                      // R = 2^256 mod r, fr.rs:43-48
+        return CQB_SEL8(i, 0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u);
+    }
+    static CQB_HD constexpr uint32_t r2(int i) {                     // R^2, fr.rs:52-57
+        return CQB_SEL8(i, 0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u);
+    }
+    static CQB_HD constexpr uint32_t r3(int i) {                     // R^3, fr.rs:61-66
+        return CQB_SEL8(i, 0xb4bf0040u, 0x5e94d8e1u, 0x1cfbb6b8u, 0x2a489cbeu, 0xa19fcfedu, 0x893cc664u, 0x7fcc657cu, 0x0cf8594bu);
+    }
+};
+
+// base field q (reference bn256/fq.rs:28-60)
+struct FqP {
+    static CQB_HD constexpr uint32_t mod(int i) {
+        return CQB_SEL8(i, 0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u);
+    }
+    static CQB_HD constexpr uint32_t inv() { return 0xe4866389u; }  // INV mod 2^32, fq.rs:37
+    static CQB_HD constexpr uint32_t r(int i) {                      // fq.rs:40-45
+        return CQB_SEL8(i, 0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u);
+    }
+    static CQB_HD constexpr uint32_t r2(int i) {                     // fq.rs:48-53
+        return CQB_SEL8(i, 0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u);
+    }
+    static CQB_HD constexpr uint32_t r3(int i) {                     // fq.rs:56-61
+        return CQB_SEL8(i, 0xda1530dfu, 0xb1cd6dafu, 0xa7283db6u, 0x62f210e6u, 0x0ada0afbu, 0xef7f0b0cu, 0x2d592544u, 0x20fd6e90u);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// field element: 8 little-endian 32-bit limbs == the reference's [u64;4] reinterpret-cast on a little-endian host
+// ---------------------------------------------------------------------------------------------------------------------
+template <class P>
+struct Fp {
+    uint32_t l[8];
+
+    static CQB_HD Fp zero() {
+        Fp z;
+#pragma unroll
+        for (int i = 0; i < 8; i++) z.l[i] = 0;
+        return z;
+    }
+    static CQB_HD Fp one() {  // Montgomery one = R
+        Fp z;
+#pragma unroll
+        for (int i = 0; i < 8; i++) z.l[i] = P::r(i);
+        return z;
+    }
+    static CQB_HD Fp r2() {
+        Fp z;
+#pragma unroll
+        for (int i = 0; i < 8; i++) z.l[i] = P::r2(i);
+        return z;
+    }
+    static CQB_HD Fp r3() {
+        Fp z;
+#pragma unroll
+        for (int i = 0; i < 8; i++) z.l[i] = P::r3(i);
+        return z;
+    }
+    CQB_HD bool is_zero() const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o |= l[i];
+        return o == 0;
+    }
+    CQB_HD bool operator==(const Fp& b) const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o |= (l[i] ^ b.l[i]);
+        return o == 0;
+    }
+    CQB_HD bool operator!=(const Fp& b) const { return !(*this == b); }
+};
+
+// r = a - p if a >= p else a      (a < 2p)
+template <class P>
+CQB_HD void fp_reduce_once(uint32_t* a) {
+    uint32_t t[8];
+    t[0] = sub_cc(a[0], P::mod(0));
+#pragma unroll
+    for (int i = 1; i < 8; i++) t[i] = subc_cc(a[i], P::mod(i));
+    uint32_t borrow = subc(0u, 0u);  // 0xffffffff if a < p
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = borrow ? a[i] : t[i];
+}
+
+// reference derive/field.rs:488-500 (sparse add: top limb cannot overflow because p < 2^254)
+template <class P>
+CQB_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
+    Fp<P> r;
+    r.l[0] = add_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
+    r.l[7] = addc(a.l[7], b.l[7]);
+    fp_reduce_once<P>(r.l);
+    return r;
+}
+
+// reference derive/field.rs:395-412
+template <class P>
+CQB_HD Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
+    Fp<P> r;
+    r.l[0] = sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) r.l[i] = subc_cc(a.l[i], b.l[i]);
+    uint32_t borrow = subc(0u, 0u);  // all-ones mask when a < b
+    r.l[0] = add_cc(r.l[0], P::mod(0) & borrow);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.l[i] = addc_cc(r.l[i], P::mod(i) & borrow);
+    r.l[7] = addc(r.l[7], P::mod(7) & borrow);
+    return r;
+}
+
+// reference derive/field.rs:351-354
+template <class P>
+CQB_HD Fp<P> fp_dbl(const Fp<P>& a) { return fp_add<P>(a, a); }
+
+// reference derive/field.rs:414-430
+template <class P>
+CQB_HD Fp<P> fp_neg(const Fp<P>& a) {
+    Fp<P> r;
+    r.l[0] = sub_cc(P::mod(0), a.l[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.l[i] = subc_cc(P::mod(i), a.l[i]);
+    r.l[7] = subc(P::mod(7), a.l[7]);
+    uint32_t nz = a.is_zero() ? 0u : 0xffffffffu;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] &= nz;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Montgomery multiplication, CIOS over 32-bit limbs with two interleaved accumulators.
+//
+// Products x[j]*y are 64 bits wide and land on limb j. Products of even j are chained into the accumulator aligned
+// on limb 0 (lo,hi,lo,hi,... = one unbroken carry chain); products of odd j go to a second accumulator aligned on limb 1.
+// After the reduction step limb 0 is zero and the frame moves up one limb: the two accumulators swap roles and the one
+// that becomes limb-1 aligned is re-read two limbs higher, so no data is ever moved. Every (mad.lo.cc, madc.hi.cc) pair
+// shares its operands, which is what lets ptxas emit one IMAD.WIDE per 32x32->64 product.
+// ---------------------------------------------------------------------------------------------------------------------
+
+// acc[0..7] = x[0,2,4,6]*y (fresh, no carries), acc[8] = 0
+CQB_HD void row_mul(uint32_t* acc, const uint32_t* x, uint32_t y) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        acc[j] = mul_lo(x[j], y);
+        acc[j + 1] = mul_hi(x[j], y);
+    }
+    acc[8] = 0;
+}
+
+// acc[0..8] += x[0,2,4,6]*y  (fresh carry chain)
+CQB_HD void row_mad(uint32_t* acc, const uint32_t* x, uint32_t y) {
+    acc[0] = mad_lo_cc(x[0], y, acc[0]);
+    acc[1] = madc_hi_cc(x[0], y, acc[1]);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+        acc[j] = madc_lo_cc(x[j], y, acc[j]);
+        acc[j + 1] = madc_hi_cc(x[j], y, acc[j + 1]);
+    }
+    acc[8] = addc(acc[8], 0u);
+}
+
+// acc[0..8] = (acc >> 64) + x[0,2,4,6]*y, with the incoming carry flag consumed at limb 0
+CQB_HD void row_madc_shift2(uint32_t* acc, const uint32_t* x, uint32_t y) {
+#pragma unroll
+    for (int j = 0; j < 6; j += 2) {
+        acc[j] = madc_lo_cc(x[j], y, acc[j + 2]);
+        acc[j + 1] = madc_hi_cc(x[j], y, acc[j + 3]);
+    }
+    acc[6] = madc_lo_cc(x[6], y, acc[8]);
+    acc[7] = madc_hi_cc(x[6], y, 0u);
+    acc[8] = addc(0u, 0u);
+}
+
+template <class P>
+CQB_HD void mod_limbs(uint32_t* m) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) m[i] = P::mod(i);
+}
+
+// reference derive/field.rs:502-562: result = a*b*2^-256 mod p, fully reduced
+template <class P>
+CQB_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+    uint32_t ev[9], od[9], p[8];
+    mod_limbs<P>(p);
+    uint32_t m;
+
+    // i = 0 : ev is limb-0 aligned, od is limb-1 aligned
+    row_mul(ev, a.l, b.l[0]);
+    row_mul(od, a.l + 1, b.l[0]);
+    m = ev[0] * P::inv();
+    row_mad(od, p + 1, m);
+    row_mad(ev, p, m);
+
+#pragma unroll
+    for (int i = 1; i < 8; i += 2) {
+        // odd i: od becomes limb-0 aligned, ev (read two limbs up) limb-1 aligned; ev[1] is the orphan at limb 0
+        od[0] = add_cc(od[0], ev[1]);
+        row_madc_shift2(ev, a.l + 1, b.l[i]);
+        row_mad(od, a.l, b.l[i]);
+        m = od[0] * P::inv();
+        row_mad(ev, p + 1, m);
+        row_mad(od, p, m);
+        if (i + 1 < 8) {
+            // even i+1: roles swap back
+            ev[0] = add_cc(ev[0], od[1]);
+            row_madc_shift2(od, a.l + 1, b.l[i + 1]);
+            row_mad(ev, a.l, b.l[i + 1]);
+            m = ev[0] * P::inv();
+            row_mad(od, p + 1, m);
+            row_mad(ev, p, m);
+        }
+    }
+    // after i = 7: od limb-0 aligned with od[0] == 0, ev limb-1 aligned. result = ev + (od >> 32)
+    Fp<P> r;
+    r.l[0] = add_cc(ev[0], od[1]);
+#pragma unroll
+    for (int k = 1; k < 7; k++) r.l[k] = addc_cc(ev[k], od[k + 1]);
+    r.l[7] = addc(ev[7], od[8]);
+    fp_reduce_once<P>(r.l);
+    return r;
+}
+
+// reference derive/field.rs:358-393. A dedicated squaring is an optimisation; the canonical result equals mul(a,a).
+template <class P>
+CQB_HD Fp<P> fp_sqr(const Fp<P>& a) { return fp_mul<P>(a, a); }
+
+// Montgomery -> canonical integer (multiply by 1): reference derive/field.rs:432-470 montgomery_reduce_short
+template <class P>
+CQB_HD Fp<P> fp_from_mont(const Fp<P>& a) {
+    Fp<P> one_raw = Fp<P>::zero();
+    one_raw.l[0] = 1;
+    return fp_mul<P>(a, one_raw);
+}
+// canonical integer (< p) -> Montgomery: multiply by R^2 (reference derive/field.rs:50-53 from_raw)
+template <class P>
+CQB_HD Fp<P> fp_to_mont(const Fp<P>& a) { return fp_mul<P>(a, Fp<P>::r2()); }
+
+// a^e for a 256-bit exponent given as 8 limbs (square-and-multiply, MSB first); used for inversion a^(p-2)
+// (reference bn256/fr.rs:200-209, fq.rs invert) — variable time is fine here, nothing is secret on this path.
+template <class P>
+CQB_HD Fp<P> fp_pow(const Fp<P>& a, const uint32_t* e) {
+    Fp<P> r = Fp<P>::one();
+    bool started = false;
+    for (int i = 7; i >= 0; i--) {
+        for (int b = 31; b >= 0; b--) {
+            if (started) r = fp_sqr<P>(r);
+            if ((e[i] >> b) & 1u) {
+                r = started ? fp_mul<P>(r, a) : a;
+                started = true;
+            }
+        }
+    }
+    return r;
+}
+
+template <class P>
+CQB_HD Fp<P> fp_inv(const Fp<P>& a) {  // returns 0 for 0, like invert().unwrap_or(zero)
+    uint32_t e[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) e[i] = P::mod(i);
+    e[0] -= 2u;  // both moduli have low limb >= 2, no borrow
+    return fp_pow<P>(a, e);
+}
+
+typedef Fp<FrP> Fr;
+typedef Fp<FqP> Fq;
+
+}  // namespace cqb
