@@ -1,0 +1,293 @@
+"""Pins the CPU oracle (oracle/bn254_oracle.c) against every known-answer test / identity the reference holds for this
+path and against an independent Python big-integer model (oracle/pyref.py).
+
+Reference KATs restated here:
+  bn256/fr.rs:320-345  root of unity, its inverse, DELTA          bn256/fr.rs:347-367 / fq.rs:331-351  from_u512(0xaa..)
+  bn256/fr.rs:29-118, fq.rs:28-90 constants R, R2, R3, INV, TWO_INV, ZETA
+  tests/field.rs:8-46  algebraic laws                               tests/curve.rs  curve laws, batch_normalize == to_affine
+  poly/kzg/commitment.rs:570-593  commit(ifft(a)) == commit_lagrange(a)
+"""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import pyref as P
+
+
+def L(x):
+    return P.int_to_limbs(x)
+
+
+def I(a):
+    return P.limbs_to_int(a)
+
+
+def test_field_constants(oracle):
+    O = oracle
+    for mod, op in ((P.R_MOD, O.fr_op), (P.Q_MOD, O.fq_op)):
+        one = L(P.MONT % mod)
+        # R2 / R3: from_raw(1) = 1*R2/R = R ; mul(R2,R2)/R = R3
+        assert I(op("from_raw", L(1))) == P.MONT % mod
+        r2 = L(P.MONT * P.MONT % mod)
+        assert I(op("mul", r2, r2)) == pow(P.MONT, 3, mod)
+        assert I(op("mul", one, one)) == P.MONT % mod
+    # fr.rs:320-345
+    root = O.fr_const("ROOT_OF_UNITY")
+    assert I(root) == P.to_mont(P.ROOT_OF_UNITY, P.R_MOD)
+    assert I(O.fr_pow(root, 1 << 28)) == P.MONT % P.R_MOD  # test_root_of_unity
+    assert I(O.fr_pow(root, 1 << 27)) != P.MONT % P.R_MOD
+    assert np.array_equal(O.fr_op("invert", root), O.fr_const("ROOT_OF_UNITY_INV"))  # test_inv_root_of_unity
+    assert np.array_equal(O.fr_pow(O.fr_const("GENERATOR"), 1 << 28), O.fr_const("DELTA"))  # test_delta
+    zeta = O.fr_const("ZETA")
+    assert I(zeta) == P.to_mont(P.ZETA, P.R_MOD)
+    assert I(O.fr_pow(zeta, 3)) == P.MONT % P.R_MOD and I(O.fr_pow(zeta, 2)) != P.MONT % P.R_MOD
+    two = O.fr_op("from_raw", L(2))
+    assert I(O.fr_op("mul", two, O.fr_const("TWO_INV"))) == P.MONT % P.R_MOD
+
+
+def test_from_u512_kats(oracle):
+    aa = np.array([0xAAAAAAAAAAAAAAAA] * 8, dtype=np.uint64)
+    # fr.rs:347-367
+    exp_fr = oracle.fr_op("from_raw", np.array([0x7E7140B5196B9E6F, 0x9ABAC9E4157B6172, 0xF04BC41062FD7322, 0x1185FA9C9FEF6326], np.uint64))
+    assert np.array_equal(oracle.fr_from_u512(aa), exp_fr)
+    # fq.rs:331-351
+    exp_fq = oracle.fq_op("from_raw", np.array([0x1F8905A172AFFA8A, 0xDE45AD177DCF3306, 0xAAA7987907D73AE2, 0x24D349431D468E30], np.uint64))
+    assert np.array_equal(oracle.fq_from_u512(aa), exp_fq)
+    big = int("aa" * 64, 16)
+    assert I(oracle.fr_from_u512(aa)) == P.to_mont(big % P.R_MOD, P.R_MOD)
+    assert I(oracle.fq_from_u512(aa)) == P.to_mont(big % P.Q_MOD, P.Q_MOD)
+
+
+@pytest.mark.parametrize("which", ["fr", "fq"])
+def test_field_ops_vs_bigint(oracle, which):
+    mod = P.R_MOD if which == "fr" else P.Q_MOD
+    op = oracle.fr_op if which == "fr" else oracle.fq_op
+    rng = random.Random(7)
+    Rinv = pow(P.MONT, -1, mod)
+    specials = [0, 1, 2, mod - 1, mod - 2, P.MONT % mod, (mod - 1) // 2, 1 << 253]
+    vals = specials + [rng.randrange(mod) for _ in range(300)]
+    for _ in range(600):
+        a, b = rng.choice(vals), rng.choice(vals)
+        assert I(op("add", L(a), L(b))) == (a + b) % mod
+        assert I(op("sub", L(a), L(b))) == (a - b) % mod
+        assert I(op("mul", L(a), L(b))) == a * b * Rinv % mod
+        assert I(op("square", L(a))) == a * a * Rinv % mod
+        assert I(op("neg", L(a))) == (-a) % mod
+        assert I(op("double", L(a))) == 2 * a % mod
+        assert I(op("from_mont", L(a))) == a * Rinv % mod
+    for a in vals[:40]:
+        inv = I(op("invert", L(a)))
+        assert inv == (0 if a == 0 else P.to_mont(pow(a * Rinv % mod, -1, mod), mod))
+
+
+def test_field_laws(oracle):
+    """arithmetic/curves/src/tests/field.rs:8-46 (seeded instead of XorShiftRng, which is not vendored)"""
+    rng = random.Random(11)
+    op = oracle.fr_op
+    for _ in range(200):
+        a, b, c = (L(rng.randrange(P.R_MOD)) for _ in range(3))
+        assert np.array_equal(op("mul", op("mul", a, b), c), op("mul", a, op("mul", b, c)))
+        assert np.array_equal(op("mul", a, op("add", b, c)), op("add", op("mul", a, b), op("mul", a, c)))
+        assert np.array_equal(op("square", a), op("mul", a, a))
+        assert np.array_equal(op("add", a, op("neg", a)), np.zeros(4, np.uint64))
+        if I(a):
+            assert I(op("mul", a, op("invert", a))) == P.MONT % P.R_MOD
+
+
+def _rand_point(rng):
+    return P.g1_mul(P.G1_GEN, rng.randrange(1, P.R_MOD))
+
+
+def test_curve_ops_vs_bigint(oracle):
+    """tests/curve.rs: on-curve, add / mixed add / double laws incl. the exceptional branches (curve.rs:818-824, 866-871)"""
+    O = oracle
+    rng = random.Random(3)
+    g = O.g1_generator()
+    assert P.g1_affine_to_ints(g)[0] == P.G1_GEN and O.g1_is_on_curve(g)
+    pts = [None, P.G1_GEN] + [_rand_point(rng) for _ in range(12)]
+    pts.append(P.g1_neg(pts[3]))
+    pts.append(pts[3])
+    aff = P.g1_affine_from_ints(pts)
+    for i in range(len(pts)):
+        assert O.g1_is_on_curve(aff[i])
+        ji = O.g1_to_curve(aff[i])
+        assert P.g1_affine_to_ints(O.g1_to_affine(O.g1_double(ji)))[0] == P.g1_add(pts[i], pts[i])
+        for k in range(len(pts)):
+            jk = O.g1_to_curve(aff[k])
+            exp = P.g1_add(pts[i], pts[k])
+            assert P.g1_affine_to_ints(O.g1_to_affine(O.g1_add_aa(aff[i], aff[k])))[0] == exp
+            assert P.g1_affine_to_ints(O.g1_to_affine(O.g1_add_ja(ji, aff[k])))[0] == exp
+            # non-trivial z on both sides
+            j2 = O.g1_double(O.g1_to_curve(aff[2]))
+            lhs = O.g1_add_jj(O.g1_add_jj(ji, j2), O.g1_add_jj(jk, O.g1_to_curve(O.g1_neg_a(O.g1_to_affine(j2)))))
+            assert P.g1_affine_to_ints(O.g1_to_affine(lhs))[0] == exp
+    # [r]G = identity, scalar mul vs bigint
+    for _ in range(4):
+        k = rng.randrange(P.R_MOD)
+        s = L(P.to_mont(k, P.R_MOD))
+        assert P.g1_affine_to_ints(O.g1_to_affine(O.g1_mul_a(g, s)))[0] == P.g1_mul(P.G1_GEN, k)
+        assert P.g1_affine_to_ints(O.g1_to_affine(O.g1_mul_j(O.g1_double(O.g1_to_curve(g)), s)))[0] == P.g1_mul(P.G1_GEN, 2 * k)
+    zero = np.zeros(4, np.uint64)
+    assert P.g1_affine_to_ints(O.g1_to_affine(O.g1_mul_a(g, zero)))[0] is None
+    rm1 = L(P.to_mont(P.R_MOD - 1, P.R_MOD))
+    assert P.g1_affine_to_ints(O.g1_to_affine(O.g1_mul_a(g, rm1)))[0] == P.g1_neg(P.G1_GEN)
+
+
+def test_batch_normalize_and_bytes(oracle):
+    O = oracle
+    rng = random.Random(5)
+    pts = [_rand_point(rng) for _ in range(6)]
+    jac = []
+    for i, p in enumerate(pts):
+        j = O.g1_to_curve(P.g1_affine_from_ints([p])[0])
+        for _ in range(i % 3):
+            j = O.g1_double(j)
+        jac.append(j)
+    jac.insert(2, np.zeros(12, np.uint64))  # identity in the middle is skipped (curve.rs:371-374)
+    jac = np.stack(jac)
+    bn = O.g1_batch_normalize(jac)
+    for i in range(jac.shape[0]):
+        assert np.array_equal(bn[i], O.g1_to_affine(jac[i]))  # tests/curve.rs batch_normalize == to_affine
+    for i in range(bn.shape[0]):
+        assert O.g1_to_bytes(bn[i]) == P.g1_compress(P.g1_affine_to_ints(bn[i])[0])
+
+
+@pytest.mark.parametrize("n,threads", [(1, 1), (3, 1), (5, 2), (31, 1), (33, 4), (200, 1), (200, 3), (257, 8)])
+def test_best_multiexp_vs_bigint(oracle, n, threads):
+    """arithmetic.rs:132-159; all three window rules (c=1, c=3, ceil(ln n)); chunked and unchunked"""
+    O = oracle
+    rng = random.Random(100 + n)
+    ks = [rng.randrange(1, 2000) for _ in range(n)]
+    pts = [P.g1_mul(P.G1_GEN, k) for k in ks]
+    sc = [rng.randrange(P.R_MOD) for _ in range(n)]
+    if n >= 5:
+        sc[0] = 0
+        sc[1] = P.R_MOD - 1
+        sc[2] = 1
+        pts[3] = None          # identity base (0,0)
+        pts[4] = pts[2]        # repeated point
+        ks[3] = 0
+        ks[4] = ks[2]
+    jac, aff = O.best_multiexp(P.fr_array_from_ints(sc), P.g1_affine_from_ints(pts), threads)
+    exp = P.g1_mul(P.G1_GEN, sum(s * k for s, k in zip(sc, ks)) % P.R_MOD)
+    assert P.g1_affine_to_ints(aff)[0] == exp
+    assert np.array_equal(O.g1_to_affine(jac), aff)
+
+
+def test_multiexp_thread_count_changes_jacobian_not_affine(oracle):
+    """raw Jacobian limbs depend on chunking; the affine normal form does not"""
+    O = oracle
+    sc = O.synth_scalars(1, 300)
+    bases = O.synth_bases(2, 300, 2)
+    j1, a1 = O.best_multiexp(sc, bases, 1)
+    j4, a4 = O.best_multiexp(sc, bases, 4)
+    assert np.array_equal(a1, a4)
+    assert not np.array_equal(j1, j4)
+
+
+@pytest.mark.parametrize("log_n", [1, 2, 3, 4, 6, 9])
+@pytest.mark.parametrize("threads", [1, 4])
+def test_best_fft_vs_definition(oracle, log_n, threads):
+    """arithmetic.rs:171-234: out[k] = sum_j a[j] omega^(jk); both the iterative (log_n <= log_threads) and recursive paths"""
+    O = oracle
+    rng = random.Random(log_n)
+    n = 1 << log_n
+    a = [rng.randrange(P.R_MOD) for _ in range(n)]
+    w = P.omega_for(log_n)
+    out = O.best_fft(P.fr_array_from_ints(a), L(P.to_mont(w, P.R_MOD)), log_n, threads)
+    assert P.fr_array_to_ints(out) == P.dft(a, w)
+
+
+def test_domain_and_coset_roundtrip(oracle):
+    """poly/domain.rs: new(), lagrange_to_coeff, coeff_to_extended, divide_by_vanishing_poly, extended_to_coeff"""
+    O = oracle
+    for j, k in ((3, 3), (4, 4), (5, 5)):
+        d = O.domain_new(j, k)
+        n = 1 << k
+        en = 1 << d.extended_k
+        assert en >= n * (j - 1) and (en >> 1) < n * (j - 1) or en == n
+        w = P.omega_for(k)
+        assert I(d.f("omega")) == P.to_mont(w, P.R_MOD)
+        assert I(d.f("omega_inv")) == P.to_mont(pow(w, -1, P.R_MOD), P.R_MOD)
+        assert I(d.f("ifft_divisor")) == P.to_mont(pow(n, -1, P.R_MOD), P.R_MOD)
+        assert I(d.f("g_coset")) == P.to_mont(P.ZETA, P.R_MOD)
+        ew = P.omega_for(d.extended_k)
+        te = P.fr_array_to_ints(d.t_evals())
+        for i, t in enumerate(te):
+            x = P.ZETA * pow(ew, i, P.R_MOD) % P.R_MOD
+            assert t == pow(pow(x, n, P.R_MOD) - 1, -1, P.R_MOD)
+        rng = random.Random(k)
+        coeffs = [rng.randrange(P.R_MOD) for _ in range(n)]
+        ev = P.dft(coeffs, w)
+        back = O.lagrange_to_coeff(d, P.fr_array_from_ints(ev))
+        assert P.fr_array_to_ints(back) == coeffs
+        ext = O.coeff_to_extended(d, P.fr_array_from_ints(coeffs))
+        ext_i = P.fr_array_to_ints(ext)
+        for i in (0, 1, 5, en - 1):
+            x = P.ZETA * pow(ew, i, P.R_MOD) % P.R_MOD
+            assert ext_i[i] == sum(c * pow(x, e, P.R_MOD) for e, c in enumerate(coeffs)) % P.R_MOD
+        rt = O.extended_to_coeff(d, ext)
+        rt_i = P.fr_array_to_ints(rt)
+        assert len(rt_i) == n * (j - 1)
+        assert rt_i[:n] == coeffs and all(v == 0 for v in rt_i[n:])
+        dv = P.fr_array_to_ints(O.divide_by_vanishing_poly(d, ext))
+        assert dv[3] == ext_i[3] * te[3 % len(te)] % P.R_MOD
+
+
+def test_commit_lagrange_identity(oracle):
+    """kzg/commitment.rs:570-593 test_commit_lagrange (K=6, a[i] = i): commit(ifft(a)) == commit_lagrange(a)"""
+    O = oracle
+    K = 6
+    s = O.synth_scalars(0xC0, 1)[0]
+    g, gl = O.params_setup(K, s)
+    s_int = P.fr_array_to_ints(s[None])[0]
+    # SRS sanity vs bigint: g[i] = [s^i]G ; sum of lagrange bases = G
+    assert P.g1_affine_to_ints(g[3])[0] == P.g1_mul(P.G1_GEN, pow(s_int, 3, P.R_MOD))
+    d = O.domain_new(1, K)
+    a = P.fr_array_from_ints(list(range(1 << K)))
+    b = O.lagrange_to_coeff(d, a)
+    _, c1 = O.best_multiexp(b, g, 2)
+    _, c2 = O.best_multiexp(a, gl, 3)
+    assert np.array_equal(c1, c2)
+    ones = P.fr_array_from_ints([1] * (1 << K))
+    _, sum_l = O.best_multiexp(ones, gl, 1)
+    assert P.g1_affine_to_ints(sum_l)[0] == P.G1_GEN
+
+
+def test_table_srs_and_sparse_commit(oracle):
+    """kzg/commitment.rs:73-178 (opening-at-0 identity) and static_lookup/prover.rs:167-170 sparse loop == dense MSM"""
+    O = oracle
+    N = 16
+    s = O.synth_scalars(0xC1, 1)[0]
+    g1, gl, op0 = O.table_srs_setup(N, s)
+    s_int = P.fr_array_to_ints(s[None])[0]
+    w = P.omega_for(4)
+    n_inv = pow(N, -1, P.R_MOD)
+    for i in (0, 1, 7, 15):
+        wi = pow(w, i, P.R_MOD)
+        li = (pow(s_int, N, P.R_MOD) - 1) * n_inv % P.R_MOD * wi % P.R_MOD * pow(s_int - wi, -1, P.R_MOD) % P.R_MOD
+        assert P.g1_affine_to_ints(gl[i])[0] == P.g1_mul(P.G1_GEN, li)
+        # (L_i(x) - L_i(0))/x with L_i(0) = 1/N
+        q = (li - n_inv) * pow(s_int, -1, P.R_MOD) % P.R_MOD
+        assert P.g1_affine_to_ints(op0[i])[0] == P.g1_mul(P.G1_GEN, q)
+    idx = np.array([1, 4, 9, 15], np.uint32)
+    sc = O.synth_scalars(9, 4)
+    sp = O.sparse_commit(gl, idx, sc)
+    dense = np.zeros((N, 4), np.uint64)
+    dense[idx] = sc
+    _, de = O.best_multiexp(dense, gl, 1)
+    assert np.array_equal(sp, de)
+
+
+def test_synth_inputs(oracle):
+    O = oracle
+    b1 = O.synth_bases(0xC0FFEE, 2050, 1)
+    b3 = O.synth_bases(0xC0FFEE, 2050, 3)
+    assert np.array_equal(b1, b3)
+    assert all(O.g1_is_on_curve(b1[i]) for i in (0, 1, 1023, 1024, 2049))
+    sc = O.synth_scalars(0xC0FFEE, 2)
+    s0, dd = P.fr_array_to_ints(sc)
+    assert P.g1_affine_to_ints(b1[5])[0] == P.g1_mul(P.G1_GEN, (s0 + 5 * dd) % P.R_MOD)
+    assert len({bytes(r) for r in b1}) == 2050
+    assert np.array_equal(O.synth_scalars(5, 10)[3:], O.synth_scalars(5, 7, start=3))
