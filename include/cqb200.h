@@ -1,0 +1,124 @@
+/* cqb200.h — C ABI of libcqb200.so: the B200-native replacement for the data-parallel hot path of
+ * aleph-zero-foundation/sha2-on-cq-halo2 (BN254 G1 multi-scalar multiplication + Fr NTT behind every KZG commitment).
+ *
+ * The reference has NO FFI/plugin interface: the boundary is two generic Rust free functions and two
+ * trait methods. Each entry point below names the reference interface it replaces (file:line in /root/reference); the
+ * Rust shim that binds them is rust-shim/ (source only; no Rust toolchain in this image) and INTEGRATION.md.
+ *
+ * Data layout (identical to the reference's in-memory layout on a little-endian host, so the shim passes slices as-is):
+ *   Fr / Fq   : 4 x uint64 little-endian limbs, Montgomery form (x * 2^256 mod p), always canonical (< p)
+ *               (arithmetic/curves/src/bn256/fr.rs:22-25, derive/field.rs:302-308 to_raw_bytes)
+ *   G1Affine  : x || y = 8 x uint64 (64 B); identity = all zero (derive/curve.rs:696-709, :667-685)
+ * MSM results are returned as the AFFINE normal form + an identity flag (only the affine form is
+ * canonical; the shim rebuilds G1 { x, y, z: one }).
+ *
+ * Conventions: every function returns 0 on success or a CQB_E_* code (the shim turns a non-zero code into the same
+ * panic the reference would raise, e.g. assert_eq!(coeffs.len(), bases.len()) arithmetic.rs:133). There is NO CPU
+ * fallback: without a CUDA device every compute entry point fails with CQB_E_NO_DEVICE. Calls are serialised per
+ * process by an internal mutex (re-entrant from multiple host threads; one process per GPU).
+ */
+#ifndef CQB200_H
+#define CQB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CQB_API __attribute__((visibility("default")))
+#else
+#define CQB_API
+#endif
+
+#define CQB_OK 0
+#define CQB_E_NO_DEVICE 1   /* no CUDA device / cqb_init not called */
+#define CQB_E_CUDA 2        /* a CUDA runtime call failed (see cqb_last_error) */
+#define CQB_E_BAD_ARG 3     /* NULL pointer, bad handle, offset+n beyond the registered bases ... */
+#define CQB_E_LEN_MISMATCH 4 /* the reference's assert_eq!(coeffs.len(), bases.len())  arithmetic.rs:133 */
+#define CQB_E_BAD_SIZE 5    /* the reference's assert_eq!(n, 1 << log_n) arithmetic.rs:184 / log_n > Fr::S = 28 */
+#define CQB_E_OOM 6
+
+typedef uint64_t cqb_bases_t; /* handle of a device-resident base set (an SRS: ParamsKZG.g / .g_lagrange, TableSRS.*) */
+
+/* ---- lifetime -------------------------------------------------------------------------------------------------- */
+CQB_API int cqb_init(int device);        /* bind this process to one GPU (one process per GPU); idempotent */
+CQB_API void cqb_shutdown(void);
+CQB_API const char* cqb_last_error(void);
+CQB_API int cqb_device_count(void);
+/* run all subsequent work on the caller's CUDA stream (cudaStream_t), e.g. torch.cuda.current_stream().cuda_stream;
+ * NULL restores the library's own stream */
+CQB_API int cqb_set_stream(void* cuda_stream);
+CQB_API int cqb_sync(void);
+CQB_API unsigned long long cqb_launch_count(void); /* kernels launched by this library so far (bench.py's gpu_launches) */
+
+/* ---- SRS residency: replaces the host Vec<G1Affine> of ParamsKZG { g, g_lagrange } (poly/kzg/commitment.rs:31-39)
+ *      and TableSRS { g1, g1_lagrange, g_lagrange_opening_at_0 } (:42-47) as MSM operands ------------------------- */
+CQB_API int cqb_bases_register(const uint64_t* affine_xy, size_t n, cqb_bases_t* out);        /* host -> device copy */
+CQB_API int cqb_bases_register_device(const void* d_affine_xy, size_t n, cqb_bases_t* out);  /* adopt device memory, no copy */
+CQB_API int cqb_bases_free(cqb_bases_t h);
+CQB_API size_t cqb_bases_len(cqb_bases_t h);
+
+/* ---- MSM: replaces best_multiexp (halo2_proofs/src/arithmetic.rs:132-159) as called by
+ *      Params::commit_lagrange (poly/kzg/commitment.rs:496-504), ParamsProver::commit (:539-543),
+ *      static_lookup/prover.rs:165,299,310, vanishing/prover.rs:58,101-105 ---------------------------------------- */
+/* sum_i scalars[i] * bases[offset + i], scalars on the host */
+CQB_API int cqb_msm_bn254_g1(cqb_bases_t b, size_t offset, const uint64_t* scalars, size_t n, uint64_t out_xy[8], int* is_inf);
+/* same, scalars already in device memory (bench "value": inputs resident in HBM) */
+CQB_API int cqb_msm_bn254_g1_dev(cqb_bases_t b, size_t offset, const void* d_scalars, size_t n, uint64_t out_xy[8], int* is_inf);
+/* one-shot: bases and scalars both on the host (exact best_multiexp(&[Fr], &[G1Affine]) shape) */
+CQB_API int cqb_msm_bn254_g1_host(const uint64_t* affine_xy, const uint64_t* scalars, size_t n, uint64_t out_xy[8], int* is_inf);
+/* sparse MSM sum_j scalars[j] * bases[idx[j]]: replaces the serial scalar-mul loops of the CQ prover for m(X), A(X),
+ * Q_A(X), A_0(X) (plonk/static_lookup/prover.rs:167-170, 245-257) */
+CQB_API int cqb_msm_bn254_g1_sparse(cqb_bases_t b, const uint32_t* idx, const uint64_t* scalars, size_t m, uint64_t out_xy[8],
+                            int* is_inf);
+/* sum of n affine points (host): the final fold of per-GPU partial results of a point-range-sharded MSM — the
+ * multi-GPU analogue of results.iter().fold(identity, |a, b| a + b), arithmetic.rs:153 */
+CQB_API int cqb_g1_sum_affine(const uint64_t* affine_xy, size_t n, uint64_t out_xy[8], int* is_inf);
+
+/* ---- NTT: replaces best_fft::<Fr> (halo2_proofs/src/arithmetic.rs:171-234) and its EvaluationDomain wrappers ---- */
+/* in place, natural order in and out: a[k] <- sum_j a[j] omega^(jk); n = 1 << log_n (arithmetic.rs:184) */
+CQB_API int cqb_ntt_bn254_fr(uint64_t* a, const uint64_t omega[4], uint32_t log_n);
+CQB_API int cqb_ntt_bn254_fr_dev(void* d_a, const uint64_t omega[4], uint32_t log_n);
+/* EvaluationDomain::ifft (poly/domain.rs:366-374): best_fft(omega_inv) then * divisor */
+CQB_API int cqb_intt_bn254_fr(uint64_t* a, const uint64_t omega_inv[4], const uint64_t divisor[4], uint32_t log_n);
+CQB_API int cqb_intt_bn254_fr_dev(void* d_a, const uint64_t omega_inv[4], const uint64_t divisor[4], uint32_t log_n);
+/* EvaluationDomain::coeff_to_extended (poly/domain.rs:252-266): a[i] *= {1, g_coset, g_coset_inv}[i % 3]
+ * (distribute_powers_zeta :347-363), zero-pad n -> 2^ext_log_n, best_fft(extended_omega). out has 2^ext_log_n elements. */
+CQB_API int cqb_coset_ntt_bn254_fr(const uint64_t* coeffs, size_t n, uint64_t* out, const uint64_t ext_omega[4],
+                           uint32_t ext_log_n, const uint64_t g_coset[4], const uint64_t g_coset_inv[4]);
+CQB_API int cqb_coset_ntt_bn254_fr_dev(const void* d_coeffs, size_t n, void* d_out, const uint64_t ext_omega[4],
+                               uint32_t ext_log_n, const uint64_t g_coset[4], const uint64_t g_coset_inv[4]);
+/* EvaluationDomain::divide_by_vanishing_poly (poly/domain.rs:319-338, skipped when t_evaluations == NULL) followed by
+ * extended_to_coeff (:293-315): a[i] *= t_evaluations[i % t_len]; ifft(extended_omega_inv, extended_ifft_divisor);
+ * a[i] *= {1, g_coset_inv, g_coset}[i % 3]. In place on 2^ext_log_n elements; the caller truncates to
+ * n * quotient_poly_degree as the reference does (:311-312). */
+CQB_API int cqb_coset_intt_bn254_fr(uint64_t* a, uint32_t ext_log_n, const uint64_t ext_omega_inv[4],
+                            const uint64_t ext_divisor[4], const uint64_t g_coset[4], const uint64_t g_coset_inv[4],
+                            const uint64_t* t_evaluations, uint32_t t_len);
+CQB_API int cqb_coset_intt_bn254_fr_dev(void* d_a, uint32_t ext_log_n, const uint64_t ext_omega_inv[4],
+                                const uint64_t ext_divisor[4], const uint64_t g_coset[4], const uint64_t g_coset_inv[4],
+                                const uint64_t* t_evaluations, uint32_t t_len);
+
+/* ---- synthetic inputs generated on the device; same definition as oracle_synth_* ------------- */
+/* scalars[i] = Fr::from_u512(splitmix64 stream(seed, start + i))  (mirrors Fr::random, bn256/fr.rs:159-170) */
+CQB_API int cqb_synth_scalars_dev(uint64_t seed, size_t start, size_t n, void* d_out);
+/* bases[i] = [s0 + (start + i) d] G, (s0, d) = first two scalars of stream `seed`; affine, normalised on the device */
+CQB_API int cqb_synth_bases_dev(uint64_t seed, size_t start, size_t n, void* d_out);
+
+/* ---- plain device memory helpers so non-CUDA hosts (ctypes, the Rust shim) need no CUDA binding of their own ---- */
+CQB_API int cqb_dev_alloc(size_t bytes, void** d_out);
+CQB_API int cqb_dev_free(void* d);
+CQB_API int cqb_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes);
+CQB_API int cqb_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes);
+CQB_API int cqb_host_alloc_pinned(size_t bytes, void** h_out);
+CQB_API int cqb_host_free_pinned(void* h);
+
+/* tuning knobs for experiments (0 = automatic): MSM window bits */
+CQB_API int cqb_msm_set_window_bits(int c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CQB200_H */

@@ -1,0 +1,113 @@
+"""ctypes binding of libcqb200.so (include/cqb200.h). The library is the product; there is no CPU fallback: if the
+shared object is missing or no CUDA device is visible, every compute call raises."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libcqb200.so")
+
+u64p = ctypes.POINTER(ctypes.c_uint64)
+u32p = ctypes.POINTER(ctypes.c_uint32)
+
+CQB_OK, CQB_E_NO_DEVICE, CQB_E_CUDA, CQB_E_BAD_ARG, CQB_E_LEN_MISMATCH, CQB_E_BAD_SIZE, CQB_E_OOM = range(7)
+
+# every symbol include/cqb200.h declares: (name, restype, argtypes)
+_vp, _sz, _u64, _u32, _int = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int
+_ip = ctypes.POINTER(ctypes.c_int)
+SYMBOLS = [
+    ("cqb_init", _int, [_int]),
+    ("cqb_shutdown", None, []),
+    ("cqb_last_error", ctypes.c_char_p, []),
+    ("cqb_device_count", _int, []),
+    ("cqb_set_stream", _int, [_vp]),
+    ("cqb_sync", _int, []),
+    ("cqb_launch_count", ctypes.c_ulonglong, []),
+    ("cqb_bases_register", _int, [u64p, _sz, u64p]),
+    ("cqb_bases_register_device", _int, [_vp, _sz, u64p]),
+    ("cqb_bases_free", _int, [_u64]),
+    ("cqb_bases_len", _sz, [_u64]),
+    ("cqb_msm_bn254_g1", _int, [_u64, _sz, u64p, _sz, u64p, _ip]),
+    ("cqb_msm_bn254_g1_dev", _int, [_u64, _sz, _vp, _sz, u64p, _ip]),
+    ("cqb_msm_bn254_g1_host", _int, [u64p, u64p, _sz, u64p, _ip]),
+    ("cqb_msm_bn254_g1_sparse", _int, [_u64, u32p, u64p, _sz, u64p, _ip]),
+    ("cqb_g1_sum_affine", _int, [u64p, _sz, u64p, _ip]),
+    ("cqb_ntt_bn254_fr", _int, [u64p, u64p, _u32]),
+    ("cqb_ntt_bn254_fr_dev", _int, [_vp, u64p, _u32]),
+    ("cqb_intt_bn254_fr", _int, [u64p, u64p, u64p, _u32]),
+    ("cqb_intt_bn254_fr_dev", _int, [_vp, u64p, u64p, _u32]),
+    ("cqb_coset_ntt_bn254_fr", _int, [u64p, _sz, u64p, u64p, _u32, u64p, u64p]),
+    ("cqb_coset_ntt_bn254_fr_dev", _int, [_vp, _sz, _vp, u64p, _u32, u64p, u64p]),
+    ("cqb_coset_intt_bn254_fr", _int, [u64p, _u32, u64p, u64p, u64p, u64p, u64p, _u32]),
+    ("cqb_coset_intt_bn254_fr_dev", _int, [_vp, _u32, u64p, u64p, u64p, u64p, u64p, _u32]),
+    ("cqb_synth_scalars_dev", _int, [_u64, _sz, _sz, _vp]),
+    ("cqb_synth_bases_dev", _int, [_u64, _sz, _sz, _vp]),
+    ("cqb_dev_alloc", _int, [_sz, ctypes.POINTER(_vp)]),
+    ("cqb_dev_free", _int, [_vp]),
+    ("cqb_memcpy_h2d", _int, [_vp, _vp, _sz]),
+    ("cqb_memcpy_d2h", _int, [_vp, _vp, _sz]),
+    ("cqb_host_alloc_pinned", _int, [_sz, ctypes.POINTER(_vp)]),
+    ("cqb_host_free_pinned", _int, [_vp]),
+    ("cqb_msm_set_window_bits", _int, [_int]),
+]
+
+
+class CqbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libcqb200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+_inited_device = None
+
+
+def load():
+    """dlopen the in-tree library and bind every declared symbol; raises if the extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise ImportError(
+                f"{SO_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback for this path)")
+        lib = ctypes.CDLL(SO_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(lib, name)  # AttributeError here means header and library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise CqbError(rc, load().cqb_last_error().decode("utf-8", "replace"))
+
+
+def init(device=None):
+    """Bind this process to one GPU (one process per GPU). Raises CqbError(CQB_E_NO_DEVICE) without a GPU."""
+    global _inited_device
+    lib = load()
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if _inited_device != device:
+        check(lib.cqb_init(device))
+        _inited_device = device
+    return lib
+
+
+def lib():
+    if _inited_device is None:
+        return init()
+    return _lib
+
+
+def p64(a):
+    return a.ctypes.data_as(u64p)
+
+
+def fr_limbs(x):
+    a = np.ascontiguousarray(x, dtype=np.uint64).reshape(-1)
+    assert a.shape[0] == 4
+    return a

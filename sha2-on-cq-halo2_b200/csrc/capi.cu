@@ -1,0 +1,497 @@
+// capi.cu — the C ABI of libcqb200.so (include/cqb200.h). Each entry point names the reference interface it replaces
+// in the header. No CPU fallback anywhere: without a device every compute call fails with CQB_E_NO_DEVICE.
+#include <stdarg.h>
+
+#include <map>
+#include <mutex>
+
+#include "internal.h"
+
+namespace cqb {
+
+static Ctx g_ctx;
+Ctx& ctx() { return g_ctx; }
+static std::recursive_mutex g_mu;
+static thread_local char g_errbuf[512];
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_errbuf, sizeof(g_errbuf), fmt, ap);
+    va_end(ap);
+    g_ctx.last_error = g_errbuf;
+    return code;
+}
+
+int Scratch::ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) {
+        cudaStreamSynchronize(g_ctx.stream);
+        cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    size_t want = bytes + bytes / 8;  // headroom so slightly larger follow-up calls do not reallocate
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            p = nullptr;
+            return fail(CQB_E_OOM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        }
+    }
+    cap = want;
+    return 0;
+}
+void Scratch::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+int Pinned::ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        p = nullptr;
+        return fail(CQB_E_OOM, "cudaMallocHost(%zu) failed", bytes);
+    }
+    cap = bytes;
+    return 0;
+}
+void Pinned::release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+}
+
+struct BaseSet { void* d; size_t n; bool owned; };
+static std::map<cqb_bases_t, BaseSet> g_bases;
+static cqb_bases_t g_next_handle = 1;
+static Scratch g_scalars, g_idx, g_io, g_tmp_bases, g_out;
+static Pinned g_out_host;
+
+static int require_init() {
+    if (!g_ctx.inited) return fail(CQB_E_NO_DEVICE, "cqb_init() has not been called or no CUDA device is available (there is no CPU fallback)");
+    return 0;
+}
+
+static int fetch_result(uint64_t out_xy[8], int* is_inf) {
+    CQB_TRY(g_out_host.ensure(128));
+    CQB_CUDA(cudaMemcpyAsync(g_out_host.p, g_out.p, 80, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    memcpy(out_xy, g_out_host.p, 64);
+    if (is_inf) *is_inf = (int)((uint32_t*)g_out_host.p)[16];
+    return 0;
+}
+
+static Fr fr_arg(const uint64_t* p) { return fr_from_u64x4(p); }
+
+}  // namespace cqb
+
+using namespace cqb;
+#define LOCK std::lock_guard<std::recursive_mutex> _lk(g_mu)
+
+extern "C" {
+
+int cqb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int cqb_init(int device) {
+    LOCK;
+    if (g_ctx.inited && g_ctx.device == device) return 0;
+    int n = cqb_device_count();
+    if (n <= 0) return fail(CQB_E_NO_DEVICE, "no CUDA device visible (there is no CPU fallback)");
+    if (device < 0 || device >= n) return fail(CQB_E_BAD_ARG, "device %d out of range (%d visible)", device, n);
+    if (g_ctx.inited) cqb_shutdown();
+    CQB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CQB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(CQB_E_NO_DEVICE, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+    g_ctx.device = device;
+    g_ctx.sm_count = prop.multiProcessorCount;
+    CQB_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    g_ctx.own_stream = true;
+    g_ctx.inited = true;
+    g_ctx.launches = 0;
+    CQB_TRY(g_out.ensure(256));
+    return 0;
+}
+
+void cqb_shutdown(void) {
+    LOCK;
+    if (!g_ctx.inited) return;
+    cudaSetDevice(g_ctx.device);
+    cudaDeviceSynchronize();
+    for (auto& kv : g_bases)
+        if (kv.second.owned) cudaFree(kv.second.d);
+    g_bases.clear();
+    g_scalars.release(); g_idx.release(); g_io.release(); g_tmp_bases.release(); g_out.release();
+    g_out_host.release();
+    ntt_release_all();
+    msm_release_all();
+    gen_release_all();
+    if (g_ctx.own_stream && g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
+    g_ctx.stream = nullptr;
+    g_ctx.own_stream = false;
+    g_ctx.inited = false;
+}
+
+const char* cqb_last_error(void) { return g_ctx.last_error.c_str(); }
+
+int cqb_set_stream(void* cuda_stream) {
+    LOCK;
+    CQB_TRY(require_init());
+    CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    if (cuda_stream == nullptr) {
+        if (!g_ctx.own_stream) {
+            CQB_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+            g_ctx.own_stream = true;
+        }
+        return 0;
+    }
+    if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.stream);
+    g_ctx.stream = (cudaStream_t)cuda_stream;
+    g_ctx.own_stream = false;
+    return 0;
+}
+
+int cqb_sync(void) {
+    LOCK;
+    CQB_TRY(require_init());
+    CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return 0;
+}
+
+unsigned long long cqb_launch_count(void) { return g_ctx.launches; }
+
+// ---- bases ------------------------------------------------------------------------------------------------------
+int cqb_bases_register(const uint64_t* affine_xy, size_t n, cqb_bases_t* out) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!out || (!affine_xy && n)) return fail(CQB_E_BAD_ARG, "cqb_bases_register: NULL argument");
+    void* d = nullptr;
+    if (cudaMalloc(&d, n ? n * 64 : 64) != cudaSuccess) return fail(CQB_E_OOM, "cudaMalloc(%zu) for bases failed", n * 64);
+    if (n) CQB_CUDA(cudaMemcpyAsync(d, affine_xy, n * 64, cudaMemcpyHostToDevice, g_ctx.stream));
+    CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    cqb_bases_t h = g_next_handle++;
+    g_bases[h] = BaseSet{d, n, true};
+    *out = h;
+    return 0;
+}
+int cqb_bases_register_device(const void* d_affine_xy, size_t n, cqb_bases_t* out) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!out || !d_affine_xy) return fail(CQB_E_BAD_ARG, "cqb_bases_register_device: NULL argument");
+    cqb_bases_t h = g_next_handle++;
+    g_bases[h] = BaseSet{const_cast<void*>(d_affine_xy), n, false};
+    *out = h;
+    return 0;
+}
+int cqb_bases_free(cqb_bases_t h) {
+    LOCK;
+    auto it = g_bases.find(h);
+    if (it == g_bases.end()) return fail(CQB_E_BAD_ARG, "unknown bases handle %llu", (unsigned long long)h);
+    if (it->second.owned) {
+        cudaStreamSynchronize(g_ctx.stream);
+        cudaFree(it->second.d);
+    }
+    g_bases.erase(it);
+    return 0;
+}
+size_t cqb_bases_len(cqb_bases_t h) {
+    LOCK;
+    auto it = g_bases.find(h);
+    return it == g_bases.end() ? 0 : it->second.n;
+}
+
+// ---- MSM --------------------------------------------------------------------------------------------------------
+static int find_bases(cqb_bases_t h, size_t offset, size_t n, const char** d) {
+    auto it = g_bases.find(h);
+    if (it == g_bases.end()) return fail(CQB_E_BAD_ARG, "unknown bases handle %llu", (unsigned long long)h);
+    // commit / commit_lagrange: assert!(self.n() >= size) poly/kzg/commitment.rs:502,541
+    if (offset > it->second.n || n > it->second.n - offset)
+        return fail(CQB_E_LEN_MISMATCH, "MSM of %zu scalars at offset %zu exceeds the %zu registered bases", n, offset, it->second.n);
+    *d = (const char*)it->second.d + offset * 64;
+    return 0;
+}
+
+int cqb_msm_bn254_g1_dev(cqb_bases_t b, size_t offset, const void* d_scalars, size_t n, uint64_t out_xy[8], int* is_inf) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!out_xy || (!d_scalars && n)) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1_dev: NULL argument");
+    const char* d_bases = nullptr;
+    CQB_TRY(find_bases(b, offset, n, &d_bases));
+    CQB_TRY(msm_run(d_bases, d_scalars, nullptr, n, g_out.p));
+    return fetch_result(out_xy, is_inf);
+}
+
+int cqb_msm_bn254_g1(cqb_bases_t b, size_t offset, const uint64_t* scalars, size_t n, uint64_t out_xy[8], int* is_inf) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!out_xy || (!scalars && n)) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1: NULL argument");
+    const char* d_bases = nullptr;
+    CQB_TRY(find_bases(b, offset, n, &d_bases));
+    CQB_TRY(g_scalars.ensure(n * 32 + 32));
+    if (n) CQB_CUDA(cudaMemcpyAsync(g_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, g_ctx.stream));
+    CQB_TRY(msm_run(d_bases, g_scalars.p, nullptr, n, g_out.p));
+    return fetch_result(out_xy, is_inf);
+}
+
+int cqb_msm_bn254_g1_host(const uint64_t* affine_xy, const uint64_t* scalars, size_t n, uint64_t out_xy[8], int* is_inf) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!out_xy || ((!scalars || !affine_xy) && n)) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1_host: NULL argument");
+    CQB_TRY(g_tmp_bases.ensure(n * 64 + 64));
+    CQB_TRY(g_scalars.ensure(n * 32 + 32));
+    if (n) {
+        CQB_CUDA(cudaMemcpyAsync(g_tmp_bases.p, affine_xy, n * 64, cudaMemcpyHostToDevice, g_ctx.stream));
+        CQB_CUDA(cudaMemcpyAsync(g_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, g_ctx.stream));
+    }
+    CQB_TRY(msm_run(g_tmp_bases.p, g_scalars.p, nullptr, n, g_out.p));
+    return fetch_result(out_xy, is_inf);
+}
+
+int cqb_msm_bn254_g1_sparse(cqb_bases_t b, const uint32_t* idx, const uint64_t* scalars, size_t m, uint64_t out_xy[8], int* is_inf) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!out_xy || ((!scalars || !idx) && m)) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1_sparse: NULL argument");
+    auto it = g_bases.find(b);
+    if (it == g_bases.end()) return fail(CQB_E_BAD_ARG, "unknown bases handle %llu", (unsigned long long)b);
+    for (size_t j = 0; j < m; j++)  // the reference would panic on an out-of-range table index (slice indexing)
+        if (idx[j] >= it->second.n) return fail(CQB_E_BAD_ARG, "sparse index %u out of range (%zu bases)", idx[j], it->second.n);
+    CQB_TRY(g_scalars.ensure(m * 32 + 32));
+    CQB_TRY(g_idx.ensure(m * 4 + 4));
+    if (m) {
+        CQB_CUDA(cudaMemcpyAsync(g_scalars.p, scalars, m * 32, cudaMemcpyHostToDevice, g_ctx.stream));
+        CQB_CUDA(cudaMemcpyAsync(g_idx.p, idx, m * 4, cudaMemcpyHostToDevice, g_ctx.stream));
+    }
+    CQB_TRY(msm_run(it->second.d, g_scalars.p, g_idx.as<uint32_t>(), m, g_out.p));
+    return fetch_result(out_xy, is_inf);
+}
+
+int cqb_g1_sum_affine(const uint64_t* affine_xy, size_t n, uint64_t out_xy[8], int* is_inf) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!out_xy || (!affine_xy && n)) return fail(CQB_E_BAD_ARG, "cqb_g1_sum_affine: NULL argument");
+    CQB_TRY(g_tmp_bases.ensure(n * 64 + 64));
+    if (n) CQB_CUDA(cudaMemcpyAsync(g_tmp_bases.p, affine_xy, n * 64, cudaMemcpyHostToDevice, g_ctx.stream));
+    CQB_TRY(g1_sum_affine_run(g_tmp_bases.p, n, g_out.p));
+    return fetch_result(out_xy, is_inf);
+}
+
+// ---- NTT --------------------------------------------------------------------------------------------------------
+static int check_log_n(uint32_t log_n) {
+    if (log_n > 28) return fail(CQB_E_BAD_SIZE, "log_n = %u exceeds Fr::S = 28 (bn256/fr.rs:72)", log_n);
+    return 0;
+}
+
+int cqb_ntt_bn254_fr_dev(void* d_a, const uint64_t omega[4], uint32_t log_n) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!d_a || !omega) return fail(CQB_E_BAD_ARG, "cqb_ntt_bn254_fr_dev: NULL argument");
+    CQB_TRY(check_log_n(log_n));
+    NttFused f;
+    return ntt_run(d_a, d_a, log_n, omega, f);
+}
+
+int cqb_intt_bn254_fr_dev(void* d_a, const uint64_t omega_inv[4], const uint64_t divisor[4], uint32_t log_n) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!d_a || !omega_inv || !divisor) return fail(CQB_E_BAD_ARG, "cqb_intt_bn254_fr_dev: NULL argument");
+    CQB_TRY(check_log_n(log_n));
+    NttFused f;
+    f.post_mode = 1;
+    f.post[0] = fr_arg(divisor);
+    return ntt_run(d_a, d_a, log_n, omega_inv, f);
+}
+
+int cqb_coset_ntt_bn254_fr_dev(const void* d_coeffs, size_t n, void* d_out, const uint64_t ext_omega[4], uint32_t ext_log_n,
+                               const uint64_t g_coset[4], const uint64_t g_coset_inv[4]) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!d_coeffs || !d_out || !ext_omega || !g_coset || !g_coset_inv) return fail(CQB_E_BAD_ARG, "cqb_coset_ntt_bn254_fr_dev: NULL argument");
+    CQB_TRY(check_log_n(ext_log_n));
+    if (n > ((size_t)1 << ext_log_n)) return fail(CQB_E_BAD_SIZE, "coset NTT: %zu coefficients do not fit 2^%u", n, ext_log_n);
+    NttFused f;
+    f.n_in = n;
+    if (n == 0) {  // all-zero polynomial
+        CQB_CUDA(cudaMemsetAsync(d_out, 0, ((size_t)32) << ext_log_n, g_ctx.stream));
+        return 0;
+    }
+    f.pre_mode = 1;  // distribute_powers_zeta(into_coset = true): [1, g_coset, g_coset_inv][i % 3]  domain.rs:347-363
+    f.pre[0] = Fr::one();
+    f.pre[1] = fr_arg(g_coset);
+    f.pre[2] = fr_arg(g_coset_inv);
+    return ntt_run(d_coeffs, d_out, ext_log_n, ext_omega, f);
+}
+
+static Scratch g_tev;
+int cqb_coset_intt_bn254_fr_dev(void* d_a, uint32_t ext_log_n, const uint64_t ext_omega_inv[4], const uint64_t ext_divisor[4],
+                                const uint64_t g_coset[4], const uint64_t g_coset_inv[4], const uint64_t* t_evaluations,
+                                uint32_t t_len) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!d_a || !ext_omega_inv || !ext_divisor || !g_coset || !g_coset_inv) return fail(CQB_E_BAD_ARG, "cqb_coset_intt_bn254_fr_dev: NULL argument");
+    CQB_TRY(check_log_n(ext_log_n));
+    NttFused f;
+    if (t_evaluations) {
+        if (t_len == 0 || (t_len & (t_len - 1)) || t_len > ((size_t)1 << ext_log_n))
+            return fail(CQB_E_BAD_ARG, "t_evaluations length %u must be a power of two <= 2^%u (domain.rs:100)", t_len, ext_log_n);
+        if (t_len <= (uint32_t)NTT_PRE_MAX_PUB) {
+            f.pre_mode = 2;
+            f.pre_len = (int)t_len;
+            for (uint32_t i = 0; i < t_len; i++) f.pre[i] = fr_arg(t_evaluations + 4 * i);
+        } else {  // long table: separate element-wise pass (divide_by_vanishing_poly, domain.rs:319-338)
+            CQB_TRY(g_tev.ensure((size_t)t_len * 32));
+            CQB_CUDA(cudaMemcpyAsync(g_tev.p, t_evaluations, (size_t)t_len * 32, cudaMemcpyHostToDevice, g_ctx.stream));
+            CQB_TRY(fr_scale_table(d_a, (size_t)1 << ext_log_n, g_tev.p, t_len));
+        }
+    }
+    // ifft divisor and distribute_powers_zeta(into_coset = false) = [1, g_coset_inv, g_coset][i % 3] fused: the field is
+    // exact, so (a * divisor) * cp == a * (divisor * cp)
+    Fr dv = fr_arg(ext_divisor);
+    f.post_mode = 2;
+    f.post[0] = dv;
+    f.post[1] = fp_mul<FrP>(dv, fr_arg(g_coset_inv));
+    f.post[2] = fp_mul<FrP>(dv, fr_arg(g_coset));
+    return ntt_run(d_a, d_a, ext_log_n, ext_omega_inv, f);
+}
+
+// host-buffer variants: H2D, device path, D2H
+static int with_host_buffer(uint64_t* a, size_t n_in, size_t n_out, int (*body)(void* d, void* user), void* user) {
+    size_t cap = (n_in > n_out ? n_in : n_out) * 32;
+    CQB_TRY(g_io.ensure(cap + 32));
+    if (n_in) CQB_CUDA(cudaMemcpyAsync(g_io.p, a, n_in * 32, cudaMemcpyHostToDevice, g_ctx.stream));
+    CQB_TRY(body(g_io.p, user));
+    if (n_out) CQB_CUDA(cudaMemcpyAsync(a, g_io.p, n_out * 32, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return 0;
+}
+
+int cqb_ntt_bn254_fr(uint64_t* a, const uint64_t omega[4], uint32_t log_n) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!a || !omega) return fail(CQB_E_BAD_ARG, "cqb_ntt_bn254_fr: NULL argument");
+    CQB_TRY(check_log_n(log_n));
+    struct U { const uint64_t* w; uint32_t l; } u{omega, log_n};
+    size_t n = (size_t)1 << log_n;
+    return with_host_buffer(a, n, n, [](void* d, void* up) { U* x = (U*)up; return cqb_ntt_bn254_fr_dev(d, x->w, x->l); }, &u);
+}
+
+int cqb_intt_bn254_fr(uint64_t* a, const uint64_t omega_inv[4], const uint64_t divisor[4], uint32_t log_n) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!a || !omega_inv || !divisor) return fail(CQB_E_BAD_ARG, "cqb_intt_bn254_fr: NULL argument");
+    CQB_TRY(check_log_n(log_n));
+    struct U { const uint64_t *w, *dv; uint32_t l; } u{omega_inv, divisor, log_n};
+    size_t n = (size_t)1 << log_n;
+    return with_host_buffer(a, n, n, [](void* d, void* up) { U* x = (U*)up; return cqb_intt_bn254_fr_dev(d, x->w, x->dv, x->l); }, &u);
+}
+
+static Scratch g_io2;
+int cqb_coset_ntt_bn254_fr(const uint64_t* coeffs, size_t n, uint64_t* out, const uint64_t ext_omega[4], uint32_t ext_log_n,
+                           const uint64_t g_coset[4], const uint64_t g_coset_inv[4]) {
+    LOCK;
+    CQB_TRY(require_init());
+    if ((!coeffs && n) || !out || !ext_omega || !g_coset || !g_coset_inv) return fail(CQB_E_BAD_ARG, "cqb_coset_ntt_bn254_fr: NULL argument");
+    CQB_TRY(check_log_n(ext_log_n));
+    size_t en = (size_t)1 << ext_log_n;
+    if (n > en) return fail(CQB_E_BAD_SIZE, "coset NTT: %zu coefficients do not fit 2^%u", n, ext_log_n);
+    CQB_TRY(g_io2.ensure(n * 32 + 32));
+    CQB_TRY(g_io.ensure(en * 32));
+    if (n) CQB_CUDA(cudaMemcpyAsync(g_io2.p, coeffs, n * 32, cudaMemcpyHostToDevice, g_ctx.stream));
+    CQB_TRY(cqb_coset_ntt_bn254_fr_dev(g_io2.p, n, g_io.p, ext_omega, ext_log_n, g_coset, g_coset_inv));
+    CQB_CUDA(cudaMemcpyAsync(out, g_io.p, en * 32, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return 0;
+}
+
+int cqb_coset_intt_bn254_fr(uint64_t* a, uint32_t ext_log_n, const uint64_t ext_omega_inv[4], const uint64_t ext_divisor[4],
+                            const uint64_t g_coset[4], const uint64_t g_coset_inv[4], const uint64_t* t_evaluations, uint32_t t_len) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!a) return fail(CQB_E_BAD_ARG, "cqb_coset_intt_bn254_fr: NULL argument");
+    CQB_TRY(check_log_n(ext_log_n));
+    struct U { uint32_t l; const uint64_t *w, *dv, *g, *gi, *t; uint32_t tl; } u{ext_log_n, ext_omega_inv, ext_divisor, g_coset, g_coset_inv, t_evaluations, t_len};
+    size_t n = (size_t)1 << ext_log_n;
+    return with_host_buffer(a, n, n, [](void* d, void* up) {
+        U* x = (U*)up;
+        return cqb_coset_intt_bn254_fr_dev(d, x->l, x->w, x->dv, x->g, x->gi, x->t, x->tl);
+    }, &u);
+}
+
+// ---- synthetic inputs ------------------------------------------------------------------------------------------------
+int cqb_synth_scalars_dev(uint64_t seed, size_t start, size_t n, void* d_out) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!d_out && n) return fail(CQB_E_BAD_ARG, "cqb_synth_scalars_dev: NULL argument");
+    return synth_scalars_run(seed, start, n, d_out);
+}
+int cqb_synth_bases_dev(uint64_t seed, size_t start, size_t n, void* d_out) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!d_out && n) return fail(CQB_E_BAD_ARG, "cqb_synth_bases_dev: NULL argument");
+    return synth_bases_run(seed, start, n, d_out);
+}
+
+// ---- memory helpers ---------------------------------------------------------------------------------------------
+int cqb_dev_alloc(size_t bytes, void** d_out) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!d_out) return fail(CQB_E_BAD_ARG, "cqb_dev_alloc: NULL argument");
+    if (cudaMalloc(d_out, bytes ? bytes : 32) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CQB_E_OOM, "cudaMalloc(%zu) failed", bytes);
+    }
+    return 0;
+}
+int cqb_dev_free(void* d) {
+    LOCK;
+    CQB_TRY(require_init());
+    CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    CQB_CUDA(cudaFree(d));
+    return 0;
+}
+int cqb_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes) {
+    LOCK;
+    CQB_TRY(require_init());
+    CQB_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, g_ctx.stream));
+    CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return 0;
+}
+int cqb_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes) {
+    LOCK;
+    CQB_TRY(require_init());
+    CQB_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return 0;
+}
+int cqb_host_alloc_pinned(size_t bytes, void** h_out) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!h_out) return fail(CQB_E_BAD_ARG, "cqb_host_alloc_pinned: NULL argument");
+    if (cudaMallocHost(h_out, bytes ? bytes : 32) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CQB_E_OOM, "cudaMallocHost(%zu) failed", bytes);
+    }
+    return 0;
+}
+int cqb_host_free_pinned(void* h) {
+    LOCK;
+    CQB_CUDA(cudaFreeHost(h));
+    return 0;
+}
+
+int cqb_msm_set_window_bits(int c) {
+    LOCK;
+    if (c != 0 && (c < 2 || c > 16)) return fail(CQB_E_BAD_ARG, "window bits must be 0 (auto) or 2..16");
+    msm_set_window_bits(c);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,38 @@
+// internal.h — declarations shared between the library's translation units (not part of the public ABI).
+#pragma once
+#include <string.h>
+
+#include "context.h"
+#include "ec.cuh"
+#include "fp.cuh"
+
+namespace cqb {
+
+// ---- ntt.cu ----
+constexpr int NTT_PRE_MAX_PUB = 16;
+struct NttFused {
+    size_t n_in = 0;  // number of valid input elements (0 => 2^log_n); the rest read as zero
+    int pre_mode = 0; // 0 none | 1: x *= pre[j % 3] for j % 3 != 0 | 2: x *= pre[j & (pre_len - 1)]
+    int pre_len = 0;
+    Fr pre[NTT_PRE_MAX_PUB];
+    int post_mode = 0; // 0 none | 1: x *= post[0] | 2: x *= post[i % 3]
+    Fr post[3];
+};
+int ntt_run(const void* d_src, void* d_dst, uint32_t log_n, const uint64_t omega[4], const NttFused& f);
+int fr_scale_table(void* d_a, size_t n, const void* d_tab, uint32_t len);
+void ntt_release_all();
+Fr fr_from_u64x4(const uint64_t* p);
+
+// ---- msm.cu ----
+// sum_i scalars[i] * bases[idx ? idx[i] : i]; d_out receives 64 B affine x||y followed by a uint32 identity flag
+int msm_run(const void* d_bases, const void* d_scalars, const uint32_t* d_idx, size_t n, void* d_out_xy_flag);
+int g1_sum_affine_run(const void* d_points, size_t n, void* d_out_xy_flag);
+void msm_release_all();
+void msm_set_window_bits(int c);
+
+// ---- gen.cu ----
+int synth_scalars_run(uint64_t seed, size_t start, size_t n, void* d_out);
+int synth_bases_run(uint64_t seed, size_t start, size_t n, void* d_out);
+void gen_release_all();
+
+}  // namespace cqb

@@ -1,0 +1,322 @@
+// ntt.cu — Fr radix-2 NTT for bn256, replacing best_fft::<Fr> (reference halo2_proofs/src/arithmetic.rs:171-274) and
+// the EvaluationDomain wrappers around it (poly/domain.rs:252-266 coeff_to_extended, :293-315 extended_to_coeff,
+// :319-338 divide_by_vanishing_poly, :366-374 ifft).
+//
+// Same mathematical object as the reference: out[k] = sum_j a[j] omega^(jk), natural order in and out, every value
+// canonical in [0, r) — so the output limbs are identical to the reference's regardless of how the butterflies are
+// scheduled. The schedule here is B200-shaped, not the reference's recursion:
+//   * decimation in time over a device-resident twiddle table W[i] = omega^i, i < n/2 (the reference's `twiddles`
+//     vector, arithmetic.rs:194-200, built in parallel instead of by a serial scan, and cached per (omega, log_n));
+//   * ceil(log_n / 8) passes over HBM; each pass runs up to 8 butterfly stages on a 1024-element (32 KB) tile held in
+//     shared memory as two uint4 planes (conflict-free 128-bit LDS/STS), 512 threads = one butterfly each per stage;
+//   * the bit-reversal permutation (arithmetic.rs:186-191) is fused into the first pass's gather — tiles are chosen so
+//     that the gather reads 128 B contiguous runs; later passes read/write (rows x 2^q contiguous elements) tiles;
+//   * the element-wise scalings that surround best_fft in the reference are fused into the first pass's load (coset
+//     powers, zero padding, division by the vanishing polynomial) and the last pass's store (1/n, coset powers out).
+// Roofline: integer-pipe bound ((n/2) log n modmuls at ~136 IMAD.WIDE each); HBM traffic is 64 B/element/pass.
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "internal.h"
+
+namespace cqb {
+
+constexpr int NTT_TILE_LOG = 10;   // elements per CTA tile (log2)
+constexpr int NTT_MAX_R = 8;       // max butterfly stages per pass
+constexpr int NTT_PRE_MAX = NTT_PRE_MAX_PUB;
+
+struct NttPassArgs {
+    const uint4* src;
+    uint4* dst;
+    const uint4* tw;
+    int L, s0, r, q;
+    int first;
+    unsigned long long n_in;
+    int pre_mode;   // 0 none | 1: x *= pre[j % 3] for j % 3 != 0 | 2: x *= pre[j & (pre_len - 1)]
+    int pre_len;
+    int post_mode;  // 0 none | 1: x *= post[0] | 2: x *= post[i % 3]
+    Fr pre[NTT_PRE_MAX];
+    Fr post[3];
+};
+
+__device__ __forceinline__ Fr ld_fr(const uint4* p, size_t i) {
+    uint4 a = p[2 * i], b = p[2 * i + 1];
+    Fr r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ Fr ldg_fr(const uint4* p, size_t i) {
+    uint4 a = __ldg(p + 2 * i), b = __ldg(p + 2 * i + 1);
+    Fr r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st_fr(uint4* p, size_t i, const Fr& v) {
+    p[2 * i] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    p[2 * i + 1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+__global__ void __launch_bounds__(512) ntt_pass_kernel(const __grid_constant__ NttPassArgs a) {
+    extern __shared__ uint4 sm[];
+    const int T = 1 << (a.r + a.q);
+    uint4* slo = sm;
+    uint4* shi = sm + T;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t blk = blockIdx.x;
+    const uint32_t qmask = (1u << a.q) - 1u;
+    // bits of the global index owned by this CTA
+    uint32_t lo = 0, hi = 0;
+    if (!a.first) {
+        lo = blk & ((1u << (a.s0 - a.q)) - 1u);
+        hi = blk >> (a.s0 - a.q);
+    }
+    // ---- load (2 elements per thread) -------------------------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        uint32_t e = tid + k * (T >> 1);
+        uint32_t row = e >> a.q, col = e & qmask;
+        Fr v;
+        if (a.first) {
+            // destination (bit-reversed-order) index i; natural source index j = bitrev_L(i)
+            uint32_t i = row | ((blk | (col << (a.L - a.r - a.q))) << a.r);
+            uint32_t j = __brev(i) >> (32 - a.L);
+            if ((unsigned long long)j < a.n_in) {
+                v = ld_fr(a.src, j);
+                if (a.pre_mode == 1) {
+                    uint32_t m = j % 3u;
+                    if (m) v = fp_mul<FrP>(v, a.pre[m]);
+                } else if (a.pre_mode == 2) {
+                    v = fp_mul<FrP>(v, a.pre[j & (uint32_t)(a.pre_len - 1)]);
+                }
+            } else {
+                v = Fr::zero();
+            }
+        } else {
+            size_t i = (size_t)col | ((size_t)lo << a.q) | ((size_t)row << a.s0) | ((size_t)hi << (a.s0 + a.r));
+            v = ld_fr(a.src, i);
+        }
+        slo[e] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+        shi[e] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+    }
+    __syncthreads();
+    // ---- butterflies: stage s = s0 + t pairs rows r0, r0 + 2^t -----------------------------------------------------
+    const uint32_t rb = tid >> a.q, c = tid & qmask;
+    const uint32_t jlow = a.first ? 0u : (c | (lo << a.q));  // low bits of (i mod 2^s) that do not depend on the row
+    for (int t = 0; t < a.r; t++) {
+        uint32_t r0 = ((rb >> t) << (t + 1)) | (rb & ((1u << t) - 1u));
+        uint32_t r1 = r0 | (1u << t);
+        uint32_t e0 = (r0 << a.q) | c, e1 = (r1 << a.q) | c;
+        int s = a.s0 + t;
+        uint32_t j = jlow | ((r0 & ((1u << t) - 1u)) << a.s0);  // i mod 2^s
+        uint32_t twi = j << (a.L - 1 - s);                        // reference: twiddles[(i) * twiddle_chunk]
+        uint4 xl = slo[e0], xh = shi[e0], yl = slo[e1], yh = shi[e1];
+        Fr x, y;
+        x.l[0] = xl.x; x.l[1] = xl.y; x.l[2] = xl.z; x.l[3] = xl.w; x.l[4] = xh.x; x.l[5] = xh.y; x.l[6] = xh.z; x.l[7] = xh.w;
+        y.l[0] = yl.x; y.l[1] = yl.y; y.l[2] = yl.z; y.l[3] = yl.w; y.l[4] = yh.x; y.l[5] = yh.y; y.l[6] = yh.z; y.l[7] = yh.w;
+        if (twi != 0) y = fp_mul<FrP>(y, ldg_fr(a.tw, twi));  // twiddle one: the reference skips the multiply too (:213-219)
+        Fr u = fp_add<FrP>(x, y), w = fp_sub<FrP>(x, y);
+        slo[e0] = make_uint4(u.l[0], u.l[1], u.l[2], u.l[3]);
+        shi[e0] = make_uint4(u.l[4], u.l[5], u.l[6], u.l[7]);
+        slo[e1] = make_uint4(w.l[0], w.l[1], w.l[2], w.l[3]);
+        shi[e1] = make_uint4(w.l[4], w.l[5], w.l[6], w.l[7]);
+        __syncthreads();
+    }
+    // ---- store -------------------------------------------------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        uint32_t e = tid + k * (T >> 1);
+        uint32_t row = e >> a.q, col = e & qmask;
+        size_t i;
+        if (a.first) i = (size_t)row | ((size_t)(blk | (col << (a.L - a.r - a.q))) << a.r);
+        else i = (size_t)col | ((size_t)lo << a.q) | ((size_t)row << a.s0) | ((size_t)hi << (a.s0 + a.r));
+        uint4 vl = slo[e], vh = shi[e];
+        if (a.post_mode) {
+            Fr v;
+            v.l[0] = vl.x; v.l[1] = vl.y; v.l[2] = vl.z; v.l[3] = vl.w; v.l[4] = vh.x; v.l[5] = vh.y; v.l[6] = vh.z; v.l[7] = vh.w;
+            v = fp_mul<FrP>(v, a.post[a.post_mode == 1 ? 0 : (int)(i % 3)]);
+            vl = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+            vh = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+        }
+        a.dst[2 * i] = vl;
+        a.dst[2 * i + 1] = vh;
+    }
+}
+
+// W[i] = omega^i for i < count. pw[t] = omega^(2^t). Each thread owns TW_RUN consecutive entries.
+constexpr int TW_RUN = 32;
+struct TwArgs {
+    uint4* out;
+    unsigned long long count;
+    Fr pw[28];
+};
+__global__ void __launch_bounds__(256) ntt_twiddle_kernel(const __grid_constant__ TwArgs a) {
+    unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long i0 = t * TW_RUN;
+    if (i0 >= a.count) return;
+    Fr x = Fr::one();
+    for (int b = 0; b < 28; b++)
+        if ((i0 >> b) & 1ull) x = fp_mul<FrP>(x, a.pw[b]);
+    for (int k = 0; k < TW_RUN && i0 + k < a.count; k++) {
+        st_fr(a.out, i0 + k, x);
+        x = fp_mul<FrP>(x, a.pw[0]);
+    }
+}
+
+// element-wise x[i] *= tab[i & (len-1)] (only used when a vanishing-division table is too long for the fused path)
+__global__ void fr_scale_table_kernel(uint4* a, size_t n, const uint4* tab, uint32_t len) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr v = fp_mul<FrP>(ld_fr(a, i), ldg_fr(tab, i & (len - 1)));
+    st_fr(a, i, v);
+}
+// n == 1 corner: a[0] = a[0] * f
+__global__ void fr_scale_one_kernel(const uint4* src, uint4* dst, Fr f) {
+    Fr v = fp_mul<FrP>(ld_fr(src, 0), f);
+    st_fr(dst, 0, v);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+struct TwKey {
+    uint64_t w[4];
+    uint32_t L;
+    bool operator<(const TwKey& o) const {
+        if (L != o.L) return L < o.L;
+        for (int i = 0; i < 4; i++)
+            if (w[i] != o.w[i]) return w[i] < o.w[i];
+        return false;
+    }
+};
+struct TwEntry { void* d; size_t bytes; unsigned long long last_use; };
+static std::map<TwKey, TwEntry> g_tw;
+static unsigned long long g_tw_clock = 0;
+static size_t g_tw_bytes = 0;
+static const size_t TW_CACHE_LIMIT = (size_t)24 << 30;  // 24 GiB of the 180 GB HBM for twiddle tables
+static Scratch g_ntt_scratch;
+
+Fr fr_from_u64x4(const uint64_t* p) {
+    Fr r;
+    for (int i = 0; i < 4; i++) { r.l[2 * i] = (uint32_t)p[i]; r.l[2 * i + 1] = (uint32_t)(p[i] >> 32); }
+    return r;
+}
+
+void ntt_release_all() {
+    for (auto& kv : g_tw) cudaFree(kv.second.d);
+    g_tw.clear();
+    g_tw_bytes = 0;
+    g_ntt_scratch.release();
+}
+
+static int get_twiddles(const uint64_t omega[4], uint32_t L, const uint4** out) {
+    TwKey key;
+    memcpy(key.w, omega, 32);
+    key.L = L;
+    auto it = g_tw.find(key);
+    if (it != g_tw.end()) {
+        it->second.last_use = ++g_tw_clock;
+        *out = (const uint4*)it->second.d;
+        return 0;
+    }
+    size_t count = L >= 1 ? ((size_t)1 << (L - 1)) : 1;
+    size_t bytes = count * 32;
+    while (g_tw_bytes + bytes > TW_CACHE_LIMIT && !g_tw.empty()) {  // evict least recently used
+        auto victim = g_tw.begin();
+        for (auto i2 = g_tw.begin(); i2 != g_tw.end(); ++i2)
+            if (i2->second.last_use < victim->second.last_use) victim = i2;
+        CQB_CUDA(cudaStreamSynchronize(ctx().stream));
+        cudaFree(victim->second.d);
+        g_tw_bytes -= victim->second.bytes;
+        g_tw.erase(victim);
+    }
+    void* d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) return fail(CQB_E_OOM, "twiddle table: cudaMalloc(%zu) failed", bytes);
+    TwArgs ta;
+    ta.out = (uint4*)d;
+    ta.count = count;
+    Fr w = fr_from_u64x4(omega);
+    for (int b = 0; b < 28; b++) { ta.pw[b] = w; w = fp_sqr<FrP>(w); }  // host path of fp.cuh
+    size_t threads = (count + TW_RUN - 1) / TW_RUN;
+    unsigned grid = (unsigned)((threads + 255) / 256);
+    ntt_twiddle_kernel<<<grid, 256, 0, ctx().stream>>>(ta);
+    CQB_LAUNCHED();
+    CQB_CUDA(cudaGetLastError());
+    g_tw[key] = TwEntry{d, bytes, ++g_tw_clock};
+    g_tw_bytes += bytes;
+    *out = (const uint4*)d;
+    return 0;
+}
+
+// d_src may alias d_dst (in place). All pointers are device pointers to 32-byte Fr elements.
+int ntt_run(const void* d_src, void* d_dst, uint32_t L, const uint64_t omega[4], const NttFused& f) {
+    if (L > 28) return fail(CQB_E_BAD_SIZE, "log_n = %u exceeds Fr::S = 28 (bn256/fr.rs:72)", L);
+    cudaStream_t st = ctx().stream;
+    size_t n = (size_t)1 << L;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CQB_CUDA(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_set = true;
+    }
+    if (L == 0) {
+        Fr m = Fr::one();
+        if (f.pre_mode == 2) m = fp_mul<FrP>(m, f.pre[0]);
+        if (f.post_mode) m = fp_mul<FrP>(m, f.post[0]);
+        fr_scale_one_kernel<<<1, 1, 0, st>>>((const uint4*)d_src, (uint4*)d_dst, m);
+        CQB_LAUNCHED();
+        CQB_CUDA(cudaGetLastError());
+        return 0;
+    }
+    const uint4* tw = nullptr;
+    CQB_TRY(get_twiddles(omega, L, &tw));
+    int P = (int)((L + NTT_MAX_R - 1) / NTT_MAX_R);
+    int rs[8];
+    for (int p = 0; p < P; p++) rs[p] = (int)L / P + (p < (int)L % P ? 1 : 0);
+    bool inplace = (d_src == d_dst);
+    uint4* work = (uint4*)d_dst;
+    if (inplace) {
+        CQB_TRY(g_ntt_scratch.ensure(n * 32));
+        work = g_ntt_scratch.as<uint4>();
+    }
+    int s0 = 0;
+    for (int p = 0; p < P; p++) {
+        NttPassArgs a;
+        a.L = (int)L;
+        a.s0 = s0;
+        a.r = rs[p];
+        a.first = (p == 0);
+        int qmax = (p == 0) ? ((int)L - a.r) : s0;
+        a.q = NTT_TILE_LOG - a.r;
+        if (a.q > qmax) a.q = qmax;
+        a.src = (p == 0) ? (const uint4*)d_src : work;
+        a.dst = (p == P - 1 && inplace && P > 1) ? (uint4*)d_dst : work;
+        a.tw = tw;
+        a.n_in = f.n_in ? f.n_in : n;
+        a.pre_mode = (p == 0) ? f.pre_mode : 0;
+        a.pre_len = f.pre_len;
+        for (int i = 0; i < NTT_PRE_MAX; i++) a.pre[i] = f.pre[i];
+        a.post_mode = (p == P - 1) ? f.post_mode : 0;
+        for (int i = 0; i < 3; i++) a.post[i] = f.post[i];
+        int T = 1 << (a.r + a.q);
+        unsigned grid = (unsigned)(n >> (a.r + a.q));
+        int threads = T >> 1;
+        if (threads < 1) threads = 1;
+        ntt_pass_kernel<<<grid, threads, (size_t)T * 32, st>>>(a);
+        CQB_LAUNCHED();
+        CQB_CUDA(cudaGetLastError());
+        s0 += a.r;
+    }
+    if (inplace && P == 1) CQB_CUDA(cudaMemcpyAsync(d_dst, work, n * 32, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int fr_scale_table(void* d_a, size_t n, const void* d_tab, uint32_t len) {
+    fr_scale_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx().stream>>>((uint4*)d_a, n, (const uint4*)d_tab, len);
+    CQB_LAUNCHED();
+    CQB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace cqb

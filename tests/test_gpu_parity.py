@@ -1,0 +1,232 @@
+"""GPU parity tests proper: every call goes through the C ABI (libcqb200.so) and is compared bit-for-bit with the CPU
+oracle (oracle/bn254_oracle.c, the restatement of the reference's best_multiexp / best_fft / domain / KZG / CQ code) on
+the same seeded inputs. Integer work => the bar is exact equality of limbs (NTT) and of the affine normal form (MSM)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import pyref as P  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def cq():
+    import cqb200
+
+    cqb200._lib.init(0)
+    return cqb200
+
+
+def L(x):
+    return P.int_to_limbs(x)
+
+
+def omega_limbs(k, inverse=False):
+    w = P.omega_for(k)
+    if inverse:
+        w = pow(w, -1, P.R_MOD)
+    return L(P.to_mont(w, P.R_MOD))
+
+
+# ---------------------------------------------------------------------------------------------------------------- NTT
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 4, 5, 7, 8, 9, 10, 11, 12, 13, 16, 17, 18])
+def test_best_fft_parity(cq, oracle, log_n):
+    n = 1 << log_n
+    a = oracle.synth_scalars(0x5EED0002 + log_n, n)
+    if n >= 8:  # structured values too: zeros, one, r-1
+        a[0] = 0
+        a[1] = L(P.MONT % P.R_MOD)
+        a[2] = L(P.to_mont(P.R_MOD - 1, P.R_MOD))
+    w = omega_limbs(log_n)
+    exp = oracle.best_fft(a, w, log_n, threads=4)
+    got = a.copy()
+    cq.best_fft(got, w, log_n)
+    assert np.array_equal(got, exp)
+
+
+def test_best_fft_wrong_size_panics(cq):
+    a = np.zeros((6, 4), np.uint64)
+    with pytest.raises(AssertionError):
+        cq.best_fft(a, omega_limbs(3), 3)  # arithmetic.rs:184
+
+
+@pytest.mark.parametrize("j,k", [(3, 3), (3, 4), (4, 5), (5, 6), (3, 10), (4, 12), (6, 9)])
+def test_domain_wrappers_parity(cq, oracle, j, k):
+    """lagrange_to_coeff, coeff_to_extended, divide_by_vanishing_poly + extended_to_coeff (poly/domain.rs)"""
+    od = oracle.domain_new(j, k)
+    d = cq.EvaluationDomain(j, k)
+    assert d.extended_k == od.extended_k and d.quotient_poly_degree == od.quotient_poly_degree
+    for name in ("omega", "omega_inv", "extended_omega", "extended_omega_inv", "g_coset", "g_coset_inv", "ifft_divisor",
+                 "extended_ifft_divisor"):
+        assert np.array_equal(getattr(d, name), od.f(name)), name
+    assert np.array_equal(d.t_evaluations, od.t_evals())
+    n = 1 << k
+    a = oracle.synth_scalars(77 + k, n)
+    coeff = d.lagrange_to_coeff(a)
+    assert np.array_equal(coeff, oracle.lagrange_to_coeff(od, a))
+    ext = d.coeff_to_extended(coeff)
+    exp_ext = oracle.coeff_to_extended(od, coeff)
+    assert np.array_equal(ext.values, exp_ext)
+    # round trip without division
+    back = d.extended_to_coeff(ext)
+    assert np.array_equal(back, oracle.extended_to_coeff(od, exp_ext))
+    assert np.array_equal(back[:n], coeff) and not back[n:].any()
+    # quotient path: divide_by_vanishing_poly -> extended_to_coeff (vanishing/prover.rs:84-87)
+    h = oracle.synth_scalars(99 + k, 1 << d.extended_k)
+    got = d.extended_to_coeff(d.divide_by_vanishing_poly(cq.domain.ExtendedLagrange(h)))
+    exp = oracle.extended_to_coeff(od, oracle.divide_by_vanishing_poly(od, h))
+    assert np.array_equal(got, exp)
+
+
+# ---------------------------------------------------------------------------------------------------------------- MSM
+def _edge_inputs(oracle, n, seed):
+    sc = oracle.synth_scalars(seed, n)
+    bases = oracle.synth_bases(seed + 1, n, 4)
+    if n >= 12:
+        sc[0] = 0                                              # zero scalar
+        sc[1] = L(P.to_mont(P.R_MOD - 1, P.R_MOD))             # r - 1
+        sc[2] = L(P.to_mont(1, P.R_MOD))
+        bases[3] = 0                                           # identity base (0,0)
+        bases[5] = bases[4]                                    # repeated point, ...
+        sc[5] = sc[4]                                          # ... same scalar => P + P inside a bucket
+        bases[7] = oracle.g1_neg_a(bases[6])                   # P + (-P) inside a bucket
+        sc[7] = sc[6]
+        sc[8] = L(P.to_mont((1 << 253) + 12345, P.R_MOD))      # top window populated
+        sc[9] = L(P.to_mont(0xFFFF, P.R_MOD))                  # carries in the signed-digit recoding
+        sc[10] = L(P.to_mont(0x8000, P.R_MOD))
+        sc[11] = L(P.to_mont((1 << 254) % P.R_MOD, P.R_MOD))
+    return sc, bases
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 12, 31, 32, 33, 100, 257, 1000, 4096, 5000, 1 << 14, (1 << 16) + 3])
+def test_best_multiexp_parity(cq, oracle, n):
+    sc, bases = _edge_inputs(oracle, n, 1000 + n)
+    _, exp = oracle.best_multiexp(sc, bases, 8)
+    got = cq.best_multiexp(sc, bases)
+    assert np.array_equal(got.to_affine(), exp)
+    assert got.is_identity == (not exp.any())
+
+
+def test_best_multiexp_empty_and_mismatch(cq):
+    got = cq.best_multiexp(np.zeros((0, 4), np.uint64), np.zeros((0, 8), np.uint64))
+    assert got.is_identity and not got.to_affine().any()
+    with pytest.raises(AssertionError):
+        cq.best_multiexp(np.zeros((3, 4), np.uint64), np.zeros((2, 8), np.uint64))  # arithmetic.rs:133
+
+
+@pytest.mark.parametrize("kind", ["all_zero", "all_equal", "small", "witness_like", "cancel"])
+def test_best_multiexp_structured_scalars(cq, oracle, kind):
+    n = 3000
+    bases = oracle.synth_bases(4242, n, 4)
+    sc = oracle.synth_scalars(4243, n)
+    rng = np.random.default_rng(5)
+    if kind == "all_zero":
+        sc[:] = 0
+    elif kind == "all_equal":
+        sc[:] = sc[0]
+    elif kind == "small":
+        sc = P.fr_array_from_ints([int(v) for v in rng.integers(0, 1 << 16, n)])
+    elif kind == "witness_like":
+        vals = [0 if rng.random() < 0.9 else int(rng.integers(0, 4)) for _ in range(n)]
+        sc = P.fr_array_from_ints(vals)
+    elif kind == "cancel":  # sum is the identity: s*P + (r-s)*P
+        bases[1::2] = bases[0::2]
+        ints = P.fr_array_to_ints(sc[0::2])
+        sc[1::2] = P.fr_array_from_ints([(P.R_MOD - v) % P.R_MOD for v in ints])
+    _, exp = oracle.best_multiexp(sc, bases, 8)
+    got = cq.best_multiexp(sc, bases)
+    assert np.array_equal(got.to_affine(), exp)
+    if kind in ("all_zero", "cancel"):
+        assert got.is_identity
+
+
+@pytest.mark.parametrize("c", [4, 7, 11, 13, 16])
+def test_msm_window_bits_do_not_change_result(cq, oracle, c):
+    n = 2000
+    sc, bases = _edge_inputs(oracle, n, 31337)
+    _, exp = oracle.best_multiexp(sc, bases, 8)
+    lib = cq._lib.lib()
+    cq._lib.check(lib.cqb_msm_set_window_bits(c))
+    try:
+        got = cq.best_multiexp(sc, bases)
+    finally:
+        cq._lib.check(lib.cqb_msm_set_window_bits(0))
+    assert np.array_equal(got.to_affine(), exp)
+
+
+def test_kzg_commit_identity_and_parity(cq, oracle):
+    """kzg/commitment.rs:570-593 test_commit_lagrange through ParamsKZG on the device, plus parity with the oracle"""
+    K = 6
+    s = oracle.synth_scalars(0xC0, 1)[0]
+    g, gl = oracle.params_setup(K, s)
+    params = cq.ParamsKZG(K, g, gl)
+    d = cq.EvaluationDomain(1, K)
+    a = P.fr_array_from_ints(list(range(1 << K)))
+    b = d.lagrange_to_coeff(a)
+    c1 = params.commit(b)
+    c2 = params.commit_lagrange(a)
+    assert c1 == c2
+    _, exp = oracle.best_multiexp(a, gl, 4)
+    assert np.array_equal(c2.to_affine(), exp)
+    short = a[:40]  # size < n is allowed (commitment.rs:502)
+    _, exp_s = oracle.best_multiexp(short, gl[:40], 2)
+    assert np.array_equal(params.commit_lagrange(short).to_affine(), exp_s)
+    with pytest.raises(AssertionError):
+        params.commit(np.zeros(((1 << K) + 1, 4), np.uint64))
+    params.free()
+
+
+def test_cq_sparse_commits_parity(cq, oracle):
+    """static_lookup/prover.rs:167-170, 245-257: serial scalar-mul loops == one sparse MSM each"""
+    N = 64
+    s = oracle.synth_scalars(0xC1, 1)[0]
+    g1, gl, op0 = oracle.table_srs_setup(N, s)
+    srs = cq.TableSRS(g1, gl, op0)
+    rng = np.random.default_rng(9)
+    idx = np.sort(rng.choice(N, 23, replace=False)).astype(np.uint32)
+    mult = P.fr_array_from_ints([int(v) for v in rng.integers(1, 50, idx.shape[0])])
+    m_sparse = {int(i): mult[t] for t, i in enumerate(idx)}
+    m_cm = cq.cq.commit_m(srs, m_sparse)
+    assert np.array_equal(m_cm.to_affine(), oracle.sparse_commit(gl, idx, mult))
+    a_vals = oracle.synth_scalars(123, idx.shape[0])
+    qs = oracle.synth_bases(555, N, 2)  # stand-in for the cached quotient commitments
+    qs_dev = cq.DeviceBases(qs)
+    a_cm, qa_cm, a0_cm = cq.cq.commit_log_derivative_sparse(srs, qs_dev, idx, a_vals)
+    assert np.array_equal(a_cm.to_affine(), oracle.sparse_commit(gl, idx, a_vals))
+    assert np.array_equal(qa_cm.to_affine(), oracle.sparse_commit(qs, idx, a_vals))
+    assert np.array_equal(a0_cm.to_affine(), oracle.sparse_commit(op0, idx, a_vals))
+    # empty support
+    assert cq.cq.commit_m(srs, {}).is_identity
+    qs_dev.free()
+    srs.free()
+
+
+def test_synth_generators_match_oracle(cq, oracle):
+    lib = cq._lib.lib()
+    n = 5000
+    d = ctypes.c_void_p()
+    cq._lib.check(lib.cqb_dev_alloc(n * 64, ctypes.byref(d)))
+    out_s = np.zeros((n, 4), np.uint64)
+    cq._lib.check(lib.cqb_synth_scalars_dev(0x5EED0001, 7, n, d))
+    cq._lib.check(lib.cqb_memcpy_d2h(out_s.ctypes.data_as(ctypes.c_void_p), d, n * 32))
+    assert np.array_equal(out_s, oracle.synth_scalars(0x5EED0001, n, start=7))
+    out_b = np.zeros((n, 8), np.uint64)
+    cq._lib.check(lib.cqb_synth_bases_dev(0xC0FFEE, 0, n, d))
+    cq._lib.check(lib.cqb_memcpy_d2h(out_b.ctypes.data_as(ctypes.c_void_p), d, n * 64))
+    assert np.array_equal(out_b, oracle.synth_bases(0xC0FFEE, n, 4))
+    cq._lib.check(lib.cqb_dev_free(d))
+
+
+def test_g1_sum_affine(cq, oracle):
+    pts = oracle.synth_bases(77, 9, 1)
+    pts[4] = 0
+    acc = np.zeros(12, np.uint64)
+    for i in range(9):
+        acc = oracle.g1_add_ja(acc, pts[i])
+    exp = oracle.g1_to_affine(acc)
+    out = np.zeros(8, np.uint64)
+    inf = ctypes.c_int(0)
+    cq._lib.check(cq._lib.lib().cqb_g1_sum_affine(cq._lib.p64(pts), 9, cq._lib.p64(out), ctypes.byref(inf)))
+    assert np.array_equal(out, exp) and inf.value == 0
