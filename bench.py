@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path: BN254 G1 MSM at 2^24 points (BASELINE.json configs[1]), with the Fr NTT
+at 2^24 (configs[2]) reported beside it at N=1.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (the reference's CPU algorithm on the host cores)
+
+One "step" = one full MSM of 2^log_n synthetic points (seeded uniform scalars x distinct curve points). With N GPUs the
+SAME MSM is sharded by contiguous point range (the decomposition the reference uses across rayon threads,
+arithmetic.rs:137-153): each rank owns n/N resident SRS points + scalars, computes its partial sum, the N affine partials
+(64 B each) are all-gathered over NCCL and folded on the device. Total work is fixed => "scaling": "strong".
+
+value  : Mpts/s with scalars and bases already resident in HBM (device-pointer C-ABI call)
+e2e    : Mpts/s through the host-pointer C-ABI call a halo2 caller would make (scalars in pinned host memory, H2D inside
+         the timed region, 64 B result read back); bases resident (the SRS is uploaded once per proving key)
+roofline: msm_accumulate_kernel, integer pipe: 21,760 MAD32 per point over its CUDA-event duration,
+         against the IMAD.WIDE peak calibrated on this pool's B200 (profiles/r01_int_pipe_calibration.md)
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SHA2-CQ prove ms; BN254 MSM Mpts/s @2^24; Fr NTT Gelem/s @2^24; 1/2/4/8 GPU"
+UNIT = "Mpts/s (BN254 G1 MSM @2^24)"
+MAD32_PER_POINT = 21760           # 16 windows x 10 modmul x 136 MAD32
+INT_PEAK_TMAD32 = 8.51            # measured: profiles/r01_int_pipe_calibration.md (carry-chained IMAD.WIDE.U32.X)
+SEED_BASES, SEED_SCALARS, SEED_NTT = 0xC0FFEE, 0x5EED0001, 0x5EED0002
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi SM clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split("\n")[0]
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nm, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------------------------------- reference
+def run_reference(args):
+    """The reference's own CPU algorithm for the path (best_multiexp, arithmetic.rs:13-159) on the host cores. The Rust
+    reference cannot be built in this image (no cargo/rustc), so this is the C restatement oracle/bn254_oracle.c
+    ("kind": "port"), all hardware threads, on a bounded sample of the same synthetic workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle_lib as O
+
+    O.build()
+    threads = O.hw_threads()
+    # size the sample so that one step is a few seconds
+    probe_n = 1 << 14
+    sc = O.synth_scalars(SEED_SCALARS, probe_n)
+    bs = O.synth_bases(SEED_BASES, probe_n, threads)
+    t = time.perf_counter()
+    O.best_multiexp(sc, bs, threads)
+    dt = max(time.perf_counter() - t, 1e-4)
+    rate = probe_n / dt
+    log_s = 16
+    while log_s < args.ref_max_log and (1 << (log_s + 1)) / rate < 4.0:
+        log_s += 1
+    n = 1 << log_s
+    sc = O.synth_scalars(SEED_SCALARS, n)
+    bs = O.synth_bases(SEED_BASES, n, threads)
+    for _ in range(args.warmup):
+        O.best_multiexp(sc, bs, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.best_multiexp(sc, bs, threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n / dt / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u64 limbs (256-bit modular integer)", "data": "synthetic",
+        "config": {"workload": f"BN254 G1 MSM, uniform scalars x distinct points, bounded sample 2^{log_s} of the 2^{args.log_n} workload",
+                   "algorithm": "best_multiexp: c=ceil(ln chunk) unsigned windows, len/threads chunks (arithmetic.rs:13-159)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"2^{log_s} points per step, {args.steps} steps; C restatement of the reference (Rust toolchain absent)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------- ours
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-n", type=int, default=24)
+    ap.add_argument("--ntt-log-n", type=int, default=24)
+    ap.add_argument("--no-ntt", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ref-max-log", type=int, default=22)
+    ap.add_argument("--window-bits", type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3 if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import cqb200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L = cqb200._lib
+    lib = L.init(local_rank)
+    stream = torch.cuda.Stream(device=local_rank)  # a real (non-NULL) stream handle shared by torch events and the library
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    L.check(lib.cqb_set_stream(ctypes.c_void_p(stream.cuda_stream)))
+    if args.window_bits:
+        L.check(lib.cqb_msm_set_window_bits(args.window_bits))
+
+    n_total = 1 << args.log_n
+    per = n_total // world
+    start = rank * per
+    dev = torch.device("cuda", local_rank)
+    bases_t = torch.empty(per * 64, dtype=torch.uint8, device=dev)
+    scal_t = torch.empty(per * 32, dtype=torch.uint8, device=dev)
+    L.check(lib.cqb_synth_bases_dev(SEED_BASES, start, per, ctypes.c_void_p(bases_t.data_ptr())))
+    L.check(lib.cqb_synth_scalars_dev(SEED_SCALARS, start, per, ctypes.c_void_p(scal_t.data_ptr())))
+    h = ctypes.c_uint64(0)
+    L.check(lib.cqb_bases_register_device(ctypes.c_void_p(bases_t.data_ptr()), per, ctypes.byref(h)))
+    scal_host = torch.empty(per * 32, dtype=torch.uint8).pin_memory()
+    scal_host.copy_(scal_t)
+    torch.cuda.synchronize()
+    host_ptr = ctypes.cast(ctypes.c_void_p(scal_host.data_ptr()), L.u64p)
+
+    out = np.zeros(8, np.uint64)
+    inf = ctypes.c_int(0)
+    gather_in = torch.zeros(8, dtype=torch.int64, device=dev)
+    gather_out = torch.zeros(8 * world, dtype=torch.int64, device=dev)
+    folded = np.zeros(8, np.uint64)
+
+    def fold_partials():
+        """all-gather the per-rank affine partials (64 B each) and fold them: arithmetic.rs:153 across GPUs"""
+        if world == 1:
+            return out
+        gather_in.copy_(torch.from_numpy(out.view(np.int64)))
+        dist.all_gather_into_tensor(gather_out, gather_in)
+        parts = gather_out.cpu().numpy().view(np.uint64).reshape(world, 8)
+        L.check(lib.cqb_g1_sum_affine(L.p64(np.ascontiguousarray(parts)), world, L.p64(folded), ctypes.byref(inf)))
+        return folded
+
+    def step_dev():
+        L.check(lib.cqb_msm_bn254_g1_dev(h.value, 0, ctypes.c_void_p(scal_t.data_ptr()), per, L.p64(out), ctypes.byref(inf)))
+        return fold_partials()
+
+    def step_e2e():
+        L.check(lib.cqb_msm_bn254_g1(h.value, 0, host_ptr, per, L.p64(out), ctypes.byref(inf)))
+        return fold_partials()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    L.check(lib.cqb_msm_set_profiling(1))
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = lib.cqb_launch_count()
+    ms_dev = timed(step_dev, args.steps, args.warmup)
+    launches = (lib.cqb_launch_count() - launches0) // (args.steps + args.warmup)
+    result_dev = step_dev().copy()
+    phases = (ctypes.c_float * 8)()
+    # average the accumulate-kernel time over a few more profiled steps
+    acc_ms, ph_avg = [], np.zeros(8)
+    for _ in range(min(5, args.steps)):
+        step_dev()
+        nph = lib.cqb_msm_phase_ms(phases, 8)
+        acc_ms.append(phases[3])
+        ph_avg += np.array([phases[i] for i in range(8)])
+    ph_avg /= max(1, len(acc_ms))
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    result_e2e = step_e2e().copy()
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join()
+    assert np.array_equal(result_dev, result_e2e), "device-resident and host-pointer paths disagree"
+
+    value = n_total / (ms_dev * 1e-3) / 1e6
+    e2e = n_total / (ms_e2e * 1e-3) / 1e6
+    t_acc = float(np.mean(acc_ms)) if acc_ms else float("nan")
+    achieved = per * MAD32_PER_POINT / (t_acc * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32 limbs (256-bit Montgomery modular integers, IMAD.WIDE on the integer pipe)", "data": "synthetic",
+        "config": {"workload": f"BN254 G1 MSM 2^{args.log_n} uniform scalars x distinct points (BASELINE.json configs[1])",
+                   "sharding": f"point range, {per} points per GPU, partials all-gathered over NCCL and folded" if world > 1 else "single GPU",
+                   "l2": f"inputs per GPU ({per * 96 / 2**20:.0f} MiB) exceed the 126 MB L2; no explicit flush",
+                   "window_bits": args.window_bits or "auto"},
+        "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": per * 32 * world,
+                "d2h_bytes_per_step": 80 * world, "note": "scalars in pinned host memory per step; SRS bases resident in HBM"},
+        "gpu_launches": int(launches) * args.steps,
+        "roofline": {"bound": "int", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": INT_PEAK_TMAD32,
+                     "unit": "TMAD32/s", "frac": achieved / INT_PEAK_TMAD32, "traffic": None,
+                     "kernel_ms": t_acc, "algorithmic_mad32_per_point": MAD32_PER_POINT,
+                     "peak_source": "measured on this pool's B200: profiles/r01_int_pipe_calibration.md (MEASURED_PEAKS.json has no integer figure)",
+                     "whole_msm_frac": n_total / world * MAD32_PER_POINT / (ms_dev * 1e-3) / 1e12 / INT_PEAK_TMAD32},
+        "msm_phase_ms": {k: float(v) for k, v in zip(["count", "scan", "scatter", "accumulate", "merge", "reduce", "window_sum", "final"], ph_avg)},
+    }
+    if sampler:
+        line["clocks"] = sampler.summary()
+
+    # ---- NTT 2^ntt_log_n beside it (N=1 only; the NTT stays per-GPU: "replicas only") ------------------
+    if world == 1 and not args.no_ntt:
+        k = args.ntt_log_n
+        n = 1 << k
+        from sha2_on_cq_halo2_b200.fields import FR_ROOT_OF_UNITY, FR_S, R_MOD, fr_to_limbs
+
+        w = FR_ROOT_OF_UNITY
+        for _ in range(k, FR_S):
+            w = w * w % R_MOD
+        omega = fr_to_limbs(w)
+        a_t = torch.empty(n * 32, dtype=torch.uint8, device=dev)
+        L.check(lib.cqb_synth_scalars_dev(SEED_NTT, 0, n, ctypes.c_void_p(a_t.data_ptr())))
+        a_host = torch.empty(n * 32, dtype=torch.uint8).pin_memory()
+        a_host.copy_(a_t)
+        a_host_ptr = ctypes.cast(ctypes.c_void_p(a_host.data_ptr()), L.u64p)
+
+        def ntt_dev():
+            L.check(lib.cqb_ntt_bn254_fr_dev(ctypes.c_void_p(a_t.data_ptr()), L.p64(omega), k))
+
+        def ntt_e2e():
+            L.check(lib.cqb_ntt_bn254_fr(a_host_ptr, L.p64(omega), k))
+
+        ms_ntt = timed(ntt_dev, args.steps, args.warmup)
+        ms_ntt_e2e = timed(ntt_e2e, max(2, args.steps // 2), 3)
+        hbm = measured_peaks().get("hbm_gbs", 6650.0)
+        gbs = 64.0 * n / (ms_ntt * 1e-3) / 1e9
+        int_t = (n / 2) * k * 136 / (ms_ntt * 1e-3) / 1e12
+        line["ntt"] = {"metric": f"Fr NTT Gelem/s @2^{k}", "value": n / (ms_ntt * 1e-3) / 1e9, "ms": ms_ntt,
+                       "e2e_value": n / (ms_ntt_e2e * 1e-3) / 1e9, "e2e_ms": ms_ntt_e2e,
+                       "roofline_hbm": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                                        "algorithmic_bytes_per_elem": 64},
+                       "roofline_int": {"bound": "int", "achieved": int_t, "peak": INT_PEAK_TMAD32, "unit": "TMAD32/s",
+                                        "frac": int_t / INT_PEAK_TMAD32}}
+        del a_t
+
+    # ---- CPU baseline (rank 0, N=1): the oracle's restatement of best_multiexp on a bounded sample -----------------
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle_lib as O
+
+        O.build()
+        threads = O.hw_threads()
+        log_s = min(args.log_n, 20)
+        ns = 1 << log_s
+        sc = np.zeros((ns, 4), np.uint64)
+        bs = np.zeros((ns, 8), np.uint64)
+        L.check(lib.cqb_memcpy_d2h(sc.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(scal_t.data_ptr()), ns * 32))
+        L.check(lib.cqb_memcpy_d2h(bs.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(bases_t.data_ptr()), ns * 64))
+        t0 = time.perf_counter()
+        _, cpu_aff = O.best_multiexp(sc, bs, threads)
+        dt = time.perf_counter() - t0
+        # the same sample on the GPU must give the same point (parity at bench size, not timed)
+        L.check(lib.cqb_msm_bn254_g1_dev(h.value, 0, ctypes.c_void_p(scal_t.data_ptr()), ns, L.p64(out), ctypes.byref(inf)))
+        line["cpu_baseline"] = {"value": ns / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"first 2^{log_s} points of the workload, 1 run ({dt:.1f} s); C restatement of the reference's "
+                                          "best_multiexp (Rust toolchain absent)",
+                                "gpu_matches_cpu_on_sample": bool(np.array_equal(out, cpu_aff))}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -115,6 +115,12 @@ CQB_API int cqb_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes);
 CQB_API int cqb_host_alloc_pinned(size_t bytes, void** h_out);
 CQB_API int cqb_host_free_pinned(void* h);
 
+/* measurement hooks: when profiling is on, every MSM records CUDA events between its kernels on the launch stream;
+ * cqb_msm_phase_ms returns how many of ms[0..7] = {count, scan, scatter, accumulate, merge, reduce, window_sum, final} it filled
+ * for the most recent MSM (device time, milliseconds) */
+CQB_API int cqb_msm_set_profiling(int on);
+CQB_API int cqb_msm_phase_ms(float* ms, int cap);
+
 /* tuning knobs for experiments (0 = automatic): MSM window bits */
 CQB_API int cqb_msm_set_window_bits(int c);
 

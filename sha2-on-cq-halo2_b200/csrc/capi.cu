@@ -487,6 +487,17 @@ int cqb_host_free_pinned(void* h) {
     return 0;
 }
 
+int cqb_msm_set_profiling(int on) {
+    LOCK;
+    msm_set_profiling(on != 0);
+    return 0;
+}
+int cqb_msm_phase_ms(float* ms, int cap) {
+    LOCK;
+    if (!ms) return 0;
+    return msm_phase_ms(ms, cap);
+}
+
 int cqb_msm_set_window_bits(int c) {
     LOCK;
     if (c != 0 && (c < 2 || c > 16)) return fail(CQB_E_BAD_ARG, "window bits must be 0 (auto) or 2..16");

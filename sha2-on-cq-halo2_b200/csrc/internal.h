@@ -29,6 +29,8 @@ int msm_run(const void* d_bases, const void* d_scalars, const uint32_t* d_idx, s
 int g1_sum_affine_run(const void* d_points, size_t n, void* d_out_xy_flag);
 void msm_release_all();
 void msm_set_window_bits(int c);
+void msm_set_profiling(bool on);
+int msm_phase_ms(float* ms, int cap);
 
 // ---- gen.cu ----
 int synth_scalars_run(uint64_t seed, size_t start, size_t n, void* d_out);

@@ -9,9 +9,11 @@
 //                    window, half the reference's bucket count), per-(window,bucket) histogram with L2 atomics;
 //   2. msm_scan    : one CTA per window, exclusive scan of the histogram -> bucket offsets;
 //   3. msm_scatter : counting-sort scatter of (point index, sign) into window-major bucket order;
-//   4. msm_accumulate : one thread per (window, bucket): XYZZ mixed additions (8M+2S) of its points, gathered from the
+//   4. msm_accumulate : the bucket-sorted lists are cut into equal chunks, one thread per chunk (load balance does not
+//                    depend on the scalar distribution): XYZZ mixed additions (8M+2S) of its points, gathered from the
 //                    device-resident SRS with 128-bit loads; negation folded into the load; all exceptional cases
 //                    (identity base, P+P, P+(-P)) handled as the reference does (derive/curve.rs:866-871);
+//                    msm_merge adds the per-chunk partials of buckets that straddle chunk boundaries;
 //   5. msm_reduce  : per window sum_d d*B_d by chunked running sums (each thread: running-sum over its chunk, then a
 //                    short double-and-add for the chunk offset), 6. window_sum: tree-add the chunk partials,
 //   7. msm_final   : Horner over windows (c doublings each), normalise to affine, write x||y + identity flag.
@@ -162,26 +164,124 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint4* __restric
     }
 }
 
-// (4) bucket accumulation: one thread per (window, bucket)
+// (4) bucket accumulation, load-balanced independently of the scalar distribution: each window's bucket-sorted list is
+// cut into chunks of 2^seg_log entries and ONE THREAD OWNS ONE CHUNK (not one bucket), so every thread performs the
+// same number of XYZZ mixed additions whether the digits are uniform, all equal, or (the top window) only a few bits
+// wide. Within its chunk a thread walks the bucket boundaries (offs[]): buckets that start and end inside the chunk are
+// complete and stored directly; the first and the last bucket of a chunk may continue in the neighbouring chunks and
+// are stored as "head" / "tail" partials which msm_merge_kernel adds up (one XYZZ add per chunk boundary).
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint4* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                              const uint32_t* __restrict__ offs, size_t n, MsmShape s,
-                                                             uint4* __restrict__ buckets) {
+                                                             int seg_log, uint32_t cpw, uint4* __restrict__ buckets,
+                                                             uint4* __restrict__ head, uint4* __restrict__ tail) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (size_t)s.nwin * s.nb) return;
-    uint32_t w = (uint32_t)(gid / s.nb), d = (uint32_t)(gid % s.nb) + 1;
+    if (gid >= (size_t)s.nwin * cpw) return;
+    uint32_t w = (uint32_t)(gid / cpw), k = (uint32_t)(gid % cpw);
     const uint32_t* o = offs + (size_t)w * s.stride;
-    uint32_t start = o[d], end = o[d + 1];
+    const uint32_t total = o[s.nb + 1];
+    const uint32_t start = k << seg_log;
+    if (start >= total) return;
+    const uint32_t end = min(start + (1u << seg_log), total);
+    // bucket d with o[d] <= start < o[d+1]: the largest d in [1, nb] with o[d] <= start
+    uint32_t lo = 1, hi = s.nb;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (o[mid] <= start) lo = mid; else hi = mid - 1;
+    }
+    uint32_t d = lo, bound = o[d + 1];
+    bool is_first = true;
     const uint32_t* lst = sorted + (size_t)w * n;
     G1Xyzz acc = G1Xyzz::identity();
-    for (uint32_t k = start; k < end; k++) {
-        uint32_t e = __ldg(lst + k);
+    for (uint32_t pos = start; pos < end; pos++) {
+        if (pos >= bound) {  // bucket d ends inside this chunk
+            if (is_first) { st_xyzz(head + gid * 8, acc); is_first = false; }
+            else st_xyzz(buckets + ((size_t)w * s.nb + (d - 1)) * 8, acc);  // started and ended inside: complete
+            acc = G1Xyzz::identity();
+            do { d++; bound = o[d + 1]; } while (pos >= bound);
+        }
+        uint32_t e = __ldg(lst + pos);
         const uint4* bp = bases + (size_t)(e >> 1) * 4;
         Fq x = ldg_fq(bp), y = ldg_fq(bp + 2);
         if (x.is_zero() && y.is_zero()) continue;  // identity base contributes nothing (reference curve.rs:857-858)
         if (e & 1u) y = fp_neg<FqP>(y);
         g1_madd(acc, x, y);
     }
+    if (is_first) st_xyzz(head + gid * 8, acc);
+    else st_xyzz(tail + gid * 8, acc);
+}
+
+// (4b) one thread per (window, bucket): add up the head/tail partials of the chunks the bucket overlaps. Buckets that
+// span more than MERGE_LONG chunks (heavily repeated digits) are queued for msm_merge_big_kernel.
+constexpr uint32_t MERGE_LONG = 32;
+__global__ void __launch_bounds__(128) msm_merge_kernel(const uint32_t* __restrict__ offs, MsmShape s, int seg_log, uint32_t cpw,
+                                                        uint4* __restrict__ buckets, const uint4* __restrict__ head,
+                                                        const uint4* __restrict__ tail, uint32_t* __restrict__ big_count,
+                                                        uint2* __restrict__ big_list, uint32_t big_cap) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)s.nwin * s.nb) return;
+    uint32_t w = (uint32_t)(gid / s.nb), d = (uint32_t)(gid % s.nb) + 1;
+    const uint32_t* o = offs + (size_t)w * s.stride;
+    const uint32_t total = o[s.nb + 1];
+    const uint32_t start = o[d], end = o[d + 1];
+    if (start == end) return;  // empty bucket: stays identity (buckets are zero-initialised, ZZ = 0)
+    const uint32_t kf = start >> seg_log, kl = (end - 1) >> seg_log;
+    const uint32_t seg = 1u << seg_log;
+    if (kf == kl) {
+        uint32_t cs = kf << seg_log, ce = min(cs + seg, total);
+        bool isfirst = start <= cs, islast = end >= ce;
+        if (!isfirst && !islast) return;  // complete bucket, already stored by the chunk thread
+        const uint4* src = (isfirst ? head : tail) + ((size_t)w * cpw + kf) * 8;
+        G1Xyzz p = ld_xyzz(src);
+        st_xyzz(buckets + gid * 8, p);
+        return;
+    }
+    if (kl - kf > MERGE_LONG) {
+        uint32_t slot = atomicAdd(big_count, 1u);
+        if (slot < big_cap) big_list[slot] = make_uint2(w, d);
+        return;
+    }
+    G1Xyzz acc = G1Xyzz::identity();
+    for (uint32_t k = kf; k <= kl; k++) {
+        bool isfirst = start <= (k << seg_log);
+        G1Xyzz p = ld_xyzz((isfirst ? head : tail) + ((size_t)w * cpw + k) * 8);
+        g1_add(acc, p);
+    }
     st_xyzz(buckets + gid * 8, acc);
+}
+
+// (4c) one CTA per queued long bucket: threads stride over its chunk partials, then a shared-memory tree of XYZZ adds
+__global__ void __launch_bounds__(128) msm_merge_big_kernel(const uint32_t* __restrict__ offs, MsmShape s, int seg_log, uint32_t cpw,
+                                                            uint4* __restrict__ buckets, const uint4* __restrict__ head,
+                                                            const uint4* __restrict__ tail, const uint32_t* __restrict__ big_count,
+                                                            const uint2* __restrict__ big_list) {
+    __shared__ uint4 sm[128 * 8];
+    if (blockIdx.x >= *big_count) return;
+    const uint2 wd = big_list[blockIdx.x];
+    const uint32_t w = wd.x, d = wd.y;
+    const uint32_t* o = offs + (size_t)w * s.stride;
+    const uint32_t start = o[d], end = o[d + 1];
+    const uint32_t kf = start >> seg_log, kl = (end - 1) >> seg_log;
+    const int tid = threadIdx.x;
+    G1Xyzz acc = G1Xyzz::identity();
+    for (uint32_t k = kf + tid; k <= kl; k += 128) {
+        bool isfirst = start <= (k << seg_log);
+        G1Xyzz p = ld_xyzz((isfirst ? head : tail) + ((size_t)w * cpw + k) * 8);
+        g1_add(acc, p);
+    }
+    st_xyzz(sm + tid * 8, acc);
+    __syncthreads();
+    for (int half = 64; half >= 1; half >>= 1) {
+        if (tid < half) {
+            G1Xyzz a = ld_xyzz(sm + tid * 8), b2 = ld_xyzz(sm + (tid + half) * 8);
+            g1_add(a, b2);
+            st_xyzz(sm + tid * 8, a);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        G1Xyzz r = ld_xyzz(sm);
+        st_xyzz(buckets + ((size_t)w * s.nb + (d - 1)) * 8, r);
+    }
 }
 
 // (5) per-window weighted bucket sum, chunked: thread t of window w owns bucket ids [t*CH + 1, (t+1)*CH]
@@ -283,13 +383,38 @@ __global__ void __launch_bounds__(128) g1_sum_affine_kernel(const uint4* __restr
 // -------------------------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------------------------
-static Scratch g_hist, g_sorted, g_buckets, g_partials;
+static Scratch g_hist, g_sorted, g_buckets, g_partials, g_chunks;
+
+// optional per-phase device timing (cudaEvents on the launch stream; no host sync until the times are read)
+static bool g_prof = false;
+static cudaEvent_t g_ev[9];
+static bool g_ev_made = false;
+static int g_ev_count = 0;
+void msm_set_profiling(bool on) { g_prof = on; }
+static void prof_mark(int i) {
+    if (!g_prof) return;
+    if (!g_ev_made) {
+        for (auto& e : g_ev) cudaEventCreate(&e);
+        g_ev_made = true;
+    }
+    cudaEventRecord(g_ev[i], ctx().stream);
+    g_ev_count = i + 1;
+}
+// ms[0..7] = count, scan, scatter, accumulate, merge, reduce, window_sum, final of the most recent MSM
+int msm_phase_ms(float* ms, int cap) {
+    if (!g_prof || g_ev_count < 9) return 0;
+    cudaEventSynchronize(g_ev[8]);
+    int k = 0;
+    for (; k < 8 && k < cap; k++) cudaEventElapsedTime(&ms[k], g_ev[k], g_ev[k + 1]);
+    return k;
+}
 
 void msm_release_all() {
     g_hist.release();
     g_sorted.release();
     g_buckets.release();
     g_partials.release();
+    g_chunks.release();
 }
 
 static int floor_log2(size_t n) {
@@ -303,7 +428,7 @@ static MsmShape choose_shape(size_t n) {
     if (g_forced_c > 0) c = g_forced_c;
     else {
         int lg = n > 1 ? floor_log2(n - 1) + 1 : 0;  // ceil(log2 n)
-        c = lg - 6;
+        c = lg - 4;
         if (c < 4) c = 4;
         if (c > 16) c = 16;
     }
@@ -341,24 +466,53 @@ int msm_run(const void* d_bases, const void* d_scalars, const uint32_t* d_idx, s
     uint4* partials = g_partials.as<uint4>();
     uint4* wins = partials + (size_t)s.nwin * tpw * 8;
 
+    // chunking of the bucket-sorted lists: aim for >= ~150k chunk threads, 16..256 entries each
+    int seg_log = 8;
+    while (seg_log > 4 && (((size_t)n * s.nwin) >> seg_log) < 150000) seg_log--;
+    uint32_t cpw = (uint32_t)((n + ((size_t)1 << seg_log) - 1) >> seg_log);  // chunks per window (upper bound)
+    size_t nchunks = (size_t)s.nwin * cpw;
+    uint32_t big_cap = (uint32_t)(s.nwin * (cpw / MERGE_LONG + 2));
+    CQB_TRY(g_chunks.ensure(nchunks * 256 + 16 + (size_t)big_cap * 8));
+    uint4* head = g_chunks.as<uint4>();
+    uint4* tail = head + nchunks * 8;
+    uint32_t* big_count = (uint32_t*)(tail + nchunks * 8);
+    uint2* big_list = (uint2*)(big_count + 4);
+
     CQB_CUDA(cudaMemsetAsync(hist, 0, hist_words * 4, st));
+    CQB_CUDA(cudaMemsetAsync(g_buckets.p, 0, nbuckets * 128, st));
+    CQB_CUDA(cudaMemsetAsync(big_count, 0, 16, st));
+    g_ev_count = 0;
+    prof_mark(0);
     unsigned gN = (unsigned)((n + 255) / 256);
     msm_count_kernel<<<gN, 256, 0, st>>>((const uint4*)d_scalars, n, s, hist);
     CQB_LAUNCHED();
+    prof_mark(1);
     msm_scan_kernel<<<s.nwin, 1024, 0, st>>>(hist, offs, cursor, s);
     CQB_LAUNCHED();
+    prof_mark(2);
     msm_scatter_kernel<<<gN, 256, 0, st>>>((const uint4*)d_scalars, d_idx, n, s, cursor, g_sorted.as<uint32_t>());
     CQB_LAUNCHED();
-    msm_accumulate_kernel<<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>((const uint4*)d_bases, g_sorted.as<uint32_t>(), offs, n, s,
-                                                                               g_buckets.as<uint4>());
+    prof_mark(3);
+    msm_accumulate_kernel<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>((const uint4*)d_bases, g_sorted.as<uint32_t>(), offs, n, s,
+                                                                              seg_log, cpw, g_buckets.as<uint4>(), head, tail);
     CQB_LAUNCHED();
+    prof_mark(4);
+    msm_merge_kernel<<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>(offs, s, seg_log, cpw, g_buckets.as<uint4>(), head, tail,
+                                                                          big_count, big_list, big_cap);
+    CQB_LAUNCHED();
+    msm_merge_big_kernel<<<big_cap, 128, 0, st>>>(offs, s, seg_log, cpw, g_buckets.as<uint4>(), head, tail, big_count, big_list);
+    CQB_LAUNCHED();
+    prof_mark(5);
     size_t nred = (size_t)s.nwin * tpw;
     msm_reduce_kernel<<<(unsigned)((nred + 127) / 128), 128, 0, st>>>(g_buckets.as<uint4>(), s, tpw, ch, partials);
     CQB_LAUNCHED();
+    prof_mark(6);
     msm_window_sum_kernel<<<s.nwin, 128, 0, st>>>(partials, tpw, wins);
     CQB_LAUNCHED();
+    prof_mark(7);
     msm_final_kernel<<<1, 32, 0, st>>>(wins, s, (uint4*)d_out);
     CQB_LAUNCHED();
+    prof_mark(8);
     CQB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -230,3 +230,22 @@ def test_g1_sum_affine(cq, oracle):
     inf = ctypes.c_int(0)
     cq._lib.check(cq._lib.lib().cqb_g1_sum_affine(cq._lib.p64(pts), 9, cq._lib.p64(out), ctypes.byref(inf)))
     assert np.array_equal(out, exp) and inf.value == 0
+
+
+@pytest.mark.parametrize("kind", ["all_equal", "two_values", "top_window_only"])
+def test_best_multiexp_long_buckets(cq, oracle, kind):
+    """heavily repeated digits: buckets spanning many chunks exercise msm_merge_kernel's long path and msm_merge_big_kernel"""
+    n = 1 << 15
+    bases = oracle.synth_bases(777, n, 8)
+    sc = oracle.synth_scalars(778, n)
+    if kind == "all_equal":
+        sc[:] = sc[0]
+    elif kind == "two_values":
+        sc[0::2] = sc[0]
+        sc[1::2] = sc[1]
+    else:  # only the two top bits of the scalar differ
+        base = (1 << 200) + 12345
+        sc = P.fr_array_from_ints([((i % 3) << 252) + base for i in range(n)])
+    _, exp = oracle.best_multiexp(sc, bases, 8)
+    got = cq.best_multiexp(sc, bases)
+    assert np.array_equal(got.to_affine(), exp)
