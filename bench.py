@@ -168,44 +168,29 @@ def main():
     if args.window_bits:
         L.check(lib.cqb_msm_set_window_bits(args.window_bits))
 
+    from sha2_on_cq_halo2_b200.sharded import CudaBackend, ShardedMSM, shard_range
+
     n_total = 1 << args.log_n
-    per = n_total // world
-    start = rank * per
+    start, per = shard_range(n_total, rank, world)
     dev = torch.device("cuda", local_rank)
     bases_t = torch.empty(per * 64, dtype=torch.uint8, device=dev)
     scal_t = torch.empty(per * 32, dtype=torch.uint8, device=dev)
     L.check(lib.cqb_synth_bases_dev(SEED_BASES, start, per, ctypes.c_void_p(bases_t.data_ptr())))
     L.check(lib.cqb_synth_scalars_dev(SEED_SCALARS, start, per, ctypes.c_void_p(scal_t.data_ptr())))
-    h = ctypes.c_uint64(0)
-    L.check(lib.cqb_bases_register_device(ctypes.c_void_p(bases_t.data_ptr()), per, ctypes.byref(h)))
+    backend = CudaBackend(device_ptr=bases_t.data_ptr(), n=per)  # the rank's SRS shard, resident in HBM
+    h = ctypes.c_uint64(backend.handle)
+    msm = ShardedMSM(backend, rank, world, group=None, device=dev)
     scal_host = torch.empty(per * 32, dtype=torch.uint8).pin_memory()
     scal_host.copy_(scal_t)
     torch.cuda.synchronize()
-    host_ptr = ctypes.cast(ctypes.c_void_p(scal_host.data_ptr()), L.u64p)
-
     out = np.zeros(8, np.uint64)
     inf = ctypes.c_int(0)
-    gather_in = torch.zeros(8, dtype=torch.int64, device=dev)
-    gather_out = torch.zeros(8 * world, dtype=torch.int64, device=dev)
-    folded = np.zeros(8, np.uint64)
-
-    def fold_partials():
-        """all-gather the per-rank affine partials (64 B each) and fold them: arithmetic.rs:153 across GPUs"""
-        if world == 1:
-            return out
-        gather_in.copy_(torch.from_numpy(out.view(np.int64)))
-        dist.all_gather_into_tensor(gather_out, gather_in)
-        parts = gather_out.cpu().numpy().view(np.uint64).reshape(world, 8)
-        L.check(lib.cqb_g1_sum_affine(L.p64(np.ascontiguousarray(parts)), world, L.p64(folded), ctypes.byref(inf)))
-        return folded
 
     def step_dev():
-        L.check(lib.cqb_msm_bn254_g1_dev(h.value, 0, ctypes.c_void_p(scal_t.data_ptr()), per, L.p64(out), ctypes.byref(inf)))
-        return fold_partials()
+        return msm.msm_dev(scal_t.data_ptr(), per).to_affine()
 
     def step_e2e():
-        L.check(lib.cqb_msm_bn254_g1(h.value, 0, host_ptr, per, L.p64(out), ctypes.byref(inf)))
-        return fold_partials()
+        return msm.msm_host_ptr(scal_host.data_ptr(), per).to_affine()
 
     def barrier():
         if world > 1:
