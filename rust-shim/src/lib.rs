@@ -1,0 +1,117 @@
+//! Rust side of the drop-in boundary (SOURCE ONLY — not compiled in this repository's image, see Cargo.toml).
+//!
+//! `best_multiexp` / `best_fft` keep the reference's signatures (halo2_proofs/src/arithmetic.rs:132,171). For the two
+//! instantiations on the prover's hot path — `C = bn256::G1Affine` and `G = bn256::Fr` — they call libcqb200.so; every
+//! other instantiation (G2Affine at static_lookup.rs:146, G1 EC-FFT at arithmetic.rs:285) keeps the generic Rust body,
+//! which is a different operation, not a fallback. There is no CPU fallback for the accelerated instantiations: a
+//! non-zero return code panics, like the reference's assert!s.
+//!
+//! Layout contract: `Fr`, `Fq` are `[u64; 4]` Montgomery limbs and `G1Affine` is `{x: Fq, y: Fq}`; the vendored crate must
+//! mark them `#[repr(transparent)]` / `#[repr(C)]` (bn256/fr.rs:22-25, derive/curve.rs:163-168), or the shim goes through
+//! `SerdeObject::to_raw_bytes` (derive/field.rs:302-308), which yields the same bytes.
+use std::any::TypeId;
+use std::os::raw::{c_char, c_int, c_void};
+
+use group::Group as _;
+use halo2curves::bn256::{Fq, Fr, G1Affine, G1};
+use halo2curves::{CurveAffine, Group};
+
+#[allow(non_camel_case_types)]
+pub type cqb_bases_t = u64;
+
+extern "C" {
+    pub fn cqb_init(device: c_int) -> c_int;
+    pub fn cqb_shutdown();
+    pub fn cqb_last_error() -> *const c_char;
+    pub fn cqb_bases_register(affine_xy: *const u64, n: usize, out: *mut cqb_bases_t) -> c_int;
+    pub fn cqb_bases_free(h: cqb_bases_t) -> c_int;
+    pub fn cqb_msm_bn254_g1(b: cqb_bases_t, offset: usize, scalars: *const u64, n: usize, out_xy: *mut u64, is_inf: *mut c_int) -> c_int;
+    pub fn cqb_msm_bn254_g1_host(affine_xy: *const u64, scalars: *const u64, n: usize, out_xy: *mut u64, is_inf: *mut c_int) -> c_int;
+    pub fn cqb_msm_bn254_g1_sparse(b: cqb_bases_t, idx: *const u32, scalars: *const u64, m: usize, out_xy: *mut u64, is_inf: *mut c_int) -> c_int;
+    pub fn cqb_ntt_bn254_fr(a: *mut u64, omega: *const u64, log_n: u32) -> c_int;
+    pub fn cqb_intt_bn254_fr(a: *mut u64, omega_inv: *const u64, divisor: *const u64, log_n: u32) -> c_int;
+    pub fn cqb_coset_ntt_bn254_fr(coeffs: *const u64, n: usize, out: *mut u64, ext_omega: *const u64, ext_log_n: u32,
+                                  g_coset: *const u64, g_coset_inv: *const u64) -> c_int;
+    pub fn cqb_coset_intt_bn254_fr(a: *mut u64, ext_log_n: u32, ext_omega_inv: *const u64, ext_divisor: *const u64,
+                                   g_coset: *const u64, g_coset_inv: *const u64, t_evaluations: *const u64, t_len: u32) -> c_int;
+}
+
+fn check(rc: c_int, what: &str) {
+    if rc != 0 {
+        let msg = unsafe { std::ffi::CStr::from_ptr(cqb_last_error()) }.to_string_lossy().into_owned();
+        panic!("{what}: libcqb200 error {rc}: {msg}"); // the reference panics on its assert!s; so does the shim
+    }
+}
+
+fn g1_from_affine_limbs(xy: [u64; 8], is_inf: c_int) -> G1 {
+    if is_inf != 0 {
+        return G1::identity();
+    }
+    // SAFETY: Fq is #[repr(transparent)] over [u64; 4] (layout contract above)
+    let x: Fq = unsafe { std::mem::transmute([xy[0], xy[1], xy[2], xy[3]]) };
+    let y: Fq = unsafe { std::mem::transmute([xy[4], xy[5], xy[6], xy[7]]) };
+    G1 { x, y, z: Fq::one() }
+}
+
+/// Replacement for halo2_proofs::arithmetic::best_multiexp (arithmetic.rs:132-159).
+pub fn best_multiexp<C: CurveAffine>(coeffs: &[C::Scalar], bases: &[C]) -> C::Curve {
+    assert_eq!(coeffs.len(), bases.len()); // arithmetic.rs:133
+    if TypeId::of::<C>() == TypeId::of::<G1Affine>() {
+        let mut out = [0u64; 8];
+        let mut inf: c_int = 0;
+        let rc = unsafe {
+            cqb_msm_bn254_g1_host(bases.as_ptr() as *const u64, coeffs.as_ptr() as *const u64, coeffs.len(), out.as_mut_ptr(), &mut inf)
+        };
+        check(rc, "best_multiexp");
+        let r = g1_from_affine_limbs(out, inf);
+        // SAFETY: C::Curve == G1 was just established through TypeId
+        return unsafe { std::mem::transmute_copy::<G1, C::Curve>(&r) };
+    }
+    generic::best_multiexp(coeffs, bases) // the reference's own body, moved verbatim into `mod generic`
+}
+
+/// Replacement for halo2_proofs::arithmetic::best_fft (arithmetic.rs:171-234).
+pub fn best_fft<G: Group>(a: &mut [G], omega: G::Scalar, log_n: u32) {
+    assert_eq!(a.len(), 1usize << log_n); // arithmetic.rs:184
+    if TypeId::of::<G>() == TypeId::of::<Fr>() {
+        let rc = unsafe { cqb_ntt_bn254_fr(a.as_mut_ptr() as *mut u64, &omega as *const G::Scalar as *const u64, log_n) };
+        check(rc, "best_fft");
+        return;
+    }
+    generic::best_fft(a, omega, log_n)
+}
+
+/// ParamsKZG keeps one handle per SRS vector (uploaded once in setup/read); commit / commit_lagrange
+/// (poly/kzg/commitment.rs:496-504, 539-543) become:
+pub fn commit_with_handle(handle: cqb_bases_t, poly: &[Fr]) -> G1 {
+    let mut out = [0u64; 8];
+    let mut inf: c_int = 0;
+    let rc = unsafe { cqb_msm_bn254_g1(handle, 0, poly.as_ptr() as *const u64, poly.len(), out.as_mut_ptr(), &mut inf) };
+    check(rc, "commit");
+    g1_from_affine_limbs(out, inf)
+}
+
+/// CQ prover: m_cm / a_cm / qa_cm / a0_cm (plonk/static_lookup/prover.rs:167-170, 245-257) as one sparse MSM each.
+pub fn commit_sparse(handle: cqb_bases_t, idx: &[u32], scalars: &[Fr]) -> G1 {
+    assert_eq!(idx.len(), scalars.len());
+    let mut out = [0u64; 8];
+    let mut inf: c_int = 0;
+    let rc = unsafe { cqb_msm_bn254_g1_sparse(handle, idx.as_ptr(), scalars.as_ptr() as *const u64, idx.len(), out.as_mut_ptr(), &mut inf) };
+    check(rc, "commit_sparse");
+    g1_from_affine_limbs(out, inf)
+}
+
+mod generic {
+    //! The reference's generic bodies of best_multiexp / best_fft (arithmetic.rs:13-159, 171-274) are moved here unchanged
+    //! when the shim is applied inside halo2_proofs; they serve the non-accelerated instantiations only.
+    use halo2curves::{CurveAffine, Group};
+    pub fn best_multiexp<C: CurveAffine>(_coeffs: &[C::Scalar], _bases: &[C]) -> C::Curve {
+        unimplemented!("reference body (arithmetic.rs:13-159) lives in halo2_proofs::arithmetic")
+    }
+    pub fn best_fft<G: Group>(_a: &mut [G], _omega: G::Scalar, _log_n: u32) {
+        unimplemented!("reference body (arithmetic.rs:171-274) lives in halo2_proofs::arithmetic")
+    }
+}
+
+#[allow(dead_code)]
+fn _unused(_: *mut c_void) {}
