@@ -59,6 +59,12 @@ CQB_API int cqb_bases_register(const uint64_t* affine_xy, size_t n, cqb_bases_t*
 CQB_API int cqb_bases_register_device(const void* d_affine_xy, size_t n, cqb_bases_t* out);  /* adopt device memory, no copy */
 CQB_API int cqb_bases_free(cqb_bases_t h);
 CQB_API size_t cqb_bases_len(cqb_bases_t h);
+/* Build the resident table 2^(c w) P_i for every window w (nwin x n x 64 B of HBM: 12 GiB for a 2^24 SRS at c = 22) so
+ * that all windows of an MSM over this set share ONE bucket set: fewer, wider windows and a single bucket reduction.
+ * One-time cost per SRS (like computing g_lagrange in setup, poly/kzg/commitment.rs:234-262). window_bits = 0 picks c
+ * from n. MSMs over >= 1/8 of the set then use the table automatically; results are identical either way. */
+CQB_API int cqb_bases_precompute(cqb_bases_t h, int window_bits);
+CQB_API int cqb_bases_drop_precomputed(cqb_bases_t h);
 
 /* ---- MSM: replaces best_multiexp (halo2_proofs/src/arithmetic.rs:132-159) as called by
  *      Params::commit_lagrange (poly/kzg/commitment.rs:496-504), ParamsProver::commit (:539-543),

@@ -28,6 +28,8 @@ SYMBOLS = [
     ("cqb_bases_register_device", _int, [_vp, _sz, u64p]),
     ("cqb_bases_free", _int, [_u64]),
     ("cqb_bases_len", _sz, [_u64]),
+    ("cqb_bases_precompute", _int, [_u64, _int]),
+    ("cqb_bases_drop_precomputed", _int, [_u64]),
     ("cqb_msm_bn254_g1", _int, [_u64, _sz, u64p, _sz, u64p, _ip]),
     ("cqb_msm_bn254_g1_dev", _int, [_u64, _sz, _vp, _sz, u64p, _ip]),
     ("cqb_msm_bn254_g1_host", _int, [u64p, u64p, _sz, u64p, _ip]),

@@ -66,7 +66,7 @@ void Pinned::release() {
     cap = 0;
 }
 
-struct BaseSet { void* d; size_t n; bool owned; };
+struct BaseSet { void* d; size_t n; bool owned; void* table; int table_c; };
 static std::map<cqb_bases_t, BaseSet> g_bases;
 static cqb_bases_t g_next_handle = 1;
 static Scratch g_scalars, g_idx, g_io, g_tmp_bases, g_out;
@@ -127,8 +127,10 @@ void cqb_shutdown(void) {
     if (!g_ctx.inited) return;
     cudaSetDevice(g_ctx.device);
     cudaDeviceSynchronize();
-    for (auto& kv : g_bases)
+    for (auto& kv : g_bases) {
         if (kv.second.owned) cudaFree(kv.second.d);
+        if (kv.second.table) cudaFree(kv.second.table);
+    }
     g_bases.clear();
     g_scalars.release(); g_idx.release(); g_io.release(); g_tmp_bases.release(); g_out.release();
     g_out_host.release();
@@ -179,7 +181,7 @@ int cqb_bases_register(const uint64_t* affine_xy, size_t n, cqb_bases_t* out) {
     if (n) CQB_CUDA(cudaMemcpyAsync(d, affine_xy, n * 64, cudaMemcpyHostToDevice, g_ctx.stream));
     CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
     cqb_bases_t h = g_next_handle++;
-    g_bases[h] = BaseSet{d, n, true};
+    g_bases[h] = BaseSet{d, n, true, nullptr, 0};
     *out = h;
     return 0;
 }
@@ -188,7 +190,7 @@ int cqb_bases_register_device(const void* d_affine_xy, size_t n, cqb_bases_t* ou
     CQB_TRY(require_init());
     if (!out || !d_affine_xy) return fail(CQB_E_BAD_ARG, "cqb_bases_register_device: NULL argument");
     cqb_bases_t h = g_next_handle++;
-    g_bases[h] = BaseSet{const_cast<void*>(d_affine_xy), n, false};
+    g_bases[h] = BaseSet{const_cast<void*>(d_affine_xy), n, false, nullptr, 0};
     *out = h;
     return 0;
 }
@@ -196,10 +198,9 @@ int cqb_bases_free(cqb_bases_t h) {
     LOCK;
     auto it = g_bases.find(h);
     if (it == g_bases.end()) return fail(CQB_E_BAD_ARG, "unknown bases handle %llu", (unsigned long long)h);
-    if (it->second.owned) {
-        cudaStreamSynchronize(g_ctx.stream);
-        cudaFree(it->second.d);
-    }
+    cudaStreamSynchronize(g_ctx.stream);
+    if (it->second.owned) cudaFree(it->second.d);
+    if (it->second.table) cudaFree(it->second.table);
     g_bases.erase(it);
     return 0;
 }
@@ -210,13 +211,54 @@ size_t cqb_bases_len(cqb_bases_t h) {
 }
 
 // ---- MSM --------------------------------------------------------------------------------------------------------
-static int find_bases(cqb_bases_t h, size_t offset, size_t n, const char** d) {
+static int find_bases(cqb_bases_t h, size_t offset, size_t n, BaseSet** out) {
     auto it = g_bases.find(h);
     if (it == g_bases.end()) return fail(CQB_E_BAD_ARG, "unknown bases handle %llu", (unsigned long long)h);
     // commit / commit_lagrange: assert!(self.n() >= size) poly/kzg/commitment.rs:502,541
     if (offset > it->second.n || n > it->second.n - offset)
         return fail(CQB_E_LEN_MISMATCH, "MSM of %zu scalars at offset %zu exceeds the %zu registered bases", n, offset, it->second.n);
-    *d = (const char*)it->second.d + offset * 64;
+    *out = &it->second;
+    return 0;
+}
+
+// picks the layout: the precomputed single-set table when it exists and the MSM covers a good part of the set
+// (its bucket count is sized for the whole set), else the windowed layout on the plain bases
+static int dispatch_msm(BaseSet* bs, size_t offset, const void* d_scalars, const uint32_t* d_idx, size_t n) {
+    if (bs->table && n * 8 >= bs->n)
+        return msm_run_precomputed(bs->table, bs->n, bs->table_c, offset, d_scalars, d_idx, n, g_out.p);
+    return msm_run(bs->d, offset, d_scalars, d_idx, n, g_out.p);
+}
+
+int cqb_bases_precompute(cqb_bases_t h, int window_bits) {
+    LOCK;
+    CQB_TRY(require_init());
+    auto it = g_bases.find(h);
+    if (it == g_bases.end()) return fail(CQB_E_BAD_ARG, "unknown bases handle %llu", (unsigned long long)h);
+    BaseSet& bs = it->second;
+    if (bs.n == 0) return 0;
+    int c = window_bits ? window_bits : msm_precompute_window_bits(bs.n);
+    if (c < 8 || c > 23) return fail(CQB_E_BAD_ARG, "precompute window bits must be 8..23 (got %d)", c);
+    if (bs.table && bs.table_c == c) return 0;
+    int nwin = msm_windows_for(c);
+    if ((size_t)nwin * bs.n >= ((size_t)1 << 31)) return fail(CQB_E_BAD_SIZE, "base set too large for a precomputed table (%zu x %d rows)", bs.n, nwin);
+    if (bs.table) { cudaStreamSynchronize(g_ctx.stream); cudaFree(bs.table); bs.table = nullptr; }
+    size_t bytes = (size_t)nwin * bs.n * 64;
+    size_t free_b = 0, total_b = 0;
+    CQB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if (bytes > free_b / 2) return fail(CQB_E_OOM, "precomputed table needs %zu bytes, only %zu free", bytes, free_b);
+    if (cudaMalloc(&bs.table, bytes) != cudaSuccess) { cudaGetLastError(); bs.table = nullptr; return fail(CQB_E_OOM, "cudaMalloc(%zu) for the precomputed table failed", bytes); }
+    bs.table_c = c;
+    int rc = msm_precompute_table(bs.d, bs.n, c, bs.table);
+    if (rc) { cudaFree(bs.table); bs.table = nullptr; return rc; }
+    CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return 0;
+}
+
+int cqb_bases_drop_precomputed(cqb_bases_t h) {
+    LOCK;
+    auto it = g_bases.find(h);
+    if (it == g_bases.end()) return fail(CQB_E_BAD_ARG, "unknown bases handle %llu", (unsigned long long)h);
+    if (it->second.table) { cudaStreamSynchronize(g_ctx.stream); cudaFree(it->second.table); it->second.table = nullptr; }
     return 0;
 }
 
@@ -224,9 +266,9 @@ int cqb_msm_bn254_g1_dev(cqb_bases_t b, size_t offset, const void* d_scalars, si
     LOCK;
     CQB_TRY(require_init());
     if (!out_xy || (!d_scalars && n)) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1_dev: NULL argument");
-    const char* d_bases = nullptr;
-    CQB_TRY(find_bases(b, offset, n, &d_bases));
-    CQB_TRY(msm_run(d_bases, d_scalars, nullptr, n, g_out.p));
+    BaseSet* bs = nullptr;
+    CQB_TRY(find_bases(b, offset, n, &bs));
+    CQB_TRY(dispatch_msm(bs, offset, d_scalars, nullptr, n));
     return fetch_result(out_xy, is_inf);
 }
 
@@ -234,11 +276,11 @@ int cqb_msm_bn254_g1(cqb_bases_t b, size_t offset, const uint64_t* scalars, size
     LOCK;
     CQB_TRY(require_init());
     if (!out_xy || (!scalars && n)) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1: NULL argument");
-    const char* d_bases = nullptr;
-    CQB_TRY(find_bases(b, offset, n, &d_bases));
+    BaseSet* bs = nullptr;
+    CQB_TRY(find_bases(b, offset, n, &bs));
     CQB_TRY(g_scalars.ensure(n * 32 + 32));
     if (n) CQB_CUDA(cudaMemcpyAsync(g_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, g_ctx.stream));
-    CQB_TRY(msm_run(d_bases, g_scalars.p, nullptr, n, g_out.p));
+    CQB_TRY(dispatch_msm(bs, offset, g_scalars.p, nullptr, n));
     return fetch_result(out_xy, is_inf);
 }
 
@@ -252,7 +294,7 @@ int cqb_msm_bn254_g1_host(const uint64_t* affine_xy, const uint64_t* scalars, si
         CQB_CUDA(cudaMemcpyAsync(g_tmp_bases.p, affine_xy, n * 64, cudaMemcpyHostToDevice, g_ctx.stream));
         CQB_CUDA(cudaMemcpyAsync(g_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, g_ctx.stream));
     }
-    CQB_TRY(msm_run(g_tmp_bases.p, g_scalars.p, nullptr, n, g_out.p));
+    CQB_TRY(msm_run(g_tmp_bases.p, 0, g_scalars.p, nullptr, n, g_out.p));
     return fetch_result(out_xy, is_inf);
 }
 
@@ -270,7 +312,7 @@ int cqb_msm_bn254_g1_sparse(cqb_bases_t b, const uint32_t* idx, const uint64_t* 
         CQB_CUDA(cudaMemcpyAsync(g_scalars.p, scalars, m * 32, cudaMemcpyHostToDevice, g_ctx.stream));
         CQB_CUDA(cudaMemcpyAsync(g_idx.p, idx, m * 4, cudaMemcpyHostToDevice, g_ctx.stream));
     }
-    CQB_TRY(msm_run(it->second.d, g_scalars.p, g_idx.as<uint32_t>(), m, g_out.p));
+    CQB_TRY(dispatch_msm(&it->second, 0, g_scalars.p, g_idx.as<uint32_t>(), m));
     return fetch_result(out_xy, is_inf);
 }
 

@@ -25,7 +25,14 @@ Fr fr_from_u64x4(const uint64_t* p);
 
 // ---- msm.cu ----
 // sum_i scalars[i] * bases[idx ? idx[i] : i]; d_out receives 64 B affine x||y followed by a uint32 identity flag
-int msm_run(const void* d_bases, const void* d_scalars, const uint32_t* d_idx, size_t n, void* d_out_xy_flag);
+// windowed layout; d_bases = element 0 of the base set, point id = idx ? idx[i] : offset + i
+int msm_run(const void* d_bases, size_t offset, const void* d_scalars, const uint32_t* d_idx, size_t n, void* d_out_xy_flag);
+// single bucket set over a precomputed table (row w = 2^(c w) * bases), table_n points per row
+int msm_run_precomputed(const void* d_table, size_t table_n, int c, size_t offset, const void* d_scalars, const uint32_t* d_idx,
+                        size_t n, void* d_out_xy_flag);
+int msm_precompute_window_bits(size_t n);
+int msm_windows_for(int c);
+int msm_precompute_table(const void* d_bases, size_t n, int c, void* d_table);
 int g1_sum_affine_run(const void* d_points, size_t n, void* d_out_xy_flag);
 void msm_release_all();
 void msm_set_window_bits(int c);

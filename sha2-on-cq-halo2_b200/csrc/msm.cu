@@ -5,20 +5,26 @@
 // running-sum reduction, c doublings between windows, rayon chunks over point ranges. Only the affine normal form of the
 // result is canonical, so any correct evaluation order yields identical output; this file evaluates the
 // same sum the B200 way:
-//   1. msm_count   : Montgomery -> canonical scalar (one modmul), SIGNED c-bit digits (c up to 16 => 2^(c-1) buckets per
-//                    window, half the reference's bucket count), per-(window,bucket) histogram with L2 atomics;
-//   2. msm_scan    : one CTA per window, exclusive scan of the histogram -> bucket offsets;
-//   3. msm_scatter : counting-sort scatter of (point index, sign) into window-major bucket order;
+//   1. msm_count   : Montgomery -> canonical scalar (one modmul), SIGNED c-bit digits (2^(c-1) buckets per window, half
+//                    the reference's bucket count), per-bucket histogram with L2 atomics;
+//   2. msm_scan    : exclusive scan of the histogram -> bucket offsets;
+//   3. msm_scatter : counting-sort scatter of (point id, sign) into bucket order;
 //   4. msm_accumulate : the bucket-sorted lists are cut into equal chunks, one thread per chunk (load balance does not
 //                    depend on the scalar distribution): XYZZ mixed additions (8M+2S) of its points, gathered from the
 //                    device-resident SRS with 128-bit loads; negation folded into the load; all exceptional cases
 //                    (identity base, P+P, P+(-P)) handled as the reference does (derive/curve.rs:866-871);
 //                    msm_merge adds the per-chunk partials of buckets that straddle chunk boundaries;
-//   5. msm_reduce  : per window sum_d d*B_d by chunked running sums (each thread: running-sum over its chunk, then a
-//                    short double-and-add for the chunk offset), 6. window_sum: tree-add the chunk partials,
-//   7. msm_final   : Horner over windows (c doublings each), normalise to affine, write x||y + identity flag.
-// Roofline: integer pipe — 10 modmuls per bucket addition x ceil(254/c) windows per point; the gather of 64 B/point per
-// window is < 10 % of HBM bandwidth at that rate.
+//   5. msm_reduce  : sum_d d*B_d by chunked running sums (each thread: running-sum over its chunk, then a short
+//                    double-and-add for the chunk offset), xyzz_sum: tree-add the chunk partials,
+//   6. msm_final   : Horner over windows (c doublings each), normalise to affine, write x||y + identity flag.
+//
+// Two layouts share these kernels:
+//   * WINDOWED (any bases, e.g. the one-shot host call): nwin = 254/c + 1 independent bucket sets, c <= 16.
+//   * SINGLE SET over a PRECOMPUTED table (registered SRS; memory laid out for the 180 GB of a B200): the table holds
+//     2^(c w) P_i for every window w (nwin x n x 64 B), so all windows feed ONE bucket set: larger c (up to 23) => fewer
+//     windows => fewer bucket additions per point, one bucket reduction instead of nwin, no inter-window doublings.
+// Roofline: integer pipe — 10 modmuls per bucket addition x nwin additions per point; the 64 B gather per addition is
+// < 10 % of HBM bandwidth at that rate.
 #include <algorithm>
 
 #include "internal.h"
@@ -58,7 +64,7 @@ __device__ __forceinline__ void st_xyzz(uint4* p, const G1Xyzz& v) {
     st_fq(p, v.x); st_fq(p + 2, v.y); st_fq(p + 4, v.zz); st_fq(p + 6, v.zzz);
 }
 
-// canonical 254-bit scalar -> signed digit of window w (c bits), given the running carry
+// canonical 254-bit scalar -> raw c-bit digit of window w
 __device__ __forceinline__ uint32_t window_bits(const uint32_t* k, int w, int c) {
     int bit = w * c;
     int limb = bit >> 5, sh = bit & 31;
@@ -69,33 +75,39 @@ __device__ __forceinline__ uint32_t window_bits(const uint32_t* k, int w, int c)
 }
 
 struct MsmShape {
-    int c;           // window bits
-    int nwin;        // number of windows
-    uint32_t nb;     // buckets per window = 2^(c-1) (bucket ids 1..nb)
-    uint32_t stride; // nb + 2 : per-window stride of the histogram / offset arrays
+    int c;            // window bits
+    int nwin;         // number of digit windows per scalar
+    int nsets;        // bucket sets: nwin (windowed) or 1 (single set over a precomputed table)
+    uint32_t nb;      // buckets per set = 2^(c-1) (bucket ids 1..nb)
+    uint32_t stride;  // nb + 2 : per-set stride of the histogram / offset arrays
+    uint32_t table_n; // single set: points per window row of the precomputed table
+    uint32_t offset;  // first base of this MSM inside the registered set
+    size_t list_cap;  // capacity of one set's sorted list: n (windowed) or n * nwin (single set)
 };
+
+__device__ __forceinline__ Fr load_scalar_canonical(const uint4* scalars, size_t i) {
+    uint4 a = __ldg(scalars + 2 * i), b = __ldg(scalars + 2 * i + 1);
+    Fr k;
+    k.l[0] = a.x; k.l[1] = a.y; k.l[2] = a.z; k.l[3] = a.w; k.l[4] = b.x; k.l[5] = b.y; k.l[6] = b.z; k.l[7] = b.w;
+    return fp_from_mont<FrP>(k);  // reference arithmetic.rs:14 to_repr()
+}
 
 // (1) histogram of signed digits. One thread per scalar.
 __global__ void __launch_bounds__(256) msm_count_kernel(const uint4* __restrict__ scalars, size_t n, MsmShape s,
                                                         uint32_t* __restrict__ hist) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Fr k;
-    {
-        uint4 a = __ldg(scalars + 2 * i), b = __ldg(scalars + 2 * i + 1);
-        k.l[0] = a.x; k.l[1] = a.y; k.l[2] = a.z; k.l[3] = a.w; k.l[4] = b.x; k.l[5] = b.y; k.l[6] = b.z; k.l[7] = b.w;
-    }
-    k = fp_from_mont<FrP>(k);  // reference arithmetic.rs:14 to_repr()
+    Fr k = load_scalar_canonical(scalars, i);
     uint32_t carry = 0;
     for (int w = 0; w < s.nwin; w++) {
         uint32_t d = window_bits(k.l, w, s.c) + carry;
         carry = 0;
         if (d > s.nb) { d = (1u << s.c) - d; carry = 1; }
-        if (d) atomicAdd(&hist[(size_t)w * s.stride + d], 1u);
+        if (d) atomicAdd(&hist[(s.nsets == 1 ? (size_t)0 : (size_t)w * s.stride) + d], 1u);
     }
 }
 
-// (2) exclusive scan per window: offs[w][d] = sum_{d' < d} hist[w][d'] for d in 1..nb+1; cursor = copy of offs
+// (2a) exclusive scan, one CTA per bucket set (windowed layout: nb <= 32768)
 __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ offs,
                                                         uint32_t* __restrict__ cursor, MsmShape s) {
     __shared__ uint32_t warp_sums[32];
@@ -107,7 +119,6 @@ __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* __restri
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) carry_s = 0;
     __syncthreads();
-    // process ids 1..nb in tiles of 1024
     for (uint32_t base = 1; base <= s.nb + 1; base += 1024) {
         uint32_t d = base + tid;
         uint32_t v = (d <= s.nb) ? h[d] : 0u;
@@ -137,6 +148,76 @@ __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* __restri
     }
 }
 
+// (2b) three-kernel scan for one large bucket set (single-set layout, nb up to 2^22): tile sums, scan of the tile sums,
+// per-tile scan with its offset. TILE = 1024 threads x 8 ids.
+constexpr uint32_t SCAN_TILE = 8192;
+__device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* warp_sums, uint32_t* total) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane >= off) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t ws = warp_sums[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, ws, off);
+            if (lane >= off) ws += y;
+        }
+        warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    uint32_t excl = (wid ? warp_sums[wid - 1] : 0u) + (x - v);
+    if (total) *total = warp_sums[31];
+    __syncthreads();
+    return excl;
+}
+__global__ void __launch_bounds__(1024) scan_tile_sums_kernel(const uint32_t* __restrict__ hist, uint32_t nb, uint32_t* __restrict__ tile_sums) {
+    __shared__ uint32_t ws[32];
+    uint32_t base = 1 + blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+    uint32_t v = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { uint32_t d = base + j; if (d <= nb) v += hist[d]; }
+    uint32_t total;
+    (void)block_excl_scan_1024(v, ws, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) scan_tile_offsets_kernel(uint32_t* __restrict__ tile_sums, uint32_t ntiles) {
+    __shared__ uint32_t ws[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < ntiles; base += 1024) {
+        uint32_t t = base + threadIdx.x;
+        uint32_t v = t < ntiles ? tile_sums[t] : 0u;
+        uint32_t total;
+        uint32_t excl = block_excl_scan_1024(v, ws, &total);
+        if (t < ntiles) tile_sums[t] = carry + excl;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(1024) scan_apply_kernel(const uint32_t* __restrict__ hist, uint32_t nb, const uint32_t* __restrict__ tile_sums,
+                                                          uint32_t* __restrict__ offs, uint32_t* __restrict__ cursor) {
+    __shared__ uint32_t ws[32];
+    uint32_t base = 1 + blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+    uint32_t vals[8], v = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { uint32_t d = base + j; vals[j] = (d <= nb) ? hist[d] : 0u; v += vals[j]; }
+    uint32_t excl = block_excl_scan_1024(v, ws, nullptr) + tile_sums[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        uint32_t d = base + j;
+        if (d <= nb + 1) { offs[d] = excl; cursor[d] = excl; }
+        excl += vals[j];
+    }
+}
+
 // (3) scatter (point id, sign) into bucket order. One thread per scalar; digits are recomputed (1 modmul) instead of
 // being stored and re-read (saves 2 x 4 B x nwin per point of HBM traffic).
 __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint4* __restrict__ scalars, const uint32_t* __restrict__ idx,
@@ -144,13 +225,8 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint4* __restric
                                                           uint32_t* __restrict__ sorted) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Fr k;
-    {
-        uint4 a = __ldg(scalars + 2 * i), b = __ldg(scalars + 2 * i + 1);
-        k.l[0] = a.x; k.l[1] = a.y; k.l[2] = a.z; k.l[3] = a.w; k.l[4] = b.x; k.l[5] = b.y; k.l[6] = b.z; k.l[7] = b.w;
-    }
-    k = fp_from_mont<FrP>(k);
-    uint32_t pid = idx ? __ldg(idx + i) : (uint32_t)i;
+    Fr k = load_scalar_canonical(scalars, i);
+    uint32_t pid = idx ? __ldg(idx + i) : (uint32_t)i + s.offset;
     uint32_t carry = 0;
     for (int w = 0; w < s.nwin; w++) {
         uint32_t d = window_bits(k.l, w, s.c) + carry;
@@ -158,24 +234,29 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint4* __restric
         uint32_t neg = 0;
         if (d > s.nb) { d = (1u << s.c) - d; carry = 1; neg = 1; }
         if (d) {
-            uint32_t pos = atomicAdd(&cursor[(size_t)w * s.stride + d], 1u);
-            sorted[(size_t)w * n + pos] = (pid << 1) | neg;
+            if (s.nsets == 1) {
+                uint32_t pos = atomicAdd(&cursor[d], 1u);
+                sorted[pos] = ((pid + (uint32_t)w * s.table_n) << 1) | neg;  // row w of the precomputed table
+            } else {
+                uint32_t pos = atomicAdd(&cursor[(size_t)w * s.stride + d], 1u);
+                sorted[(size_t)w * s.list_cap + pos] = (pid << 1) | neg;
+            }
         }
     }
 }
 
-// (4) bucket accumulation, load-balanced independently of the scalar distribution: each window's bucket-sorted list is
+// (4) bucket accumulation, load-balanced independently of the scalar distribution: each set's bucket-sorted list is
 // cut into chunks of 2^seg_log entries and ONE THREAD OWNS ONE CHUNK (not one bucket), so every thread performs the
 // same number of XYZZ mixed additions whether the digits are uniform, all equal, or (the top window) only a few bits
 // wide. Within its chunk a thread walks the bucket boundaries (offs[]): buckets that start and end inside the chunk are
 // complete and stored directly; the first and the last bucket of a chunk may continue in the neighbouring chunks and
 // are stored as "head" / "tail" partials which msm_merge_kernel adds up (one XYZZ add per chunk boundary).
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint4* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                                             const uint32_t* __restrict__ offs, size_t n, MsmShape s,
-                                                             int seg_log, uint32_t cpw, uint4* __restrict__ buckets,
+                                                             const uint32_t* __restrict__ offs, MsmShape s, int seg_log,
+                                                             uint32_t cpw, uint4* __restrict__ buckets,
                                                              uint4* __restrict__ head, uint4* __restrict__ tail) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (size_t)s.nwin * cpw) return;
+    if (gid >= (size_t)s.nsets * cpw) return;
     uint32_t w = (uint32_t)(gid / cpw), k = (uint32_t)(gid % cpw);
     const uint32_t* o = offs + (size_t)w * s.stride;
     const uint32_t total = o[s.nb + 1];
@@ -190,7 +271,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint4* __rest
     }
     uint32_t d = lo, bound = o[d + 1];
     bool is_first = true;
-    const uint32_t* lst = sorted + (size_t)w * n;
+    const uint32_t* lst = sorted + (size_t)w * s.list_cap;
     G1Xyzz acc = G1Xyzz::identity();
     for (uint32_t pos = start; pos < end; pos++) {
         if (pos >= bound) {  // bucket d ends inside this chunk
@@ -210,15 +291,15 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint4* __rest
     else st_xyzz(tail + gid * 8, acc);
 }
 
-// (4b) one thread per (window, bucket): add up the head/tail partials of the chunks the bucket overlaps. Buckets that
-// span more than MERGE_LONG chunks (heavily repeated digits) are queued for msm_merge_big_kernel.
+// (4b) one thread per bucket: add up the head/tail partials of the chunks the bucket overlaps. Buckets that span more
+// than MERGE_LONG chunks (heavily repeated digits) are queued for msm_merge_big_kernel.
 constexpr uint32_t MERGE_LONG = 32;
 __global__ void __launch_bounds__(128) msm_merge_kernel(const uint32_t* __restrict__ offs, MsmShape s, int seg_log, uint32_t cpw,
                                                         uint4* __restrict__ buckets, const uint4* __restrict__ head,
                                                         const uint4* __restrict__ tail, uint32_t* __restrict__ big_count,
                                                         uint2* __restrict__ big_list, uint32_t big_cap) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (size_t)s.nwin * s.nb) return;
+    if (gid >= (size_t)s.nsets * s.nb) return;
     uint32_t w = (uint32_t)(gid / s.nb), d = (uint32_t)(gid % s.nb) + 1;
     const uint32_t* o = offs + (size_t)w * s.stride;
     const uint32_t total = o[s.nb + 1];
@@ -249,6 +330,22 @@ __global__ void __launch_bounds__(128) msm_merge_kernel(const uint32_t* __restri
     st_xyzz(buckets + gid * 8, acc);
 }
 
+// shared-memory tree of XYZZ adds over 128 threads; result valid in thread 0
+__device__ __forceinline__ G1Xyzz block_sum_128(G1Xyzz acc, uint4* sm) {
+    const int tid = threadIdx.x;
+    st_xyzz(sm + tid * 8, acc);
+    __syncthreads();
+    for (int half = 64; half >= 1; half >>= 1) {
+        if (tid < half) {
+            G1Xyzz a = ld_xyzz(sm + tid * 8), b2 = ld_xyzz(sm + (tid + half) * 8);
+            g1_add(a, b2);
+            st_xyzz(sm + tid * 8, a);
+        }
+        __syncthreads();
+    }
+    return ld_xyzz(sm);
+}
+
 // (4c) one CTA per queued long bucket: threads stride over its chunk partials, then a shared-memory tree of XYZZ adds
 __global__ void __launch_bounds__(128) msm_merge_big_kernel(const uint32_t* __restrict__ offs, MsmShape s, int seg_log, uint32_t cpw,
                                                             uint4* __restrict__ buckets, const uint4* __restrict__ head,
@@ -261,34 +358,21 @@ __global__ void __launch_bounds__(128) msm_merge_big_kernel(const uint32_t* __re
     const uint32_t* o = offs + (size_t)w * s.stride;
     const uint32_t start = o[d], end = o[d + 1];
     const uint32_t kf = start >> seg_log, kl = (end - 1) >> seg_log;
-    const int tid = threadIdx.x;
     G1Xyzz acc = G1Xyzz::identity();
-    for (uint32_t k = kf + tid; k <= kl; k += 128) {
+    for (uint32_t k = kf + threadIdx.x; k <= kl; k += 128) {
         bool isfirst = start <= (k << seg_log);
         G1Xyzz p = ld_xyzz((isfirst ? head : tail) + ((size_t)w * cpw + k) * 8);
         g1_add(acc, p);
     }
-    st_xyzz(sm + tid * 8, acc);
-    __syncthreads();
-    for (int half = 64; half >= 1; half >>= 1) {
-        if (tid < half) {
-            G1Xyzz a = ld_xyzz(sm + tid * 8), b2 = ld_xyzz(sm + (tid + half) * 8);
-            g1_add(a, b2);
-            st_xyzz(sm + tid * 8, a);
-        }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        G1Xyzz r = ld_xyzz(sm);
-        st_xyzz(buckets + ((size_t)w * s.nb + (d - 1)) * 8, r);
-    }
+    G1Xyzz r = block_sum_128(acc, sm);
+    if (threadIdx.x == 0) st_xyzz(buckets + ((size_t)w * s.nb + (d - 1)) * 8, r);
 }
 
-// (5) per-window weighted bucket sum, chunked: thread t of window w owns bucket ids [t*CH + 1, (t+1)*CH]
+// (5) per-set weighted bucket sum, chunked: thread t of set w owns bucket ids [t*CH + 1, (t+1)*CH]
 __global__ void __launch_bounds__(128) msm_reduce_kernel(const uint4* __restrict__ buckets, MsmShape s, uint32_t tpw, uint32_t ch,
                                                          uint4* __restrict__ partials) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (size_t)s.nwin * tpw) return;
+    if (gid >= (size_t)s.nsets * tpw) return;
     uint32_t w = (uint32_t)(gid / tpw), t = (uint32_t)(gid % tpw);
     const uint4* b = buckets + ((size_t)w * s.nb + (size_t)t * ch) * 8;
     G1Xyzz running = G1Xyzz::identity(), acc = G1Xyzz::identity();
@@ -310,37 +394,28 @@ __global__ void __launch_bounds__(128) msm_reduce_kernel(const uint4* __restrict
     st_xyzz(partials + gid * 8, acc);
 }
 
-// (6) per-window sum of the chunk partials: one CTA of 128 threads per window
-__global__ void __launch_bounds__(128) msm_window_sum_kernel(const uint4* __restrict__ partials, uint32_t tpw, uint4* __restrict__ wins) {
+// (5b) segmented tree sum: set w has `count` XYZZ inputs; CTA (w, j) adds inputs [j*2048, (j+1)*2048) into out[w][j]
+__global__ void __launch_bounds__(128) xyzz_sum_kernel(const uint4* __restrict__ in, uint32_t count, uint32_t out_per_set,
+                                                       uint4* __restrict__ out) {
     __shared__ uint4 sm[128 * 8];
-    const int w = blockIdx.x, tid = threadIdx.x;
+    const uint32_t w = blockIdx.x / out_per_set, j = blockIdx.x % out_per_set;
+    const uint32_t lo = j * 2048u, hi = min(lo + 2048u, count);
     G1Xyzz acc = G1Xyzz::identity();
-    for (uint32_t j = tid; j < tpw; j += 128) {
-        G1Xyzz p = ld_xyzz(partials + ((size_t)w * tpw + j) * 8);
+    for (uint32_t k = lo + threadIdx.x; k < hi; k += 128) {
+        G1Xyzz p = ld_xyzz(in + ((size_t)w * count + k) * 8);
         g1_add(acc, p);
     }
-    st_xyzz(sm + tid * 8, acc);
-    __syncthreads();
-    for (int half = 64; half >= 1; half >>= 1) {
-        if (tid < half) {
-            G1Xyzz a = ld_xyzz(sm + tid * 8), b2 = ld_xyzz(sm + (tid + half) * 8);
-            g1_add(a, b2);
-            st_xyzz(sm + tid * 8, a);
-        }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        G1Xyzz r = ld_xyzz(sm);
-        st_xyzz(wins + (size_t)w * 8, r);
-    }
+    G1Xyzz r = block_sum_128(acc, sm);
+    if (threadIdx.x == 0) st_xyzz(out + ((size_t)w * out_per_set + j) * 8, r);
 }
 
-// (7) Horner over windows + affine normalisation: out = 64 B x||y, then uint32 is_identity
+// (6) Horner over the bucket sets + affine normalisation: out = 64 B x||y, then uint32 is_identity
 __global__ void msm_final_kernel(const uint4* __restrict__ wins, MsmShape s, uint4* __restrict__ out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     G1Xyzz acc = G1Xyzz::identity();
-    for (int w = s.nwin - 1; w >= 0; w--) {
-        for (int k = 0; k < s.c; k++) acc = g1_double(acc);  // reference arithmetic.rs:47-49
+    for (int w = s.nsets - 1; w >= 0; w--) {
+        if (!acc.is_identity())
+            for (int k = 0; k < s.c; k++) acc = g1_double(acc);  // reference arithmetic.rs:47-49
         G1Xyzz ww = ld_xyzz(wins + (size_t)w * 8);
         g1_add(acc, ww);
     }
@@ -354,25 +429,14 @@ __global__ void msm_final_kernel(const uint4* __restrict__ wins, MsmShape s, uin
 // sum of n affine points (multi-GPU partial fold). Single CTA; n is tiny (number of GPUs) but any n works.
 __global__ void __launch_bounds__(128) g1_sum_affine_kernel(const uint4* __restrict__ pts, size_t n, uint4* __restrict__ out) {
     __shared__ uint4 sm[128 * 8];
-    const int tid = threadIdx.x;
     G1Xyzz acc = G1Xyzz::identity();
-    for (size_t j = tid; j < n; j += 128) {
+    for (size_t j = threadIdx.x; j < n; j += 128) {
         Fq x = ld_fq(pts + j * 4), y = ld_fq(pts + j * 4 + 2);
         if (x.is_zero() && y.is_zero()) continue;
         g1_madd(acc, x, y);
     }
-    st_xyzz(sm + tid * 8, acc);
-    __syncthreads();
-    for (int half = 64; half >= 1; half >>= 1) {
-        if (tid < half) {
-            G1Xyzz a = ld_xyzz(sm + tid * 8), b2 = ld_xyzz(sm + (tid + half) * 8);
-            g1_add(a, b2);
-            st_xyzz(sm + tid * 8, a);
-        }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        G1Xyzz r = ld_xyzz(sm);
+    G1Xyzz r = block_sum_128(acc, sm);
+    if (threadIdx.x == 0) {
         G1Affine a = g1_to_affine(r);
         st_fq(out, a.x);
         st_fq(out + 2, a.y);
@@ -380,10 +444,51 @@ __global__ void __launch_bounds__(128) g1_sum_affine_kernel(const uint4* __restr
     }
 }
 
+// ---- precomputed table: row w holds 2^(c w) P_i. One launch per row: each thread turns PRE_RUN consecutive points of
+// row w-1 into row w with c doublings in XYZZ and ONE shared inversion (batch_normalize, derive/curve.rs:362-397).
+constexpr int PRE_RUN = 32;
+__global__ void __launch_bounds__(128) msm_precompute_row_kernel(const uint4* __restrict__ prev, uint4* __restrict__ next, size_t n, int c,
+                                                                 uint4* __restrict__ tmp) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t p0 = t * PRE_RUN;
+    if (p0 >= n) return;
+    size_t cnt = (n - p0 < (size_t)PRE_RUN) ? (n - p0) : (size_t)PRE_RUN;
+    Fq prod = Fq::one();
+    for (size_t j = 0; j < cnt; j++) {
+        const uint4* src = prev + (p0 + j) * 4;
+        Fq x = ld_fq(src), y = ld_fq(src + 2);
+        G1Xyzz P = G1Xyzz::identity();
+        if (!(x.is_zero() && y.is_zero())) {
+            P = g1_double_affine(x, y);
+            for (int k = 1; k < c; k++) P = g1_double(P);
+        }
+        uint4* slot = tmp + (p0 + j) * 10;
+        st_xyzz(slot, P);
+        st_fq(slot + 8, prod);
+        if (!P.is_identity()) prod = fp_mul<FqP>(prod, fp_mul<FqP>(P.zz, P.zzz));
+    }
+    Fq inv = fp_inv<FqP>(prod);
+    for (size_t j = cnt; j-- > 0;) {
+        const uint4* slot = tmp + (p0 + j) * 10;
+        G1Xyzz P = ld_xyzz(slot);
+        Fq pre = ld_fq(slot + 8);
+        Fq ax = Fq::zero(), ay = Fq::zero();
+        if (!P.is_identity()) {
+            Fq zi = fp_mul<FqP>(inv, pre);
+            inv = fp_mul<FqP>(inv, fp_mul<FqP>(P.zz, P.zzz));
+            ax = fp_mul<FqP>(P.x, fp_mul<FqP>(zi, P.zzz));
+            ay = fp_mul<FqP>(P.y, fp_mul<FqP>(zi, P.zz));
+        }
+        uint4* dst = next + (p0 + j) * 4;
+        st_fq(dst, ax);
+        st_fq(dst + 2, ay);
+    }
+}
+
 // -------------------------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------------------------
-static Scratch g_hist, g_sorted, g_buckets, g_partials, g_chunks;
+static Scratch g_hist, g_sorted, g_buckets, g_partials, g_chunks, g_pre_tmp;
 
 // optional per-phase device timing (cudaEvents on the launch stream; no host sync until the times are read)
 static bool g_prof = false;
@@ -400,7 +505,7 @@ static void prof_mark(int i) {
     cudaEventRecord(g_ev[i], ctx().stream);
     g_ev_count = i + 1;
 }
-// ms[0..7] = count, scan, scatter, accumulate, merge, reduce, window_sum, final of the most recent MSM
+// ms[0..7] = count, scan, scatter, accumulate, merge, reduce, sum, final of the most recent MSM
 int msm_phase_ms(float* ms, int cap) {
     if (!g_prof || g_ev_count < 9) return 0;
     cudaEventSynchronize(g_ev[8]);
@@ -415,63 +520,102 @@ void msm_release_all() {
     g_buckets.release();
     g_partials.release();
     g_chunks.release();
+    g_pre_tmp.release();
 }
 
-static int floor_log2(size_t n) {
+static int ceil_log2(size_t n) {
     int l = 0;
-    while (((size_t)1 << (l + 1)) <= n) l++;
+    while (((size_t)1 << l) < n) l++;
     return l;
 }
 
-static MsmShape choose_shape(size_t n) {
+int msm_windows_for(int c) { return 254 / c + 1; }  // scalars < r < 2^254; the extra window absorbs the signed-digit carry
+
+// window bits for the single-set layout: minimise nwin(c) * n * 10 (bucket additions) + 2^(c-1) * 40 (bucket reduction)
+int msm_precompute_window_bits(size_t n) {
+    if (g_forced_c >= 8) return std::min(g_forced_c, 23);
+    double best = 1e300;
+    int best_c = 12;
+    for (int c = 10; c <= 23; c++) {
+        double cost = msm_windows_for(c) * (double)n * 10.0 + (double)((size_t)1 << (c - 1)) * 40.0;
+        if (cost < best) { best = cost; best_c = c; }
+    }
+    return best_c;
+}
+
+// builds the table: row 0 = the bases themselves (copied), row w = 2^c * row (w-1); d_table has nwin * n * 64 bytes
+int msm_precompute_table(const void* d_bases, size_t n, int c, void* d_table) {
+    cudaStream_t st = ctx().stream;
+    int nwin = msm_windows_for(c);
+    CQB_CUDA(cudaMemcpyAsync(d_table, d_bases, n * 64, cudaMemcpyDeviceToDevice, st));
+    const size_t CHUNK = (size_t)1 << 22;
+    CQB_TRY(g_pre_tmp.ensure(std::min(n, CHUNK) * 160));
+    for (int w = 1; w < nwin; w++) {
+        const char* prev = (const char*)d_table + (size_t)(w - 1) * n * 64;
+        char* next = (char*)d_table + (size_t)w * n * 64;
+        for (size_t off = 0; off < n; off += CHUNK) {
+            size_t m = std::min(CHUNK, n - off);
+            size_t threads = (m + PRE_RUN - 1) / PRE_RUN;
+            msm_precompute_row_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>((const uint4*)(prev + off * 64), (uint4*)(next + off * 64), m, c,
+                                                                                          g_pre_tmp.as<uint4>());
+            CQB_LAUNCHED();
+        }
+    }
+    CQB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static MsmShape windowed_shape(size_t n) {
     int c;
-    if (g_forced_c > 0) c = g_forced_c;
+    if (g_forced_c > 0) c = std::min(g_forced_c, 16);
     else {
-        int lg = n > 1 ? floor_log2(n - 1) + 1 : 0;  // ceil(log2 n)
-        c = lg - 4;
+        c = ceil_log2(n) - 4;
         if (c < 4) c = 4;
         if (c > 16) c = 16;
     }
     if (c < 2) c = 2;
-    if (c > 16) c = 16;
     MsmShape s;
     s.c = c;
-    s.nwin = 254 / c + 1;  // scalars < r < 2^254; one extra window absorbs the signed-digit carry
+    s.nwin = msm_windows_for(c);
+    s.nsets = s.nwin;
     s.nb = 1u << (c - 1);
     s.stride = s.nb + 2;
+    s.table_n = 0;
+    s.offset = 0;
+    s.list_cap = n;
     return s;
 }
 
-int msm_run(const void* d_bases, const void* d_scalars, const uint32_t* d_idx, size_t n, void* d_out) {
+// d_bases: windowed layout -> element 0 of the registered set (pid = offset + i); single-set layout -> the table base.
+static int msm_run_shape(const void* d_bases, const void* d_scalars, const uint32_t* d_idx, size_t n, MsmShape s, void* d_out) {
     cudaStream_t st = ctx().stream;
-    if (n == 0) {  // empty sum = identity (best_multiexp of empty slices returns identity)
-        static const uint32_t zero_pt[20] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0};
-        CQB_CUDA(cudaMemcpyAsync(d_out, zero_pt, sizeof(zero_pt), cudaMemcpyHostToDevice, st));
-        return 0;
-    }
-    if (n > ((size_t)1 << 31) - 1) return fail(CQB_E_BAD_SIZE, "MSM of %zu points exceeds the 2^31-1 index range", n);
-    MsmShape s = choose_shape(n);
-    size_t hist_words = (size_t)s.nwin * s.stride;
-    CQB_TRY(g_hist.ensure(hist_words * 4 * 3));
+    size_t hist_words = (size_t)s.nsets * s.stride;
+    uint32_t ntiles = (s.nb + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    CQB_TRY(g_hist.ensure((hist_words * 3 + ntiles + 8) * 4));
     uint32_t* hist = g_hist.as<uint32_t>();
     uint32_t* offs = hist + hist_words;
     uint32_t* cursor = offs + hist_words;
-    CQB_TRY(g_sorted.ensure((size_t)s.nwin * n * 4));
-    size_t nbuckets = (size_t)s.nwin * s.nb;
+    uint32_t* tile_sums = cursor + hist_words;
+    CQB_TRY(g_sorted.ensure((size_t)s.nsets * s.list_cap * 4));
+    size_t nbuckets = (size_t)s.nsets * s.nb;
     CQB_TRY(g_buckets.ensure(nbuckets * 128));
-    uint32_t tpw = std::min<uint32_t>(s.nb, 1024);
-    if (s.nb / tpw < 2 && s.nb >= 2) tpw = s.nb / 2;  // at least 2 buckets per thread
+    // bucket reduction: tpw threads per set, ch buckets each (both powers of two, ch >= 2)
+    uint32_t tpw = std::min<uint32_t>(s.nb / 2, s.nsets == 1 ? 65536u : 1024u);
+    if (tpw < 1) tpw = 1;
     uint32_t ch = s.nb / tpw;
-    CQB_TRY(g_partials.ensure(((size_t)s.nwin * tpw + s.nwin) * 128));
+    uint32_t lvl1 = (tpw + 2047) / 2048;  // tree-sum levels over the tpw partials per set
+    CQB_TRY(g_partials.ensure(((size_t)s.nsets * (tpw + lvl1 + 1) + 1) * 128));
     uint4* partials = g_partials.as<uint4>();
-    uint4* wins = partials + (size_t)s.nwin * tpw * 8;
+    uint4* sums1 = partials + (size_t)s.nsets * tpw * 8;
+    uint4* wins = sums1 + (size_t)s.nsets * lvl1 * 8;
 
     // chunking of the bucket-sorted lists: aim for >= ~150k chunk threads, 16..256 entries each
+    size_t entries = (size_t)n * s.nwin;
     int seg_log = 8;
-    while (seg_log > 4 && (((size_t)n * s.nwin) >> seg_log) < 150000) seg_log--;
-    uint32_t cpw = (uint32_t)((n + ((size_t)1 << seg_log) - 1) >> seg_log);  // chunks per window (upper bound)
-    size_t nchunks = (size_t)s.nwin * cpw;
-    uint32_t big_cap = (uint32_t)(s.nwin * (cpw / MERGE_LONG + 2));
+    while (seg_log > 4 && (entries >> seg_log) < 150000) seg_log--;
+    uint32_t cpw = (uint32_t)((s.list_cap + ((size_t)1 << seg_log) - 1) >> seg_log);  // chunks per set (upper bound)
+    size_t nchunks = (size_t)s.nsets * cpw;
+    uint32_t big_cap = (uint32_t)(s.nsets * (cpw / MERGE_LONG + 2));
     CQB_TRY(g_chunks.ensure(nchunks * 256 + 16 + (size_t)big_cap * 8));
     uint4* head = g_chunks.as<uint4>();
     uint4* tail = head + nchunks * 8;
@@ -487,34 +631,83 @@ int msm_run(const void* d_bases, const void* d_scalars, const uint32_t* d_idx, s
     msm_count_kernel<<<gN, 256, 0, st>>>((const uint4*)d_scalars, n, s, hist);
     CQB_LAUNCHED();
     prof_mark(1);
-    msm_scan_kernel<<<s.nwin, 1024, 0, st>>>(hist, offs, cursor, s);
-    CQB_LAUNCHED();
+    if (s.nsets == 1 && s.nb > 32768) {
+        scan_tile_sums_kernel<<<ntiles, 1024, 0, st>>>(hist, s.nb, tile_sums);
+        CQB_LAUNCHED();
+        scan_tile_offsets_kernel<<<1, 1024, 0, st>>>(tile_sums, ntiles);
+        CQB_LAUNCHED();
+        scan_apply_kernel<<<ntiles, 1024, 0, st>>>(hist, s.nb, tile_sums, offs, cursor);
+        CQB_LAUNCHED();
+    } else {
+        msm_scan_kernel<<<s.nsets, 1024, 0, st>>>(hist, offs, cursor, s);
+        CQB_LAUNCHED();
+    }
     prof_mark(2);
     msm_scatter_kernel<<<gN, 256, 0, st>>>((const uint4*)d_scalars, d_idx, n, s, cursor, g_sorted.as<uint32_t>());
     CQB_LAUNCHED();
     prof_mark(3);
-    msm_accumulate_kernel<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>((const uint4*)d_bases, g_sorted.as<uint32_t>(), offs, n, s,
-                                                                              seg_log, cpw, g_buckets.as<uint4>(), head, tail);
+    msm_accumulate_kernel<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>((const uint4*)d_bases, g_sorted.as<uint32_t>(), offs, s, seg_log, cpw,
+                                                                              g_buckets.as<uint4>(), head, tail);
     CQB_LAUNCHED();
     prof_mark(4);
-    msm_merge_kernel<<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>(offs, s, seg_log, cpw, g_buckets.as<uint4>(), head, tail,
-                                                                          big_count, big_list, big_cap);
+    msm_merge_kernel<<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>(offs, s, seg_log, cpw, g_buckets.as<uint4>(), head, tail, big_count,
+                                                                          big_list, big_cap);
     CQB_LAUNCHED();
     msm_merge_big_kernel<<<big_cap, 128, 0, st>>>(offs, s, seg_log, cpw, g_buckets.as<uint4>(), head, tail, big_count, big_list);
     CQB_LAUNCHED();
     prof_mark(5);
-    size_t nred = (size_t)s.nwin * tpw;
+    size_t nred = (size_t)s.nsets * tpw;
     msm_reduce_kernel<<<(unsigned)((nred + 127) / 128), 128, 0, st>>>(g_buckets.as<uint4>(), s, tpw, ch, partials);
     CQB_LAUNCHED();
     prof_mark(6);
-    msm_window_sum_kernel<<<s.nwin, 128, 0, st>>>(partials, tpw, wins);
-    CQB_LAUNCHED();
+    if (lvl1 > 1) {
+        xyzz_sum_kernel<<<s.nsets * lvl1, 128, 0, st>>>(partials, tpw, lvl1, sums1);
+        CQB_LAUNCHED();
+        xyzz_sum_kernel<<<s.nsets, 128, 0, st>>>(sums1, lvl1, 1, wins);
+        CQB_LAUNCHED();
+    } else {
+        xyzz_sum_kernel<<<s.nsets, 128, 0, st>>>(partials, tpw, 1, wins);
+        CQB_LAUNCHED();
+    }
     prof_mark(7);
     msm_final_kernel<<<1, 32, 0, st>>>(wins, s, (uint4*)d_out);
     CQB_LAUNCHED();
     prof_mark(8);
     CQB_CUDA(cudaGetLastError());
     return 0;
+}
+
+static int msm_empty(void* d_out) {
+    static const uint32_t zero_pt[20] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0};
+    CQB_CUDA(cudaMemcpyAsync(d_out, zero_pt, sizeof(zero_pt), cudaMemcpyHostToDevice, ctx().stream));
+    return 0;
+}
+
+// windowed layout: sum_i scalars[i] * bases[idx ? idx[i] : offset + i]
+int msm_run(const void* d_bases, size_t offset, const void* d_scalars, const uint32_t* d_idx, size_t n, void* d_out) {
+    if (n == 0) return msm_empty(d_out);  // best_multiexp of empty slices returns the identity
+    if (n > ((size_t)1 << 30)) return fail(CQB_E_BAD_SIZE, "MSM of %zu points exceeds the supported 2^30", n);
+    MsmShape s = windowed_shape(n);
+    s.offset = (uint32_t)offset;
+    return msm_run_shape(d_bases, d_scalars, d_idx, n, s, d_out);
+}
+
+// single-set layout over a precomputed table of `table_n` points per row built with window bits c
+int msm_run_precomputed(const void* d_table, size_t table_n, int c, size_t offset, const void* d_scalars, const uint32_t* d_idx, size_t n,
+                        void* d_out) {
+    if (n == 0) return msm_empty(d_out);
+    MsmShape s;
+    s.c = c;
+    s.nwin = msm_windows_for(c);
+    s.nsets = 1;
+    s.nb = 1u << (c - 1);
+    s.stride = s.nb + 2;
+    s.table_n = (uint32_t)table_n;
+    s.offset = (uint32_t)offset;
+    s.list_cap = n * (size_t)s.nwin;
+    if (s.list_cap >= ((size_t)1 << 32) || (size_t)s.nwin * table_n >= ((size_t)1 << 31))
+        return fail(CQB_E_BAD_SIZE, "precomputed MSM: %zu x %d entries exceed the 32-bit index range", n, s.nwin);
+    return msm_run_shape(d_table, d_scalars, d_idx, n, s, d_out);
 }
 
 int g1_sum_affine_run(const void* d_points, size_t n, void* d_out) {

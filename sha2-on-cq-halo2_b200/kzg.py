@@ -12,12 +12,21 @@ from .arithmetic import G1, _as_fr, _as_g1
 class DeviceBases:
     """A device-resident Vec<G1Affine>"""
 
-    def __init__(self, affine):
+    def __init__(self, affine, precompute=None, window_bits=0):
+        """precompute: build the resident 2^(c w) P_i table (cqb_bases_precompute) so that MSMs over this set use one
+        bucket set with wider windows. None = automatically for sets of >= 2^16 points."""
         affine = _as_g1(affine)
         self.n = affine.shape[0]
         h = ctypes.c_uint64(0)
         _lib.check(_lib.lib().cqb_bases_register(_lib.p64(affine), self.n, ctypes.byref(h)))
         self.handle = h.value
+        if precompute is None:
+            precompute = self.n >= (1 << 16)
+        if precompute and self.n:
+            self.precompute(window_bits)
+
+    def precompute(self, window_bits=0):
+        _lib.check(_lib.lib().cqb_bases_precompute(self.handle, window_bits))
 
     def free(self):
         if self.handle:
@@ -45,12 +54,12 @@ class DeviceBases:
 class ParamsKZG:
     """reference poly/kzg/commitment.rs:31-39 { k, n, g, g_lagrange, .. } (g2 / s_g2 are verifier-side, out of scope)"""
 
-    def __init__(self, k, g, g_lagrange):
+    def __init__(self, k, g, g_lagrange, precompute=None):
         self.k = k
         self.n = 1 << k
         assert g.shape == (self.n, 8) and g_lagrange.shape == (self.n, 8)
-        self.g = DeviceBases(g)
-        self.g_lagrange = DeviceBases(g_lagrange)
+        self.g = DeviceBases(g, precompute)
+        self.g_lagrange = DeviceBases(g_lagrange, precompute)
 
     def commit_lagrange(self, poly, _blind=None):
         """reference commitment.rs:496-504: assert!(self.n() >= size); best_multiexp(poly, &self.g_lagrange[0..size])"""

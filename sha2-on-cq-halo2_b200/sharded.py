@@ -27,7 +27,7 @@ def shard_range(n, rank, world):
 class CudaBackend:
     """device operations through the C ABI"""
 
-    def __init__(self, bases_affine=None, device_ptr=None, n=None):
+    def __init__(self, bases_affine=None, device_ptr=None, n=None, precompute=False, window_bits=0):
         lib = _lib.lib()
         h = ctypes.c_uint64(0)
         if device_ptr is not None:
@@ -38,6 +38,8 @@ class CudaBackend:
             self.n = bases_affine.shape[0]
             _lib.check(lib.cqb_bases_register(_lib.p64(bases_affine), self.n, ctypes.byref(h)))
         self.handle = h.value
+        if precompute:
+            _lib.check(lib.cqb_bases_precompute(self.handle, window_bits))
         self._out = np.zeros(8, np.uint64)
         self._inf = ctypes.c_int(0)
 

@@ -249,3 +249,34 @@ def test_best_multiexp_long_buckets(cq, oracle, kind):
     _, exp = oracle.best_multiexp(sc, bases, 8)
     got = cq.best_multiexp(sc, bases)
     assert np.array_equal(got.to_affine(), exp)
+
+
+@pytest.mark.parametrize("n,c", [(1 << 12, 10), (5000, 12), (1 << 15, 0), (1 << 16, 17), (40000, 20)])
+def test_precomputed_table_msm_parity(cq, oracle, n, c):
+    """single-bucket-set layout over the per-SRS table 2^(c w) P_i (cqb_bases_precompute): same result as the windowed
+    layout and as the oracle, for full-size, prefix, offset and sparse MSMs"""
+    sc, bases = _edge_inputs(oracle, n, 9000 + n)
+    dev = cq.DeviceBases(bases, precompute=True, window_bits=c)
+    _, exp = oracle.best_multiexp(sc, bases, 8)
+    assert np.array_equal(dev.msm(sc).to_affine(), exp)
+    m = n // 2 + 3                      # prefix (commit of a shorter polynomial, commitment.rs:502)
+    _, exp_p = oracle.best_multiexp(sc[:m], bases[:m], 8)
+    assert np.array_equal(dev.msm(sc[:m]).to_affine(), exp_p)
+    off = n // 3                        # offset slice (degree-bound commit over the tail of the SRS)
+    _, exp_o = oracle.best_multiexp(sc[: n - off], bases[off:], 8)
+    assert np.array_equal(dev.msm(sc[: n - off], offset=off).to_affine(), exp_o)
+    tiny = 17                           # far below 1/8 of the set: falls back to the windowed layout
+    _, exp_t = oracle.best_multiexp(sc[:tiny], bases[:tiny], 1)
+    assert np.array_equal(dev.msm(sc[:tiny]).to_affine(), exp_t)
+    rng = np.random.default_rng(3)
+    idx = np.sort(rng.choice(n, n // 2, replace=False)).astype(np.uint32)
+    dense = np.zeros((n, 4), np.uint64)
+    dense[idx] = sc[: idx.shape[0]]
+    _, exp_s = oracle.best_multiexp(dense, bases, 8)
+    assert np.array_equal(dev.msm_sparse(idx, sc[: idx.shape[0]]).to_affine(), exp_s)
+    # skewed scalars on the single-set layout
+    sk = sc.copy()
+    sk[:] = sk[5]
+    _, exp_k = oracle.best_multiexp(sk, bases, 8)
+    assert np.array_equal(dev.msm(sk).to_affine(), exp_k)
+    dev.free()

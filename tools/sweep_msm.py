@@ -28,10 +28,21 @@ L.check(lib.cqb_bases_register_device(ctypes.c_void_p(bases.data_ptr()), nmax, c
 out = np.zeros(8, np.uint64)
 inf = ctypes.c_int(0)
 ph = (ctypes.c_float * 8)()
+pre = len(sys.argv) > 3 and sys.argv[3] == "pre"
 for lg in logs:
     n = 1 << lg
+    if pre:
+        hh = ctypes.c_uint64(0)
+        L.check(lib.cqb_bases_register_device(ctypes.c_void_p(bases.data_ptr()), n, ctypes.byref(hh)))
     for c in cs:
-        L.check(lib.cqb_msm_set_window_bits(c))
+        if pre:
+            import time
+            t0 = time.time()
+            L.check(lib.cqb_bases_precompute(hh.value, c))
+            pre_s = time.time() - t0
+            h = hh
+        else:
+            L.check(lib.cqb_msm_set_window_bits(c))
         def run():
             L.check(lib.cqb_msm_bn254_g1_dev(h.value, 0, ctypes.c_void_p(scal.data_ptr()), n, L.p64(out), ctypes.byref(inf)))
         for _ in range(2):
@@ -46,4 +57,6 @@ for lg in logs:
         ms = e0.elapsed_time(e1) / reps
         lib.cqb_msm_phase_ms(ph, 8)
         print(json.dumps({"log_n": lg, "c": c, "ms": round(ms, 4), "mpts": round(n / ms / 1e3, 2),
-                          "phases": [round(ph[i], 4) for i in range(8)], "x0": hex(int(out[0]))}), flush=True)
+                          "phases": [round(ph[i], 4) for i in range(8)], "x0": hex(int(out[0])), "precompute_s": round(pre_s, 3) if pre else None}), flush=True)
+    if pre:
+        L.check(lib.cqb_bases_free(hh.value))

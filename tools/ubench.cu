@@ -89,6 +89,36 @@ __global__ void k_wide_plus_add(Res* out, uint32_t s) {
     if (threadIdx.x == 0) out[blockIdx.x].cyc = t1 - t0;
     if (z == 0x12345) out[blockIdx.x].sink = (uint32_t)z;
 }
+// FP64 pipe: dependent-free DFMA chains
+__global__ void k_dfma(Res* out, uint32_t s) {
+    double a[CH], x = 1.0000001 + s * 1e-12, y = 0.5 + s * 1e-13;
+    for (int k = 0; k < CH; k++) a[k] = threadIdx.x + k;
+    LOOP_BODY(asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(a[k]) : "d"(x), "d"(y)))
+    double z = 0; for (int k = 0; k < CH; k++) z += a[k];
+    if (threadIdx.x == 0) out[blockIdx.x].cyc = t1 - t0;
+    if (z == 12345.678) out[blockIdx.x].sink = 1;
+}
+// DFMA and IMAD.WIDE-row interleaved: do the FP64 pipe and the integer multiplier run concurrently?
+__global__ void k_dfma_plus_row(Res* out, uint32_t s) {
+    double a[CH], x = 1.0000001 + s * 1e-12, y = 0.5 + s * 1e-13;
+    for (int k = 0; k < CH; k++) a[k] = threadIdx.x + k;
+    uint32_t acc[2][9], xx[8]; uint32_t yy = s * 7u + 3u;
+    for (int k = 0; k < 9; k++) { acc[0][k] = threadIdx.x + k; acc[1][k] = threadIdx.x * 3 + k; }
+    for (int k = 0; k < 8; k++) xx[k] = 0x9e3779b9u * (threadIdx.x + k + s);
+    unsigned long long t0 = clock64();
+    for (int it = 0; it < ITERS; it++) {
+        row_mad(acc[0], xx, yy);
+#pragma unroll
+        for (int k = 0; k < CH; k++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(a[k]) : "d"(x), "d"(y));
+        row_mad(acc[1], xx + 1, yy);
+        yy += acc[0][0];
+    }
+    unsigned long long t1 = clock64();
+    double z = 0; for (int k = 0; k < CH; k++) z += a[k];
+    uint32_t zi = 0; for (int k = 0; k < 9; k++) zi ^= acc[0][k] ^ acc[1][k];
+    if (threadIdx.x == 0) out[blockIdx.x].cyc = t1 - t0;
+    if (z == 12345.678 || zi == 0x12345) out[blockIdx.x].sink = 1;
+}
 // full Montgomery multiplications, NCHAIN independent dependent-chains per thread
 template <class P, int NCHAIN>
 __global__ void k_fpmul(Res* out, const Fp<P>* in, Fp<P>* o, int iters) {
@@ -143,6 +173,8 @@ int main(int argc, char** argv) {
         run("row_chain_wideX", [&](Res* d) { k_row_chain<<<blocks, th>>>(d, s); }, (double)ITERS * 8, blocks, th, nsm);
         run("iadd3", [&](Res* d) { k_iadd3<<<blocks, th>>>(d, s); }, per, blocks, th, nsm);
         run("wide_plus_add(pairs)", [&](Res* d) { k_wide_plus_add<<<blocks, th>>>(d, s); }, per, blocks, th, nsm);
+        run("dfma", [&](Res* d) { k_dfma<<<blocks, th>>>(d, s); }, per, blocks, th, nsm);
+        run("dfma(8)+row_wideX(8)", [&](Res* d) { k_dfma_plus_row<<<blocks, th>>>(d, s); }, (double)ITERS * 8, blocks, th, nsm);
     }
     // modmul throughput
     std::vector<uint32_t> hin(8 * 32 * 16);
