@@ -96,14 +96,20 @@ __device__ __forceinline__ Fr load_scalar_canonical(const uint4* scalars, size_t
 __global__ void __launch_bounds__(256) msm_count_kernel(const uint4* __restrict__ scalars, size_t n, MsmShape s,
                                                         uint32_t* __restrict__ hist) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Fr k = load_scalar_canonical(scalars, i);
+    const bool active = i < n;
+    const uint32_t lane = threadIdx.x & 31u;
+    Fr k = active ? load_scalar_canonical(scalars, i) : Fr::zero();
     uint32_t carry = 0;
     for (int w = 0; w < s.nwin; w++) {
         uint32_t d = window_bits(k.l, w, s.c) + carry;
         carry = 0;
         if (d > s.nb) { d = (1u << s.c) - d; carry = 1; }
-        if (d) atomicAdd(&hist[(s.nsets == 1 ? (size_t)0 : (size_t)w * s.stride) + d], 1u);
+        // warp-aggregated histogram update: lanes that hit the same bucket elect one leader that adds their count, so a
+        // narrow top window or heavily repeated scalars (0/1 witnesses) do not serialise on one L2 address
+        uint32_t key = active ? d : 0u;
+        uint32_t peers = __match_any_sync(0xffffffffu, key);
+        if (key && lane == (uint32_t)(__ffs(peers) - 1))
+            atomicAdd(&hist[(s.nsets == 1 ? (size_t)0 : (size_t)w * s.stride) + key], (uint32_t)__popc(peers));
     }
 }
 
@@ -224,23 +230,29 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint4* __restric
                                                           size_t n, MsmShape s, uint32_t* __restrict__ cursor,
                                                           uint32_t* __restrict__ sorted) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Fr k = load_scalar_canonical(scalars, i);
-    uint32_t pid = idx ? __ldg(idx + i) : (uint32_t)i + s.offset;
+    const bool active = i < n;
+    const uint32_t lane = threadIdx.x & 31u;
+    Fr k = active ? load_scalar_canonical(scalars, i) : Fr::zero();
+    uint32_t pid = active ? (idx ? __ldg(idx + i) : (uint32_t)i + s.offset) : 0u;
     uint32_t carry = 0;
     for (int w = 0; w < s.nwin; w++) {
         uint32_t d = window_bits(k.l, w, s.c) + carry;
         carry = 0;
         uint32_t neg = 0;
         if (d > s.nb) { d = (1u << s.c) - d; carry = 1; neg = 1; }
-        if (d) {
-            if (s.nsets == 1) {
-                uint32_t pos = atomicAdd(&cursor[d], 1u);
-                sorted[pos] = ((pid + (uint32_t)w * s.table_n) << 1) | neg;  // row w of the precomputed table
-            } else {
-                uint32_t pos = atomicAdd(&cursor[(size_t)w * s.stride + d], 1u);
-                sorted[(size_t)w * s.list_cap + pos] = (pid << 1) | neg;
-            }
+        // warp-aggregated cursor bump: one atomic per distinct bucket per warp, lanes take consecutive slots
+        uint32_t key = active ? d : 0u;
+        uint32_t peers = __match_any_sync(0xffffffffu, key);
+        uint32_t leader = (uint32_t)(__ffs(peers) - 1);
+        uint32_t rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        uint32_t base = 0;
+        if (key && lane == leader)
+            base = atomicAdd(&cursor[(s.nsets == 1 ? (size_t)0 : (size_t)w * s.stride) + key], (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (key) {
+            uint32_t pos = base + rank;
+            if (s.nsets == 1) sorted[pos] = ((pid + (uint32_t)w * s.table_n) << 1) | neg;  // row w of the precomputed table
+            else sorted[(size_t)w * s.list_cap + pos] = (pid << 1) | neg;
         }
     }
 }
