@@ -2,6 +2,7 @@
 // in the header. No CPU fallback anywhere: without a device every compute call fails with CQB_E_NO_DEVICE.
 #include <stdarg.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 
@@ -71,6 +72,8 @@ static std::map<cqb_bases_t, BaseSet> g_bases;
 static cqb_bases_t g_next_handle = 1;
 static Scratch g_scalars, g_idx, g_io, g_tmp_bases, g_out;
 static Pinned g_out_host;
+static cudaStream_t g_copy_stream = nullptr;  // H2D of part p+1 overlaps the kernels of part p (host-pointer MSM)
+static cudaEvent_t g_copy_ev[4];
 
 static int require_init() {
     if (!g_ctx.inited) return fail(CQB_E_NO_DEVICE, "cqb_init() has not been called or no CUDA device is available (there is no CPU fallback)");
@@ -137,6 +140,11 @@ void cqb_shutdown(void) {
     ntt_release_all();
     msm_release_all();
     gen_release_all();
+    if (g_copy_stream) {
+        for (auto& e : g_copy_ev) cudaEventDestroy(e);
+        cudaStreamDestroy(g_copy_stream);
+        g_copy_stream = nullptr;
+    }
     if (g_ctx.own_stream && g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
     g_ctx.stream = nullptr;
     g_ctx.own_stream = false;
@@ -279,6 +287,36 @@ int cqb_msm_bn254_g1(cqb_bases_t b, size_t offset, const uint64_t* scalars, size
     BaseSet* bs = nullptr;
     CQB_TRY(find_bases(b, offset, n, &bs));
     CQB_TRY(g_scalars.ensure(n * 32 + 32));
+    // Large MSM from PINNED host memory: cut into parts; the H2D copy of part p+1 (copy stream) overlaps the kernels of
+    // part p (compute stream). Pageable memory cannot overlap (the copy is staged synchronously), so it takes the plain path.
+    const int PARTS = 4;
+    bool pinned = false;
+    if (n >= ((size_t)1 << 21)) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, scalars) == cudaSuccess) pinned = (attr.type == cudaMemoryTypeHost);
+        else cudaGetLastError();
+    }
+    if (pinned) {
+        if (!g_copy_stream) {
+            CQB_CUDA(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+            for (auto& e : g_copy_ev) CQB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        size_t per = (n + PARTS - 1) / PARTS;
+        bool use_table = bs->table && n * 8 >= bs->n;
+        CQB_TRY(msm_job_begin(n, per, PARTS, use_table ? bs->table : nullptr, use_table ? bs->n : 0, bs->table_c));
+        for (int p = 0; p < PARTS; p++) {
+            size_t lo = (size_t)p * per, cnt = lo < n ? std::min(per, n - lo) : 0;
+            if (cnt) CQB_CUDA(cudaMemcpyAsync((char*)g_scalars.p + lo * 32, scalars + lo * 4, cnt * 32, cudaMemcpyHostToDevice, g_copy_stream));
+            CQB_CUDA(cudaEventRecord(g_copy_ev[p], g_copy_stream));
+        }
+        for (int p = 0; p < PARTS; p++) {
+            size_t lo = (size_t)p * per, cnt = lo < n ? std::min(per, n - lo) : 0;
+            CQB_CUDA(cudaStreamWaitEvent(g_ctx.stream, g_copy_ev[p], 0));
+            CQB_TRY(msm_job_part(use_table ? bs->table : bs->d, offset + lo, (char*)g_scalars.p + lo * 32, cnt, p));
+        }
+        CQB_TRY(msm_job_finish(g_out.p));
+        return fetch_result(out_xy, is_inf);
+    }
     if (n) CQB_CUDA(cudaMemcpyAsync(g_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, g_ctx.stream));
     CQB_TRY(dispatch_msm(bs, offset, g_scalars.p, nullptr, n));
     return fetch_result(out_xy, is_inf);

@@ -30,6 +30,10 @@ int msm_run(const void* d_bases, size_t offset, const void* d_scalars, const uin
 // single bucket set over a precomputed table (row w = 2^(c w) * bases), table_n points per row
 int msm_run_precomputed(const void* d_table, size_t table_n, int c, size_t offset, const void* d_scalars, const uint32_t* d_idx,
                         size_t n, void* d_out_xy_flag);
+// part-wise interface (same shape for every part; bucket arrays of the parts are summed in msm_job_finish)
+int msm_job_begin(size_t n_total, size_t part_cap, int nparts, const void* d_table, size_t table_n, int c);
+int msm_job_part(const void* d_bases_or_table, size_t offset, const void* d_scalars, size_t n, int part);
+int msm_job_finish(void* d_out);
 int msm_precompute_window_bits(size_t n);
 int msm_windows_for(int c);
 int msm_precompute_table(const void* d_bases, size_t n, int c, void* d_table);

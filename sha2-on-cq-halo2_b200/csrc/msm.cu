@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(128) msm_merge_big_kernel(const uint32_t* __re
 
 // (5) per-set weighted bucket sum, chunked: thread t of set w owns bucket ids [t*CH + 1, (t+1)*CH]
 __global__ void __launch_bounds__(128) msm_reduce_kernel(const uint4* __restrict__ buckets, MsmShape s, uint32_t tpw, uint32_t ch,
-                                                         uint4* __restrict__ partials) {
+                                                         int nparts, size_t part_stride, uint4* __restrict__ partials) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)s.nsets * tpw) return;
     uint32_t w = (uint32_t)(gid / tpw), t = (uint32_t)(gid % tpw);
@@ -390,6 +390,10 @@ __global__ void __launch_bounds__(128) msm_reduce_kernel(const uint4* __restrict
     G1Xyzz running = G1Xyzz::identity(), acc = G1Xyzz::identity();
     for (int j = (int)ch - 1; j >= 0; j--) {  // summation by parts, reference arithmetic.rs:95-99
         G1Xyzz bj = ld_xyzz(b + (size_t)j * 8);
+        for (int p = 1; p < nparts; p++) {  // parts of a pipelined host-pointer MSM
+            G1Xyzz bp = ld_xyzz(b + (size_t)p * part_stride + (size_t)j * 8);
+            g1_add(bj, bp);
+        }
         g1_add(running, bj);
         g1_add(acc, running);
     }
@@ -548,8 +552,8 @@ int msm_precompute_window_bits(size_t n) {
     if (g_forced_c >= 8) return std::min(g_forced_c, 23);
     double best = 1e300;
     int best_c = 12;
-    for (int c = 10; c <= 23; c++) {
-        double cost = msm_windows_for(c) * (double)n * 10.0 + (double)((size_t)1 << (c - 1)) * 40.0;
+    for (int c = 10; c <= 20; c++) {  // beyond 2^19 buckets the scatter's open write streams thrash L2
+        double cost = msm_windows_for(c) * (double)n * 10.0 + (double)((size_t)1 << (c - 1)) * 130.0;  // measured: tools/sweep_msm.py
         if (cost < best) { best = cost; best_c = c; }
     }
     return best_c;
@@ -598,8 +602,11 @@ static MsmShape windowed_shape(size_t n) {
     return s;
 }
 
+// One PART of an MSM: count / scan / scatter / accumulate / merge of `n` scalars into bucket array number `part` (of
+// `nparts`, all with the same shape). A host-pointer MSM is cut into parts so that the H2D copy of part p+1 overlaps the
+// kernels of part p; msm_finish adds the parts' bucket arrays while it reduces them.
 // d_bases: windowed layout -> element 0 of the registered set (pid = offset + i); single-set layout -> the table base.
-static int msm_run_shape(const void* d_bases, const void* d_scalars, const uint32_t* d_idx, size_t n, MsmShape s, void* d_out) {
+static int msm_part(const void* d_bases, const void* d_scalars, const uint32_t* d_idx, size_t n, MsmShape s, int part, int nparts) {
     cudaStream_t st = ctx().stream;
     size_t hist_words = (size_t)s.nsets * s.stride;
     uint32_t ntiles = (s.nb + 1 + SCAN_TILE - 1) / SCAN_TILE;
@@ -610,16 +617,8 @@ static int msm_run_shape(const void* d_bases, const void* d_scalars, const uint3
     uint32_t* tile_sums = cursor + hist_words;
     CQB_TRY(g_sorted.ensure((size_t)s.nsets * s.list_cap * 4));
     size_t nbuckets = (size_t)s.nsets * s.nb;
-    CQB_TRY(g_buckets.ensure(nbuckets * 128));
-    // bucket reduction: tpw threads per set, ch buckets each (both powers of two, ch >= 2)
-    uint32_t tpw = std::min<uint32_t>(s.nb / 2, s.nsets == 1 ? 65536u : 1024u);
-    if (tpw < 1) tpw = 1;
-    uint32_t ch = s.nb / tpw;
-    uint32_t lvl1 = (tpw + 2047) / 2048;  // tree-sum levels over the tpw partials per set
-    CQB_TRY(g_partials.ensure(((size_t)s.nsets * (tpw + lvl1 + 1) + 1) * 128));
-    uint4* partials = g_partials.as<uint4>();
-    uint4* sums1 = partials + (size_t)s.nsets * tpw * 8;
-    uint4* wins = sums1 + (size_t)s.nsets * lvl1 * 8;
+    CQB_TRY(g_buckets.ensure((size_t)nparts * nbuckets * 128));
+    uint4* buckets = g_buckets.as<uint4>() + (size_t)part * nbuckets * 8;
 
     // chunking of the bucket-sorted lists: aim for >= ~150k chunk threads, 16..256 entries each
     size_t entries = (size_t)n * s.nwin;
@@ -635,7 +634,7 @@ static int msm_run_shape(const void* d_bases, const void* d_scalars, const uint3
     uint2* big_list = (uint2*)(big_count + 4);
 
     CQB_CUDA(cudaMemsetAsync(hist, 0, hist_words * 4, st));
-    CQB_CUDA(cudaMemsetAsync(g_buckets.p, 0, nbuckets * 128, st));
+    CQB_CUDA(cudaMemsetAsync(buckets, 0, nbuckets * 128, st));
     CQB_CUDA(cudaMemsetAsync(big_count, 0, 16, st));
     g_ev_count = 0;
     prof_mark(0);
@@ -659,17 +658,34 @@ static int msm_run_shape(const void* d_bases, const void* d_scalars, const uint3
     CQB_LAUNCHED();
     prof_mark(3);
     msm_accumulate_kernel<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>((const uint4*)d_bases, g_sorted.as<uint32_t>(), offs, s, seg_log, cpw,
-                                                                              g_buckets.as<uint4>(), head, tail);
+                                                                              buckets, head, tail);
     CQB_LAUNCHED();
     prof_mark(4);
-    msm_merge_kernel<<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>(offs, s, seg_log, cpw, g_buckets.as<uint4>(), head, tail, big_count,
+    msm_merge_kernel<<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>(offs, s, seg_log, cpw, buckets, head, tail, big_count,
                                                                           big_list, big_cap);
     CQB_LAUNCHED();
-    msm_merge_big_kernel<<<big_cap, 128, 0, st>>>(offs, s, seg_log, cpw, g_buckets.as<uint4>(), head, tail, big_count, big_list);
+    msm_merge_big_kernel<<<big_cap, 128, 0, st>>>(offs, s, seg_log, cpw, buckets, head, tail, big_count, big_list);
     CQB_LAUNCHED();
     prof_mark(5);
+    CQB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// bucket reduction over the sum of the parts' bucket arrays, window combination, affine normalisation
+static int msm_finish(MsmShape s, int nparts, void* d_out) {
+    cudaStream_t st = ctx().stream;
+    size_t nbuckets = (size_t)s.nsets * s.nb;
+    // tpw threads per set, ch buckets each (both powers of two, ch >= 2)
+    uint32_t tpw = std::min<uint32_t>(s.nb / 2, s.nsets == 1 ? 65536u : 1024u);
+    if (tpw < 1) tpw = 1;
+    uint32_t ch = s.nb / tpw;
+    uint32_t lvl1 = (tpw + 2047) / 2048;  // tree-sum levels over the tpw partials per set
+    CQB_TRY(g_partials.ensure(((size_t)s.nsets * (tpw + lvl1 + 1) + 1) * 128));
+    uint4* partials = g_partials.as<uint4>();
+    uint4* sums1 = partials + (size_t)s.nsets * tpw * 8;
+    uint4* wins = sums1 + (size_t)s.nsets * lvl1 * 8;
     size_t nred = (size_t)s.nsets * tpw;
-    msm_reduce_kernel<<<(unsigned)((nred + 127) / 128), 128, 0, st>>>(g_buckets.as<uint4>(), s, tpw, ch, partials);
+    msm_reduce_kernel<<<(unsigned)((nred + 127) / 128), 128, 0, st>>>(g_buckets.as<uint4>(), s, tpw, ch, nparts, nbuckets * 8, partials);
     CQB_LAUNCHED();
     prof_mark(6);
     if (lvl1 > 1) {
@@ -687,6 +703,11 @@ static int msm_run_shape(const void* d_bases, const void* d_scalars, const uint3
     prof_mark(8);
     CQB_CUDA(cudaGetLastError());
     return 0;
+}
+
+static int msm_run_shape(const void* d_bases, const void* d_scalars, const uint32_t* d_idx, size_t n, MsmShape s, void* d_out) {
+    CQB_TRY(msm_part(d_bases, d_scalars, d_idx, n, s, 0, 1));
+    return msm_finish(s, 1, d_out);
 }
 
 static int msm_empty(void* d_out) {
@@ -721,6 +742,38 @@ int msm_run_precomputed(const void* d_table, size_t table_n, int c, size_t offse
         return fail(CQB_E_BAD_SIZE, "precomputed MSM: %zu x %d entries exceed the 32-bit index range", n, s.nwin);
     return msm_run_shape(d_table, d_scalars, d_idx, n, s, d_out);
 }
+
+// ---- part-wise interface used by the host-pointer entry points to overlap H2D with compute ---------------------------
+static MsmShape g_job_shape;
+static int g_job_parts = 0;
+int msm_job_begin(size_t n_total, size_t part_cap, int nparts, const void* d_table, size_t table_n, int c) {
+    (void)d_table;
+    if (table_n) {
+        MsmShape s;
+        s.c = c;
+        s.nwin = msm_windows_for(c);
+        s.nsets = 1;
+        s.nb = 1u << (c - 1);
+        s.stride = s.nb + 2;
+        s.table_n = (uint32_t)table_n;
+        s.offset = 0;
+        s.list_cap = part_cap * (size_t)s.nwin;
+        if (s.list_cap >= ((size_t)1 << 32) || (size_t)s.nwin * table_n >= ((size_t)1 << 31))
+            return fail(CQB_E_BAD_SIZE, "precomputed MSM: %zu x %d entries exceed the 32-bit index range", part_cap, s.nwin);
+        g_job_shape = s;
+    } else {
+        g_job_shape = windowed_shape(n_total);
+        g_job_shape.list_cap = part_cap;
+    }
+    g_job_parts = nparts;
+    return 0;
+}
+int msm_job_part(const void* d_bases_or_table, size_t offset, const void* d_scalars, size_t n, int part) {
+    MsmShape s = g_job_shape;
+    s.offset = (uint32_t)offset;
+    return msm_part(d_bases_or_table, d_scalars, nullptr, n, s, part, g_job_parts);
+}
+int msm_job_finish(void* d_out) { return msm_finish(g_job_shape, g_job_parts, d_out); }
 
 int g1_sum_affine_run(const void* d_points, size_t n, void* d_out) {
     g1_sum_affine_kernel<<<1, 128, 0, ctx().stream>>>((const uint4*)d_points, n, (uint4*)d_out);

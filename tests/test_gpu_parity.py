@@ -280,3 +280,42 @@ def test_precomputed_table_msm_parity(cq, oracle, n, c):
     _, exp_k = oracle.best_multiexp(sk, bases, 8)
     assert np.array_equal(dev.msm(sk).to_affine(), exp_k)
     dev.free()
+
+
+@pytest.mark.parametrize("precompute", [False, True])
+def test_pipelined_host_msm_matches_device_path(cq, oracle, precompute):
+    """host-pointer MSM from pinned memory is cut into 4 parts (H2D of part p+1 overlaps the kernels of part p): the result
+    must equal the device-resident single-shot path and the oracle's result on a sample-sized check of linearity"""
+    lib = cq._lib.lib()
+    n = (1 << 21) + 12345
+    d_b, d_s, h_pin = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    cq._lib.check(lib.cqb_dev_alloc(n * 64, ctypes.byref(d_b)))
+    cq._lib.check(lib.cqb_dev_alloc(n * 32, ctypes.byref(d_s)))
+    cq._lib.check(lib.cqb_host_alloc_pinned(n * 32, ctypes.byref(h_pin)))
+    cq._lib.check(lib.cqb_synth_bases_dev(0xABCD, 0, n, d_b))
+    cq._lib.check(lib.cqb_synth_scalars_dev(0xABCE, 0, n, d_s))
+    cq._lib.check(lib.cqb_memcpy_d2h(h_pin, d_s, n * 32))
+    h = ctypes.c_uint64(0)
+    cq._lib.check(lib.cqb_bases_register_device(d_b, n, ctypes.byref(h)))
+    if precompute:
+        cq._lib.check(lib.cqb_bases_precompute(h.value, 0))
+    out_dev, out_pin, out_page = (np.zeros(8, np.uint64) for _ in range(3))
+    inf = ctypes.c_int(0)
+    cq._lib.check(lib.cqb_msm_bn254_g1_dev(h.value, 0, d_s, n, cq._lib.p64(out_dev), ctypes.byref(inf)))
+    cq._lib.check(lib.cqb_msm_bn254_g1(h.value, 0, ctypes.cast(h_pin, cq._lib.u64p), n, cq._lib.p64(out_pin), ctypes.byref(inf)))
+    pageable = np.ctypeslib.as_array(ctypes.cast(h_pin, cq._lib.u64p), shape=(n * 4,)).copy()
+    cq._lib.check(lib.cqb_msm_bn254_g1(h.value, 0, cq._lib.p64(pageable), n, cq._lib.p64(out_page), ctypes.byref(inf)))
+    assert np.array_equal(out_dev, out_pin) and np.array_equal(out_dev, out_page) and out_dev.any()
+    # anchor to the oracle: MSM over the first 2^14 points through the same handle
+    m = 1 << 14
+    sc = pageable.reshape(n, 4)[:m].copy()
+    bs = np.zeros((m, 8), np.uint64)
+    cq._lib.check(lib.cqb_memcpy_d2h(bs.ctypes.data_as(ctypes.c_void_p), d_b, m * 64))
+    _, exp = oracle.best_multiexp(sc, bs, 8)
+    out_s = np.zeros(8, np.uint64)
+    cq._lib.check(lib.cqb_msm_bn254_g1(h.value, 0, cq._lib.p64(sc), m, cq._lib.p64(out_s), ctypes.byref(inf)))
+    assert np.array_equal(out_s, exp)
+    cq._lib.check(lib.cqb_bases_free(h.value))
+    cq._lib.check(lib.cqb_host_free_pinned(h_pin))
+    cq._lib.check(lib.cqb_dev_free(d_b))
+    cq._lib.check(lib.cqb_dev_free(d_s))
