@@ -138,6 +138,8 @@ def main():
     ap.add_argument("--ntt-log-n", type=int, default=24)
     ap.add_argument("--no-ntt", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-prove", action="store_true")
+    ap.add_argument("--prove-k", type=lambda v: [int(x) for x in v.split(",")], default=[16, 20])
     ap.add_argument("--ref-max-log", type=int, default=22)
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--no-precompute", action="store_true", help="windowed layout on the plain bases (no per-SRS table)")
@@ -299,6 +301,16 @@ def main():
                        "roofline_int": {"bound": "int", "achieved": int_t, "peak": INT_PEAK_TMAD32, "unit": "TMAD32/s",
                                         "frac": int_t / INT_PEAK_TMAD32}}
         del a_t
+
+    # ---- "SHA2-CQ prove ms": the synthetic CQ-prover-shaped op list of SURVEY.md §8(d) (no SHA circuit exists in the
+    #      reference, F1), host-pointer C-ABI calls, N=1 only -------------------------------------------------------
+    if world == 1 and not args.no_prove:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import prove_workload
+
+        line["prove_ms"] = [prove_workload.run(cqb200, k, reps=2) for k in args.prove_k]
+        line["prove_ms_note"] = ("synthetic CQ-prover-shaped MSM/NTT op list (8 advice columns, one CQ lookup, table 2^16), host "
+                                 "buffers; witness synthesis / evaluate_h / transcript are CPU work outside the path and excluded")
 
     # ---- CPU baseline (rank 0, N=1): the oracle's restatement of best_multiexp on a bounded sample -----------------
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -1,0 +1,133 @@
+"""tools/prove_workload.py — the synthetic CQ-prover-shaped workload of SURVEY.md §8(d) ("End-to-end prove ms").
+
+No SHA-256 circuit exists in the reference, so "prove ms" is reported on the op list of §3.1 for a circuit with
+A advice columns and one CQ static lookup over a table of N rows, at n = 2^k rows, through the HOST-pointer C ABI (the
+calls the Rust prover would make): per proof
+    A x commit_lagrange(n)                      plonk/prover.rs:356-360
+    f commit_lagrange, m sparse MSM             static_lookup/prover.rs:165, 167-170
+    A_cm, Q_A, A_0 sparse MSMs (|supp| = min(n, N))                    :245-257
+    B iNTT(n), P = MSM(n-1) over the bound SRS slice, B_0 = commit(n)  :271, 299, 310
+    f iNTT(n)                                                          :326-332
+    random-poly commit(n)                        vanishing/prover.rs:58
+    A x lagrange_to_coeff(n), (A + 2) x coeff_to_extended(n -> 2n)     plonk/prover.rs:587-603, evaluation.rs:317-334, 535-536
+    quotient: divide_by_vanishing + extended_to_coeff(2n), 2 x commit(n)   vanishing/prover.rs:84-107
+    1 GWC witness commit(n-1)                    gwc/prover.rs:80-86
+Witness synthesis, evaluate_h's row program, transcript hashing and challenges are CPU work outside the hot path and are
+NOT included. Returns milliseconds per proof (wall clock around the synchronous C-ABI calls).
+"""
+import ctypes
+import time
+
+import numpy as np
+
+
+def run(cq, k, A=8, table_log=16, reps=2, seed=0x70726F76):
+    L = cq._lib
+    lib = L.lib()
+    n = 1 << k
+    N = 1 << table_log
+    Nt = max(N, n)
+    dom = cq.EvaluationDomain(3, k)
+    en = 1 << dom.extended_k
+
+    def dev_bases(count, sd):
+        d = ctypes.c_void_p()
+        L.check(lib.cqb_dev_alloc(count * 64, ctypes.byref(d)))
+        L.check(lib.cqb_synth_bases_dev(sd, 0, count, d))
+        h = ctypes.c_uint64(0)
+        L.check(lib.cqb_bases_register_device(d, count, ctypes.byref(h)))
+        if count >= (1 << 16):
+            L.check(lib.cqb_bases_precompute(h.value, 0))
+        return d, h.value
+
+    # SRS stand-ins (any distinct curve points give the same cost): g, g_lagrange, table g1 / lagrange / opening-at-0 / qs
+    keep = [dev_bases(n, seed + i) for i in range(2)]
+    (_, g), (_, g_lag) = keep
+    tabs = [dev_bases(Nt, seed + 10 + i) for i in range(4)]
+    t_g1, t_lag, t_op0, t_qs = (h for _, h in tabs)
+
+    def pinned_scalars(count, sd):
+        hp = ctypes.c_void_p()
+        L.check(lib.cqb_host_alloc_pinned(count * 32, ctypes.byref(hp)))
+        d = ctypes.c_void_p()
+        L.check(lib.cqb_dev_alloc(count * 32, ctypes.byref(d)))
+        L.check(lib.cqb_synth_scalars_dev(sd, 0, count, d))
+        L.check(lib.cqb_memcpy_d2h(hp, d, count * 32))
+        L.check(lib.cqb_dev_free(d))
+        return hp
+
+    cols = [pinned_scalars(n, seed + 100 + i) for i in range(A + 4)]  # advice, f, bs, random, h pieces reuse
+    ext = pinned_scalars(en, seed + 200)
+    ext_out = pinned_scalars(en, seed + 201)
+    supp = min(n, N)
+    idx = np.sort(np.random.default_rng(1).choice(Nt, supp, replace=False)).astype(np.uint32)
+    sp = pinned_scalars(supp, seed + 300)
+    out = np.zeros(8, np.uint64)
+    inf = ctypes.c_int(0)
+    u64 = L.u64p
+
+    def msm(h, ptr, count, offset=0):
+        L.check(lib.cqb_msm_bn254_g1(h, offset, ctypes.cast(ptr, u64), count, L.p64(out), ctypes.byref(inf)))
+
+    def sparse(h):
+        L.check(lib.cqb_msm_bn254_g1_sparse(h, idx.ctypes.data_as(L.u32p), ctypes.cast(sp, u64), supp, L.p64(out), ctypes.byref(inf)))
+
+    def intt(ptr):
+        L.check(lib.cqb_intt_bn254_fr(ctypes.cast(ptr, u64), L.p64(dom.omega_inv), L.p64(dom.ifft_divisor), k))
+
+    def coset(ptr):
+        L.check(lib.cqb_coset_ntt_bn254_fr(ctypes.cast(ptr, u64), n, ctypes.cast(ext_out, u64), L.p64(dom.extended_omega),
+                                           dom.extended_k, L.p64(dom.g_coset), L.p64(dom.g_coset_inv)))
+
+    def proof():
+        for a in range(A):
+            msm(g_lag, cols[a], n)
+        msm(g_lag, cols[A], n)          # f
+        sparse(t_lag)                   # m
+        sparse(t_lag); sparse(t_qs); sparse(t_op0)   # A, Q_A, A_0
+        intt(cols[A + 1])               # B
+        msm(t_g1, cols[A + 1], n - 1, offset=Nt - (n - 1))   # P over the degree-bound slice
+        msm(g, cols[A + 1], n)          # B_0
+        intt(cols[A])                   # f -> coeff
+        msm(g, cols[A + 2], n)          # random poly
+        for a in range(A):
+            intt(cols[a])
+        for a in range(A):
+            coset(cols[a])
+        coset(cols[A]); coset(cols[A + 1])
+        L.check(lib.cqb_coset_intt_bn254_fr(ctypes.cast(ext, u64), dom.extended_k, L.p64(dom.extended_omega_inv),
+                                            L.p64(dom.extended_ifft_divisor), L.p64(dom.g_coset), L.p64(dom.g_coset_inv),
+                                            L.p64(dom.t_evaluations), dom.t_evaluations.shape[0]))
+        msm(g, cols[A + 3], n); msm(g, cols[A + 2], n)   # two h pieces
+        msm(g, cols[A + 3], n - 1)      # GWC witness
+
+    proof()  # warm-up (twiddle tables, scratch growth)
+    L.check(lib.cqb_sync())
+    l0 = lib.cqb_launch_count()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        proof()
+    L.check(lib.cqb_sync())
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    launches = (lib.cqb_launch_count() - l0) // reps
+    for p in cols + [ext, ext_out, sp]:
+        L.check(lib.cqb_host_free_pinned(p))
+    for d, h in keep + tabs:
+        L.check(lib.cqb_bases_free(h))
+        L.check(lib.cqb_dev_free(d))
+    n_msm = A + 1 + 4 + 2 + 1 + 2 + 1
+    return {"k": k, "advice_columns": A, "table_rows": N, "ms_per_proof": ms, "gpu_launches_per_proof": int(launches),
+            "ops": {"dense_msm": n_msm - 4, "sparse_msm": 4, "intt_n": A + 2, "coset_ntt_2n": A + 2, "coset_intt_2n": 1}}
+
+
+if __name__ == "__main__":
+    import json
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import cqb200
+
+    cqb200._lib.init(0)
+    for k in [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["16", "20"])]:
+        print(json.dumps(run(cqb200, k)), flush=True)
