@@ -135,6 +135,18 @@ CQB_HD G1Affine g1_to_affine(const G1Xyzz& p) {
     return a;
 }
 
+// same result through the low-latency binary inversion: for kernels where a single thread normalises a single point
+CQB_HD G1Affine g1_to_affine_lowlat(const G1Xyzz& p) {
+    G1Affine a;
+    if (p.is_identity()) { a.x = Fq::zero(); a.y = Fq::zero(); return a; }
+    Fq inv = fp_inv_binary<FqP>(FQM(p.zz, p.zzz));
+    Fq zz_inv = FQM(inv, p.zzz);
+    Fq zzz_inv = FQM(inv, p.zz);
+    a.x = FQM(p.x, zz_inv);
+    a.y = FQM(p.y, zzz_inv);
+    return a;
+}
+
 #undef FQM
 #undef FQS
 #undef FQA

@@ -365,6 +365,72 @@ CQB_HD Fp<P> fp_inv(const Fp<P>& a) {  // returns 0 for 0, like invert().unwrap_
     return fp_pow<P>(a, e);
 }
 
+// Low-latency inversion for the places where ONE thread inverts ONE element on the critical path (the affine
+// normalisation at the end of an MSM): binary extended Euclid on the 8-limb integers — ~20k simple ALU instructions instead
+// of ~380 dependent Montgomery multiplications. Input/output in Montgomery form: for x = aR it returns a^-1 R
+// (= x^-1 * R^2, obtained as mont_mul(x^-1, R^3)). Returns 0 for 0. Same value as fp_inv (the inverse is unique).
+template <class P>
+CQB_HD Fp<P> fp_inv_binary(const Fp<P>& a) {
+    if (a.is_zero()) return a;
+    uint32_t u[8], v[8], x1[8], x2[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { u[i] = a.l[i]; v[i] = P::mod(i); x1[i] = 0; x2[i] = 0; }
+    x1[0] = 1;
+    auto is_one = [](const uint32_t* w) {
+        uint32_t o = w[0] ^ 1u;
+#pragma unroll
+        for (int i = 1; i < 8; i++) o |= w[i];
+        return o == 0;
+    };
+    auto shr1 = [](uint32_t* w) {
+#pragma unroll
+        for (int i = 0; i < 7; i++) w[i] = (w[i] >> 1) | (w[i + 1] << 31);
+        w[7] >>= 1;
+    };
+    auto half_mod = [&](uint32_t* x) {  // x <- x/2 mod p  (x < p < 2^254, so x + p < 2^255 cannot overflow)
+        if (x[0] & 1u) {
+            uint64_t c = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { c += (uint64_t)x[i] + P::mod(i); x[i] = (uint32_t)c; c >>= 32; }
+        }
+        shr1(x);
+    };
+    auto geq = [](const uint32_t* a_, const uint32_t* b_) {
+        for (int i = 7; i >= 0; i--) {
+            if (a_[i] != b_[i]) return a_[i] > b_[i];
+        }
+        return true;
+    };
+    auto sub = [](uint32_t* a_, const uint32_t* b_) {  // a -= b, returns borrow
+        uint64_t br = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint64_t d = (uint64_t)a_[i] - b_[i] - br;
+            a_[i] = (uint32_t)d;
+            br = (d >> 32) & 1u;
+        }
+        return (uint32_t)br;
+    };
+    auto sub_mod = [&](uint32_t* a_, const uint32_t* b_) {  // a <- a - b mod p
+        if (sub(a_, b_)) {
+            uint64_t c = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { c += (uint64_t)a_[i] + P::mod(i); a_[i] = (uint32_t)c; c >>= 32; }
+        }
+    };
+    while (!is_one(u) && !is_one(v)) {
+        while (!(u[0] & 1u)) { shr1(u); half_mod(x1); }
+        while (!(v[0] & 1u)) { shr1(v); half_mod(x2); }
+        if (geq(u, v)) { sub(u, v); sub_mod(x1, x2); }
+        else { sub(v, u); sub_mod(x2, x1); }
+    }
+    Fp<P> r;
+    const bool from_u = is_one(u);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = from_u ? x1[i] : x2[i];
+    return fp_mul<P>(r, Fp<P>::r3());
+}
+
 typedef Fp<FrP> Fr;
 typedef Fp<FqP> Fq;
 

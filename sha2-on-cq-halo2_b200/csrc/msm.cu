@@ -435,7 +435,7 @@ __global__ void msm_final_kernel(const uint4* __restrict__ wins, MsmShape s, uin
         G1Xyzz ww = ld_xyzz(wins + (size_t)w * 8);
         g1_add(acc, ww);
     }
-    G1Affine a = g1_to_affine(acc);
+    G1Affine a = g1_to_affine_lowlat(acc);
     st_fq(out, a.x);
     st_fq(out + 2, a.y);
     uint32_t inf = acc.is_identity() ? 1u : 0u;
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(128) g1_sum_affine_kernel(const uint4* __restr
     }
     G1Xyzz r = block_sum_128(acc, sm);
     if (threadIdx.x == 0) {
-        G1Affine a = g1_to_affine(r);
+        G1Affine a = g1_to_affine_lowlat(r);
         st_fq(out, a.x);
         st_fq(out + 2, a.y);
         out[4] = make_uint4(r.is_identity() ? 1u : 0u, 0, 0, 0);

@@ -46,8 +46,12 @@ def test_fp_limb_algorithm(fp_bin):
             lines.append(f"{name} mul {a:064x} {b:064x}")
             exp.append(a * b * rinv % p)
         for a in vals[:24]:
-            lines.append(f"{name} inv {a:064x} {0:064x}")
-            exp.append(0 if a == 0 else pow(a * rinv % p, -1, p) * P.MONT % p)
+            for op in ("inv", "invb"):  # Fermat and binary-Euclid inversions agree (the inverse is unique)
+                lines.append(f"{name} {op} {a:064x} {0:064x}")
+                exp.append(0 if a == 0 else pow(a * rinv % p, -1, p) * P.MONT % p)
+        for a in vals[24:120]:
+            lines.append(f"{name} invb {a:064x} {0:064x}")
+            exp.append(pow(a * rinv % p, -1, p) * P.MONT % p)
     out = subprocess.run([fp_bin], input="\n".join(lines), capture_output=True, text=True, check=True).stdout.split()
     assert len(out) == len(exp)
     bad = [(l, o) for l, o, e in zip(lines, out, exp) if int(o, 16) != e]

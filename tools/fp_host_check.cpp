@@ -25,6 +25,7 @@ template <class P> static void run(const std::string& op, const std::string& sa,
     else if (op == "neg") put(fp_neg<P>(a));
     else if (op == "dbl") put(fp_dbl<P>(a));
     else if (op == "inv") put(fp_inv<P>(a));
+    else if (op == "invb") put(fp_inv_binary<P>(a));
     else if (op == "frommont") put(fp_from_mont<P>(a));
     else if (op == "tomont") put(fp_to_mont<P>(a));
     else printf("?\n");
