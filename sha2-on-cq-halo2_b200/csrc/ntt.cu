@@ -8,7 +8,8 @@
 //   * decimation in time over a device-resident twiddle table W[i] = omega^i, i < n/2 (the reference's `twiddles`
 //     vector, arithmetic.rs:194-200, built in parallel instead of by a serial scan, and cached per (omega, log_n));
 //   * ceil(log_n / 8) passes over HBM; each pass runs up to 8 butterfly stages on a 1024-element (32 KB) tile held in
-//     shared memory as two uint4 planes (conflict-free 128-bit LDS/STS), 512 threads = one butterfly each per stage;
+//     shared memory as two uint4 planes (conflict-free 128-bit LDS/STS); 256 threads, each carrying 4 elements through
+//     2 stages in registers (radix-4 steps: half the shared-memory round trips and barriers, 2 independent modmuls);
 //   * the bit-reversal permutation (arithmetic.rs:186-191) is fused into the first pass's gather — tiles are chosen so
 //     that the gather reads 128 B contiguous runs; later passes read/write (rows x 2^q contiguous elements) tiles;
 //   * the element-wise scalings that surround best_fft in the reference are fused into the first pass's load (coset
@@ -59,12 +60,33 @@ __device__ __forceinline__ void st_fr(uint4* p, size_t i, const Fr& v) {
     p[2 * i + 1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 
-__global__ void __launch_bounds__(512) ntt_pass_kernel(const __grid_constant__ NttPassArgs a) {
+__device__ __forceinline__ Fr sm_ld(const uint4* slo, const uint4* shi, uint32_t e) {
+    uint4 l = slo[e], h = shi[e];
+    Fr v;
+    v.l[0] = l.x; v.l[1] = l.y; v.l[2] = l.z; v.l[3] = l.w; v.l[4] = h.x; v.l[5] = h.y; v.l[6] = h.z; v.l[7] = h.w;
+    return v;
+}
+__device__ __forceinline__ void sm_st(uint4* slo, uint4* shi, uint32_t e, const Fr& v) {
+    slo[e] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    shi[e] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+// (x, y) <- (x + w y, x - w y); w = W[twi], twi == 0 means w = 1 (the reference skips that multiply too, :213-219)
+__device__ __forceinline__ void butterfly(Fr& x, Fr& y, const uint4* tw, uint32_t twi) {
+    if (twi != 0) y = fp_mul<FrP>(y, ldg_fr(tw, twi));
+    Fr u = fp_add<FrP>(x, y);
+    y = fp_sub<FrP>(x, y);
+    x = u;
+}
+
+// One pass = up to 8 butterfly stages on a tile of T = 2^(r+q) elements in shared memory. T/4 threads; each thread
+// carries FOUR elements through TWO stages in registers (a radix-4 step = 2 + 2 butterflies), so a pass needs r/2
+// shared-memory round trips and barriers instead of r, and every thread has two independent multiplications in flight.
+__global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const __grid_constant__ NttPassArgs a) {
     extern __shared__ uint4 sm[];
-    const int T = 1 << (a.r + a.q);
+    const uint32_t T = 1u << (a.r + a.q);
     uint4* slo = sm;
     uint4* shi = sm + T;
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
     const uint32_t blk = blockIdx.x;
     const uint32_t qmask = (1u << a.q) - 1u;
     // bits of the global index owned by this CTA
@@ -73,10 +95,8 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const __grid_constant__ N
         lo = blk & ((1u << (a.s0 - a.q)) - 1u);
         hi = blk >> (a.s0 - a.q);
     }
-    // ---- load (2 elements per thread) -------------------------------------------------------------------------
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        uint32_t e = tid + k * (T >> 1);
+    // ---- load ----------------------------------------------------------------------------------------------------
+    for (uint32_t e = tid; e < T; e += nthr) {
         uint32_t row = e >> a.q, col = e & qmask;
         Fr v;
         if (a.first) {
@@ -98,50 +118,57 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const __grid_constant__ N
             size_t i = (size_t)col | ((size_t)lo << a.q) | ((size_t)row << a.s0) | ((size_t)hi << (a.s0 + a.r));
             v = ld_fr(a.src, i);
         }
-        slo[e] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
-        shi[e] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+        sm_st(slo, shi, e, v);
     }
     __syncthreads();
-    // ---- butterflies: stage s = s0 + t pairs rows r0, r0 + 2^t -----------------------------------------------------
-    const uint32_t rb = tid >> a.q, c = tid & qmask;
-    const uint32_t jlow = a.first ? 0u : (c | (lo << a.q));  // low bits of (i mod 2^s) that do not depend on the row
-    for (int t = 0; t < a.r; t++) {
-        uint32_t r0 = ((rb >> t) << (t + 1)) | (rb & ((1u << t) - 1u));
-        uint32_t r1 = r0 | (1u << t);
-        uint32_t e0 = (r0 << a.q) | c, e1 = (r1 << a.q) | c;
-        int s = a.s0 + t;
-        uint32_t j = jlow | ((r0 & ((1u << t) - 1u)) << a.s0);  // i mod 2^s
-        uint32_t twi = j << (a.L - 1 - s);                        // reference: twiddles[(i) * twiddle_chunk]
-        uint4 xl = slo[e0], xh = shi[e0], yl = slo[e1], yh = shi[e1];
-        Fr x, y;
-        x.l[0] = xl.x; x.l[1] = xl.y; x.l[2] = xl.z; x.l[3] = xl.w; x.l[4] = xh.x; x.l[5] = xh.y; x.l[6] = xh.z; x.l[7] = xh.w;
-        y.l[0] = yl.x; y.l[1] = yl.y; y.l[2] = yl.z; y.l[3] = yl.w; y.l[4] = yh.x; y.l[5] = yh.y; y.l[6] = yh.z; y.l[7] = yh.w;
-        if (twi != 0) y = fp_mul<FrP>(y, ldg_fr(a.tw, twi));  // twiddle one: the reference skips the multiply too (:213-219)
-        Fr u = fp_add<FrP>(x, y), w = fp_sub<FrP>(x, y);
-        slo[e0] = make_uint4(u.l[0], u.l[1], u.l[2], u.l[3]);
-        shi[e0] = make_uint4(u.l[4], u.l[5], u.l[6], u.l[7]);
-        slo[e1] = make_uint4(w.l[0], w.l[1], w.l[2], w.l[3]);
-        shi[e1] = make_uint4(w.l[4], w.l[5], w.l[6], w.l[7]);
+    // ---- butterflies: stage s = s0 + t pairs rows that differ in bit t ----------------------------------------------
+    // twiddle index of a butterfly whose upper row is `row` at stage t: (i mod 2^s) << (L-1-s), s = s0 + t
+    //   (reference arithmetic.rs:263-272: twiddles[(i + 1) * twiddle_chunk] over the chunk-local index)
+    int t = 0;
+    for (; t + 1 < a.r; t += 2) {
+        for (uint32_t qd = tid; qd < (T >> 2); qd += nthr) {
+            const uint32_t c = qd & qmask, rq = qd >> a.q;
+            const uint32_t jlow = a.first ? 0u : (c | (lo << a.q));
+            const uint32_t r00 = ((rq >> t) << (t + 2)) | (rq & ((1u << t) - 1u));
+            const uint32_t r01 = r00 | (1u << t), r10 = r00 | (2u << t), r11 = r00 | (3u << t);
+            const uint32_t e00 = (r00 << a.q) | c, e01 = (r01 << a.q) | c, e10 = (r10 << a.q) | c, e11 = (r11 << a.q) | c;
+            Fr x00 = sm_ld(slo, shi, e00), x01 = sm_ld(slo, shi, e01), x10 = sm_ld(slo, shi, e10), x11 = sm_ld(slo, shi, e11);
+            const uint32_t low_t = r00 & ((1u << t) - 1u);
+            const int s = a.s0 + t;
+            const uint32_t tw0 = (jlow | (low_t << a.s0)) << (a.L - 1 - s);              // stage t (same for both pairs)
+            butterfly(x00, x01, a.tw, tw0);
+            butterfly(x10, x11, a.tw, tw0);
+            const uint32_t tw1a = (jlow | (low_t << a.s0)) << (a.L - 2 - s);              // stage t+1, rows r00 / r10
+            const uint32_t tw1b = (jlow | ((low_t | (1u << t)) << a.s0)) << (a.L - 2 - s);  // stage t+1, rows r01 / r11
+            butterfly(x00, x10, a.tw, tw1a);
+            butterfly(x01, x11, a.tw, tw1b);
+            sm_st(slo, shi, e00, x00); sm_st(slo, shi, e01, x01); sm_st(slo, shi, e10, x10); sm_st(slo, shi, e11, x11);
+        }
         __syncthreads();
     }
-    // ---- store -------------------------------------------------------------------------------------------------
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        uint32_t e = tid + k * (T >> 1);
+    if (t < a.r) {  // odd number of stages: one plain radix-2 stage
+        for (uint32_t b = tid; b < (T >> 1); b += nthr) {
+            const uint32_t c = b & qmask, rb = b >> a.q;
+            const uint32_t jlow = a.first ? 0u : (c | (lo << a.q));
+            const uint32_t r0 = ((rb >> t) << (t + 1)) | (rb & ((1u << t) - 1u));
+            const uint32_t r1 = r0 | (1u << t);
+            const uint32_t e0 = (r0 << a.q) | c, e1 = (r1 << a.q) | c;
+            Fr x = sm_ld(slo, shi, e0), y = sm_ld(slo, shi, e1);
+            const int s = a.s0 + t;
+            butterfly(x, y, a.tw, (jlow | ((r0 & ((1u << t) - 1u)) << a.s0)) << (a.L - 1 - s));
+            sm_st(slo, shi, e0, x); sm_st(slo, shi, e1, y);
+        }
+        __syncthreads();
+    }
+    // ---- store ---------------------------------------------------------------------------------------------------
+    for (uint32_t e = tid; e < T; e += nthr) {
         uint32_t row = e >> a.q, col = e & qmask;
         size_t i;
         if (a.first) i = (size_t)row | ((size_t)(blk | (col << (a.L - a.r - a.q))) << a.r);
         else i = (size_t)col | ((size_t)lo << a.q) | ((size_t)row << a.s0) | ((size_t)hi << (a.s0 + a.r));
-        uint4 vl = slo[e], vh = shi[e];
-        if (a.post_mode) {
-            Fr v;
-            v.l[0] = vl.x; v.l[1] = vl.y; v.l[2] = vl.z; v.l[3] = vl.w; v.l[4] = vh.x; v.l[5] = vh.y; v.l[6] = vh.z; v.l[7] = vh.w;
-            v = fp_mul<FrP>(v, a.post[a.post_mode == 1 ? 0 : (int)(i % 3)]);
-            vl = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
-            vh = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
-        }
-        a.dst[2 * i] = vl;
-        a.dst[2 * i + 1] = vh;
+        Fr v = sm_ld(slo, shi, e);
+        if (a.post_mode) v = fp_mul<FrP>(v, a.post[a.post_mode == 1 ? 0 : (int)(i % 3)]);
+        st_fr(a.dst, i, v);
     }
 }
 
@@ -301,7 +328,7 @@ int ntt_run(const void* d_src, void* d_dst, uint32_t L, const uint64_t omega[4],
         for (int i = 0; i < 3; i++) a.post[i] = f.post[i];
         int T = 1 << (a.r + a.q);
         unsigned grid = (unsigned)(n >> (a.r + a.q));
-        int threads = T >> 1;
+        int threads = T >> 2;
         if (threads < 1) threads = 1;
         ntt_pass_kernel<<<grid, threads, (size_t)T * 32, st>>>(a);
         CQB_LAUNCHED();
