@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libcqb200.so")
+SO_PATH = os.environ.get("CQB200_LIB") or os.path.join(_HERE, "libcqb200.so")  # env override: A/B experiments only
 
 u64p = ctypes.POINTER(ctypes.c_uint64)
 u32p = ctypes.POINTER(ctypes.c_uint32)

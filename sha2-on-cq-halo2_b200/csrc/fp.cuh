@@ -282,7 +282,12 @@ CQB_HD void mod_limbs(uint32_t* m) {
 
 // reference derive/field.rs:502-562: result = a*b*2^-256 mod p, fully reduced
 template <class P>
+CQB_HD Fp<P> fp_mul_kar(const Fp<P>& a, const Fp<P>& b);
+template <class P>
 CQB_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+#ifdef CQB_KARATSUBA
+    return fp_mul_kar<P>(a, b);
+#else
     uint32_t ev[9], od[9], p[8];
     mod_limbs<P>(p);
     uint32_t m;
@@ -321,6 +326,153 @@ CQB_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
     r.l[7] = addc(ev[7], od[8]);
     fp_reduce_once<P>(r.l);
     return r;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant: separated product + reduction with one level of Karatsuba on the 8x8-limb product (3 x 16 = 48 wide products
+// instead of 64; the reduction keeps 64 + 8). The multiplier ("fmaheavy") pipe is the bottleneck of every kernel here
+// while the ALU pipe idles at ~30 %, so trading 16 IMAD.WIDE for ~100 IADD3 is a net win if ptxas keeps the chains fused.
+// Same canonical result as fp_mul.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int N>
+CQB_HD void rowN_mul(uint32_t* acc, const uint32_t* x, uint32_t y) {
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+        const uint64_t pr = (uint64_t)x[j] * (uint64_t)y;  // mul.wide.u32 -> one IMAD.WIDE
+        acc[j] = (uint32_t)pr;
+        acc[j + 1] = (uint32_t)(pr >> 32);
+    }
+    acc[N] = 0;
+}
+template <int N>
+CQB_HD void rowN_mad(uint32_t* acc, const uint32_t* x, uint32_t y) {
+    acc[0] = mad_lo_cc(x[0], y, acc[0]);
+    acc[1] = madc_hi_cc(x[0], y, acc[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+        acc[j] = madc_lo_cc(x[j], y, acc[j]);
+        acc[j + 1] = madc_hi_cc(x[j], y, acc[j + 1]);
+    }
+    acc[N] = addc(acc[N], 0u);
+}
+template <int N>
+CQB_HD void rowN_madc_shift2(uint32_t* acc, const uint32_t* x, uint32_t y) {
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) {
+        acc[j] = madc_lo_cc(x[j], y, acc[j + 2]);
+        acc[j + 1] = madc_hi_cc(x[j], y, acc[j + 3]);
+    }
+    acc[N - 2] = madc_lo_cc(x[N - 2], y, acc[N]);
+    acc[N - 1] = madc_hi_cc(x[N - 2], y, 0u);
+    acc[N] = addc(0u, 0u);
+}
+
+// r[0..2N) = a[0..N) * b[0..N), N even: the even/odd two-accumulator scheme of fp_mul without the reduction rows; the
+// limb that leaves the frame after each row is a finished limb of the product.
+template <int N>
+CQB_HD void mul_nxn(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint32_t ev[N + 1], od[N + 1];
+    rowN_mul<N>(ev, a, b[0]);
+    rowN_mul<N>(od, a + 1, b[0]);
+    r[0] = ev[0];
+#pragma unroll
+    for (int i = 1; i < N; i += 2) {
+        od[0] = add_cc(od[0], ev[1]);
+        rowN_madc_shift2<N>(ev, a + 1, b[i]);
+        rowN_mad<N>(od, a, b[i]);
+        r[i] = od[0];
+        if (i + 1 < N) {
+            ev[0] = add_cc(ev[0], od[1]);
+            rowN_madc_shift2<N>(od, a + 1, b[i + 1]);
+            rowN_mad<N>(ev, a, b[i + 1]);
+            r[i + 1] = ev[0];
+        }
+    }
+    r[N] = add_cc(ev[0], od[1]);
+#pragma unroll
+    for (int k = 1; k < N - 1; k++) r[N + k] = addc_cc(ev[k], od[k + 1]);
+    r[2 * N - 1] = addc(ev[N - 1], od[N]);
+}
+
+// t[0..16) = a * b with one Karatsuba level over 4-limb halves
+CQB_HD void mul_8x8_karatsuba(uint32_t* t, const uint32_t* a, const uint32_t* b) {
+    uint32_t z0[8], z2[8], z1[9], sa[4], sb[4];
+    mul_nxn<4>(z0, a, b);
+    mul_nxn<4>(z2, a + 4, b + 4);
+    sa[0] = add_cc(a[0], a[4]); sa[1] = addc_cc(a[1], a[5]); sa[2] = addc_cc(a[2], a[6]); sa[3] = addc_cc(a[3], a[7]);
+    const uint32_t ca = addc(0u, 0u);
+    sb[0] = add_cc(b[0], b[4]); sb[1] = addc_cc(b[1], b[5]); sb[2] = addc_cc(b[2], b[6]); sb[3] = addc_cc(b[3], b[7]);
+    const uint32_t cb = addc(0u, 0u);
+    mul_nxn<4>(z1, sa, sb);
+    z1[8] = ca & cb;
+    const uint32_t ma = 0u - ca, mb = 0u - cb;
+    // (sa + ca 2^128)(sb + cb 2^128) = sa sb + (ca sb + cb sa) 2^128 + ca cb 2^256
+    z1[4] = add_cc(z1[4], sb[0] & ma); z1[5] = addc_cc(z1[5], sb[1] & ma); z1[6] = addc_cc(z1[6], sb[2] & ma);
+    z1[7] = addc_cc(z1[7], sb[3] & ma); z1[8] = addc(z1[8], 0u);
+    z1[4] = add_cc(z1[4], sa[0] & mb); z1[5] = addc_cc(z1[5], sa[1] & mb); z1[6] = addc_cc(z1[6], sa[2] & mb);
+    z1[7] = addc_cc(z1[7], sa[3] & mb); z1[8] = addc(z1[8], 0u);
+    // z1 -= z0 + z2  (the middle term a0 b1 + a1 b0 is non-negative and < 2^257)
+    z1[0] = sub_cc(z1[0], z0[0]);
+#pragma unroll
+    for (int k = 1; k < 8; k++) z1[k] = subc_cc(z1[k], z0[k]);
+    z1[8] = subc(z1[8], 0u);
+    z1[0] = sub_cc(z1[0], z2[0]);
+#pragma unroll
+    for (int k = 1; k < 8; k++) z1[k] = subc_cc(z1[k], z2[k]);
+    z1[8] = subc(z1[8], 0u);
+    // t = z0 + z1 2^128 + z2 2^256
+#pragma unroll
+    for (int k = 0; k < 4; k++) t[k] = z0[k];
+    t[4] = add_cc(z0[4], z1[0]); t[5] = addc_cc(z0[5], z1[1]); t[6] = addc_cc(z0[6], z1[2]); t[7] = addc_cc(z0[7], z1[3]);
+    t[8] = addc_cc(z2[0], z1[4]); t[9] = addc_cc(z2[1], z1[5]); t[10] = addc_cc(z2[2], z1[6]); t[11] = addc_cc(z2[3], z1[7]);
+    t[12] = addc_cc(z2[4], z1[8]); t[13] = addc_cc(z2[5], 0u); t[14] = addc_cc(z2[6], 0u); t[15] = addc(z2[7], 0u);
+}
+
+// Montgomery reduction of a 16-limb product t < p * 2^256: (t + M p) / 2^256 with M chosen limb by limb, then one
+// conditional subtraction (reference derive/field.rs:564-617 montgomery_reduce, restructured into the even/odd chains)
+template <class P>
+CQB_HD Fp<P> fp_reduce16(const uint32_t* t) {
+    uint32_t ev[9], od[9], p[8];
+    mod_limbs<P>(p);
+#pragma unroll
+    for (int k = 0; k < 8; k++) ev[k] = t[k];
+    ev[8] = 0;
+    uint32_t m = ev[0] * P::inv();
+    rowN_mul<8>(od, p + 1, m);
+    rowN_mad<8>(ev, p, m);
+#pragma unroll
+    for (int i = 1; i < 8; i += 2) {
+        od[0] = add_cc(od[0], ev[1]);
+        m = od[0] * P::inv();  // mul.lo does not touch the carry flag consumed by the chain below
+        rowN_madc_shift2<8>(ev, p + 1, m);
+        rowN_mad<8>(od, p, m);
+        if (i + 1 < 8) {
+            ev[0] = add_cc(ev[0], od[1]);
+            m = ev[0] * P::inv();
+            rowN_madc_shift2<8>(od, p + 1, m);
+            rowN_mad<8>(ev, p, m);
+        }
+    }
+    Fp<P> r;
+    // U = ev + (od >> 32) <= p ; result = U + t_hi < 2p
+    r.l[0] = add_cc(ev[0], od[1]);
+#pragma unroll
+    for (int k = 1; k < 7; k++) r.l[k] = addc_cc(ev[k], od[k + 1]);
+    r.l[7] = addc(ev[7], od[8]);
+    r.l[0] = add_cc(r.l[0], t[8]);
+#pragma unroll
+    for (int k = 1; k < 7; k++) r.l[k] = addc_cc(r.l[k], t[8 + k]);
+    r.l[7] = addc(r.l[7], t[15]);
+    fp_reduce_once<P>(r.l);
+    return r;
+}
+
+template <class P>
+CQB_HD Fp<P> fp_mul_kar(const Fp<P>& a, const Fp<P>& b) {
+    uint32_t t[16];
+    mul_8x8_karatsuba(t, a.l, b.l);
+    return fp_reduce16<P>(t);
 }
 
 // reference derive/field.rs:358-393. A dedicated squaring is an optimisation; the canonical result equals mul(a,a).

@@ -36,15 +36,16 @@ def test_fp_limb_algorithm(fp_bin):
         vals = [0, 1, 2, p - 1, p - 2, P.MONT % p, (1 << 254) % p, (p - 1) // 2] + [rng.randrange(p) for _ in range(300)]
         for _ in range(500):
             a, b = rng.choice(vals), rng.choice(vals)
-            for op, res in (("mul", a * b * rinv % p), ("add", (a + b) % p), ("sub", (a - b) % p), ("neg", (-a) % p),
+            for op, res in (("mul", a * b * rinv % p), ("mulk", a * b * rinv % p), ("add", (a + b) % p), ("sub", (a - b) % p), ("neg", (-a) % p),
                             ("dbl", 2 * a % p), ("sqr", a * a * rinv % p), ("frommont", a * rinv % p), ("tomont", a * P.MONT % p)):
                 lines.append(f"{name} {op} {a:064x} {b:064x}")
                 exp.append(res)
         # from_u512's first operand is an arbitrary 256-bit value (derive/field.rs:29-48): unreduced multiplicand
         for _ in range(200):
             a, b = rng.randrange(1 << 256), rng.choice(vals)
-            lines.append(f"{name} mul {a:064x} {b:064x}")
-            exp.append(a * b * rinv % p)
+            for op in ("mul", "mulk"):
+                lines.append(f"{name} {op} {a:064x} {b:064x}")
+                exp.append(a * b * rinv % p)
         for a in vals[:24]:
             for op in ("inv", "invb"):  # Fermat and binary-Euclid inversions agree (the inverse is unique)
                 lines.append(f"{name} {op} {a:064x} {0:064x}")

@@ -19,6 +19,7 @@ template <class P> static void run(const std::string& op, const std::string& sa,
     typedef Fp<P> F;
     F a = parse<F>(sa), b = parse<F>(sb);
     if (op == "mul") put(fp_mul<P>(a, b));
+    else if (op == "mulk") put(fp_mul_kar<P>(a, b));
     else if (op == "sqr") put(fp_sqr<P>(a));
     else if (op == "add") put(fp_add<P>(a, b));
     else if (op == "sub") put(fp_sub<P>(a, b));
