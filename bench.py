@@ -309,6 +309,7 @@ def main():
         import prove_workload
 
         line["prove_ms"] = [prove_workload.run(cqb200, k, reps=2) for k in args.prove_k]
+        line["prove_ms_resident"] = [prove_workload.run(cqb200, k, reps=2, resident=True) for k in args.prove_k]
         line["prove_ms_note"] = ("synthetic CQ-prover-shaped MSM/NTT op list (8 advice columns, one CQ lookup, table 2^16), host "
                                  "buffers; witness synthesis / evaluate_h / transcript are CPU work outside the path and excluded")
 

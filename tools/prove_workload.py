@@ -21,7 +21,11 @@ import time
 import numpy as np
 
 
-def run(cq, k, A=8, table_log=16, reps=2, seed=0x70726F76):
+def run(cq, k, A=8, table_log=16, reps=2, seed=0x70726F76, resident=False):
+    """resident=False: every call takes HOST pointers (what the drop-in Rust shim does: each op copies its operands).
+    resident=True : each column is uploaded ONCE per proof and stays in HBM (the *_dev entry points): commit_lagrange,
+    lagrange_to_coeff and coeff_to_extended of a column share one upload, extended evaluations never leave the device
+    (they feed evaluate_h, which is the next row of SURVEY §8f), only the 64 B commitments come back."""
     L = cq._lib
     lib = L.lib()
     n = 1 << k
@@ -79,7 +83,44 @@ def run(cq, k, A=8, table_log=16, reps=2, seed=0x70726F76):
         L.check(lib.cqb_coset_ntt_bn254_fr(ctypes.cast(ptr, u64), n, ctypes.cast(ext_out, u64), L.p64(dom.extended_omega),
                                            dom.extended_k, L.p64(dom.g_coset), L.p64(dom.g_coset_inv)))
 
-    def proof():
+    dcols = []
+    if resident:
+        for _ in range(A + 4):
+            d = ctypes.c_void_p()
+            L.check(lib.cqb_dev_alloc(n * 32, ctypes.byref(d)))
+            dcols.append(d)
+        d_ext, d_ext_out = ctypes.c_void_p(), ctypes.c_void_p()
+        L.check(lib.cqb_dev_alloc(en * 32, ctypes.byref(d_ext)))
+        L.check(lib.cqb_dev_alloc(en * 32, ctypes.byref(d_ext_out)))
+
+    def msm_d(h, dptr, count, offset=0):
+        L.check(lib.cqb_msm_bn254_g1_dev(h, offset, dptr, count, L.p64(out), ctypes.byref(inf)))
+
+    def proof_resident():
+        for i in range(A + 4):   # one upload per column per proof
+            L.check(lib.cqb_memcpy_h2d(dcols[i], cols[i], n * 32))
+        L.check(lib.cqb_memcpy_h2d(d_ext, ext, en * 32))   # stands in for evaluate_h's output (computed on device in a full port)
+        for a in range(A):
+            msm_d(g_lag, dcols[a], n)
+        msm_d(g_lag, dcols[A], n)
+        sparse(t_lag); sparse(t_lag); sparse(t_qs); sparse(t_op0)
+        L.check(lib.cqb_intt_bn254_fr_dev(dcols[A + 1], L.p64(dom.omega_inv), L.p64(dom.ifft_divisor), k))
+        msm_d(t_g1, dcols[A + 1], n - 1, offset=Nt - (n - 1))
+        msm_d(g, dcols[A + 1], n)
+        L.check(lib.cqb_intt_bn254_fr_dev(dcols[A], L.p64(dom.omega_inv), L.p64(dom.ifft_divisor), k))
+        msm_d(g, dcols[A + 2], n)
+        for a in range(A):
+            L.check(lib.cqb_intt_bn254_fr_dev(dcols[a], L.p64(dom.omega_inv), L.p64(dom.ifft_divisor), k))
+        for a in list(range(A)) + [A, A + 1]:
+            L.check(lib.cqb_coset_ntt_bn254_fr_dev(dcols[a], n, d_ext_out, L.p64(dom.extended_omega), dom.extended_k,
+                                                   L.p64(dom.g_coset), L.p64(dom.g_coset_inv)))
+        L.check(lib.cqb_coset_intt_bn254_fr_dev(d_ext, dom.extended_k, L.p64(dom.extended_omega_inv), L.p64(dom.extended_ifft_divisor),
+                                                L.p64(dom.g_coset), L.p64(dom.g_coset_inv), L.p64(dom.t_evaluations),
+                                                dom.t_evaluations.shape[0]))
+        msm_d(g, d_ext, n); msm_d(g, ctypes.c_void_p(d_ext.value + n * 32), n)   # the two h pieces, straight from the device
+        msm_d(g, dcols[A + 3], n - 1)
+
+    def proof_host():
         for a in range(A):
             msm(g_lag, cols[a], n)
         msm(g_lag, cols[A], n)          # f
@@ -101,6 +142,7 @@ def run(cq, k, A=8, table_log=16, reps=2, seed=0x70726F76):
         msm(g, cols[A + 3], n); msm(g, cols[A + 2], n)   # two h pieces
         msm(g, cols[A + 3], n - 1)      # GWC witness
 
+    proof = proof_resident if resident else proof_host
     proof()  # warm-up (twiddle tables, scratch growth)
     L.check(lib.cqb_sync())
     l0 = lib.cqb_launch_count()
@@ -112,11 +154,14 @@ def run(cq, k, A=8, table_log=16, reps=2, seed=0x70726F76):
     launches = (lib.cqb_launch_count() - l0) // reps
     for p in cols + [ext, ext_out, sp]:
         L.check(lib.cqb_host_free_pinned(p))
+    if resident:
+        for d in dcols + [d_ext, d_ext_out]:
+            L.check(lib.cqb_dev_free(d))
     for d, h in keep + tabs:
         L.check(lib.cqb_bases_free(h))
         L.check(lib.cqb_dev_free(d))
     n_msm = A + 1 + 4 + 2 + 1 + 2 + 1
-    return {"k": k, "advice_columns": A, "table_rows": N, "ms_per_proof": ms, "gpu_launches_per_proof": int(launches),
+    return {"k": k, "mode": "device-resident polynomials" if resident else "host-pointer calls (drop-in)", "advice_columns": A, "table_rows": N, "ms_per_proof": ms, "gpu_launches_per_proof": int(launches),
             "ops": {"dense_msm": n_msm - 4, "sparse_msm": 4, "intt_n": A + 2, "coset_ntt_2n": A + 2, "coset_intt_2n": 1}}
 
 
@@ -131,3 +176,4 @@ if __name__ == "__main__":
     cqb200._lib.init(0)
     for k in [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["16", "20"])]:
         print(json.dumps(run(cqb200, k)), flush=True)
+        print(json.dumps(run(cqb200, k, resident=True)), flush=True)
