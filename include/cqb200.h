@@ -113,6 +113,19 @@ CQB_API int cqb_synth_scalars_dev(uint64_t seed, size_t start, size_t n, void* d
 /* bases[i] = [s0 + (start + i) d] G, (s0, d) = first two scalars of stream `seed`; affine, normalised on the device */
 CQB_API int cqb_synth_bases_dev(uint64_t seed, size_t start, size_t n, void* d_out);
 
+/* ---- SRS generation + element-wise helpers ------------------------------------------
+ * cqb_srs_setup_dev replaces the scalar-multiplication loops of ParamsKZG::setup_from_toxic_waste / setup
+ * (poly/kzg/commitment.rs:209-276, 280-348; identical G1 formulas in TableSRS::setup_from_toxic_waste :73-141):
+ * d_g[i] = [s^i]G, d_g_lagrange[i] = [(s^n - 1)/n * w^i/(s - w^i)]G for n = 2^k, affine, 64 B each, written to device
+ * memory (register them with cqb_bases_register_device — the SRS never has to exist on the host). */
+CQB_API int cqb_srs_setup_dev(uint32_t k, const uint64_t s[4], void* d_g, void* d_g_lagrange);
+/* out[i] = [scalars[i]] G (fixed-base batch multiplication by the bn256 generator (1,2)), affine */
+CQB_API int cqb_g1_generator_mul_dev(const void* d_scalars, size_t n, void* d_out);
+/* in place a[i] <- 1/a[i], zeros stay zero: ff::BatchInvert as used at poly/domain.rs:118-125, static_lookup/prover.rs:261-269 */
+CQB_API int cqb_fr_batch_invert_dev(void* d_a, size_t n);
+/* out[i] = base^i, i < n (the serial scans at arithmetic.rs:194-200, commitment.rs:153-156) */
+CQB_API int cqb_fr_powers_dev(const uint64_t base[4], size_t n, void* d_out);
+
 /* ---- plain device memory helpers so non-CUDA hosts (ctypes, the Rust shim) need no CUDA binding of their own ---- */
 CQB_API int cqb_dev_alloc(size_t bytes, void** d_out);
 CQB_API int cqb_dev_free(void* d);

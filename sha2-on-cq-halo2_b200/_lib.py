@@ -45,6 +45,10 @@ SYMBOLS = [
     ("cqb_coset_intt_bn254_fr_dev", _int, [_vp, _u32, u64p, u64p, u64p, u64p, u64p, _u32]),
     ("cqb_synth_scalars_dev", _int, [_u64, _sz, _sz, _vp]),
     ("cqb_synth_bases_dev", _int, [_u64, _sz, _sz, _vp]),
+    ("cqb_srs_setup_dev", _int, [_u32, u64p, _vp, _vp]),
+    ("cqb_g1_generator_mul_dev", _int, [_vp, _sz, _vp]),
+    ("cqb_fr_batch_invert_dev", _int, [_vp, _sz]),
+    ("cqb_fr_powers_dev", _int, [u64p, _sz, _vp]),
     ("cqb_dev_alloc", _int, [_sz, ctypes.POINTER(_vp)]),
     ("cqb_dev_free", _int, [_vp]),
     ("cqb_memcpy_h2d", _int, [_vp, _vp, _sz]),

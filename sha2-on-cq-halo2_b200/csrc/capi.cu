@@ -140,6 +140,7 @@ void cqb_shutdown(void) {
     ntt_release_all();
     msm_release_all();
     gen_release_all();
+    srs_release_all();
     if (g_copy_stream) {
         for (auto& e : g_copy_ev) cudaEventDestroy(e);
         cudaStreamDestroy(g_copy_stream);
@@ -517,6 +518,32 @@ int cqb_synth_bases_dev(uint64_t seed, size_t start, size_t n, void* d_out) {
     CQB_TRY(require_init());
     if (!d_out && n) return fail(CQB_E_BAD_ARG, "cqb_synth_bases_dev: NULL argument");
     return synth_bases_run(seed, start, n, d_out);
+}
+
+// ---- SRS generation and element-wise helpers ----------------------------------------------
+int cqb_srs_setup_dev(uint32_t k, const uint64_t s[4], void* d_g, void* d_g_lagrange) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!s || !d_g || !d_g_lagrange) return fail(CQB_E_BAD_ARG, "cqb_srs_setup_dev: NULL argument");
+    return srs_setup_run(k, s, d_g, d_g_lagrange);
+}
+int cqb_g1_generator_mul_dev(const void* d_scalars, size_t n, void* d_out) {
+    LOCK;
+    CQB_TRY(require_init());
+    if ((!d_scalars || !d_out) && n) return fail(CQB_E_BAD_ARG, "cqb_g1_generator_mul_dev: NULL argument");
+    return g1_generator_mul_run(d_scalars, n, d_out);
+}
+int cqb_fr_batch_invert_dev(void* d_a, size_t n) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!d_a && n) return fail(CQB_E_BAD_ARG, "cqb_fr_batch_invert_dev: NULL argument");
+    return fr_batch_invert_run(d_a, n);
+}
+int cqb_fr_powers_dev(const uint64_t base[4], size_t n, void* d_out) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!base || (!d_out && n)) return fail(CQB_E_BAD_ARG, "cqb_fr_powers_dev: NULL argument");
+    return fr_powers_run(base, n, d_out);
 }
 
 // ---- memory helpers ---------------------------------------------------------------------------------------------

@@ -2,6 +2,8 @@
 #pragma once
 #include <string.h>
 
+#include <algorithm>
+
 #include "context.h"
 #include "ec.cuh"
 #include "fp.cuh"
@@ -42,6 +44,13 @@ void msm_release_all();
 void msm_set_window_bits(int c);
 void msm_set_profiling(bool on);
 int msm_phase_ms(float* ms, int cap);
+
+// ---- srs.cu ----
+int fr_powers_run(const uint64_t base[4], size_t count, void* d_out);  // defined in ntt.cu
+int fr_batch_invert_run(void* d_a, size_t n);
+int g1_generator_mul_run(const void* d_scalars, size_t n, void* d_out);
+int srs_setup_run(uint32_t k, const uint64_t s_limbs[4], void* d_g, void* d_g_lagrange);
+void srs_release_all();
 
 // ---- gen.cu ----
 int synth_scalars_run(uint64_t seed, size_t start, size_t n, void* d_out);

@@ -277,6 +277,21 @@ static int get_twiddles(const uint64_t omega[4], uint32_t L, const uint4** out) 
     return 0;
 }
 
+// out[i] = base^i for i < count (the twiddle kernel on an arbitrary base); used by the SRS generator
+int fr_powers_run(const uint64_t base[4], size_t count, void* d_out) {
+    if (count == 0) return 0;
+    TwArgs ta;
+    ta.out = (uint4*)d_out;
+    ta.count = count;
+    Fr w = fr_from_u64x4(base);
+    for (int b = 0; b < 28; b++) { ta.pw[b] = w; w = fp_sqr<FrP>(w); }
+    size_t threads = (count + TW_RUN - 1) / TW_RUN;
+    ntt_twiddle_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx().stream>>>(ta);
+    CQB_LAUNCHED();
+    CQB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // d_src may alias d_dst (in place). All pointers are device pointers to 32-byte Fr elements.
 int ntt_run(const void* d_src, void* d_dst, uint32_t L, const uint64_t omega[4], const NttFused& f) {
     if (L > 28) return fail(CQB_E_BAD_SIZE, "log_n = %u exceeds Fr::S = 28 (bn256/fr.rs:72)", L);

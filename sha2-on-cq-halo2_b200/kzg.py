@@ -12,6 +12,27 @@ from .arithmetic import G1, _as_fr, _as_g1
 class DeviceBases:
     """A device-resident Vec<G1Affine>"""
 
+    @classmethod
+    def adopt(cls, device_ptr, n, precompute=None, window_bits=0):
+        """wrap points that already live in device memory (no host copy); the caller keeps the allocation alive"""
+        self = cls.__new__(cls)
+        self.n = n
+        h = ctypes.c_uint64(0)
+        _lib.check(_lib.lib().cqb_bases_register_device(ctypes.c_void_p(device_ptr), n, ctypes.byref(h)))
+        self.handle = h.value
+        self._device_ptr = device_ptr
+        if precompute is None:
+            precompute = n >= (1 << 16)
+        if precompute and n:
+            self.precompute(window_bits)
+        return self
+
+    def to_host(self):
+        """download the points (only possible for adopted device memory)"""
+        out = np.zeros((self.n, 8), np.uint64)
+        _lib.check(_lib.lib().cqb_memcpy_d2h(out.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(self._device_ptr), self.n * 64))
+        return out
+
     def __init__(self, affine, precompute=None, window_bits=0):
         """precompute: build the resident 2^(c w) P_i table (cqb_bases_precompute) so that MSMs over this set use one
         bucket set with wider windows. None = automatically for sets of >= 2^16 points."""
@@ -54,12 +75,57 @@ class DeviceBases:
 class ParamsKZG:
     """reference poly/kzg/commitment.rs:31-39 { k, n, g, g_lagrange, .. } (g2 / s_g2 are verifier-side, out of scope)"""
 
-    def __init__(self, k, g, g_lagrange, precompute=None):
+    def __init__(self, k, g, g_lagrange, precompute=None, g2=None, s_g2=None):
         self.k = k
         self.n = 1 << k
         assert g.shape == (self.n, 8) and g_lagrange.shape == (self.n, 8)
         self.g = DeviceBases(g, precompute)
         self.g_lagrange = DeviceBases(g_lagrange, precompute)
+        self.g2, self.s_g2 = g2, s_g2  # 128-byte raw G2Affine blobs: verifier-side data, carried opaquely
+        self._dev_alloc = None
+
+    @classmethod
+    def setup_from_toxic_waste(cls, k, s, precompute=None):
+        """reference poly/kzg/commitment.rs:209-276, G1 part: g[i] = [s^i]G and g_lagrange[i] = [L_i(s)]G are generated
+        ON THE DEVICE (cqb_srs_setup_dev) and registered in place; the SRS never exists in host memory. `s`: (4,) uint64
+        Montgomery limbs. (g2 / s_g2 = [s]G2 are verifier-side; supply them separately if the params are to be written.)"""
+        assert k <= 28, "assert!(k <= E::Scalar::S)"  # commitment.rs:212
+        lib = _lib.lib()
+        n = 1 << k
+        d = ctypes.c_void_p()
+        _lib.check(lib.cqb_dev_alloc(2 * n * 64, ctypes.byref(d)))
+        _lib.check(lib.cqb_srs_setup_dev(k, _lib.p64(_lib.fr_limbs(s)), d, ctypes.c_void_p(d.value + n * 64)))
+        _lib.check(lib.cqb_sync())
+        self = cls.__new__(cls)
+        self.k, self.n = k, n
+        self.g = DeviceBases.adopt(d.value, n, precompute)
+        self.g_lagrange = DeviceBases.adopt(d.value + n * 64, n, precompute)
+        self.g2 = self.s_g2 = None
+        self._dev_alloc = d
+        return self
+
+    def write(self, writer, g2=None, s_g2=None):
+        """reference commitment.rs:366-380 write_custom(RawBytesUnchecked): k as u32 LE, g, g_lagrange (x||y Montgomery
+        limbs, 64 B each), then g2 and s_g2 (128 B raw G2Affine each)"""
+        g2 = g2 if g2 is not None else self.g2
+        s_g2 = s_g2 if s_g2 is not None else self.s_g2
+        assert g2 is not None and s_g2 is not None and len(g2) == 128 and len(s_g2) == 128, "g2 / s_g2 raw bytes required"
+        writer.write(int(self.k).to_bytes(4, "little"))
+        for b in (self.g, self.g_lagrange):
+            writer.write(b.to_host().tobytes())
+        writer.write(bytes(g2))
+        writer.write(bytes(s_g2))
+
+    @classmethod
+    def read(cls, reader, precompute=None):
+        """reference commitment.rs:383-459 read_custom(RawBytesUnchecked): the point arrays go straight to the device"""
+        k = int.from_bytes(reader.read(4), "little")
+        n = 1 << k
+        g = np.frombuffer(reader.read(n * 64), dtype=np.uint64).reshape(n, 8)
+        gl = np.frombuffer(reader.read(n * 64), dtype=np.uint64).reshape(n, 8)
+        g2, s_g2 = reader.read(128), reader.read(128)
+        assert len(s_g2) == 128, "truncated params file"
+        return cls(k, g, gl, precompute, g2=g2, s_g2=s_g2)
 
     def commit_lagrange(self, poly, _blind=None):
         """reference commitment.rs:496-504: assert!(self.n() >= size); best_multiexp(poly, &self.g_lagrange[0..size])"""
@@ -76,6 +142,9 @@ class ParamsKZG:
     def free(self):
         self.g.free()
         self.g_lagrange.free()
+        if self._dev_alloc is not None:
+            _lib.check(_lib.lib().cqb_dev_free(self._dev_alloc))
+            self._dev_alloc = None
 
 
 class TableSRS:

@@ -1,0 +1,131 @@
+"""SRS generation on the device and the element-wise helpers it uses, checked against the CPU
+oracle's restatement of ParamsKZG::setup_from_toxic_waste (poly/kzg/commitment.rs:209-276)."""
+import ctypes
+import io
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import pyref as P  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def cq():
+    import cqb200
+
+    cqb200._lib.init(0)
+    return cqb200
+
+
+def _dev(cq, arr):
+    lib = cq._lib.lib()
+    d = ctypes.c_void_p()
+    cq._lib.check(lib.cqb_dev_alloc(max(arr.nbytes, 64), ctypes.byref(d)))
+    if arr.nbytes:
+        cq._lib.check(lib.cqb_memcpy_h2d(d, arr.ctypes.data_as(ctypes.c_void_p), arr.nbytes))
+    return d
+
+
+def _host(cq, d, shape):
+    out = np.zeros(shape, np.uint64)
+    cq._lib.check(cq._lib.lib().cqb_memcpy_d2h(out.ctypes.data_as(ctypes.c_void_p), d, out.nbytes))
+    return out
+
+
+@pytest.mark.parametrize("k", [0, 1, 3, 6, 10])
+def test_srs_setup_matches_reference_formulas(cq, oracle, k):
+    s = oracle.synth_scalars(0xC0 + k, 1)[0]
+    g_exp, gl_exp = oracle.params_setup(k, s)
+    params = cq.ParamsKZG.setup_from_toxic_waste(k, s, precompute=False)
+    assert np.array_equal(params.g.to_host(), g_exp)
+    assert np.array_equal(params.g_lagrange.to_host(), gl_exp)
+    # and it is usable as an SRS: kzg/commitment.rs:570-593 commit(ifft(a)) == commit_lagrange(a)
+    if k >= 1:
+        d = cq.EvaluationDomain(1, k)
+        a = oracle.synth_scalars(5, 1 << k)
+        assert params.commit(d.lagrange_to_coeff(a)) == params.commit_lagrange(a)
+    params.free()
+
+
+def test_srs_large_k_identities(cq, oracle):
+    """k = 16: too slow for the CPU oracle's 2^17 scalar multiplications; checked through identities instead:
+    sum_i g_lagrange[i] = G (the Lagrange basis sums to 1), g[0] = G, g[1] = [s]G, commit identity with the precomputed layout"""
+    k = 16
+    s = oracle.synth_scalars(0xD00D, 1)[0]
+    params = cq.ParamsKZG.setup_from_toxic_waste(k, s)
+    n = 1 << k
+    ones = np.tile(P.int_to_limbs(P.MONT % P.R_MOD), (n, 1))
+    assert np.array_equal(params.commit_lagrange(ones).to_affine(), oracle.g1_generator())
+    e0 = np.zeros((n, 4), np.uint64)
+    e0[0] = ones[0]
+    assert np.array_equal(params.commit(e0).to_affine(), oracle.g1_generator())
+    e1 = np.zeros((n, 4), np.uint64)
+    e1[1] = ones[0]
+    assert np.array_equal(params.commit(e1).to_affine(), oracle.g1_to_affine(oracle.g1_mul_a(oracle.g1_generator(), s)))
+    d = cq.EvaluationDomain(1, k)
+    a = oracle.synth_scalars(6, n)
+    assert params.commit(d.lagrange_to_coeff(a)) == params.commit_lagrange(a)
+    params.free()
+
+
+def test_params_raw_format_roundtrip(cq, oracle):
+    """commitment.rs:366-459 write_custom / read_custom (RawBytesUnchecked) and test_parameter_serialisation_roundtrip :595-621"""
+    k = 4
+    s = oracle.synth_scalars(0xC4, 1)[0]
+    p0 = cq.ParamsKZG.setup_from_toxic_waste(k, s, precompute=False)
+    g2, s_g2 = bytes(range(128)), bytes(reversed(range(128)))
+    buf = io.BytesIO()
+    p0.write(buf, g2=g2, s_g2=s_g2)
+    raw = buf.getvalue()
+    assert len(raw) == 4 + 2 * 16 * 64 + 256 and raw[:4] == (4).to_bytes(4, "little")
+    g_exp, gl_exp = oracle.params_setup(k, s)
+    assert raw[4:4 + 16 * 64] == g_exp.tobytes() and raw[4 + 16 * 64:4 + 32 * 64] == gl_exp.tobytes()
+    p1 = cq.ParamsKZG.read(io.BytesIO(raw), precompute=False)
+    assert p1.k == 4 and p1.g2 == g2 and p1.s_g2 == s_g2
+    a = oracle.synth_scalars(8, 16)
+    assert p0.commit(a) == p1.commit(a) and p0.commit_lagrange(a) == p1.commit_lagrange(a)
+    p0.free()
+    p1.free()
+
+
+def test_generator_mul_batch(cq, oracle):
+    lib = cq._lib.lib()
+    n = 300
+    sc = oracle.synth_scalars(0xF00, n)
+    sc[0] = 0
+    sc[1] = P.int_to_limbs(P.to_mont(P.R_MOD - 1, P.R_MOD))
+    sc[2] = P.int_to_limbs(P.to_mont(1, P.R_MOD))
+    sc[3] = P.int_to_limbs(P.to_mont(0x8000, P.R_MOD))
+    sc[4] = P.int_to_limbs(P.to_mont(0xFFFF_FFFF, P.R_MOD))
+    d_s = _dev(cq, sc)
+    d_o = _dev(cq, np.zeros((n, 8), np.uint64))
+    cq._lib.check(lib.cqb_g1_generator_mul_dev(d_s, n, d_o))
+    got = _host(cq, d_o, (n, 8))
+    g = oracle.g1_generator()
+    for i in list(range(8)) + [57, 131, 299]:
+        assert np.array_equal(got[i], oracle.g1_to_affine(oracle.g1_mul_a(g, sc[i]))), i
+    cq._lib.check(lib.cqb_dev_free(d_s))
+    cq._lib.check(lib.cqb_dev_free(d_o))
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000])
+def test_batch_invert_and_powers(cq, oracle, n):
+    lib = cq._lib.lib()
+    a = oracle.synth_scalars(0xB1 + n, n)
+    if n > 5:
+        a[3] = 0  # zeros are skipped, as ff::BatchInvert does
+    d = _dev(cq, a)
+    cq._lib.check(lib.cqb_fr_batch_invert_dev(d, n))
+    got = _host(cq, d, (n, 4))
+    for i in range(n):
+        assert np.array_equal(got[i], oracle.fr_op("invert", a[i])), i
+    base = oracle.synth_scalars(0xB2, 1)[0]
+    cq._lib.check(lib.cqb_fr_powers_dev(cq._lib.p64(base), n, d))
+    pw = _host(cq, d, (n, 4))
+    acc = oracle.fr_const("ONE")
+    for i in range(n):
+        assert np.array_equal(pw[i], acc), i
+        acc = oracle.fr_op("mul", acc, base)
+    cq._lib.check(lib.cqb_dev_free(d))
