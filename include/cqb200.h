@@ -119,6 +119,10 @@ CQB_API int cqb_synth_bases_dev(uint64_t seed, size_t start, size_t n, void* d_o
  * d_g[i] = [s^i]G, d_g_lagrange[i] = [(s^n - 1)/n * w^i/(s - w^i)]G for n = 2^k, affine, 64 B each, written to device
  * memory (register them with cqb_bases_register_device — the SRS never has to exist on the host). */
 CQB_API int cqb_srs_setup_dev(uint32_t k, const uint64_t s[4], void* d_g, void* d_g_lagrange);
+/* g_to_lagrange (halo2_proofs/src/arithmetic.rs:277-301): radix-2 FFT over G1 of the first 2^k monomial SRS points, scaled
+ * by 1/n and normalised -> the Lagrange SRS; what ParamsKZG::downsize needs (poly/kzg/commitment.rs:482-490).
+ * d_g and d_out: 2^k affine points each, must not alias. */
+CQB_API int cqb_g_to_lagrange_dev(const void* d_g, uint32_t k, void* d_out);
 /* out[i] = [scalars[i]] G (fixed-base batch multiplication by the bn256 generator (1,2)), affine */
 CQB_API int cqb_g1_generator_mul_dev(const void* d_scalars, size_t n, void* d_out);
 /* in place a[i] <- 1/a[i], zeros stay zero: ff::BatchInvert as used at poly/domain.rs:118-125, static_lookup/prover.rs:261-269 */
@@ -131,6 +135,7 @@ CQB_API int cqb_dev_alloc(size_t bytes, void** d_out);
 CQB_API int cqb_dev_free(void* d);
 CQB_API int cqb_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes);
 CQB_API int cqb_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes);
+CQB_API int cqb_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes); /* stream-ordered, asynchronous */
 CQB_API int cqb_host_alloc_pinned(size_t bytes, void** h_out);
 CQB_API int cqb_host_free_pinned(void* h);
 

@@ -758,3 +758,51 @@ API int oracle_hw_threads(void) {
     long n = sysconf(_SC_NPROCESSORS_ONLN);
     return n > 0 ? (int)n : 1;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * g_to_lagrange — halo2_proofs/src/arithmetic.rs:277-301: best_fft over G = G1 (group_add / group_sub = Jacobian
+ * add / sub, group_scale = 256-bit scalar multiplication), then * n_inv, then batch_normalize. Reached from
+ * ParamsKZG::downsize (poly/kzg/commitment.rs:482-490). Serial iterative form of best_fft (arithmetic.rs:202-230).
+ * ------------------------------------------------------------------------------------------------------------------ */
+static void best_fft_g1(g1j* a, fe omega, uint32_t log_n) {
+    size_t n = (size_t)1 << log_n;
+    for (size_t k = 0; k < n; k++) {
+        size_t rk = bitreverse(k, log_n);
+        if (k < rk) { g1j t = a[rk]; a[rk] = a[k]; a[k] = t; }
+    }
+    size_t nt = n / 2;
+    fe* twiddles = (fe*)malloc(sizeof(fe) * (nt ? nt : 1));
+    fe w = fr_one();
+    for (size_t i = 0; i < nt; i++) { twiddles[i] = w; w = fr_mul(w, omega); }
+    size_t chunk = 2, twiddle_chunk = n / 2;
+    for (uint32_t s = 0; s < log_n; s++) {
+        for (size_t base = 0; base < n; base += chunk) {
+            g1j* left = a + base;
+            g1j* right = a + base + chunk / 2;
+            for (size_t i = 0; i < chunk / 2; i++) {
+                g1j t = right[i];
+                if (i != 0) t = g1j_mul(&t, twiddles[i * twiddle_chunk]); /* twiddle one is skipped (:213-219) */
+                g1j nt_ = g1j_neg(&t);
+                right[i] = g1j_add(&left[i], &nt_);
+                left[i] = g1j_add(&left[i], &t);
+            }
+        }
+        chunk *= 2;
+        twiddle_chunk /= 2;
+    }
+    free(twiddles);
+}
+
+API void oracle_g_to_lagrange(const uint64_t* g_affine, uint32_t k, uint64_t* out_affine) {
+    size_t n = (size_t)1 << k;
+    uint64_t kk[1] = {k};
+    fe n_inv = fr_pow_vartime(fr_two_inv(), kk, 1);      /* TWO_INV.pow_vartime(&[k]) :278 */
+    fe omega_inv = fr_root_of_unity_inv();
+    for (uint32_t i = k; i < FR_S; i++) omega_inv = fr_square(omega_inv); /* :279-282 */
+    g1j* p = (g1j*)malloc(sizeof(g1j) * n);
+    for (size_t i = 0; i < n; i++) p[i] = g1a_to_curve(&((const g1a*)g_affine)[i]);
+    best_fft_g1(p, omega_inv, k);                        /* :285 */
+    for (size_t i = 0; i < n; i++) p[i] = g1j_mul(&p[i], n_inv); /* :286-290 */
+    g1j_batch_normalize(p, (g1a*)out_affine, n);         /* :292-298 */
+    free(p);
+}

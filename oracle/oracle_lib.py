@@ -295,3 +295,12 @@ def synth_bases(seed, n, threads=None):
     out = np.zeros((n, 8), np.uint64)
     lib().oracle_synth_bases(ctypes.c_uint64(seed), ctypes.c_size_t(n), ctypes.c_size_t(threads or hw_threads()), _p(out))
     return out
+
+
+def g_to_lagrange(g_affine, k):
+    """reference arithmetic.rs:277-301 (G1 EC-FFT), as used by ParamsKZG::downsize (commitment.rs:482-490)"""
+    g_affine = _c(g_affine, 8)
+    assert g_affine.shape[0] == 1 << k
+    out = np.zeros((1 << k, 8), np.uint64)
+    lib().oracle_g_to_lagrange(_p(g_affine), ctypes.c_uint32(k), _p(out))
+    return out

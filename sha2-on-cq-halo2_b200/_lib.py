@@ -47,12 +47,14 @@ SYMBOLS = [
     ("cqb_synth_bases_dev", _int, [_u64, _sz, _sz, _vp]),
     ("cqb_srs_setup_dev", _int, [_u32, u64p, _vp, _vp]),
     ("cqb_g1_generator_mul_dev", _int, [_vp, _sz, _vp]),
+    ("cqb_g_to_lagrange_dev", _int, [_vp, _u32, _vp]),
     ("cqb_fr_batch_invert_dev", _int, [_vp, _sz]),
     ("cqb_fr_powers_dev", _int, [u64p, _sz, _vp]),
     ("cqb_dev_alloc", _int, [_sz, ctypes.POINTER(_vp)]),
     ("cqb_dev_free", _int, [_vp]),
     ("cqb_memcpy_h2d", _int, [_vp, _vp, _sz]),
     ("cqb_memcpy_d2h", _int, [_vp, _vp, _sz]),
+    ("cqb_memcpy_d2d", _int, [_vp, _vp, _sz]),
     ("cqb_host_alloc_pinned", _int, [_sz, ctypes.POINTER(_vp)]),
     ("cqb_host_free_pinned", _int, [_vp]),
     ("cqb_msm_set_window_bits", _int, [_int]),

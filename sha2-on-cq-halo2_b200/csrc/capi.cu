@@ -141,6 +141,7 @@ void cqb_shutdown(void) {
     msm_release_all();
     gen_release_all();
     srs_release_all();
+    ecntt_release_all();
     if (g_copy_stream) {
         for (auto& e : g_copy_ev) cudaEventDestroy(e);
         cudaStreamDestroy(g_copy_stream);
@@ -527,6 +528,12 @@ int cqb_srs_setup_dev(uint32_t k, const uint64_t s[4], void* d_g, void* d_g_lagr
     if (!s || !d_g || !d_g_lagrange) return fail(CQB_E_BAD_ARG, "cqb_srs_setup_dev: NULL argument");
     return srs_setup_run(k, s, d_g, d_g_lagrange);
 }
+int cqb_g_to_lagrange_dev(const void* d_g, uint32_t k, void* d_out) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!d_g || !d_out || d_g == d_out) return fail(CQB_E_BAD_ARG, "cqb_g_to_lagrange_dev: NULL or aliasing arguments");
+    return g_to_lagrange_run(d_g, k, d_out);
+}
 int cqb_g1_generator_mul_dev(const void* d_scalars, size_t n, void* d_out) {
     LOCK;
     CQB_TRY(require_init());
@@ -569,6 +576,12 @@ int cqb_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes) {
     CQB_TRY(require_init());
     CQB_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, g_ctx.stream));
     CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return 0;
+}
+int cqb_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes) {
+    LOCK;
+    CQB_TRY(require_init());
+    CQB_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, g_ctx.stream));
     return 0;
 }
 int cqb_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes) {

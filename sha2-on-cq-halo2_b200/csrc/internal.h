@@ -45,6 +45,11 @@ void msm_set_window_bits(int c);
 void msm_set_profiling(bool on);
 int msm_phase_ms(float* ms, int cap);
 
+// ---- ecntt.cu ----
+int ntt_get_twiddles(const uint64_t omega[4], uint32_t log_n, const void** d_table);  // defined in ntt.cu (cached table)
+int g_to_lagrange_run(const void* d_g, uint32_t k, void* d_out);
+void ecntt_release_all();
+
 // ---- srs.cu ----
 int fr_powers_run(const uint64_t base[4], size_t count, void* d_out);  // defined in ntt.cu
 int fr_batch_invert_run(void* d_a, size_t n);

@@ -277,6 +277,13 @@ static int get_twiddles(const uint64_t omega[4], uint32_t L, const uint4** out) 
     return 0;
 }
 
+int ntt_get_twiddles(const uint64_t omega[4], uint32_t L, const void** out) {
+    const uint4* p = nullptr;
+    CQB_TRY(get_twiddles(omega, L, &p));
+    *out = p;
+    return 0;
+}
+
 // out[i] = base^i for i < count (the twiddle kernel on an arbitrary base); used by the SRS generator
 int fr_powers_run(const uint64_t base[4], size_t count, void* d_out) {
     if (count == 0) return 0;

@@ -104,6 +104,27 @@ class ParamsKZG:
         self._dev_alloc = d
         return self
 
+    def downsize(self, k):
+        """reference commitment.rs:482-490: truncate g to 2^k points and rebuild g_lagrange with g_to_lagrange (the G1
+        EC-FFT of arithmetic.rs:277-301) — on the device, from the resident monomial SRS"""
+        assert k <= self.k, "assert!(k <= self.k)"
+        if self._dev_alloc is None:
+            raise NotImplementedError("downsize needs the device-generated layout (setup_from_toxic_waste)")
+        lib = _lib.lib()
+        n = 1 << k
+        d = ctypes.c_void_p()
+        _lib.check(lib.cqb_dev_alloc(2 * n * 64, ctypes.byref(d)))
+        _lib.check(lib.cqb_memcpy_d2d(d, ctypes.c_void_p(self.g._device_ptr), n * 64))
+        _lib.check(lib.cqb_g_to_lagrange_dev(d, k, ctypes.c_void_p(d.value + n * 64)))
+        _lib.check(lib.cqb_sync())
+        old = self._dev_alloc
+        self.g.free()
+        self.g_lagrange.free()
+        _lib.check(lib.cqb_dev_free(old))
+        self.k, self.n, self._dev_alloc = k, n, d
+        self.g = DeviceBases.adopt(d.value, n, precompute=False)
+        self.g_lagrange = DeviceBases.adopt(d.value + n * 64, n, precompute=False)
+
     def write(self, writer, g2=None, s_g2=None):
         """reference commitment.rs:366-380 write_custom(RawBytesUnchecked): k as u32 LE, g, g_lagrange (x||y Montgomery
         limbs, 64 B each), then g2 and s_g2 (128 B raw G2Affine each)"""

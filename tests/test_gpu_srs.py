@@ -129,3 +129,34 @@ def test_batch_invert_and_powers(cq, oracle, n):
         assert np.array_equal(pw[i], acc), i
         acc = oracle.fr_op("mul", acc, base)
     cq._lib.check(lib.cqb_dev_free(d))
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, 5, 8])
+def test_g_to_lagrange_parity(cq, oracle, k):
+    """arithmetic.rs:277-301 (G1 EC-FFT) vs the oracle's restatement, on arbitrary curve points"""
+    lib = cq._lib.lib()
+    n = 1 << k
+    g = oracle.synth_bases(0xEC + k, n, 2)
+    if n >= 8:
+        g[3] = 0                 # identity input
+        g[5] = g[4]              # repeated point
+    exp = oracle.g_to_lagrange(g, k)
+    d_g = _dev(cq, g)
+    d_o = _dev(cq, np.zeros((n, 8), np.uint64))
+    cq._lib.check(lib.cqb_g_to_lagrange_dev(d_g, k, d_o))
+    assert np.array_equal(_host(cq, d_o, (n, 8)), exp)
+    cq._lib.check(lib.cqb_dev_free(d_g))
+    cq._lib.check(lib.cqb_dev_free(d_o))
+
+
+def test_downsize_matches_fresh_setup(cq, oracle):
+    """poly/kzg/commitment.rs:482-490: downsize(k') of a k-params equals setup(k') with the same toxic waste"""
+    s = oracle.synth_scalars(0xD5, 1)[0]
+    big = cq.ParamsKZG.setup_from_toxic_waste(10, s, precompute=False)
+    small = cq.ParamsKZG.setup_from_toxic_waste(7, s, precompute=False)
+    big.downsize(7)
+    assert big.k == 7 and big.n == 128
+    assert np.array_equal(big.g.to_host(), small.g.to_host())
+    assert np.array_equal(big.g_lagrange.to_host(), small.g_lagrange.to_host())
+    big.free()
+    small.free()

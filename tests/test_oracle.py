@@ -291,3 +291,11 @@ def test_synth_inputs(oracle):
     assert P.g1_affine_to_ints(b1[5])[0] == P.g1_mul(P.G1_GEN, (s0 + 5 * dd) % P.R_MOD)
     assert len({bytes(r) for r in b1}) == 2050
     assert np.array_equal(O.synth_scalars(5, 10)[3:], O.synth_scalars(5, 7, start=3))
+
+
+def test_g_to_lagrange_consistent_with_setup(oracle):
+    """arithmetic.rs:277-301 applied to g of a toxic-waste SRS reproduces that SRS's g_lagrange (what downsize relies on)"""
+    for k in (0, 1, 3, 5):
+        s = oracle.synth_scalars(0xC0 + k, 1)[0]
+        g, gl = oracle.params_setup(k, s)
+        assert np.array_equal(oracle.g_to_lagrange(g, k), gl)
