@@ -119,6 +119,10 @@ CQB_API int cqb_synth_bases_dev(uint64_t seed, size_t start, size_t n, void* d_o
  * d_g[i] = [s^i]G, d_g_lagrange[i] = [(s^n - 1)/n * w^i/(s - w^i)]G for n = 2^k, affine, 64 B each, written to device
  * memory (register them with cqb_bases_register_device — the SRS never has to exist on the host). */
 CQB_API int cqb_srs_setup_dev(uint32_t k, const uint64_t s[4], void* d_g, void* d_g_lagrange);
+/* G1 parts of TableSRS::setup_from_toxic_waste (poly/kzg/commitment.rs:73-178) for a table SRS of 2^log_len powers:
+ * g1, g1_lagrange and g_lagrange_opening_at_0[i] = [(L_i(x) - L_i(0))/x]_1 (:143-170), what the CQ prover's m / A / A_0
+ * commitments index into (plonk/static_lookup/prover.rs:167-170, 245-257) */
+CQB_API int cqb_table_srs_setup_dev(uint32_t log_len, const uint64_t s[4], void* d_g1, void* d_g1_lagrange, void* d_opening_at_0);
 /* g_to_lagrange (halo2_proofs/src/arithmetic.rs:277-301): radix-2 FFT over G1 of the first 2^k monomial SRS points, scaled
  * by 1/n and normalised -> the Lagrange SRS; what ParamsKZG::downsize needs (poly/kzg/commitment.rs:482-490).
  * d_g and d_out: 2^k affine points each, must not alias. */

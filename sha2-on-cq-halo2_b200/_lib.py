@@ -46,6 +46,7 @@ SYMBOLS = [
     ("cqb_synth_scalars_dev", _int, [_u64, _sz, _sz, _vp]),
     ("cqb_synth_bases_dev", _int, [_u64, _sz, _sz, _vp]),
     ("cqb_srs_setup_dev", _int, [_u32, u64p, _vp, _vp]),
+    ("cqb_table_srs_setup_dev", _int, [_u32, u64p, _vp, _vp, _vp]),
     ("cqb_g1_generator_mul_dev", _int, [_vp, _sz, _vp]),
     ("cqb_g_to_lagrange_dev", _int, [_vp, _u32, _vp]),
     ("cqb_fr_batch_invert_dev", _int, [_vp, _sz]),

@@ -526,7 +526,13 @@ int cqb_srs_setup_dev(uint32_t k, const uint64_t s[4], void* d_g, void* d_g_lagr
     LOCK;
     CQB_TRY(require_init());
     if (!s || !d_g || !d_g_lagrange) return fail(CQB_E_BAD_ARG, "cqb_srs_setup_dev: NULL argument");
-    return srs_setup_run(k, s, d_g, d_g_lagrange);
+    return srs_setup_run(k, s, d_g, d_g_lagrange, nullptr);
+}
+int cqb_table_srs_setup_dev(uint32_t log_len, const uint64_t s[4], void* d_g1, void* d_g1_lagrange, void* d_opening_at_0) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!s || !d_g1 || !d_g1_lagrange || !d_opening_at_0) return fail(CQB_E_BAD_ARG, "cqb_table_srs_setup_dev: NULL argument");
+    return srs_setup_run(log_len, s, d_g1, d_g1_lagrange, d_opening_at_0);
 }
 int cqb_g_to_lagrange_dev(const void* d_g, uint32_t k, void* d_out) {
     LOCK;

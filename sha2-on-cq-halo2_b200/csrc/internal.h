@@ -54,7 +54,7 @@ void ecntt_release_all();
 int fr_powers_run(const uint64_t base[4], size_t count, void* d_out);  // defined in ntt.cu
 int fr_batch_invert_run(void* d_a, size_t n);
 int g1_generator_mul_run(const void* d_scalars, size_t n, void* d_out);
-int srs_setup_run(uint32_t k, const uint64_t s_limbs[4], void* d_g, void* d_g_lagrange);
+int srs_setup_run(uint32_t k, const uint64_t s_limbs[4], void* d_g, void* d_g_lagrange, void* d_opening_at_0);
 void srs_release_all();
 
 // ---- gen.cu ----

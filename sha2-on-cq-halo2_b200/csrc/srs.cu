@@ -76,6 +76,14 @@ __global__ void srs_lagrange_scalar_kernel(const uint4* __restrict__ w, uint4* _
     s_st_fr(dinv_inout + 2 * i, v);
 }
 
+// o[i] = l[i] * winv[i] - c   (reference commitment.rs:146-168: l_i * w^-i - [x^(N-1)]/N, as a scalar of G)
+__global__ void srs_opening_scalar_kernel(const uint4* __restrict__ l, uint4* __restrict__ winv_inout, size_t n, Fr c) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr v = fp_sub<FrP>(fp_mul<FrP>(s_ld_fr(l + 2 * i), s_ld_fr(winv_inout + 2 * i)), c);
+    s_st_fr(winv_inout + 2 * i, v);
+}
+
 // ---- fixed-base table: T[w][d-1] = d * B_w, B_w = 2^(16 w) G, d = 1..32768 --------------------------------------------
 constexpr int FB_C = 16, FB_WIN = 16, FB_NB = 1 << (FB_C - 1), FB_RUN = 64;
 __global__ void __launch_bounds__(128) fb_table_kernel(const uint4* __restrict__ rows, uint4* __restrict__ table, uint4* __restrict__ tmp) {
@@ -228,15 +236,17 @@ int g1_generator_mul_run(const void* d_scalars, size_t n, void* d_out) {
     return 0;
 }
 
-// commitment.rs:209-276: g and g_lagrange for n = 2^k from the toxic waste s (Montgomery limbs)
-int srs_setup_run(uint32_t k, const uint64_t s_limbs[4], void* d_g, void* d_g_lagrange) {
+// commitment.rs:209-276: g and g_lagrange for n = 2^k from the toxic waste s (Montgomery limbs); with d_opening_at_0 also
+// TableSRS's g_lagrange_opening_at_0 (commitment.rs:143-170): [(L_i(x) - L_i(0))/x]_1 = w^-i [L_i(x)]_1 - (1/N) [x^(N-1)]_1
+int srs_setup_run(uint32_t k, const uint64_t s_limbs[4], void* d_g, void* d_g_lagrange, void* d_opening_at_0) {
     if (k > 28) return fail(CQB_E_BAD_SIZE, "k = %u exceeds Fr::S = 28 (commitment.rs:212)", k);
     cudaStream_t st = ctx().stream;
     size_t n = (size_t)1 << k;
     Fr s = fr_from_u64x4(s_limbs);
-    CQB_TRY(g_srs_vec.ensure(n * 32 * 2));
+    CQB_TRY(g_srs_vec.ensure(n * 32 * 3));
     void* d_pow = g_srs_vec.p;
     void* d_aux = (char*)g_srs_vec.p + n * 32;
+    void* d_aux2 = (char*)g_srs_vec.p + 2 * n * 32;
     // g[i] = [s^i] G
     CQB_TRY(fr_powers_run(s_limbs, n, d_pow));
     CQB_TRY(g1_generator_mul_run(d_pow, n, d_g));
@@ -264,6 +274,17 @@ int srs_setup_run(uint32_t k, const uint64_t s_limbs[4], void* d_g, void* d_g_la
     srs_lagrange_scalar_kernel<<<grid, 256, 0, st>>>((const uint4*)d_pow, (uint4*)d_aux, n, mult);
     CQB_LAUNCHED();
     CQB_TRY(g1_generator_mul_run(d_aux, n, d_g_lagrange));
+    if (d_opening_at_0) {
+        Fr root_inv = fp_inv<FrP>(root);
+        uint64_t ri_limbs[4];
+        for (int i = 0; i < 4; i++) ri_limbs[i] = (uint64_t)root_inv.l[2 * i] | ((uint64_t)root_inv.l[2 * i + 1] << 32);
+        CQB_TRY(fr_powers_run(ri_limbs, n, d_aux2));  // w^-i  (commitment.rs:146-150 successors(..).batch_invert())
+        // c = s^(N-1) / N : s^N / s ... computed as s_n * s^-1 * n_inv
+        Fr c = fp_mul<FrP>(fp_mul<FrP>(s_n, fp_inv<FrP>(s)), n_inv);
+        srs_opening_scalar_kernel<<<grid, 256, 0, st>>>((const uint4*)d_aux, (uint4*)d_aux2, n, c);
+        CQB_LAUNCHED();
+        CQB_TRY(g1_generator_mul_run(d_aux2, n, d_opening_at_0));
+    }
     CQB_CUDA(cudaGetLastError());
     return 0;
 }

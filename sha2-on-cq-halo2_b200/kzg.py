@@ -176,8 +176,32 @@ class TableSRS:
         self.g1 = DeviceBases(g1)
         self.g1_lagrange = DeviceBases(g1_lagrange)
         self.g_lagrange_opening_at_0 = DeviceBases(g_lagrange_opening_at_0)
+        self._dev_alloc = None
+
+    @classmethod
+    def setup_from_toxic_waste(cls, max_g1_power, s, precompute=None):
+        """reference commitment.rs:73-178 (G1 parts; the G2 powers are verifier/keygen-side): generated on the device"""
+        g1_len = max_g1_power + 1
+        assert g1_len & (g1_len - 1) == 0, "assert!(is_pow_2(g1_len))"  # commitment.rs:77
+        log_len = g1_len.bit_length() - 1
+        lib = _lib.lib()
+        d = ctypes.c_void_p()
+        _lib.check(lib.cqb_dev_alloc(3 * g1_len * 64, ctypes.byref(d)))
+        _lib.check(lib.cqb_table_srs_setup_dev(log_len, _lib.p64(_lib.fr_limbs(s)), d, ctypes.c_void_p(d.value + g1_len * 64),
+                                               ctypes.c_void_p(d.value + 2 * g1_len * 64)))
+        _lib.check(lib.cqb_sync())
+        self = cls.__new__(cls)
+        self.size = g1_len
+        self.g1 = DeviceBases.adopt(d.value, g1_len, precompute)
+        self.g1_lagrange = DeviceBases.adopt(d.value + g1_len * 64, g1_len, precompute)
+        self.g_lagrange_opening_at_0 = DeviceBases.adopt(d.value + 2 * g1_len * 64, g1_len, precompute)
+        self._dev_alloc = d
+        return self
 
     def free(self):
         self.g1.free()
         self.g1_lagrange.free()
         self.g_lagrange_opening_at_0.free()
+        if self._dev_alloc is not None:
+            _lib.check(_lib.lib().cqb_dev_free(self._dev_alloc))
+            self._dev_alloc = None

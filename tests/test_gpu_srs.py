@@ -160,3 +160,15 @@ def test_downsize_matches_fresh_setup(cq, oracle):
     assert np.array_equal(big.g_lagrange.to_host(), small.g_lagrange.to_host())
     big.free()
     small.free()
+
+
+@pytest.mark.parametrize("N", [2, 16, 64])
+def test_table_srs_setup_matches_reference(cq, oracle, N):
+    """poly/kzg/commitment.rs:73-178 TableSRS::setup_from_toxic_waste, G1 parts incl. g_lagrange_opening_at_0"""
+    s = oracle.synth_scalars(0xC7 + N, 1)[0]
+    g1, gl, op0 = oracle.table_srs_setup(N, s)
+    t = cq.TableSRS.setup_from_toxic_waste(N - 1, s, precompute=False)
+    assert np.array_equal(t.g1.to_host(), g1)
+    assert np.array_equal(t.g1_lagrange.to_host(), gl)
+    assert np.array_equal(t.g_lagrange_opening_at_0.to_host(), op0)
+    t.free()
