@@ -127,6 +127,12 @@ CQB_API int cqb_table_srs_setup_dev(uint32_t log_len, const uint64_t s[4], void*
  * by 1/n and normalised -> the Lagrange SRS; what ParamsKZG::downsize needs (poly/kzg/commitment.rs:482-490).
  * d_g and d_out: 2^k affine points each, must not alias. */
 CQB_API int cqb_g_to_lagrange_dev(const void* d_g, uint32_t k, void* d_out);
+/* CQ table preprocessing: all N = 2^log_n cached quotient commitments of StaticTableValues::new
+ * (plonk/static_lookup.rs:77-126): qs[i] = [ (T(X) - T(w^i))/(X - w^i) * w^i/N ]_1, T given by its N coefficients
+ * (= ifft of the table values, :99-105), d_srs_g1 = the first N powers [x^j]_1. The reference runs N kate_divisions and N
+ * MSMs of N-1 points (O(N^2), "TODO: THIS SHOULD BE DONE WITH FK METHOD" :107); this is the FK algorithm: three G1
+ * EC-NTTs (sizes 2N, 2N, N) + 3N scalar multiplications, O(N log N). Output: N affine points (device). */
+CQB_API int cqb_cq_table_qs_dev(const void* d_table_coeffs, uint32_t log_n, const void* d_srs_g1, void* d_qs_out);
 /* out[i] = [scalars[i]] G (fixed-base batch multiplication by the bn256 generator (1,2)), affine */
 CQB_API int cqb_g1_generator_mul_dev(const void* d_scalars, size_t n, void* d_out);
 /* in place a[i] <- 1/a[i], zeros stay zero: ff::BatchInvert as used at poly/domain.rs:118-125, static_lookup/prover.rs:261-269 */

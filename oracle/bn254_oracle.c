@@ -806,3 +806,62 @@ API void oracle_g_to_lagrange(const uint64_t* g_affine, uint32_t k, uint64_t* ou
     g1j_batch_normalize(p, (g1a*)out_affine, n);         /* :292-298 */
     free(p);
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * eval_polynomial / kate_division — halo2_proofs/src/arithmetic.rs:304-329, 351-387 (serial forms)
+ * ------------------------------------------------------------------------------------------------------------------ */
+static fe eval_polynomial(const fe* poly, size_t n, fe point) { /* :305-309 Horner fold from the top coefficient */
+    fe acc = fr_zero();
+    for (size_t i = n; i-- > 0;) acc = fr_add(fr_mul(acc, point), poly[i]);
+    return acc;
+}
+/* q has n-1 entries: a(X) - a(b) = q(X) (X - b) */
+static void kate_division(const fe* a, size_t n, fe b, fe* q) { /* :351-368 */
+    fe nb = fr_neg(b);
+    fe tmp = fr_zero();
+    for (size_t k = n - 1; k-- > 0;) {
+        fe lead = fr_sub(a[k + 1], tmp);
+        q[k] = lead;
+        tmp = fr_mul(lead, nb);
+    }
+}
+API void oracle_eval_polynomial(const uint64_t* poly, size_t n, const uint64_t* point, uint64_t* out) {
+    fe p; memcpy(&p, point, 32);
+    fe r = eval_polynomial((const fe*)poly, n, p);
+    memcpy(out, &r, 32);
+}
+API void oracle_kate_division(const uint64_t* a, size_t n, const uint64_t* b, uint64_t* q) {
+    fe bb; memcpy(&bb, b, 32);
+    kate_division((const fe*)a, n, bb, (fe*)q);
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * StaticTableValues::new — halo2_proofs/src/plonk/static_lookup.rs:77-126: the cached quotient commitments `qs` of the
+ * CQ argument: table_coeffs = ifft(values); for every root g_i = w^i: quotient = kate_division(table_coeffs, g_i) scaled
+ * by g_i / N; qs[i] = best_multiexp(quotient, srs_g1[..N-1]). O(N^2) ("TODO: THIS SHOULD BE DONE WITH FK METHOD" :107).
+ * ------------------------------------------------------------------------------------------------------------------ */
+API void oracle_cq_table_qs(const uint64_t* values, size_t size, const uint64_t* srs_g1, size_t threads, uint64_t* qs_affine) {
+    uint32_t k = log2_floor(size);
+    oracle_domain_t d;
+    oracle_domain_new(2, k, &d);
+    fe n_inv = fr_invert(fr_from_u64((uint64_t)size));
+    fe* coeffs = (fe*)malloc(sizeof(fe) * size);
+    memcpy(coeffs, values, sizeof(fe) * size);
+    domain_ifft(coeffs, d.omega_inv, k, d.ifft_divisor, threads); /* :99-105 */
+    fe* quot = (fe*)malloc(sizeof(fe) * (size > 1 ? size - 1 : 1));
+    fe gi = fr_one();
+    for (size_t i = 0; i < size; i++) { /* :108-119 */
+        g1j acc = g1j_identity();
+        if (size > 1) {
+            kate_division(coeffs, size, gi, quot);
+            fe sc = fr_mul(gi, n_inv);
+            for (size_t j = 0; j + 1 < size; j++) quot[j] = fr_mul(quot[j], sc); /* v * g_i * n_inv */
+            acc = best_multiexp(quot, (const g1a*)srs_g1, size - 1, threads);
+        }
+        g1a a = g1j_to_affine(&acc);
+        memcpy(qs_affine + 8 * i, &a, 64);
+        gi = fr_mul(gi, d.omega);
+    }
+    free(quot);
+    free(coeffs);
+}

@@ -304,3 +304,30 @@ def g_to_lagrange(g_affine, k):
     out = np.zeros((1 << k, 8), np.uint64)
     lib().oracle_g_to_lagrange(_p(g_affine), ctypes.c_uint32(k), _p(out))
     return out
+
+
+def eval_polynomial(poly, point):
+    """reference arithmetic.rs:304-329"""
+    poly = _c(poly, 4)
+    out = np.zeros(4, np.uint64)
+    lib().oracle_eval_polynomial(_p(poly), ctypes.c_size_t(poly.shape[0]), _p(_c(point, 4)), _p(out))
+    return out
+
+
+def kate_division(a, b):
+    """reference arithmetic.rs:351-387: (a(X) - a(b)) / (X - b), n-1 coefficients"""
+    a = _c(a, 4)
+    q = np.zeros((a.shape[0] - 1, 4), np.uint64)
+    lib().oracle_kate_division(_p(a), ctypes.c_size_t(a.shape[0]), _p(_c(b, 4)), _p(q))
+    return q
+
+
+def cq_table_qs(values, srs_g1, threads=None):
+    """reference plonk/static_lookup.rs:77-126 StaticTableValues::new: the N cached quotient commitments (affine)"""
+    values = _c(values, 4)
+    srs_g1 = _c(srs_g1, 8)
+    n = values.shape[0]
+    assert n & (n - 1) == 0 and srs_g1.shape[0] >= max(n - 1, 1)
+    out = np.zeros((n, 8), np.uint64)
+    lib().oracle_cq_table_qs(_p(values), ctypes.c_size_t(n), _p(srs_g1), ctypes.c_size_t(threads or hw_threads()), _p(out))
+    return out

@@ -49,6 +49,7 @@ SYMBOLS = [
     ("cqb_table_srs_setup_dev", _int, [_u32, u64p, _vp, _vp, _vp]),
     ("cqb_g1_generator_mul_dev", _int, [_vp, _sz, _vp]),
     ("cqb_g_to_lagrange_dev", _int, [_vp, _u32, _vp]),
+    ("cqb_cq_table_qs_dev", _int, [_vp, _u32, _vp, _vp]),
     ("cqb_fr_batch_invert_dev", _int, [_vp, _sz]),
     ("cqb_fr_powers_dev", _int, [u64p, _sz, _vp]),
     ("cqb_dev_alloc", _int, [_sz, ctypes.POINTER(_vp)]),

@@ -36,3 +36,44 @@ def commit_b0_and_p(params, b0_bound_bases, b_coeffs):
     b0_full = np.concatenate([b0, np.zeros((1, 4), np.uint64)])
     b0_cm = params.commit(b0_full)
     return b0_cm, p_cm
+
+
+class StaticTableValues:
+    """reference plonk/static_lookup.rs:69-126: the per-table cached quotient commitments `qs` of the CQ argument.
+
+    The reference computes them with N kate_divisions and N MSMs of N-1 points (O(N^2); ":107 TODO: THIS SHOULD BE DONE
+    WITH FK METHOD"). Here: ifft of the values on the device, then the FK algorithm (cqb_cq_table_qs_dev: three G1
+    EC-NTTs), O(N log N). `qs` stays resident as a DeviceBases so that Q_A commitments (prover.rs:245-257) index it."""
+
+    def __init__(self, values, srs_g1):
+        import ctypes
+
+        from . import _lib
+        from .domain import EvaluationDomain
+
+        values = np.ascontiguousarray(values, dtype=np.uint64)
+        size = values.shape[0]
+        assert size & (size - 1) == 0, "assert!(is_pow_2(size))"          # static_lookup.rs:80
+        assert len({bytes(v) for v in values}) == size, "table is all unique values"  # :82-85
+        assert isinstance(srs_g1, DeviceBases) and srs_g1.n >= size and hasattr(srs_g1, "_device_ptr"), \
+            "srs_g1 must be a device-resident SRS with at least `size` powers"
+        self.size = size
+        self.value_index_mapping = {bytes(v): i for i, v in enumerate(values)}
+        k = size.bit_length() - 1
+        lib = _lib.lib()
+        dom = EvaluationDomain(2, k)
+        d_vals = ctypes.c_void_p()
+        _lib.check(lib.cqb_dev_alloc(size * 32 + size * 64, ctypes.byref(d_vals)))
+        d_qs = ctypes.c_void_p(d_vals.value + size * 32)
+        _lib.check(lib.cqb_memcpy_h2d(d_vals, values.ctypes.data_as(ctypes.c_void_p), size * 32))
+        _lib.check(lib.cqb_intt_bn254_fr_dev(d_vals, _lib.p64(dom.omega_inv), _lib.p64(dom.ifft_divisor), k))  # :99-105
+        _lib.check(lib.cqb_cq_table_qs_dev(d_vals, k, ctypes.c_void_p(srs_g1._device_ptr), d_qs))
+        _lib.check(lib.cqb_sync())
+        self._dev_alloc = d_vals
+        self.qs = DeviceBases.adopt(d_qs.value, size, precompute=False)
+
+    def free(self):
+        from . import _lib
+
+        self.qs.free()
+        _lib.check(_lib.lib().cqb_dev_free(self._dev_alloc))

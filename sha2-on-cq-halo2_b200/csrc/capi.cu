@@ -540,6 +540,12 @@ int cqb_g_to_lagrange_dev(const void* d_g, uint32_t k, void* d_out) {
     if (!d_g || !d_out || d_g == d_out) return fail(CQB_E_BAD_ARG, "cqb_g_to_lagrange_dev: NULL or aliasing arguments");
     return g_to_lagrange_run(d_g, k, d_out);
 }
+int cqb_cq_table_qs_dev(const void* d_table_coeffs, uint32_t log_n, const void* d_srs_g1, void* d_qs_out) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!d_table_coeffs || !d_srs_g1 || !d_qs_out) return fail(CQB_E_BAD_ARG, "cqb_cq_table_qs_dev: NULL argument");
+    return cq_table_qs_run(d_table_coeffs, log_n, d_srs_g1, d_qs_out);
+}
 int cqb_g1_generator_mul_dev(const void* d_scalars, size_t n, void* d_out) {
     LOCK;
     CQB_TRY(require_init());

@@ -48,6 +48,7 @@ int msm_phase_ms(float* ms, int cap);
 // ---- ecntt.cu ----
 int ntt_get_twiddles(const uint64_t omega[4], uint32_t log_n, const void** d_table);  // defined in ntt.cu (cached table)
 int g_to_lagrange_run(const void* d_g, uint32_t k, void* d_out);
+int cq_table_qs_run(const void* d_table_coeffs, uint32_t log_n, const void* d_srs_g1, void* d_qs_out);
 void ecntt_release_all();
 
 // ---- srs.cu ----

@@ -60,6 +60,13 @@ class CudaBackend:
                                                    ctypes.byref(self._inf)))
         return self._out.copy(), self._inf.value
 
+    def msm_sparse(self, idx, scalars):
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
+        _lib.check(_lib.lib().cqb_msm_bn254_g1_sparse(self.handle, idx.ctypes.data_as(_lib.u32p), _lib.p64(scalars), idx.shape[0],
+                                                      _lib.p64(self._out), ctypes.byref(self._inf)))
+        return self._out.copy(), self._inf.value
+
     def sum_affine(self, points):
         points = np.ascontiguousarray(points, dtype=np.uint64)
         out = np.zeros(8, np.uint64)
@@ -97,6 +104,14 @@ class ShardedMSM:
 
     def msm(self, local_scalars):
         partial, _ = self.backend.msm(local_scalars)
+        return self.fold(partial)
+
+    def msm_sparse(self, idx, scalars, shard_start):
+        """CQ sparse commitments (m, A, Q_A, A_0) over a table SRS sharded by index range: this rank keeps
+        the entries whose table index falls in its shard [shard_start, shard_start + backend.n) and rebases them"""
+        idx = np.asarray(idx, dtype=np.int64)
+        keep = (idx >= shard_start) & (idx < shard_start + self.backend.n)
+        partial, _ = self.backend.msm_sparse((idx[keep] - shard_start).astype(np.uint32), np.ascontiguousarray(scalars)[keep])
         return self.fold(partial)
 
     def msm_dev(self, device_ptr, m):

@@ -172,3 +172,42 @@ def test_table_srs_setup_matches_reference(cq, oracle, N):
     assert np.array_equal(t.g1_lagrange.to_host(), gl)
     assert np.array_equal(t.g_lagrange_opening_at_0.to_host(), op0)
     t.free()
+
+
+@pytest.mark.parametrize("N", [2, 4, 16, 64])
+def test_cq_table_qs_fk_matches_reference(cq, oracle, N):
+    """SURVEY §8(f) row 2: StaticTableValues::new's qs (plonk/static_lookup.rs:77-126) — FK on the device vs the oracle's
+    restatement of the reference's O(N^2) loop (N kate_divisions + N MSMs)"""
+    s = oracle.synth_scalars(0xF4 + N, 1)[0]
+    srs = cq.TableSRS.setup_from_toxic_waste(N - 1, s, precompute=False)
+    rng = np.random.default_rng(N)
+    vals = P.fr_array_from_ints([int(v) for v in rng.choice(1 << 30, N, replace=False)])
+    exp = oracle.cq_table_qs(vals, srs.g1.to_host(), 4)
+    tv = cq.cq.StaticTableValues(vals, srs.g1)
+    assert np.array_equal(tv.qs.to_host(), exp)
+    tv.free()
+    srs.free()
+
+
+def test_cq_table_qs_large_n_spot_check(cq, oracle):
+    """N = 2^12: the oracle's O(N^2) loop would take minutes; spot-check a few rows against one kate_division + MSM each"""
+    N, k = 1 << 12, 12
+    s = oracle.synth_scalars(0xF5, 1)[0]
+    srs = cq.TableSRS.setup_from_toxic_waste(N - 1, s, precompute=False)
+    vals = oracle.synth_scalars(0xF6, N)
+    tv = cq.cq.StaticTableValues(vals, srs.g1)
+    qs = tv.qs.to_host()
+    g1 = srs.g1.to_host()
+    od = oracle.domain_new(2, k)
+    coeffs = oracle.lagrange_to_coeff(od, vals)
+    w = P.omega_for(k)
+    n_inv = pow(N, -1, P.R_MOD)
+    for i in (0, 1, 77, N - 1):
+        gi = pow(w, i, P.R_MOD)
+        q = oracle.kate_division(coeffs, P.int_to_limbs(P.to_mont(gi, P.R_MOD)))
+        sc = P.int_to_limbs(P.to_mont(gi * n_inv % P.R_MOD, P.R_MOD))
+        q = np.stack([oracle.fr_op("mul", row, sc) for row in q])
+        _, exp = oracle.best_multiexp(q, g1[: N - 1], 8)
+        assert np.array_equal(qs[i], exp), i
+    tv.free()
+    srs.free()

@@ -39,6 +39,10 @@ def _worker(rank, world, port, n, q):
             _, aff = O.best_multiexp(scalars, self.bases, 1)
             return aff, int(not aff.any())
 
+        def msm_sparse(self, idx, scalars):
+            aff = O.sparse_commit(self.bases, idx, scalars) if len(idx) else np.zeros(8, np.uint64)
+            return aff, int(not aff.any())
+
         def sum_affine(self, pts):
             acc = np.zeros(12, np.uint64)
             for p in pts:
@@ -60,6 +64,14 @@ def _worker(rank, world, port, n, q):
     z = ShardedMSM(OracleBackend(bases[start:start + cnt]), rank, world)
     zero = z.msm(np.zeros((cnt, 4), np.uint64))
     ok = ok and zero.is_identity
+    # sparse CQ commitment over the same sharded set
+    rng = np.random.default_rng(3)
+    sidx = np.sort(rng.choice(n, n // 3, replace=False)).astype(np.uint32)
+    ssc = O.synth_scalars(77, sidx.shape[0])
+    got_s = ShardedMSM(OracleBackend(bases[start:start + cnt]), rank, world)
+    got_s.backend.n = cnt
+    sp = got_s.msm_sparse(sidx, ssc, start)
+    ok = ok and bool(np.array_equal(sp.to_affine(), O.sparse_commit(bases, sidx, ssc)))
     q.put((rank, ok, start, cnt))
     dist.barrier()
     dist.destroy_process_group()
