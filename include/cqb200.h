@@ -135,6 +135,11 @@ CQB_API int cqb_g_to_lagrange_dev(const void* d_g, uint32_t k, void* d_out);
 CQB_API int cqb_cq_table_qs_dev(const void* d_table_coeffs, uint32_t log_n, const void* d_srs_g1, void* d_qs_out);
 /* out[i] = [scalars[i]] G (fixed-base batch multiplication by the bn256 generator (1,2)), affine */
 CQB_API int cqb_g1_generator_mul_dev(const void* d_scalars, size_t n, void* d_out);
+/* eval_polynomial (halo2_proofs/src/arithmetic.rs:304-329): out = sum_i coeffs[i] point^i, coefficients device-resident */
+CQB_API int cqb_eval_polynomial_dev(const void* d_coeffs, size_t n, const uint64_t point[4], uint64_t out[4]);
+/* kate_division (arithmetic.rs:351-387): d_q[0..n-1) = (a(X) - a(b)) / (X - b); as used by the multiopen provers
+ * (poly/kzg/multiopen/gwc/prover.rs:80-86) and the CQ table preprocessing; d_q must not alias d_a */
+CQB_API int cqb_kate_division_dev(const void* d_a, size_t n, const uint64_t b[4], void* d_q);
 /* in place a[i] <- 1/a[i], zeros stay zero: ff::BatchInvert as used at poly/domain.rs:118-125, static_lookup/prover.rs:261-269 */
 CQB_API int cqb_fr_batch_invert_dev(void* d_a, size_t n);
 /* out[i] = base^i, i < n (the serial scans at arithmetic.rs:194-200, commitment.rs:153-156) */

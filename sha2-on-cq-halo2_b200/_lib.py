@@ -51,6 +51,8 @@ SYMBOLS = [
     ("cqb_g_to_lagrange_dev", _int, [_vp, _u32, _vp]),
     ("cqb_cq_table_qs_dev", _int, [_vp, _u32, _vp, _vp]),
     ("cqb_fr_batch_invert_dev", _int, [_vp, _sz]),
+    ("cqb_eval_polynomial_dev", _int, [_vp, _sz, u64p, u64p]),
+    ("cqb_kate_division_dev", _int, [_vp, _sz, u64p, _vp]),
     ("cqb_fr_powers_dev", _int, [u64p, _sz, _vp]),
     ("cqb_dev_alloc", _int, [_sz, ctypes.POINTER(_vp)]),
     ("cqb_dev_free", _int, [_vp]),

@@ -72,3 +72,46 @@ def best_fft(a, omega, log_n):
     assert a.shape[0] == 1 << log_n, "assert_eq!(n, 1 << log_n)"  # arithmetic.rs:184
     lib = _lib.lib()
     _lib.check(lib.cqb_ntt_bn254_fr(_lib.p64(a), _lib.p64(_lib.fr_limbs(omega)), log_n))
+
+
+def _with_device_copy(a):
+    lib = _lib.lib()
+    d = ctypes.c_void_p()
+    _lib.check(lib.cqb_dev_alloc(max(a.nbytes, 64), ctypes.byref(d)))
+    if a.nbytes:
+        _lib.check(lib.cqb_memcpy_h2d(d, a.ctypes.data_as(ctypes.c_void_p), a.nbytes))
+    return d
+
+
+def eval_polynomial(poly, point):
+    """reference arithmetic.rs:304-329: evaluates a polynomial in coefficient form at `point` -> (4,) uint64"""
+    poly = _as_fr(poly)
+    lib = _lib.lib()
+    d = _with_device_copy(poly)
+    out = np.zeros(4, np.uint64)
+    try:
+        _lib.check(lib.cqb_eval_polynomial_dev(d, poly.shape[0], _lib.p64(_lib.fr_limbs(point)), _lib.p64(out)))
+    finally:
+        _lib.check(lib.cqb_dev_free(d))
+    return out
+
+
+def kate_division(a, b):
+    """reference arithmetic.rs:351-387: divides a(X) by (X - b) with no remainder -> (n-1, 4) uint64"""
+    a = _as_fr(a)
+    n = a.shape[0]
+    assert n >= 1
+    lib = _lib.lib()
+    q = np.zeros((n - 1, 4), np.uint64)
+    if n == 1:
+        return q
+    d = _with_device_copy(a)
+    dq = ctypes.c_void_p()
+    _lib.check(lib.cqb_dev_alloc(q.nbytes, ctypes.byref(dq)))
+    try:
+        _lib.check(lib.cqb_kate_division_dev(d, n, _lib.p64(_lib.fr_limbs(b)), dq))
+        _lib.check(lib.cqb_memcpy_d2h(q.ctypes.data_as(ctypes.c_void_p), dq, q.nbytes))
+    finally:
+        _lib.check(lib.cqb_dev_free(d))
+        _lib.check(lib.cqb_dev_free(dq))
+    return q

@@ -142,6 +142,7 @@ void cqb_shutdown(void) {
     gen_release_all();
     srs_release_all();
     ecntt_release_all();
+    poly_release_all();
     if (g_copy_stream) {
         for (auto& e : g_copy_ev) cudaEventDestroy(e);
         cudaStreamDestroy(g_copy_stream);
@@ -551,6 +552,23 @@ int cqb_g1_generator_mul_dev(const void* d_scalars, size_t n, void* d_out) {
     CQB_TRY(require_init());
     if ((!d_scalars || !d_out) && n) return fail(CQB_E_BAD_ARG, "cqb_g1_generator_mul_dev: NULL argument");
     return g1_generator_mul_run(d_scalars, n, d_out);
+}
+int cqb_eval_polynomial_dev(const void* d_coeffs, size_t n, const uint64_t point[4], uint64_t out[4]) {
+    LOCK;
+    CQB_TRY(require_init());
+    if ((!d_coeffs && n) || !point || !out) return fail(CQB_E_BAD_ARG, "cqb_eval_polynomial_dev: NULL argument");
+    CQB_TRY(eval_polynomial_run(d_coeffs, n, point, g_out.p));
+    CQB_TRY(g_out_host.ensure(128));
+    CQB_CUDA(cudaMemcpyAsync(g_out_host.p, g_out.p, 32, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    memcpy(out, g_out_host.p, 32);
+    return 0;
+}
+int cqb_kate_division_dev(const void* d_a, size_t n, const uint64_t b[4], void* d_q) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!b || ((!d_a || !d_q) && n > 1) || (d_a == d_q && n > 1)) return fail(CQB_E_BAD_ARG, "cqb_kate_division_dev: NULL or aliasing arguments");
+    return kate_division_run(d_a, n, b, d_q);
 }
 int cqb_fr_batch_invert_dev(void* d_a, size_t n) {
     LOCK;

@@ -51,6 +51,11 @@ int g_to_lagrange_run(const void* d_g, uint32_t k, void* d_out);
 int cq_table_qs_run(const void* d_table_coeffs, uint32_t log_n, const void* d_srs_g1, void* d_qs_out);
 void ecntt_release_all();
 
+// ---- poly.cu ----
+int eval_polynomial_run(const void* d_coeffs, size_t n, const uint64_t point[4], void* d_out);
+int kate_division_run(const void* d_a, size_t n, const uint64_t b[4], void* d_q);
+void poly_release_all();
+
 // ---- srs.cu ----
 int fr_powers_run(const uint64_t base[4], size_t count, void* d_out);  // defined in ntt.cu
 int fr_batch_invert_run(void* d_a, size_t n);

@@ -211,3 +211,17 @@ def test_cq_table_qs_large_n_spot_check(cq, oracle):
         assert np.array_equal(qs[i], exp), i
     tv.free()
     srs.free()
+
+
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 4096, 4097, 300000])
+def test_eval_polynomial_and_kate_division(cq, oracle, n):
+    """arithmetic.rs:304-329 and :351-387 on the device vs the oracle's serial restatements"""
+    a = oracle.synth_scalars(0xE0 + n, n)
+    x = oracle.synth_scalars(0xE1, 1)[0]
+    assert np.array_equal(cq.eval_polynomial(a, x), oracle.eval_polynomial(a, x))
+    zero = np.zeros(4, np.uint64)
+    assert np.array_equal(cq.eval_polynomial(a, zero), a[0])
+    q = cq.kate_division(a, x)
+    assert q.shape == (n - 1, 4)
+    if n > 1:
+        assert np.array_equal(q, oracle.kate_division(a, x))
