@@ -145,6 +145,39 @@ CQB_API int cqb_fr_batch_invert_dev(void* d_a, size_t n);
 /* out[i] = base^i, i < n (the serial scans at arithmetic.rs:194-200, commitment.rs:153-156) */
 CQB_API int cqb_fr_powers_dev(const uint64_t base[4], size_t n, void* d_out);
 
+/* ---- evaluate_h on the device (halo2_proofs/src/plonk/evaluation.rs:285-551) ---------------------
+ * A GraphEvaluator (evaluation.rs:197-207) is passed serialised (host memory):
+ *   constants  : n_constants Fr (Montgomery limbs); rotations: n_rotations int32 (Rotation.0)
+ *   code       : the calculations in order, as 32-bit words. A ValueSource (:41-65) is 2 words
+ *                { kind | rotation_index << 8 , index }, kind = 0 Constant, 1 Intermediate, 2 Fixed, 3 Advice, 4 Instance,
+ *                5 Challenge, 6 Beta, 7 Gamma, 8 Theta, 9 Y, 10 PreviousValue (index = constant / intermediate / column /
+ *                challenge index). A Calculation (:114-132) is { op, target, operands... }, op = 0 Add(a,b), 1 Sub(a,b),
+ *                2 Mul(a,b), 3 Square(a), 4 Double(a), 5 Negate(a), 6 Horner(start, factor, nparts, parts...), 7 Store(a).
+ * Limits: <= 32 rotations, <= 512 intermediates. */
+typedef struct {
+    const uint64_t* constants; uint32_t n_constants;
+    const int32_t* rotations;  uint32_t n_rotations;
+    const uint32_t* code;      uint32_t code_words;
+    uint32_t n_calculations;   uint32_t num_intermediates;
+} cqb_graph_t;
+/* GraphEvaluator::evaluate (:718-775) for every row idx < size of the extended domain, in place on d_values
+ * (values[idx] is the PreviousValue and receives the result; custom gates :348-374). d_fixed / d_advice / d_instance: HOST
+ * arrays of DEVICE pointers to the coset evaluations (size Fr each). */
+CQB_API int cqb_graph_evaluate_dev(const cqb_graph_t* graph, const void* const* d_fixed, uint32_t n_fixed, const void* const* d_advice,
+                                   uint32_t n_advice, const void* const* d_instance, uint32_t n_instance, const uint64_t* challenges,
+                                   uint32_t n_challenges, const uint64_t beta[4], const uint64_t gamma[4], const uint64_t theta[4],
+                                   const uint64_t y[4], void* d_values, uint64_t size, int32_t rot_scale);
+/* the static-lookup (CQ) term (:533-548): values = values * y + (b_coset * (f_coset * l_active_row + beta) - 1) */
+CQB_API int cqb_cq_lookup_h_dev(void* d_values, const void* d_b_coset, const void* d_f_coset, const void* d_l_active_row,
+                                const uint64_t beta[4], const uint64_t y[4], uint64_t size);
+/* the permutation argument terms (:376-452); d_sets: nsets product cosets, d_columns / d_perm_cosets: ncols column value /
+ * permutation cosets grouped chunk_len per set (HOST arrays of DEVICE pointers) */
+CQB_API int cqb_permutation_h_dev(void* d_values, uint64_t size, int32_t rot_scale, int32_t last_rotation, uint32_t chunk_len,
+                                  const void* const* d_sets, uint32_t nsets, const void* const* d_columns,
+                                  const void* const* d_perm_cosets, uint32_t ncols, const void* d_l0, const void* d_l_last,
+                                  const void* d_l_active_row, const uint64_t beta[4], const uint64_t gamma[4], const uint64_t y[4],
+                                  const uint64_t extended_omega[4]);
+
 /* ---- plain device memory helpers so non-CUDA hosts (ctypes, the Rust shim) need no CUDA binding of their own ---- */
 CQB_API int cqb_dev_alloc(size_t bytes, void** d_out);
 CQB_API int cqb_dev_free(void* d);

@@ -865,3 +865,126 @@ API void oracle_cq_table_qs(const uint64_t* values, size_t size, const uint64_t*
     free(quot);
     free(coeffs);
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * evaluate_h pieces — halo2_proofs/src/plonk/evaluation.rs
+ *   GraphEvaluator::evaluate (:718-775) over the serialised graph (same word format the CUDA path takes, see
+ *   include/cqb200.h): ValueSource = 2 words {kind | rot_idx << 8, index}; kinds follow the enum order (:41-65);
+ *   Calculation = {op, target, ...} with op following the enum order (:114-132).
+ *   static-lookup (CQ) term (:533-548) and permutation term (:376-452).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+    const fe* constants; const int32_t* rotations; uint32_t n_rot; const uint32_t* code; uint32_t n_calc;
+    const fe* const* fixed; const fe* const* advice; const fe* const* instance; const fe* challenges;
+    fe beta, gamma, theta, y;
+} graph_ctx_t;
+
+static size_t get_rotation_idx(size_t idx, int32_t rot, int32_t rot_scale, int64_t isize) { /* :37-39 rem_euclid */
+    int64_t v = ((int64_t)idx + (int64_t)rot * rot_scale) % isize;
+    if (v < 0) v += isize;
+    return (size_t)v;
+}
+static fe vs_get(const graph_ctx_t* g, const uint32_t* w, const size_t* rots, const fe* inter, fe prev) { /* :69-109 */
+    uint32_t kind = w[0] & 0xff, rot = w[0] >> 8, idx = w[1];
+    switch (kind) {
+        case 0: return g->constants[idx];
+        case 1: return inter[idx];
+        case 2: return g->fixed[idx][rots[rot]];
+        case 3: return g->advice[idx][rots[rot]];
+        case 4: return g->instance[idx][rots[rot]];
+        case 5: return g->challenges[idx];
+        case 6: return g->beta;
+        case 7: return g->gamma;
+        case 8: return g->theta;
+        case 9: return g->y;
+        default: return prev;
+    }
+}
+API void oracle_graph_evaluate(const uint64_t* constants, const int32_t* rotations, uint32_t n_rot, const uint32_t* code, uint32_t n_calc,
+                               uint32_t num_intermediates, const uint64_t* const* fixed, const uint64_t* const* advice,
+                               const uint64_t* const* instance, const uint64_t* challenges, const uint64_t* bgty /* beta,gamma,theta,y */,
+                               uint64_t* values, size_t size, int32_t rot_scale) {
+    graph_ctx_t g;
+    g.constants = (const fe*)constants; g.rotations = rotations; g.n_rot = n_rot; g.code = code; g.n_calc = n_calc;
+    g.fixed = (const fe* const*)fixed; g.advice = (const fe* const*)advice; g.instance = (const fe* const*)instance;
+    g.challenges = (const fe*)challenges;
+    memcpy(&g.beta, bgty, 32); memcpy(&g.gamma, bgty + 4, 32); memcpy(&g.theta, bgty + 8, 32); memcpy(&g.y, bgty + 12, 32);
+    fe* inter = (fe*)malloc(sizeof(fe) * (num_intermediates ? num_intermediates : 1));
+    size_t* rots = (size_t*)malloc(sizeof(size_t) * (n_rot ? n_rot : 1));
+    fe* vals = (fe*)values;
+    for (size_t idx = 0; idx < size; idx++) {
+        for (uint32_t r = 0; r < n_rot; r++) rots[r] = get_rotation_idx(idx, rotations[r], rot_scale, (int64_t)size); /* :733-736 */
+        fe prev = vals[idx], last = fr_zero();
+        const uint32_t* pc = code;
+        for (uint32_t c = 0; c < n_calc; c++) { /* :739-757 */
+            uint32_t op = pc[0], target = pc[1];
+            fe r;
+            switch (op) { /* Calculation::evaluate :135-193 */
+                case 0: r = fr_add(vs_get(&g, pc + 2, rots, inter, prev), vs_get(&g, pc + 4, rots, inter, prev)); pc += 6; break;
+                case 1: r = fr_sub(vs_get(&g, pc + 2, rots, inter, prev), vs_get(&g, pc + 4, rots, inter, prev)); pc += 6; break;
+                case 2: r = fr_mul(vs_get(&g, pc + 2, rots, inter, prev), vs_get(&g, pc + 4, rots, inter, prev)); pc += 6; break;
+                case 3: r = fr_square(vs_get(&g, pc + 2, rots, inter, prev)); pc += 4; break;
+                case 4: r = fr_dbl(vs_get(&g, pc + 2, rots, inter, prev)); pc += 4; break;
+                case 5: r = fr_neg(vs_get(&g, pc + 2, rots, inter, prev)); pc += 4; break;
+                case 6: { /* Horner(start, parts, factor): words = start, factor, nparts, parts... */
+                    fe factor = vs_get(&g, pc + 4, rots, inter, prev);
+                    r = vs_get(&g, pc + 2, rots, inter, prev);
+                    uint32_t np = pc[6];
+                    for (uint32_t p = 0; p < np; p++) r = fr_add(fr_mul(r, factor), vs_get(&g, pc + 7 + 2 * p, rots, inter, prev));
+                    pc += 7 + 2 * np;
+                    break;
+                }
+                default: r = vs_get(&g, pc + 2, rots, inter, prev); pc += 4; break; /* Store */
+            }
+            inter[target] = r;
+            last = r;
+        }
+        vals[idx] = n_calc ? last : fr_zero(); /* :760-765 */
+    }
+    free(inter);
+    free(rots);
+}
+/* evaluation.rs:533-548: value = value * y + (b_coset * (f_coset * l_active_row + beta) - 1) */
+API void oracle_cq_lookup_h(uint64_t* values, const uint64_t* b_coset, const uint64_t* f_coset, const uint64_t* l_active_row,
+                            const uint64_t* beta_, const uint64_t* y_, size_t size) {
+    fe beta, y; memcpy(&beta, beta_, 32); memcpy(&y, y_, 32);
+    fe* v = (fe*)values; const fe* b = (const fe*)b_coset; const fe* f = (const fe*)f_coset; const fe* l = (const fe*)l_active_row;
+    for (size_t i = 0; i < size; i++)
+        v[i] = fr_add(fr_mul(v[i], y), fr_sub(fr_mul(b[i], fr_add(fr_mul(f[i], l[i]), beta)), fr_one()));
+}
+/* evaluation.rs:376-452 permutation constraints. sets: nsets product cosets; columns / perm cosets: ncols each, chunked by
+ * chunk_len per set */
+API void oracle_permutation_h(uint64_t* values, size_t size, int32_t rot_scale, int32_t last_rotation, uint32_t chunk_len,
+                              const uint64_t* const* sets, uint32_t nsets, const uint64_t* const* columns,
+                              const uint64_t* const* perm_cosets, uint32_t ncols, const uint64_t* l0_, const uint64_t* l_last_,
+                              const uint64_t* l_active_, const uint64_t* beta_, const uint64_t* gamma_, const uint64_t* y_,
+                              const uint64_t* extended_omega_) {
+    fe beta, gamma, y, ew; memcpy(&beta, beta_, 32); memcpy(&gamma, gamma_, 32); memcpy(&y, y_, 32); memcpy(&ew, extended_omega_, 32);
+    fe* v = (fe*)values; const fe* l0 = (const fe*)l0_; const fe* l_last = (const fe*)l_last_; const fe* l_active = (const fe*)l_active_;
+    fe one = fr_one(), delta = fr_delta();
+    fe delta_start = fr_mul(beta, fr_zeta()); /* :383 */
+    fe beta_term = fr_one();                  /* extended_omega^start, start = 0 (:390) */
+    for (size_t idx = 0; idx < size; idx++) {
+        size_t r_next = get_rotation_idx(idx, 1, rot_scale, (int64_t)size);
+        size_t r_last = get_rotation_idx(idx, last_rotation, rot_scale, (int64_t)size);
+        const fe* first = (const fe*)sets[0]; const fe* last = (const fe*)sets[nsets - 1];
+        v[idx] = fr_add(fr_mul(v[idx], y), fr_mul(fr_sub(one, first[idx]), l0[idx]));                                   /* :397-399 */
+        v[idx] = fr_add(fr_mul(v[idx], y), fr_mul(fr_sub(fr_mul(last[idx], last[idx]), last[idx]), l_last[idx]));       /* :402-406 */
+        for (uint32_t s = 1; s < nsets; s++)                                                                             /* :409-417 */
+            v[idx] = fr_add(fr_mul(v[idx], y), fr_mul(fr_sub(((const fe*)sets[s])[idx], ((const fe*)sets[s - 1])[r_last]), l0[idx]));
+        fe current_delta = fr_mul(delta_start, beta_term);                                                               /* :423 */
+        for (uint32_t s = 0; s < nsets; s++) {                                                                           /* :424-449 */
+            uint32_t c0 = s * chunk_len, c1 = c0 + chunk_len < ncols ? c0 + chunk_len : ncols;
+            fe left = ((const fe*)sets[s])[r_next];
+            for (uint32_t c = c0; c < c1; c++)
+                left = fr_mul(left, fr_add(fr_add(((const fe*)columns[c])[idx], fr_mul(beta, ((const fe*)perm_cosets[c])[idx])), gamma));
+            fe right = ((const fe*)sets[s])[idx];
+            for (uint32_t c = c0; c < c1; c++) {
+                right = fr_mul(right, fr_add(fr_add(((const fe*)columns[c])[idx], current_delta), gamma));
+                current_delta = fr_mul(current_delta, delta);
+            }
+            v[idx] = fr_add(fr_mul(v[idx], y), fr_mul(fr_sub(left, right), l_active[idx]));
+        }
+        beta_term = fr_mul(beta_term, ew);                                                                               /* :450 */
+    }
+}

@@ -331,3 +331,48 @@ def cq_table_qs(values, srs_g1, threads=None):
     out = np.zeros((n, 8), np.uint64)
     lib().oracle_cq_table_qs(_p(values), ctypes.c_size_t(n), _p(srs_g1), ctypes.c_size_t(threads or hw_threads()), _p(out))
     return out
+
+
+def _ptr_array(arrs):
+    keep = [np.ascontiguousarray(a, dtype=np.uint64) for a in arrs]
+    arr = (ctypes.c_void_p * max(len(keep), 1))(*[a.ctypes.data_as(ctypes.c_void_p) for a in keep])
+    return arr, keep
+
+
+def graph_evaluate(constants, rotations, code, n_calc, num_intermediates, fixed, advice, instance, challenges, beta, gamma, theta, y,
+                   values, rot_scale):
+    """reference plonk/evaluation.rs:718-775 GraphEvaluator::evaluate over all rows, on the serialised graph"""
+    values = np.array(_c(values, 4), copy=True)
+    constants = _c(constants, 4)
+    rotations = np.ascontiguousarray(rotations, dtype=np.int32)
+    code = np.ascontiguousarray(code, dtype=np.uint32)
+    fa, k1 = _ptr_array(fixed)
+    aa, k2 = _ptr_array(advice)
+    ia, k3 = _ptr_array(instance)
+    ch = _c(challenges, 4) if len(challenges) else np.zeros((1, 4), np.uint64)
+    bgty = np.concatenate([_c(beta, 4), _c(gamma, 4), _c(theta, 4), _c(y, 4)])
+    lib().oracle_graph_evaluate(_p(constants), rotations.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.c_uint32(rotations.shape[0]),
+                                code.ctypes.data_as(u32p), ctypes.c_uint32(n_calc), ctypes.c_uint32(num_intermediates), fa, aa, ia, _p(ch),
+                                _p(bgty), _p(values), ctypes.c_size_t(values.shape[0]), ctypes.c_int32(rot_scale))
+    return values
+
+
+def cq_lookup_h(values, b_coset, f_coset, l_active_row, beta, y):
+    """reference plonk/evaluation.rs:533-548"""
+    values = np.array(_c(values, 4), copy=True)
+    lib().oracle_cq_lookup_h(_p(values), _p(_c(b_coset, 4)), _p(_c(f_coset, 4)), _p(_c(l_active_row, 4)), _p(_c(beta, 4)), _p(_c(y, 4)),
+                             ctypes.c_size_t(values.shape[0]))
+    return values
+
+
+def permutation_h(values, rot_scale, last_rotation, chunk_len, sets, columns, perm_cosets, l0, l_last, l_active, beta, gamma, y, extended_omega):
+    """reference plonk/evaluation.rs:376-452"""
+    values = np.array(_c(values, 4), copy=True)
+    sa, k1 = _ptr_array(sets)
+    ca, k2 = _ptr_array(columns)
+    pa, k3 = _ptr_array(perm_cosets)
+    lib().oracle_permutation_h(_p(values), ctypes.c_size_t(values.shape[0]), ctypes.c_int32(rot_scale), ctypes.c_int32(last_rotation),
+                               ctypes.c_uint32(chunk_len), sa, ctypes.c_uint32(len(sets)), ca, pa, ctypes.c_uint32(len(columns)),
+                               _p(_c(l0, 4)), _p(_c(l_last, 4)), _p(_c(l_active, 4)), _p(_c(beta, 4)), _p(_c(gamma, 4)), _p(_c(y, 4)),
+                               _p(_c(extended_omega, 4)))
+    return values

@@ -143,6 +143,7 @@ void cqb_shutdown(void) {
     srs_release_all();
     ecntt_release_all();
     poly_release_all();
+    evalh_release_all();
     if (g_copy_stream) {
         for (auto& e : g_copy_ev) cudaEventDestroy(e);
         cudaStreamDestroy(g_copy_stream);
@@ -552,6 +553,33 @@ int cqb_g1_generator_mul_dev(const void* d_scalars, size_t n, void* d_out) {
     CQB_TRY(require_init());
     if ((!d_scalars || !d_out) && n) return fail(CQB_E_BAD_ARG, "cqb_g1_generator_mul_dev: NULL argument");
     return g1_generator_mul_run(d_scalars, n, d_out);
+}
+int cqb_graph_evaluate_dev(const cqb_graph_t* graph, const void* const* d_fixed, uint32_t n_fixed, const void* const* d_advice,
+                           uint32_t n_advice, const void* const* d_instance, uint32_t n_instance, const uint64_t* challenges,
+                           uint32_t n_challenges, const uint64_t beta[4], const uint64_t gamma[4], const uint64_t theta[4],
+                           const uint64_t y[4], void* d_values, uint64_t size, int32_t rot_scale) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!graph || !beta || !gamma || !theta || !y || (!d_values && size)) return fail(CQB_E_BAD_ARG, "cqb_graph_evaluate_dev: NULL argument");
+    return graph_evaluate_run(graph, d_fixed, n_fixed, d_advice, n_advice, d_instance, n_instance, challenges, n_challenges, beta, gamma, theta,
+                              y, d_values, size, rot_scale);
+}
+int cqb_cq_lookup_h_dev(void* d_values, const void* d_b_coset, const void* d_f_coset, const void* d_l_active_row, const uint64_t beta[4],
+                        const uint64_t y[4], uint64_t size) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!beta || !y || ((!d_values || !d_b_coset || !d_f_coset || !d_l_active_row) && size)) return fail(CQB_E_BAD_ARG, "cqb_cq_lookup_h_dev: NULL argument");
+    return cq_lookup_h_run(d_values, d_b_coset, d_f_coset, d_l_active_row, beta, y, size);
+}
+int cqb_permutation_h_dev(void* d_values, uint64_t size, int32_t rot_scale, int32_t last_rotation, uint32_t chunk_len,
+                          const void* const* d_sets, uint32_t nsets, const void* const* d_columns, const void* const* d_perm_cosets,
+                          uint32_t ncols, const void* d_l0, const void* d_l_last, const void* d_l_active_row, const uint64_t beta[4],
+                          const uint64_t gamma[4], const uint64_t y[4], const uint64_t extended_omega[4]) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!beta || !gamma || !y || !extended_omega) return fail(CQB_E_BAD_ARG, "cqb_permutation_h_dev: NULL argument");
+    return permutation_h_run(d_values, size, rot_scale, last_rotation, chunk_len, d_sets, nsets, d_columns, d_perm_cosets, ncols, d_l0, d_l_last,
+                             d_l_active_row, beta, gamma, y, extended_omega);
 }
 int cqb_eval_polynomial_dev(const void* d_coeffs, size_t n, const uint64_t point[4], uint64_t out[4]) {
     LOCK;

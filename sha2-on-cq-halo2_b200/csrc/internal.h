@@ -51,6 +51,18 @@ int g_to_lagrange_run(const void* d_g, uint32_t k, void* d_out);
 int cq_table_qs_run(const void* d_table_coeffs, uint32_t log_n, const void* d_srs_g1, void* d_qs_out);
 void ecntt_release_all();
 
+// ---- evalh.cu ----
+int graph_evaluate_run(const cqb_graph_t* g, const void* const* d_fixed, uint32_t n_fixed, const void* const* d_advice, uint32_t n_advice,
+                       const void* const* d_instance, uint32_t n_instance, const uint64_t* challenges, uint32_t n_challenges,
+                       const uint64_t* beta, const uint64_t* gamma, const uint64_t* theta, const uint64_t* y, void* d_values, uint64_t size,
+                       int32_t rot_scale);
+int cq_lookup_h_run(void* d_values, const void* d_b, const void* d_f, const void* d_l_active, const uint64_t* beta, const uint64_t* y, uint64_t size);
+int permutation_h_run(void* d_values, uint64_t size, int32_t rot_scale, int32_t last_rotation, uint32_t chunk_len, const void* const* d_sets,
+                      uint32_t nsets, const void* const* d_columns, const void* const* d_perm_cosets, uint32_t ncols, const void* d_l0,
+                      const void* d_l_last, const void* d_l_active, const uint64_t* beta, const uint64_t* gamma, const uint64_t* y,
+                      const uint64_t* extended_omega);
+void evalh_release_all();
+
 // ---- poly.cu ----
 int eval_polynomial_run(const void* d_coeffs, size_t n, const uint64_t point[4], void* d_out);
 int kate_division_run(const void* d_a, size_t n, const uint64_t b[4], void* d_q);
