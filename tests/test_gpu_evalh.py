@@ -98,3 +98,66 @@ def test_permutation_terms_parity(cq, oracle, nsets, ncols, chunk_len):
                       [dv.up(p) for p in perms], dv.up(l0), dv.up(l_last), dv.up(l_act), beta, gamma, y, ew)
     assert np.array_equal(dv.down(d_v, size), exp)
     dv.free()
+
+
+def test_quotient_pipeline_device_resident(cq, oracle):
+    """The chain evaluate_h sits in (plonk/prover.rs:606-627): coeff_to_extended of the advice / CQ polynomials (a8) ->
+    custom gates + CQ term row by row (evaluate_h) -> divide_by_vanishing_poly + extended_to_coeff (a9/a10) -> commit the
+    h pieces (a16) — every intermediate stays in HBM; only the commitments come back. Compared with the oracle doing the
+    same steps on the host."""
+    from sha2_on_cq_halo2_b200.evaluation import Expr, cq_lookup_h_dev, custom_gates_evaluator
+
+    L, lib = cq._lib, cq._lib.lib()
+    k = 6
+    n = 1 << k
+    dom = cq.EvaluationDomain(3, k)
+    od = oracle.domain_new(3, k)
+    en = 1 << dom.extended_k
+    rot_scale = 1 << (dom.extended_k - k)
+    s = oracle.synth_scalars(0xAB, 1)[0]
+    g, gl = oracle.params_setup(k, s)
+    params = cq.ParamsKZG(k, g, gl, precompute=False)
+    # coefficient-form polynomials: two advice columns, one fixed (selector-like), CQ's b and f, and l_active_row
+    polys = {name: oracle.synth_scalars(0x900 + i, n) for i, name in enumerate(["a0", "a1", "q", "b", "f", "lact"])}
+    beta, gamma, theta, y = oracle.synth_scalars(0x950, 4)
+    # gate: q * (a0 * a1(rot 1) - a1) ; q * (a0 - a0(rot -1)) * 7
+    a0, a1, a1n, a0p, q = Expr("advice", 0, 0), Expr("advice", 1, 0), Expr("advice", 1, 1), Expr("advice", 0, -1), Expr("fixed", 0, 0)
+    ev = custom_gates_evaluator([q * (a0 * a1n - a1), (q * (a0 - a0p)) * 7])
+    consts, rots, code = ev.serialize()
+    # ---- oracle ----
+    ext = {name: oracle.coeff_to_extended(od, p) for name, p in polys.items()}
+    h = oracle.graph_evaluate(consts, rots, code, len(ev.calculations), ev.num_intermediates, [ext["q"]], [ext["a0"], ext["a1"]], [],
+                              np.zeros((0, 4), np.uint64), beta, gamma, theta, y, np.zeros((en, 4), np.uint64), rot_scale)
+    h = oracle.cq_lookup_h(h, ext["b"], ext["f"], ext["lact"], beta, y)
+    h_coeff = oracle.extended_to_coeff(od, oracle.divide_by_vanishing_poly(od, h))
+    exp_cms = [oracle.best_multiexp(np.ascontiguousarray(h_coeff[i * n:(i + 1) * n]), g, 2)[1] for i in range(dom.quotient_poly_degree)]
+    # ---- device-resident ----
+    def dalloc(nbytes):
+        d = ctypes.c_void_p()
+        L.check(lib.cqb_dev_alloc(nbytes, ctypes.byref(d)))
+        return d
+
+    d_ext = {}
+    d_coeff = dalloc(n * 32)
+    for name, p in polys.items():
+        L.check(lib.cqb_memcpy_h2d(d_coeff, p.ctypes.data_as(ctypes.c_void_p), n * 32))
+        d_ext[name] = dalloc(en * 32)
+        L.check(lib.cqb_coset_ntt_bn254_fr_dev(d_coeff, n, d_ext[name], L.p64(dom.extended_omega), dom.extended_k, L.p64(dom.g_coset),
+                                               L.p64(dom.g_coset_inv)))
+    d_h = dalloc(en * 32)
+    L.check(lib.cqb_memcpy_h2d(d_h, np.zeros((en, 4), np.uint64).ctypes.data_as(ctypes.c_void_p), en * 32))
+    ev.evaluate_dev([d_ext["q"].value], [d_ext["a0"].value, d_ext["a1"].value], [], [], beta, gamma, theta, y, d_h.value, en, rot_scale)
+    cq_lookup_h_dev(d_h.value, d_ext["b"].value, d_ext["f"].value, d_ext["lact"].value, beta, y, en)
+    L.check(lib.cqb_coset_intt_bn254_fr_dev(d_h, dom.extended_k, L.p64(dom.extended_omega_inv), L.p64(dom.extended_ifft_divisor),
+                                            L.p64(dom.g_coset), L.p64(dom.g_coset_inv), L.p64(dom.t_evaluations), dom.t_evaluations.shape[0]))
+    out = np.zeros(8, np.uint64)
+    inf = ctypes.c_int(0)
+    for i in range(dom.quotient_poly_degree):
+        L.check(lib.cqb_msm_bn254_g1_dev(params.g.handle, 0, ctypes.c_void_p(d_h.value + i * n * 32), n, L.p64(out), ctypes.byref(inf)))
+        assert np.array_equal(out, exp_cms[i]), i
+    got_h = np.zeros((n * dom.quotient_poly_degree, 4), np.uint64)
+    L.check(lib.cqb_memcpy_d2h(got_h.ctypes.data_as(ctypes.c_void_p), d_h, got_h.nbytes))
+    assert np.array_equal(got_h, h_coeff)
+    for d in list(d_ext.values()) + [d_coeff, d_h]:
+        L.check(lib.cqb_dev_free(d))
+    params.free()
