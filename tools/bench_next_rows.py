@@ -94,3 +94,41 @@ t = time.perf_counter()
 O.kate_division(a20, x)
 res["cpu_kate_division_2^20_ms_1thread"] = round((time.perf_counter() - t) * 1e3, 1)
 print(json.dumps(res))
+
+# evaluate_h (plonk/evaluation.rs:285-551): custom-gate graph over 2^22 extended rows + CQ term
+import random
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from tests.evalh_common import random_expr
+from sha2_on_cq_halo2_b200.evaluation import Expr, cq_lookup_h_dev, custom_gates_evaluator
+
+rng = random.Random(5)
+polys = [random_expr(rng, Expr, 6, ncols=(4, 8, 1), nchal=2) for _ in range(16)]
+ev = custom_gates_evaluator(polys)
+size = 1 << 22
+cols = []
+for i in range(13):
+    dcol = dev(size * 32)
+    L.check(lib.cqb_synth_scalars_dev(100 + i, 0, size, dcol))
+    cols.append(dcol)
+d_vals = dev(size * 32)
+L.check(lib.cqb_synth_scalars_dev(99, 0, size, d_vals))
+chal = O.synth_scalars(400, 2)
+beta, gamma, theta, y = O.synth_scalars(500, 4)
+fixed, advice, inst = [c.value for c in cols[:4]], [c.value for c in cols[4:12]], [cols[12].value]
+ms = wall(lambda: ev.evaluate_dev(fixed, advice, inst, chal, beta, gamma, theta, y, d_vals.value, size, 2))
+nmul = sum(1 for c, _ in ev.calculations if c[0] in (2, 3)) + sum(len(c[2]) for c, _ in ev.calculations if c[0] == 6)
+res["evaluate_h_graph_2^22_rows_ms"] = round(ms, 3)
+res["evaluate_h_graph_calculations"] = len(ev.calculations)
+res["evaluate_h_graph_intermediates"] = ev.num_intermediates
+res["evaluate_h_graph_modmuls_per_row"] = nmul
+res["evaluate_h_graph_Gmodmul_per_s"] = round(nmul * size / ms / 1e6, 2)
+res["cq_lookup_term_2^22_rows_ms"] = round(wall(lambda: cq_lookup_h_dev(d_vals.value, cols[0].value, cols[1].value, cols[2].value, beta, y, size)), 3)
+small = 1 << 14
+c_small = [O.synth_scalars(100 + i, small) for i in range(13)]
+consts, rots, code = ev.serialize()
+t = time.perf_counter()
+O.graph_evaluate(consts, rots, code, len(ev.calculations), ev.num_intermediates, c_small[:4], c_small[4:12], c_small[12:], chal, beta, gamma,
+                 theta, y, O.synth_scalars(99, small), 2)
+res["cpu_evaluate_h_graph_2^14_rows_ms_1thread"] = round((time.perf_counter() - t) * 1e3, 1)
+print(json.dumps(res))
