@@ -28,6 +28,22 @@ extern "C" {
     pub fn cqb_msm_bn254_g1(b: cqb_bases_t, offset: usize, scalars: *const u64, n: usize, out_xy: *mut u64, is_inf: *mut c_int) -> c_int;
     pub fn cqb_msm_bn254_g1_host(affine_xy: *const u64, scalars: *const u64, n: usize, out_xy: *mut u64, is_inf: *mut c_int) -> c_int;
     pub fn cqb_msm_bn254_g1_sparse(b: cqb_bases_t, idx: *const u32, scalars: *const u64, m: usize, out_xy: *mut u64, is_inf: *mut c_int) -> c_int;
+    pub fn cqb_bases_register_device(d_affine_xy: *const c_void, n: usize, out: *mut cqb_bases_t) -> c_int;
+    pub fn cqb_bases_precompute(h: cqb_bases_t, window_bits: c_int) -> c_int;
+    pub fn cqb_msm_bn254_g1_dev(b: cqb_bases_t, offset: usize, d_scalars: *const c_void, n: usize, out_xy: *mut u64, is_inf: *mut c_int) -> c_int;
+    pub fn cqb_srs_setup_dev(k: u32, s: *const u64, d_g: *mut c_void, d_g_lagrange: *mut c_void) -> c_int;
+    pub fn cqb_table_srs_setup_dev(log_len: u32, s: *const u64, d_g1: *mut c_void, d_g1_lagrange: *mut c_void, d_opening_at_0: *mut c_void) -> c_int;
+    pub fn cqb_g_to_lagrange_dev(d_g: *const c_void, k: u32, d_out: *mut c_void) -> c_int;
+    pub fn cqb_cq_table_qs_dev(d_table_coeffs: *const c_void, log_n: u32, d_srs_g1: *const c_void, d_qs_out: *mut c_void) -> c_int;
+    pub fn cqb_cq_lookup_h_dev(d_values: *mut c_void, d_b_coset: *const c_void, d_f_coset: *const c_void, d_l_active_row: *const c_void,
+                               beta: *const u64, y: *const u64, size: u64) -> c_int;
+    pub fn cqb_eval_polynomial_dev(d_coeffs: *const c_void, n: usize, point: *const u64, out: *mut u64) -> c_int;
+    pub fn cqb_kate_division_dev(d_a: *const c_void, n: usize, b: *const u64, d_q: *mut c_void) -> c_int;
+    pub fn cqb_fr_batch_invert_dev(d_a: *mut c_void, n: usize) -> c_int;
+    pub fn cqb_dev_alloc(bytes: usize, d_out: *mut *mut c_void) -> c_int;
+    pub fn cqb_dev_free(d: *mut c_void) -> c_int;
+    pub fn cqb_memcpy_h2d(d_dst: *mut c_void, h_src: *const c_void, bytes: usize) -> c_int;
+    pub fn cqb_memcpy_d2h(h_dst: *mut c_void, d_src: *const c_void, bytes: usize) -> c_int;
     pub fn cqb_ntt_bn254_fr(a: *mut u64, omega: *const u64, log_n: u32) -> c_int;
     pub fn cqb_intt_bn254_fr(a: *mut u64, omega_inv: *const u64, divisor: *const u64, log_n: u32) -> c_int;
     pub fn cqb_coset_ntt_bn254_fr(coeffs: *const u64, n: usize, out: *mut u64, ext_omega: *const u64, ext_log_n: u32,
