@@ -319,3 +319,76 @@ def test_pipelined_host_msm_matches_device_path(cq, oracle, precompute):
     cq._lib.check(lib.cqb_host_free_pinned(h_pin))
     cq._lib.check(lib.cqb_dev_free(d_b))
     cq._lib.check(lib.cqb_dev_free(d_s))
+
+
+def test_error_codes_mirror_reference_panics(cq, oracle):
+    """the ABI returns CQB_E_* codes where the reference panics; nothing crashes, nothing falls back"""
+    lib, L = cq._lib.lib(), cq._lib
+    out = np.zeros(8, np.uint64)
+    inf = ctypes.c_int(0)
+    sc = oracle.synth_scalars(1, 8)
+    bs = oracle.synth_bases(2, 8, 1)
+    dev = cq.DeviceBases(bs, precompute=False)
+    # assert!(self.n() >= size) poly/kzg/commitment.rs:502
+    assert lib.cqb_msm_bn254_g1(dev.handle, 0, L.p64(np.zeros((9, 4), np.uint64)), 9, L.p64(out), ctypes.byref(inf)) == L.CQB_E_LEN_MISMATCH
+    assert lib.cqb_msm_bn254_g1(dev.handle, 5, L.p64(sc), 4, L.p64(out), ctypes.byref(inf)) == L.CQB_E_LEN_MISMATCH
+    assert lib.cqb_msm_bn254_g1(12345678, 0, L.p64(sc), 8, L.p64(out), ctypes.byref(inf)) == L.CQB_E_BAD_ARG
+    assert lib.cqb_msm_bn254_g1(dev.handle, 0, None, 8, L.p64(out), ctypes.byref(inf)) == L.CQB_E_BAD_ARG
+    bad_idx = np.array([0, 99], np.uint32)  # slice index out of range in the reference's loop
+    assert lib.cqb_msm_bn254_g1_sparse(dev.handle, bad_idx.ctypes.data_as(L.u32p), L.p64(sc), 2, L.p64(out), ctypes.byref(inf)) == L.CQB_E_BAD_ARG
+    assert lib.cqb_ntt_bn254_fr(L.p64(sc), L.p64(sc[0]), 29) == L.CQB_E_BAD_SIZE  # k <= Fr::S = 28
+    assert lib.cqb_bases_precompute(dev.handle, 99) == L.CQB_E_BAD_ARG
+    assert b"window bits" in lib.cqb_last_error()
+    # still healthy afterwards
+    _, exp = oracle.best_multiexp(sc, bs, 1)
+    assert np.array_equal(dev.msm(sc).to_affine(), exp)
+    dev.free()
+
+
+def test_concurrent_callers_are_serialised(cq, oracle):
+    """nothing forbids concurrent callers (rayon), so the library must be re-entrant: four host threads issue
+    MSMs and NTTs at once (ctypes drops the GIL during the calls); every result must match the oracle"""
+    import threading
+
+    n, k = 3000, 11
+    bs = oracle.synth_bases(50, n, 4)
+    dev = cq.DeviceBases(bs, precompute=False)
+    w = omega_limbs(k)
+    jobs, errors = [], []
+    for t in range(4):
+        sc = oracle.synth_scalars(60 + t, n)
+        a = oracle.synth_scalars(70 + t, 1 << k)
+        jobs.append((sc, oracle.best_multiexp(sc, bs, 2)[1], a, oracle.best_fft(a, w, k, 2)))
+
+    def work(job):
+        sc, exp_pt, a, exp_fft = job
+        try:
+            for _ in range(5):
+                if not np.array_equal(dev.msm(sc).to_affine(), exp_pt):
+                    errors.append("msm")
+                b = a.copy()
+                cq.best_fft(b, w, k)
+                if not np.array_equal(b, exp_fft):
+                    errors.append("fft")
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(j,)) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    dev.free()
+
+
+def test_shutdown_and_reinit(cq, oracle):
+    lib, L = cq._lib.lib(), cq._lib
+    sc, bs = oracle.synth_scalars(80, 100), oracle.synth_bases(81, 100, 1)
+    _, exp = oracle.best_multiexp(sc, bs, 1)
+    lib.cqb_shutdown()
+    out = np.zeros(8, np.uint64)
+    inf = ctypes.c_int(0)
+    assert lib.cqb_msm_bn254_g1_host(L.p64(bs), L.p64(sc), 100, L.p64(out), ctypes.byref(inf)) == L.CQB_E_NO_DEVICE
+    L.check(lib.cqb_init(0))
+    assert np.array_equal(cq.best_multiexp(sc, bs).to_affine(), exp)
