@@ -73,6 +73,12 @@ CQB_API int cqb_bases_drop_precomputed(cqb_bases_t h);
 CQB_API int cqb_msm_bn254_g1(cqb_bases_t b, size_t offset, const uint64_t* scalars, size_t n, uint64_t out_xy[8], int* is_inf);
 /* same, scalars already in device memory (bench "value": inputs resident in HBM) */
 CQB_API int cqb_msm_bn254_g1_dev(cqb_bases_t b, size_t offset, const void* d_scalars, size_t n, uint64_t out_xy[8], int* is_inf);
+/* `batch` MSMs over the same base range in one pass: scalars = batch contiguous vectors of n scalars, out_xy = batch x 8
+ * limbs, is_inf = batch flags. What the prover's commitment loops are (`advice.iter().map(|poly| params.commit_lagrange(poly))`
+ * plonk/prover.rs:356-360; the h pieces vanishing/prover.rs:101-105): with a precomputed table every MSM gets its own bucket
+ * set and all kernels run once for the whole batch, so the latency-bound tail is paid once. 1 <= batch <= 64. */
+CQB_API int cqb_msm_bn254_g1_batch(cqb_bases_t b, size_t offset, const uint64_t* scalars, size_t n, int batch, uint64_t* out_xy, int* is_inf);
+CQB_API int cqb_msm_bn254_g1_batch_dev(cqb_bases_t b, size_t offset, const void* d_scalars, size_t n, int batch, uint64_t* out_xy, int* is_inf);
 /* one-shot: bases and scalars both on the host (exact best_multiexp(&[Fr], &[G1Affine]) shape) */
 CQB_API int cqb_msm_bn254_g1_host(const uint64_t* affine_xy, const uint64_t* scalars, size_t n, uint64_t out_xy[8], int* is_inf);
 /* sparse MSM sum_j scalars[j] * bases[idx[j]]: replaces the serial scalar-mul loops of the CQ prover for m(X), A(X),

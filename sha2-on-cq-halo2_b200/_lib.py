@@ -32,6 +32,8 @@ SYMBOLS = [
     ("cqb_bases_drop_precomputed", _int, [_u64]),
     ("cqb_msm_bn254_g1", _int, [_u64, _sz, u64p, _sz, u64p, _ip]),
     ("cqb_msm_bn254_g1_dev", _int, [_u64, _sz, _vp, _sz, u64p, _ip]),
+    ("cqb_msm_bn254_g1_batch", _int, [_u64, _sz, u64p, _sz, _int, u64p, _ip]),
+    ("cqb_msm_bn254_g1_batch_dev", _int, [_u64, _sz, _vp, _sz, _int, u64p, _ip]),
     ("cqb_msm_bn254_g1_host", _int, [u64p, u64p, _sz, u64p, _ip]),
     ("cqb_msm_bn254_g1_sparse", _int, [_u64, u32p, u64p, _sz, u64p, _ip]),
     ("cqb_g1_sum_affine", _int, [u64p, _sz, u64p, _ip]),

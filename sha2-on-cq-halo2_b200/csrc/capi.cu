@@ -326,6 +326,46 @@ int cqb_msm_bn254_g1(cqb_bases_t b, size_t offset, const uint64_t* scalars, size
     return fetch_result(out_xy, is_inf);
 }
 
+// B MSMs over the same base range in one pass (commit_lagrange of all advice columns, the h pieces, ...)
+static int msm_batch_common(BaseSet* bs, size_t offset, const void* d_scalars, size_t n, int batch, uint64_t* out_xy, int* is_inf) {
+    CQB_TRY(g_out.ensure((size_t)batch * 80 + 80));
+    CQB_TRY(g_out_host.ensure((size_t)batch * 80 + 80));
+    if (bs->table && n * 8 >= bs->n && batch > 1) {
+        CQB_TRY(msm_run_precomputed(bs->table, bs->n, bs->table_c, offset, d_scalars, nullptr, n, g_out.p, batch));
+    } else {
+        for (int b = 0; b < batch; b++) {  // no table for this set: one MSM after the other (same results)
+            const char* sc = (const char*)d_scalars + (size_t)b * n * 32;
+            if (bs->table && n * 8 >= bs->n) CQB_TRY(msm_run_precomputed(bs->table, bs->n, bs->table_c, offset, sc, nullptr, n, (char*)g_out.p + (size_t)b * 80));
+            else CQB_TRY(msm_run(bs->d, offset, sc, nullptr, n, (char*)g_out.p + (size_t)b * 80));
+        }
+    }
+    CQB_CUDA(cudaMemcpyAsync(g_out_host.p, g_out.p, (size_t)batch * 80, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    for (int b = 0; b < batch; b++) {
+        memcpy(out_xy + 8 * b, (char*)g_out_host.p + (size_t)b * 80, 64);
+        if (is_inf) is_inf[b] = (int)((uint32_t*)((char*)g_out_host.p + (size_t)b * 80))[16];
+    }
+    return 0;
+}
+int cqb_msm_bn254_g1_batch_dev(cqb_bases_t h, size_t offset, const void* d_scalars, size_t n, int batch, uint64_t* out_xy, int* is_inf) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!out_xy || (!d_scalars && n) || batch < 1 || batch > 64) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1_batch_dev: bad argument (1 <= batch <= 64)");
+    BaseSet* bs = nullptr;
+    CQB_TRY(find_bases(h, offset, n, &bs));
+    return msm_batch_common(bs, offset, d_scalars, n, batch, out_xy, is_inf);
+}
+int cqb_msm_bn254_g1_batch(cqb_bases_t h, size_t offset, const uint64_t* scalars, size_t n, int batch, uint64_t* out_xy, int* is_inf) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!out_xy || (!scalars && n) || batch < 1 || batch > 64) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1_batch: bad argument (1 <= batch <= 64)");
+    BaseSet* bs = nullptr;
+    CQB_TRY(find_bases(h, offset, n, &bs));
+    CQB_TRY(g_scalars.ensure((size_t)batch * n * 32 + 32));
+    if (n) CQB_CUDA(cudaMemcpyAsync(g_scalars.p, scalars, (size_t)batch * n * 32, cudaMemcpyHostToDevice, g_ctx.stream));
+    return msm_batch_common(bs, offset, g_scalars.p, n, batch, out_xy, is_inf);
+}
+
 int cqb_msm_bn254_g1_host(const uint64_t* affine_xy, const uint64_t* scalars, size_t n, uint64_t out_xy[8], int* is_inf) {
     LOCK;
     CQB_TRY(require_init());

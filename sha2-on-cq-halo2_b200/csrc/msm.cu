@@ -77,7 +77,8 @@ __device__ __forceinline__ uint32_t window_bits(const uint32_t* k, int w, int c)
 struct MsmShape {
     int c;            // window bits
     int nwin;         // number of digit windows per scalar
-    int nsets;        // bucket sets: nwin (windowed) or 1 (single set over a precomputed table)
+    int nsets;        // bucket sets: nwin (windowed) or the batch size B (one set per MSM over a precomputed table)
+    int single;       // 1 = precomputed-table layout: all windows of an MSM share one bucket set
     uint32_t nb;      // buckets per set = 2^(c-1) (bucket ids 1..nb)
     uint32_t stride;  // nb + 2 : per-set stride of the histogram / offset arrays
     uint32_t table_n; // single set: points per window row of the precomputed table
@@ -98,7 +99,8 @@ __global__ void __launch_bounds__(256) msm_count_kernel(const uint4* __restrict_
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < n;
     const uint32_t lane = threadIdx.x & 31u;
-    Fr k = active ? load_scalar_canonical(scalars, i) : Fr::zero();
+    const uint32_t bset = blockIdx.y;  // batch member (single layout); 0 otherwise
+    Fr k = active ? load_scalar_canonical(scalars + (size_t)bset * n * 2, i) : Fr::zero();
     uint32_t carry = 0;
     for (int w = 0; w < s.nwin; w++) {
         uint32_t d = window_bits(k.l, w, s.c) + carry;
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(256) msm_count_kernel(const uint4* __restrict_
         uint32_t key = active ? d : 0u;
         uint32_t peers = __match_any_sync(0xffffffffu, key);
         if (key && lane == (uint32_t)(__ffs(peers) - 1))
-            atomicAdd(&hist[(s.nsets == 1 ? (size_t)0 : (size_t)w * s.stride) + key], (uint32_t)__popc(peers));
+            atomicAdd(&hist[(s.single ? (size_t)bset : (size_t)w) * s.stride + key], (uint32_t)__popc(peers));
     }
 }
 
@@ -232,7 +234,8 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint4* __restric
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < n;
     const uint32_t lane = threadIdx.x & 31u;
-    Fr k = active ? load_scalar_canonical(scalars, i) : Fr::zero();
+    const uint32_t bset = blockIdx.y;
+    Fr k = active ? load_scalar_canonical(scalars + (size_t)bset * n * 2, i) : Fr::zero();
     uint32_t pid = active ? (idx ? __ldg(idx + i) : (uint32_t)i + s.offset) : 0u;
     uint32_t carry = 0;
     for (int w = 0; w < s.nwin; w++) {
@@ -247,11 +250,11 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint4* __restric
         uint32_t rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
         uint32_t base = 0;
         if (key && lane == leader)
-            base = atomicAdd(&cursor[(s.nsets == 1 ? (size_t)0 : (size_t)w * s.stride) + key], (uint32_t)__popc(peers));
+            base = atomicAdd(&cursor[(s.single ? (size_t)bset : (size_t)w) * s.stride + key], (uint32_t)__popc(peers));
         base = __shfl_sync(0xffffffffu, base, leader);
         if (key) {
             uint32_t pos = base + rank;
-            if (s.nsets == 1) sorted[pos] = ((pid + (uint32_t)w * s.table_n) << 1) | neg;  // row w of the precomputed table
+            if (s.single) sorted[(size_t)bset * s.list_cap + pos] = ((pid + (uint32_t)w * s.table_n) << 1) | neg;  // table row w
             else sorted[(size_t)w * s.list_cap + pos] = (pid << 1) | neg;
         }
     }
@@ -442,6 +445,17 @@ __global__ void msm_final_kernel(const uint4* __restrict__ wins, MsmShape s, uin
     out[4] = make_uint4(inf, 0, 0, 0);
 }
 
+// batched single-layout MSMs: bucket set b is MSM b; no Horner, one normalisation per block
+__global__ void msm_final_batch_kernel(const uint4* __restrict__ wins, uint4* __restrict__ out) {
+    if (threadIdx.x != 0) return;
+    const uint32_t b = blockIdx.x;
+    G1Xyzz acc = ld_xyzz(wins + (size_t)b * 8);
+    G1Affine a = g1_to_affine_lowlat(acc);
+    st_fq(out + (size_t)b * 5, a.x);
+    st_fq(out + (size_t)b * 5 + 2, a.y);
+    out[(size_t)b * 5 + 4] = make_uint4(acc.is_identity() ? 1u : 0u, 0, 0, 0);
+}
+
 // sum of n affine points (multi-GPU partial fold). Single CTA; n is tiny (number of GPUs) but any n works.
 __global__ void __launch_bounds__(128) g1_sum_affine_kernel(const uint4* __restrict__ pts, size_t n, uint4* __restrict__ out) {
     __shared__ uint4 sm[128 * 8];
@@ -594,6 +608,7 @@ static MsmShape windowed_shape(size_t n) {
     s.c = c;
     s.nwin = msm_windows_for(c);
     s.nsets = s.nwin;
+    s.single = 0;
     s.nb = 1u << (c - 1);
     s.stride = s.nb + 2;
     s.table_n = 0;
@@ -639,22 +654,26 @@ static int msm_part(const void* d_bases, const void* d_scalars, const uint32_t* 
     g_ev_count = 0;
     prof_mark(0);
     unsigned gN = (unsigned)((n + 255) / 256);
-    msm_count_kernel<<<gN, 256, 0, st>>>((const uint4*)d_scalars, n, s, hist);
+    const dim3 gridN(gN, s.single ? (unsigned)s.nsets : 1u);
+    msm_count_kernel<<<gridN, 256, 0, st>>>((const uint4*)d_scalars, n, s, hist);
     CQB_LAUNCHED();
     prof_mark(1);
-    if (s.nsets == 1 && s.nb > 32768) {
-        scan_tile_sums_kernel<<<ntiles, 1024, 0, st>>>(hist, s.nb, tile_sums);
-        CQB_LAUNCHED();
-        scan_tile_offsets_kernel<<<1, 1024, 0, st>>>(tile_sums, ntiles);
-        CQB_LAUNCHED();
-        scan_apply_kernel<<<ntiles, 1024, 0, st>>>(hist, s.nb, tile_sums, offs, cursor);
-        CQB_LAUNCHED();
+    if (s.single && s.nb > 32768) {
+        for (int b = 0; b < s.nsets; b++) {  // one tiled scan per bucket set
+            const size_t o = (size_t)b * s.stride;
+            scan_tile_sums_kernel<<<ntiles, 1024, 0, st>>>(hist + o, s.nb, tile_sums);
+            CQB_LAUNCHED();
+            scan_tile_offsets_kernel<<<1, 1024, 0, st>>>(tile_sums, ntiles);
+            CQB_LAUNCHED();
+            scan_apply_kernel<<<ntiles, 1024, 0, st>>>(hist + o, s.nb, tile_sums, offs + o, cursor + o);
+            CQB_LAUNCHED();
+        }
     } else {
         msm_scan_kernel<<<s.nsets, 1024, 0, st>>>(hist, offs, cursor, s);
         CQB_LAUNCHED();
     }
     prof_mark(2);
-    msm_scatter_kernel<<<gN, 256, 0, st>>>((const uint4*)d_scalars, d_idx, n, s, cursor, g_sorted.as<uint32_t>());
+    msm_scatter_kernel<<<gridN, 256, 0, st>>>((const uint4*)d_scalars, d_idx, n, s, cursor, g_sorted.as<uint32_t>());
     CQB_LAUNCHED();
     prof_mark(3);
     msm_accumulate_kernel<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>((const uint4*)d_bases, g_sorted.as<uint32_t>(), offs, s, seg_log, cpw,
@@ -676,7 +695,7 @@ static int msm_finish(MsmShape s, int nparts, void* d_out) {
     cudaStream_t st = ctx().stream;
     size_t nbuckets = (size_t)s.nsets * s.nb;
     // tpw threads per set, ch buckets each (both powers of two, ch >= 2)
-    uint32_t tpw = std::min<uint32_t>(s.nb / 2, s.nsets == 1 ? 65536u : 1024u);
+    uint32_t tpw = std::min<uint32_t>(s.nb / 2, s.single ? (s.nsets == 1 ? 65536u : 16384u) : 1024u);
     if (tpw < 1) tpw = 1;
     uint32_t ch = s.nb / tpw;
     uint32_t lvl1 = (tpw + 2047) / 2048;  // tree-sum levels over the tpw partials per set
@@ -698,7 +717,8 @@ static int msm_finish(MsmShape s, int nparts, void* d_out) {
         CQB_LAUNCHED();
     }
     prof_mark(7);
-    msm_final_kernel<<<1, 32, 0, st>>>(wins, s, (uint4*)d_out);
+    if (s.single && s.nsets > 1) msm_final_batch_kernel<<<s.nsets, 32, 0, st>>>(wins, (uint4*)d_out);
+    else msm_final_kernel<<<1, 32, 0, st>>>(wins, s, (uint4*)d_out);
     CQB_LAUNCHED();
     prof_mark(8);
     CQB_CUDA(cudaGetLastError());
@@ -727,12 +747,16 @@ int msm_run(const void* d_bases, size_t offset, const void* d_scalars, const uin
 
 // single-set layout over a precomputed table of `table_n` points per row built with window bits c
 int msm_run_precomputed(const void* d_table, size_t table_n, int c, size_t offset, const void* d_scalars, const uint32_t* d_idx, size_t n,
-                        void* d_out) {
-    if (n == 0) return msm_empty(d_out);
+                        void* d_out, int batch) {
+    if (n == 0) {
+        for (int b = 0; b < batch; b++) CQB_TRY(msm_empty((char*)d_out + (size_t)b * 80));
+        return 0;
+    }
     MsmShape s;
     s.c = c;
     s.nwin = msm_windows_for(c);
-    s.nsets = 1;
+    s.nsets = batch;
+    s.single = 1;
     s.nb = 1u << (c - 1);
     s.stride = s.nb + 2;
     s.table_n = (uint32_t)table_n;
@@ -753,6 +777,7 @@ int msm_job_begin(size_t n_total, size_t part_cap, int nparts, const void* d_tab
         s.c = c;
         s.nwin = msm_windows_for(c);
         s.nsets = 1;
+        s.single = 1;
         s.nb = 1u << (c - 1);
         s.stride = s.nb + 2;
         s.table_n = (uint32_t)table_n;

@@ -61,6 +61,17 @@ class DeviceBases:
         _lib.check(_lib.lib().cqb_msm_bn254_g1(self.handle, offset, _lib.p64(scalars), scalars.shape[0], _lib.p64(out), ctypes.byref(inf)))
         return G1(out, inf.value)
 
+    def msm_batch(self, polys, offset=0):
+        """commit to several polynomials of equal length at once (plonk/prover.rs:356-360 commits every advice column in a
+        loop); polys: (B, n, 4) uint64 -> list of G1"""
+        polys = np.ascontiguousarray(polys, dtype=np.uint64)
+        assert polys.ndim == 3 and polys.shape[2] == 4
+        B, n = polys.shape[0], polys.shape[1]
+        out = np.zeros((B, 8), np.uint64)
+        inf = (ctypes.c_int * B)()
+        _lib.check(_lib.lib().cqb_msm_bn254_g1_batch(self.handle, offset, _lib.p64(polys), n, B, _lib.p64(out), inf))
+        return [G1(out[b].copy(), inf[b]) for b in range(B)]
+
     def msm_sparse(self, idx, scalars):
         idx = np.ascontiguousarray(idx, dtype=np.uint32)
         scalars = _as_fr(scalars)

@@ -392,3 +392,24 @@ def test_shutdown_and_reinit(cq, oracle):
     assert lib.cqb_msm_bn254_g1_host(L.p64(bs), L.p64(sc), 100, L.p64(out), ctypes.byref(inf)) == L.CQB_E_NO_DEVICE
     L.check(lib.cqb_init(0))
     assert np.array_equal(cq.best_multiexp(sc, bs).to_affine(), exp)
+
+
+@pytest.mark.parametrize("n,B,c,pre", [(1 << 12, 5, 10, True), (3000, 3, 0, True), (1 << 15, 8, 17, True), (2000, 4, 0, False)])
+def test_batched_msm_matches_individual(cq, oracle, n, B, c, pre):
+    """cqb_msm_bn254_g1_batch: B commitments over the same SRS in one pass == B separate best_multiexp calls"""
+    bases = oracle.synth_bases(0xBA + n, n, 4)
+    dev = cq.DeviceBases(bases, precompute=pre, window_bits=c)
+    polys = np.stack([oracle.synth_scalars(0xBB + b, n) for b in range(B)])
+    polys[1][:] = polys[1][7]          # a skewed member
+    polys[2][:] = 0                    # an all-zero member -> identity
+    got = dev.msm_batch(polys)
+    for b in range(B):
+        _, exp = oracle.best_multiexp(polys[b], bases, 8)
+        assert np.array_equal(got[b].to_affine(), exp), b
+    assert got[2].is_identity
+    m = n - 5                          # shorter polynomials with an offset into the set
+    got = dev.msm_batch(np.ascontiguousarray(polys[:, :m]), offset=5)
+    for b in range(B):
+        _, exp = oracle.best_multiexp(np.ascontiguousarray(polys[b, :m]), bases[5:], 8)
+        assert np.array_equal(got[b].to_affine(), exp), b
+    dev.free()
