@@ -241,6 +241,8 @@ def main():
         sampler.join()
     assert np.array_equal(result_dev, result_e2e), "device-resident and host-pointer paths disagree"
 
+    # windows per point actually executed: 254/c + 1 with the c the library picked (20 for the table layout at >= 2^22)
+    nwin_eff = 16 if args.no_precompute else (254 // (args.window_bits or (20 if per >= (1 << 22) else 16)) + 1)
     value = n_total / (ms_dev * 1e-3) / 1e6
     e2e = n_total / (ms_e2e * 1e-3) / 1e6
     t_acc = float(np.mean(acc_ms)) if acc_ms else float("nan")
@@ -258,10 +260,19 @@ def main():
                 "d2h_bytes_per_step": 80 * world, "note": "scalars in pinned host memory per step; SRS bases resident in HBM"},
         "gpu_launches": int(launches) * args.steps,
         "roofline": {"bound": "int", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": INT_PEAK_TMAD32,
-                     "unit": "TMAD32/s", "frac": achieved / INT_PEAK_TMAD32, "traffic": None,
+                     "unit": "TMAD32/s", "frac": achieved / INT_PEAK_TMAD32, "traffic": 29.6e9 if (world == 1 and args.log_n == 24 and not args.no_precompute) else None,
                      "kernel_ms": t_acc, "algorithmic_mad32_per_point": MAD32_PER_POINT,
                      "peak_source": "measured on this pool's B200: profiles/r01_int_pipe_calibration.md (MEASURED_PEAKS.json has no integer figure)",
                      "whole_msm_frac": n_total / world * MAD32_PER_POINT / (ms_dev * 1e-3) / 1e12 / INT_PEAK_TMAD32},
+        # the same kernel against the HBM roofline, in the canonical schema: it is NOT bandwidth-bound (frac << 1 by design)
+        "roofline_hbm": {"bound": "hbm", "kernel": "msm_accumulate_kernel",
+                         "achieved": per * nwin_eff * 68 / (t_acc * 1e-3) / 1e9, "peak": measured_peaks().get("hbm_gbs", 6650.0),
+                         "unit": "GB/s", "frac": per * nwin_eff * 68 / (t_acc * 1e-3) / 1e9 / measured_peaks().get("hbm_gbs", 6650.0),
+                         "traffic": 29.6e9 if (world == 1 and args.log_n == 24 and not args.no_precompute) else None,
+                         "algorithmic_bytes_per_launch": per * nwin_eff * 68,
+                         "note": "68 B per bucket addition (64 B affine point + 4 B sorted index) x windows per point; traffic = dram read+write "
+                                 "of one ncu --set full capture of this launch (profiles/r01_ncu_msm_accumulate_final_raw.csv)",
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in measured_peaks() else "fallback 6650 GB/s"},
         "msm_phase_ms": {k: float(v) for k, v in zip(["count", "scan", "scatter", "accumulate", "merge", "reduce", "window_sum", "final"], ph_avg)},
     }
     if sampler:
