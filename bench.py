@@ -242,7 +242,9 @@ def main():
     assert np.array_equal(result_dev, result_e2e), "device-resident and host-pointer paths disagree"
 
     # windows per point actually executed: 254/c + 1 with the c the library picked (20 for the table layout at >= 2^22)
-    nwin_eff = 16 if args.no_precompute else (254 // (args.window_bits or (20 if per >= (1 << 22) else 16)) + 1)
+    c_tab = lib.cqb_bases_precomputed_window_bits(h.value)
+    c_eff = c_tab if c_tab else (args.window_bits or 16)
+    nwin_eff = 254 // c_eff + 1
     value = n_total / (ms_dev * 1e-3) / 1e6
     e2e = n_total / (ms_e2e * 1e-3) / 1e6
     t_acc = float(np.mean(acc_ms)) if acc_ms else float("nan")
@@ -254,7 +256,7 @@ def main():
         "config": {"workload": f"BN254 G1 MSM 2^{args.log_n} uniform scalars x distinct points (BASELINE.json configs[1])",
                    "sharding": f"point range, {per} points per GPU, partials all-gathered over NCCL and folded" if world > 1 else "single GPU",
                    "l2": f"inputs per GPU ({per * 96 / 2**20:.0f} MiB) exceed the 126 MB L2; no explicit flush",
-                   "window_bits": args.window_bits or "auto",
+                   "window_bits": c_eff, "windows_per_point": nwin_eff,
                    "layout": "windowed" if args.no_precompute else "single bucket set over the per-SRS precomputed table (built once at SRS registration)"},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": per * 32 * world,
                 "d2h_bytes_per_step": 80 * world, "note": "scalars in pinned host memory per step; SRS bases resident in HBM"},

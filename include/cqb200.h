@@ -65,6 +65,7 @@ CQB_API size_t cqb_bases_len(cqb_bases_t h);
  * from n. MSMs over >= 1/8 of the set then use the table automatically; results are identical either way. */
 CQB_API int cqb_bases_precompute(cqb_bases_t h, int window_bits);
 CQB_API int cqb_bases_drop_precomputed(cqb_bases_t h);
+CQB_API int cqb_bases_precomputed_window_bits(cqb_bases_t h); /* c of the table, 0 if none: windows per point = 254/c + 1 */
 
 /* ---- MSM: replaces best_multiexp (halo2_proofs/src/arithmetic.rs:132-159) as called by
  *      Params::commit_lagrange (poly/kzg/commitment.rs:496-504), ParamsProver::commit (:539-543),

@@ -30,6 +30,7 @@ SYMBOLS = [
     ("cqb_bases_len", _sz, [_u64]),
     ("cqb_bases_precompute", _int, [_u64, _int]),
     ("cqb_bases_drop_precomputed", _int, [_u64]),
+    ("cqb_bases_precomputed_window_bits", _int, [_u64]),
     ("cqb_msm_bn254_g1", _int, [_u64, _sz, u64p, _sz, u64p, _ip]),
     ("cqb_msm_bn254_g1_dev", _int, [_u64, _sz, _vp, _sz, u64p, _ip]),
     ("cqb_msm_bn254_g1_batch", _int, [_u64, _sz, u64p, _sz, _int, u64p, _ip]),

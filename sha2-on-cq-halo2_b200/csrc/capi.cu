@@ -266,6 +266,11 @@ int cqb_bases_precompute(cqb_bases_t h, int window_bits) {
     return 0;
 }
 
+int cqb_bases_precomputed_window_bits(cqb_bases_t h) {
+    LOCK;
+    auto it = g_bases.find(h);
+    return (it == g_bases.end() || !it->second.table) ? 0 : it->second.table_c;
+}
 int cqb_bases_drop_precomputed(cqb_bases_t h) {
     LOCK;
     auto it = g_bases.find(h);
