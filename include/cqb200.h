@@ -147,6 +147,8 @@ CQB_API int cqb_eval_polynomial_dev(const void* d_coeffs, size_t n, const uint64
 /* kate_division (arithmetic.rs:351-387): d_q[0..n-1) = (a(X) - a(b)) / (X - b); as used by the multiopen provers
  * (poly/kzg/multiopen/gwc/prover.rs:80-86) and the CQ table preprocessing; d_q must not alias d_a */
 CQB_API int cqb_kate_division_dev(const void* d_a, size_t n, const uint64_t b[4], void* d_q);
+/* in place a[i] <- a[i] * factor (the parallelize()d scaling loops, e.g. poly/domain.rs:369-373) */
+CQB_API int cqb_fr_scale_dev(void* d_a, size_t n, const uint64_t factor[4]);
 /* in place a[i] <- 1/a[i], zeros stay zero: ff::BatchInvert as used at poly/domain.rs:118-125, static_lookup/prover.rs:261-269 */
 CQB_API int cqb_fr_batch_invert_dev(void* d_a, size_t n);
 /* out[i] = base^i, i < n (the serial scans at arithmetic.rs:194-200, commitment.rs:153-156) */

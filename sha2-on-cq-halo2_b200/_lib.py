@@ -53,6 +53,7 @@ SYMBOLS = [
     ("cqb_g1_generator_mul_dev", _int, [_vp, _sz, _vp]),
     ("cqb_g_to_lagrange_dev", _int, [_vp, _u32, _vp]),
     ("cqb_cq_table_qs_dev", _int, [_vp, _u32, _vp, _vp]),
+    ("cqb_fr_scale_dev", _int, [_vp, _sz, u64p]),
     ("cqb_fr_batch_invert_dev", _int, [_vp, _sz]),
     ("cqb_graph_evaluate_dev", _int, [_vp, _vp, _u32, _vp, _u32, _vp, _u32, u64p, _u32, u64p, u64p, u64p, u64p, _vp, _u64, ctypes.c_int32]),
     ("cqb_cq_lookup_h_dev", _int, [_vp, _vp, _vp, _vp, u64p, u64p, _u64]),

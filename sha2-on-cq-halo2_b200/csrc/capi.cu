@@ -643,6 +643,16 @@ int cqb_kate_division_dev(const void* d_a, size_t n, const uint64_t b[4], void* 
     if (!b || ((!d_a || !d_q) && n > 1) || (d_a == d_q && n > 1)) return fail(CQB_E_BAD_ARG, "cqb_kate_division_dev: NULL or aliasing arguments");
     return kate_division_run(d_a, n, b, d_q);
 }
+static Scratch g_scale_tab;
+int cqb_fr_scale_dev(void* d_a, size_t n, const uint64_t factor[4]) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!factor || (!d_a && n)) return fail(CQB_E_BAD_ARG, "cqb_fr_scale_dev: NULL argument");
+    if (n == 0) return 0;
+    CQB_TRY(g_scale_tab.ensure(64));
+    CQB_CUDA(cudaMemcpyAsync(g_scale_tab.p, factor, 32, cudaMemcpyHostToDevice, g_ctx.stream));
+    return fr_scale_table(d_a, n, g_scale_tab.p, 1);
+}
 int cqb_fr_batch_invert_dev(void* d_a, size_t n) {
     LOCK;
     CQB_TRY(require_init());
