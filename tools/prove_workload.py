@@ -16,6 +16,8 @@ Witness synthesis, evaluate_h's row program, transcript hashing and challenges a
 NOT included. Returns milliseconds per proof (wall clock around the synchronous C-ABI calls).
 """
 import ctypes
+import os
+import sys
 import time
 
 import numpy as np
@@ -98,7 +100,6 @@ def run(cq, k, A=8, table_log=16, reps=2, seed=0x70726F76, resident=False):
     def proof_resident():
         for i in range(A + 4):   # one upload per column per proof
             L.check(lib.cqb_memcpy_h2d(dcols[i], cols[i], n * 32))
-        L.check(lib.cqb_memcpy_h2d(d_ext, ext, en * 32))   # stands in for evaluate_h's output (computed on device in a full port)
         # the A advice commitments and f in ONE batched pass (plonk/prover.rs:356-360 + static_lookup/prover.rs:165)
         outs = np.zeros((A + 1, 8), np.uint64)
         infs = (ctypes.c_int * (A + 1))()
@@ -111,14 +112,51 @@ def run(cq, k, A=8, table_log=16, reps=2, seed=0x70726F76, resident=False):
         msm_d(g, dcols[A + 2], n)
         for a in range(A):
             L.check(lib.cqb_intt_bn254_fr_dev(dcols[a], L.p64(dom.omega_inv), L.p64(dom.ifft_divisor), k))
-        for a in list(range(A)) + [A, A + 1]:
-            L.check(lib.cqb_coset_ntt_bn254_fr_dev(dcols[a], n, d_ext_out, L.p64(dom.extended_omega), dom.extended_k,
-                                                   L.p64(dom.g_coset), L.p64(dom.g_coset_inv)))
+        evaluate_h_resident()   # the (A + 2) coset NTTs + custom gates + permutation + CQ terms, device-resident
         L.check(lib.cqb_coset_intt_bn254_fr_dev(d_ext, dom.extended_k, L.p64(dom.extended_omega_inv), L.p64(dom.extended_ifft_divisor),
                                                 L.p64(dom.g_coset), L.p64(dom.g_coset_inv), L.p64(dom.t_evaluations),
                                                 dom.t_evaluations.shape[0]))
         msm_d(g, d_ext, n); msm_d(g, ctypes.c_void_p(d_ext.value + n * 32), n)   # the two h pieces, straight from the device
         msm_d(g, dcols[A + 3], n - 1)
+
+    # ---- the row program of evaluate_h (custom gates + permutation + CQ term) for the resident mode -------------------
+    if resident:
+        import random
+
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from tests.evalh_common import random_expr
+        from sha2_on_cq_halo2_b200.evaluation import Expr, cq_lookup_h_dev, custom_gates_evaluator, permutation_h_dev
+
+        rng = random.Random(11)
+        gate_polys = [random_expr(rng, Expr, 5, ncols=(2, A, 1), nchal=1) for _ in range(12)]   # 12 gate polynomials
+        ev = custom_gates_evaluator(gate_polys)
+        rot_scale = 1 << (dom.extended_k - k)
+        d_ext_cols = ctypes.c_void_p()   # coset evaluations of the A advice columns + f + b + 2 fixed + 1 instance + A permutation cosets
+        n_ext_cols = A + 2 + 3 + A + 3 + 2
+        L.check(lib.cqb_dev_alloc(n_ext_cols * en * 32, ctypes.byref(d_ext_cols)))
+        ext_ptr = [d_ext_cols.value + i * en * 32 for i in range(n_ext_cols)]
+        for i in range(A + 2, n_ext_cols):   # key material (fixed / permutation cosets, l0 / l_last / l_active, z columns): resident, filled once
+            L.check(lib.cqb_synth_scalars_dev(seed + 500 + i, 0, en, ctypes.c_void_p(ext_ptr[i])))
+        chal1 = np.zeros((1, 4), np.uint64)
+        bgty = [np.array([3 + i, 0, 0, 0], np.uint64) for i in range(4)]
+        nsets = (A + 2) // 3   # chunk_len = cs.degree() - 2 = 3 columns per permutation set
+
+    def evaluate_h_resident():
+        """plonk/prover.rs:606-624: coset NTT of every advice / CQ polynomial, then the row program, all in HBM"""
+        for a in list(range(A)) + [A, A + 1]:
+            L.check(lib.cqb_coset_ntt_bn254_fr_dev(dcols[a], n, ctypes.c_void_p(ext_ptr[a]), L.p64(dom.extended_omega), dom.extended_k,
+                                                   L.p64(dom.g_coset), L.p64(dom.g_coset_inv)))
+        L.check(lib.cqb_memcpy_d2d(d_ext, ctypes.c_void_p(ext_ptr[n_ext_cols - 1]), en * 32))   # values := 0-like start (any vector)
+        fixed = ext_ptr[A + 2:A + 4]
+        inst = ext_ptr[A + 4:A + 5]
+        ev.evaluate_dev(fixed, ext_ptr[:A], inst, chal1, bgty[0], bgty[1], bgty[2], bgty[3], d_ext.value, en, rot_scale)
+        perm = ext_ptr[A + 5:A + 5 + A]
+        l0, l_last, l_act = ext_ptr[2 * A + 5:2 * A + 8]
+        sets = ext_ptr[2 * A + 8:2 * A + 10][:max(1, min(nsets, 2))]
+        ncols_p = min(A, 3 * len(sets))
+        permutation_h_dev(d_ext.value, en, rot_scale, -(5 + 1), 3, sets, ext_ptr[:ncols_p], perm[:ncols_p], l0, l_last, l_act, bgty[0], bgty[1],
+                          bgty[3], dom.extended_omega)
+        cq_lookup_h_dev(d_ext.value, ext_ptr[A + 1], ext_ptr[A], l_act, bgty[0], bgty[3], en)
 
     def proof_host():
         for a in range(A):
@@ -155,13 +193,14 @@ def run(cq, k, A=8, table_log=16, reps=2, seed=0x70726F76, resident=False):
     for p in cols + [ext, ext_out, sp]:
         L.check(lib.cqb_host_free_pinned(p))
     if resident:
-        for d in [d_block, d_ext, d_ext_out]:
+        for d in [d_block, d_ext, d_ext_out, d_ext_cols]:
             L.check(lib.cqb_dev_free(d))
     for d, h in keep + tabs:
         L.check(lib.cqb_bases_free(h))
         L.check(lib.cqb_dev_free(d))
     n_msm = A + 1 + 4 + 2 + 1 + 2 + 1
-    return {"k": k, "mode": "device-resident polynomials, advice commitments batched" if resident else "host-pointer calls (drop-in)", "advice_columns": A, "table_rows": N, "ms_per_proof": ms, "gpu_launches_per_proof": int(launches),
+    return {"k": k, "mode": "device-resident polynomials, advice commitments batched, evaluate_h row program (12 gate polynomials, "
+                            "permutation + CQ terms) on the device" if resident else "host-pointer calls (drop-in)", "advice_columns": A, "table_rows": N, "ms_per_proof": ms, "gpu_launches_per_proof": int(launches),
             "ops": {"dense_msm": n_msm - 4, "sparse_msm": 4, "intt_n": A + 2, "coset_ntt_2n": A + 2, "coset_intt_2n": 1}}
 
 
