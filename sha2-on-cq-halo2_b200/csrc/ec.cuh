@@ -36,6 +36,8 @@ struct G1Xyzz {
 #define FQS(a) fp_sqr<FqP>(a)
 #define FQA(a, b) fp_add<FqP>(a, b)
 #define FQSUB(a, b) fp_sub<FqP>(a, b)
+// a*b - c*d with one Montgomery reduction (the negation is 8 ALU ops; the fused product saves 72 wide multiplies)
+#define FQMSUB(a, b, c, d) fp_mul2<FqP>(a, b, fp_neg<FqP>(c), d)
 
 // 2*(x,y) for an affine, non-identity point (mdbl-2008-s-1). y == 0 cannot happen on this curve (no 2-torsion), but
 // the formula degrades gracefully to ZZ = 0 = identity anyway.
@@ -48,7 +50,7 @@ CQB_HD G1Xyzz g1_double_affine(const Fq& x1, const Fq& y1) {
     Fq xx = FQS(x1);
     Fq m = FQA(fp_dbl<FqP>(xx), xx);
     r.x = FQSUB(FQS(m), fp_dbl<FqP>(s));
-    r.y = FQSUB(FQM(m, FQSUB(s, r.x)), FQM(w, y1));
+    r.y = FQMSUB(m, FQSUB(s, r.x), y1, w);
     r.zz = v;
     r.zzz = w;
     return r;
@@ -65,7 +67,7 @@ CQB_HD G1Xyzz g1_double(const G1Xyzz& p) {
     Fq xx = FQS(p.x);
     Fq m = FQA(fp_dbl<FqP>(xx), xx);
     r.x = FQSUB(FQS(m), fp_dbl<FqP>(s));
-    r.y = FQSUB(FQM(m, FQSUB(s, r.x)), FQM(w, p.y));
+    r.y = FQMSUB(m, FQSUB(s, r.x), p.y, w);
     r.zz = FQM(v, p.zz);
     r.zzz = FQM(w, p.zzz);
     return r;
@@ -90,7 +92,7 @@ CQB_HD void g1_madd(G1Xyzz& acc, const Fq& x2, const Fq& y2) {
     Fq ppp = FQM(p, pp);
     Fq q = FQM(acc.x, pp);
     Fq x3 = FQSUB(FQSUB(FQS(r), ppp), fp_dbl<FqP>(q));
-    Fq y3 = FQSUB(FQM(r, FQSUB(q, x3)), FQM(acc.y, ppp));
+    Fq y3 = FQMSUB(r, FQSUB(q, x3), acc.y, ppp);
     acc.x = x3;
     acc.y = y3;
     acc.zz = FQM(acc.zz, pp);
@@ -116,7 +118,7 @@ CQB_HD void g1_add(G1Xyzz& acc, const G1Xyzz& b) {
     Fq ppp = FQM(p, pp);
     Fq q = FQM(u1, pp);
     Fq x3 = FQSUB(FQSUB(FQS(r), ppp), fp_dbl<FqP>(q));
-    Fq y3 = FQSUB(FQM(r, FQSUB(q, x3)), FQM(s1, ppp));
+    Fq y3 = FQMSUB(r, FQSUB(q, x3), s1, ppp);
     acc.x = x3;
     acc.y = y3;
     acc.zz = FQM(FQM(acc.zz, b.zz), pp);
@@ -151,5 +153,6 @@ CQB_HD G1Affine g1_to_affine_lowlat(const G1Xyzz& p) {
 #undef FQS
 #undef FQA
 #undef FQSUB
+#undef FQMSUB
 
 }  // namespace cqb

@@ -475,9 +475,119 @@ CQB_HD Fp<P> fp_mul_kar(const Fp<P>& a, const Fp<P>& b) {
     return fp_reduce16<P>(t);
 }
 
-// reference derive/field.rs:358-393. A dedicated squaring is an optimisation; the canonical result equals mul(a,a).
+
+// t[0..16) = a^2 with 36 wide products instead of 64: the 28 off-diagonal products a_i a_j (i < j) are accumulated once,
+// doubled with funnel shifts on the ALU pipe, and the 8 diagonal products are added by one carry chain. Product a_i a_j
+// lands on limb i+j: those with i+j even go to the limb-0-aligned accumulator E, those with i+j odd to the limb-1-aligned
+// accumulator O (O[k] is limb k+1), so that within a row consecutive j of equal parity form one unbroken lo,hi,lo,hi
+// carry chain (one IMAD.WIDE per product, as in fp_mul). Rows are visited in increasing i, which makes the limb that
+// receives a chain's final carry one that no product has been written to yet: a single addc, no carry propagation.
+CQB_HD void sqr_8(uint32_t* t, const uint32_t* a) {
+    uint32_t E[16], O[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { E[k] = 0; O[k] = 0; }
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+        if (i + 2 < 8) {  // j = i+2, i+4, ... : limb i+j of E
+            E[2 * i + 2] = mad_lo_cc(a[i], a[i + 2], E[2 * i + 2]);
+            E[2 * i + 3] = madc_hi_cc(a[i], a[i + 2], E[2 * i + 3]);
+            int end = 2 * i + 4;
+#pragma unroll
+            for (int j = i + 4; j < 8; j += 2) {
+                E[i + j] = madc_lo_cc(a[i], a[j], E[i + j]);
+                E[i + j + 1] = madc_hi_cc(a[i], a[j], E[i + j + 1]);
+                end = i + j + 2;
+            }
+            E[end] = addc(E[end], 0u);
+        }
+        {  // j = i+1, i+3, ... : index i+j-1 of O
+            O[2 * i] = mad_lo_cc(a[i], a[i + 1], O[2 * i]);
+            O[2 * i + 1] = madc_hi_cc(a[i], a[i + 1], O[2 * i + 1]);
+            int end = 2 * i + 2;
+#pragma unroll
+            for (int j = i + 3; j < 8; j += 2) {
+                O[i + j - 1] = madc_lo_cc(a[i], a[j], O[i + j - 1]);
+                O[i + j] = madc_hi_cc(a[i], a[j], O[i + j]);
+                end = i + j + 1;
+            }
+            O[end] = addc(O[end], 0u);
+        }
+    }
+    // S = E + (O << 32)  (E[0] = E[1] = 0), S < 2^511
+    uint32_t s[16];
+    s[0] = 0;
+    s[1] = O[0];
+    s[2] = add_cc(E[2], O[1]);
+#pragma unroll
+    for (int k = 3; k < 15; k++) s[k] = addc_cc(E[k], O[k - 1]);
+    s[15] = addc(E[15], O[14]);
+    // t = 2 S + sum_i a_i^2 2^(64 i)
+    t[0] = mad_lo_cc(a[0], a[0], 0u);
+    t[1] = madc_hi_cc(a[0], a[0], s[1] << 1);
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+        t[2 * i] = madc_lo_cc(a[i], a[i], (s[2 * i] << 1) | (s[2 * i - 1] >> 31));
+        t[2 * i + 1] = madc_hi_cc(a[i], a[i], (s[2 * i + 1] << 1) | (s[2 * i] >> 31));
+    }
+}
+
+// reference derive/field.rs:358-393 (square + montgomery_reduce): same canonical result as mul(a, a), 36 + 72 wide
+// multiplies instead of 136.
 template <class P>
-CQB_HD Fp<P> fp_sqr(const Fp<P>& a) { return fp_mul<P>(a, a); }
+CQB_HD Fp<P> fp_sqr(const Fp<P>& a) {
+#ifdef CQB_NO_FAST_SQR
+    return fp_mul<P>(a, a);
+#else
+    uint32_t t[16];
+    sqr_8(t, a.l);
+    return fp_reduce16<P>(t);
+#endif
+}
+
+// a*b + c*d (Montgomery form, fully reduced) with ONE reduction: CIOS with two product rows per reduction row
+// (2 x 64 + 72 wide multiplies instead of 2 x 136). Bound: a, b, c, d <= p < 2^254, so the running sum stays below 4p and
+// the result before the conditional subtraction below (2 p^2 + 2^256 p) / 2^256 < 2p.
+template <class P>
+CQB_HD Fp<P> fp_mul2(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) {
+    uint32_t ev[9], od[9], p[8];
+    mod_limbs<P>(p);
+    uint32_t m;
+    row_mul(ev, a.l, b.l[0]);
+    row_mul(od, a.l + 1, b.l[0]);
+    row_mad(ev, c.l, d.l[0]);
+    row_mad(od, c.l + 1, d.l[0]);
+    m = ev[0] * P::inv();
+    row_mad(od, p + 1, m);
+    row_mad(ev, p, m);
+#pragma unroll
+    for (int i = 1; i < 8; i += 2) {
+        od[0] = add_cc(od[0], ev[1]);
+        row_madc_shift2(ev, a.l + 1, b.l[i]);
+        row_mad(od, a.l, b.l[i]);
+        row_mad(ev, c.l + 1, d.l[i]);
+        row_mad(od, c.l, d.l[i]);
+        m = od[0] * P::inv();
+        row_mad(ev, p + 1, m);
+        row_mad(od, p, m);
+        if (i + 1 < 8) {
+            ev[0] = add_cc(ev[0], od[1]);
+            row_madc_shift2(od, a.l + 1, b.l[i + 1]);
+            row_mad(ev, a.l, b.l[i + 1]);
+            row_mad(od, c.l + 1, d.l[i + 1]);
+            row_mad(ev, c.l, d.l[i + 1]);
+            m = ev[0] * P::inv();
+            row_mad(od, p + 1, m);
+            row_mad(ev, p, m);
+        }
+    }
+    Fp<P> r;
+    r.l[0] = add_cc(ev[0], od[1]);
+#pragma unroll
+    for (int k = 1; k < 7; k++) r.l[k] = addc_cc(ev[k], od[k + 1]);
+    r.l[7] = addc(ev[7], od[8]);
+    fp_reduce_once<P>(r.l);
+    return r;
+}
 
 // Montgomery -> canonical integer (multiply by 1): reference derive/field.rs:432-470 montgomery_reduce_short
 template <class P>

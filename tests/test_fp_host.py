@@ -33,13 +33,19 @@ def test_fp_limb_algorithm(fp_bin):
     lines, exp = [], []
     for name, p in (("fr", P.R_MOD), ("fq", P.Q_MOD)):
         rinv = pow(P.MONT, -1, p)
-        vals = [0, 1, 2, p - 1, p - 2, P.MONT % p, (1 << 254) % p, (p - 1) // 2] + [rng.randrange(p) for _ in range(300)]
+        vals = [0, 1, 2, p - 1, p - 2, P.MONT % p, (1 << 254) % p, (p - 1) // 2]
+        vals += [(1 << k) - 1 for k in (32, 64, 96, 128, 160, 192, 224, 253)] + [((1 << 253) - 1) ^ ((1 << k) - 1) for k in (31, 97, 200)]
+        vals += [rng.randrange(p) for _ in range(300)]
         for _ in range(500):
             a, b = rng.choice(vals), rng.choice(vals)
             for op, res in (("mul", a * b * rinv % p), ("mulk", a * b * rinv % p), ("add", (a + b) % p), ("sub", (a - b) % p), ("neg", (-a) % p),
                             ("dbl", 2 * a % p), ("sqr", a * a * rinv % p), ("frommont", a * rinv % p), ("tomont", a * P.MONT % p)):
                 lines.append(f"{name} {op} {a:064x} {b:064x}")
                 exp.append(res)
+        for _ in range(400):  # a*b + c*d with a single reduction; operands up to p itself (a negated zero)
+            a, b, c, d = (rng.choice(vals + [p]) for _ in range(4))
+            lines.append(f"{name} mul2 {a:064x} {b:064x} {c:064x} {d:064x}")
+            exp.append((a * b + c * d) * rinv % p)
         # from_u512's first operand is an arbitrary 256-bit value (derive/field.rs:29-48): unreduced multiplicand
         for _ in range(200):
             a, b = rng.randrange(1 << 256), rng.choice(vals)

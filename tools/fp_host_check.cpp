@@ -34,6 +34,13 @@ template <class P> static void run(const std::string& op, const std::string& sa,
 int main() {
     std::string f, op, a, b;
     while (std::cin >> f >> op >> a >> b) {
+        if (op == "mul2") {  // a*b + c*d with one reduction
+            std::string c, d;
+            std::cin >> c >> d;
+            if (f == "fr") put(fp_mul2<FrP>(parse<Fr>(a), parse<Fr>(b), parse<Fr>(c), parse<Fr>(d)));
+            else put(fp_mul2<FqP>(parse<Fq>(a), parse<Fq>(b), parse<Fq>(c), parse<Fq>(d)));
+            continue;
+        }
         if (f == "fr") run<FrP>(op, a, b); else run<FqP>(op, a, b);
     }
     return 0;
