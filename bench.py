@@ -335,7 +335,7 @@ def main():
 
         O.build()
         threads = O.hw_threads()
-        log_s = min(args.log_n, 20)
+        log_s = min(args.log_n, 22)
         ns = 1 << log_s
         sc = np.zeros((ns, 4), np.uint64)
         bs = np.zeros((ns, 8), np.uint64)

@@ -196,14 +196,18 @@ CQB_API int cqb_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes); /* str
 CQB_API int cqb_host_alloc_pinned(size_t bytes, void** h_out);
 CQB_API int cqb_host_free_pinned(void* h);
 
-/* measurement hooks: when profiling is on, every MSM records CUDA events between its kernels on the launch stream;
+/* measurement hooks: when profiling is on, every MSM records CUDA events around its kernels on the streams they run on;
  * cqb_msm_phase_ms returns how many of ms[0..7] = {count, scan, scatter, accumulate, merge, reduce, window_sum, final} it filled
- * for the most recent MSM (device time, milliseconds) */
+ * for the most recent MSM (device time, milliseconds, summed over the parts of a pipelined MSM — sort phases of part p+1
+ * overlap the accumulation of part p, so the phases can add up to more than the MSM's wall time) */
 CQB_API int cqb_msm_set_profiling(int on);
 CQB_API int cqb_msm_phase_ms(float* ms, int cap);
 
 /* tuning knobs for experiments (0 = automatic): MSM window bits */
 CQB_API int cqb_msm_set_window_bits(int c);
+/* number of point-range parts a large device-resident MSM is cut into (the sort phase of part p+1 runs on a second stream
+ * under the bucket accumulation of part p); 0 = automatic, 1 = no pipelining, at most 8. Results do not depend on it. */
+CQB_API int cqb_msm_set_parts(int parts);
 
 #ifdef __cplusplus
 }

@@ -70,6 +70,7 @@ SYMBOLS = [
     ("cqb_host_alloc_pinned", _int, [_sz, ctypes.POINTER(_vp)]),
     ("cqb_host_free_pinned", _int, [_vp]),
     ("cqb_msm_set_window_bits", _int, [_int]),
+    ("cqb_msm_set_parts", _int, [_int]),
     ("cqb_msm_set_profiling", _int, [_int]),
     ("cqb_msm_phase_ms", _int, [ctypes.POINTER(ctypes.c_float), _int]),
 ]

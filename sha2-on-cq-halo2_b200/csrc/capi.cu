@@ -310,20 +310,16 @@ int cqb_msm_bn254_g1(cqb_bases_t b, size_t offset, const uint64_t* scalars, size
             CQB_CUDA(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
             for (auto& e : g_copy_ev) CQB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
-        size_t per = (n + PARTS - 1) / PARTS;
+        size_t per = (n + PARTS - 1) / PARTS;  // the same split msm_run* makes for PARTS parts
         bool use_table = bs->table && n * 8 >= bs->n;
-        CQB_TRY(msm_job_begin(n, per, PARTS, use_table ? bs->table : nullptr, use_table ? bs->n : 0, bs->table_c));
         for (int p = 0; p < PARTS; p++) {
             size_t lo = (size_t)p * per, cnt = lo < n ? std::min(per, n - lo) : 0;
             if (cnt) CQB_CUDA(cudaMemcpyAsync((char*)g_scalars.p + lo * 32, scalars + lo * 4, cnt * 32, cudaMemcpyHostToDevice, g_copy_stream));
             CQB_CUDA(cudaEventRecord(g_copy_ev[p], g_copy_stream));
         }
-        for (int p = 0; p < PARTS; p++) {
-            size_t lo = (size_t)p * per, cnt = lo < n ? std::min(per, n - lo) : 0;
-            CQB_CUDA(cudaStreamWaitEvent(g_ctx.stream, g_copy_ev[p], 0));
-            CQB_TRY(msm_job_part(use_table ? bs->table : bs->d, offset + lo, (char*)g_scalars.p + lo * 32, cnt, p));
-        }
-        CQB_TRY(msm_job_finish(g_out.p));
+        // the sort of part p waits for its copy; the accumulation of part p-1 runs meanwhile on the main stream
+        if (use_table) CQB_TRY(msm_run_precomputed(bs->table, bs->n, bs->table_c, offset, g_scalars.p, nullptr, n, g_out.p, 1, PARTS, g_copy_ev));
+        else CQB_TRY(msm_run(bs->d, offset, g_scalars.p, nullptr, n, g_out.p, PARTS, g_copy_ev));
         return fetch_result(out_xy, is_inf);
     }
     if (n) CQB_CUDA(cudaMemcpyAsync(g_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, g_ctx.stream));
@@ -735,6 +731,13 @@ int cqb_msm_set_window_bits(int c) {
     LOCK;
     if (c != 0 && (c < 2 || c > 16)) return fail(CQB_E_BAD_ARG, "window bits must be 0 (auto) or 2..16");
     msm_set_window_bits(c);
+    return 0;
+}
+
+int cqb_msm_set_parts(int parts) {
+    LOCK;
+    if (parts < 0 || parts > 8) return fail(CQB_E_BAD_ARG, "parts must be 0 (auto) or 1..8");
+    msm_set_parts(parts);
     return 0;
 }
 

@@ -28,16 +28,16 @@ Fr fr_from_u64x4(const uint64_t* p);
 // ---- msm.cu ----
 // sum_i scalars[i] * bases[idx ? idx[i] : i]; d_out receives 64 B affine x||y followed by a uint32 identity flag
 // windowed layout; d_bases = element 0 of the base set, point id = idx ? idx[i] : offset + i
-int msm_run(const void* d_bases, size_t offset, const void* d_scalars, const uint32_t* d_idx, size_t n, void* d_out_xy_flag);
+// nparts: 0 = automatic (large MSMs are cut into point-range parts whose sort phase overlaps the previous part's bucket
+// accumulation on a second stream); ready[p] (optional, with nparts > 0): event the sort of part p waits for (H2D of its scalars)
+int msm_run(const void* d_bases, size_t offset, const void* d_scalars, const uint32_t* d_idx, size_t n, void* d_out_xy_flag, int nparts = 0,
+            const cudaEvent_t* ready = nullptr);
 // single bucket set over a precomputed table (row w = 2^(c w) * bases), table_n points per row
 // batch > 1: d_scalars holds `batch` contiguous vectors of n scalars, d_out receives batch x 80 B; each MSM gets its own
 // bucket set, all kernels run once for the whole batch (the latency-bound tails are shared)
 int msm_run_precomputed(const void* d_table, size_t table_n, int c, size_t offset, const void* d_scalars, const uint32_t* d_idx,
-                        size_t n, void* d_out_xy_flag, int batch = 1);
-// part-wise interface (same shape for every part; bucket arrays of the parts are summed in msm_job_finish)
-int msm_job_begin(size_t n_total, size_t part_cap, int nparts, const void* d_table, size_t table_n, int c);
-int msm_job_part(const void* d_bases_or_table, size_t offset, const void* d_scalars, size_t n, int part);
-int msm_job_finish(void* d_out);
+                        size_t n, void* d_out_xy_flag, int batch = 1, int nparts = 0, const cudaEvent_t* ready = nullptr);
+void msm_set_parts(int p);
 int msm_precompute_window_bits(size_t n);
 int msm_windows_for(int c);
 int msm_precompute_table(const void* d_bases, size_t n, int c, void* d_table);

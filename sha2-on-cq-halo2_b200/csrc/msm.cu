@@ -26,6 +26,7 @@
 // Roofline: integer pipe — 10 modmuls per bucket addition x nwin additions per point; the 64 B gather per addition is
 // < 10 % of HBM bandwidth at that rate.
 #include <algorithm>
+#include <vector>
 
 #include "internal.h"
 
@@ -520,27 +521,56 @@ __global__ void __launch_bounds__(128) msm_precompute_row_kernel(const uint4* __
 // -------------------------------------------------------------------------------------------------------------------
 static Scratch g_hist, g_sorted, g_buckets, g_partials, g_chunks, g_pre_tmp;
 
-// optional per-phase device timing (cudaEvents on the launch stream; no host sync until the times are read)
-static bool g_prof = false;
-static cudaEvent_t g_ev[9];
-static bool g_ev_made = false;
-static int g_ev_count = 0;
-void msm_set_profiling(bool on) { g_prof = on; }
-static void prof_mark(int i) {
-    if (!g_prof) return;
-    if (!g_ev_made) {
-        for (auto& e : g_ev) cudaEventCreate(&e);
-        g_ev_made = true;
-    }
-    cudaEventRecord(g_ev[i], ctx().stream);
-    g_ev_count = i + 1;
+// Second stream (high priority) for the sort phases (count / scan / scatter) of part p+1 of a large MSM, which overlap the
+// bucket accumulation of part p on the main stream: the sort is atomics/latency bound, the accumulation multiplier bound.
+constexpr int MSM_MAX_PARTS = 8;
+static cudaStream_t g_sort_stream = nullptr;
+static cudaEvent_t g_ev_start = nullptr, g_ev_sorted[MSM_MAX_PARTS];
+static int ensure_sort_stream() {
+    if (g_sort_stream) return 0;
+    int lo = 0, hi = 0;
+    CQB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CQB_CUDA(cudaStreamCreateWithPriority(&g_sort_stream, cudaStreamNonBlocking, hi));
+    CQB_CUDA(cudaEventCreateWithFlags(&g_ev_start, cudaEventDisableTiming));
+    for (auto& e : g_ev_sorted) CQB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return 0;
 }
-// ms[0..7] = count, scan, scatter, accumulate, merge, reduce, sum, final of the most recent MSM
+
+// optional per-phase device timing: spans of (phase id, start event, end event) recorded on whichever stream the phase
+// runs on; msm_phase_ms sums the spans of each phase (a pipelined MSM has one span per phase and part). No host sync
+// until the times are read.
+static bool g_prof = false;
+struct ProfSpan { int phase; cudaEvent_t a, b; };
+static std::vector<ProfSpan> g_spans;
+static size_t g_spans_used = 0;
+void msm_set_profiling(bool on) { g_prof = on; }
+static int prof_begin(int phase, cudaStream_t st) {
+    if (!g_prof) return -1;
+    if (g_spans_used == g_spans.size()) {
+        ProfSpan sp;
+        sp.phase = 0;
+        cudaEventCreate(&sp.a);
+        cudaEventCreate(&sp.b);
+        g_spans.push_back(sp);
+    }
+    g_spans[g_spans_used].phase = phase;
+    cudaEventRecord(g_spans[g_spans_used].a, st);
+    return (int)g_spans_used++;
+}
+static void prof_end(int h, cudaStream_t st) {
+    if (h >= 0) cudaEventRecord(g_spans[h].b, st);
+}
+// ms[0..7] = count, scan, scatter, accumulate, merge, reduce, sum, final of the most recent MSM (summed over its parts)
 int msm_phase_ms(float* ms, int cap) {
-    if (!g_prof || g_ev_count < 9) return 0;
-    cudaEventSynchronize(g_ev[8]);
-    int k = 0;
-    for (; k < 8 && k < cap; k++) cudaEventElapsedTime(&ms[k], g_ev[k], g_ev[k + 1]);
+    if (!g_prof || g_spans_used == 0) return 0;
+    int k = std::min(cap, 8);
+    for (int i = 0; i < k; i++) ms[i] = 0.f;
+    for (size_t i = 0; i < g_spans_used; i++) {
+        float t = 0.f;
+        cudaEventSynchronize(g_spans[i].b);
+        cudaEventElapsedTime(&t, g_spans[i].a, g_spans[i].b);
+        if (g_spans[i].phase < k) ms[g_spans[i].phase] += t;
+    }
     return k;
 }
 
@@ -551,6 +581,15 @@ void msm_release_all() {
     g_partials.release();
     g_chunks.release();
     g_pre_tmp.release();
+    for (auto& sp : g_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    g_spans.clear();
+    g_spans_used = 0;
+    if (g_sort_stream) {
+        cudaStreamDestroy(g_sort_stream);
+        g_sort_stream = nullptr;
+        cudaEventDestroy(g_ev_start);
+        for (auto& e : g_ev_sorted) cudaEventDestroy(e);
+    }
 }
 
 static int ceil_log2(size_t n) {
@@ -617,29 +656,81 @@ static MsmShape windowed_shape(size_t n) {
     return s;
 }
 
-// One PART of an MSM: count / scan / scatter / accumulate / merge of `n` scalars into bucket array number `part` (of
-// `nparts`, all with the same shape). A host-pointer MSM is cut into parts so that the H2D copy of part p+1 overlaps the
-// kernels of part p; msm_finish adds the parts' bucket arrays while it reduces them.
-// d_bases: windowed layout -> element 0 of the registered set (pid = offset + i); single-set layout -> the table base.
-static int msm_part(const void* d_bases, const void* d_scalars, const uint32_t* d_idx, size_t n, MsmShape s, int part, int nparts) {
-    cudaStream_t st = ctx().stream;
-    size_t hist_words = (size_t)s.nsets * s.stride;
-    uint32_t ntiles = (s.nb + 1 + SCAN_TILE - 1) / SCAN_TILE;
-    CQB_TRY(g_hist.ensure((hist_words * 3 + ntiles + 8) * 4));
-    uint32_t* hist = g_hist.as<uint32_t>();
-    uint32_t* offs = hist + hist_words;
-    uint32_t* cursor = offs + hist_words;
-    uint32_t* tile_sums = cursor + hist_words;
-    CQB_TRY(g_sorted.ensure((size_t)s.nsets * s.list_cap * 4));
-    size_t nbuckets = (size_t)s.nsets * s.nb;
-    CQB_TRY(g_buckets.ensure((size_t)nparts * nbuckets * 128));
-    uint4* buckets = g_buckets.as<uint4>() + (size_t)part * nbuckets * 8;
+// An MSM runs as `nparts` PARTS over contiguous point ranges (1 part unless it is large). Each part has its own histogram
+// / offsets / sorted list / bucket array; its SORT phase (count, scan, scatter) may run on the sort stream while the
+// ACCUMULATE phase (accumulate, merge) of the previous part runs on the main stream. msm_finish adds the parts' bucket
+// arrays while it reduces them. For a host-pointer MSM the sort of part p additionally waits for the H2D copy of part p.
+struct PartBuf {
+    uint32_t *hist, *offs, *cursor, *tile_sums;
+    uint32_t* sorted;
+    uint4* buckets;
+};
+struct PartPlan {
+    size_t hist_words, part_hist_words, nbuckets;
+    uint32_t ntiles;
+};
+static int plan_parts(const MsmShape& s, int nparts, PartPlan* pl) {
+    pl->hist_words = (size_t)s.nsets * s.stride;
+    pl->ntiles = (s.nb + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    pl->part_hist_words = pl->hist_words * 3 + pl->ntiles + 8;
+    pl->nbuckets = (size_t)s.nsets * s.nb;
+    CQB_TRY(g_hist.ensure((size_t)nparts * pl->part_hist_words * 4));
+    CQB_TRY(g_sorted.ensure((size_t)nparts * s.nsets * s.list_cap * 4));
+    CQB_TRY(g_buckets.ensure((size_t)nparts * pl->nbuckets * 128));
+    return 0;
+}
+static PartBuf part_buf(const MsmShape& s, const PartPlan& pl, int part) {
+    PartBuf b;
+    b.hist = g_hist.as<uint32_t>() + (size_t)part * pl.part_hist_words;
+    b.offs = b.hist + pl.hist_words;
+    b.cursor = b.offs + pl.hist_words;
+    b.tile_sums = b.cursor + pl.hist_words;
+    b.sorted = g_sorted.as<uint32_t>() + (size_t)part * s.nsets * s.list_cap;
+    b.buckets = g_buckets.as<uint4>() + (size_t)part * pl.nbuckets * 8;
+    return b;
+}
 
+// d_bases: windowed layout -> element 0 of the registered set (pid = offset + i); single-set layout -> the table base.
+static int msm_sort_phase(const void* d_scalars, const uint32_t* d_idx, size_t n, const MsmShape& s, const PartPlan& pl, const PartBuf& b,
+                          cudaStream_t st) {
+    CQB_CUDA(cudaMemsetAsync(b.hist, 0, pl.hist_words * 4, st));
+    int h = prof_begin(0, st);
+    unsigned gN = (unsigned)((n + 255) / 256);
+    const dim3 gridN(gN, s.single ? (unsigned)s.nsets : 1u);
+    msm_count_kernel<<<gridN, 256, 0, st>>>((const uint4*)d_scalars, n, s, b.hist);
+    CQB_LAUNCHED();
+    prof_end(h, st);
+    h = prof_begin(1, st);
+    if (s.single && s.nb > 32768) {
+        for (int k = 0; k < s.nsets; k++) {  // one tiled scan per bucket set
+            const size_t o = (size_t)k * s.stride;
+            scan_tile_sums_kernel<<<pl.ntiles, 1024, 0, st>>>(b.hist + o, s.nb, b.tile_sums);
+            CQB_LAUNCHED();
+            scan_tile_offsets_kernel<<<1, 1024, 0, st>>>(b.tile_sums, pl.ntiles);
+            CQB_LAUNCHED();
+            scan_apply_kernel<<<pl.ntiles, 1024, 0, st>>>(b.hist + o, s.nb, b.tile_sums, b.offs + o, b.cursor + o);
+            CQB_LAUNCHED();
+        }
+    } else {
+        msm_scan_kernel<<<s.nsets, 1024, 0, st>>>(b.hist, b.offs, b.cursor, s);
+        CQB_LAUNCHED();
+    }
+    prof_end(h, st);
+    h = prof_begin(2, st);
+    msm_scatter_kernel<<<gridN, 256, 0, st>>>((const uint4*)d_scalars, d_idx, n, s, b.cursor, b.sorted);
+    CQB_LAUNCHED();
+    prof_end(h, st);
+    CQB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int msm_acc_phase(const void* d_bases, size_t n, const MsmShape& s, const PartPlan& pl, const PartBuf& b, cudaStream_t st) {
     // chunking of the bucket-sorted lists: aim for >= ~150k chunk threads, 16..256 entries each
     size_t entries = (size_t)n * s.nwin;
     int seg_log = 8;
     while (seg_log > 4 && (entries >> seg_log) < 150000) seg_log--;
-    uint32_t cpw = (uint32_t)((s.list_cap + ((size_t)1 << seg_log) - 1) >> seg_log);  // chunks per set (upper bound)
+    size_t list_len = s.single ? entries : n;  // entries one set's list can hold for this part
+    uint32_t cpw = (uint32_t)((list_len + ((size_t)1 << seg_log) - 1) >> seg_log);  // chunks per set (upper bound)
     size_t nchunks = (size_t)s.nsets * cpw;
     uint32_t big_cap = (uint32_t)(s.nsets * (cpw / MERGE_LONG + 2));
     CQB_TRY(g_chunks.ensure(nchunks * 256 + 16 + (size_t)big_cap * 8));
@@ -647,51 +738,26 @@ static int msm_part(const void* d_bases, const void* d_scalars, const uint32_t* 
     uint4* tail = head + nchunks * 8;
     uint32_t* big_count = (uint32_t*)(tail + nchunks * 8);
     uint2* big_list = (uint2*)(big_count + 4);
-
-    CQB_CUDA(cudaMemsetAsync(hist, 0, hist_words * 4, st));
-    CQB_CUDA(cudaMemsetAsync(buckets, 0, nbuckets * 128, st));
+    CQB_CUDA(cudaMemsetAsync(b.buckets, 0, pl.nbuckets * 128, st));
     CQB_CUDA(cudaMemsetAsync(big_count, 0, 16, st));
-    g_ev_count = 0;
-    prof_mark(0);
-    unsigned gN = (unsigned)((n + 255) / 256);
-    const dim3 gridN(gN, s.single ? (unsigned)s.nsets : 1u);
-    msm_count_kernel<<<gridN, 256, 0, st>>>((const uint4*)d_scalars, n, s, hist);
+    int h = prof_begin(3, st);
+    msm_accumulate_kernel<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>((const uint4*)d_bases, b.sorted, b.offs, s, seg_log, cpw, b.buckets,
+                                                                              head, tail);
     CQB_LAUNCHED();
-    prof_mark(1);
-    if (s.single && s.nb > 32768) {
-        for (int b = 0; b < s.nsets; b++) {  // one tiled scan per bucket set
-            const size_t o = (size_t)b * s.stride;
-            scan_tile_sums_kernel<<<ntiles, 1024, 0, st>>>(hist + o, s.nb, tile_sums);
-            CQB_LAUNCHED();
-            scan_tile_offsets_kernel<<<1, 1024, 0, st>>>(tile_sums, ntiles);
-            CQB_LAUNCHED();
-            scan_apply_kernel<<<ntiles, 1024, 0, st>>>(hist + o, s.nb, tile_sums, offs + o, cursor + o);
-            CQB_LAUNCHED();
-        }
-    } else {
-        msm_scan_kernel<<<s.nsets, 1024, 0, st>>>(hist, offs, cursor, s);
-        CQB_LAUNCHED();
-    }
-    prof_mark(2);
-    msm_scatter_kernel<<<gridN, 256, 0, st>>>((const uint4*)d_scalars, d_idx, n, s, cursor, g_sorted.as<uint32_t>());
+    prof_end(h, st);
+    h = prof_begin(4, st);
+    msm_merge_kernel<<<(unsigned)((pl.nbuckets + 127) / 128), 128, 0, st>>>(b.offs, s, seg_log, cpw, b.buckets, head, tail, big_count, big_list,
+                                                                             big_cap);
     CQB_LAUNCHED();
-    prof_mark(3);
-    msm_accumulate_kernel<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>((const uint4*)d_bases, g_sorted.as<uint32_t>(), offs, s, seg_log, cpw,
-                                                                              buckets, head, tail);
+    msm_merge_big_kernel<<<big_cap, 128, 0, st>>>(b.offs, s, seg_log, cpw, b.buckets, head, tail, big_count, big_list);
     CQB_LAUNCHED();
-    prof_mark(4);
-    msm_merge_kernel<<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>(offs, s, seg_log, cpw, buckets, head, tail, big_count,
-                                                                          big_list, big_cap);
-    CQB_LAUNCHED();
-    msm_merge_big_kernel<<<big_cap, 128, 0, st>>>(offs, s, seg_log, cpw, buckets, head, tail, big_count, big_list);
-    CQB_LAUNCHED();
-    prof_mark(5);
+    prof_end(h, st);
     CQB_CUDA(cudaGetLastError());
     return 0;
 }
 
 // bucket reduction over the sum of the parts' bucket arrays, window combination, affine normalisation
-static int msm_finish(MsmShape s, int nparts, void* d_out) {
+static int msm_finish(const MsmShape& s, int nparts, void* d_out) {
     cudaStream_t st = ctx().stream;
     size_t nbuckets = (size_t)s.nsets * s.nb;
     // tpw threads per set, ch buckets each (both powers of two, ch >= 2)
@@ -704,9 +770,11 @@ static int msm_finish(MsmShape s, int nparts, void* d_out) {
     uint4* sums1 = partials + (size_t)s.nsets * tpw * 8;
     uint4* wins = sums1 + (size_t)s.nsets * lvl1 * 8;
     size_t nred = (size_t)s.nsets * tpw;
+    int h = prof_begin(5, st);
     msm_reduce_kernel<<<(unsigned)((nred + 127) / 128), 128, 0, st>>>(g_buckets.as<uint4>(), s, tpw, ch, nparts, nbuckets * 8, partials);
     CQB_LAUNCHED();
-    prof_mark(6);
+    prof_end(h, st);
+    h = prof_begin(6, st);
     if (lvl1 > 1) {
         xyzz_sum_kernel<<<s.nsets * lvl1, 128, 0, st>>>(partials, tpw, lvl1, sums1);
         CQB_LAUNCHED();
@@ -716,18 +784,73 @@ static int msm_finish(MsmShape s, int nparts, void* d_out) {
         xyzz_sum_kernel<<<s.nsets, 128, 0, st>>>(partials, tpw, 1, wins);
         CQB_LAUNCHED();
     }
-    prof_mark(7);
+    prof_end(h, st);
+    h = prof_begin(7, st);
     if (s.single && s.nsets > 1) msm_final_batch_kernel<<<s.nsets, 32, 0, st>>>(wins, (uint4*)d_out);
     else msm_final_kernel<<<1, 32, 0, st>>>(wins, s, (uint4*)d_out);
     CQB_LAUNCHED();
-    prof_mark(8);
+    prof_end(h, st);
     CQB_CUDA(cudaGetLastError());
     return 0;
 }
 
-static int msm_run_shape(const void* d_bases, const void* d_scalars, const uint32_t* d_idx, size_t n, MsmShape s, void* d_out) {
-    CQB_TRY(msm_part(d_bases, d_scalars, d_idx, n, s, 0, 1));
-    return msm_finish(s, 1, d_out);
+// number of parts a device-resident MSM of n points is cut into (sort of part p+1 overlaps the accumulation of part p)
+static int g_forced_parts = 0;
+void msm_set_parts(int p) { g_forced_parts = p; }
+static int auto_parts(size_t n, const MsmShape& s, const uint32_t* d_idx) {
+    if (s.nsets > 1 && s.single) return 1;  // batched MSMs: one launch sequence for the whole batch
+    if (d_idx) return 1;
+    if (g_forced_parts > 0) return std::min(g_forced_parts, MSM_MAX_PARTS);
+    // Measured (B200, 2^20..2^24, tools/sweep_msm.py with CQB_PARTS=1/2/4/8): overlapping the sort with the accumulation does
+    // not pay for device-resident scalars — the co-resident sort CTAs take register-file space from the accumulate warps and
+    // slow them by about the time the sort would have taken alone (2^24: 39.5 / 39.3 / 41.1 / 42.1 ms). Parts are used only
+    // where there is a copy to hide (host-pointer MSM from pinned memory).
+    (void)n;
+    return 1;
+}
+
+// `ready[p]` (optional): event the sort of part p must wait for (the H2D copy of its scalars)
+static int msm_run_shape(const void* d_bases, const void* d_scalars, const uint32_t* d_idx, size_t n, MsmShape s, int nparts,
+                         const cudaEvent_t* ready, void* d_out) {
+    cudaStream_t st = ctx().stream;
+    g_spans_used = 0;
+    if (nparts > MSM_MAX_PARTS) nparts = MSM_MAX_PARTS;
+    size_t per = (n + nparts - 1) / nparts;
+    nparts = (int)((n + per - 1) / per);
+    if (nparts <= 1 && !ready) {
+        PartPlan pl;
+        CQB_TRY(plan_parts(s, 1, &pl));
+        PartBuf b = part_buf(s, pl, 0);
+        CQB_TRY(msm_sort_phase(d_scalars, d_idx, n, s, pl, b, st));
+        CQB_TRY(msm_acc_phase(d_bases, n, s, pl, b, st));
+        return msm_finish(s, 1, d_out);
+    }
+    // per-part list capacity
+    s.list_cap = s.single ? per * (size_t)s.nwin : per;
+    PartPlan pl;
+    CQB_TRY(plan_parts(s, nparts, &pl));
+    CQB_TRY(ensure_sort_stream());
+    const uint32_t offset0 = s.offset;
+    CQB_CUDA(cudaEventRecord(g_ev_start, st));  // the sort stream starts after everything already queued on the main stream
+    CQB_CUDA(cudaStreamWaitEvent(g_sort_stream, g_ev_start, 0));
+    for (int p = 0; p < nparts; p++) {
+        size_t lo = (size_t)p * per, cnt = std::min(per, n - lo);
+        MsmShape sp = s;
+        sp.offset = offset0 + (uint32_t)lo;
+        PartBuf b = part_buf(s, pl, p);
+        if (ready) CQB_CUDA(cudaStreamWaitEvent(g_sort_stream, ready[p], 0));
+        CQB_TRY(msm_sort_phase((const char*)d_scalars + lo * 32, d_idx ? d_idx + lo : nullptr, cnt, sp, pl, b, g_sort_stream));
+        CQB_CUDA(cudaEventRecord(g_ev_sorted[p], g_sort_stream));
+    }
+    for (int p = 0; p < nparts; p++) {
+        size_t lo = (size_t)p * per, cnt = std::min(per, n - lo);
+        MsmShape sp = s;
+        sp.offset = offset0 + (uint32_t)lo;
+        PartBuf b = part_buf(s, pl, p);
+        CQB_CUDA(cudaStreamWaitEvent(st, g_ev_sorted[p], 0));
+        CQB_TRY(msm_acc_phase(d_bases, cnt, sp, pl, b, st));
+    }
+    return msm_finish(s, nparts, d_out);
 }
 
 static int msm_empty(void* d_out) {
@@ -737,17 +860,18 @@ static int msm_empty(void* d_out) {
 }
 
 // windowed layout: sum_i scalars[i] * bases[idx ? idx[i] : offset + i]
-int msm_run(const void* d_bases, size_t offset, const void* d_scalars, const uint32_t* d_idx, size_t n, void* d_out) {
+int msm_run(const void* d_bases, size_t offset, const void* d_scalars, const uint32_t* d_idx, size_t n, void* d_out, int nparts,
+            const cudaEvent_t* ready) {
     if (n == 0) return msm_empty(d_out);  // best_multiexp of empty slices returns the identity
     if (n > ((size_t)1 << 30)) return fail(CQB_E_BAD_SIZE, "MSM of %zu points exceeds the supported 2^30", n);
     MsmShape s = windowed_shape(n);
     s.offset = (uint32_t)offset;
-    return msm_run_shape(d_bases, d_scalars, d_idx, n, s, d_out);
+    return msm_run_shape(d_bases, d_scalars, d_idx, n, s, nparts > 0 ? nparts : auto_parts(n, s, d_idx), ready, d_out);
 }
 
 // single-set layout over a precomputed table of `table_n` points per row built with window bits c
 int msm_run_precomputed(const void* d_table, size_t table_n, int c, size_t offset, const void* d_scalars, const uint32_t* d_idx, size_t n,
-                        void* d_out, int batch) {
+                        void* d_out, int batch, int nparts, const cudaEvent_t* ready) {
     if (n == 0) {
         for (int b = 0; b < batch; b++) CQB_TRY(msm_empty((char*)d_out + (size_t)b * 80));
         return 0;
@@ -764,41 +888,8 @@ int msm_run_precomputed(const void* d_table, size_t table_n, int c, size_t offse
     s.list_cap = n * (size_t)s.nwin;
     if (s.list_cap >= ((size_t)1 << 32) || (size_t)s.nwin * table_n >= ((size_t)1 << 31))
         return fail(CQB_E_BAD_SIZE, "precomputed MSM: %zu x %d entries exceed the 32-bit index range", n, s.nwin);
-    return msm_run_shape(d_table, d_scalars, d_idx, n, s, d_out);
+    return msm_run_shape(d_table, d_scalars, d_idx, n, s, nparts > 0 ? nparts : auto_parts(n, s, d_idx), ready, d_out);
 }
-
-// ---- part-wise interface used by the host-pointer entry points to overlap H2D with compute ---------------------------
-static MsmShape g_job_shape;
-static int g_job_parts = 0;
-int msm_job_begin(size_t n_total, size_t part_cap, int nparts, const void* d_table, size_t table_n, int c) {
-    (void)d_table;
-    if (table_n) {
-        MsmShape s;
-        s.c = c;
-        s.nwin = msm_windows_for(c);
-        s.nsets = 1;
-        s.single = 1;
-        s.nb = 1u << (c - 1);
-        s.stride = s.nb + 2;
-        s.table_n = (uint32_t)table_n;
-        s.offset = 0;
-        s.list_cap = part_cap * (size_t)s.nwin;
-        if (s.list_cap >= ((size_t)1 << 32) || (size_t)s.nwin * table_n >= ((size_t)1 << 31))
-            return fail(CQB_E_BAD_SIZE, "precomputed MSM: %zu x %d entries exceed the 32-bit index range", part_cap, s.nwin);
-        g_job_shape = s;
-    } else {
-        g_job_shape = windowed_shape(n_total);
-        g_job_shape.list_cap = part_cap;
-    }
-    g_job_parts = nparts;
-    return 0;
-}
-int msm_job_part(const void* d_bases_or_table, size_t offset, const void* d_scalars, size_t n, int part) {
-    MsmShape s = g_job_shape;
-    s.offset = (uint32_t)offset;
-    return msm_part(d_bases_or_table, d_scalars, nullptr, n, s, part, g_job_parts);
-}
-int msm_job_finish(void* d_out) { return msm_finish(g_job_shape, g_job_parts, d_out); }
 
 int g1_sum_affine_run(const void* d_points, size_t n, void* d_out) {
     g1_sum_affine_kernel<<<1, 128, 0, ctx().stream>>>((const uint4*)d_points, n, (uint4*)d_out);

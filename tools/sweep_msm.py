@@ -16,6 +16,7 @@ stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 L.check(lib.cqb_set_stream(ctypes.c_void_p(stream.cuda_stream)))
 L.check(lib.cqb_msm_set_profiling(1))
+L.check(lib.cqb_msm_set_parts(int(os.environ.get("CQB_PARTS", "0"))))  # 0 = automatic
 logs = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else "16,18,20,22,24".split(","))]
 cs = [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else "0".split(","))]
 nmax = 1 << max(logs)
