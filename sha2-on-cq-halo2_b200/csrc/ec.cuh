@@ -32,15 +32,36 @@ struct G1Xyzz {
     }
 };
 
-#define FQM(a, b) fp_mul<FqP>(a, b)
-#define FQS(a) fp_sqr<FqP>(a)
+// Multiplier policies. FqInline expands every multiplication in place (straight-line code, ~2.8 KB per modmul): right for
+// the throughput kernels, where several warps per scheduler walk one hot loop. FqCall routes them through ONE non-inlined
+// copy per kernel: the latency-bound tail kernels (bucket merge / reduction / final sums: chains of dependent XYZZ
+// operations executed by one warp per scheduler) otherwise run out of the instruction caches — a single inlined g1_add
+// is ~40 KB of code — and stall on instruction fetch.
+struct FqInline {
+    static CQB_HD Fq mul(const Fq& a, const Fq& b) { return fp_mul<FqP>(a, b); }
+    static CQB_HD Fq sqr(const Fq& a) { return fp_sqr<FqP>(a); }
+    static CQB_HD Fq msub(const Fq& a, const Fq& b, const Fq& c, const Fq& d) { return fp_mul2<FqP>(a, b, fp_neg<FqP>(c), d); }
+};
+#if defined(__CUDACC__)
+struct FqCall {
+    static __device__ __noinline__ Fq mul(Fq a, Fq b) { return fp_mul<FqP>(a, b); }
+    static __device__ __forceinline__ Fq sqr(const Fq& a) { return mul(a, a); }
+    static __device__ __noinline__ Fq msub(Fq a, Fq b, Fq c, Fq d) { return fp_mul2<FqP>(a, b, fp_neg<FqP>(c), d); }
+};
+#else
+typedef FqInline FqCall;
+#endif
+
+#define FQM(a, b) M::mul(a, b)
+#define FQS(a) M::sqr(a)
 #define FQA(a, b) fp_add<FqP>(a, b)
 #define FQSUB(a, b) fp_sub<FqP>(a, b)
 // a*b - c*d with one Montgomery reduction (the negation is 8 ALU ops; the fused product saves 72 wide multiplies)
-#define FQMSUB(a, b, c, d) fp_mul2<FqP>(a, b, fp_neg<FqP>(c), d)
+#define FQMSUB(a, b, c, d) M::msub(a, b, c, d)
 
 // 2*(x,y) for an affine, non-identity point (mdbl-2008-s-1). y == 0 cannot happen on this curve (no 2-torsion), but
 // the formula degrades gracefully to ZZ = 0 = identity anyway.
+template <class M = FqInline>
 CQB_HD G1Xyzz g1_double_affine(const Fq& x1, const Fq& y1) {
     G1Xyzz r;
     Fq u = fp_dbl<FqP>(y1);
@@ -57,6 +78,7 @@ CQB_HD G1Xyzz g1_double_affine(const Fq& x1, const Fq& y1) {
 }
 
 // 2*P (dbl-2008-s-1)
+template <class M = FqInline>
 CQB_HD G1Xyzz g1_double(const G1Xyzz& p) {
     if (p.is_identity()) return p;
     G1Xyzz r;
@@ -74,6 +96,7 @@ CQB_HD G1Xyzz g1_double(const G1Xyzz& p) {
 }
 
 // acc += (x2, y2) with (x2,y2) affine and NOT the identity (madd-2008-s); all exceptional cases handled.
+template <class M = FqInline>
 CQB_HD void g1_madd(G1Xyzz& acc, const Fq& x2, const Fq& y2) {
     if (acc.is_identity()) {
         acc.x = x2; acc.y = y2; acc.zz = Fq::one(); acc.zzz = Fq::one();
@@ -84,7 +107,7 @@ CQB_HD void g1_madd(G1Xyzz& acc, const Fq& x2, const Fq& y2) {
     Fq p = FQSUB(u2, acc.x);
     Fq r = FQSUB(s2, acc.y);
     if (p.is_zero()) {
-        if (r.is_zero()) acc = g1_double_affine(x2, y2);  // same point: reference curve.rs:866-868
+        if (r.is_zero()) acc = g1_double_affine<M>(x2, y2);  // same point: reference curve.rs:866-868
         else acc = G1Xyzz::identity();                    // opposite points: curve.rs:869-870
         return;
     }
@@ -100,6 +123,7 @@ CQB_HD void g1_madd(G1Xyzz& acc, const Fq& x2, const Fq& y2) {
 }
 
 // acc += b (add-2008-s), all exceptional cases handled.
+template <class M = FqInline>
 CQB_HD void g1_add(G1Xyzz& acc, const G1Xyzz& b) {
     if (b.is_identity()) return;
     if (acc.is_identity()) { acc = b; return; }
@@ -110,7 +134,7 @@ CQB_HD void g1_add(G1Xyzz& acc, const G1Xyzz& b) {
     Fq p = FQSUB(u2, u1);
     Fq r = FQSUB(s2, s1);
     if (p.is_zero()) {
-        if (r.is_zero()) acc = g1_double(acc);  // reference curve.rs:818-820
+        if (r.is_zero()) acc = g1_double<M>(acc);  // reference curve.rs:818-820
         else acc = G1Xyzz::identity();          // curve.rs:821-823
         return;
     }
@@ -126,6 +150,7 @@ CQB_HD void g1_add(G1Xyzz& acc, const G1Xyzz& b) {
 }
 
 // XYZZ -> affine normal form (what the reference's to_affine / batch_normalize produce, curve.rs:399-412): one inversion.
+template <class M = FqInline>
 CQB_HD G1Affine g1_to_affine(const G1Xyzz& p) {
     G1Affine a;
     if (p.is_identity()) { a.x = Fq::zero(); a.y = Fq::zero(); return a; }
@@ -138,6 +163,7 @@ CQB_HD G1Affine g1_to_affine(const G1Xyzz& p) {
 }
 
 // same result through the low-latency binary inversion: for kernels where a single thread normalises a single point
+template <class M = FqInline>
 CQB_HD G1Affine g1_to_affine_lowlat(const G1Xyzz& p) {
     G1Affine a;
     if (p.is_identity()) { a.x = Fq::zero(); a.y = Fq::zero(); return a; }

@@ -307,6 +307,14 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint4* __rest
     else st_xyzz(tail + gid * 8, acc);
 }
 
+// the kernels from here to the precompute kernel are latency-bound chains of XYZZ operations: compact code (ec.cuh FqCall)
+typedef FqCall TailMul;
+// one copy of each point operation per kernel as well (a g1_add is still ~1.2k instructions around its 13 multiplier calls)
+__device__ __noinline__ G1Xyzz tail_add_fn(G1Xyzz a, G1Xyzz b) { g1_add<TailMul>(a, b); return a; }
+__device__ __noinline__ G1Xyzz tail_double_fn(G1Xyzz a) { return g1_double<TailMul>(a); }
+__device__ __forceinline__ void tail_add(G1Xyzz& acc, const G1Xyzz& b) { acc = tail_add_fn(acc, b); }
+__device__ __forceinline__ G1Xyzz tail_double(const G1Xyzz& a) { return tail_double_fn(a); }
+
 // (4b) one thread per bucket: add up the head/tail partials of the chunks the bucket overlaps. Buckets that span more
 // than MERGE_LONG chunks (heavily repeated digits) are queued for msm_merge_big_kernel.
 constexpr uint32_t MERGE_LONG = 32;
@@ -341,26 +349,29 @@ __global__ void __launch_bounds__(128) msm_merge_kernel(const uint32_t* __restri
     for (uint32_t k = kf; k <= kl; k++) {
         bool isfirst = start <= (k << seg_log);
         G1Xyzz p = ld_xyzz((isfirst ? head : tail) + ((size_t)w * cpw + k) * 8);
-        g1_add(acc, p);
+        tail_add(acc, p);
     }
     st_xyzz(buckets + gid * 8, acc);
 }
 
-// shared-memory tree of XYZZ adds over 128 threads; result valid in thread 0
-__device__ __forceinline__ G1Xyzz block_sum_128(G1Xyzz acc, uint4* sm) {
+// shared-memory tree of XYZZ adds over NT threads (power of two); result valid in thread 0
+template <int NT>
+__device__ __forceinline__ G1Xyzz block_sum(G1Xyzz acc, uint4* sm) {
     const int tid = threadIdx.x;
     st_xyzz(sm + tid * 8, acc);
     __syncthreads();
-    for (int half = 64; half >= 1; half >>= 1) {
+#pragma unroll 1
+    for (int half = NT / 2; half >= 1; half >>= 1) {
         if (tid < half) {
             G1Xyzz a = ld_xyzz(sm + tid * 8), b2 = ld_xyzz(sm + (tid + half) * 8);
-            g1_add(a, b2);
+            tail_add(a, b2);
             st_xyzz(sm + tid * 8, a);
         }
         __syncthreads();
     }
     return ld_xyzz(sm);
 }
+__device__ __forceinline__ G1Xyzz block_sum_128(G1Xyzz acc, uint4* sm) { return block_sum<128>(acc, sm); }
 
 // (4c) one CTA per queued long bucket: threads stride over its chunk partials, then a shared-memory tree of XYZZ adds
 __global__ void __launch_bounds__(128) msm_merge_big_kernel(const uint32_t* __restrict__ offs, MsmShape s, int seg_log, uint32_t cpw,
@@ -378,40 +389,48 @@ __global__ void __launch_bounds__(128) msm_merge_big_kernel(const uint32_t* __re
     for (uint32_t k = kf + threadIdx.x; k <= kl; k += 128) {
         bool isfirst = start <= (k << seg_log);
         G1Xyzz p = ld_xyzz((isfirst ? head : tail) + ((size_t)w * cpw + k) * 8);
-        g1_add(acc, p);
+        tail_add(acc, p);
     }
     G1Xyzz r = block_sum_128(acc, sm);
     if (threadIdx.x == 0) st_xyzz(buckets + ((size_t)w * s.nb + (d - 1)) * 8, r);
 }
 
-// (5) per-set weighted bucket sum, chunked: thread t of set w owns bucket ids [t*CH + 1, (t+1)*CH]
-__global__ void __launch_bounds__(128) msm_reduce_kernel(const uint4* __restrict__ buckets, MsmShape s, uint32_t tpw, uint32_t ch,
-                                                         int nparts, size_t part_stride, uint4* __restrict__ partials) {
+// (5) per-set weighted bucket sum, chunked: thread t of set w owns bucket ids [t*CH + 1, (t+1)*CH]; the CTA's RED_CTA
+// results are tree-added in shared memory and ONE partial per CTA is stored (tpw is a multiple of RED_CTA, so a CTA never
+// straddles two sets). Sized for latency, not occupancy: about one warp per SM sub-partition (the whole phase is a chain
+// of dependent XYZZ operations per thread; more threads with shorter chains only add multiply-by-t overhead).
+constexpr int RED_CTA = 32;
+__global__ void __launch_bounds__(RED_CTA) msm_reduce_kernel(const uint4* __restrict__ buckets, MsmShape s, uint32_t tpw, uint32_t ch,
+                                                             int nparts, size_t part_stride, uint4* __restrict__ partials) {
+    __shared__ uint4 sm[RED_CTA * 8];
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (size_t)s.nsets * tpw) return;
-    uint32_t w = (uint32_t)(gid / tpw), t = (uint32_t)(gid % tpw);
-    const uint4* b = buckets + ((size_t)w * s.nb + (size_t)t * ch) * 8;
-    G1Xyzz running = G1Xyzz::identity(), acc = G1Xyzz::identity();
-    for (int j = (int)ch - 1; j >= 0; j--) {  // summation by parts, reference arithmetic.rs:95-99
-        G1Xyzz bj = ld_xyzz(b + (size_t)j * 8);
-        for (int p = 1; p < nparts; p++) {  // parts of a pipelined host-pointer MSM
-            G1Xyzz bp = ld_xyzz(b + (size_t)p * part_stride + (size_t)j * 8);
-            g1_add(bj, bp);
+    G1Xyzz acc = G1Xyzz::identity();
+    const uint32_t w = (uint32_t)(gid / tpw), t = (uint32_t)(gid % tpw);
+    if (w < (uint32_t)s.nsets && (size_t)t * ch < s.nb) {  // tpw is padded to a multiple of RED_CTA for tiny bucket sets
+        const uint4* b = buckets + ((size_t)w * s.nb + (size_t)t * ch) * 8;
+        G1Xyzz running = G1Xyzz::identity();
+        for (int j = (int)ch - 1; j >= 0; j--) {  // summation by parts, reference arithmetic.rs:95-99
+            G1Xyzz bj = ld_xyzz(b + (size_t)j * 8);
+            for (int p = 1; p < nparts; p++) {  // parts of a pipelined host-pointer MSM
+                G1Xyzz bp = ld_xyzz(b + (size_t)p * part_stride + (size_t)j * 8);
+                tail_add(bj, bp);
+            }
+            tail_add(running, bj);
+            tail_add(acc, running);
         }
-        g1_add(running, bj);
-        g1_add(acc, running);
-    }
-    // acc = sum (j+1) * B ; add (t*ch) * running
-    if (t != 0 && !running.is_identity()) {
-        G1Xyzz m = G1Xyzz::identity();
-        for (int bit = 31 - __clz(t); bit >= 0; bit--) {
-            m = g1_double(m);
-            if ((t >> bit) & 1u) g1_add(m, running);
+        // acc = sum (j+1) * B ; add (t*ch) * running
+        if (t != 0 && !running.is_identity()) {
+            G1Xyzz m = G1Xyzz::identity();
+            for (int bit = 31 - __clz(t); bit >= 0; bit--) {
+                m = tail_double(m);
+                if ((t >> bit) & 1u) tail_add(m, running);
+            }
+            for (uint32_t x = ch; x > 1; x >>= 1) m = tail_double(m);  // ch is a power of two
+            tail_add(acc, m);
         }
-        for (uint32_t x = ch; x > 1; x >>= 1) m = g1_double(m);  // ch is a power of two
-        g1_add(acc, m);
     }
-    st_xyzz(partials + gid * 8, acc);
+    G1Xyzz r = block_sum<RED_CTA>(acc, sm);
+    if (threadIdx.x == 0) st_xyzz(partials + (size_t)blockIdx.x * 8, r);
 }
 
 // (5b) segmented tree sum: set w has `count` XYZZ inputs; CTA (w, j) adds inputs [j*2048, (j+1)*2048) into out[w][j]
@@ -423,7 +442,7 @@ __global__ void __launch_bounds__(128) xyzz_sum_kernel(const uint4* __restrict__
     G1Xyzz acc = G1Xyzz::identity();
     for (uint32_t k = lo + threadIdx.x; k < hi; k += 128) {
         G1Xyzz p = ld_xyzz(in + ((size_t)w * count + k) * 8);
-        g1_add(acc, p);
+        tail_add(acc, p);
     }
     G1Xyzz r = block_sum_128(acc, sm);
     if (threadIdx.x == 0) st_xyzz(out + ((size_t)w * out_per_set + j) * 8, r);
@@ -435,11 +454,11 @@ __global__ void msm_final_kernel(const uint4* __restrict__ wins, MsmShape s, uin
     G1Xyzz acc = G1Xyzz::identity();
     for (int w = s.nsets - 1; w >= 0; w--) {
         if (!acc.is_identity())
-            for (int k = 0; k < s.c; k++) acc = g1_double(acc);  // reference arithmetic.rs:47-49
+            for (int k = 0; k < s.c; k++) acc = tail_double(acc);  // reference arithmetic.rs:47-49
         G1Xyzz ww = ld_xyzz(wins + (size_t)w * 8);
-        g1_add(acc, ww);
+        tail_add(acc, ww);
     }
-    G1Affine a = g1_to_affine_lowlat(acc);
+    G1Affine a = g1_to_affine_lowlat<TailMul>(acc);
     st_fq(out, a.x);
     st_fq(out + 2, a.y);
     uint32_t inf = acc.is_identity() ? 1u : 0u;
@@ -451,7 +470,7 @@ __global__ void msm_final_batch_kernel(const uint4* __restrict__ wins, uint4* __
     if (threadIdx.x != 0) return;
     const uint32_t b = blockIdx.x;
     G1Xyzz acc = ld_xyzz(wins + (size_t)b * 8);
-    G1Affine a = g1_to_affine_lowlat(acc);
+    G1Affine a = g1_to_affine_lowlat<TailMul>(acc);
     st_fq(out + (size_t)b * 5, a.x);
     st_fq(out + (size_t)b * 5 + 2, a.y);
     out[(size_t)b * 5 + 4] = make_uint4(acc.is_identity() ? 1u : 0u, 0, 0, 0);
@@ -464,11 +483,11 @@ __global__ void __launch_bounds__(128) g1_sum_affine_kernel(const uint4* __restr
     for (size_t j = threadIdx.x; j < n; j += 128) {
         Fq x = ld_fq(pts + j * 4), y = ld_fq(pts + j * 4 + 2);
         if (x.is_zero() && y.is_zero()) continue;
-        g1_madd(acc, x, y);
+        g1_madd<TailMul>(acc, x, y);
     }
     G1Xyzz r = block_sum_128(acc, sm);
     if (threadIdx.x == 0) {
-        G1Affine a = g1_to_affine_lowlat(r);
+        G1Affine a = g1_to_affine_lowlat<TailMul>(r);
         st_fq(out, a.x);
         st_fq(out + 2, a.y);
         out[4] = make_uint4(r.is_identity() ? 1u : 0u, 0, 0, 0);
@@ -760,28 +779,30 @@ static int msm_acc_phase(const void* d_bases, size_t n, const MsmShape& s, const
 static int msm_finish(const MsmShape& s, int nparts, void* d_out) {
     cudaStream_t st = ctx().stream;
     size_t nbuckets = (size_t)s.nsets * s.nb;
-    // tpw threads per set, ch buckets each (both powers of two, ch >= 2)
-    uint32_t tpw = std::min<uint32_t>(s.nb / 2, s.single ? (s.nsets == 1 ? 65536u : 16384u) : 1024u);
-    if (tpw < 1) tpw = 1;
-    uint32_t ch = s.nb / tpw;
-    uint32_t lvl1 = (tpw + 2047) / 2048;  // tree-sum levels over the tpw partials per set
-    CQB_TRY(g_partials.ensure(((size_t)s.nsets * (tpw + lvl1 + 1) + 1) * 128));
+    // tpw threads per set, ch buckets each (both powers of two): about 16k threads in total (one warp per SM sub-partition)
+    uint32_t tpw = 256u;
+    while ((size_t)tpw * 2 * s.nsets <= 16384u) tpw *= 2;
+    tpw = std::min<uint32_t>(tpw, s.nb);
+    uint32_t ch = s.nb / tpw;                            // >= 1; tpw * ch == nb (powers of two)
+    tpw = std::max<uint32_t>(tpw, (uint32_t)RED_CTA);    // pad: threads with t * ch >= nb idle
+    uint32_t cps = (tpw + RED_CTA - 1) / RED_CTA;  // CTA partials per set
+    uint32_t lvl1 = (cps + 2047) / 2048;           // tree-sum levels over them
+    CQB_TRY(g_partials.ensure(((size_t)s.nsets * (cps + lvl1 + 1) + 1) * 128));
     uint4* partials = g_partials.as<uint4>();
-    uint4* sums1 = partials + (size_t)s.nsets * tpw * 8;
+    uint4* sums1 = partials + (size_t)s.nsets * cps * 8;
     uint4* wins = sums1 + (size_t)s.nsets * lvl1 * 8;
-    size_t nred = (size_t)s.nsets * tpw;
     int h = prof_begin(5, st);
-    msm_reduce_kernel<<<(unsigned)((nred + 127) / 128), 128, 0, st>>>(g_buckets.as<uint4>(), s, tpw, ch, nparts, nbuckets * 8, partials);
+    msm_reduce_kernel<<<(unsigned)(s.nsets * cps), RED_CTA, 0, st>>>(g_buckets.as<uint4>(), s, tpw, ch, nparts, nbuckets * 8, partials);
     CQB_LAUNCHED();
     prof_end(h, st);
     h = prof_begin(6, st);
     if (lvl1 > 1) {
-        xyzz_sum_kernel<<<s.nsets * lvl1, 128, 0, st>>>(partials, tpw, lvl1, sums1);
+        xyzz_sum_kernel<<<s.nsets * lvl1, 128, 0, st>>>(partials, cps, lvl1, sums1);
         CQB_LAUNCHED();
         xyzz_sum_kernel<<<s.nsets, 128, 0, st>>>(sums1, lvl1, 1, wins);
         CQB_LAUNCHED();
     } else {
-        xyzz_sum_kernel<<<s.nsets, 128, 0, st>>>(partials, tpw, 1, wins);
+        xyzz_sum_kernel<<<s.nsets, 128, 0, st>>>(partials, cps, 1, wins);
         CQB_LAUNCHED();
     }
     prof_end(h, st);
