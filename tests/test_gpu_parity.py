@@ -116,7 +116,7 @@ def test_best_multiexp_empty_and_mismatch(cq):
         cq.best_multiexp(np.zeros((3, 4), np.uint64), np.zeros((2, 8), np.uint64))  # arithmetic.rs:133
 
 
-@pytest.mark.parametrize("kind", ["all_zero", "all_equal", "small", "witness_like", "cancel"])
+@pytest.mark.parametrize("kind", ["all_zero", "all_equal", "small", "witness_like", "cancel", "negative_small", "few_values", "bits"])
 def test_best_multiexp_structured_scalars(cq, oracle, kind):
     n = 3000
     bases = oracle.synth_bases(4242, n, 4)
@@ -131,6 +131,12 @@ def test_best_multiexp_structured_scalars(cq, oracle, kind):
     elif kind == "witness_like":
         vals = [0 if rng.random() < 0.9 else int(rng.integers(0, 4)) for _ in range(n)]
         sc = P.fr_array_from_ints(vals)
+    elif kind == "negative_small":  # r - x: identical upper digits in every lane, varying low window
+        sc = P.fr_array_from_ints([P.R_MOD - int(v) for v in rng.integers(1, 1 << 10, n)])
+    elif kind == "few_values":      # 5 distinct scalars: warps straddle the hot-key threshold of the count/scatter kernels
+        sc = sc[rng.integers(0, 5, n)]
+    elif kind == "bits":
+        sc = P.fr_array_from_ints([int(v) for v in rng.integers(0, 2, n)])
     elif kind == "cancel":  # sum is the identity: s*P + (r-s)*P
         bases[1::2] = bases[0::2]
         ints = P.fr_array_to_ints(sc[0::2])

@@ -77,6 +77,10 @@ for lg in range(16, max_log + 1, 2):
             "witness_like_90pct_zero_rest_lt_2^16": mont_small(np.where(rng.random(n) < 0.9, 0, rng.integers(0, 1 << 16, n))),
             "bits_0_1": mont_small(rng.integers(0, 2, n)),
             "all_equal": np.repeat(full[:1], n, axis=0),
+            "negative_small_r_minus_lt_2^16": mont_small(np.array([R_MOD - int(v) for v in range(1, 1 << 12)], dtype=object)[rng.integers(0, (1 << 12) - 1, n)]),
+            "two_values": full[rng.integers(0, 2, n)],
+            "32_values": full[rng.integers(0, 32, n)],
+            "small_range_lt_2^8": mont_small(rng.integers(0, 256, n)),
         }
         tmp = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
         for name, arr in dists.items():

@@ -24,6 +24,25 @@ bases = torch.empty(nmax * 64, dtype=torch.uint8, device="cuda")
 scal = torch.empty(nmax * 32, dtype=torch.uint8, device="cuda")
 L.check(lib.cqb_synth_bases_dev(0xC0FFEE, 0, nmax, ctypes.c_void_p(bases.data_ptr())))
 L.check(lib.cqb_synth_scalars_dev(0x5EED0001, 0, nmax, ctypes.c_void_p(scal.data_ptr())))
+dist = os.environ.get("CQB_DIST", "")  # optional skewed scalar distribution (same definitions as tools/sweep_all.py)
+if dist:
+    from oracle import pyref as P
+    rng = np.random.default_rng(7)
+    full = np.zeros((nmax, 4), np.uint64)
+    L.check(lib.cqb_memcpy_d2h(full.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(scal.data_ptr()), nmax * 32))
+    if dist == "negative_small":
+        tab = P.fr_array_from_ints([P.R_MOD - v for v in range(1, 1 << 12)])
+        arr = tab[rng.integers(0, (1 << 12) - 1, nmax)]
+    elif dist == "all_equal":
+        arr = np.repeat(full[:1], nmax, axis=0)
+    elif dist == "two_values":
+        arr = full[rng.integers(0, 2, nmax)]
+    elif dist == "bits":
+        arr = P.fr_array_from_ints([0, 1])[rng.integers(0, 2, nmax)]
+    else:
+        raise SystemExit("unknown CQB_DIST")
+    arr = np.ascontiguousarray(arr)
+    L.check(lib.cqb_memcpy_h2d(ctypes.c_void_p(scal.data_ptr()), arr.ctypes.data_as(ctypes.c_void_p), nmax * 32))
 h = ctypes.c_uint64(0)
 L.check(lib.cqb_bases_register_device(ctypes.c_void_p(bases.data_ptr()), nmax, ctypes.byref(h)))
 out = np.zeros(8, np.uint64)
