@@ -101,9 +101,15 @@ __device__ __forceinline__ Fr load_scalar_canonical(const uint4* scalars, size_t
 // __match_any_sync (MATCH runs on the ADU pipe at a fraction of the ballot rate and was the bound of the count kernel:
 // 91 % ADU utilisation) and lets one leader per distinct bucket add the lanes' total. Uniform digits take the plain path.
 constexpr int DUP_MIN = 4;
-__device__ __forceinline__ bool warp_has_hot_key(uint32_t key, uint32_t nz) {
-    uint32_t first = __shfl_sync(0xffffffffu, key, __ffs(nz) - 1);
-    return __popc(__ballot_sync(0xffffffffu, key == first)) >= DUP_MIN;
+// 0: every lane has a zero digit (nothing to do) | 1: plain per-lane atomics | 2: aggregate with __match_any_sync.
+// Lane 0's digit is the probe (one shuffle + one ballot per window). A zero probe shared by >= DUP_MIN lanes also takes
+// the aggregated path: correct, just not the cheapest — zero digits are either rare (uniform scalars) or warp-wide (small
+// scalars: every upper window is zero in all lanes and is skipped).
+__device__ __forceinline__ int warp_key_mode(uint32_t key) {
+    const uint32_t first = __shfl_sync(0xffffffffu, key, 0);
+    const uint32_t same = __ballot_sync(0xffffffffu, key == first);
+    if (first == 0u && same == 0xffffffffu) return 0;
+    return __popc(same) >= DUP_MIN ? 2 : 1;
 }
 
 // (1) histogram of signed digits. One thread per scalar.
@@ -120,10 +126,10 @@ __global__ void __launch_bounds__(256) msm_count_kernel(const uint4* __restrict_
         carry = 0;
         if (d > s.nb) { d = (1u << s.c) - d; carry = 1; }
         const uint32_t key = active ? d : 0u;
-        const uint32_t nz = __ballot_sync(0xffffffffu, key != 0u);
-        if (nz == 0u) continue;  // zero digits contribute nothing (warp-uniform branch)
+        const int mode = warp_key_mode(key);
+        if (mode == 0) continue;  // zero digits contribute nothing (warp-uniform branch)
         uint32_t* h = hist + (s.single ? (size_t)bset : (size_t)w) * s.stride;
-        if (warp_has_hot_key(key, nz)) {
+        if (mode == 2) {
             uint32_t peers = __match_any_sync(0xffffffffu, key);
             if (key && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(h + key, (uint32_t)__popc(peers));
         } else if (key) {
@@ -344,11 +350,15 @@ __global__ void __launch_bounds__(1024) scan_apply_kernel(uint32_t* __restrict__
 constexpr int SCAT_G = 4;
 __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint4* __restrict__ scalars, const uint32_t* __restrict__ idx,
                                                           size_t n, MsmShape s, uint32_t* __restrict__ cursor,
-                                                          uint32_t* __restrict__ sorted) {
+                                                          uint32_t* __restrict__ sorted, int range_shift) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < n;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t bset = blockIdx.y;
+    // bucket-range passes (gridDim.z of them, executed one after the other: z is the slowest grid dimension): pass z only
+    // places the digits whose bucket id lies in its range, so the number of write streams open at a time — one partially
+    // written 128 B line per bucket — fits the L2 and the lines leave it complete
+    const uint32_t my_range = blockIdx.z;
     Fr k = active ? load_scalar_canonical(scalars + (size_t)bset * n * 2, i) : Fr::zero();
     uint32_t pid = active ? (idx ? __ldg(idx + i) : (uint32_t)i + s.offset) : 0u;
     uint32_t carry = 0;
@@ -362,11 +372,11 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint4* __restric
             uint32_t d = window_bits(k.l, w, s.c) + carry;
             carry = 0;
             if (d > s.nb) { d = (1u << s.c) - d; carry = 1; neg[g] = 1; }
-            key[g] = active ? d : 0u;
-            const uint32_t nz = __ballot_sync(0xffffffffu, key[g] != 0u);
-            if (nz == 0u) continue;
+            key[g] = (active && ((d - 1u) >> range_shift) == my_range) ? d : 0u;  // d == 0 wraps to a range that does not exist
+            const int mode = warp_key_mode(key[g]);
+            if (mode == 0) continue;
             uint32_t* cu = cursor + (s.single ? (size_t)bset : (size_t)w) * s.stride;
-            if (warp_has_hot_key(key[g], nz)) {
+            if (mode == 2) {
                 // one atomic per distinct bucket per warp, lanes take consecutive slots
                 uint32_t peers = __match_any_sync(0xffffffffu, key[g]);
                 leader[g] = (uint32_t)(__ffs(peers) - 1);
@@ -887,7 +897,20 @@ static int msm_sort_phase(const void* d_scalars, const uint32_t* d_idx, size_t n
     }
     prof_end(h, st);
     h = prof_begin(2, st);
-    msm_scatter_kernel<<<gridN, 256, 0, st>>>((const uint4*)d_scalars, d_idx, n, s, b.cursor, b.sorted);
+    // bucket-range passes of the scatter: keep <= 2^17 write streams open at a time
+    int range_shift = 31;
+    unsigned passes = 1;
+    if (s.nb >= (1u << 19) && n >= ((size_t)1 << 23)) passes = 2;  // measured at 2^24 / c = 20: 3.66 ms (1 pass), 3.14 (2), 4.19 (4: each pass re-derives the digits)
+    if (const char* e = getenv("CQB_SCATTER_PASSES")) passes = (unsigned)atoi(e);  // tuning experiments only
+    if (passes > 1) {
+        int lp = 0;
+        while ((1u << lp) < passes) lp++;
+        passes = 1u << lp;
+        range_shift = std::max(0, (s.c - 1) - lp);
+        passes = (s.nb + (1u << range_shift) - 1) >> range_shift;
+    }
+    const dim3 gridS(gN, s.single ? (unsigned)s.nsets : 1u, passes);
+    msm_scatter_kernel<<<gridS, 256, 0, st>>>((const uint4*)d_scalars, d_idx, n, s, b.cursor, b.sorted, range_shift);
     CQB_LAUNCHED();
     prof_end(h, st);
     CQB_CUDA(cudaGetLastError());
