@@ -147,6 +147,19 @@ CQB_API int cqb_eval_polynomial_dev(const void* d_coeffs, size_t n, const uint64
 /* kate_division (arithmetic.rs:351-387): d_q[0..n-1) = (a(X) - a(b)) / (X - b); as used by the multiopen provers
  * (poly/kzg/multiopen/gwc/prover.rs:80-86) and the CQ table preprocessing; d_q must not alias d_a */
 CQB_API int cqb_kate_division_dev(const void* d_a, size_t n, const uint64_t b[4], void* d_q);
+/* Exclusive running product, the serial z-loop of the grand-product arguments (plonk/permutation/prover.rs:157-163):
+ * d_out[0] = init, d_out[i] = init * d_in[0] * ... * d_in[i-1] for i < n. d_out may alias d_in. */
+CQB_API int cqb_fr_prefix_product_dev(const void* d_in, size_t n, const uint64_t init[4], void* d_out);
+/* One column set of permutation::Argument::commit (plonk/permutation/prover.rs:82-166): the grand-product vector z (2^k
+ * Lagrange values) of `ncols` (<= 16 = chunk_len) columns d_columns[j] against their permutation polynomials d_perms[j]
+ * (pkey.permutations, Lagrange values), all 2^k Fr on the device:
+ *   z[0] = last_z, z[i+1] = z[i] * prod_j (col_j[i] + delta^j' omega^i beta + gamma) / (col_j[i] + beta perm_j[i] + gamma).
+ * deltaomega_io: in = DELTA^(index of the set's first column), out = the value for the next set (:144); delta = Fr::DELTA;
+ * omega = the domain generator. The blinding rows z[n - blinding_factors..] are overwritten by the caller from its rng
+ * (:152-155), and last_z of the next set is z[n - (blinding_factors + 1)] (:157). */
+CQB_API int cqb_permutation_product_dev(const void* const* d_columns, const void* const* d_perms, uint32_t ncols, uint32_t k,
+                                        const uint64_t beta[4], const uint64_t gamma[4], const uint64_t omega[4], const uint64_t delta[4],
+                                        uint64_t deltaomega_io[4], const uint64_t last_z[4], void* d_z);
 /* in place a[i] <- a[i] * factor (the parallelize()d scaling loops, e.g. poly/domain.rs:369-373) */
 CQB_API int cqb_fr_scale_dev(void* d_a, size_t n, const uint64_t factor[4]);
 /* in place a[i] <- 1/a[i], zeros stay zero: ff::BatchInvert as used at poly/domain.rs:118-125, static_lookup/prover.rs:261-269 */

@@ -988,3 +988,39 @@ API void oracle_permutation_h(uint64_t* values, size_t size, int32_t rot_scale, 
         beta_term = fr_mul(beta_term, ew);                                                                               /* :450 */
     }
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * permutation::Argument::commit — halo2_proofs/src/plonk/permutation/prover.rs:82-166, ONE column set (one iteration of
+ * the `for (columns, permutations) in self.columns.chunks(chunk_len)...` loop): the grand-product vector z in Lagrange
+ * form BEFORE the blinding rows are overwritten (:152-155 draws them from the rng; the caller owns that).
+ *   modified_values[i]  = prod_j (beta * perm_j[i] + gamma + col_j[i])            (:103-118)
+ *   modified_values    <- 1 / modified_values  (batch_invert == element-wise inverse, exact)   (:121)
+ *   modified_values[i] *= prod_j (deltaomega_j * omega^i * beta + gamma + col_j[i]),  deltaomega_{j+1} = deltaomega_j * DELTA  (:125-144)
+ *   z[0] = last_z ; z[row] = z[row-1] * modified_values[row-1]                     (:157-163)
+ * deltaomega_io: in = DELTA^(index of the set's first column), out = value for the next set (:144).
+ * ------------------------------------------------------------------------------------------------------------------ */
+API void oracle_permutation_product(const uint64_t* const* columns, const uint64_t* const* perms, uint32_t ncols, size_t n,
+                                    const uint64_t* beta_, const uint64_t* gamma_, const uint64_t* omega_, uint64_t* deltaomega_io,
+                                    const uint64_t* last_z_, uint64_t* z_out) {
+    fe beta, gamma, omega, deltaomega, last_z;
+    memcpy(&beta, beta_, 32); memcpy(&gamma, gamma_, 32); memcpy(&omega, omega_, 32); memcpy(&deltaomega, deltaomega_io, 32); memcpy(&last_z, last_z_, 32);
+    fe* mv = (fe*)malloc(sizeof(fe) * n);
+    for (size_t i = 0; i < n; i++) mv[i] = fr_one();
+    for (uint32_t j = 0; j < ncols; j++)
+        for (size_t i = 0; i < n; i++)
+            mv[i] = fr_mul(mv[i], fr_add(fr_add(fr_mul(beta, ((const fe*)perms[j])[i]), gamma), ((const fe*)columns[j])[i]));
+    for (size_t i = 0; i < n; i++) mv[i] = fr_invert(mv[i]);
+    for (uint32_t j = 0; j < ncols; j++) {
+        fe dw = deltaomega; /* start = 0: deltaomega * omega^0 */
+        for (size_t i = 0; i < n; i++) {
+            mv[i] = fr_mul(mv[i], fr_add(fr_add(fr_mul(dw, beta), gamma), ((const fe*)columns[j])[i]));
+            dw = fr_mul(dw, omega);
+        }
+        deltaomega = fr_mul(deltaomega, fr_delta());
+    }
+    fe* z = (fe*)z_out;
+    z[0] = last_z;
+    for (size_t row = 1; row < n; row++) z[row] = fr_mul(z[row - 1], mv[row - 1]);
+    memcpy(deltaomega_io, &deltaomega, 32);
+    free(mv);
+}

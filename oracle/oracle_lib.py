@@ -376,3 +376,18 @@ def permutation_h(values, rot_scale, last_rotation, chunk_len, sets, columns, pe
                                _p(_c(l0, 4)), _p(_c(l_last, 4)), _p(_c(l_active, 4)), _p(_c(beta, 4)), _p(_c(gamma, 4)), _p(_c(y, 4)),
                                _p(_c(extended_omega, 4)))
     return values
+
+
+def permutation_product(columns, perms, beta, gamma, omega, deltaomega, last_z):
+    """one column set of permutation::Argument::commit (permutation/prover.rs:82-166): returns (z, next deltaomega);
+    z is the Lagrange grand-product vector before the blinding rows are overwritten"""
+    cols = [_c(a, 4) for a in columns]
+    prm = [_c(a, 4) for a in perms]
+    n = cols[0].shape[0]
+    z = np.zeros((n, 4), np.uint64)
+    dw = np.array(deltaomega, dtype=np.uint64).copy()
+    pc, _k1 = _ptr_array(cols)
+    pp, _k2 = _ptr_array(prm)
+    lib().oracle_permutation_product(pc, pp, len(cols), ctypes.c_size_t(n), _p(_c(beta, 4)), _p(_c(gamma, 4)), _p(_c(omega, 4)), _p(dw),
+                                     _p(_c(last_z, 4)), _p(z))
+    return z, dw

@@ -62,6 +62,8 @@ SYMBOLS = [
     ("cqb_eval_polynomial_dev", _int, [_vp, _sz, u64p, u64p]),
     ("cqb_kate_division_dev", _int, [_vp, _sz, u64p, _vp]),
     ("cqb_fr_powers_dev", _int, [u64p, _sz, _vp]),
+    ("cqb_fr_prefix_product_dev", _int, [_vp, _sz, u64p, _vp]),
+    ("cqb_permutation_product_dev", _int, [_vp, _vp, _u32, _u32, u64p, u64p, u64p, u64p, u64p, u64p, _vp]),
     ("cqb_dev_alloc", _int, [_sz, ctypes.POINTER(_vp)]),
     ("cqb_dev_free", _int, [_vp]),
     ("cqb_memcpy_h2d", _int, [_vp, _vp, _sz]),

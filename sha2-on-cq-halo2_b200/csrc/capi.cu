@@ -143,6 +143,7 @@ void cqb_shutdown(void) {
     srs_release_all();
     ecntt_release_all();
     poly_release_all();
+    products_release_all();
     evalh_release_all();
     if (g_copy_stream) {
         for (auto& e : g_copy_ev) cudaEventDestroy(e);
@@ -638,6 +639,23 @@ int cqb_kate_division_dev(const void* d_a, size_t n, const uint64_t b[4], void* 
     CQB_TRY(require_init());
     if (!b || ((!d_a || !d_q) && n > 1) || (d_a == d_q && n > 1)) return fail(CQB_E_BAD_ARG, "cqb_kate_division_dev: NULL or aliasing arguments");
     return kate_division_run(d_a, n, b, d_q);
+}
+int cqb_fr_prefix_product_dev(const void* d_in, size_t n, const uint64_t init[4], void* d_out) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!init || ((!d_in || !d_out) && n)) return fail(CQB_E_BAD_ARG, "cqb_fr_prefix_product_dev: NULL argument");
+    return fr_prefix_product_run(d_in, n, init, d_out);
+}
+int cqb_permutation_product_dev(const void* const* d_columns, const void* const* d_perms, uint32_t ncols, uint32_t k, const uint64_t beta[4],
+                                const uint64_t gamma[4], const uint64_t omega[4], const uint64_t delta[4], uint64_t deltaomega_io[4],
+                                const uint64_t last_z[4], void* d_z) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!d_columns || !d_perms || !beta || !gamma || !omega || !delta || !deltaomega_io || !last_z || !d_z)
+        return fail(CQB_E_BAD_ARG, "cqb_permutation_product_dev: NULL argument");
+    for (uint32_t j = 0; j < ncols; j++)
+        if (!d_columns[j] || !d_perms[j]) return fail(CQB_E_BAD_ARG, "cqb_permutation_product_dev: NULL column %u", j);
+    return permutation_product_run(d_columns, d_perms, ncols, k, beta, gamma, omega, delta, deltaomega_io, last_z, d_z);
 }
 static Scratch g_scale_tab;
 int cqb_fr_scale_dev(void* d_a, size_t n, const uint64_t factor[4]) {

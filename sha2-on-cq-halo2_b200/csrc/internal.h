@@ -70,6 +70,13 @@ int eval_polynomial_run(const void* d_coeffs, size_t n, const uint64_t point[4],
 int kate_division_run(const void* d_a, size_t n, const uint64_t b[4], void* d_q);
 void poly_release_all();
 
+// ---- products.cu ----
+int fr_prefix_product_run(const void* d_in, size_t n, const uint64_t init[4], void* d_out);
+int permutation_product_run(const void* const* d_columns, const void* const* d_perms, uint32_t ncols, uint32_t k, const uint64_t beta[4],
+                            const uint64_t gamma[4], const uint64_t omega[4], const uint64_t delta[4], uint64_t deltaomega_io[4],
+                            const uint64_t last_z[4], void* d_z);
+void products_release_all();
+
 // ---- srs.cu ----
 int fr_powers_run(const uint64_t base[4], size_t count, void* d_out);  // defined in ntt.cu
 int fr_batch_invert_run(void* d_a, size_t n);

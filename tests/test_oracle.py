@@ -299,3 +299,38 @@ def test_g_to_lagrange_consistent_with_setup(oracle):
         s = oracle.synth_scalars(0xC0 + k, 1)[0]
         g, gl = oracle.params_setup(k, s)
         assert np.array_equal(oracle.g_to_lagrange(g, k), gl)
+
+
+def test_permutation_product_against_python_bigints():
+    """oracle_permutation_product (permutation/prover.rs:82-166 restated in C) vs the same loop over Python integers"""
+    from oracle import oracle_lib as O
+
+    k, ncols = 4, 3
+    n = 1 << k
+    rng = random.Random(11)
+    omega = P.omega_for(k)
+    delta = 0x09226b6e22c6f0ca64ec26aad4c86e715b5f898e5e963f25870e56bbe533e9a2  # bn256/fr.rs:87-92
+    assert P.fr_array_to_ints(O.fr_const("DELTA")[None, :])[0] == delta
+    cols = [[rng.randrange(P.R_MOD) for _ in range(n)] for _ in range(ncols)]
+    perms = [[rng.randrange(P.R_MOD) for _ in range(n)] for _ in range(ncols)]
+    beta, gamma, last_z, dw0 = (rng.randrange(P.R_MOD) for _ in range(4))
+    mv = [1] * n
+    for j in range(ncols):
+        for i in range(n):
+            mv[i] = mv[i] * (beta * perms[j][i] + gamma + cols[j][i]) % P.R_MOD
+    mv = [pow(v, -1, P.R_MOD) for v in mv]
+    dw = dw0
+    for j in range(ncols):
+        cur = dw
+        for i in range(n):
+            mv[i] = mv[i] * (cur * beta + gamma + cols[j][i]) % P.R_MOD
+            cur = cur * omega % P.R_MOD
+        dw = dw * delta % P.R_MOD
+    z = [last_z]
+    for row in range(1, n):
+        z.append(z[-1] * mv[row - 1] % P.R_MOD)
+    one = lambda x: P.fr_array_from_ints([x])[0]  # noqa: E731
+    got_z, got_dw = O.permutation_product([P.fr_array_from_ints(c) for c in cols], [P.fr_array_from_ints(p) for p in perms], one(beta), one(gamma),
+                                          one(omega), one(dw0), one(last_z))
+    assert P.fr_array_to_ints(got_z) == z
+    assert P.fr_array_to_ints(got_dw[None, :])[0] == dw

@@ -89,6 +89,24 @@ out = np.zeros(4, np.uint64)
 res["eval_polynomial_2^24_ms"] = round(wall(lambda: L.check(lib.cqb_eval_polynomial_dev(d, n, L.p64(x), L.p64(out)))), 3)
 res["kate_division_2^24_ms"] = round(wall(lambda: L.check(lib.cqb_kate_division_dev(d, n, L.p64(x), dq))), 3)
 res["batch_invert_2^24_ms"] = round(wall(lambda: L.check(lib.cqb_fr_batch_invert_dev(d, n))), 3)
+res["prefix_product_2^24_ms"] = round(wall(lambda: L.check(lib.cqb_fr_prefix_product_dev(d, n, L.p64(x), dq))), 3)
+# permutation grand product (permutation/prover.rs:82-166): one set of 4 columns at k = 20 and k = 24
+from sha2_on_cq_halo2_b200.permutation import product_set_dev
+from oracle import pyref as P
+for kk in (20, 24):
+    nn = 1 << kk
+    pcols = [dev(nn * 32) for _ in range(8)]
+    for i, c in enumerate(pcols):
+        L.check(lib.cqb_synth_scalars_dev(700 + i, 0, nn, c))
+    res[f"permutation_product_4cols_k{kk}_ms"] = round(wall(lambda: product_set_dev([c.value for c in pcols[:4]], [c.value for c in pcols[4:]], kk, 5, 7,
+                                                                                P.omega_for(kk), 1, 1, dq.value if kk == 24 else pcols[0].value)), 3)
+    for c in pcols:
+        L.check(lib.cqb_dev_free(c))
+pc = [O.synth_scalars(700 + i, 1 << 16) for i in range(8)]
+one = P.fr_array_from_ints([1])[0]
+t = time.perf_counter()
+O.permutation_product(pc[:4], pc[4:], P.fr_array_from_ints([5])[0], P.fr_array_from_ints([7])[0], P.fr_array_from_ints([P.omega_for(16)])[0], one, one)
+res["cpu_permutation_product_4cols_k16_ms_1thread"] = round((time.perf_counter() - t) * 1e3, 1)
 a20 = O.synth_scalars(13, 1 << 20)
 t = time.perf_counter()
 O.kate_division(a20, x)
