@@ -38,19 +38,23 @@ __device__ __forceinline__ void s_st_fr(uint4* p, const Fr& v) {
 }
 
 // ---- Fr batch inversion in place: a[i] <- a[i]^-1, zeros stay zero (ff::BatchInvert semantics) ------------------------
-constexpr int INV_RUN = 32;
-__global__ void __launch_bounds__(128) fr_batch_invert_kernel(uint4* __restrict__ a, size_t n, uint4* __restrict__ tmp) {
+// One thread inverts a run of `run` consecutive elements with Montgomery's trick: 3 multiplications per element plus one
+// field inversion per run. The run length grows with n (32 ... 256): long runs amortise the inversion, short ones keep
+// enough threads in flight for small vectors. BINARY selects the binary-Euclid inversion (ALU pipe, ~1/4 of the pipe time
+// of the 380-multiplication Fermat ladder, at the price of divergent trip counts inside a warp).
+template <bool BINARY>
+__global__ void __launch_bounds__(128) fr_batch_invert_kernel(uint4* __restrict__ a, size_t n, uint4* __restrict__ tmp, uint32_t run) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t p0 = t * INV_RUN;
+    size_t p0 = t * run;
     if (p0 >= n) return;
-    size_t cnt = (n - p0 < (size_t)INV_RUN) ? (n - p0) : (size_t)INV_RUN;
+    size_t cnt = (n - p0 < (size_t)run) ? (n - p0) : (size_t)run;
     Fr prod = Fr::one();
     for (size_t j = 0; j < cnt; j++) {
         Fr v = s_ld_fr(a + (p0 + j) * 2);
         s_st_fr(tmp + (p0 + j) * 2, prod);
         if (!v.is_zero()) prod = fp_mul<FrP>(prod, v);
     }
-    Fr inv = fp_inv<FrP>(prod);
+    Fr inv = BINARY ? fp_inv_binary<FrP>(prod) : fp_inv<FrP>(prod);
     for (size_t j = cnt; j-- > 0;) {
         Fr v = s_ld_fr(a + (p0 + j) * 2);
         if (v.is_zero()) continue;
@@ -187,8 +191,17 @@ void srs_release_all() {
 int fr_batch_invert_run(void* d_a, size_t n) {
     if (n == 0) return 0;
     CQB_TRY(g_srs_tmp.ensure(n * 32));
-    size_t threads = (n + INV_RUN - 1) / INV_RUN;
-    fr_batch_invert_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx().stream>>>((uint4*)d_a, n, g_srs_tmp.as<uint4>());
+    uint32_t run = 32;
+    while (run < 256 && n / (run * 2) >= 32768) run *= 2;  // keep >= 32k threads in flight, then lengthen the runs
+    // measured (B200, ms at 2^20 / 2^22 / 2^24): run 32: 0.31 / 0.96 / 3.62, 64: 0.30 / 0.73 / 2.27, 128: 0.44 / 0.58 / 1.65,
+    // 256: 0.73 / 0.77 / 1.59; the binary inversion was not faster at any size (divergent trip counts)
+    bool binary = false;
+    if (const char* e = getenv("CQB_INV_RUN")) run = (uint32_t)atoi(e);        // tuning experiments only
+    if (const char* e = getenv("CQB_INV_BINARY")) binary = atoi(e) != 0;      // tuning experiments only
+    size_t threads = (n + run - 1) / run;
+    unsigned grid = (unsigned)((threads + 127) / 128);
+    if (binary) fr_batch_invert_kernel<true><<<grid, 128, 0, ctx().stream>>>((uint4*)d_a, n, g_srs_tmp.as<uint4>(), run);
+    else fr_batch_invert_kernel<false><<<grid, 128, 0, ctx().stream>>>((uint4*)d_a, n, g_srs_tmp.as<uint4>(), run);
     CQB_LAUNCHED();
     CQB_CUDA(cudaGetLastError());
     return 0;
