@@ -325,8 +325,8 @@ def main():
         line["prove_ms_resident"] = [prove_workload.run(cqb200, k, reps=2, resident=True) for k in args.prove_k]
         line["prove_ms_note"] = ("synthetic CQ-prover-shaped op list of SURVEY 8(d): 8 advice columns, one CQ lookup over a 2^16-row table. "
                                  "prove_ms = drop-in host-pointer calls (MSM/NTT only; evaluate_h stays on the CPU and is NOT timed). "
-                                 "prove_ms_resident = polynomials resident in HBM, advice commitments batched, evaluate_h's row program "
-                                 "(12 gate polynomials + permutation + CQ terms) on the device. Witness synthesis and transcript hashing "
+                                 "prove_ms_resident = polynomials resident in HBM, advice commitments batched, the permutation argument's grand products "
+                                 "and z commitments, evaluate_h's row program (12 gate polynomials + permutation + CQ terms) on the device. Witness synthesis and transcript hashing "
                                  "are CPU work outside the path in both.")
 
     # ---- CPU baseline (rank 0, N=1): the oracle's restatement of best_multiexp on a bounded sample -----------------

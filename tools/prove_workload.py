@@ -104,6 +104,18 @@ def run(cq, k, A=8, table_log=16, reps=2, seed=0x70726F76, resident=False):
         outs = np.zeros((A + 1, 8), np.uint64)
         infs = (ctypes.c_int * (A + 1))()
         L.check(lib.cqb_msm_bn254_g1_batch_dev(g_lag, 0, dcols[0], n, A + 1, L.p64(outs), infs))
+        # permutation argument (plonk/permutation/prover.rs:46-200): grand product of every column set on the device, the
+        # z commitments in one batched pass, lagrange_to_coeff; their coset NTTs feed evaluate_h below
+        dw, last_z = 1, 1
+        for st_ in range(nsets):
+            cs_ = [dcols[a].value for a in range(3 * st_, min(3 * st_ + 3, A))]
+            dw = product_set_dev(cs_, [d_perm_lag.value + a * n * 32 for a in range(3 * st_, 3 * st_ + len(cs_))], k, 3, 4, omega_int, dw, last_z,
+                                 d_z.value + st_ * n * 32)
+        zo = np.zeros((nsets, 8), np.uint64)
+        zi = (ctypes.c_int * nsets)()
+        L.check(lib.cqb_msm_bn254_g1_batch_dev(g_lag, 0, d_z, n, nsets, L.p64(zo), zi))
+        for st_ in range(nsets):
+            L.check(lib.cqb_intt_bn254_fr_dev(ctypes.c_void_p(d_z.value + st_ * n * 32), L.p64(dom.omega_inv), L.p64(dom.ifft_divisor), k))
         sparse(t_lag); sparse(t_lag); sparse(t_qs); sparse(t_op0)
         L.check(lib.cqb_intt_bn254_fr_dev(dcols[A + 1], L.p64(dom.omega_inv), L.p64(dom.ifft_divisor), k))
         msm_d(t_g1, dcols[A + 1], n - 1, offset=Nt - (n - 1))
@@ -140,12 +152,22 @@ def run(cq, k, A=8, table_log=16, reps=2, seed=0x70726F76, resident=False):
         chal1 = np.zeros((1, 4), np.uint64)
         bgty = [np.array([3 + i, 0, 0, 0], np.uint64) for i in range(4)]
         nsets = (A + 2) // 3   # chunk_len = cs.degree() - 2 = 3 columns per permutation set
+        from sha2_on_cq_halo2_b200.permutation import product_set_dev
+        from sha2_on_cq_halo2_b200.fields import fr_from_limbs
+        omega_int = fr_from_limbs(dom.omega)
+        d_perm_lag, d_z = ctypes.c_void_p(), ctypes.c_void_p()   # pkey.permutations (Lagrange, key material) and the z vectors
+        L.check(lib.cqb_dev_alloc(A * n * 32, ctypes.byref(d_perm_lag)))
+        L.check(lib.cqb_dev_alloc(nsets * n * 32, ctypes.byref(d_z)))
+        L.check(lib.cqb_synth_scalars_dev(seed + 900, 0, A * n, d_perm_lag))
 
     def evaluate_h_resident():
         """plonk/prover.rs:606-624: coset NTT of every advice / CQ polynomial, then the row program, all in HBM"""
         for a in list(range(A)) + [A, A + 1]:
             L.check(lib.cqb_coset_ntt_bn254_fr_dev(dcols[a], n, ctypes.c_void_p(ext_ptr[a]), L.p64(dom.extended_omega), dom.extended_k,
                                                    L.p64(dom.g_coset), L.p64(dom.g_coset_inv)))
+        for st_ in range(min(nsets, 2)):   # the z polynomials' cosets (evaluation.rs:376-452 reads them)
+            L.check(lib.cqb_coset_ntt_bn254_fr_dev(ctypes.c_void_p(d_z.value + st_ * n * 32), n, ctypes.c_void_p(ext_ptr[2 * A + 8 + st_]),
+                                                   L.p64(dom.extended_omega), dom.extended_k, L.p64(dom.g_coset), L.p64(dom.g_coset_inv)))
         L.check(lib.cqb_memcpy_d2d(d_ext, ctypes.c_void_p(ext_ptr[n_ext_cols - 1]), en * 32))   # values := 0-like start (any vector)
         fixed = ext_ptr[A + 2:A + 4]
         inst = ext_ptr[A + 4:A + 5]
@@ -193,14 +215,14 @@ def run(cq, k, A=8, table_log=16, reps=2, seed=0x70726F76, resident=False):
     for p in cols + [ext, ext_out, sp]:
         L.check(lib.cqb_host_free_pinned(p))
     if resident:
-        for d in [d_block, d_ext, d_ext_out, d_ext_cols]:
+        for d in [d_block, d_ext, d_ext_out, d_ext_cols, d_perm_lag, d_z]:
             L.check(lib.cqb_dev_free(d))
     for d, h in keep + tabs:
         L.check(lib.cqb_bases_free(h))
         L.check(lib.cqb_dev_free(d))
     n_msm = A + 1 + 4 + 2 + 1 + 2 + 1
-    return {"k": k, "mode": "device-resident polynomials, advice commitments batched, evaluate_h row program (12 gate polynomials, "
-                            "permutation + CQ terms) on the device" if resident else "host-pointer calls (drop-in)", "advice_columns": A, "table_rows": N, "ms_per_proof": ms, "gpu_launches_per_proof": int(launches),
+    return {"k": k, "mode": "device-resident polynomials, advice commitments batched, permutation grand products + z commitments, evaluate_h "
+                            "row program (12 gate polynomials, permutation + CQ terms) on the device" if resident else "host-pointer calls (drop-in)", "advice_columns": A, "table_rows": N, "ms_per_proof": ms, "gpu_launches_per_proof": int(launches),
             "ops": {"dense_msm": n_msm - 4, "sparse_msm": 4, "intt_n": A + 2, "coset_ntt_2n": A + 2, "coset_intt_2n": 1}}
 
 
