@@ -147,6 +147,18 @@ CQB_API int cqb_eval_polynomial_dev(const void* d_coeffs, size_t n, const uint64
 /* kate_division (arithmetic.rs:351-387): d_q[0..n-1) = (a(X) - a(b)) / (X - b); as used by the multiopen provers
  * (poly/kzg/multiopen/gwc/prover.rs:80-86) and the CQ table preprocessing; d_q must not alias d_a */
 CQB_API int cqb_kate_division_dev(const void* d_a, size_t n, const uint64_t b[4], void* d_q);
+/* Element-wise pieces of the CQ prover (plonk/static_lookup/prover.rs) on device-resident vectors:
+ *   cqb_fr_compress_dev   : d_out[i] = fold_k (acc * theta + cols[k][row]) from acc = 0, row = d_idx ? d_idx[i] : i — the
+ *                           theta-compression of the lookup's input expressions (:108-117, d_idx NULL) and of the table values
+ *                           over the support of m (:224-229, d_idx = support, device pointer); ncols <= 16.
+ *   cqb_fr_inv_shifted_dev: d_out[i] = (d_in[i] + shift)^-1 for i < usable, shift^-1 above — B's evaluations 1/(f_i + beta)
+ *                           with 1/beta on the blinding rows (:261-269); with usable = n, the 1/(t_i + beta) of A (:243).
+ *   cqb_fr_mul_dev        : element-wise product (a_i = multiplicity_i * 1/(t_i + beta), :243).
+ *   cqb_msm_bn254_g1_sparse_dev: cqb_msm_bn254_g1_sparse with device-resident indices and scalars (indices are not range-checked). */
+CQB_API int cqb_fr_compress_dev(const void* const* d_cols, uint32_t ncols, const uint32_t* d_idx, size_t n, const uint64_t theta[4], void* d_out);
+CQB_API int cqb_fr_inv_shifted_dev(const void* d_in, size_t n, size_t usable, const uint64_t shift[4], void* d_out);
+CQB_API int cqb_fr_mul_dev(const void* d_a, const void* d_b, size_t n, void* d_out);
+CQB_API int cqb_msm_bn254_g1_sparse_dev(cqb_bases_t b, const uint32_t* d_idx, const void* d_scalars, size_t m, uint64_t out_xy[8], int* is_inf);
 /* Exclusive running product, the serial z-loop of the grand-product arguments (plonk/permutation/prover.rs:157-163):
  * d_out[0] = init, d_out[i] = init * d_in[0] * ... * d_in[i-1] for i < n. d_out may alias d_in. */
 CQB_API int cqb_fr_prefix_product_dev(const void* d_in, size_t n, const uint64_t init[4], void* d_out);

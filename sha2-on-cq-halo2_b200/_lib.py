@@ -63,6 +63,10 @@ SYMBOLS = [
     ("cqb_kate_division_dev", _int, [_vp, _sz, u64p, _vp]),
     ("cqb_fr_powers_dev", _int, [u64p, _sz, _vp]),
     ("cqb_fr_prefix_product_dev", _int, [_vp, _sz, u64p, _vp]),
+    ("cqb_fr_compress_dev", _int, [_vp, _u32, _vp, _sz, u64p, _vp]),
+    ("cqb_fr_inv_shifted_dev", _int, [_vp, _sz, _sz, u64p, _vp]),
+    ("cqb_fr_mul_dev", _int, [_vp, _vp, _sz, _vp]),
+    ("cqb_msm_bn254_g1_sparse_dev", _int, [_u64, _vp, _vp, _sz, u64p, _ip]),
     ("cqb_permutation_product_dev", _int, [_vp, _vp, _u32, _u32, u64p, u64p, u64p, u64p, u64p, u64p, _vp]),
     ("cqb_dev_alloc", _int, [_sz, ctypes.POINTER(_vp)]),
     ("cqb_dev_free", _int, [_vp]),

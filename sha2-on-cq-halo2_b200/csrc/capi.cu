@@ -657,6 +657,36 @@ int cqb_permutation_product_dev(const void* const* d_columns, const void* const*
         if (!d_columns[j] || !d_perms[j]) return fail(CQB_E_BAD_ARG, "cqb_permutation_product_dev: NULL column %u", j);
     return permutation_product_run(d_columns, d_perms, ncols, k, beta, gamma, omega, delta, deltaomega_io, last_z, d_z);
 }
+int cqb_fr_compress_dev(const void* const* d_cols, uint32_t ncols, const uint32_t* d_idx, size_t n, const uint64_t theta[4], void* d_out) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!d_cols || !theta || (!d_out && n)) return fail(CQB_E_BAD_ARG, "cqb_fr_compress_dev: NULL argument");
+    for (uint32_t k = 0; k < ncols; k++)
+        if (!d_cols[k] && n) return fail(CQB_E_BAD_ARG, "cqb_fr_compress_dev: NULL column %u", k);
+    return fr_compress_run(d_cols, ncols, d_idx, n, theta, d_out);
+}
+int cqb_fr_inv_shifted_dev(const void* d_in, size_t n, size_t usable, const uint64_t shift[4], void* d_out) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!shift || ((!d_in || !d_out) && n)) return fail(CQB_E_BAD_ARG, "cqb_fr_inv_shifted_dev: NULL argument");
+    if (usable > n) return fail(CQB_E_LEN_MISMATCH, "cqb_fr_inv_shifted_dev: usable rows %zu exceed n = %zu", usable, n);
+    return fr_inv_shifted_run(d_in, n, usable, shift, d_out);
+}
+int cqb_fr_mul_dev(const void* d_a, const void* d_b, size_t n, void* d_out) {
+    LOCK;
+    CQB_TRY(require_init());
+    if ((!d_a || !d_b || !d_out) && n) return fail(CQB_E_BAD_ARG, "cqb_fr_mul_dev: NULL argument");
+    return fr_mul_run(d_a, d_b, n, d_out);
+}
+int cqb_msm_bn254_g1_sparse_dev(cqb_bases_t b, const uint32_t* d_idx, const void* d_scalars, size_t m, uint64_t out_xy[8], int* is_inf) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!out_xy || ((!d_scalars || !d_idx) && m)) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1_sparse_dev: NULL argument");
+    auto it = g_bases.find(b);
+    if (it == g_bases.end()) return fail(CQB_E_BAD_ARG, "unknown bases handle %llu", (unsigned long long)b);
+    CQB_TRY(dispatch_msm(&it->second, 0, d_scalars, d_idx, m));  // indices are the caller's responsibility (device-resident)
+    return fetch_result(out_xy, is_inf);
+}
 static Scratch g_scale_tab;
 int cqb_fr_scale_dev(void* d_a, size_t n, const uint64_t factor[4]) {
     LOCK;

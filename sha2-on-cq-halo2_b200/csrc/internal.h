@@ -75,6 +75,9 @@ int fr_prefix_product_run(const void* d_in, size_t n, const uint64_t init[4], vo
 int permutation_product_run(const void* const* d_columns, const void* const* d_perms, uint32_t ncols, uint32_t k, const uint64_t beta[4],
                             const uint64_t gamma[4], const uint64_t omega[4], const uint64_t delta[4], uint64_t deltaomega_io[4],
                             const uint64_t last_z[4], void* d_z);
+int fr_compress_run(const void* const* d_cols, uint32_t ncols, const uint32_t* d_idx, size_t n, const uint64_t theta[4], void* d_out);
+int fr_inv_shifted_run(const void* d_in, size_t n, size_t usable, const uint64_t shift[4], void* d_out);
+int fr_mul_run(const void* d_a, const void* d_b, size_t n, void* d_out);
 void products_release_all();
 
 // ---- srs.cu ----

@@ -157,4 +157,67 @@ int permutation_product_run(const void* const* d_columns, const void* const* d_p
     return 0;
 }
 
+
+// ---- element-wise pieces of the CQ prover (plonk/static_lookup/prover.rs), device-resident -------------------------------
+constexpr int CQ_MAX_COLS = 16;
+struct CompressArgs {
+    const uint4* col[CQ_MAX_COLS];
+    uint32_t ncols;
+    size_t n;
+    Fr theta;
+    const uint32_t* idx;  // null: row i reads col[k][i]; else col[k][idx[i]]
+};
+// out[i] = fold_k (acc * theta + col_k[row]) starting from 0: compress_expressions (prover.rs:108-117, row = i) and the
+// scalar half of compress_tables (prover.rs:224-229, row = idx[i])
+__global__ void __launch_bounds__(256) fr_compress_kernel(const __grid_constant__ CompressArgs a, uint4* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    size_t row = a.idx ? (size_t)a.idx[i] : i;
+    Fr acc = q_ld(a.col[0], row);  // 0 * theta + col_0
+    for (uint32_t k = 1; k < a.ncols; k++) acc = fp_add<FrP>(fp_mul<FrP>(acc, a.theta), q_ld(a.col[k], row));
+    q_st(out, i, acc);
+}
+// out[i] = in[i] + shift for i < usable, shift for i >= usable (the reference's bs before inversion, prover.rs:261-269)
+__global__ void __launch_bounds__(256) fr_shift_kernel(const uint4* __restrict__ in, size_t n, size_t usable, Fr shift, uint4* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    q_st(out, i, i < usable ? fp_add<FrP>(q_ld(in, i), shift) : shift);
+}
+__global__ void __launch_bounds__(256) fr_mul_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, size_t n, uint4* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    q_st(out, i, fp_mul<FrP>(q_ld(a, i), q_ld(b, i)));
+}
+
+int fr_compress_run(const void* const* d_cols, uint32_t ncols, const uint32_t* d_idx, size_t n, const uint64_t theta[4], void* d_out) {
+    if (ncols == 0 || ncols > CQ_MAX_COLS) return fail(CQB_E_BAD_ARG, "compress: 1..%d columns (got %u)", CQ_MAX_COLS, ncols);
+    if (n == 0) return 0;
+    CompressArgs a;
+    for (uint32_t k = 0; k < ncols; k++) a.col[k] = (const uint4*)d_cols[k];
+    a.ncols = ncols;
+    a.n = n;
+    a.theta = fr_from_u64x4(theta);
+    a.idx = d_idx;
+    fr_compress_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx().stream>>>(a, (uint4*)d_out);
+    CQB_LAUNCHED();
+    CQB_CUDA(cudaGetLastError());
+    return 0;
+}
+// d_out[i] = (d_in[i] + shift)^-1 for i < usable, shift^-1 for usable <= i < n (zero stays zero, ff::BatchInvert)
+int fr_inv_shifted_run(const void* d_in, size_t n, size_t usable, const uint64_t shift[4], void* d_out) {
+    if (n == 0) return 0;
+    fr_shift_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx().stream>>>((const uint4*)d_in, n, usable, fr_from_u64x4(shift), (uint4*)d_out);
+    CQB_LAUNCHED();
+    CQB_TRY(fr_batch_invert_run(d_out, n));
+    CQB_CUDA(cudaGetLastError());
+    return 0;
+}
+int fr_mul_run(const void* d_a, const void* d_b, size_t n, void* d_out) {
+    if (n == 0) return 0;
+    fr_mul_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx().stream>>>((const uint4*)d_a, (const uint4*)d_b, n, (uint4*)d_out);
+    CQB_LAUNCHED();
+    CQB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace cqb
