@@ -264,6 +264,10 @@ def main():
         "roofline": {"bound": "int", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": INT_PEAK_TMAD32,
                      "unit": "TMAD32/s", "frac": achieved / INT_PEAK_TMAD32, "traffic": 29.6e9 if (world == 1 and args.log_n == 24 and not args.no_precompute) else None,
                      "kernel_ms": t_acc, "algorithmic_mad32_per_point": MAD32_PER_POINT,
+                     # what the kernel really executes: windows_per_point bucket additions x (6 mul x 136 + 2 sqr x 108 + one
+                     # fused a*b-c*d x 200) MAD32 — the fraction of the multiplier peak actually in use (< 1 by construction)
+                     "executed_mad32_per_point": nwin_eff * 1232,
+                     "executed_frac": per * nwin_eff * 1232 / (t_acc * 1e-3) / 1e12 / INT_PEAK_TMAD32,
                      "peak_source": "measured on this pool's B200: profiles/r01_int_pipe_calibration.md (MEASURED_PEAKS.json has no integer figure)",
                      "whole_msm_frac": n_total / world * MAD32_PER_POINT / (ms_dev * 1e-3) / 1e12 / INT_PEAK_TMAD32},
         # the same kernel against the HBM roofline, in the canonical schema: it is NOT bandwidth-bound (frac << 1 by design)
