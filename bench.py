@@ -29,6 +29,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's own banner (NCCL_DEBUG=VERSION/INFO on some boxes) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "SHA2-CQ prove ms; BN254 MSM Mpts/s @2^24; Fr NTT Gelem/s @2^24; 1/2/4/8 GPU"
 UNIT = "Mpts/s (BN254 G1 MSM @2^24)"
