@@ -901,7 +901,6 @@ static int msm_sort_phase(const void* d_scalars, const uint32_t* d_idx, size_t n
     int range_shift = 31;
     unsigned passes = 1;
     if (s.nb >= (1u << 19) && n >= ((size_t)1 << 23)) passes = 2;  // measured at 2^24 / c = 20: 3.66 ms (1 pass), 3.14 (2), 4.19 (4: each pass re-derives the digits)
-    if (const char* e = getenv("CQB_SCATTER_PASSES")) passes = (unsigned)atoi(e);  // tuning experiments only
     if (passes > 1) {
         int lp = 0;
         while ((1u << lp) < passes) lp++;

@@ -40,9 +40,8 @@ __device__ __forceinline__ void s_st_fr(uint4* p, const Fr& v) {
 // ---- Fr batch inversion in place: a[i] <- a[i]^-1, zeros stay zero (ff::BatchInvert semantics) ------------------------
 // One thread inverts a run of `run` consecutive elements with Montgomery's trick: 3 multiplications per element plus one
 // field inversion per run. The run length grows with n (32 ... 256): long runs amortise the inversion, short ones keep
-// enough threads in flight for small vectors. BINARY selects the binary-Euclid inversion (ALU pipe, ~1/4 of the pipe time
-// of the 380-multiplication Fermat ladder, at the price of divergent trip counts inside a warp).
-template <bool BINARY>
+// enough threads in flight for small vectors. (The binary-Euclid inversion was tried here too: never faster — the lanes of
+// a warp run different trip counts.)
 __global__ void __launch_bounds__(128) fr_batch_invert_kernel(uint4* __restrict__ a, size_t n, uint4* __restrict__ tmp, uint32_t run) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t p0 = t * run;
@@ -54,7 +53,7 @@ __global__ void __launch_bounds__(128) fr_batch_invert_kernel(uint4* __restrict_
         s_st_fr(tmp + (p0 + j) * 2, prod);
         if (!v.is_zero()) prod = fp_mul<FrP>(prod, v);
     }
-    Fr inv = BINARY ? fp_inv_binary<FrP>(prod) : fp_inv<FrP>(prod);
+    Fr inv = fp_inv<FrP>(prod);
     for (size_t j = cnt; j-- > 0;) {
         Fr v = s_ld_fr(a + (p0 + j) * 2);
         if (v.is_zero()) continue;
@@ -195,13 +194,8 @@ int fr_batch_invert_run(void* d_a, size_t n) {
     while (run < 256 && n / (run * 2) >= 32768) run *= 2;  // keep >= 32k threads in flight, then lengthen the runs
     // measured (B200, ms at 2^20 / 2^22 / 2^24): run 32: 0.31 / 0.96 / 3.62, 64: 0.30 / 0.73 / 2.27, 128: 0.44 / 0.58 / 1.65,
     // 256: 0.73 / 0.77 / 1.59; the binary inversion was not faster at any size (divergent trip counts)
-    bool binary = false;
-    if (const char* e = getenv("CQB_INV_RUN")) run = (uint32_t)atoi(e);        // tuning experiments only
-    if (const char* e = getenv("CQB_INV_BINARY")) binary = atoi(e) != 0;      // tuning experiments only
     size_t threads = (n + run - 1) / run;
-    unsigned grid = (unsigned)((threads + 127) / 128);
-    if (binary) fr_batch_invert_kernel<true><<<grid, 128, 0, ctx().stream>>>((uint4*)d_a, n, g_srs_tmp.as<uint4>(), run);
-    else fr_batch_invert_kernel<false><<<grid, 128, 0, ctx().stream>>>((uint4*)d_a, n, g_srs_tmp.as<uint4>(), run);
+    fr_batch_invert_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx().stream>>>((uint4*)d_a, n, g_srs_tmp.as<uint4>(), run);
     CQB_LAUNCHED();
     CQB_CUDA(cudaGetLastError());
     return 0;
