@@ -311,10 +311,11 @@ int cqb_msm_bn254_g1(cqb_bases_t b, size_t offset, const uint64_t* scalars, size
             CQB_CUDA(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
             for (auto& e : g_copy_ev) CQB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
-        size_t per = (n + PARTS - 1) / PARTS;  // the same split msm_run* makes for PARTS parts
+        size_t bounds[PARTS + 1];
+        msm_part_bounds(n, PARTS, true, bounds);  // the same split msm_run* makes (small first part: its copy is the exposed one)
         bool use_table = bs->table && n * 8 >= bs->n;
         for (int p = 0; p < PARTS; p++) {
-            size_t lo = (size_t)p * per, cnt = lo < n ? std::min(per, n - lo) : 0;
+            size_t lo = bounds[p], cnt = bounds[p + 1] - lo;
             if (cnt) CQB_CUDA(cudaMemcpyAsync((char*)g_scalars.p + lo * 32, scalars + lo * 4, cnt * 32, cudaMemcpyHostToDevice, g_copy_stream));
             CQB_CUDA(cudaEventRecord(g_copy_ev[p], g_copy_stream));
         }

@@ -38,6 +38,8 @@ int msm_run(const void* d_bases, size_t offset, const void* d_scalars, const uin
 int msm_run_precomputed(const void* d_table, size_t table_n, int c, size_t offset, const void* d_scalars, const uint32_t* d_idx,
                         size_t n, void* d_out_xy_flag, int batch = 1, int nparts = 0, const cudaEvent_t* ready = nullptr);
 void msm_set_parts(int p);
+// bounds[0..nparts]: the point ranges the parts of an MSM cover (small_first: host-pointer MSMs, see msm.cu)
+void msm_part_bounds(size_t n, int nparts, bool small_first, size_t* bounds);
 int msm_precompute_window_bits(size_t n);
 int msm_windows_for(int c);
 int msm_precompute_table(const void* d_bases, size_t n, int c, void* d_table);

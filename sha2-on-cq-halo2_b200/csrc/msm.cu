@@ -1007,14 +1007,30 @@ static int auto_parts(size_t n, const MsmShape& s, const uint32_t* d_idx) {
     return 1;
 }
 
+// Part boundaries. Device-resident scalars: equal parts. Host-pointer MSM (ready != null): the H2D copy runs ~4x faster
+// than the MSM consumes points, so only the FIRST part's copy is exposed — it is made small (1/16 of the points) and the
+// rest is split evenly; capi.cu issues its copies with the same function.
+void msm_part_bounds(size_t n, int nparts, bool small_first, size_t* bounds) {
+    if (nparts < 1) nparts = 1;
+    if (nparts > MSM_MAX_PARTS) nparts = MSM_MAX_PARTS;
+    bounds[0] = 0;
+    if (small_first && nparts >= 2 && n >= ((size_t)1 << 20)) {
+        size_t first = n / 16, rest = n - first, per = (rest + (nparts - 1) - 1) / (nparts - 1);
+        bounds[1] = first;
+        for (int p = 2; p <= nparts; p++) bounds[p] = std::min(n, first + (size_t)(p - 1) * per);
+    } else {
+        size_t per = (n + nparts - 1) / nparts;
+        for (int p = 1; p <= nparts; p++) bounds[p] = std::min(n, (size_t)p * per);
+    }
+    bounds[nparts] = n;
+}
+
 // `ready[p]` (optional): event the sort of part p must wait for (the H2D copy of its scalars)
 static int msm_run_shape(const void* d_bases, const void* d_scalars, const uint32_t* d_idx, size_t n, MsmShape s, int nparts,
                          const cudaEvent_t* ready, void* d_out) {
     cudaStream_t st = ctx().stream;
     g_spans_used = 0;
     if (nparts > MSM_MAX_PARTS) nparts = MSM_MAX_PARTS;
-    size_t per = (n + nparts - 1) / nparts;
-    nparts = (int)((n + per - 1) / per);
     if (nparts <= 1 && !ready) {
         PartPlan pl;
         CQB_TRY(plan_parts(s, 1, &pl));
@@ -1023,6 +1039,10 @@ static int msm_run_shape(const void* d_bases, const void* d_scalars, const uint3
         CQB_TRY(msm_acc_phase(d_bases, n, s, pl, b, st));
         return msm_finish(s, 1, d_out);
     }
+    size_t bounds[MSM_MAX_PARTS + 1];
+    msm_part_bounds(n, nparts, ready != nullptr, bounds);
+    size_t per = 0;
+    for (int p = 0; p < nparts; p++) per = std::max(per, bounds[p + 1] - bounds[p]);
     // per-part list capacity
     s.list_cap = s.single ? per * (size_t)s.nwin : per;
     PartPlan pl;
@@ -1031,24 +1051,30 @@ static int msm_run_shape(const void* d_bases, const void* d_scalars, const uint3
     const uint32_t offset0 = s.offset;
     CQB_CUDA(cudaEventRecord(g_ev_start, st));  // the sort stream starts after everything already queued on the main stream
     CQB_CUDA(cudaStreamWaitEvent(g_sort_stream, g_ev_start, 0));
+    int used = 0;  // parts that hold points (bucket arrays of the others are never touched and must not be summed)
     for (int p = 0; p < nparts; p++) {
-        size_t lo = (size_t)p * per, cnt = std::min(per, n - lo);
-        MsmShape sp = s;
-        sp.offset = offset0 + (uint32_t)lo;
-        PartBuf b = part_buf(s, pl, p);
+        size_t lo = bounds[p], cnt = bounds[p + 1] - lo;
         if (ready) CQB_CUDA(cudaStreamWaitEvent(g_sort_stream, ready[p], 0));
-        CQB_TRY(msm_sort_phase((const char*)d_scalars + lo * 32, d_idx ? d_idx + lo : nullptr, cnt, sp, pl, b, g_sort_stream));
-        CQB_CUDA(cudaEventRecord(g_ev_sorted[p], g_sort_stream));
-    }
-    for (int p = 0; p < nparts; p++) {
-        size_t lo = (size_t)p * per, cnt = std::min(per, n - lo);
+        if (cnt == 0) continue;
         MsmShape sp = s;
         sp.offset = offset0 + (uint32_t)lo;
-        PartBuf b = part_buf(s, pl, p);
-        CQB_CUDA(cudaStreamWaitEvent(st, g_ev_sorted[p], 0));
-        CQB_TRY(msm_acc_phase(d_bases, cnt, sp, pl, b, st));
+        PartBuf b = part_buf(s, pl, used);
+        CQB_TRY(msm_sort_phase((const char*)d_scalars + lo * 32, d_idx ? d_idx + lo : nullptr, cnt, sp, pl, b, g_sort_stream));
+        CQB_CUDA(cudaEventRecord(g_ev_sorted[used], g_sort_stream));
+        used++;
     }
-    return msm_finish(s, nparts, d_out);
+    used = 0;
+    for (int p = 0; p < nparts; p++) {
+        size_t lo = bounds[p], cnt = bounds[p + 1] - lo;
+        if (cnt == 0) continue;
+        MsmShape sp = s;
+        sp.offset = offset0 + (uint32_t)lo;
+        PartBuf b = part_buf(s, pl, used);
+        CQB_CUDA(cudaStreamWaitEvent(st, g_ev_sorted[used], 0));
+        CQB_TRY(msm_acc_phase(d_bases, cnt, sp, pl, b, st));
+        used++;
+    }
+    return msm_finish(s, used, d_out);
 }
 
 static int msm_empty(void* d_out) {

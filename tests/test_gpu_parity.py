@@ -419,3 +419,24 @@ def test_batched_msm_matches_individual(cq, oracle, n, B, c, pre):
         _, exp = oracle.best_multiexp(np.ascontiguousarray(polys[b, :m]), bases[5:], 8)
         assert np.array_equal(got[b].to_affine(), exp), b
     dev.free()
+
+
+@pytest.mark.parametrize("parts", [2, 3, 8])
+def test_msm_parts_do_not_change_result(cq, oracle, parts):
+    """cqb_msm_set_parts: the point-range parts of a pipelined MSM (own histogram / sorted list / bucket array each, sort on a
+    second stream) give the single-shot result, on both layouts and with an offset"""
+    lib = cq._lib.lib()
+    n = 50021
+    sc, bases = _edge_inputs(oracle, n, 4711)
+    _, exp = oracle.best_multiexp(sc, bases, 8)
+    off = 1234
+    _, exp_o = oracle.best_multiexp(sc[: n - off], bases[off:], 8)
+    for pre in (False, True):
+        dev = cq.DeviceBases(bases, precompute=pre, window_bits=13 if pre else 0)
+        cq._lib.check(lib.cqb_msm_set_parts(parts))
+        try:
+            assert np.array_equal(dev.msm(sc).to_affine(), exp)
+            assert np.array_equal(dev.msm(sc[: n - off], offset=off).to_affine(), exp_o)
+        finally:
+            cq._lib.check(lib.cqb_msm_set_parts(0))
+        dev.free()
