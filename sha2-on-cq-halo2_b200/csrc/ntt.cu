@@ -70,9 +70,15 @@ __device__ __forceinline__ void sm_st(uint4* slo, uint4* shi, uint32_t e, const 
     slo[e] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
     shi[e] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
-// (x, y) <- (x + w y, x - w y); w = W[twi], twi == 0 means w = 1 (the reference skips that multiply too, :213-219)
-__device__ __forceinline__ void butterfly(Fr& x, Fr& y, const uint4* tw, uint32_t twi) {
-    if (twi != 0) y = fp_mul<FrP>(y, ldg_fr(tw, twi));
+// (x, y) <- (x + w y, x - w y)
+__device__ __forceinline__ void butterfly_w(Fr& x, Fr& y, const Fr& w) {
+    y = fp_mul<FrP>(y, w);
+    Fr u = fp_add<FrP>(x, y);
+    y = fp_sub<FrP>(x, y);
+    x = u;
+}
+// w = 1 (the reference skips that multiply too, arithmetic.rs:213-219)
+__device__ __forceinline__ void butterfly_1(Fr& x, Fr& y) {
     Fr u = fp_add<FrP>(x, y);
     y = fp_sub<FrP>(x, y);
     x = u;
@@ -124,38 +130,58 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const __grid_constant_
     // ---- butterflies: stage s = s0 + t pairs rows that differ in bit t ----------------------------------------------
     // twiddle index of a butterfly whose upper row is `row` at stage t: (i mod 2^s) << (L-1-s), s = s0 + t
     //   (reference arithmetic.rs:263-272: twiddles[(i + 1) * twiddle_chunk] over the chunk-local index)
+    // The twiddles of a radix-4 step are fetched (L2, ~700 cycles) BEFORE the shared-memory loads and the first multiply, all
+    // three at once: behind a per-butterfly `if (twi != 0)` the loads stayed where they were and every butterfly pair waited
+    // for its own round trip. W[0] = 1 in Montgomery form, so an index of 0 needs no special case (same limbs); only the one
+    // step whose twiddles are 1 for EVERY lane — stages 1-2 of the first pass: one multiplication instead of four — is
+    // specialised, on a warp-uniform condition.
     int t = 0;
     for (; t + 1 < a.r; t += 2) {
+        const bool first_step = a.first && t == 0;
         for (uint32_t qd = tid; qd < (T >> 2); qd += nthr) {
             const uint32_t c = qd & qmask, rq = qd >> a.q;
             const uint32_t jlow = a.first ? 0u : (c | (lo << a.q));
             const uint32_t r00 = ((rq >> t) << (t + 2)) | (rq & ((1u << t) - 1u));
             const uint32_t r01 = r00 | (1u << t), r10 = r00 | (2u << t), r11 = r00 | (3u << t);
             const uint32_t e00 = (r00 << a.q) | c, e01 = (r01 << a.q) | c, e10 = (r10 << a.q) | c, e11 = (r11 << a.q) | c;
-            Fr x00 = sm_ld(slo, shi, e00), x01 = sm_ld(slo, shi, e01), x10 = sm_ld(slo, shi, e10), x11 = sm_ld(slo, shi, e11);
             const uint32_t low_t = r00 & ((1u << t) - 1u);
             const int s = a.s0 + t;
             const uint32_t tw0 = (jlow | (low_t << a.s0)) << (a.L - 1 - s);              // stage t (same for both pairs)
-            butterfly(x00, x01, a.tw, tw0);
-            butterfly(x10, x11, a.tw, tw0);
             const uint32_t tw1a = (jlow | (low_t << a.s0)) << (a.L - 2 - s);              // stage t+1, rows r00 / r10
             const uint32_t tw1b = (jlow | ((low_t | (1u << t)) << a.s0)) << (a.L - 2 - s);  // stage t+1, rows r01 / r11
-            butterfly(x00, x10, a.tw, tw1a);
-            butterfly(x01, x11, a.tw, tw1b);
-            sm_st(slo, shi, e00, x00); sm_st(slo, shi, e01, x01); sm_st(slo, shi, e10, x10); sm_st(slo, shi, e11, x11);
+            const Fr w1b = ldg_fr(a.tw, tw1b);
+            if (first_step) {  // tw0 == tw1a == 0 on every lane
+                Fr x00 = sm_ld(slo, shi, e00), x01 = sm_ld(slo, shi, e01), x10 = sm_ld(slo, shi, e10), x11 = sm_ld(slo, shi, e11);
+                butterfly_1(x00, x01);
+                butterfly_1(x10, x11);
+                butterfly_1(x00, x10);
+                butterfly_w(x01, x11, w1b);
+                sm_st(slo, shi, e00, x00); sm_st(slo, shi, e01, x01); sm_st(slo, shi, e10, x10); sm_st(slo, shi, e11, x11);
+            } else {
+                const Fr w0 = ldg_fr(a.tw, tw0), w1a = ldg_fr(a.tw, tw1a);
+                Fr x00 = sm_ld(slo, shi, e00), x01 = sm_ld(slo, shi, e01), x10 = sm_ld(slo, shi, e10), x11 = sm_ld(slo, shi, e11);
+                butterfly_w(x00, x01, w0);
+                butterfly_w(x10, x11, w0);
+                butterfly_w(x00, x10, w1a);
+                butterfly_w(x01, x11, w1b);
+                sm_st(slo, shi, e00, x00); sm_st(slo, shi, e01, x01); sm_st(slo, shi, e10, x10); sm_st(slo, shi, e11, x11);
+            }
         }
         __syncthreads();
     }
     if (t < a.r) {  // odd number of stages: one plain radix-2 stage
+        const bool first_stage = a.first && t == 0;  // a one-stage first pass (tiny transforms): every twiddle is 1
         for (uint32_t b = tid; b < (T >> 1); b += nthr) {
             const uint32_t c = b & qmask, rb = b >> a.q;
             const uint32_t jlow = a.first ? 0u : (c | (lo << a.q));
             const uint32_t r0 = ((rb >> t) << (t + 1)) | (rb & ((1u << t) - 1u));
             const uint32_t r1 = r0 | (1u << t);
             const uint32_t e0 = (r0 << a.q) | c, e1 = (r1 << a.q) | c;
-            Fr x = sm_ld(slo, shi, e0), y = sm_ld(slo, shi, e1);
             const int s = a.s0 + t;
-            butterfly(x, y, a.tw, (jlow | ((r0 & ((1u << t) - 1u)) << a.s0)) << (a.L - 1 - s));
+            const uint32_t twi = (jlow | ((r0 & ((1u << t) - 1u)) << a.s0)) << (a.L - 1 - s);
+            Fr x = sm_ld(slo, shi, e0), y = sm_ld(slo, shi, e1);
+            if (first_stage) butterfly_1(x, y);
+            else butterfly_w(x, y, ldg_fr(a.tw, twi));
             sm_st(slo, shi, e0, x); sm_st(slo, shi, e1, y);
         }
         __syncthreads();
