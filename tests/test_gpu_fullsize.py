@@ -121,3 +121,56 @@ def test_ntt_2p24_properties(env, oracle):
     tail = np.ones((4, 4), np.uint64)
     L.check(lib.cqb_memcpy_d2h(tail.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(d_s2.value + (n - 4) * 32), 128))
     assert not tail.any()
+
+
+def test_msm_and_ntt_2p26_properties(oracle):
+    """the top of BASELINE.json's sweeps (2^26): table-layout MSM == fold of four range parts, linearity; NTT round trip"""
+    import cqb200
+
+    cqb200._lib.init(0)
+    L, lib = cqb200._lib, cqb200._lib.lib()
+    k = 26
+    n = 1 << k
+
+    def dalloc(nbytes):
+        d = ctypes.c_void_p()
+        L.check(lib.cqb_dev_alloc(nbytes, ctypes.byref(d)))
+        return d
+
+    d_b, d_s, d_s2 = dalloc(n * 64), dalloc(n * 32), dalloc(n * 32)
+    try:
+        L.check(lib.cqb_synth_bases_dev(0xC0FFEE, 0, n, d_b))
+        L.check(lib.cqb_synth_scalars_dev(0x5EED0001, 0, n, d_s))
+        h = ctypes.c_uint64(0)
+        L.check(lib.cqb_bases_register_device(d_b, n, ctypes.byref(h)))
+        L.check(lib.cqb_bases_precompute(h.value, 0))
+        whole = _msm(L, lib, h.value, d_s, n)
+        parts = np.stack([_msm(L, lib, h.value, ctypes.c_void_p(d_s.value + i * (n // 4) * 32), n // 4, offset=i * (n // 4)) for i in range(4)])
+        fold = np.zeros(8, np.uint64)
+        inf = ctypes.c_int(0)
+        L.check(lib.cqb_g1_sum_affine(L.p64(parts), 4, L.p64(fold), ctypes.byref(inf)))
+        assert whole.any() and np.array_equal(fold, whole)
+        three = P.int_to_limbs(P.to_mont(3, P.R_MOD))
+        L.check(lib.cqb_memcpy_d2d(d_s2, d_s, n * 32))
+        L.check(lib.cqb_fr_scale_dev(d_s2, n, L.p64(three)))
+        exp = np.zeros(8, np.uint64)
+        L.check(lib.cqb_g1_sum_affine(L.p64(np.stack([whole, whole, whole])), 3, L.p64(exp), ctypes.byref(inf)))
+        assert np.array_equal(_msm(L, lib, h.value, d_s2, n), exp)
+        L.check(lib.cqb_bases_free(h.value))
+        # NTT 2^26: inverse(forward(a)) == a through a random evaluation point, and A[0] = sum a
+        dom = cqb200.EvaluationDomain(1, k)
+        x = oracle.synth_scalars(0x78, 1)[0]
+        one = P.int_to_limbs(P.MONT % P.R_MOD)
+        e1, e2, asum, first = (np.zeros(4, np.uint64) for _ in range(4))
+        L.check(lib.cqb_memcpy_d2d(d_s2, d_s, n * 32))
+        L.check(lib.cqb_ntt_bn254_fr_dev(d_s2, L.p64(dom.omega), k))
+        L.check(lib.cqb_eval_polynomial_dev(d_s, n, L.p64(one), L.p64(asum)))
+        L.check(lib.cqb_memcpy_d2h(first.ctypes.data_as(ctypes.c_void_p), d_s2, 32))
+        assert np.array_equal(first, asum)
+        L.check(lib.cqb_intt_bn254_fr_dev(d_s2, L.p64(dom.omega_inv), L.p64(dom.ifft_divisor), k))
+        L.check(lib.cqb_eval_polynomial_dev(d_s, n, L.p64(x), L.p64(e1)))
+        L.check(lib.cqb_eval_polynomial_dev(d_s2, n, L.p64(x), L.p64(e2)))
+        assert np.array_equal(e1, e2)
+    finally:
+        for d in (d_b, d_s, d_s2):
+            L.check(lib.cqb_dev_free(d))
