@@ -147,6 +147,20 @@ CQB_API int cqb_eval_polynomial_dev(const void* d_coeffs, size_t n, const uint64
 /* kate_division (arithmetic.rs:351-387): d_q[0..n-1) = (a(X) - a(b)) / (X - b); as used by the multiopen provers
  * (poly/kzg/multiopen/gwc/prover.rs:80-86) and the CQ table preprocessing; d_q must not alias d_a */
 CQB_API int cqb_kate_division_dev(const void* d_a, size_t n, const uint64_t b[4], void* d_q);
+/* plookup (the original halo2 lookup argument; the CQ circuits of this repository use static lookups instead, but
+ * create_proof runs both):
+ *   cqb_lookup_product_dev: lookup::prover::Permuted::commit_product (plonk/lookup/prover.rs:173-262) — the grand product z of
+ *     (a_i + beta)(s_i + gamma) / ((a'_i + beta)(s'_i + gamma)) over the theta-compressed input / table expressions and their
+ *     permuted versions (2^k Lagrange values each, device-resident): d_z[0] = 1, d_z[i] = product of the first i fractions.
+ *     The caller overwrites d_z[n - blinding_factors..] with its random blinding rows (:259).
+ *   cqb_lookup_h_dev: the five plookup constraints of evaluate_h (plonk/evaluation.rs:458-531) folded into d_values with y;
+ *     d_table_value = the lookup's GraphEvaluator output (compressed input + beta)(compressed table + gamma) per extended row,
+ *     e.g. from cqb_graph_evaluate_dev on a zeroed vector. */
+CQB_API int cqb_lookup_product_dev(const void* d_compressed_input, const void* d_compressed_table, const void* d_permuted_input,
+                                   const void* d_permuted_table, uint32_t k, const uint64_t beta[4], const uint64_t gamma[4], void* d_z);
+CQB_API int cqb_lookup_h_dev(void* d_values, const void* d_table_value, const void* d_product_coset, const void* d_permuted_input_coset,
+                             const void* d_permuted_table_coset, const void* d_l0, const void* d_l_last, const void* d_l_active_row,
+                             const uint64_t beta[4], const uint64_t gamma[4], const uint64_t y[4], uint64_t size, int32_t rot_scale);
 /* Element-wise pieces of the CQ prover (plonk/static_lookup/prover.rs) on device-resident vectors:
  *   cqb_fr_compress_dev   : d_out[i] = fold_k (acc * theta + cols[k][row]) from acc = 0, row = d_idx ? d_idx[i] : i — the
  *                           theta-compression of the lookup's input expressions (:108-117, d_idx NULL) and of the table values

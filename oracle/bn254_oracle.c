@@ -1024,3 +1024,48 @@ API void oracle_permutation_product(const uint64_t* const* columns, const uint64
     memcpy(deltaomega_io, &deltaomega, 32);
     free(mv);
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * lookup::prover::Permuted::commit_product — halo2_proofs/src/plonk/lookup/prover.rs:173-262: the plookup grand product in
+ * Lagrange form BEFORE the blinding rows are appended (:259 draws them from the rng; the caller owns that): z has n entries,
+ * z[0] = 1, z[i] = prod_{r<i} (a_r + beta)(s_r + gamma) / ((a'_r + beta)(s'_r + gamma)).
+ * ------------------------------------------------------------------------------------------------------------------ */
+API void oracle_lookup_product(const uint64_t* cin, const uint64_t* ctab, const uint64_t* pin, const uint64_t* ptab, size_t n,
+                               const uint64_t* beta_, const uint64_t* gamma_, uint64_t* z_out) {
+    fe beta, gamma; memcpy(&beta, beta_, 32); memcpy(&gamma, gamma_, 32);
+    const fe *a = (const fe*)cin, *s = (const fe*)ctab, *ap = (const fe*)pin, *sp = (const fe*)ptab;
+    fe* z = (fe*)z_out;
+    fe state = fr_one();
+    z[0] = state; /* iter::once(one) scanned from state = one (:249-254) */
+    for (size_t i = 0; i + 1 < n; i++) {
+        fe lp = fr_mul(fr_add(beta, ap[i]), fr_add(gamma, sp[i]));   /* :214 */
+        lp = fr_invert(lp);                                           /* :220 */
+        lp = fr_mul(lp, fr_add(a[i], beta));                          /* :229 */
+        lp = fr_mul(lp, fr_add(s[i], gamma));                         /* :230 */
+        state = fr_mul(state, lp);
+        z[i + 1] = state;
+    }
+}
+
+/* evaluation.rs:458-531: the plookup constraints of ONE lookup folded into values with y. table_value: the lookup
+ * GraphEvaluator's output per row (evaluated by the caller with oracle_graph_evaluate). */
+API void oracle_lookup_h(uint64_t* values, size_t size, int32_t rot_scale, const uint64_t* table_value_, const uint64_t* product_,
+                         const uint64_t* pin_, const uint64_t* ptab_, const uint64_t* l0_, const uint64_t* l_last_, const uint64_t* l_active_,
+                         const uint64_t* beta_, const uint64_t* gamma_, const uint64_t* y_) {
+    fe beta, gamma, y; memcpy(&beta, beta_, 32); memcpy(&gamma, gamma_, 32); memcpy(&y, y_, 32);
+    fe* v = (fe*)values;
+    const fe *tv = (const fe*)table_value_, *z = (const fe*)product_, *a = (const fe*)pin_, *s = (const fe*)ptab_;
+    const fe *l0 = (const fe*)l0_, *l_last = (const fe*)l_last_, *l_active = (const fe*)l_active_;
+    fe one = fr_one();
+    for (size_t idx = 0; idx < size; idx++) {
+        size_t r_next = get_rotation_idx(idx, 1, rot_scale, (int64_t)size);
+        size_t r_prev = get_rotation_idx(idx, -1, rot_scale, (int64_t)size);
+        fe a_minus_s = fr_sub(a[idx], s[idx]);
+        v[idx] = fr_add(fr_mul(v[idx], y), fr_mul(fr_sub(one, z[idx]), l0[idx]));                                   /* :494-495 */
+        v[idx] = fr_add(fr_mul(v[idx], y), fr_mul(fr_sub(fr_mul(z[idx], z[idx]), z[idx]), l_last[idx]));             /* :497-500 */
+        fe left = fr_mul(fr_mul(z[r_next], fr_add(a[idx], beta)), fr_add(s[idx], gamma));
+        v[idx] = fr_add(fr_mul(v[idx], y), fr_mul(fr_sub(left, fr_mul(z[idx], tv[idx])), l_active[idx]));            /* :506-512 */
+        v[idx] = fr_add(fr_mul(v[idx], y), fr_mul(a_minus_s, l0[idx]));                                              /* :516 */
+        v[idx] = fr_add(fr_mul(v[idx], y), fr_mul(fr_mul(a_minus_s, fr_sub(a[idx], a[r_prev])), l_active[idx]));     /* :521-525 */
+    }
+}

@@ -391,3 +391,21 @@ def permutation_product(columns, perms, beta, gamma, omega, deltaomega, last_z):
     lib().oracle_permutation_product(pc, pp, len(cols), ctypes.c_size_t(n), _p(_c(beta, 4)), _p(_c(gamma, 4)), _p(_c(omega, 4)), _p(dw),
                                      _p(_c(last_z, 4)), _p(z))
     return z, dw
+
+
+def lookup_product(compressed_input, compressed_table, permuted_input, permuted_table, beta, gamma):
+    """lookup::prover::Permuted::commit_product (plonk/lookup/prover.rs:173-262): z before the blinding rows"""
+    a, s, ap, sp = (_c(x, 4) for x in (compressed_input, compressed_table, permuted_input, permuted_table))
+    n = a.shape[0]
+    z = np.zeros((n, 4), np.uint64)
+    lib().oracle_lookup_product(_p(a), _p(s), _p(ap), _p(sp), ctypes.c_size_t(n), _p(_c(beta, 4)), _p(_c(gamma, 4)), _p(z))
+    return z
+
+
+def lookup_h(values, rot_scale, table_value, product, permuted_input, permuted_table, l0, l_last, l_active, beta, gamma, y):
+    """evaluate_h, plookup constraints of one lookup (plonk/evaluation.rs:458-531); returns the updated values"""
+    v = _c(values, 4).copy()
+    arrs = [_c(x, 4) for x in (table_value, product, permuted_input, permuted_table, l0, l_last, l_active)]
+    lib().oracle_lookup_h(_p(v), ctypes.c_size_t(v.shape[0]), ctypes.c_int32(rot_scale), *[_p(x) for x in arrs], _p(_c(beta, 4)), _p(_c(gamma, 4)),
+                          _p(_c(y, 4)))
+    return v

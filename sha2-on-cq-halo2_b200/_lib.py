@@ -63,6 +63,8 @@ SYMBOLS = [
     ("cqb_kate_division_dev", _int, [_vp, _sz, u64p, _vp]),
     ("cqb_fr_powers_dev", _int, [u64p, _sz, _vp]),
     ("cqb_fr_prefix_product_dev", _int, [_vp, _sz, u64p, _vp]),
+    ("cqb_lookup_product_dev", _int, [_vp, _vp, _vp, _vp, _u32, u64p, u64p, _vp]),
+    ("cqb_lookup_h_dev", _int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, u64p, u64p, u64p, _u64, ctypes.c_int32]),
     ("cqb_fr_compress_dev", _int, [_vp, _u32, _vp, _sz, u64p, _vp]),
     ("cqb_fr_inv_shifted_dev", _int, [_vp, _sz, _sz, u64p, _vp]),
     ("cqb_fr_mul_dev", _int, [_vp, _vp, _sz, _vp]),

@@ -688,6 +688,25 @@ int cqb_msm_bn254_g1_sparse_dev(cqb_bases_t b, const uint32_t* d_idx, const void
     CQB_TRY(dispatch_msm(&it->second, 0, d_scalars, d_idx, m));  // indices are the caller's responsibility (device-resident)
     return fetch_result(out_xy, is_inf);
 }
+int cqb_lookup_product_dev(const void* d_compressed_input, const void* d_compressed_table, const void* d_permuted_input,
+                           const void* d_permuted_table, uint32_t k, const uint64_t beta[4], const uint64_t gamma[4], void* d_z) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!d_compressed_input || !d_compressed_table || !d_permuted_input || !d_permuted_table || !beta || !gamma || !d_z)
+        return fail(CQB_E_BAD_ARG, "cqb_lookup_product_dev: NULL argument");
+    return lookup_product_run(d_compressed_input, d_compressed_table, d_permuted_input, d_permuted_table, k, beta, gamma, d_z);
+}
+int cqb_lookup_h_dev(void* d_values, const void* d_table_value, const void* d_product_coset, const void* d_permuted_input_coset,
+                     const void* d_permuted_table_coset, const void* d_l0, const void* d_l_last, const void* d_l_active_row, const uint64_t beta[4],
+                     const uint64_t gamma[4], const uint64_t y[4], uint64_t size, int32_t rot_scale) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!beta || !gamma || !y || ((!d_values || !d_table_value || !d_product_coset || !d_permuted_input_coset || !d_permuted_table_coset || !d_l0 ||
+                                   !d_l_last || !d_l_active_row) && size))
+        return fail(CQB_E_BAD_ARG, "cqb_lookup_h_dev: NULL argument");
+    return lookup_h_run(d_values, d_table_value, d_product_coset, d_permuted_input_coset, d_permuted_table_coset, d_l0, d_l_last, d_l_active_row, beta,
+                        gamma, y, size, rot_scale);
+}
 static Scratch g_scale_tab;
 int cqb_fr_scale_dev(void* d_a, size_t n, const uint64_t factor[4]) {
     LOCK;

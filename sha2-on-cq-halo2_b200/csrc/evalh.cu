@@ -7,7 +7,7 @@
 //     hardware interleaves across lanes, so their traffic is coalesced.
 //   * cq_lookup_h_kernel  — the static-lookup (CQ) term (:533-548).
 //   * permutation_h_kernel — the permutation argument terms (:376-452).
-// plookup terms (:455-531) are not part of the CQ path and stay with the reference.
+//   * lookup_h_kernel     — the plookup terms (:458-531); table_value comes from the lookup's own GraphEvaluator run.
 #include <vector>
 
 #include "internal.h"
@@ -115,6 +115,34 @@ __global__ void cq_lookup_h_kernel(uint4* __restrict__ values, const uint4* __re
     Fr v = h_ld_rw(values, i);
     Fr t = fp_sub<FrP>(fp_mul<FrP>(h_ld(b, i), fp_add<FrP>(fp_mul<FrP>(h_ld(f, i), h_ld(l_active, i)), beta)), Fr::one());
     h_st(values, i, fp_add<FrP>(fp_mul<FrP>(v, y), t));
+}
+
+// evaluation.rs:458-531: the five plookup constraints of one lookup argument. table_value[idx] is the value of the lookup's
+// GraphEvaluator, (compressed input + beta)(compressed table + gamma) (:238-283), computed by graph_evaluate_run.
+__global__ void __launch_bounds__(256) lookup_h_kernel(uint4* __restrict__ values, const uint4* __restrict__ table_value,
+                                                       const uint4* __restrict__ product, const uint4* __restrict__ pin, const uint4* __restrict__ ptab,
+                                                       const uint4* __restrict__ l0, const uint4* __restrict__ l_last, const uint4* __restrict__ l_active,
+                                                       Fr beta, Fr gamma, Fr y, unsigned long long size, int rot_scale) {
+    const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= size) return;
+    auto rot_idx = [&](int rot) {  // get_rotation_idx, evaluation.rs:37-39
+        long long v = ((long long)idx + (long long)rot * rot_scale) % (long long)size;
+        if (v < 0) v += (long long)size;
+        return (size_t)v;
+    };
+    const size_t r_next = rot_idx(1), r_prev = rot_idx(-1);
+    const Fr z = h_ld(product, idx), a = h_ld(pin, idx), s = h_ld(ptab, idx);
+    const Fr l0v = h_ld(l0, idx), lact = h_ld(l_active, idx);
+    const Fr a_minus_s = fp_sub<FrP>(a, s);
+    Fr v = h_ld_rw(values, idx);
+    v = fp_add<FrP>(fp_mul<FrP>(v, y), fp_mul<FrP>(fp_sub<FrP>(Fr::one(), z), l0v));                                   // l_0 (1 - z)
+    v = fp_add<FrP>(fp_mul<FrP>(v, y), fp_mul<FrP>(fp_sub<FrP>(fp_sqr<FrP>(z), z), h_ld(l_last, idx)));               // l_last (z^2 - z)
+    Fr left = fp_mul<FrP>(fp_mul<FrP>(h_ld(product, r_next), fp_add<FrP>(a, beta)), fp_add<FrP>(s, gamma));
+    Fr right = fp_mul<FrP>(z, h_ld(table_value, idx));
+    v = fp_add<FrP>(fp_mul<FrP>(v, y), fp_mul<FrP>(fp_sub<FrP>(left, right), lact));                                   // the product rule
+    v = fp_add<FrP>(fp_mul<FrP>(v, y), fp_mul<FrP>(a_minus_s, l0v));                                                   // l_0 (a' - s')
+    v = fp_add<FrP>(fp_mul<FrP>(v, y), fp_mul<FrP>(fp_mul<FrP>(a_minus_s, fp_sub<FrP>(a, h_ld(pin, r_prev))), lact));  // (a' - s')(a' - a'(w^-1 X))
+    h_st(values, idx, v);
 }
 
 struct PermArgs {
@@ -232,6 +260,19 @@ int cq_lookup_h_run(void* d_values, const void* d_b, const void* d_f, const void
     if (size == 0) return 0;
     cq_lookup_h_kernel<<<(unsigned)((size + 255) / 256), 256, 0, ctx().stream>>>((uint4*)d_values, (const uint4*)d_b, (const uint4*)d_f,
                                                                                   (const uint4*)d_l_active, fr_from_u64x4(beta), fr_from_u64x4(y), size);
+    CQB_LAUNCHED();
+    CQB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int lookup_h_run(void* d_values, const void* d_table_value, const void* d_product, const void* d_permuted_input, const void* d_permuted_table,
+                 const void* d_l0, const void* d_l_last, const void* d_l_active, const uint64_t* beta, const uint64_t* gamma, const uint64_t* y,
+                 uint64_t size, int32_t rot_scale) {
+    if (size == 0) return 0;
+    lookup_h_kernel<<<(unsigned)((size + 255) / 256), 256, 0, ctx().stream>>>(
+        (uint4*)d_values, (const uint4*)d_table_value, (const uint4*)d_product, (const uint4*)d_permuted_input, (const uint4*)d_permuted_table,
+        (const uint4*)d_l0, (const uint4*)d_l_last, (const uint4*)d_l_active, fr_from_u64x4(beta), fr_from_u64x4(gamma), fr_from_u64x4(y), size,
+        rot_scale);
     CQB_LAUNCHED();
     CQB_CUDA(cudaGetLastError());
     return 0;

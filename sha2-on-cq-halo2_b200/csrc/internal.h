@@ -65,6 +65,9 @@ int permutation_h_run(void* d_values, uint64_t size, int32_t rot_scale, int32_t 
                       uint32_t nsets, const void* const* d_columns, const void* const* d_perm_cosets, uint32_t ncols, const void* d_l0,
                       const void* d_l_last, const void* d_l_active, const uint64_t* beta, const uint64_t* gamma, const uint64_t* y,
                       const uint64_t* extended_omega);
+int lookup_h_run(void* d_values, const void* d_table_value, const void* d_product, const void* d_permuted_input, const void* d_permuted_table,
+                 const void* d_l0, const void* d_l_last, const void* d_l_active, const uint64_t* beta, const uint64_t* gamma, const uint64_t* y,
+                 uint64_t size, int32_t rot_scale);
 void evalh_release_all();
 
 // ---- poly.cu ----
@@ -80,6 +83,8 @@ int permutation_product_run(const void* const* d_columns, const void* const* d_p
 int fr_compress_run(const void* const* d_cols, uint32_t ncols, const uint32_t* d_idx, size_t n, const uint64_t theta[4], void* d_out);
 int fr_inv_shifted_run(const void* d_in, size_t n, size_t usable, const uint64_t shift[4], void* d_out);
 int fr_mul_run(const void* d_a, const void* d_b, size_t n, void* d_out);
+int lookup_product_run(const void* d_compressed_input, const void* d_compressed_table, const void* d_permuted_input, const void* d_permuted_table,
+                       uint32_t k, const uint64_t beta[4], const uint64_t gamma[4], void* d_z);
 void products_release_all();
 
 // ---- srs.cu ----

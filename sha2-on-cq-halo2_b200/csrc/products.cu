@@ -158,6 +158,45 @@ int permutation_product_run(const void* const* d_columns, const void* const* d_p
 }
 
 
+// ---- plookup grand product: lookup::prover::Permuted::commit_product (plonk/lookup/prover.rs:173-262) -------------------
+// lookup_product[i] = (beta + a'_i)(gamma + s'_i)                                     (:208-216)
+__global__ void __launch_bounds__(256) lookup_denominator_kernel(const uint4* __restrict__ pin, const uint4* __restrict__ ptab, size_t n, Fr beta,
+                                                                 Fr gamma, uint4* __restrict__ lp) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    q_st(lp, i, fp_mul<FrP>(fp_add<FrP>(beta, q_ld(pin, i)), fp_add<FrP>(gamma, q_ld(ptab, i))));
+}
+// lookup_product[i] *= (a_i + beta)(s_i + gamma), a / s the theta-compressed input / table expressions   (:225-232)
+__global__ void __launch_bounds__(256) lookup_numerator_kernel(const uint4* __restrict__ cin, const uint4* __restrict__ ctab, size_t n, Fr beta,
+                                                               Fr gamma, uint4* __restrict__ lp) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr v = fp_mul<FrP>(q_ld(lp, i), fp_add<FrP>(q_ld(cin, i), beta));
+    q_st(lp, i, fp_mul<FrP>(v, fp_add<FrP>(q_ld(ctab, i), gamma)));
+}
+// d_z[0] = 1, d_z[i] = prod_{r < i} lookup_product[r], i < 2^k (:249-254; the caller overwrites the blinding rows, :259)
+int lookup_product_run(const void* d_compressed_input, const void* d_compressed_table, const void* d_permuted_input, const void* d_permuted_table,
+                       uint32_t k, const uint64_t beta[4], const uint64_t gamma[4], void* d_z) {
+    if (k > 28) return fail(CQB_E_BAD_SIZE, "log_n = %u exceeds Fr::S = 28", k);
+    cudaStream_t st = ctx().stream;
+    size_t n = (size_t)1 << k;
+    Fr b = fr_from_u64x4(beta), g = fr_from_u64x4(gamma);
+    CQB_TRY(g_prod_mv.ensure(n * 32));
+    uint4* lp = g_prod_mv.as<uint4>();
+    unsigned grid = (unsigned)((n + 255) / 256);
+    lookup_denominator_kernel<<<grid, 256, 0, st>>>((const uint4*)d_permuted_input, (const uint4*)d_permuted_table, n, b, g, lp);
+    CQB_LAUNCHED();
+    CQB_TRY(fr_batch_invert_run(lp, n));  // :220
+    lookup_numerator_kernel<<<grid, 256, 0, st>>>((const uint4*)d_compressed_input, (const uint4*)d_compressed_table, n, b, g, lp);
+    CQB_LAUNCHED();
+    Fr one = Fr::one();
+    uint64_t one_l[4];
+    for (int i = 0; i < 4; i++) one_l[i] = (uint64_t)one.l[2 * i] | ((uint64_t)one.l[2 * i + 1] << 32);
+    CQB_TRY(fr_prefix_product_run(lp, n, one_l, d_z));
+    CQB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ---- element-wise pieces of the CQ prover (plonk/static_lookup/prover.rs), device-resident -------------------------------
 constexpr int CQ_MAX_COLS = 16;
 struct CompressArgs {

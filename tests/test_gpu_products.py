@@ -168,3 +168,45 @@ def test_permutation_product_of_a_true_permutation_closes(cq, oracle):
     assert last == 1
     for d in d_cols + d_perms + [d_z]:
         d.free()
+
+
+@pytest.mark.parametrize("k,bf", [(4, 3), (9, 5), (14, 5)])
+def test_plookup_commit_product_and_h_terms(cq, oracle, k, bf):
+    """lookup/prover.rs:173-262 commit_product and evaluation.rs:458-531 on the device vs the oracle's restatement. The
+    permuted columns are built as the reference's permute_expression_pair would (sorted input; table entries aligned to the
+    first occurrence of every input value), so the product closes to 1 at row n - bf - 1."""
+    n = 1 << k
+    usable = n - (bf + 1)
+    rng = np.random.default_rng(7 + k)
+    table_vals = [int(v) for v in rng.choice(1 << 30, usable, replace=False)]
+    inputs = [table_vals[int(j)] for j in rng.integers(0, max(1, usable // 3), usable)]
+    perm_in = sorted(inputs)
+    used = sorted(set(inputs))
+    rest = [t for t in table_vals if t not in set(used)]
+    perm_tab, ri = [], 0
+    for i, v in enumerate(perm_in):
+        if i == 0 or v != perm_in[i - 1]:
+            perm_tab.append(v)
+        else:
+            perm_tab.append(rest[ri]); ri += 1
+    assert sorted(perm_tab) == sorted(table_vals)
+    pad = lambda xs: xs + [int(v) for v in rng.integers(0, 1 << 60, n - usable)]  # noqa: E731  blinded tail rows
+    a, s, ap, sp = (P.fr_array_from_ints(pad(list(x))) for x in (inputs, table_vals, perm_in, perm_tab))
+    beta, gamma = 0x1357913579, 0x2468024680
+    L1 = lambda x: P.fr_array_from_ints([x])[0]  # noqa: E731
+    exp_z = oracle.lookup_product(a, s, ap, sp, L1(beta), L1(gamma))
+    assert P.fr_array_to_ints(exp_z[usable:usable + 1])[0] == 1     # the grand product closes on the usable rows
+    d = [Dev(cq, x) for x in (a, s, ap, sp)]
+    d_z = Dev(cq, n=n)
+    cq.lookup.commit_product_dev(d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, k, beta, gamma, d_z.ptr)
+    assert np.array_equal(d_z.get(n), exp_z)
+    # evaluate_h terms on an "extended domain" of 4n rows with arbitrary vectors (the arithmetic is what is checked)
+    size, rot_scale = 4 * n, 4
+    vecs = [oracle.synth_scalars(0x900 + i, size) for i in range(8)]  # values, table_value, product, pin, ptab, l0, l_last, l_active
+    y = oracle.synth_scalars(0x99, 1)[0]
+    exp_v = oracle.lookup_h(vecs[0], rot_scale, *vecs[1:], L1(beta), L1(gamma), y)
+    dv = [Dev(cq, v) for v in vecs]
+    cq.lookup.lookup_h_dev(*[x.ptr for x in dv], L1(beta), L1(gamma), y, size, rot_scale)
+    assert np.array_equal(dv[0].get(size), exp_v)
+    for x in d + [d_z] + dv:
+        x.free()

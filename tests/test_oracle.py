@@ -334,3 +334,36 @@ def test_permutation_product_against_python_bigints():
                                           one(omega), one(dw0), one(last_z))
     assert P.fr_array_to_ints(got_z) == z
     assert P.fr_array_to_ints(got_dw[None, :])[0] == dw
+
+
+def test_plookup_product_and_h_against_python_bigints():
+    """oracle_lookup_product (lookup/prover.rs:173-262) and oracle_lookup_h (evaluation.rs:458-531) vs Python integers"""
+    from oracle import oracle_lib as O
+
+    n = 16
+    rng = random.Random(12)
+    R = P.R_MOD
+    a, s, ap, sp = ([rng.randrange(R) for _ in range(n)] for _ in range(4))
+    beta, gamma, y = (rng.randrange(R) for _ in range(3))
+    z = [1]
+    for i in range(n - 1):
+        lp = pow((beta + ap[i]) * (gamma + sp[i]) % R, -1, R) * (a[i] + beta) % R * (s[i] + gamma) % R
+        z.append(z[-1] * lp % R)
+    one = lambda x: P.fr_array_from_ints([x])[0]  # noqa: E731
+    A = P.fr_array_from_ints
+    assert P.fr_array_to_ints(O.lookup_product(A(a), A(s), A(ap), A(sp), one(beta), one(gamma))) == z
+    size, rot_scale = 32, 2
+    v, tv, zz, pi, pt, l0, ll, la = ([rng.randrange(R) for _ in range(size)] for _ in range(8))
+    exp = []
+    for idx in range(size):
+        rn, rp = (idx + rot_scale) % size, (idx - rot_scale) % size
+        x = v[idx]
+        ams = (pi[idx] - pt[idx]) % R
+        x = (x * y + (1 - zz[idx]) * l0[idx]) % R
+        x = (x * y + (zz[idx] * zz[idx] - zz[idx]) * ll[idx]) % R
+        x = (x * y + (zz[rn] * (pi[idx] + beta) * (pt[idx] + gamma) - zz[idx] * tv[idx]) * la[idx]) % R
+        x = (x * y + ams * l0[idx]) % R
+        x = (x * y + ams * (pi[idx] - pi[rp]) * la[idx]) % R
+        exp.append(x)
+    got = O.lookup_h(A(v), rot_scale, A(tv), A(zz), A(pi), A(pt), A(l0), A(ll), A(la), one(beta), one(gamma), one(y))
+    assert P.fr_array_to_ints(got) == exp
