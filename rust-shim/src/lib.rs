@@ -40,6 +40,22 @@ extern "C" {
     pub fn cqb_eval_polynomial_dev(d_coeffs: *const c_void, n: usize, point: *const u64, out: *mut u64) -> c_int;
     pub fn cqb_kate_division_dev(d_a: *const c_void, n: usize, b: *const u64, d_q: *mut c_void) -> c_int;
     pub fn cqb_fr_batch_invert_dev(d_a: *mut c_void, n: usize) -> c_int;
+    // grand products and the CQ prover's element-wise pieces (device-resident vectors)
+    pub fn cqb_fr_prefix_product_dev(d_in: *const c_void, n: usize, init: *const u64, d_out: *mut c_void) -> c_int;
+    pub fn cqb_permutation_product_dev(d_columns: *const *const c_void, d_perms: *const *const c_void, ncols: u32, k: u32, beta: *const u64,
+                                       gamma: *const u64, omega: *const u64, delta: *const u64, deltaomega_io: *mut u64, last_z: *const u64,
+                                       d_z: *mut c_void) -> c_int;
+    pub fn cqb_lookup_product_dev(d_compressed_input: *const c_void, d_compressed_table: *const c_void, d_permuted_input: *const c_void,
+                                  d_permuted_table: *const c_void, k: u32, beta: *const u64, gamma: *const u64, d_z: *mut c_void) -> c_int;
+    pub fn cqb_lookup_h_dev(d_values: *mut c_void, d_table_value: *const c_void, d_product_coset: *const c_void,
+                            d_permuted_input_coset: *const c_void, d_permuted_table_coset: *const c_void, d_l0: *const c_void,
+                            d_l_last: *const c_void, d_l_active_row: *const c_void, beta: *const u64, gamma: *const u64, y: *const u64,
+                            size: u64, rot_scale: i32) -> c_int;
+    pub fn cqb_fr_compress_dev(d_cols: *const *const c_void, ncols: u32, d_idx: *const u32, n: usize, theta: *const u64, d_out: *mut c_void) -> c_int;
+    pub fn cqb_fr_inv_shifted_dev(d_in: *const c_void, n: usize, usable: usize, shift: *const u64, d_out: *mut c_void) -> c_int;
+    pub fn cqb_fr_mul_dev(d_a: *const c_void, d_b: *const c_void, n: usize, d_out: *mut c_void) -> c_int;
+    pub fn cqb_msm_bn254_g1_sparse_dev(b: cqb_bases_t, d_idx: *const u32, d_scalars: *const c_void, m: usize, out_xy: *mut u64,
+                                       is_inf: *mut c_int) -> c_int;
     pub fn cqb_dev_alloc(bytes: usize, d_out: *mut *mut c_void) -> c_int;
     pub fn cqb_dev_free(d: *mut c_void) -> c_int;
     pub fn cqb_memcpy_h2d(d_dst: *mut c_void, h_src: *const c_void, bytes: usize) -> c_int;
