@@ -264,7 +264,7 @@ def main():
                 "d2h_bytes_per_step": 80 * world, "note": "scalars in pinned host memory per step; SRS bases resident in HBM"},
         "gpu_launches": int(launches) * args.steps,
         "roofline": {"bound": "int", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": INT_PEAK_TMAD32,
-                     "unit": "TMAD32/s", "frac": achieved / INT_PEAK_TMAD32, "traffic": 29.6e9 if (world == 1 and args.log_n == 24 and not args.no_precompute) else None,
+                     "unit": "TMAD32/s", "frac": achieved / INT_PEAK_TMAD32, "traffic": 29.66e9 if (world == 1 and args.log_n == 24 and not args.no_precompute) else None,
                      "kernel_ms": t_acc, "algorithmic_mad32_per_point": MAD32_PER_POINT,
                      # what the kernel really executes: windows_per_point bucket additions x (6 mul x 136 + 2 sqr x 108 + one
                      # fused a*b-c*d x 200) MAD32 — the fraction of the multiplier peak actually in use (< 1 by construction)
@@ -276,10 +276,10 @@ def main():
         "roofline_hbm": {"bound": "hbm", "kernel": "msm_accumulate_kernel",
                          "achieved": per * nwin_eff * 68 / (t_acc * 1e-3) / 1e9, "peak": measured_peaks().get("hbm_gbs", 6650.0),
                          "unit": "GB/s", "frac": per * nwin_eff * 68 / (t_acc * 1e-3) / 1e9 / measured_peaks().get("hbm_gbs", 6650.0),
-                         "traffic": 29.6e9 if (world == 1 and args.log_n == 24 and not args.no_precompute) else None,
+                         "traffic": 29.66e9 if (world == 1 and args.log_n == 24 and not args.no_precompute) else None,
                          "algorithmic_bytes_per_launch": per * nwin_eff * 68,
                          "note": "68 B per bucket addition (64 B affine point + 4 B sorted index) x windows per point; traffic = dram read+write "
-                                 "of one ncu --set full capture of this launch (profiles/r01_ncu_msm_accumulate_final_raw.csv)",
+                                 "of one ncu --set full capture of this launch (profiles/r01b_ncu_msm_accumulate_raw.csv: 29.47 GB read + 0.18 GB written)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in measured_peaks() else "fallback 6650 GB/s"},
         "msm_phase_ms": {k: float(v) for k, v in zip(["count", "scan", "scatter", "accumulate", "merge", "reduce", "window_sum", "final"], ph_avg)},
     }

@@ -466,6 +466,19 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint4* __rest
     else st_xyzz(tail + gid * 8, acc);
 }
 
+// buckets[0][i] += buckets[p][i], p = 1..nparts-1: the bucket arrays of a pipelined MSM's parts are folded by one thread
+// per bucket (a throughput kernel) before the latency-sized reduction, which then reads a single array
+__global__ void __launch_bounds__(128) msm_fold_parts_kernel(uint4* __restrict__ buckets, size_t nbuckets, int nparts) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbuckets) return;
+    G1Xyzz acc = ld_xyzz(buckets + i * 8);
+    for (int p = 1; p < nparts; p++) {
+        G1Xyzz b = ld_xyzz(buckets + ((size_t)p * nbuckets + i) * 8);
+        g1_add(acc, b);
+    }
+    st_xyzz(buckets + i * 8, acc);
+}
+
 // the kernels from here to the precompute kernel are latency-bound chains of XYZZ operations: compact code (ec.cuh FqCall)
 typedef FqCall TailMul;
 // one copy of each point operation per kernel as well (a g1_add is still ~1.2k instructions around its 13 multiplier calls)
@@ -953,7 +966,7 @@ static int msm_acc_phase(const void* d_bases, size_t n, const MsmShape& s, const
 }
 
 // bucket reduction over the sum of the parts' bucket arrays, window combination, affine normalisation
-static int msm_finish(const MsmShape& s, int nparts, void* d_out) {
+static int msm_finish(const MsmShape& s, int nparts, void* d_out) {  // nparts is folded to 1 below
     cudaStream_t st = ctx().stream;
     size_t nbuckets = (size_t)s.nsets * s.nb;
     // tpw threads per set, ch buckets each (both powers of two): about 16k threads in total (one warp per SM sub-partition)
@@ -969,6 +982,11 @@ static int msm_finish(const MsmShape& s, int nparts, void* d_out) {
     uint4* sums1 = partials + (size_t)s.nsets * cps * 8;
     uint4* wins = sums1 + (size_t)s.nsets * lvl1 * 8;
     int h = prof_begin(5, st);
+    if (nparts > 1) {
+        msm_fold_parts_kernel<<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>(g_buckets.as<uint4>(), nbuckets, nparts);
+        CQB_LAUNCHED();
+        nparts = 1;
+    }
     msm_reduce_kernel<<<(unsigned)(s.nsets * cps), RED_CTA, 0, st>>>(g_buckets.as<uint4>(), s, tpw, ch, nparts, nbuckets * 8, partials);
     CQB_LAUNCHED();
     prof_end(h, st);
