@@ -96,6 +96,15 @@ CQB_API int cqb_ntt_bn254_fr(uint64_t* a, const uint64_t omega[4], uint32_t log_
 CQB_API int cqb_ntt_bn254_fr_dev(void* d_a, const uint64_t omega[4], uint32_t log_n);
 /* EvaluationDomain::ifft (poly/domain.rs:366-374): best_fft(omega_inv) then * divisor */
 CQB_API int cqb_intt_bn254_fr(uint64_t* a, const uint64_t omega_inv[4], const uint64_t divisor[4], uint32_t log_n);
+/* Building blocks of the distributed (multi-GPU) four-step NTT — ShardedNTT in the Python mirror; the exchange between the
+ * steps is an all-to-all over NCCL / NVLink, outside this library:
+ *   cqb_ntt_bn254_fr_batch_dev : `batch` (<= 65535) independent in-place transforms of 2^log_n contiguous elements each;
+ *   cqb_fr_mul_omega_powers_dev: a[r][c] *= omega^((row0 + r) * c) over a rows x cols matrix, omega a 2^log_n-th root of unity
+ *                                (the twiddle step between the column and the row transforms);
+ *   cqb_fr_transpose_dev       : out[c][r] = in[r][c] for 32-byte elements (d_out must not alias d_in). */
+CQB_API int cqb_ntt_bn254_fr_batch_dev(void* d_a, const uint64_t omega[4], uint32_t log_n, uint32_t batch);
+CQB_API int cqb_fr_mul_omega_powers_dev(void* d_a, size_t rows, size_t cols, size_t row0, const uint64_t omega[4], uint32_t log_n);
+CQB_API int cqb_fr_transpose_dev(const void* d_in, void* d_out, size_t rows, size_t cols);
 CQB_API int cqb_intt_bn254_fr_dev(void* d_a, const uint64_t omega_inv[4], const uint64_t divisor[4], uint32_t log_n);
 /* EvaluationDomain::coeff_to_extended (poly/domain.rs:252-266): a[i] *= {1, g_coset, g_coset_inv}[i % 3]
  * (distribute_powers_zeta :347-363), zero-pad n -> 2^ext_log_n, best_fft(extended_omega). out has 2^ext_log_n elements. */

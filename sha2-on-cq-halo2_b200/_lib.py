@@ -40,6 +40,9 @@ SYMBOLS = [
     ("cqb_g1_sum_affine", _int, [u64p, _sz, u64p, _ip]),
     ("cqb_ntt_bn254_fr", _int, [u64p, u64p, _u32]),
     ("cqb_ntt_bn254_fr_dev", _int, [_vp, u64p, _u32]),
+    ("cqb_ntt_bn254_fr_batch_dev", _int, [_vp, u64p, _u32, _u32]),
+    ("cqb_fr_mul_omega_powers_dev", _int, [_vp, _sz, _sz, _sz, u64p, _u32]),
+    ("cqb_fr_transpose_dev", _int, [_vp, _vp, _sz, _sz]),
     ("cqb_intt_bn254_fr", _int, [u64p, u64p, u64p, _u32]),
     ("cqb_intt_bn254_fr_dev", _int, [_vp, u64p, u64p, _u32]),
     ("cqb_coset_ntt_bn254_fr", _int, [u64p, _sz, u64p, u64p, _u32, u64p, u64p]),

@@ -426,6 +426,28 @@ int cqb_ntt_bn254_fr_dev(void* d_a, const uint64_t omega[4], uint32_t log_n) {
     return ntt_run(d_a, d_a, log_n, omega, f);
 }
 
+// ---- building blocks of the distributed four-step NTT (one process per GPU; the exchange itself is NCCL, in sharded.py) ----
+int cqb_ntt_bn254_fr_batch_dev(void* d_a, const uint64_t omega[4], uint32_t log_n, uint32_t batch) {
+    LOCK;
+    CQB_TRY(require_init());
+    if ((!d_a && batch) || !omega) return fail(CQB_E_BAD_ARG, "cqb_ntt_bn254_fr_batch_dev: NULL argument");
+    CQB_TRY(check_log_n(log_n));
+    NttFused f;
+    return ntt_run(d_a, d_a, log_n, omega, f, batch);
+}
+int cqb_fr_mul_omega_powers_dev(void* d_a, size_t rows, size_t cols, size_t row0, const uint64_t omega[4], uint32_t log_n) {
+    LOCK;
+    CQB_TRY(require_init());
+    if ((!d_a && rows && cols) || !omega) return fail(CQB_E_BAD_ARG, "cqb_fr_mul_omega_powers_dev: NULL argument");
+    return fr_mul_omega_powers_run(d_a, rows, cols, row0, omega, log_n);
+}
+int cqb_fr_transpose_dev(const void* d_in, void* d_out, size_t rows, size_t cols) {
+    LOCK;
+    CQB_TRY(require_init());
+    if ((!d_in || !d_out || d_in == d_out) && rows && cols) return fail(CQB_E_BAD_ARG, "cqb_fr_transpose_dev: NULL or aliasing argument");
+    return fr_transpose_run(d_in, d_out, rows, cols);
+}
+
 int cqb_intt_bn254_fr_dev(void* d_a, const uint64_t omega_inv[4], const uint64_t divisor[4], uint32_t log_n) {
     LOCK;
     CQB_TRY(require_init());

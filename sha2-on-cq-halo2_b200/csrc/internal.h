@@ -20,7 +20,10 @@ struct NttFused {
     int post_mode = 0; // 0 none | 1: x *= post[0] | 2: x *= post[i % 3]
     Fr post[3];
 };
-int ntt_run(const void* d_src, void* d_dst, uint32_t log_n, const uint64_t omega[4], const NttFused& f);
+// batch > 1: `batch` independent transforms of 2^log_n contiguous elements each, stored back to back
+int ntt_run(const void* d_src, void* d_dst, uint32_t log_n, const uint64_t omega[4], const NttFused& f, uint32_t batch = 1);
+int fr_mul_omega_powers_run(void* d_a, size_t rows, size_t cols, size_t row0, const uint64_t omega[4], uint32_t log_n);
+int fr_transpose_run(const void* d_in, void* d_out, size_t rows, size_t cols);
 int fr_scale_table(void* d_a, size_t n, const void* d_tab, uint32_t len);
 void ntt_release_all();
 Fr fr_from_u64x4(const uint64_t* p);

@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const __grid_constant_
     uint4* shi = sm + T;
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;
     const uint32_t blk = blockIdx.x;
+    const size_t boff = (size_t)blockIdx.y << a.L;  // batched transforms: member blockIdx.y of gridDim.y independent vectors
     const uint32_t qmask = (1u << a.q) - 1u;
     // bits of the global index owned by this CTA
     uint32_t lo = 0, hi = 0;
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const __grid_constant_
             uint32_t i = row | ((blk | (col << (a.L - a.r - a.q))) << a.r);
             uint32_t j = __brev(i) >> (32 - a.L);
             if ((unsigned long long)j < a.n_in) {
-                v = ld_fr(a.src, j);
+                v = ld_fr(a.src, boff + j);
                 if (a.pre_mode == 1) {
                     uint32_t m = j % 3u;
                     if (m) v = fp_mul<FrP>(v, a.pre[m]);
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const __grid_constant_
             }
         } else {
             size_t i = (size_t)col | ((size_t)lo << a.q) | ((size_t)row << a.s0) | ((size_t)hi << (a.s0 + a.r));
-            v = ld_fr(a.src, i);
+            v = ld_fr(a.src, boff + i);
         }
         sm_st(slo, shi, e, v);
     }
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const __grid_constant_
         else i = (size_t)col | ((size_t)lo << a.q) | ((size_t)row << a.s0) | ((size_t)hi << (a.s0 + a.r));
         Fr v = sm_ld(slo, shi, e);
         if (a.post_mode) v = fp_mul<FrP>(v, a.post[a.post_mode == 1 ? 0 : (int)(i % 3)]);
-        st_fr(a.dst, i, v);
+        st_fr(a.dst, boff + i, v);
     }
 }
 
@@ -326,7 +327,9 @@ int fr_powers_run(const uint64_t base[4], size_t count, void* d_out) {
 }
 
 // d_src may alias d_dst (in place). All pointers are device pointers to 32-byte Fr elements.
-int ntt_run(const void* d_src, void* d_dst, uint32_t L, const uint64_t omega[4], const NttFused& f) {
+int ntt_run(const void* d_src, void* d_dst, uint32_t L, const uint64_t omega[4], const NttFused& f, uint32_t batch) {
+    if (batch == 0) return 0;
+    if (batch > 65535u) return fail(CQB_E_BAD_SIZE, "NTT batch of %u exceeds 65535", batch);
     if (L > 28) return fail(CQB_E_BAD_SIZE, "log_n = %u exceeds Fr::S = 28 (bn256/fr.rs:72)", L);
     cudaStream_t st = ctx().stream;
     size_t n = (size_t)1 << L;
@@ -339,6 +342,7 @@ int ntt_run(const void* d_src, void* d_dst, uint32_t L, const uint64_t omega[4],
         Fr m = Fr::one();
         if (f.pre_mode == 2) m = fp_mul<FrP>(m, f.pre[0]);
         if (f.post_mode) m = fp_mul<FrP>(m, f.post[0]);
+        if (batch != 1) return fail(CQB_E_BAD_SIZE, "batched NTT of length 1 is not supported");
         fr_scale_one_kernel<<<1, 1, 0, st>>>((const uint4*)d_src, (uint4*)d_dst, m);
         CQB_LAUNCHED();
         CQB_CUDA(cudaGetLastError());
@@ -352,7 +356,7 @@ int ntt_run(const void* d_src, void* d_dst, uint32_t L, const uint64_t omega[4],
     bool inplace = (d_src == d_dst);
     uint4* work = (uint4*)d_dst;
     if (inplace) {
-        CQB_TRY(g_ntt_scratch.ensure(n * 32));
+        CQB_TRY(g_ntt_scratch.ensure((size_t)batch * n * 32));
         work = g_ntt_scratch.as<uint4>();
     }
     int s0 = 0;
@@ -378,12 +382,72 @@ int ntt_run(const void* d_src, void* d_dst, uint32_t L, const uint64_t omega[4],
         unsigned grid = (unsigned)(n >> (a.r + a.q));
         int threads = T >> 2;
         if (threads < 1) threads = 1;
-        ntt_pass_kernel<<<grid, threads, (size_t)T * 32, st>>>(a);
+        ntt_pass_kernel<<<dim3(grid, batch), threads, (size_t)T * 32, st>>>(a);
         CQB_LAUNCHED();
         CQB_CUDA(cudaGetLastError());
         s0 += a.r;
     }
-    if (inplace && P == 1) CQB_CUDA(cudaMemcpyAsync(d_dst, work, n * 32, cudaMemcpyDeviceToDevice, st));
+    if (inplace && P == 1) CQB_CUDA(cudaMemcpyAsync(d_dst, work, (size_t)batch * n * 32, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// ---- pieces of the distributed four-step NTT (sharded.py ShardedNTT) ------------------------------------------------------
+// a[r][c] *= omega^((row0 + r) * c), omega = the 2^L-th root whose table tw[i] = omega^i (i < 2^(L-1)) is resident:
+// the twiddle step between the column and the row transforms of the four-step decomposition
+__global__ void __launch_bounds__(256) fr_mul_omega_powers_kernel(uint4* __restrict__ a, size_t rows, size_t cols, size_t row0,
+                                                                  const uint4* __restrict__ tw, uint32_t L) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const size_t r = i / cols, c = i % cols;
+    const size_t e = ((row0 + r) * c) & (((size_t)1 << L) - 1);
+    const size_t half = (size_t)1 << (L - 1);
+    if (e == 0) return;
+    Fr w = e < half ? ldg_fr(tw, e) : fp_neg<FrP>(ldg_fr(tw, e - half));  // omega^(n/2) = -1
+    st_fr(a, i, fp_mul<FrP>(ld_fr(a, i), w));
+}
+int fr_mul_omega_powers_run(void* d_a, size_t rows, size_t cols, size_t row0, const uint64_t omega[4], uint32_t L) {
+    if (rows == 0 || cols == 0) return 0;
+    if (L == 0 || L > 28) return fail(CQB_E_BAD_SIZE, "omega powers: log_n = %u out of range", L);
+    const uint4* tw = nullptr;
+    CQB_TRY(get_twiddles(omega, L, &tw));
+    size_t total = rows * cols;
+    fr_mul_omega_powers_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx().stream>>>((uint4*)d_a, rows, cols, row0, tw, L);
+    CQB_LAUNCHED();
+    CQB_CUDA(cudaGetLastError());
+    return 0;
+}
+// out[c][r] = in[r][c] for 32-byte elements: 32 x 32 tiles staged in shared memory as two uint4 planes (+1 padding), so that
+// both the global reads and the global writes are 128-bit and row-contiguous
+__global__ void __launch_bounds__(256) fr_transpose_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t rows, uint32_t cols) {
+    __shared__ uint4 tlo[32][33], thi[32][33];
+    const uint32_t c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (uint32_t j = ty; j < 32; j += 8) {
+        const uint32_t r = r0 + j, c = c0 + tx;
+        if (r < rows && c < cols) {
+            const size_t i = (size_t)r * cols + c;
+            tlo[j][tx] = in[2 * i];
+            thi[j][tx] = in[2 * i + 1];
+        }
+    }
+    __syncthreads();
+    for (uint32_t j = ty; j < 32; j += 8) {
+        const uint32_t c = c0 + j, r = r0 + tx;
+        if (r < rows && c < cols) {
+            const size_t o = (size_t)c * rows + r;
+            out[2 * o] = tlo[tx][j];
+            out[2 * o + 1] = thi[tx][j];
+        }
+    }
+}
+int fr_transpose_run(const void* d_in, void* d_out, size_t rows, size_t cols) {
+    if (rows == 0 || cols == 0) return 0;
+    if (rows > 0xffffffffull || cols > 0xffffffffull) return fail(CQB_E_BAD_SIZE, "transpose dimensions exceed 32 bits");
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+    if (grid.y > 65535u) return fail(CQB_E_BAD_SIZE, "transpose: more than 2^21 rows");
+    fr_transpose_kernel<<<grid, 256, 0, ctx().stream>>>((const uint4*)d_in, (uint4*)d_out, (uint32_t)rows, (uint32_t)cols);
+    CQB_LAUNCHED();
+    CQB_CUDA(cudaGetLastError());
     return 0;
 }
 

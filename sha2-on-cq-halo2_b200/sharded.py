@@ -121,3 +121,109 @@ class ShardedMSM:
     def msm_host_ptr(self, host_ptr, m):
         partial, _ = self.backend.msm_host_ptr(host_ptr, m)
         return self.fold(partial)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Distributed four-step NTT (SURVEY.md §8e "NTT: natural only via four-step"): measured to win on one NVSwitch box
+# (tools/a2a_probe.py: the all-to-all of a 2^26-element vector over 8 GPUs takes 0.45 ms, the single-GPU transform 16.7 ms).
+#
+# The vector of n = n1 * n2 elements is block-distributed: rank g holds the contiguous range [g n/G, (g+1) n/G) on input AND
+# on output (natural order both ways — the layout a caller that shards polynomials by index range already has). With
+# j = j1 n2 + j2 and k = k1 + n1 k2:   X[k1 + n1 k2] = sum_j2 w_n2^(j2 k2) [ w^(j2 k1) sum_j1 x[j1 n2 + j2] w_n1^(j1 k1) ]
+#   T1  distributed transpose  [j1][j2] -> [j2][j1]           (local 32-byte-element transpose + all-to-all + interleave)
+#   A   n2/G local transforms of length n1 over j1 (batched)  -> [j2][k1]
+#   B   multiply by w^(j2 k1)                                  (cqb_fr_mul_omega_powers_dev)
+#   T2  distributed transpose  -> [k1][j2]
+#   C   n1/G local transforms of length n2 over j2             -> [k1][k2]
+#   T3  distributed transpose  -> [k2][k1] = natural order k = k2 n1 + k1, block-distributed
+# The only data-path collective is the all-to-all of the three transposes (NCCL over NVLink; gloo in the CPU test).
+# Field arithmetic is exact, so the result has the limbs of the reference's best_fft on the whole vector.
+# ---------------------------------------------------------------------------------------------------------------------
+class CudaNttBackend:
+    """device operations of ShardedNTT through the C ABI, on torch uint8 CUDA tensors of 32 bytes per element"""
+
+    def __init__(self, device):
+        import torch
+
+        self.torch = torch
+        self.device = device
+
+    def empty(self, nelem):
+        return self.torch.empty(nelem * 32, dtype=self.torch.uint8, device=self.device)
+
+    def transpose(self, t, rows, cols):
+        out = self.empty(rows * cols)
+        _lib.check(_lib.lib().cqb_fr_transpose_dev(ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(out.data_ptr()), rows, cols))
+        return out
+
+    def ntt_batch(self, t, omega_limbs, log_n, batch):
+        done = 0
+        while done < batch:  # gridDim.y limit of the batched kernel
+            b = min(65535, batch - done)
+            _lib.check(_lib.lib().cqb_ntt_bn254_fr_batch_dev(ctypes.c_void_p(t.data_ptr() + (done << log_n) * 32), _lib.p64(omega_limbs), log_n, b))
+            done += b
+
+    def mul_omega_powers(self, t, rows, cols, row0, omega_limbs, log_n):
+        _lib.check(_lib.lib().cqb_fr_mul_omega_powers_dev(ctypes.c_void_p(t.data_ptr()), rows, cols, row0, _lib.p64(omega_limbs), log_n))
+
+    def scale(self, t, nelem, factor_limbs):
+        _lib.check(_lib.lib().cqb_fr_scale_dev(ctypes.c_void_p(t.data_ptr()), nelem, _lib.p64(factor_limbs)))
+
+    def interleave(self, recv, world, q_local, p_local):
+        """recv = [src rank][q_local][p_local] -> [q_local][src rank][p_local] (rows of the transposed matrix, whole)"""
+        return recv.view(world, q_local, p_local * 32).permute(1, 0, 2).contiguous().view(-1)
+
+
+class ShardedNTT:
+    """One rank's view of a forward / inverse NTT of 2^log_n elements block-distributed over `world` ranks."""
+
+    def __init__(self, backend, log_n, rank=0, world=1, group=None):
+        from .fields import FR_ROOT_OF_UNITY, FR_S, R_MOD, fr_to_limbs
+
+        assert world & (world - 1) == 0, "world must be a power of two"
+        self.backend, self.rank, self.world, self.group = backend, rank, world, group
+        self.log_n = log_n
+        self.l1 = log_n // 2            # n1 = 2^l1 rows (j1 / k1), n2 = 2^l2 columns (j2 / k2)
+        self.l2 = log_n - self.l1
+        g = world.bit_length() - 1
+        assert self.l1 >= g and self.l2 >= g, "every rank needs at least one row and one column"
+        assert log_n <= FR_S
+        w = FR_ROOT_OF_UNITY
+        for _ in range(log_n, FR_S):
+            w = w * w % R_MOD
+        self._mod = R_MOD
+        self._limbs = fr_to_limbs
+        self.omega = w                                   # the 2^log_n-th root the reference's domain would use (domain.rs:54-61)
+
+    def _dist_transpose(self, x, p_rows, q_cols):
+        """global (p_rows x q_cols) matrix distributed by row blocks -> its transpose, distributed by row blocks"""
+        import torch.distributed as dist
+
+        G = self.world
+        pl, ql = p_rows // G, q_cols // G
+        t = self.backend.transpose(x, pl, q_cols)        # [q][p_local]; rows q in block h are contiguous: chunk h
+        if G == 1:
+            return t
+        recv = self.backend.empty(q_cols * pl)
+        dist.all_to_all_single(recv, t, group=self.group)
+        return self.backend.interleave(recv, G, ql, pl)  # [q_local][p]
+
+    def _run(self, x_local, omega):
+        n1, n2, G = 1 << self.l1, 1 << self.l2, self.world
+        lim = self._limbs
+        y = self._dist_transpose(x_local, n1, n2)                                    # T1: [j2_local][j1]
+        self.backend.ntt_batch(y, lim(pow(omega, n2, self._mod)), self.l1, n2 // G)  # A
+        self.backend.mul_omega_powers(y, n2 // G, n1, self.rank * (n2 // G), lim(omega), self.log_n)  # B
+        z = self._dist_transpose(y, n2, n1)                                          # T2: [k1_local][j2]
+        self.backend.ntt_batch(z, lim(pow(omega, n1, self._mod)), self.l2, n1 // G)  # C
+        return self._dist_transpose(z, n1, n2)                                       # T3: [k2_local][k1] = natural order
+
+    def forward(self, x_local):
+        """best_fft(a, omega, log_n) (arithmetic.rs:171) on the distributed vector; returns this rank's block of the result"""
+        return self._run(x_local, self.omega)
+
+    def inverse(self, x_local):
+        """EvaluationDomain::ifft (poly/domain.rs:366-374): best_fft with omega^-1, then the 1/n scaling"""
+        out = self._run(x_local, pow(self.omega, -1, self._mod))
+        self.backend.scale(out, (1 << self.log_n) // self.world, self._limbs(pow(1 << self.log_n, -1, self._mod)))
+        return out

@@ -113,3 +113,82 @@ def test_shard_range_balanced():
             assert max(c for _, c in rs) - min(c for _, c in rs) <= 1
             for (s0, c0), (s1, _) in zip(rs, rs[1:]):
                 assert s0 + c0 == s1
+
+
+def _ntt_worker(rank, world, port, log_n, q):
+    """ShardedNTT host logic (three distributed transposes, batched local transforms, twiddles) with an oracle-backed
+    stand-in device: the result block of every rank must equal the oracle's best_fft of the whole vector"""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    import cqb200  # noqa: F401
+    from oracle import oracle_lib as O
+    from oracle import pyref as P
+    from sha2_on_cq_halo2_b200.sharded import ShardedNTT
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class OracleNttBackend:  # torch uint8 CPU tensors, 32 bytes per element
+        def empty(self, nelem):
+            return torch.empty(nelem * 32, dtype=torch.uint8)
+
+        @staticmethod
+        def _np(t):
+            return t.numpy().view(np.uint64).reshape(-1, 4)
+
+        def transpose(self, t, rows, cols):
+            a = self._np(t).reshape(rows, cols, 4).transpose(1, 0, 2)
+            return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1))
+
+        def ntt_batch(self, t, omega_limbs, log_n, batch):
+            a = self._np(t).reshape(batch, 1 << log_n, 4)
+            for b in range(batch):
+                a[b] = O.best_fft(np.ascontiguousarray(a[b]), omega_limbs, log_n, 1)
+
+        def mul_omega_powers(self, t, rows, cols, row0, omega_limbs, log_n):
+            a = self._np(t).reshape(rows, cols, 4)
+            w = P.fr_array_to_ints(np.asarray(omega_limbs)[None, :])[0]
+            for r in range(rows):
+                vals = P.fr_array_to_ints(a[r])
+                a[r] = P.fr_array_from_ints([v * pow(w, (row0 + r) * c, P.R_MOD) % P.R_MOD for c, v in enumerate(vals)])
+
+        def scale(self, t, nelem, factor_limbs):
+            a = self._np(t)
+            f = P.fr_array_to_ints(np.asarray(factor_limbs)[None, :])[0]
+            a[:] = P.fr_array_from_ints([v * f % P.R_MOD for v in P.fr_array_to_ints(a)])
+
+        def interleave(self, recv, world, q_local, p_local):
+            return recv.view(world, q_local, p_local * 32).permute(1, 0, 2).contiguous().view(-1)
+
+    n = 1 << log_n
+    per = n // world
+    full = O.synth_scalars(0x5EED0002, n)
+    sn = ShardedNTT(OracleNttBackend(), log_n, rank, world)
+    mine = torch.from_numpy(np.ascontiguousarray(full[rank * per:(rank + 1) * per]).view(np.uint8).reshape(-1).copy())
+    got = sn.forward(mine).numpy().view(np.uint64).reshape(-1, 4)
+    exp = O.best_fft(full.copy(), P.int_to_limbs(P.to_mont(sn.omega, P.R_MOD)), log_n, 1)
+    ok = np.array_equal(got, exp[rank * per:(rank + 1) * per])
+    back = sn.inverse(torch.from_numpy(np.ascontiguousarray(got).view(np.uint8).reshape(-1).copy())).numpy().view(np.uint64).reshape(-1, 4)
+    ok = ok and np.array_equal(back, full[rank * per:(rank + 1) * per])
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,log_n", [(2, 5), (2, 8), (4, 7), (1, 6)])
+def test_sharded_ntt_host_logic_gloo(world, log_n):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ntt_worker, args=(r, world, port, log_n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
