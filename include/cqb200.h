@@ -103,6 +103,13 @@ CQB_API int cqb_intt_bn254_fr(uint64_t* a, const uint64_t omega_inv[4], const ui
  *                                (the twiddle step between the column and the row transforms);
  *   cqb_fr_transpose_dev       : out[c][r] = in[r][c] for 32-byte elements (d_out must not alias d_in). */
 CQB_API int cqb_ntt_bn254_fr_batch_dev(void* d_a, const uint64_t omega[4], uint32_t log_n, uint32_t batch);
+/* The batched transform with the layout changes of the distributed NTT fused into its first gather and last store (out of
+ * place): in_seg_log >= 0: member b's element idx is read from an all-to-all receive buffer laid out
+ * [idx >> in_seg_log][b][idx & (2^in_seg_log - 1)] (source rank, member, segment); out_transposed != 0: results are stored
+ * as [idx][b] (already in destination-rank order for the next all-to-all); tw_omega != NULL: result idx of member b is also
+ * multiplied by tw_omega^((tw_row0 + b) * idx), tw_omega a 2^tw_log_n-th root of unity. */
+CQB_API int cqb_ntt_bn254_fr_batch_map_dev(const void* d_src, void* d_dst, const uint64_t omega[4], uint32_t log_n, uint32_t batch,
+                                           int in_seg_log, int out_transposed, const uint64_t tw_omega[4], uint32_t tw_log_n, size_t tw_row0);
 CQB_API int cqb_fr_mul_omega_powers_dev(void* d_a, size_t rows, size_t cols, size_t row0, const uint64_t omega[4], uint32_t log_n);
 CQB_API int cqb_fr_transpose_dev(const void* d_in, void* d_out, size_t rows, size_t cols);
 CQB_API int cqb_intt_bn254_fr_dev(void* d_a, const uint64_t omega_inv[4], const uint64_t divisor[4], uint32_t log_n);

@@ -41,6 +41,7 @@ SYMBOLS = [
     ("cqb_ntt_bn254_fr", _int, [u64p, u64p, _u32]),
     ("cqb_ntt_bn254_fr_dev", _int, [_vp, u64p, _u32]),
     ("cqb_ntt_bn254_fr_batch_dev", _int, [_vp, u64p, _u32, _u32]),
+    ("cqb_ntt_bn254_fr_batch_map_dev", _int, [_vp, _vp, u64p, _u32, _u32, _int, _int, u64p, _u32, _sz]),
     ("cqb_fr_mul_omega_powers_dev", _int, [_vp, _sz, _sz, _sz, u64p, _u32]),
     ("cqb_fr_transpose_dev", _int, [_vp, _vp, _sz, _sz]),
     ("cqb_intt_bn254_fr", _int, [u64p, u64p, u64p, _u32]),

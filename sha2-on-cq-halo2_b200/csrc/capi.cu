@@ -435,6 +435,36 @@ int cqb_ntt_bn254_fr_batch_dev(void* d_a, const uint64_t omega[4], uint32_t log_
     NttFused f;
     return ntt_run(d_a, d_a, log_n, omega, f, batch);
 }
+int cqb_ntt_bn254_fr_batch_map_dev(const void* d_src, void* d_dst, const uint64_t omega[4], uint32_t log_n, uint32_t batch, int in_seg_log,
+                                   int out_transposed, const uint64_t tw_omega[4], uint32_t tw_log_n, size_t tw_row0) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (((!d_src || !d_dst) && batch) || !omega || d_src == d_dst) return fail(CQB_E_BAD_ARG, "cqb_ntt_bn254_fr_batch_map_dev: NULL or aliasing argument");
+    CQB_TRY(check_log_n(log_n));
+    if (in_seg_log > (int)log_n) return fail(CQB_E_BAD_ARG, "segment longer than the transform");
+    NttFused f;
+    if (in_seg_log >= 0) {
+        f.in_map = 1;
+        f.in_s = (unsigned)in_seg_log;
+        f.in_A = (unsigned long long)batch << in_seg_log;
+        f.in_B = 1ull << in_seg_log;
+    }
+    if (out_transposed) {
+        f.out_map = 1;
+        f.out_s = 0;
+        f.out_A = batch;
+        f.out_B = 1;
+    }
+    if (tw_omega) {
+        if (tw_log_n == 0 || tw_log_n > 28) return fail(CQB_E_BAD_SIZE, "twiddle log_n = %u out of range", tw_log_n);
+        const void* t2 = nullptr;
+        CQB_TRY(ntt_get_twiddles(tw_omega, tw_log_n, &t2));
+        f.tw2 = t2;
+        f.tw2_L = tw_log_n;
+        f.tw2_row0 = tw_row0;
+    }
+    return ntt_run(d_src, d_dst, log_n, omega, f, batch);
+}
 int cqb_fr_mul_omega_powers_dev(void* d_a, size_t rows, size_t cols, size_t row0, const uint64_t omega[4], uint32_t log_n) {
     LOCK;
     CQB_TRY(require_init());

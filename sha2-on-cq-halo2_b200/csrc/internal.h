@@ -19,6 +19,13 @@ struct NttFused {
     Fr pre[NTT_PRE_MAX_PUB];
     int post_mode = 0; // 0 none | 1: x *= post[0] | 2: x *= post[i % 3]
     Fr post[3];
+    // distributed four-step NTT (batched, out of place): see NttPassArgs in ntt.cu
+    int in_map = 0, out_map = 0;
+    unsigned in_s = 0, out_s = 0;
+    unsigned long long in_A = 0, in_B = 0, out_A = 0, out_B = 0;
+    const void* tw2 = nullptr;
+    unsigned tw2_L = 0;
+    unsigned long long tw2_row0 = 0;
 };
 // batch > 1: `batch` independent transforms of 2^log_n contiguous elements each, stored back to back
 int ntt_run(const void* d_src, void* d_dst, uint32_t log_n, const uint64_t omega[4], const NttFused& f, uint32_t batch = 1);

@@ -39,6 +39,20 @@ struct NttPassArgs {
     int post_mode;  // 0 none | 1: x *= post[0] | 2: x *= post[i % 3]
     Fr pre[NTT_PRE_MAX];
     Fr post[3];
+    // Address maps of the distributed four-step NTT (batched transforms only). Element idx of member b lives at
+    //   (idx >> s) * A + b * B + (idx & (2^s - 1))
+    // in_map : the FIRST pass gathers straight out of an all-to-all receive buffer [source rank][member][segment]
+    //          (s = log2 segment, A = batch * segment, B = segment) — no interleaving copy;
+    // out_map: the LAST pass stores transposed, [idx][member] (s = 0, A = batch, B = 1), i.e. already in the
+    //          [destination rank][...] order the next all-to-all sends — no transposition pass;
+    // tw2    : the last pass also multiplies element idx of member b by w^((tw2_row0 + b) * idx), w the 2^tw2_L-th root whose
+    //          power table is tw2 — the twiddle step of the four-step decomposition, fused into the store.
+    int in_map, out_map;
+    unsigned in_s, out_s;
+    unsigned long long in_A, in_B, out_A, out_B;
+    const uint4* tw2;
+    unsigned tw2_L;
+    unsigned long long tw2_row0;
 };
 
 __device__ __forceinline__ Fr ld_fr(const uint4* p, size_t i) {
@@ -111,7 +125,7 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const __grid_constant_
             uint32_t i = row | ((blk | (col << (a.L - a.r - a.q))) << a.r);
             uint32_t j = __brev(i) >> (32 - a.L);
             if ((unsigned long long)j < a.n_in) {
-                v = ld_fr(a.src, boff + j);
+                v = ld_fr(a.src, a.in_map ? (size_t)((j >> a.in_s) * a.in_A + blockIdx.y * a.in_B + (j & ((1u << a.in_s) - 1u))) : boff + j);
                 if (a.pre_mode == 1) {
                     uint32_t m = j % 3u;
                     if (m) v = fp_mul<FrP>(v, a.pre[m]);
@@ -195,7 +209,12 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const __grid_constant_
         else i = (size_t)col | ((size_t)lo << a.q) | ((size_t)row << a.s0) | ((size_t)hi << (a.s0 + a.r));
         Fr v = sm_ld(slo, shi, e);
         if (a.post_mode) v = fp_mul<FrP>(v, a.post[a.post_mode == 1 ? 0 : (int)(i % 3)]);
-        st_fr(a.dst, boff + i, v);
+        if (a.tw2) {
+            const size_t ex = ((a.tw2_row0 + blockIdx.y) * i) & (((size_t)1 << a.tw2_L) - 1);
+            const size_t half = (size_t)1 << (a.tw2_L - 1);
+            if (ex) v = fp_mul<FrP>(v, ex < half ? ldg_fr(a.tw2, ex) : fp_neg<FrP>(ldg_fr(a.tw2, ex - half)));
+        }
+        st_fr(a.dst, a.out_map ? (size_t)((i >> a.out_s) * a.out_A + blockIdx.y * a.out_B + (i & (((size_t)1 << a.out_s) - 1))) : boff + i, v);
     }
 }
 
@@ -354,8 +373,10 @@ int ntt_run(const void* d_src, void* d_dst, uint32_t L, const uint64_t omega[4],
     int rs[8];
     for (int p = 0; p < P; p++) rs[p] = (int)L / P + (p < (int)L % P ? 1 : 0);
     bool inplace = (d_src == d_dst);
+    if (inplace && (f.in_map || f.out_map)) return fail(CQB_E_BAD_ARG, "mapped NTT must be out of place");
+    const bool use_scratch = inplace || f.out_map;  // a mapped (scattered) last store must not land on data still to be read
     uint4* work = (uint4*)d_dst;
-    if (inplace) {
+    if (use_scratch) {
         CQB_TRY(g_ntt_scratch.ensure((size_t)batch * n * 32));
         work = g_ntt_scratch.as<uint4>();
     }
@@ -370,13 +391,19 @@ int ntt_run(const void* d_src, void* d_dst, uint32_t L, const uint64_t omega[4],
         a.q = NTT_TILE_LOG - a.r;
         if (a.q > qmax) a.q = qmax;
         a.src = (p == 0) ? (const uint4*)d_src : work;
-        a.dst = (p == P - 1 && inplace && P > 1) ? (uint4*)d_dst : work;
+        a.dst = (p == P - 1 && use_scratch && (P > 1 || !inplace)) ? (uint4*)d_dst : work;
         a.tw = tw;
         a.n_in = f.n_in ? f.n_in : n;
         a.pre_mode = (p == 0) ? f.pre_mode : 0;
         a.pre_len = f.pre_len;
         for (int i = 0; i < NTT_PRE_MAX; i++) a.pre[i] = f.pre[i];
         a.post_mode = (p == P - 1) ? f.post_mode : 0;
+        a.in_map = (p == 0) ? f.in_map : 0;
+        a.in_s = f.in_s; a.in_A = f.in_A; a.in_B = f.in_B;
+        a.out_map = (p == P - 1) ? f.out_map : 0;
+        a.out_s = f.out_s; a.out_A = f.out_A; a.out_B = f.out_B;
+        a.tw2 = (p == P - 1) ? (const uint4*)f.tw2 : nullptr;
+        a.tw2_L = f.tw2_L; a.tw2_row0 = f.tw2_row0;
         for (int i = 0; i < 3; i++) a.post[i] = f.post[i];
         int T = 1 << (a.r + a.q);
         unsigned grid = (unsigned)(n >> (a.r + a.q));

@@ -163,6 +163,16 @@ class CudaNttBackend:
             _lib.check(_lib.lib().cqb_ntt_bn254_fr_batch_dev(ctypes.c_void_p(t.data_ptr() + (done << log_n) * 32), _lib.p64(omega_limbs), log_n, b))
             done += b
 
+    def ntt_batch_map(self, src, omega_limbs, log_n, batch, in_seg_log, tw_omega_limbs=None, tw_log_n=0, tw_row0=0):
+        """batched transform out of `src` (an all-to-all receive buffer [source rank][member][segment]) into a new buffer laid
+        out [idx][member] — the gather, the twiddle step and the transposition are fused into the kernel's first and last pass"""
+        assert batch <= 65535
+        out = self.empty(batch << log_n)
+        _lib.check(_lib.lib().cqb_ntt_bn254_fr_batch_map_dev(
+            ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(out.data_ptr()), _lib.p64(omega_limbs), log_n, batch, in_seg_log, 1,
+            _lib.p64(tw_omega_limbs) if tw_omega_limbs is not None else None, tw_log_n, tw_row0))
+        return out
+
     def mul_omega_powers(self, t, rows, cols, row0, omega_limbs, log_n):
         _lib.check(_lib.lib().cqb_fr_mul_omega_powers_dev(ctypes.c_void_p(t.data_ptr()), rows, cols, row0, _lib.p64(omega_limbs), log_n))
 
@@ -208,8 +218,34 @@ class ShardedNTT:
         dist.all_to_all_single(recv, t, group=self.group)
         return self.backend.interleave(recv, G, ql, pl)  # [q_local][p]
 
+    def _all_to_all(self, t):
+        if self.world == 1:
+            return t
+        import torch.distributed as dist
+
+        recv = self.backend.empty(t.numel() // 32)
+        dist.all_to_all_single(recv, t, group=self.group)
+        return recv
+
+    def _run_fused(self, x_local, omega):
+        """the same six steps with every layout change but the first transposition and the last interleave folded into the
+        batched transforms (cqb_ntt_bn254_fr_batch_map_dev): 2 memory passes besides the transforms instead of 7"""
+        n1, n2, G = 1 << self.l1, 1 << self.l2, self.world
+        pl, ql = n1 // G, n2 // G
+        lim, be = self._limbs, self.backend
+        t = be.transpose(x_local, pl, n2)                                            # [j2][j1_local]: chunk h = rows j2 of rank h
+        r1 = self._all_to_all(t)                                                     # [src][j2_local][j1_local]
+        a = be.ntt_batch_map(r1, lim(pow(omega, n2, self._mod)), self.l1, ql, pl.bit_length() - 1,
+                             lim(omega), self.log_n, self.rank * ql)                 # A + B -> [k1][j2_local]: chunk h = rows k1 of rank h
+        r2 = self._all_to_all(a)                                                     # [src][k1_local][j2_local(src)]
+        c = be.ntt_batch_map(r2, lim(pow(omega, n1, self._mod)), self.l2, pl, ql.bit_length() - 1)  # C -> [k2][k1_local]
+        r3 = self._all_to_all(c)                                                     # [src][k2_local][k1_local(src)]
+        return be.interleave(r3, G, ql, pl) if G > 1 else r3                         # [k2_local][k1]: natural order
+
     def _run(self, x_local, omega):
         n1, n2, G = 1 << self.l1, 1 << self.l2, self.world
+        if hasattr(self.backend, "ntt_batch_map") and max(n1, n2) // G <= 65535:
+            return self._run_fused(x_local, omega)
         lim = self._limbs
         y = self._dist_transpose(x_local, n1, n2)                                    # T1: [j2_local][j1]
         self.backend.ntt_batch(y, lim(pow(omega, n2, self._mod)), self.l1, n2 // G)  # A

@@ -87,3 +87,30 @@ def test_sharded_ntt_world1_equals_single_call(env, oracle, log_n):
     back = sn.inverse(got)
     L.check(lib.cqb_sync())
     assert np.array_equal(_to_host(back), a)
+
+
+@pytest.mark.parametrize("log_n,batch,seg_log", [(6, 8, 2), (10, 4, 0), (12, 16, 5), (9, 3, 9)])
+def test_mapped_batched_ntt(env, oracle, log_n, batch, seg_log):
+    """cqb_ntt_bn254_fr_batch_map_dev: segmented gather, transposed store and fused omega-power twiddle against the plain
+    batched transform + explicit permutations on the host"""
+    cq, torch = env
+    L, lib = cq._lib, cq._lib.lib()
+    n, seg = 1 << log_n, 1 << seg_log
+    nat = oracle.synth_scalars(0x900 + log_n, n * batch).reshape(batch, n, 4)            # member-major natural layout
+    src = np.ascontiguousarray(nat.reshape(batch, n // seg, seg, 4).transpose(1, 0, 2, 3))  # [segment index][member][segment]
+    w_int = P.omega_for(log_n)
+    w = P.int_to_limbs(P.to_mont(w_int, P.R_MOD))
+    big_log, row0 = 14, 5
+    wb_int = P.omega_for(big_log)
+    wb = P.int_to_limbs(P.to_mont(wb_int, P.R_MOD))
+    exp = np.stack([oracle.best_fft(np.ascontiguousarray(nat[b]), w, log_n, 1) for b in range(batch)])
+    for b in range(batch):
+        vals = P.fr_array_to_ints(exp[b])
+        exp[b] = P.fr_array_from_ints([v * pow(wb_int, (row0 + b) * i, P.R_MOD) % P.R_MOD for i, v in enumerate(vals)])
+    exp_t = np.ascontiguousarray(exp.transpose(1, 0, 2))                                    # [idx][member]
+    d_src = _to_dev(torch, src)
+    d_dst = torch.empty_like(d_src)
+    L.check(lib.cqb_ntt_bn254_fr_batch_map_dev(ctypes.c_void_p(d_src.data_ptr()), ctypes.c_void_p(d_dst.data_ptr()), L.p64(w), log_n, batch, seg_log, 1,
+                                               L.p64(wb), big_log, row0))
+    L.check(lib.cqb_sync())
+    assert np.array_equal(_to_host(d_dst).reshape(n, batch, 4), exp_t)
