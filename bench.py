@@ -321,6 +321,26 @@ def main():
                                         "frac": int_t / INT_PEAK_TMAD32}}
         del a_t
 
+    # ---- N > 1: the distributed four-step NTT (sharded.ShardedNTT), 2^ntt_log_n elements block-distributed over the ranks in
+    #      natural order on input and output; the exchange is three NCCL all-to-alls ---------------------------
+    if world > 1 and not args.no_ntt and (world & (world - 1)) == 0:
+        from sha2_on_cq_halo2_b200.sharded import CudaNttBackend, ShardedNTT
+
+        k = args.ntt_log_n
+        n = 1 << k
+        per_ntt = n // world
+        sn = ShardedNTT(CudaNttBackend(dev), k, rank, world)
+        x_t = torch.empty(per_ntt * 32, dtype=torch.uint8, device=dev)
+        L.check(lib.cqb_synth_scalars_dev(SEED_NTT, rank * per_ntt, per_ntt, ctypes.c_void_p(x_t.data_ptr())))
+        ms_ntt = timed(lambda: sn.forward(x_t), args.steps, args.warmup)
+        int_t = (n / 2) * k * 136 / (ms_ntt * 1e-3) / 1e12
+        line["ntt"] = {"metric": f"Fr NTT Gelem/s @2^{k}", "value": n / (ms_ntt * 1e-3) / 1e9, "ms": ms_ntt, "n_gpus": world, "scaling": "strong",
+                       "algorithm": "distributed four-step: transpose, 3 x all-to-all (NCCL over NVLink), two batched local transforms with the "
+                                    "gather / twiddle / transposed store fused in; block-distributed natural order in and out",
+                       "roofline_int": {"bound": "int", "achieved": int_t, "peak": INT_PEAK_TMAD32 * world, "unit": "TMAD32/s",
+                                        "frac": int_t / (INT_PEAK_TMAD32 * world)}}
+        del x_t
+
     # ---- "SHA2-CQ prove ms": the synthetic CQ-prover-shaped op list of SURVEY.md §8(d) (no SHA circuit exists in the
     #      reference, F1), host-pointer C-ABI calls, N=1 only -------------------------------------------------------
     if world == 1 and not args.no_prove:

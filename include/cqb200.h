@@ -110,6 +110,17 @@ CQB_API int cqb_ntt_bn254_fr_batch_dev(void* d_a, const uint64_t omega[4], uint3
  * multiplied by tw_omega^((tw_row0 + b) * idx), tw_omega a 2^tw_log_n-th root of unity. */
 CQB_API int cqb_ntt_bn254_fr_batch_map_dev(const void* d_src, void* d_dst, const uint64_t omega[4], uint32_t log_n, uint32_t batch,
                                            int in_seg_log, int out_transposed, const uint64_t tw_omega[4], uint32_t tw_log_n, size_t tw_row0);
+/* ... and with the exchange itself fused in: the last pass stores result idx of member b into the receive buffer of the rank
+ * that owns it, peer_dst[idx >> (log_n - log2 n_peers)], at [self_rank][idx & mask][b] — peer memory over NVLink (pointers
+ * from cqb_ipc_open; peer_dst[self_rank] is the caller's own buffer). d_scratch (batch * 2^log_n elements, local) holds the
+ * intermediate passes. The caller synchronises the ranks before the buffers are read (any stream-ordered collective). */
+CQB_API int cqb_ntt_bn254_fr_batch_p2p_dev(const void* d_src, void* d_scratch, void* const* peer_dst, uint32_t n_peers, uint32_t self_rank,
+                                           const uint64_t omega[4], uint32_t log_n, uint32_t batch, int in_seg_log,
+                                           const uint64_t tw_omega[4], uint32_t tw_log_n, size_t tw_row0);
+/* CUDA IPC plumbing (one process per GPU): export a cqb_dev_alloc'ed buffer as a 64-byte handle, open a peer's handle, close it */
+CQB_API int cqb_ipc_export(const void* d_ptr, unsigned char handle_out[64]);
+CQB_API int cqb_ipc_open(const unsigned char handle[64], void** d_out);
+CQB_API int cqb_ipc_close(void* d_ptr);
 CQB_API int cqb_fr_mul_omega_powers_dev(void* d_a, size_t rows, size_t cols, size_t row0, const uint64_t omega[4], uint32_t log_n);
 CQB_API int cqb_fr_transpose_dev(const void* d_in, void* d_out, size_t rows, size_t cols);
 CQB_API int cqb_intt_bn254_fr_dev(void* d_a, const uint64_t omega_inv[4], const uint64_t divisor[4], uint32_t log_n);

@@ -465,6 +465,69 @@ int cqb_ntt_bn254_fr_batch_map_dev(const void* d_src, void* d_dst, const uint64_
     }
     return ntt_run(d_src, d_dst, log_n, omega, f, batch);
 }
+// the same transform with its last store going into the peers' receive buffers (out_map == 2); d_scratch: batch * 2^log_n
+// elements of local scratch for the intermediate passes (never written by a peer)
+int cqb_ntt_bn254_fr_batch_p2p_dev(const void* d_src, void* d_scratch, void* const* peer_dst, uint32_t n_peers, uint32_t self_rank,
+                                   const uint64_t omega[4], uint32_t log_n, uint32_t batch, int in_seg_log, const uint64_t tw_omega[4],
+                                   uint32_t tw_log_n, size_t tw_row0) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!d_src || !d_scratch || !peer_dst || !omega || d_src == d_scratch) return fail(CQB_E_BAD_ARG, "cqb_ntt_bn254_fr_batch_p2p_dev: NULL or aliasing argument");
+    if (n_peers < 1 || n_peers > 8 || (n_peers & (n_peers - 1)) || self_rank >= n_peers) return fail(CQB_E_BAD_ARG, "peers: 1, 2, 4 or 8 (got %u)", n_peers);
+    CQB_TRY(check_log_n(log_n));
+    uint32_t g = 0;
+    while ((1u << g) < n_peers) g++;
+    if (log_n < g || in_seg_log > (int)log_n) return fail(CQB_E_BAD_ARG, "transform shorter than the peer count / segment");
+    NttFused f;
+    if (in_seg_log >= 0) {
+        f.in_map = 1;
+        f.in_s = (unsigned)in_seg_log;
+        f.in_A = (unsigned long long)batch << in_seg_log;
+        f.in_B = 1ull << in_seg_log;
+    }
+    f.out_map = 2;
+    f.peer_rows_log = log_n - g;
+    f.peer_self_off = ((unsigned long long)self_rank << (log_n - g)) * batch;
+    for (uint32_t h = 0; h < n_peers; h++) {
+        if (!peer_dst[h]) return fail(CQB_E_BAD_ARG, "NULL peer buffer %u", h);
+        f.peer[h] = peer_dst[h];
+    }
+    if (tw_omega) {
+        if (tw_log_n == 0 || tw_log_n > 28) return fail(CQB_E_BAD_SIZE, "twiddle log_n = %u out of range", tw_log_n);
+        const void* t2 = nullptr;
+        CQB_TRY(ntt_get_twiddles(tw_omega, tw_log_n, &t2));
+        f.tw2 = t2;
+        f.tw2_L = tw_log_n;
+        f.tw2_row0 = tw_row0;
+    }
+    return ntt_run(d_src, d_scratch, log_n, omega, f, batch);
+}
+// CUDA IPC plumbing for the peer buffers (one process per GPU): export a cqb_dev_alloc'ed buffer, open a peer's, close it
+int cqb_ipc_export(const void* d_ptr, unsigned char handle_out[64]) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!d_ptr || !handle_out) return fail(CQB_E_BAD_ARG, "cqb_ipc_export: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CQB_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)));
+    memcpy(handle_out, &h, 64);
+    return 0;
+}
+int cqb_ipc_open(const unsigned char handle[64], void** d_out) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!handle || !d_out) return fail(CQB_E_BAD_ARG, "cqb_ipc_open: NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CQB_CUDA(cudaIpcOpenMemHandle(d_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int cqb_ipc_close(void* d_ptr) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (d_ptr) CQB_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return 0;
+}
 int cqb_fr_mul_omega_powers_dev(void* d_a, size_t rows, size_t cols, size_t row0, const uint64_t omega[4], uint32_t log_n) {
     LOCK;
     CQB_TRY(require_init());

@@ -26,6 +26,9 @@ struct NttFused {
     const void* tw2 = nullptr;
     unsigned tw2_L = 0;
     unsigned long long tw2_row0 = 0;
+    void* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // out_map == 2
+    unsigned peer_rows_log = 0;
+    unsigned long long peer_self_off = 0;
 };
 // batch > 1: `batch` independent transforms of 2^log_n contiguous elements each, stored back to back
 int ntt_run(const void* d_src, void* d_dst, uint32_t log_n, const uint64_t omega[4], const NttFused& f, uint32_t batch = 1);

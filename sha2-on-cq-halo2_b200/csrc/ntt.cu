@@ -53,6 +53,12 @@ struct NttPassArgs {
     const uint4* tw2;
     unsigned tw2_L;
     unsigned long long tw2_row0;
+    // out_map == 2: the transposed store goes STRAIGHT INTO THE PEERS' receive buffers over NVLink (CUDA IPC pointers): result
+    // idx of member b belongs to rank h = idx >> peer_rows_log and lands at peer[h][peer_self_off + (idx & mask) * batch + b]
+    // — the exchange of the distributed NTT is the transform's own last store, tile by tile, with no separate collective.
+    uint4* peer[8];
+    unsigned peer_rows_log;
+    unsigned long long peer_self_off;
 };
 
 __device__ __forceinline__ Fr ld_fr(const uint4* p, size_t i) {
@@ -214,7 +220,12 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const __grid_constant_
             const size_t half = (size_t)1 << (a.tw2_L - 1);
             if (ex) v = fp_mul<FrP>(v, ex < half ? ldg_fr(a.tw2, ex) : fp_neg<FrP>(ldg_fr(a.tw2, ex - half)));
         }
-        st_fr(a.dst, a.out_map ? (size_t)((i >> a.out_s) * a.out_A + blockIdx.y * a.out_B + (i & (((size_t)1 << a.out_s) - 1))) : boff + i, v);
+        if (a.out_map == 2) {
+            const size_t h = i >> a.peer_rows_log;
+            st_fr(a.peer[h], (size_t)(a.peer_self_off + (i & (((size_t)1 << a.peer_rows_log) - 1)) * gridDim.y + blockIdx.y), v);
+        } else {
+            st_fr(a.dst, a.out_map ? (size_t)((i >> a.out_s) * a.out_A + blockIdx.y * a.out_B + (i & (((size_t)1 << a.out_s) - 1))) : boff + i, v);
+        }
     }
 }
 
@@ -402,6 +413,9 @@ int ntt_run(const void* d_src, void* d_dst, uint32_t L, const uint64_t omega[4],
         a.in_s = f.in_s; a.in_A = f.in_A; a.in_B = f.in_B;
         a.out_map = (p == P - 1) ? f.out_map : 0;
         a.out_s = f.out_s; a.out_A = f.out_A; a.out_B = f.out_B;
+        for (int h = 0; h < 8; h++) a.peer[h] = (uint4*)f.peer[h];
+        a.peer_rows_log = f.peer_rows_log;
+        a.peer_self_off = f.peer_self_off;
         a.tw2 = (p == P - 1) ? (const uint4*)f.tw2 : nullptr;
         a.tw2_L = f.tw2_L; a.tw2_row0 = f.tw2_row0;
         for (int i = 0; i < 3; i++) a.post[i] = f.post[i];

@@ -173,6 +173,63 @@ class CudaNttBackend:
             _lib.p64(tw_omega_limbs) if tw_omega_limbs is not None else None, tw_log_n, tw_row0))
         return out
 
+    # ---- peer-memory exchange (CUDA IPC): receive buffers every rank exposes to the others ---------------------------------
+    class _RawBuffer:
+        """a cqb_dev_alloc'ed buffer viewed as a torch tensor through the CUDA array interface"""
+
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+    def peer_buffers(self, nelem, count, rank, world, group):
+        """allocate `count` receive buffers of nelem elements, exchange their IPC handles; returns (own tensors, per buffer the
+        list of `world` device pointers: peers' buffers opened through CUDA IPC, own pointer at index rank)"""
+        import torch.distributed as dist
+
+        lib = _lib.lib()
+        own_ptrs, own_tensors, handles = [], [], []
+        for _ in range(count):
+            d = ctypes.c_void_p()
+            _lib.check(lib.cqb_dev_alloc(nelem * 32, ctypes.byref(d)))
+            h = ctypes.create_string_buffer(64)
+            _lib.check(lib.cqb_ipc_export(d, h))
+            own_ptrs.append(d.value)
+            handles.append(h.raw)
+            own_tensors.append(self.torch.as_tensor(self._RawBuffer(d.value, nelem * 32), device=self.device))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, handles, group=group)
+        tables, opened = [], []
+        for c in range(count):
+            ptrs = []
+            for r in range(world):
+                if r == rank:
+                    ptrs.append(own_ptrs[c])
+                else:
+                    p = ctypes.c_void_p()
+                    _lib.check(lib.cqb_ipc_open(gathered[r][c], ctypes.byref(p)))
+                    ptrs.append(p.value)
+                    opened.append(p.value)
+            tables.append(ptrs)
+        self._ipc_state = getattr(self, "_ipc_state", []) + [(own_ptrs, opened)]
+        return own_tensors, tables
+
+    def release_peer_buffers(self):
+        lib = _lib.lib()
+        for own_ptrs, opened in getattr(self, "_ipc_state", []):
+            for p in opened:
+                _lib.check(lib.cqb_ipc_close(ctypes.c_void_p(p)))
+            for p in own_ptrs:
+                _lib.check(lib.cqb_dev_free(ctypes.c_void_p(p)))
+        self._ipc_state = []
+
+    def ntt_batch_p2p(self, src, peer_ptrs, rank, omega_limbs, log_n, batch, in_seg_log, tw_omega_limbs=None, tw_log_n=0, tw_row0=0):
+        """the batched transform whose last pass stores into the peers' receive buffers (the exchange is the store)"""
+        assert batch <= 65535
+        scratch = self.empty(32)  # the library keeps its own scratch for the intermediate passes; d_scratch only has to differ from src
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[ctypes.c_void_p(p) for p in peer_ptrs])
+        _lib.check(_lib.lib().cqb_ntt_bn254_fr_batch_p2p_dev(
+            ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(scratch.data_ptr()), arr, len(peer_ptrs), rank, _lib.p64(omega_limbs), log_n, batch,
+            in_seg_log, _lib.p64(tw_omega_limbs) if tw_omega_limbs is not None else None, tw_log_n, tw_row0))
+
     def mul_omega_powers(self, t, rows, cols, row0, omega_limbs, log_n):
         _lib.check(_lib.lib().cqb_fr_mul_omega_powers_dev(ctypes.c_void_p(t.data_ptr()), rows, cols, row0, _lib.p64(omega_limbs), log_n))
 
@@ -242,8 +299,39 @@ class ShardedNTT:
         r3 = self._all_to_all(c)                                                     # [src][k2_local][k1_local(src)]
         return be.interleave(r3, G, ql, pl) if G > 1 else r3                         # [k2_local][k1]: natural order
 
+    def enable_peer_exchange(self):
+        """switch to the peer-memory exchange: two receive buffers per rank, opened by every peer through CUDA IPC. After this,
+        the second and third exchange are the last store of the batched transforms (cqb_ntt_bn254_fr_batch_p2p_dev) and only a
+        stream-ordered one-element all-reduce separates the steps."""
+        assert self.world > 1 and hasattr(self.backend, "peer_buffers")
+        per = (1 << self.log_n) // self.world
+        self._recv, self._peer_tables = self.backend.peer_buffers(per, 2, self.rank, self.world, self.group)
+        self._flag = self.backend.torch.zeros(1, dtype=self.backend.torch.int32, device=self.backend.device)
+        self._p2p = True
+
+    def _rank_sync(self):
+        import torch.distributed as dist
+
+        dist.all_reduce(self._flag, group=self.group)  # stream-ordered: completes when every rank's preceding kernel has finished
+
+    def _run_p2p(self, x_local, omega):
+        n1, n2, G = 1 << self.l1, 1 << self.l2, self.world
+        pl, ql = n1 // G, n2 // G
+        lim, be = self._limbs, self.backend
+        t = be.transpose(x_local, pl, n2)
+        r1 = self._all_to_all(t)
+        self._rank_sync()                       # nobody is still reading the receive buffers of the previous call
+        be.ntt_batch_p2p(r1, self._peer_tables[0], self.rank, lim(pow(omega, n2, self._mod)), self.l1, ql, pl.bit_length() - 1,
+                         lim(omega), self.log_n, self.rank * ql)
+        self._rank_sync()                       # every rank's stores into my buffer 0 have landed
+        be.ntt_batch_p2p(self._recv[0], self._peer_tables[1], self.rank, lim(pow(omega, n1, self._mod)), self.l2, pl, ql.bit_length() - 1)
+        self._rank_sync()
+        return be.interleave(self._recv[1], G, ql, pl)
+
     def _run(self, x_local, omega):
         n1, n2, G = 1 << self.l1, 1 << self.l2, self.world
+        if getattr(self, "_p2p", False) and max(n1, n2) // G <= 65535:
+            return self._run_p2p(x_local, omega)
         if hasattr(self.backend, "ntt_batch_map") and max(n1, n2) // G <= 65535:
             return self._run_fused(x_local, omega)
         lim = self._limbs

@@ -35,11 +35,14 @@ def synth(start, count):
     return t
 
 
+modes = ["nccl"] + (["peer"] if world > 1 else [])
 # ---- correctness: every rank's block equals the single-GPU transform of the whole vector -------------------------------
-for log_n in (10, 16, 20):
+for log_n, mode in [(l, m) for l in (10, 16, 20) for m in modes]:
     n = 1 << log_n
     per = n // world
     sn = ShardedNTT(be, log_n, rank, world)
+    if mode == "peer":
+        sn.enable_peer_exchange()
     got = sn.forward(synth(rank * per, per))
     full = synth(0, n)
     L.check(lib.cqb_ntt_bn254_fr_dev(ctypes.c_void_p(full.data_ptr()), L.p64(fr_to_limbs(sn.omega)), log_n))
@@ -49,15 +52,20 @@ for log_n in (10, 16, 20):
     torch.cuda.synchronize()
     assert torch.equal(back, synth(rank * per, per)), f"rank {rank}: inverse mismatch at 2^{log_n}"
     del full, got, back
+    if mode == "peer":
+        dist.barrier()
+        be.release_peer_buffers()
 if rank == 0:
     print(json.dumps({"check": "blocks of the distributed transform == single-GPU transform, inverse round trip", "sizes": [10, 16, 20],
                       "n_gpus": world, "ok": True}), flush=True)
 
 # ---- timing ---------------------------------------------------------------------------------------------------------------
-for log_n in [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["24", "26"])]:
+for log_n, mode in [(int(x), m) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["24", "26"]) for m in modes]:
     n = 1 << log_n
     per = n // world
     sn = ShardedNTT(be, log_n, rank, world)
+    if mode == "peer":
+        sn.enable_peer_exchange()
     x = synth(rank * per, per)
     for _ in range(3):
         y = sn.forward(x)
@@ -76,8 +84,12 @@ for log_n in [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else 
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(json.dumps({"log_n": log_n, "n_gpus": world, "distributed_forward_ms": round(float(ms.item()), 3),
-                          "gelem_per_s": round(n / float(ms.item()) / 1e6, 3), "layout": "block-distributed natural order in and out"}), flush=True)
+                          "gelem_per_s": round(n / float(ms.item()) / 1e6, 3), "exchange": mode,
+                          "layout": "block-distributed natural order in and out"}), flush=True)
     del x, y
+    if mode == "peer":
+        dist.barrier()
+        be.release_peer_buffers()
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
