@@ -56,5 +56,44 @@ g1, l1, op0 = O.table_srs_setup(16, s)
 vals = O.synth_scalars(32, 16)
 qs = O.cq_table_qs(vals, g1, 2)
 out["cq"].append({"N": 16, "toxic_seed": 31, "value_seed": 32, "opening_at_0_last": hx(op0[-1]), "qs_first": hx(qs[0]), "qs_last": hx(qs[-1])})
+# grand products (permutation/prover.rs:82-166, lookup/prover.rs:173-262), cross-checked against Python integers
+DELTA = 0x09226b6e22c6f0ca64ec26aad4c86e715b5f898e5e963f25870e56bbe533e9a2
+out["products"] = []
+k, ncols = 5, 3
+n = 1 << k
+cols = [O.synth_scalars(41 + j, n) for j in range(ncols)]
+perms = [O.synth_scalars(51 + j, n) for j in range(ncols)]
+beta, gamma, last_z = (P.fr_array_to_ints(O.synth_scalars(61 + j, 1))[0] for j in range(3))
+one = lambda x: P.fr_array_from_ints([x])[0]  # noqa: E731
+w = P.omega_for(k)
+z, dw = O.permutation_product(cols, perms, one(beta), one(gamma), one(w), one(1), one(last_z))
+ci, pi = [P.fr_array_to_ints(c) for c in cols], [P.fr_array_to_ints(p_) for p_ in perms]
+mv = [1] * n
+for j in range(ncols):
+    for i in range(n):
+        mv[i] = mv[i] * (beta * pi[j][i] + gamma + ci[j][i]) % P.R_MOD
+mv = [pow(v, -1, P.R_MOD) for v in mv]
+d = 1
+for j in range(ncols):
+    cur = d
+    for i in range(n):
+        mv[i] = mv[i] * (cur * beta + gamma + ci[j][i]) % P.R_MOD
+        cur = cur * w % P.R_MOD
+    d = d * DELTA % P.R_MOD
+zz = [last_z]
+for i in range(1, n):
+    zz.append(zz[-1] * mv[i - 1] % P.R_MOD)
+assert P.fr_array_to_ints(z) == zz and P.fr_array_to_ints(dw[None, :])[0] == d
+out["products"].append({"kind": "permutation", "k": k, "ncols": ncols, "col_seed": 41, "perm_seed": 51, "challenge_seed": 61, "z_last": hx(z[-1]),
+                        "z_xor": hx(np.bitwise_xor.reduce(z, axis=0)), "deltaomega_out": hx(dw)})
+a, sv, ap, sp = (O.synth_scalars(71 + j, n) for j in range(4))
+lz = O.lookup_product(a, sv, ap, sp, one(beta), one(gamma))
+ai, si, api, spi = (P.fr_array_to_ints(x) for x in (a, sv, ap, sp))
+acc, lzz = 1, [1]
+for i in range(n - 1):
+    acc = acc * pow((beta + api[i]) * (gamma + spi[i]) % P.R_MOD, -1, P.R_MOD) * (ai[i] + beta) % P.R_MOD * (si[i] + gamma) % P.R_MOD
+    lzz.append(acc)
+assert P.fr_array_to_ints(lz) == lzz
+out["products"].append({"kind": "lookup", "k": k, "seed": 71, "challenge_seed": 61, "z_last": hx(lz[-1]), "z_xor": hx(np.bitwise_xor.reduce(lz, axis=0))})
 json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "vectors.json"), "w"), indent=1)
 print("wrote vectors.json")

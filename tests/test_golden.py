@@ -42,6 +42,70 @@ def test_oracle_reproduces_golden(oracle):
     assert hx(g[-1]) == G["kzg"][0]["g_last"] and hx(gl[-1]) == G["kzg"][0]["g_lagrange_last"]
 
 
+def _product_inputs(O, row):
+    n = 1 << row["k"]
+    beta, gamma, last_z = (O.synth_scalars(row["challenge_seed"] + j, 1)[0] for j in range(3))
+    if row["kind"] == "permutation":
+        cols = [O.synth_scalars(row["col_seed"] + j, n) for j in range(row["ncols"])]
+        perms = [O.synth_scalars(row["perm_seed"] + j, n) for j in range(row["ncols"])]
+        return cols, perms, beta, gamma, last_z
+    return [O.synth_scalars(row["seed"] + j, n) for j in range(4)], None, beta, gamma, last_z
+
+
+def test_oracle_reproduces_golden_products(oracle):
+    O = oracle
+    one = P.fr_array_from_ints([1])[0]
+    for row in G["products"]:
+        vecs, perms, beta, gamma, last_z = _product_inputs(O, row)
+        if row["kind"] == "permutation":
+            z, dw = O.permutation_product(vecs, perms, beta, gamma, P.int_to_limbs(P.to_mont(P.omega_for(row["k"]), P.R_MOD)), one, last_z)
+            assert hx(dw) == row["deltaomega_out"]
+        else:
+            z = O.lookup_product(*vecs, beta, gamma)
+        assert hx(z[-1]) == row["z_last"] and hx(np.bitwise_xor.reduce(z, axis=0)) == row["z_xor"]
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_golden_products(oracle):
+    import ctypes
+
+    import cqb200
+
+    cqb200._lib.init(0)
+    L, lib = cqb200._lib, cqb200._lib.lib()
+    O = oracle
+
+    def dev(arr):
+        d = ctypes.c_void_p()
+        L.check(lib.cqb_dev_alloc(max(arr.nbytes, 64), ctypes.byref(d)))
+        L.check(lib.cqb_memcpy_h2d(d, np.ascontiguousarray(arr).ctypes.data_as(ctypes.c_void_p), arr.nbytes))
+        return d
+
+    for row in G["products"]:
+        n = 1 << row["k"]
+        vecs, perms, beta, gamma, last_z = _product_inputs(O, row)
+        d_z = dev(np.zeros((n, 4), np.uint64))
+        if row["kind"] == "permutation":
+            dc, dp = [dev(c) for c in vecs], [dev(p_) for p_ in perms]
+            dw = P.fr_array_from_ints([1])[0].copy()
+            arr_c = (ctypes.c_void_p * len(dc))(*dc)
+            arr_p = (ctypes.c_void_p * len(dp))(*dp)
+            L.check(lib.cqb_permutation_product_dev(arr_c, arr_p, len(dc), row["k"], L.p64(beta), L.p64(gamma),
+                                                    L.p64(P.int_to_limbs(P.to_mont(P.omega_for(row["k"]), P.R_MOD))),
+                                                    L.p64(P.int_to_limbs(P.to_mont(cqb200.permutation.FR_DELTA, P.R_MOD))), L.p64(dw), L.p64(last_z), d_z))
+            assert hx(dw) == row["deltaomega_out"]
+            bufs = dc + dp
+        else:
+            bufs = [dev(v) for v in vecs]
+            L.check(lib.cqb_lookup_product_dev(bufs[0], bufs[1], bufs[2], bufs[3], row["k"], L.p64(beta), L.p64(gamma), d_z))
+        z = np.zeros((n, 4), np.uint64)
+        L.check(lib.cqb_memcpy_d2h(z.ctypes.data_as(ctypes.c_void_p), d_z, n * 32))
+        L.check(lib.cqb_sync())
+        assert hx(z[-1]) == row["z_last"] and hx(np.bitwise_xor.reduce(z, axis=0)) == row["z_xor"]
+        for b in bufs + [d_z]:
+            L.check(lib.cqb_dev_free(b))
+
+
 @pytest.mark.gpu
 def test_cuda_reproduces_golden(oracle):
     import cqb200
