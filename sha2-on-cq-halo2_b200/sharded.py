@@ -1,4 +1,5 @@
-"""Point-range-sharded MSM across the GPUs of one box.
+"""Multi-GPU forms of the two hot operations on one box: the point-range-sharded MSM (below) and the
+distributed four-step NTT (ShardedNTT, second half of this file).
 
 The reference splits a large multiexp into contiguous point ranges across rayon threads and folds the partial results
 with Jacobian additions (halo2_proofs/src/arithmetic.rs:137-153). The multi-GPU form is the same decomposition with one
