@@ -75,7 +75,7 @@ def test_prefix_product_matches_serial_loop(cq, oracle, n):
     d_out.free()
 
 
-@pytest.mark.parametrize("k,ncols,cs_degree,blinding_factors", [(3, 2, 3, 2), (6, 5, 4, 5), (10, 7, 5, 5), (13, 3, 9, 6)])
+@pytest.mark.parametrize("k,ncols,cs_degree,blinding_factors", [(0, 1, 3, 0), (1, 2, 4, 0), (3, 2, 3, 2), (6, 5, 4, 5), (10, 7, 5, 5), (13, 3, 9, 6)])
 def test_permutation_commit_matches_reference_loop(cq, oracle, k, ncols, cs_degree, blinding_factors):
     """permutation::Argument::commit over all column sets: z vectors (with the caller's blinding rows), last_z / deltaomega
     threading between sets, and the commitment of every z (params.commit_lagrange, :166)"""
