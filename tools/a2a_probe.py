@@ -17,7 +17,8 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 L = cqb200._lib
 lib = L.init(local)
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream(device=local)  # a real (non-NULL) stream shared by torch's events / NCCL and the library
+torch.cuda.set_stream(stream)
 L.check(lib.cqb_set_stream(ctypes.c_void_p(stream.cuda_stream)))
 from sha2_on_cq_halo2_b200.fields import FR_ROOT_OF_UNITY, FR_S, R_MOD, fr_to_limbs
 
@@ -33,10 +34,10 @@ for log_n in [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else 
             fn()
         dist.barrier(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(stream)
         for _ in range(reps):
             fn()
-        e1.record()
+        e1.record(stream)
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
