@@ -299,7 +299,10 @@ int cqb_msm_bn254_g1(cqb_bases_t b, size_t offset, const uint64_t* scalars, size
     CQB_TRY(g_scalars.ensure(n * 32 + 32));
     // Large MSM from PINNED host memory: cut into parts; the H2D copy of part p+1 (copy stream) overlaps the kernels of
     // part p (compute stream). Pageable memory cannot overlap (the copy is staged synchronously), so it takes the plain path.
-    const int PARTS = 4;
+#ifndef CQB_HOST_PARTS
+#define CQB_HOST_PARTS 3
+#endif
+    const int PARTS = CQB_HOST_PARTS;
     bool pinned = false;
     if (n >= ((size_t)1 << 21)) {
         cudaPointerAttributes attr;

@@ -1032,10 +1032,14 @@ void msm_part_bounds(size_t n, int nparts, bool small_first, size_t* bounds) {
     if (nparts < 1) nparts = 1;
     if (nparts > MSM_MAX_PARTS) nparts = MSM_MAX_PARTS;
     bounds[0] = 0;
-    if (small_first && nparts >= 2 && n >= ((size_t)1 << 20)) {
-        size_t first = n / 16, rest = n - first, per = (rest + (nparts - 1) - 1) / (nparts - 1);
+    if (small_first && nparts >= 3 && n >= ((size_t)1 << 20)) {
+        // geometric start: 1/16, then 1/4, then the rest evenly — each part's copy finishes while the previous part computes
+        size_t first = n / 16, second = n / 4, rest = n - first - second, per = (rest + (nparts - 2) - 1) / (nparts - 2);
         bounds[1] = first;
-        for (int p = 2; p <= nparts; p++) bounds[p] = std::min(n, first + (size_t)(p - 1) * per);
+        bounds[2] = first + second;
+        for (int p = 3; p <= nparts; p++) bounds[p] = std::min(n, first + second + (size_t)(p - 2) * per);
+    } else if (small_first && nparts == 2 && n >= ((size_t)1 << 20)) {
+        bounds[1] = n / 16;
     } else {
         size_t per = (n + nparts - 1) / nparts;
         for (int p = 1; p <= nparts; p++) bounds[p] = std::min(n, (size_t)p * per);

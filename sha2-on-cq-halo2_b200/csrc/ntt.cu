@@ -23,6 +23,9 @@
 
 namespace cqb {
 
+#ifndef NTT_MIN_CTAS
+#define NTT_MIN_CTAS 3
+#endif
 constexpr int NTT_TILE_LOG = 10;   // elements per CTA tile (log2)
 constexpr int NTT_MAX_R = 8;       // max butterfly stages per pass
 constexpr int NTT_PRE_MAX = NTT_PRE_MAX_PUB;
@@ -107,7 +110,7 @@ __device__ __forceinline__ void butterfly_1(Fr& x, Fr& y) {
 // One pass = up to 8 butterfly stages on a tile of T = 2^(r+q) elements in shared memory. T/4 threads; each thread
 // carries FOUR elements through TWO stages in registers (a radix-4 step = 2 + 2 butterflies), so a pass needs r/2
 // shared-memory round trips and barriers instead of r, and every thread has two independent multiplications in flight.
-__global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const __grid_constant__ NttPassArgs a) {
+__global__ void __launch_bounds__(256, NTT_MIN_CTAS) ntt_pass_kernel(const __grid_constant__ NttPassArgs a) {
     extern __shared__ uint4 sm[];
     const uint32_t T = 1u << (a.r + a.q);
     uint4* slo = sm;
