@@ -1019,8 +1019,9 @@ static int auto_parts(size_t n, const MsmShape& s, const uint32_t* d_idx) {
     if (g_forced_parts > 0) return std::min(g_forced_parts, MSM_MAX_PARTS);
     // Measured (B200, 2^20..2^24, tools/sweep_msm.py with CQB_PARTS=1/2/4/8): overlapping the sort with the accumulation does
     // not pay for device-resident scalars — the co-resident sort CTAs take register-file space from the accumulate warps and
-    // slow them by about the time the sort would have taken alone (2^24: 39.5 / 39.3 / 41.1 / 42.1 ms). Parts are used only
-    // where there is a copy to hide (host-pointer MSM from pinned memory).
+    // slow them by about the time the sort would have taken alone (2^24: 39.5 / 39.3 / 41.1 / 42.1 ms; re-measured with the
+    // geometric part sizes and the bucket-array fold: 38.0 / 38.6 / 38.7 / 40.1 ms). Parts are used only where there is a copy
+    // to hide (host-pointer MSM from pinned memory).
     (void)n;
     return 1;
 }
