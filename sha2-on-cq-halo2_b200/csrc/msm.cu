@@ -930,9 +930,12 @@ static int msm_sort_phase(const void* d_scalars, const uint32_t* d_idx, size_t n
 }
 
 static int msm_acc_phase(const void* d_bases, size_t n, const MsmShape& s, const PartPlan& pl, const PartBuf& b, cudaStream_t st) {
-    // chunking of the bucket-sorted lists: aim for >= ~150k chunk threads, 16..256 entries each
+    // chunking of the bucket-sorted lists: 16..256 entries per chunk thread. One wave is 148 SMs x 4 CTAs x 128 threads = 76k
+    // chunks; with fewer than ~10 waves the last, partly filled wave shows (2^22: 213k chunks of 256 = 2.8 waves -> 10.9 ms, 852k
+    // chunks of 64 -> 10.3 ms), so the chunks shrink to 64 entries until there are ~1M of them, and further only to keep >= 150k.
     size_t entries = (size_t)n * s.nwin;
     int seg_log = 8;
+    while (seg_log > 6 && (entries >> seg_log) < 1000000) seg_log--;
     while (seg_log > 4 && (entries >> seg_log) < 150000) seg_log--;
     size_t list_len = s.single ? entries : n;  // entries one set's list can hold for this part
     uint32_t cpw = (uint32_t)((list_len + ((size_t)1 << seg_log) - 1) >> seg_log);  // chunks per set (upper bound)
