@@ -133,6 +133,58 @@ pub fn commit_sparse(handle: cqb_bases_t, idx: &[u32], scalars: &[Fr]) -> G1 {
     g1_from_affine_limbs(out, inf)
 }
 
+/// A device-resident vector of `Fr` (cqb_dev_alloc / cqb_memcpy_h2d): the prover keeps its polynomials here between the calls
+/// below instead of in `Polynomial<F, B>`'s `Vec`.
+#[derive(Copy, Clone)]
+pub struct DevFr(pub *mut c_void);
+
+/// One iteration of the column-set loop of `permutation::Argument::commit` (plonk/permutation/prover.rs:82-166): the caller
+/// passes the set's columns and `pkey.permutations` (device-resident Lagrange values), gets z in `z`, then writes its random
+/// blinding rows into `z[n - blinding_factors..]` (:152-155), reads `last_z = z[n - blinding_factors - 1]` (:157) and commits
+/// with `commit_with_handle(g_lagrange_handle, ..)` / `cqb_msm_bn254_g1_dev` (:166). `deltaomega` is updated as at :144.
+pub fn permutation_product_set(columns: &[DevFr], permutations: &[DevFr], k: u32, beta: Fr, gamma: Fr, omega: Fr, deltaomega: &mut Fr, last_z: Fr, z: DevFr) {
+    assert_eq!(columns.len(), permutations.len());
+    let cols: Vec<*const c_void> = columns.iter().map(|c| c.0 as *const c_void).collect();
+    let perms: Vec<*const c_void> = permutations.iter().map(|c| c.0 as *const c_void).collect();
+    let delta = Fr::DELTA;
+    let rc = unsafe {
+        cqb_permutation_product_dev(cols.as_ptr(), perms.as_ptr(), cols.len() as u32, k, &beta as *const Fr as *const u64, &gamma as *const Fr as *const u64,
+                                    &omega as *const Fr as *const u64, &delta as *const Fr as *const u64, deltaomega as *mut Fr as *mut u64,
+                                    &last_z as *const Fr as *const u64, z.0)
+    };
+    check(rc, "permutation product");
+}
+
+/// The device part of `Committed::commit_log_derivatives` (plonk/static_lookup/prover.rs:187-342) up to the sparse
+/// commitments: a_i = multiplicity_i / (theta-compressed table value_i + beta) over the support of m, then
+/// (a_cm, per-table Q_A parts, a0_cm). `table_values` are the tables' resident value vectors, `qs` their resident cached
+/// quotient commitments (StaticTableValues.qs registered with cqb_bases_register_device). The caller combines the Q_A parts
+/// with the powers of theta (sum_k theta^(K-1-k) * part_k — the reference's per-index compress_tables, :220-240, by linearity).
+pub fn cq_log_derivative_commitments(g1_lagrange: cqb_bases_t, opening_at_0: cqb_bases_t, qs: &[cqb_bases_t], table_values: &[DevFr], support: &[u32],
+                                     multiplicities: &[Fr], beta: Fr, theta: Fr, scratch: DevFr /* 3 * |support| Fr + |support| u32 */) -> (G1, Vec<G1>, G1) {
+    let m = support.len();
+    assert_eq!(m, multiplicities.len());
+    unsafe {
+        let d_a = scratch.0;
+        let d_tv = (scratch.0 as *mut u8).add(m * 32) as *mut c_void;
+        let d_mult = (scratch.0 as *mut u8).add(2 * m * 32) as *mut c_void;
+        let d_idx = (scratch.0 as *mut u8).add(3 * m * 32) as *mut u32;
+        check(cqb_memcpy_h2d(d_idx as *mut c_void, support.as_ptr() as *const c_void, m * 4), "h2d idx");
+        check(cqb_memcpy_h2d(d_mult, multiplicities.as_ptr() as *const c_void, m * 32), "h2d multiplicities");
+        let tv: Vec<*const c_void> = table_values.iter().map(|t| t.0 as *const c_void).collect();
+        check(cqb_fr_compress_dev(tv.as_ptr(), tv.len() as u32, d_idx, m, &theta as *const Fr as *const u64, d_tv), "compress_tables");
+        check(cqb_fr_inv_shifted_dev(d_tv, m, m, &beta as *const Fr as *const u64, d_a), "1/(t + beta)");
+        check(cqb_fr_mul_dev(d_a, d_mult, m, d_a), "a_i");
+        let sparse = |h: cqb_bases_t| {
+            let mut out = [0u64; 8];
+            let mut inf: c_int = 0;
+            check(cqb_msm_bn254_g1_sparse_dev(h, d_idx, d_a, m, out.as_mut_ptr(), &mut inf), "sparse commit");
+            g1_from_affine_limbs(out, inf)
+        };
+        (sparse(g1_lagrange), qs.iter().map(|&h| sparse(h)).collect(), sparse(opening_at_0))
+    }
+}
+
 mod generic {
     //! The reference's generic bodies of best_multiexp / best_fft (arithmetic.rs:13-159, 171-274) are moved here unchanged
     //! when the shim is applied inside halo2_proofs; they serve the non-accelerated instantiations only.
