@@ -109,7 +109,8 @@ CQB_API int cqb_ntt_bn254_fr_batch_dev(void* d_a, const uint64_t omega[4], uint3
  * as [idx][b] (already in destination-rank order for the next all-to-all); tw_omega != NULL: result idx of member b is also
  * multiplied by tw_omega^((tw_row0 + b) * idx), tw_omega a 2^tw_log_n-th root of unity. */
 CQB_API int cqb_ntt_bn254_fr_batch_map_dev(const void* d_src, void* d_dst, const uint64_t omega[4], uint32_t log_n, uint32_t batch,
-                                           int in_seg_log, int out_transposed, const uint64_t tw_omega[4], uint32_t tw_log_n, size_t tw_row0);
+                                           int in_seg_log, int out_transposed, const uint64_t tw_omega[4], uint32_t tw_log_n, size_t tw_row0,
+                                           uint32_t in_batch_total /* 0 = batch; else members per segment of the source buffer */);
 /* ... and with the exchange itself fused in: the last pass stores result idx of member b into the receive buffer of the rank
  * that owns it, peer_dst[idx >> (log_n - log2 n_peers)], at [self_rank][idx & mask][b] — peer memory over NVLink (pointers
  * from cqb_ipc_open; peer_dst[self_rank] is the caller's own buffer). d_scratch (batch * 2^log_n elements, local) holds the

@@ -41,7 +41,7 @@ SYMBOLS = [
     ("cqb_ntt_bn254_fr", _int, [u64p, u64p, _u32]),
     ("cqb_ntt_bn254_fr_dev", _int, [_vp, u64p, _u32]),
     ("cqb_ntt_bn254_fr_batch_dev", _int, [_vp, u64p, _u32, _u32]),
-    ("cqb_ntt_bn254_fr_batch_map_dev", _int, [_vp, _vp, u64p, _u32, _u32, _int, _int, u64p, _u32, _sz]),
+    ("cqb_ntt_bn254_fr_batch_map_dev", _int, [_vp, _vp, u64p, _u32, _u32, _int, _int, u64p, _u32, _sz, _u32]),
     ("cqb_ntt_bn254_fr_batch_p2p_dev", _int, [_vp, _vp, _vp, _u32, _u32, u64p, _u32, _u32, _int, u64p, _u32, _sz]),
     ("cqb_ipc_export", _int, [_vp, ctypes.c_char_p]),
     ("cqb_ipc_open", _int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),

@@ -439,7 +439,7 @@ int cqb_ntt_bn254_fr_batch_dev(void* d_a, const uint64_t omega[4], uint32_t log_
     return ntt_run(d_a, d_a, log_n, omega, f, batch);
 }
 int cqb_ntt_bn254_fr_batch_map_dev(const void* d_src, void* d_dst, const uint64_t omega[4], uint32_t log_n, uint32_t batch, int in_seg_log,
-                                   int out_transposed, const uint64_t tw_omega[4], uint32_t tw_log_n, size_t tw_row0) {
+                                   int out_transposed, const uint64_t tw_omega[4], uint32_t tw_log_n, size_t tw_row0, uint32_t in_batch_total) {
     LOCK;
     CQB_TRY(require_init());
     if (((!d_src || !d_dst) && batch) || !omega || d_src == d_dst) return fail(CQB_E_BAD_ARG, "cqb_ntt_bn254_fr_batch_map_dev: NULL or aliasing argument");
@@ -449,7 +449,9 @@ int cqb_ntt_bn254_fr_batch_map_dev(const void* d_src, void* d_dst, const uint64_
     if (in_seg_log >= 0) {
         f.in_map = 1;
         f.in_s = (unsigned)in_seg_log;
-        f.in_A = (unsigned long long)batch << in_seg_log;
+        // in_batch_total > batch: this call transforms a GROUP of the members held by the receive buffer (d_src then points at
+        // the group's first member inside the first segment)
+        f.in_A = (unsigned long long)(in_batch_total ? in_batch_total : batch) << in_seg_log;
         f.in_B = 1ull << in_seg_log;
     }
     if (out_transposed) {

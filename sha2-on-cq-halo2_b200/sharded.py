@@ -164,14 +164,15 @@ class CudaNttBackend:
             _lib.check(_lib.lib().cqb_ntt_bn254_fr_batch_dev(ctypes.c_void_p(t.data_ptr() + (done << log_n) * 32), _lib.p64(omega_limbs), log_n, b))
             done += b
 
-    def ntt_batch_map(self, src, omega_limbs, log_n, batch, in_seg_log, tw_omega_limbs=None, tw_log_n=0, tw_row0=0):
+    def ntt_batch_map(self, src, omega_limbs, log_n, batch, in_seg_log, tw_omega_limbs=None, tw_log_n=0, tw_row0=0, src_offset_elems=0,
+                      in_batch_total=0):
         """batched transform out of `src` (an all-to-all receive buffer [source rank][member][segment]) into a new buffer laid
         out [idx][member] — the gather, the twiddle step and the transposition are fused into the kernel's first and last pass"""
         assert batch <= 65535
         out = self.empty(batch << log_n)
         _lib.check(_lib.lib().cqb_ntt_bn254_fr_batch_map_dev(
-            ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(out.data_ptr()), _lib.p64(omega_limbs), log_n, batch, in_seg_log, 1,
-            _lib.p64(tw_omega_limbs) if tw_omega_limbs is not None else None, tw_log_n, tw_row0))
+            ctypes.c_void_p(src.data_ptr() + src_offset_elems * 32), ctypes.c_void_p(out.data_ptr()), _lib.p64(omega_limbs), log_n, batch, in_seg_log, 1,
+            _lib.p64(tw_omega_limbs) if tw_omega_limbs is not None else None, tw_log_n, tw_row0, in_batch_total))
         return out
 
     # ---- peer-memory exchange (CUDA IPC): receive buffers every rank exposes to the others ---------------------------------
@@ -329,8 +330,61 @@ class ShardedNTT:
         self._rank_sync()
         return be.interleave(self._recv[1], G, ql, pl)
 
+    def enable_overlap(self, groups=2):
+        """split the batched transforms into `groups` member groups: the all-to-all of a finished group (NCCL on a second
+        stream, list form, chunks placed [source rank][group]) runs under the transform of the next group"""
+        assert self.world > 1 and hasattr(self.backend, "ntt_batch_map")
+        torch = self.backend.torch
+        self._groups = groups
+        self._comm_stream = torch.cuda.Stream(device=self.backend.device)
+
+    def _run_overlap(self, x_local, omega):
+        import torch.distributed as dist
+
+        torch = self.backend.torch
+        n1, n2, G, S = 1 << self.l1, 1 << self.l2, self.world, self._groups
+        pl, ql = n1 // G, n2 // G
+        lim, be = self._limbs, self.backend
+        main = torch.cuda.current_stream()
+        comm = self._comm_stream
+        t = be.transpose(x_local, pl, n2)
+        r1 = self._all_to_all(t)                                   # [src][j2_local][j1_local]
+
+        def stage(src, length_log, members, seg, tw):
+            """transform `members` members in S groups out of src = [G * S' segments][members][seg]; returns the receive buffer
+            laid out [src rank][group][rows of this rank][members / S]"""
+            gm = members // S
+            rows = (1 << length_log) // G
+            recv = be.empty(rows * members * G)
+            rv = recv.view(G, S, rows * gm * 32)
+            outs, evs = [], []
+            for s in range(S):
+                o = be.ntt_batch_map(src, lim(pow(omega, (1 << self.log_n) >> length_log, self._mod)), length_log, gm, seg.bit_length() - 1,
+                                     lim(omega) if tw else None, self.log_n if tw else 0, self.rank * members + s * gm if tw else 0,
+                                     src_offset_elems=s * gm * seg, in_batch_total=members)
+                outs.append(o)                                   # [idx][gm]: chunk h = rows idx of rank h
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(comm):
+                    comm.wait_event(ev)
+                    dist.all_to_all([rv[g][s] for g in range(G)], list(o.view(G, rows * gm * 32).unbind(0)), group=self.group)
+                    done = torch.cuda.Event()
+                    done.record(comm)
+                evs.append(done)
+            for e in evs:
+                main.wait_event(e)
+            return recv, outs
+
+        r2, keep_a = stage(r1, self.l1, ql, pl, True)             # A + B; r2 = [src][s][k1_local][ql / S]
+        r3, keep_c = stage(r2, self.l2, pl, ql // S, False)       # C;     r3 = [src][s][k2_local][pl / S]
+        out = r3.view(G, S, ql, (pl // S) * 32).permute(2, 0, 1, 3).contiguous().view(-1)   # [k2_local][k1]
+        del keep_a, keep_c
+        return out
+
     def _run(self, x_local, omega):
         n1, n2, G = 1 << self.l1, 1 << self.l2, self.world
+        if getattr(self, "_groups", 0) > 1 and min(n1, n2) // G >= self._groups and max(n1, n2) // G <= 65535:
+            return self._run_overlap(x_local, omega)
         if getattr(self, "_p2p", False) and max(n1, n2) // G <= 65535:
             return self._run_p2p(x_local, omega)
         if hasattr(self.backend, "ntt_batch_map") and max(n1, n2) // G <= 65535:

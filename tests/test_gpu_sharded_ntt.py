@@ -111,6 +111,6 @@ def test_mapped_batched_ntt(env, oracle, log_n, batch, seg_log):
     d_src = _to_dev(torch, src)
     d_dst = torch.empty_like(d_src)
     L.check(lib.cqb_ntt_bn254_fr_batch_map_dev(ctypes.c_void_p(d_src.data_ptr()), ctypes.c_void_p(d_dst.data_ptr()), L.p64(w), log_n, batch, seg_log, 1,
-                                               L.p64(wb), big_log, row0))
+                                               L.p64(wb), big_log, row0, 0))
     L.check(lib.cqb_sync())
     assert np.array_equal(_to_host(d_dst).reshape(n, batch, 4), exp_t)

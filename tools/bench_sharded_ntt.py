@@ -35,7 +35,9 @@ def synth(start, count):
     return t
 
 
-modes = ["nccl"] + (["peer"] if world > 1 else [])
+modes = ["nccl"] + (["overlap", "peer"] if world > 1 else [])
+if len(sys.argv) > 2:
+    modes = [m for m in modes if m in sys.argv[2].split(",")]
 # ---- correctness: every rank's block equals the single-GPU transform of the whole vector -------------------------------
 for log_n, mode in [(l, m) for l in (10, 16, 20) for m in modes]:
     n = 1 << log_n
@@ -43,6 +45,8 @@ for log_n, mode in [(l, m) for l in (10, 16, 20) for m in modes]:
     sn = ShardedNTT(be, log_n, rank, world)
     if mode == "peer":
         sn.enable_peer_exchange()
+    if mode == "overlap":
+        sn.enable_overlap(int(os.environ.get("NTT_GROUPS", "2")))
     got = sn.forward(synth(rank * per, per))
     full = synth(0, n)
     L.check(lib.cqb_ntt_bn254_fr_dev(ctypes.c_void_p(full.data_ptr()), L.p64(fr_to_limbs(sn.omega)), log_n))
@@ -66,6 +70,8 @@ for log_n, mode in [(int(x), m) for x in (sys.argv[1].split(",") if len(sys.argv
     sn = ShardedNTT(be, log_n, rank, world)
     if mode == "peer":
         sn.enable_peer_exchange()
+    if mode == "overlap":
+        sn.enable_overlap(int(os.environ.get("NTT_GROUPS", "2")))
     x = synth(rank * per, per)
     for _ in range(3):
         y = sn.forward(x)
