@@ -115,7 +115,7 @@ def test_shard_range_balanced():
                 assert s0 + c0 == s1
 
 
-def _ntt_worker(rank, world, port, log_n, q):
+def _ntt_worker(rank, world, port, log_n, q, fused=False):
     """ShardedNTT host logic (three distributed transposes, batched local transforms, twiddles) with an oracle-backed
     stand-in device: the result block of every rank must equal the oracle's best_fft of the whole vector"""
     sys.path.insert(0, ROOT)
@@ -163,10 +163,30 @@ def _ntt_worker(rank, world, port, log_n, q):
         def interleave(self, recv, world, q_local, p_local):
             return recv.view(world, q_local, p_local * 32).permute(1, 0, 2).contiguous().view(-1)
 
+    class FusedOracleNttBackend(OracleNttBackend):
+        """adds the mapped batched transform (cqb_ntt_bn254_fr_batch_map_dev's address maps, restated with numpy indexing), so
+        that ShardedNTT takes the SAME fused path it takes on the GPUs: gather from the all-to-all buffer, twiddles, transposed
+        store"""
+
+        def ntt_batch_map(self, src, omega_limbs, log_n, batch, in_seg_log, tw_omega_limbs=None, tw_log_n=0, tw_row0=0, src_offset_elems=0,
+                          in_batch_total=0):
+            n, seg, total = 1 << log_n, 1 << in_seg_log, (in_batch_total or batch)
+            a = self._np(src)
+            idx = np.arange(n)
+            out = np.zeros((n, batch, 4), np.uint64)
+            for b in range(batch):
+                off = src_offset_elems + (idx >> in_seg_log) * (total * seg) + b * seg + (idx & (seg - 1))
+                res = O.best_fft(np.ascontiguousarray(a[off]), omega_limbs, log_n, 1)
+                if tw_omega_limbs is not None:
+                    w = P.fr_array_to_ints(np.asarray(tw_omega_limbs)[None, :])[0]
+                    res = P.fr_array_from_ints([v * pow(w, (tw_row0 + b) * i, P.R_MOD) % P.R_MOD for i, v in enumerate(P.fr_array_to_ints(res))])
+                out[:, b] = res
+            return torch.from_numpy(out.view(np.uint8).reshape(-1))
+
     n = 1 << log_n
     per = n // world
     full = O.synth_scalars(0x5EED0002, n)
-    sn = ShardedNTT(OracleNttBackend(), log_n, rank, world)
+    sn = ShardedNTT(FusedOracleNttBackend() if fused else OracleNttBackend(), log_n, rank, world)
     mine = torch.from_numpy(np.ascontiguousarray(full[rank * per:(rank + 1) * per]).view(np.uint8).reshape(-1).copy())
     got = sn.forward(mine).numpy().view(np.uint64).reshape(-1, 4)
     exp = O.best_fft(full.copy(), P.int_to_limbs(P.to_mont(sn.omega, P.R_MOD)), log_n, 1)
@@ -178,14 +198,14 @@ def _ntt_worker(rank, world, port, log_n, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,log_n", [(2, 5), (2, 8), (4, 7), (1, 6)])
-def test_sharded_ntt_host_logic_gloo(world, log_n):
+@pytest.mark.parametrize("world,log_n,fused", [(2, 5, False), (2, 8, False), (4, 7, False), (1, 6, False), (2, 7, True), (4, 8, True), (1, 5, True)])
+def test_sharded_ntt_host_logic_gloo(world, log_n, fused):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_ntt_worker, args=(r, world, port, log_n, q)) for r in range(world)]
+    procs = [ctx.Process(target=_ntt_worker, args=(r, world, port, log_n, q, fused)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in range(world)]
