@@ -87,6 +87,7 @@ SYMBOLS = [
     ("cqb_host_free_pinned", _int, [_vp]),
     ("cqb_msm_set_window_bits", _int, [_int]),
     ("cqb_msm_set_parts", _int, [_int]),
+    ("cqb_msm_set_accumulator", _int, [_int, _int]),
     ("cqb_msm_set_profiling", _int, [_int]),
     ("cqb_msm_phase_ms", _int, [ctypes.POINTER(ctypes.c_float), _int]),
 ]

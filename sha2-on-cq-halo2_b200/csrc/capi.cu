@@ -922,6 +922,13 @@ int cqb_msm_set_window_bits(int c) {
     return 0;
 }
 
+int cqb_msm_set_accumulator(int mode, int affine_seg_log) {
+    LOCK;
+    if (mode < 0 || mode > 2 || affine_seg_log < 0 || affine_seg_log > 10) return fail(CQB_E_BAD_ARG, "cqb_msm_set_accumulator: mode 0..2, segment log 0..10");
+    msm_set_accumulator(mode);
+    msm_set_affine_segment(affine_seg_log);
+    return 0;
+}
 int cqb_msm_set_parts(int parts) {
     LOCK;
     if (parts < 0 || parts > 8) return fail(CQB_E_BAD_ARG, "parts must be 0 (auto) or 1..8");

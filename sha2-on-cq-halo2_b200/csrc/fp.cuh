@@ -693,6 +693,134 @@ CQB_HD Fp<P> fp_inv_binary(const Fp<P>& a) {
     return fp_mul<P>(r, Fp<P>::r3());
 }
 
+// Branch-free inversion for the places where EVERY lane of a warp inverts its own element at the same time (the batched-affine
+// bucket accumulation: one inversion per thread per batch of additions). Fermat costs ~380 dependent modmuls on the
+// multiplier pipe the additions themselves are bound by; the loops of fp_inv_binary diverge across lanes. This is the
+// Bernstein-Yang "safegcd" iteration in its half-delta form over signed 30-bit limbs: 20 rounds of 30 division steps decided
+// on the low limbs only (plain ALU work, uniform control flow), each round applied to f, g and to the Bezout coefficients
+// d, e (mod p) as one 2x2 matrix (4 + 6 signed wide multiply-adds per limb). 600 steps suffice for any input below 2^256.
+// Input/output in Montgomery form like fp_inv_binary: for x = aR it returns a^-1 R; 0 for 0. Same value as fp_inv.
+template <class P>
+struct SafeGcd {
+    static constexpr uint32_t M30 = 0x3fffffffu;
+    // limb j (30 bits) of the modulus
+    static CQB_HD constexpr int32_t mod30(int j) {
+        return (int32_t)((((uint64_t)P::mod((30 * j) / 32) | ((30 * j) / 32 + 1 < 8 ? (uint64_t)P::mod((30 * j) / 32 + 1) << 32 : 0ull)) >> ((30 * j) % 32)) & M30);
+    }
+    static CQB_HD constexpr uint32_t minv30() { return (0u - P::inv()) & M30; }  // p^-1 mod 2^30 (P::inv() is -p^-1 mod 2^32)
+};
+
+template <class P>
+CQB_HD Fp<P> fp_inv_safegcd(const Fp<P>& a) {
+    typedef SafeGcd<P> S;
+    const int32_t M30 = (int32_t)S::M30;
+    int32_t f[9], g[9], d[9], e[9];
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+        f[j] = S::mod30(j);
+        const int lo = (30 * j) / 32, sh = (30 * j) % 32;
+        uint64_t w = a.l[lo];
+        if (lo + 1 < 8) w |= (uint64_t)a.l[lo + 1] << 32;
+        g[j] = (int32_t)((uint32_t)(w >> sh) & S::M30);
+        d[j] = 0;
+        e[j] = 0;
+    }
+    e[0] = 1;
+    int32_t zeta = -1;  // -(delta + 1/2), delta = 1/2
+#pragma unroll 1
+    for (int round = 0; round < 20; round++) {
+        // 30 division steps on the low limbs: the matrix [u v; q r] with [f'; g'] = 2^-30 [u v; q r] [f; g]
+        uint32_t u = 1, v = 0, q = 0, r = 1, fl = (uint32_t)f[0], gl = (uint32_t)g[0];
+#pragma unroll 6
+        for (int i = 0; i < 30; i++) {
+            uint32_t m1 = (uint32_t)(zeta >> 31);  // zeta < 0
+            const uint32_t m2 = 0u - (gl & 1u);    // g odd
+            const uint32_t x = (fl ^ m1) - m1, y = (u ^ m1) - m1, z = (v ^ m1) - m1;
+            gl += x & m2;
+            q += y & m2;
+            r += z & m2;
+            m1 &= m2;
+            zeta = (int32_t)((uint32_t)zeta ^ m1) - 1;
+            fl += gl & m1;
+            u += q & m1;
+            v += r & m1;
+            gl >>= 1;
+            u <<= 1;
+            v <<= 1;
+        }
+        const int32_t su = (int32_t)u, sv = (int32_t)v, sq = (int32_t)q, sr = (int32_t)r;
+        {   // [d; e] <- 2^-30 [u v; q r] [d; e] mod p, kept in (-2p, p)
+            const int32_t sd = d[8] >> 31, se = e[8] >> 31;
+            int32_t md = (su & sd) + (sv & se), me = (sq & sd) + (sr & se);
+            int64_t cd = (int64_t)su * d[0] + (int64_t)sv * e[0];
+            int64_t ce = (int64_t)sq * d[0] + (int64_t)sr * e[0];
+            md -= (int32_t)((S::minv30() * (uint32_t)cd + (uint32_t)md) & S::M30);
+            me -= (int32_t)((S::minv30() * (uint32_t)ce + (uint32_t)me) & S::M30);
+            cd += (int64_t)S::mod30(0) * md;
+            ce += (int64_t)S::mod30(0) * me;
+            cd >>= 30;
+            ce >>= 30;
+#pragma unroll
+            for (int i = 1; i < 9; i++) {
+                const int32_t di = d[i], ei = e[i];
+                cd += (int64_t)su * di + (int64_t)sv * ei;
+                ce += (int64_t)sq * di + (int64_t)sr * ei;
+                cd += (int64_t)S::mod30(i) * md;
+                ce += (int64_t)S::mod30(i) * me;
+                d[i - 1] = (int32_t)cd & M30;
+                cd >>= 30;
+                e[i - 1] = (int32_t)ce & M30;
+                ce >>= 30;
+            }
+            d[8] = (int32_t)cd;
+            e[8] = (int32_t)ce;
+        }
+        {   // [f; g] <- 2^-30 [u v; q r] [f; g] (exact: the low 30 bits vanish by construction)
+            int64_t cf = (int64_t)su * f[0] + (int64_t)sv * g[0];
+            int64_t cg = (int64_t)sq * f[0] + (int64_t)sr * g[0];
+            cf >>= 30;
+            cg >>= 30;
+#pragma unroll
+            for (int i = 1; i < 9; i++) {
+                const int32_t fi = f[i], gi = g[i];
+                cf += (int64_t)su * fi + (int64_t)sv * gi;
+                cg += (int64_t)sq * fi + (int64_t)sr * gi;
+                f[i - 1] = (int32_t)cf & M30;
+                cf >>= 30;
+                g[i - 1] = (int32_t)cg & M30;
+                cg >>= 30;
+            }
+            f[8] = (int32_t)cf;
+            g[8] = (int32_t)cg;
+        }
+    }
+    // now g = 0 and f = +-1 (for a != 0): the inverse is sign(f) * d, brought from (-2p, p) into [0, p)
+    {
+        int32_t add = d[8] >> 31;
+#pragma unroll
+        for (int j = 0; j < 9; j++) d[j] += S::mod30(j) & add;
+        const int32_t neg = f[8] >> 31;
+#pragma unroll
+        for (int j = 0; j < 9; j++) d[j] = (d[j] ^ neg) - neg;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { d[j + 1] += d[j] >> 30; d[j] &= M30; }
+        add = d[8] >> 31;
+#pragma unroll
+        for (int j = 0; j < 9; j++) d[j] += S::mod30(j) & add;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { d[j + 1] += d[j] >> 30; d[j] &= M30; }
+    }
+    Fp<P> r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {  // 9 x 30-bit limbs -> 8 x 32-bit limbs
+        const int lo = (32 * i) / 30, sh = (32 * i) % 30;
+        uint64_t w = (uint64_t)(uint32_t)d[lo] | ((uint64_t)(uint32_t)d[lo + 1] << 30);
+        if (lo + 2 < 9) w |= (uint64_t)(uint32_t)d[lo + 2] << 60;
+        r.l[i] = (uint32_t)(w >> sh);
+    }
+    return fp_mul<P>(r, Fp<P>::r3());
+}
+
 typedef Fp<FrP> Fr;
 typedef Fp<FqP> Fq;
 

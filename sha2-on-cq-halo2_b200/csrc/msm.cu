@@ -466,6 +466,191 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint4* __rest
     else st_xyzz(tail + gid * 8, acc);
 }
 
+// (4') BATCHED-AFFINE bucket accumulation (the CPU form is the reference's batch_add, arithmetic/curves/src/derive/curve.rs:4-141).
+// An affine addition needs one field inversion; shared by a batch through Montgomery's trick it costs 5M + 1S = 788 MAD32
+// instead of the XYZZ mixed addition's 1,232 — the accumulation is multiplier-bound, so that is the lever. The shape that fits
+// the B200: every thread runs AFF_K independent STREAMS, each a sub-chunk of 2^seg_log consecutive entries of the bucket-sorted
+// list with its own affine accumulator in shared memory (64 B per stream, thread-private: no barriers). One step adds the next
+// entry of every stream: forward pass (denominators x2 - x1 and their running product, the partial products parked in an
+// L2-resident scratch), ONE inversion per thread per step — the branch-free safegcd of fp.cuh, ALU work that overlaps the other
+// warps' multiplier work — and a backward pass that peels the inverses off and finishes the additions. No data leaves the
+// thread, HBM traffic stays the 64 B gather per entry (the backward pass re-reads the points from L2).
+// Exceptional cases as the reference (derive/curve.rs:866-871 / batch_add's own branches): identity base, empty accumulator,
+// P + P (the doubling's denominator 2y joins the batch), P + (-P). The first entry of every bucket carries AFF_FIRST (set by
+// msm_mark_first_kernel), so a stream sees bucket boundaries without tracking offsets. Outputs are AFFINE (identity = zeros):
+// complete buckets, and per-sub-chunk head / tail partials that msm_merge_affine_kernel adds up into the XYZZ bucket array.
+constexpr int AFF_K = 14;             // streams per thread: 14 x 64 B x 128 threads = 112 KB of shared memory, two CTAs per SM
+constexpr int AFF_THREADS = 128;
+constexpr uint32_t AFF_FIRST = 0x80000000u;
+
+__global__ void __launch_bounds__(256) msm_mark_first_kernel(const uint32_t* __restrict__ offs, MsmShape s, uint32_t* __restrict__ sorted) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)s.nsets * s.nb) return;
+    const uint32_t w = (uint32_t)(gid / s.nb), d = (uint32_t)(gid % s.nb) + 1;
+    const uint32_t* o = offs + (size_t)w * s.stride;
+    const uint32_t a = o[d];
+    if (o[d + 1] > a) sorted[(size_t)w * s.list_cap + a] |= AFF_FIRST;  // one writer per word
+}
+
+struct AffSmem {
+    uint4* base;  // [stream][quarter][thread]
+    __device__ __forceinline__ uint4* at(int k, int c) const { return base + ((k * 4 + c) * AFF_THREADS + threadIdx.x); }
+    __device__ __forceinline__ Fq x(int k) const { return fq_of(*at(k, 0), *at(k, 1)); }
+    __device__ __forceinline__ Fq y(int k) const { return fq_of(*at(k, 2), *at(k, 3)); }
+    __device__ __forceinline__ void set(int k, const Fq& X, const Fq& Y) const {
+        *at(k, 0) = make_uint4(X.l[0], X.l[1], X.l[2], X.l[3]);
+        *at(k, 1) = make_uint4(X.l[4], X.l[5], X.l[6], X.l[7]);
+        *at(k, 2) = make_uint4(Y.l[0], Y.l[1], Y.l[2], Y.l[3]);
+        *at(k, 3) = make_uint4(Y.l[4], Y.l[5], Y.l[6], Y.l[7]);
+    }
+    static __device__ __forceinline__ Fq fq_of(const uint4& a, const uint4& b) {
+        Fq r;
+        r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w; r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+        return r;
+    }
+};
+
+// what the forward pass decided for a stream's entry (2 bits per stream in a register)
+enum : uint32_t { AFF_SKIP = 0, AFF_LOAD = 1, AFF_ADD = 2, AFF_DBL = 3 };
+
+// one non-inlined copy of the field multiplication for the two passes (the inlined passes would be ~20 KB of code each)
+__device__ __noinline__ Fq aff_mul(Fq a, Fq b) { return fp_mul<FqP>(a, b); }
+__device__ __noinline__ Fq aff_inv(Fq a) { return fp_inv_safegcd<FqP>(a); }
+
+__global__ void __launch_bounds__(AFF_THREADS, 2) msm_accumulate_affine_kernel(const uint4* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                                               const uint32_t* __restrict__ offs, const uint32_t* __restrict__ nxt,
+                                                                               MsmShape s, int seg_log, uint32_t cpw, uint32_t tpw,
+                                                                               uint4* __restrict__ baff, uint4* __restrict__ head,
+                                                                               uint4* __restrict__ tail, uint4* __restrict__ prefix,
+                                                                               uint32_t* __restrict__ cur) {
+    extern __shared__ uint4 aff_smem[];
+    const AffSmem acc{aff_smem};
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nthreads = (size_t)s.nsets * tpw;
+    if (gid >= nthreads) return;
+    const uint32_t w = (uint32_t)(gid / tpw), tj = (uint32_t)(gid % tpw);
+    const uint32_t* o = offs + (size_t)w * s.stride;
+    const uint32_t* nx = nxt + (size_t)w * s.stride;
+    const uint32_t* lst = sorted + (size_t)w * s.list_cap;
+    const uint32_t total = o[s.nb + 1];
+    const uint32_t seg = 1u << seg_log;
+    const uint32_t j0 = tj * AFF_K;                     // first sub-chunk of this thread inside set w
+    if (((size_t)j0 << seg_log) >= total) return;
+    // streams that hold entries: sub-chunk j0 + k starts below `total`
+    int nact = 0;
+#pragma unroll 1
+    for (int k = 0; k < AFF_K; k++) {
+        acc.set(k, Fq::zero(), Fq::zero());
+        if ((((size_t)j0 + k) << seg_log) < total) nact = k + 1;
+    }
+    // current bucket of every stream: the largest d with o[d] <= start (K binary searches side by side)
+    {
+        uint32_t lo[AFF_K], hi[AFF_K];
+#pragma unroll
+        for (int k = 0; k < AFF_K; k++) { lo[k] = 1; hi[k] = s.nb; }
+        for (uint32_t span = s.nb; span > 1; span = (span + 1) >> 1) {
+#pragma unroll
+            for (int k = 0; k < AFF_K; k++) {
+                if (k < nact && lo[k] < hi[k]) {
+                    const uint32_t mid = (lo[k] + hi[k] + 1) >> 1;
+                    if (o[mid] <= ((j0 + k) << seg_log)) lo[k] = mid; else hi[k] = mid - 1;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < AFF_K; k++)
+            if (k < nact) cur[(size_t)k * nthreads + gid] = lo[k];
+    }
+    uint32_t first_mask = (1u << AFF_K) - 1u;  // stream has not crossed a bucket boundary yet: its accumulator is the head partial
+    uint32_t full_mask = 0;                     // stream's accumulator holds a point
+    uint4* const pre = prefix + gid * 2;        // stream k's parked product at pre[k * nthreads * 2]
+#pragma unroll 1
+    for (uint32_t step = 0; step < seg; step++) {
+        // ---- forward: denominators and their running product --------------------------------------------------------------
+        Fq run = Fq::one();
+        uint32_t kinds = 0;
+#pragma unroll 1
+        for (int k = 0; k < nact; k++) {
+            const uint32_t pos = ((j0 + k) << seg_log) + step;
+            if (pos >= total) continue;
+            const uint32_t e = __ldg(lst + pos);
+            if ((e & AFF_FIRST) && step != 0) {
+                // the stream's bucket ended with the previous entry
+                const size_t q = (size_t)w * cpw + j0 + k;
+                uint32_t* cu = cur + (size_t)k * nthreads + gid;
+                const uint32_t d = *cu;
+                uint4* dst = (first_mask >> k) & 1u ? head + q * 4 : baff + ((size_t)w * s.nb + (d - 1)) * 4;
+                dst[0] = *acc.at(k, 0); dst[1] = *acc.at(k, 1); dst[2] = *acc.at(k, 2); dst[3] = *acc.at(k, 3);
+                first_mask &= ~(1u << k);
+                full_mask &= ~(1u << k);
+                acc.set(k, Fq::zero(), Fq::zero());
+                *cu = nx[d + 1];  // next non-empty bucket: the one this entry opens
+            }
+            const uint4* bp = bases + (size_t)((e & ~AFF_FIRST) >> 1) * 4;
+            const Fq x2 = ldg_fq(bp);
+            Fq y2 = ldg_fq(bp + 2);
+            if (x2.is_zero() && y2.is_zero()) continue;  // identity base contributes nothing: reference curve.rs:857-858
+            if (!((full_mask >> k) & 1u)) {              // empty accumulator: the backward pass just loads the point
+                kinds |= AFF_LOAD << (2 * k);
+                continue;
+            }
+            uint32_t kind = AFF_ADD;
+            Fq den = fp_sub<FqP>(x2, acc.x(k));
+            if (den.is_zero()) {
+                // same x: the same point (double: the denominator is 2y) or opposite points (the sum is the identity)
+                if (e & 1u) y2 = fp_neg<FqP>(y2);
+                const Fq y1 = acc.y(k);
+                den = fp_dbl<FqP>(y1);
+                if (y2 == y1 && !den.is_zero()) kind = AFF_DBL;
+                else {
+                    full_mask &= ~(1u << k);
+                    acc.set(k, Fq::zero(), Fq::zero());
+                    continue;
+                }
+            }
+            kinds |= kind << (2 * k);
+            st_fq(pre + (size_t)k * nthreads * 2, run);
+            run = aff_mul(run, den);
+        }
+        if (kinds == 0) continue;
+        // ---- one inversion for the whole step --------------------------------------------------------------------------------
+        Fq inv = (kinds & 0xaaaaaaaau) ? aff_inv(run) : run;  // no ADD / DBL in this step: nothing to invert
+        // ---- backward: peel the inverses off, finish the additions -------------------------------------------------------------
+#pragma unroll 1
+        for (int k = nact - 1; k >= 0; k--) {
+            const uint32_t kind = (kinds >> (2 * k)) & 3u;
+            if (kind == AFF_SKIP) continue;
+            const uint32_t pos = ((j0 + k) << seg_log) + step;
+            const uint32_t e = __ldg(lst + pos);
+            const uint4* bp = bases + (size_t)((e & ~AFF_FIRST) >> 1) * 4;
+            Fq x2 = ldg_fq(bp), y2 = ldg_fq(bp + 2);
+            if (e & 1u) y2 = fp_neg<FqP>(y2);
+            if (kind == AFF_LOAD) {
+                acc.set(k, x2, y2);
+                full_mask |= 1u << k;
+                continue;
+            }
+            const Fq x1 = acc.x(k), y1 = acc.y(k);
+            const Fq den = kind == AFF_ADD ? fp_sub<FqP>(x2, x1) : fp_dbl<FqP>(y1);
+            const Fq dinv = aff_mul(inv, ld_fq(pre + (size_t)k * nthreads * 2));
+            inv = aff_mul(inv, den);
+            Fq num;
+            if (kind == AFF_ADD) num = fp_sub<FqP>(y2, y1);
+            else { const Fq xx = fp_sqr<FqP>(x1); num = fp_add<FqP>(fp_dbl<FqP>(xx), xx); }  // 3 x^2 (a = 0)
+            const Fq lam = aff_mul(num, dinv);
+            const Fq x3 = fp_sub<FqP>(fp_sub<FqP>(fp_sqr<FqP>(lam), x1), x2);  // x2 == x1 in the doubling
+            const Fq y3 = fp_sub<FqP>(aff_mul(lam, fp_sub<FqP>(x1, x3)), y1);
+            acc.set(k, x3, y3);
+        }
+    }
+#pragma unroll 1
+    for (int k = 0; k < nact; k++) {
+        const size_t q = (size_t)w * cpw + j0 + k;
+        uint4* dst = ((first_mask >> k) & 1u ? head : tail) + q * 4;
+        dst[0] = *acc.at(k, 0); dst[1] = *acc.at(k, 1); dst[2] = *acc.at(k, 2); dst[3] = *acc.at(k, 3);
+    }
+}
+
 // buckets[0][i] += buckets[p][i], p = 1..nparts-1: the bucket arrays of a pipelined MSM's parts are folded by one thread
 // per bucket (a throughput kernel) before the latency-sized reduction, which then reads a single array
 __global__ void __launch_bounds__(128) msm_fold_parts_kernel(uint4* __restrict__ buckets, size_t nbuckets, int nparts) {
@@ -564,6 +749,69 @@ __global__ void __launch_bounds__(128) msm_merge_big_kernel(const uint32_t* __re
         tail_add(acc, p);
     }
     G1Xyzz r = block_sum_128(acc, sm);
+    if (threadIdx.x == 0) st_xyzz(buckets + ((size_t)w * s.nb + (d - 1)) * 8, r);
+}
+
+// (4b') the same two kernels for the batched-affine accumulation: partials and complete buckets are affine points (zeros =
+// identity); the XYZZ bucket array the reduction reads is produced here.
+__device__ __forceinline__ void tail_madd_affine(G1Xyzz& acc, const uint4* p) {
+    const Fq x = ld_fq(p), y = ld_fq(p + 2);
+    if (x.is_zero() && y.is_zero()) return;
+    g1_madd<TailMul>(acc, x, y);
+}
+__global__ void __launch_bounds__(128) msm_merge_affine_kernel(const uint32_t* __restrict__ offs, MsmShape s, int seg_log, uint32_t cpw,
+                                                               uint4* __restrict__ buckets, const uint4* __restrict__ baff,
+                                                               const uint4* __restrict__ head, const uint4* __restrict__ tail,
+                                                               uint32_t* __restrict__ big_count, uint2* __restrict__ big_list, uint32_t big_cap) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)s.nsets * s.nb) return;
+    uint32_t w = (uint32_t)(gid / s.nb), d = (uint32_t)(gid % s.nb) + 1;
+    const uint32_t* o = offs + (size_t)w * s.stride;
+    const uint32_t total = o[s.nb + 1];
+    const uint32_t start = o[d], end = o[d + 1];
+    if (start == end) return;  // empty bucket: stays identity (the XYZZ array is zero-initialised)
+    const uint32_t kf = start >> seg_log, kl = (end - 1) >> seg_log;
+    const uint32_t seg = 1u << seg_log;
+    G1Xyzz acc = G1Xyzz::identity();
+    if (kf == kl) {
+        uint32_t cs = kf << seg_log, ce = min(cs + seg, total);
+        bool isfirst = start <= cs, islast = end >= ce;
+        const uint4* src = (!isfirst && !islast) ? baff + gid * 4 : (isfirst ? head : tail) + ((size_t)w * cpw + kf) * 4;
+        const Fq x = ld_fq(src), y = ld_fq(src + 2);
+        if (!(x.is_zero() && y.is_zero())) { acc.x = x; acc.y = y; acc.zz = Fq::one(); acc.zzz = Fq::one(); }
+        st_xyzz(buckets + gid * 8, acc);
+        return;
+    }
+    if (kl - kf > MERGE_LONG) {
+        uint32_t slot = atomicAdd(big_count, 1u);
+        if (slot < big_cap) big_list[slot] = make_uint2(w, d);
+        return;
+    }
+    for (uint32_t k = kf; k <= kl; k++) {
+        bool isfirst = start <= (k << seg_log);
+        tail_madd_affine(acc, (isfirst ? head : tail) + ((size_t)w * cpw + k) * 4);
+    }
+    st_xyzz(buckets + gid * 8, acc);
+}
+constexpr int MERGE_BIG_AFF_THREADS = 512;
+__global__ void __launch_bounds__(MERGE_BIG_AFF_THREADS) msm_merge_big_affine_kernel(const uint32_t* __restrict__ offs, MsmShape s, int seg_log,
+                                                                                     uint32_t cpw, uint4* __restrict__ buckets,
+                                                                                     const uint4* __restrict__ head, const uint4* __restrict__ tail,
+                                                                                     const uint32_t* __restrict__ big_count,
+                                                                                     const uint2* __restrict__ big_list) {
+    extern __shared__ uint4 big_sm[];
+    if (blockIdx.x >= *big_count) return;
+    const uint2 wd = big_list[blockIdx.x];
+    const uint32_t w = wd.x, d = wd.y;
+    const uint32_t* o = offs + (size_t)w * s.stride;
+    const uint32_t start = o[d], end = o[d + 1];
+    const uint32_t kf = start >> seg_log, kl = (end - 1) >> seg_log;
+    G1Xyzz acc = G1Xyzz::identity();
+    for (uint32_t k = kf + threadIdx.x; k <= kl; k += MERGE_BIG_AFF_THREADS) {
+        bool isfirst = start <= (k << seg_log);
+        tail_madd_affine(acc, (isfirst ? head : tail) + ((size_t)w * cpw + k) * 4);
+    }
+    G1Xyzz r = block_sum<MERGE_BIG_AFF_THREADS>(acc, big_sm);
     if (threadIdx.x == 0) st_xyzz(buckets + ((size_t)w * s.nb + (d - 1)) * 8, r);
 }
 
@@ -710,7 +958,7 @@ __global__ void __launch_bounds__(128) msm_precompute_row_kernel(const uint4* __
 // -------------------------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------------------------
-static Scratch g_hist, g_sorted, g_buckets, g_partials, g_chunks, g_pre_tmp;
+static Scratch g_hist, g_sorted, g_buckets, g_partials, g_chunks, g_pre_tmp, g_aff;
 
 // Second stream (high priority) for the sort phases (count / scan / scatter) of part p+1 of a large MSM, which overlap the
 // bucket accumulation of part p on the main stream: the sort is atomics/latency bound, the accumulation multiplier bound.
@@ -772,6 +1020,7 @@ void msm_release_all() {
     g_partials.release();
     g_chunks.release();
     g_pre_tmp.release();
+    g_aff.release();
     for (auto& sp : g_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     g_spans.clear();
     g_spans_used = 0;
@@ -929,11 +1178,71 @@ static int msm_sort_phase(const void* d_scalars, const uint32_t* d_idx, size_t n
     return 0;
 }
 
+// bucket accumulation variant: 0 = automatic (batched affine for large MSMs), 1 = XYZZ mixed additions, 2 = batched affine
+static int g_acc_mode = 0;
+void msm_set_accumulator(int mode) { g_acc_mode = mode; }
+static int g_aff_seg_log = 0;  // experiments: entries per stream = 2^g_aff_seg_log (0 = automatic)
+void msm_set_affine_segment(int seg_log) { g_aff_seg_log = seg_log; }
+
+// batched-affine accumulation + merge (kernel comment above); the XYZZ bucket array comes out as msm_acc_phase leaves it
+static int msm_acc_phase_affine(const void* d_bases, size_t n, const MsmShape& s, const PartPlan& pl, const PartBuf& b, cudaStream_t st) {
+    static bool attr_set = false;
+    const size_t smem = (size_t)AFF_K * 64 * AFF_THREADS;
+    if (!attr_set) {
+        CQB_CUDA(cudaFuncSetAttribute(msm_accumulate_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CQB_CUDA(cudaFuncSetAttribute(msm_merge_big_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MERGE_BIG_AFF_THREADS * 128));
+        attr_set = true;
+    }
+    const size_t entries = (size_t)n * s.nwin;
+    // entries per stream: 32, shrinking while the grid would be shorter than ~4 waves of 2 CTAs x 148 SMs
+    int seg_log = 5;
+    const size_t wave = (size_t)2 * ctx().sm_count * AFF_THREADS * AFF_K;
+    while (seg_log > 3 && (entries >> seg_log) < 4 * wave) seg_log--;
+    if (g_aff_seg_log > 0) seg_log = g_aff_seg_log;
+    const size_t list_len = s.single ? entries : n;
+    const uint32_t cpw = (uint32_t)((list_len + ((size_t)1 << seg_log) - 1) >> seg_log);  // sub-chunks (streams) per set
+    const uint32_t tpw = (cpw + AFF_K - 1) / AFF_K;                                        // threads per set
+    const size_t nsub = (size_t)s.nsets * cpw, nthreads = (size_t)s.nsets * tpw;
+    const uint32_t big_cap = (uint32_t)(s.nsets * (cpw / MERGE_LONG + 2));
+    // head, tail: 64 B per sub-chunk; baff: 64 B per bucket; parked products: 32 B per stream; current bucket: 4 B per stream
+    const size_t head_b = nsub * 64, baff_b = pl.nbuckets * 64, pre_b = nthreads * AFF_K * 32, cur_b = nthreads * AFF_K * 4;
+    CQB_TRY(g_aff.ensure(2 * head_b + baff_b + pre_b + cur_b + 16 + (size_t)big_cap * 8));
+    uint4* head = g_aff.as<uint4>();
+    uint4* tail = head + nsub * 4;
+    uint4* baff = tail + nsub * 4;
+    uint4* prefix = baff + pl.nbuckets * 4;
+    uint32_t* cur = (uint32_t*)(prefix + nthreads * AFF_K * 2);
+    uint32_t* big_count = cur + nthreads * AFF_K;
+    uint2* big_list = (uint2*)(big_count + 4);
+    CQB_CUDA(cudaMemsetAsync(b.buckets, 0, pl.nbuckets * 128, st));
+    CQB_CUDA(cudaMemsetAsync(big_count, 0, 16, st));
+    int h = prof_begin(3, st);
+    msm_mark_first_kernel<<<(unsigned)((pl.nbuckets + 255) / 256), 256, 0, st>>>(b.offs, s, b.sorted);
+    CQB_LAUNCHED();
+    msm_accumulate_affine_kernel<<<(unsigned)((nthreads + AFF_THREADS - 1) / AFF_THREADS), AFF_THREADS, smem, st>>>(
+        (const uint4*)d_bases, b.sorted, b.offs, b.hist, s, seg_log, cpw, tpw, baff, head, tail, prefix, cur);
+    CQB_LAUNCHED();
+    prof_end(h, st);
+    h = prof_begin(4, st);
+    msm_merge_affine_kernel<<<(unsigned)((pl.nbuckets + 127) / 128), 128, 0, st>>>(b.offs, s, seg_log, cpw, b.buckets, baff, head, tail, big_count,
+                                                                                    big_list, big_cap);
+    CQB_LAUNCHED();
+    msm_merge_big_affine_kernel<<<big_cap, MERGE_BIG_AFF_THREADS, MERGE_BIG_AFF_THREADS * 128, st>>>(b.offs, s, seg_log, cpw, b.buckets, head, tail,
+                                                                                                      big_count, big_list);
+    CQB_LAUNCHED();
+    prof_end(h, st);
+    CQB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 static int msm_acc_phase(const void* d_bases, size_t n, const MsmShape& s, const PartPlan& pl, const PartBuf& b, cudaStream_t st) {
     // chunking of the bucket-sorted lists: 16..256 entries per chunk thread. One wave is 148 SMs x 4 CTAs x 128 threads = 76k
     // chunks; with fewer than ~10 waves the last, partly filled wave shows (2^22: 213k chunks of 256 = 2.8 waves -> 10.9 ms, 852k
     // chunks of 64 -> 10.3 ms), so the chunks shrink to 64 entries until there are ~1M of them, and further only to keep >= 150k.
     size_t entries = (size_t)n * s.nwin;
+    // batched affine: the sorted entries must leave bit 31 free for the first-of-bucket mark
+    const bool idx_fits = s.single ? ((size_t)s.nwin * s.table_n < ((size_t)1 << 30)) : true;
+    if (idx_fits && (g_acc_mode == 2 || (g_acc_mode == 0 && entries >= ((size_t)1 << 24)))) return msm_acc_phase_affine(d_bases, n, s, pl, b, st);
     int seg_log = 8;
     while (seg_log > 6 && (entries >> seg_log) < 1000000) seg_log--;
     while (seg_log > 4 && (entries >> seg_log) < 150000) seg_log--;

@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: about a minute of CPU oracle time (still part of -m gpu; deselect with -m 'gpu and not slow')")
 
 
 @pytest.fixture(scope="session")

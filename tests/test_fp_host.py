@@ -59,6 +59,11 @@ def test_fp_limb_algorithm(fp_bin):
         for a in vals[24:120]:
             lines.append(f"{name} invb {a:064x} {0:064x}")
             exp.append(pow(a * rinv % p, -1, p) * P.MONT % p)
+        # the branch-free safegcd inversion (batched-affine bucket accumulation): structured values and 2000 random ones
+        for a in vals + [rng.randrange(p) for _ in range(2000)] + [rng.randrange(1 << k) for k in (1, 2, 31, 33, 60, 61, 90, 120, 150, 250) for _ in range(20)]:
+            a %= p
+            lines.append(f"{name} invs {a:064x} {0:064x}")
+            exp.append(0 if a == 0 else pow(a * rinv % p, -1, p) * P.MONT % p)
     out = subprocess.run([fp_bin], input="\n".join(lines), capture_output=True, text=True, check=True).stdout.split()
     assert len(out) == len(exp)
     bad = [(l, o) for l, o, e in zip(lines, out, exp) if int(o, 16) != e]

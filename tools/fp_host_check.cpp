@@ -27,6 +27,7 @@ template <class P> static void run(const std::string& op, const std::string& sa,
     else if (op == "dbl") put(fp_dbl<P>(a));
     else if (op == "inv") put(fp_inv<P>(a));
     else if (op == "invb") put(fp_inv_binary<P>(a));
+    else if (op == "invs") put(fp_inv_safegcd<P>(a));
     else if (op == "frommont") put(fp_from_mont<P>(a));
     else if (op == "tomont") put(fp_to_mont<P>(a));
     else printf("?\n");

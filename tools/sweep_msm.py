@@ -17,6 +17,8 @@ torch.cuda.set_stream(stream)
 L.check(lib.cqb_set_stream(ctypes.c_void_p(stream.cuda_stream)))
 L.check(lib.cqb_msm_set_profiling(1))
 L.check(lib.cqb_msm_set_parts(int(os.environ.get("CQB_PARTS", "0"))))  # 0 = automatic
+_acc = [int(x) for x in os.environ.get("CQB_ACC", "0,0").split(",")]  # accumulation variant, affine segment log
+L.check(lib.cqb_msm_set_accumulator(_acc[0], _acc[1]))
 logs = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else "16,18,20,22,24".split(","))]
 cs = [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else "0".split(","))]
 nmax = 1 << max(logs)
@@ -77,6 +79,6 @@ for lg in logs:
         ms = e0.elapsed_time(e1) / reps
         lib.cqb_msm_phase_ms(ph, 8)
         print(json.dumps({"log_n": lg, "c": c, "ms": round(ms, 4), "mpts": round(n / ms / 1e3, 2),
-                          "phases": [round(ph[i], 4) for i in range(8)], "x0": hex(int(out[0])), "precompute_s": round(pre_s, 3) if pre else None}), flush=True)
+                          "phases": [round(ph[i], 4) for i in range(8)], "x0": hex(int(out[0])), "acc": _acc, "precompute_s": round(pre_s, 3) if pre else None}), flush=True)
     if pre:
         L.check(lib.cqb_bases_free(hh.value))

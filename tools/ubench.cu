@@ -72,6 +72,42 @@ __global__ void k_row_chain(Res* out, uint32_t s) {
     if (threadIdx.x == 0) out[blockIdx.x].cyc = t1 - t0;
     if (z == 0x12345) out[blockIdx.x].sink = z;
 }
+// the same chain with a run-time trip count: calibration runs of >= 20 ms, long enough for the SM clock to settle where a
+// real MSM runs (the sub-millisecond tests above read 1.2-1.9 GHz effective); cycles / event time = the clock sample
+__global__ void k_row_chain_long(Res* out, uint32_t s, int iters) {
+    uint32_t acc[2][9], x[8]; uint32_t y = s * 7u + 3u;
+    for (int k = 0; k < 9; k++) { acc[0][k] = threadIdx.x + k; acc[1][k] = threadIdx.x * 3 + k; }
+    for (int k = 0; k < 8; k++) x[k] = 0x9e3779b9u * (threadIdx.x + k + s);
+    unsigned long long t0 = clock64();
+#pragma unroll 4
+    for (int it = 0; it < iters; it++) {
+        row_mad(acc[0], x, y);
+        row_mad(acc[1], x + 1, y);
+        y += acc[0][0];
+    }
+    unsigned long long t1 = clock64();
+    uint32_t z = 0; for (int k = 0; k < 9; k++) z ^= acc[0][k] ^ acc[1][k];
+    if (threadIdx.x == 0) out[blockIdx.x].cyc = t1 - t0;
+    if (z == 0x12345) out[blockIdx.x].sink = z;
+}
+// four independent row accumulators per thread, multiplier word fixed: no dependency between rows at all
+__global__ void k_row_chain4_long(Res* out, uint32_t s, int iters) {
+    uint32_t acc[4][9], x[8]; uint32_t y = s * 7u + 3u;
+    for (int r = 0; r < 4; r++) for (int k = 0; k < 9; k++) acc[r][k] = threadIdx.x * (r + 1) + k;
+    for (int k = 0; k < 8; k++) x[k] = 0x9e3779b9u * (threadIdx.x + k + s);
+    unsigned long long t0 = clock64();
+#pragma unroll 2
+    for (int it = 0; it < iters; it++) {
+        row_mad(acc[0], x, y);
+        row_mad(acc[1], x + 1, y);
+        row_mad(acc[2], x, y);
+        row_mad(acc[3], x + 1, y);
+    }
+    unsigned long long t1 = clock64();
+    uint32_t z = 0; for (int r = 0; r < 4; r++) for (int k = 0; k < 9; k++) z ^= acc[r][k];
+    if (threadIdx.x == 0) out[blockIdx.x].cyc = t1 - t0;
+    if (z == 0x12345) out[blockIdx.x].sink = z;
+}
 __global__ void k_iadd3(Res* out, uint32_t s) {
     uint32_t a[CH], x = s | 1u;
     for (int k = 0; k < CH; k++) a[k] = threadIdx.x + k;
@@ -176,11 +212,34 @@ int main(int argc, char** argv) {
         run("dfma", [&](Res* d) { k_dfma<<<blocks, th>>>(d, s); }, per, blocks, th, nsm);
         run("dfma(8)+row_wideX(8)", [&](Res* d) { k_dfma_plus_row<<<blocks, th>>>(d, s); }, (double)ITERS * 8, blocks, th, nsm);
     }
+    // long calibration runs (>= 20 ms each): the roofline denominator bench.py uses comes from these lines
+    for (int bps : {2, 4}) {
+        int blocks = nsm * bps, th = 256;
+        for (int iters : {100000, 400000}) {
+            char nm[64];
+            snprintf(nm, 64, "row_chain_wideX_long_%dk", iters / 1000);
+            run(nm, [&](Res* d) { k_row_chain_long<<<blocks, th>>>(d, s, iters); }, (double)iters * 8, blocks, th, nsm);
+        }
+    }
+    for (int bps : {1, 2, 4}) {
+        int blocks = nsm * bps, th = 256, iters = 200000;
+        char nm[64];
+        snprintf(nm, 64, "row_chain4_wideX_long_%dk", iters / 1000);
+        run(nm, [&](Res* d) { k_row_chain4_long<<<blocks, th>>>(d, s, iters); }, (double)iters * 16, blocks, th, nsm);
+    }
     // modmul throughput
     std::vector<uint32_t> hin(8 * 32 * 16);
     for (size_t i = 0; i < hin.size(); i++) hin[i] = (uint32_t)(0x9e3779b9u * (i + 1)) >> ((i % 8 == 7) ? 3 : 0);
     Fq* din; CK(cudaMalloc(&din, hin.size() * 4)); CK(cudaMemcpy(din, hin.data(), hin.size() * 4, cudaMemcpyHostToDevice));
     Fq* dout; CK(cudaMalloc(&dout, sizeof(Fq) * nsm * 16 * 1024));
+    {   // long modmul runs: 256 threads x 4 CTAs/SM, two chains
+        int blocks = nsm * 4, th = 256;
+        for (int itl : {20000, 80000}) {
+            char nm[64];
+            snprintf(nm, 64, "fq_mul_chain2_long_%dk", itl / 1000);
+            run(nm, [&](Res* d) { k_fpmul<FqP, 2><<<blocks, th>>>(d, din, dout, itl); }, (double)itl * 2, blocks, th, nsm);
+        }
+    }
     const int it = 2000;
     for (int th : {128, 256, 512}) for (int bps : {1, 2, 4}) {
         if (th * bps > 1024) continue;
