@@ -59,6 +59,10 @@ CQB_API int cqb_bases_register(const uint64_t* affine_xy, size_t n, cqb_bases_t*
 CQB_API int cqb_bases_register_device(const void* d_affine_xy, size_t n, cqb_bases_t* out);  /* adopt device memory, no copy */
 CQB_API int cqb_bases_free(cqb_bases_t h);
 CQB_API size_t cqb_bases_len(cqb_bases_t h);
+/* points [offset, offset + n) of a registered set back to the host (ParamsKZG::write_custom, poly/kzg/commitment.rs:366-380)
+ * or into other device memory, stream-ordered (ParamsKZG::downsize, :482-490, truncates g before rebuilding g_lagrange) */
+CQB_API int cqb_bases_download(cqb_bases_t h, size_t offset, size_t n, uint64_t* affine_xy_out);
+CQB_API int cqb_bases_copy_dev(cqb_bases_t h, size_t offset, size_t n, void* d_affine_xy_out);
 /* Build the resident table 2^(c w) P_i for every window w (nwin x n x 64 B of HBM: 12 GiB for a 2^24 SRS at c = 22) so
  * that all windows of an MSM over this set share ONE bucket set: fewer, wider windows and a single bucket reduction.
  * One-time cost per SRS (like computing g_lagrange in setup, poly/kzg/commitment.rs:234-262). window_bits = 0 picks c

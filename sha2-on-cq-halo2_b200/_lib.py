@@ -28,6 +28,8 @@ SYMBOLS = [
     ("cqb_bases_register_device", _int, [_vp, _sz, u64p]),
     ("cqb_bases_free", _int, [_u64]),
     ("cqb_bases_len", _sz, [_u64]),
+    ("cqb_bases_download", _int, [_u64, _sz, _sz, u64p]),
+    ("cqb_bases_copy_dev", _int, [_u64, _sz, _sz, _vp]),
     ("cqb_bases_precompute", _int, [_u64, _int]),
     ("cqb_bases_drop_precomputed", _int, [_u64]),
     ("cqb_bases_precomputed_window_bits", _int, [_u64]),

@@ -217,6 +217,27 @@ int cqb_bases_free(cqb_bases_t h) {
     g_bases.erase(it);
     return 0;
 }
+int cqb_bases_download(cqb_bases_t h, size_t offset, size_t n, uint64_t* affine_xy_out) {
+    LOCK;
+    CQB_TRY(require_init());
+    auto it = g_bases.find(h);
+    if (it == g_bases.end()) return fail(CQB_E_BAD_ARG, "unknown bases handle %llu", (unsigned long long)h);
+    if (!affine_xy_out && n) return fail(CQB_E_BAD_ARG, "cqb_bases_download: NULL argument");
+    if (offset > it->second.n || n > it->second.n - offset) return fail(CQB_E_LEN_MISMATCH, "download of %zu points at offset %zu exceeds the %zu registered bases", n, offset, it->second.n);
+    if (n) CQB_CUDA(cudaMemcpyAsync(affine_xy_out, (const char*)it->second.d + offset * 64, n * 64, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return 0;
+}
+int cqb_bases_copy_dev(cqb_bases_t h, size_t offset, size_t n, void* d_affine_xy_out) {
+    LOCK;
+    CQB_TRY(require_init());
+    auto it = g_bases.find(h);
+    if (it == g_bases.end()) return fail(CQB_E_BAD_ARG, "unknown bases handle %llu", (unsigned long long)h);
+    if (!d_affine_xy_out && n) return fail(CQB_E_BAD_ARG, "cqb_bases_copy_dev: NULL argument");
+    if (offset > it->second.n || n > it->second.n - offset) return fail(CQB_E_LEN_MISMATCH, "copy of %zu points at offset %zu exceeds the %zu registered bases", n, offset, it->second.n);
+    if (n) CQB_CUDA(cudaMemcpyAsync(d_affine_xy_out, (const char*)it->second.d + offset * 64, n * 64, cudaMemcpyDeviceToDevice, g_ctx.stream));
+    return 0;
+}
 size_t cqb_bases_len(cqb_bases_t h) {
     LOCK;
     auto it = g_bases.find(h);
@@ -927,6 +948,7 @@ int cqb_msm_set_accumulator(int mode, int affine_seg_log) {
     if (mode < 0 || mode > 2 || affine_seg_log < 0 || affine_seg_log > 10) return fail(CQB_E_BAD_ARG, "cqb_msm_set_accumulator: mode 0..2, segment log 0..10");
     msm_set_accumulator(mode);
     msm_set_affine_segment(affine_seg_log);
+    if (const char* v = getenv("CQB_AFF_VARIANT")) msm_set_affine_variant(atoi(v));
     return 0;
 }
 int cqb_msm_set_parts(int parts) {

@@ -53,6 +53,7 @@ int msm_run_precomputed(const void* d_table, size_t table_n, int c, size_t offse
 void msm_set_parts(int p);
 void msm_set_accumulator(int mode);     // 0 auto | 1 XYZZ mixed additions | 2 batched affine
 void msm_set_affine_segment(int seg_log);
+void msm_set_affine_variant(int v);
 // bounds[0..nparts]: the point ranges the parts of an MSM cover (small_first: host-pointer MSMs, see msm.cu)
 void msm_part_bounds(size_t n, int nparts, bool small_first, size_t* bounds);
 int msm_precompute_window_bits(size_t n);

@@ -479,7 +479,6 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint4* __rest
 // P + P (the doubling's denominator 2y joins the batch), P + (-P). The first entry of every bucket carries AFF_FIRST (set by
 // msm_mark_first_kernel), so a stream sees bucket boundaries without tracking offsets. Outputs are AFFINE (identity = zeros):
 // complete buckets, and per-sub-chunk head / tail partials that msm_merge_affine_kernel adds up into the XYZZ bucket array.
-constexpr int AFF_K = 14;             // streams per thread: 14 x 64 B x 128 threads = 112 KB of shared memory, two CTAs per SM
 constexpr int AFF_THREADS = 128;
 constexpr uint32_t AFF_FIRST = 0x80000000u;
 
@@ -492,9 +491,15 @@ __global__ void __launch_bounds__(256) msm_mark_first_kernel(const uint32_t* __r
     if (o[d + 1] > a) sorted[(size_t)w * s.list_cap + a] |= AFF_FIRST;  // one writer per word
 }
 
-struct AffSmem {
-    uint4* base;  // [stream][quarter][thread]
-    __device__ __forceinline__ uint4* at(int k, int c) const { return base + ((k * 4 + c) * AFF_THREADS + threadIdx.x); }
+// accumulator storage of the streams: shared memory ([stream][quarter][thread], conflict-free 128-bit accesses) or an
+// L2-resident global scratch ([stream][quarter][global thread]: coalesced), which lifts the shared-memory limit on the
+// number of resident warps
+template <bool SMEM>
+struct AffAcc {
+    uint4* base;
+    size_t stride;  // threads per (stream, quarter) plane
+    size_t me;      // this thread's slot in a plane
+    __device__ __forceinline__ uint4* at(int k, int c) const { return base + ((size_t)(k * 4 + c) * stride + me); }
     __device__ __forceinline__ Fq x(int k) const { return fq_of(*at(k, 0), *at(k, 1)); }
     __device__ __forceinline__ Fq y(int k) const { return fq_of(*at(k, 2), *at(k, 3)); }
     __device__ __forceinline__ void set(int k, const Fq& X, const Fq& Y) const {
@@ -509,6 +514,7 @@ struct AffSmem {
         return r;
     }
 };
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // what the forward pass decided for a stream's entry (2 bits per stream in a register)
 enum : uint32_t { AFF_SKIP = 0, AFF_LOAD = 1, AFF_ADD = 2, AFF_DBL = 3 };
@@ -517,17 +523,18 @@ enum : uint32_t { AFF_SKIP = 0, AFF_LOAD = 1, AFF_ADD = 2, AFF_DBL = 3 };
 __device__ __noinline__ Fq aff_mul(Fq a, Fq b) { return fp_mul<FqP>(a, b); }
 __device__ __noinline__ Fq aff_inv(Fq a) { return fp_inv_safegcd<FqP>(a); }
 
-__global__ void __launch_bounds__(AFF_THREADS, 2) msm_accumulate_affine_kernel(const uint4* __restrict__ bases, const uint32_t* __restrict__ sorted,
+template <int AFF_K, bool SMEM>
+__global__ void __launch_bounds__(AFF_THREADS, SMEM ? (AFF_K <= 9 ? 3 : 2) : 4) msm_accumulate_affine_kernel(const uint4* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                                                const uint32_t* __restrict__ offs, const uint32_t* __restrict__ nxt,
                                                                                MsmShape s, int seg_log, uint32_t cpw, uint32_t tpw,
                                                                                uint4* __restrict__ baff, uint4* __restrict__ head,
                                                                                uint4* __restrict__ tail, uint4* __restrict__ prefix,
-                                                                               uint32_t* __restrict__ cur) {
+                                                                               uint32_t* __restrict__ cur, uint4* __restrict__ acc_scratch, int fake_inv) {
     extern __shared__ uint4 aff_smem[];
-    const AffSmem acc{aff_smem};
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nthreads = (size_t)s.nsets * tpw;
     if (gid >= nthreads) return;
+    const AffAcc<SMEM> acc{SMEM ? aff_smem : acc_scratch, SMEM ? (size_t)AFF_THREADS : nthreads, SMEM ? (size_t)threadIdx.x : gid};
     const uint32_t w = (uint32_t)(gid / tpw), tj = (uint32_t)(gid % tpw);
     const uint32_t* o = offs + (size_t)w * s.stride;
     const uint32_t* nx = nxt + (size_t)w * s.stride;
@@ -568,7 +575,7 @@ __global__ void __launch_bounds__(AFF_THREADS, 2) msm_accumulate_affine_kernel(c
     for (uint32_t step = 0; step < seg; step++) {
         // ---- forward: denominators and their running product --------------------------------------------------------------
         Fq run = Fq::one();
-        uint32_t kinds = 0;
+        uint64_t kinds = 0;
 #pragma unroll 1
         for (int k = 0; k < nact; k++) {
             const uint32_t pos = ((j0 + k) << seg_log) + step;
@@ -587,11 +594,16 @@ __global__ void __launch_bounds__(AFF_THREADS, 2) msm_accumulate_affine_kernel(c
                 *cu = nx[d + 1];  // next non-empty bucket: the one this entry opens
             }
             const uint4* bp = bases + (size_t)((e & ~AFF_FIRST) >> 1) * 4;
+            if (step + 1 < seg && pos + 1 < total) {  // the next step's gather: HBM -> L2 while this step computes
+                const uint4* np = bases + (size_t)((__ldg(lst + pos + 1) & ~AFF_FIRST) >> 1) * 4;
+                prefetch_l2(np);
+                prefetch_l2(np + 2);
+            }
             const Fq x2 = ldg_fq(bp);
             Fq y2 = ldg_fq(bp + 2);
             if (x2.is_zero() && y2.is_zero()) continue;  // identity base contributes nothing: reference curve.rs:857-858
             if (!((full_mask >> k) & 1u)) {              // empty accumulator: the backward pass just loads the point
-                kinds |= AFF_LOAD << (2 * k);
+                kinds |= (uint64_t)AFF_LOAD << (2 * k);
                 continue;
             }
             uint32_t kind = AFF_ADD;
@@ -608,17 +620,17 @@ __global__ void __launch_bounds__(AFF_THREADS, 2) msm_accumulate_affine_kernel(c
                     continue;
                 }
             }
-            kinds |= kind << (2 * k);
+            kinds |= (uint64_t)kind << (2 * k);
             st_fq(pre + (size_t)k * nthreads * 2, run);
             run = aff_mul(run, den);
         }
         if (kinds == 0) continue;
         // ---- one inversion for the whole step --------------------------------------------------------------------------------
-        Fq inv = (kinds & 0xaaaaaaaau) ? aff_inv(run) : run;  // no ADD / DBL in this step: nothing to invert
+        Fq inv = ((kinds & 0xaaaaaaaaaaaaaaaaull) && !fake_inv) ? aff_inv(run) : run;  // no ADD / DBL in this step: nothing to invert
         // ---- backward: peel the inverses off, finish the additions -------------------------------------------------------------
 #pragma unroll 1
         for (int k = nact - 1; k >= 0; k--) {
-            const uint32_t kind = (kinds >> (2 * k)) & 3u;
+            const uint32_t kind = (uint32_t)(kinds >> (2 * k)) & 3u;
             if (kind == AFF_SKIP) continue;
             const uint32_t pos = ((j0 + k) << seg_log) + step;
             const uint32_t e = __ldg(lst + pos);
@@ -1185,42 +1197,56 @@ static int g_aff_seg_log = 0;  // experiments: entries per stream = 2^g_aff_seg_
 void msm_set_affine_segment(int seg_log) { g_aff_seg_log = seg_log; }
 
 // batched-affine accumulation + merge (kernel comment above); the XYZZ bucket array comes out as msm_acc_phase leaves it
+static int g_aff_variant = 0;  // experiments: 0 = accumulators in shared memory, K = 14 | 1 = global scratch, K = 14 | 2 = global scratch, K = 28
+void msm_set_affine_variant(int v) { g_aff_variant = v; }
 static int msm_acc_phase_affine(const void* d_bases, size_t n, const MsmShape& s, const PartPlan& pl, const PartBuf& b, cudaStream_t st) {
     static bool attr_set = false;
-    const size_t smem = (size_t)AFF_K * 64 * AFF_THREADS;
+    const int K = g_aff_variant == 2 ? 28 : g_aff_variant == 3 ? 9 : 14;
+    const bool in_smem = g_aff_variant == 0 || g_aff_variant == 3;
+    const size_t smem = in_smem ? (size_t)K * 64 * AFF_THREADS : 0;
     if (!attr_set) {
-        CQB_CUDA(cudaFuncSetAttribute(msm_accumulate_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CQB_CUDA(cudaFuncSetAttribute(msm_accumulate_affine_kernel<14, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 14 * 64 * AFF_THREADS));
+        CQB_CUDA(cudaFuncSetAttribute(msm_accumulate_affine_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 64 * AFF_THREADS));
         CQB_CUDA(cudaFuncSetAttribute(msm_merge_big_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MERGE_BIG_AFF_THREADS * 128));
         attr_set = true;
     }
     const size_t entries = (size_t)n * s.nwin;
     // entries per stream: 32, shrinking while the grid would be shorter than ~4 waves of 2 CTAs x 148 SMs
     int seg_log = 5;
-    const size_t wave = (size_t)2 * ctx().sm_count * AFF_THREADS * AFF_K;
+    const size_t wave = (size_t)2 * ctx().sm_count * AFF_THREADS * K;
     while (seg_log > 3 && (entries >> seg_log) < 4 * wave) seg_log--;
     if (g_aff_seg_log > 0) seg_log = g_aff_seg_log;
     const size_t list_len = s.single ? entries : n;
     const uint32_t cpw = (uint32_t)((list_len + ((size_t)1 << seg_log) - 1) >> seg_log);  // sub-chunks (streams) per set
-    const uint32_t tpw = (cpw + AFF_K - 1) / AFF_K;                                        // threads per set
+    const uint32_t tpw = (cpw + K - 1) / K;                                                // threads per set
     const size_t nsub = (size_t)s.nsets * cpw, nthreads = (size_t)s.nsets * tpw;
     const uint32_t big_cap = (uint32_t)(s.nsets * (cpw / MERGE_LONG + 2));
     // head, tail: 64 B per sub-chunk; baff: 64 B per bucket; parked products: 32 B per stream; current bucket: 4 B per stream
-    const size_t head_b = nsub * 64, baff_b = pl.nbuckets * 64, pre_b = nthreads * AFF_K * 32, cur_b = nthreads * AFF_K * 4;
-    CQB_TRY(g_aff.ensure(2 * head_b + baff_b + pre_b + cur_b + 16 + (size_t)big_cap * 8));
+    const size_t head_b = nsub * 64, baff_b = pl.nbuckets * 64, pre_b = nthreads * K * 32, cur_b = nthreads * K * 4;
+    const size_t acc_b = in_smem ? 0 : nthreads * K * 64;
+    CQB_TRY(g_aff.ensure(2 * head_b + baff_b + pre_b + acc_b + cur_b + 16 + (size_t)big_cap * 8));
     uint4* head = g_aff.as<uint4>();
     uint4* tail = head + nsub * 4;
     uint4* baff = tail + nsub * 4;
     uint4* prefix = baff + pl.nbuckets * 4;
-    uint32_t* cur = (uint32_t*)(prefix + nthreads * AFF_K * 2);
-    uint32_t* big_count = cur + nthreads * AFF_K;
+    uint4* accs = prefix + nthreads * K * 2;
+    uint32_t* cur = (uint32_t*)(accs + acc_b / 16);
+    uint32_t* big_count = cur + nthreads * K;
     uint2* big_list = (uint2*)(big_count + 4);
     CQB_CUDA(cudaMemsetAsync(b.buckets, 0, pl.nbuckets * 128, st));
     CQB_CUDA(cudaMemsetAsync(big_count, 0, 16, st));
     int h = prof_begin(3, st);
     msm_mark_first_kernel<<<(unsigned)((pl.nbuckets + 255) / 256), 256, 0, st>>>(b.offs, s, b.sorted);
     CQB_LAUNCHED();
-    msm_accumulate_affine_kernel<<<(unsigned)((nthreads + AFF_THREADS - 1) / AFF_THREADS), AFF_THREADS, smem, st>>>(
-        (const uint4*)d_bases, b.sorted, b.offs, b.hist, s, seg_log, cpw, tpw, baff, head, tail, prefix, cur);
+    const unsigned grid = (unsigned)((nthreads + AFF_THREADS - 1) / AFF_THREADS);
+#define AFF_LAUNCH(KK, SM)                                                                                                              \
+    msm_accumulate_affine_kernel<KK, SM><<<grid, AFF_THREADS, smem, st>>>((const uint4*)d_bases, b.sorted, b.offs, b.hist, s, seg_log, cpw, tpw, \
+                                                                         baff, head, tail, prefix, cur, accs, getenv("CQB_AFF_FAKEINV") ? 1 : 0)
+    if (g_aff_variant == 0) AFF_LAUNCH(14, true);
+    else if (g_aff_variant == 1) AFF_LAUNCH(14, false);
+    else if (g_aff_variant == 3) AFF_LAUNCH(9, true);
+    else AFF_LAUNCH(28, false);
+#undef AFF_LAUNCH
     CQB_LAUNCHED();
     prof_end(h, st);
     h = prof_begin(4, st);

@@ -35,8 +35,9 @@ __global__ void __launch_bounds__(128) chunk_horner_kernel(const uint4* __restri
     p_st(L, c, acc);
 }
 // S[k] = v[k] + beta S[k+1] inside chunk c, with carry-in Y[c+1] (0 for the top chunk). Y may be null (single chunk).
-__global__ void __launch_bounds__(128) chunk_replay_kernel(const uint4* __restrict__ v, size_t m, Fr beta, const uint4* __restrict__ Y,
-                                                           size_t nchunks, uint4* __restrict__ S) {
+// v / S may alias (the recursive scan runs in place): no __restrict__ on them
+__global__ void __launch_bounds__(128) chunk_replay_kernel(const uint4* v, size_t m, Fr beta, const uint4* Y,
+                                                           size_t nchunks, uint4* S) {
     size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t lo = c * PCH;
     if (lo >= m) return;

@@ -34,8 +34,9 @@ __global__ void __launch_bounds__(128) chunk_product_kernel(const uint4* __restr
 }
 // out[k] = carry * v[lo] * ... * v[k-1] for k in chunk c; carry = Y[c] (or init when Y is null: a single chunk).
 // out may alias v (each element is read before its slot is written, by the same thread).
-__global__ void __launch_bounds__(128) chunk_exclusive_replay_kernel(const uint4* __restrict__ v, size_t m, Fr init, const uint4* __restrict__ Y,
-                                                                     uint4* __restrict__ out) {
+// in / out may alias (the recursive scans run in place): no __restrict__ on them
+__global__ void __launch_bounds__(128) chunk_exclusive_replay_kernel(const uint4* v, size_t m, Fr init, const uint4* Y,
+                                                                     uint4* out) {
     size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t lo = c * QCH;
     if (lo >= m) return;
@@ -217,12 +218,12 @@ __global__ void __launch_bounds__(256) fr_compress_kernel(const __grid_constant_
     q_st(out, i, acc);
 }
 // out[i] = in[i] + shift for i < usable, shift for i >= usable (the reference's bs before inversion, prover.rs:261-269)
-__global__ void __launch_bounds__(256) fr_shift_kernel(const uint4* __restrict__ in, size_t n, size_t usable, Fr shift, uint4* __restrict__ out) {
+__global__ void __launch_bounds__(256) fr_shift_kernel(const uint4* in, size_t n, size_t usable, Fr shift, uint4* out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     q_st(out, i, i < usable ? fp_add<FrP>(q_ld(in, i), shift) : shift);
 }
-__global__ void __launch_bounds__(256) fr_mul_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, size_t n, uint4* __restrict__ out) {
+__global__ void __launch_bounds__(256) fr_mul_kernel(const uint4* a, const uint4* b, size_t n, uint4* out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     q_st(out, i, fp_mul<FrP>(q_ld(a, i), q_ld(b, i)));

@@ -28,9 +28,9 @@ class DeviceBases:
         return self
 
     def to_host(self):
-        """download the points (only possible for adopted device memory)"""
+        """download the points (ParamsKZG::write_custom needs them back: read -> write and downsize round trips)"""
         out = np.zeros((self.n, 8), np.uint64)
-        _lib.check(_lib.lib().cqb_memcpy_d2h(out.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(self._device_ptr), self.n * 64))
+        _lib.check(_lib.lib().cqb_bases_download(self.handle, 0, self.n, _lib.p64(out)))
         return out
 
     def __init__(self, affine, precompute=None, window_bits=0):
@@ -119,19 +119,18 @@ class ParamsKZG:
         """reference commitment.rs:482-490: truncate g to 2^k points and rebuild g_lagrange with g_to_lagrange (the G1
         EC-FFT of arithmetic.rs:277-301) — on the device, from the resident monomial SRS"""
         assert k <= self.k, "assert!(k <= self.k)"
-        if self._dev_alloc is None:
-            raise NotImplementedError("downsize needs the device-generated layout (setup_from_toxic_waste)")
         lib = _lib.lib()
         n = 1 << k
         d = ctypes.c_void_p()
         _lib.check(lib.cqb_dev_alloc(2 * n * 64, ctypes.byref(d)))
-        _lib.check(lib.cqb_memcpy_d2d(d, ctypes.c_void_p(self.g._device_ptr), n * 64))
+        _lib.check(lib.cqb_bases_copy_dev(self.g.handle, 0, n, d))
         _lib.check(lib.cqb_g_to_lagrange_dev(d, k, ctypes.c_void_p(d.value + n * 64)))
         _lib.check(lib.cqb_sync())
         old = self._dev_alloc
         self.g.free()
         self.g_lagrange.free()
-        _lib.check(lib.cqb_dev_free(old))
+        if old is not None:  # params read from a file / built from host arrays own their points through the handles
+            _lib.check(lib.cqb_dev_free(old))
         self.k, self.n, self._dev_alloc = k, n, d
         self.g = DeviceBases.adopt(d.value, n, precompute=False)
         self.g_lagrange = DeviceBases.adopt(d.value + n * 64, n, precompute=False)

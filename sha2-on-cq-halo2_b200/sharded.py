@@ -148,6 +148,17 @@ class CudaNttBackend:
 
         self.torch = torch
         self.device = device
+        self.bind_stream()
+
+    def bind_stream(self):
+        """The library's kernels and torch's (NCCL collectives, permute / copy kernels, the caching allocator) must be ordered
+        on ONE stream: hand torch's current stream to the library (cqb_set_stream). Called at construction and again at the
+        top of every distributed transform, so a caller that never touched cqb_set_stream — or switched torch streams in
+        between — cannot race the all-to-all against the transpose / batched NTT kernels."""
+        st = self.torch.cuda.current_stream(self.device).cuda_stream or 1  # 0 = torch's default stream = cudaStreamLegacy (handle 0x1)
+        if getattr(self, "_bound", None) != st:
+            _lib.check(_lib.lib().cqb_set_stream(ctypes.c_void_p(st)))
+            self._bound = st
 
     def empty(self, nelem):
         return self.torch.empty(nelem * 32, dtype=self.torch.uint8, device=self.device)
@@ -334,6 +345,7 @@ class ShardedNTT:
         """split the batched transforms into `groups` member groups: the all-to-all of a finished group (NCCL on a second
         stream, list form, chunks placed [source rank][group]) runs under the transform of the next group"""
         assert self.world > 1 and hasattr(self.backend, "ntt_batch_map")
+        assert groups >= 1 and (groups & (groups - 1)) == 0, "member groups must be a power of two (segment logs are taken from them)"
         torch = self.backend.torch
         self._groups = groups
         self._comm_stream = torch.cuda.Stream(device=self.backend.device)
@@ -383,7 +395,10 @@ class ShardedNTT:
 
     def _run(self, x_local, omega):
         n1, n2, G = 1 << self.l1, 1 << self.l2, self.world
-        if getattr(self, "_groups", 0) > 1 and min(n1, n2) // G >= self._groups and max(n1, n2) // G <= 65535:
+        if hasattr(self.backend, "bind_stream"):
+            self.backend.bind_stream()
+        S = getattr(self, "_groups", 0)
+        if S > 1 and min(n1, n2) // G >= S and (n1 // G) % S == 0 and (n2 // G) % S == 0 and max(n1, n2) // G <= 65535:
             return self._run_overlap(x_local, omega)
         if getattr(self, "_p2p", False) and max(n1, n2) // G <= 65535:
             return self._run_p2p(x_local, omega)

@@ -172,6 +172,24 @@ __global__ void k_fpmul(Res* out, const Fp<P>* in, Fp<P>* o, int iters) {
     o[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
+// safegcd inversions (fp_inv_safegcd), NCHAIN independent dependent-chains per thread: latency and throughput of the
+// branch-free inversion the batched-affine accumulation runs once per thread per step
+template <int NCHAIN>
+__global__ void k_fqinv(Res* out, const Fq* in, Fq* o, int iters) {
+    Fq x[NCHAIN], y = in[threadIdx.x];
+    for (int k = 0; k < NCHAIN; k++) x[k] = in[threadIdx.x + 32 * (k + 1)];
+    unsigned long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < NCHAIN; k++) x[k] = fp_add<FqP>(fp_inv_safegcd<FqP>(x[k]), y);
+    }
+    unsigned long long t1 = clock64();
+    if (threadIdx.x == 0) out[blockIdx.x].cyc = t1 - t0;
+    Fq acc = x[0];
+    for (int k = 1; k < NCHAIN; k++) acc = fp_add<FqP>(acc, x[k]);
+    o[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 template <class F>
 static void run(const char* name, F launch, double ops_per_thread, int blocks, int threads, int nsm) {
     Res* d; CK(cudaMalloc(&d, sizeof(Res) * blocks)); CK(cudaMemset(d, 0, sizeof(Res) * blocks));
@@ -232,6 +250,14 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < hin.size(); i++) hin[i] = (uint32_t)(0x9e3779b9u * (i + 1)) >> ((i % 8 == 7) ? 3 : 0);
     Fq* din; CK(cudaMalloc(&din, hin.size() * 4)); CK(cudaMemcpy(din, hin.data(), hin.size() * 4, cudaMemcpyHostToDevice));
     Fq* dout; CK(cudaMalloc(&dout, sizeof(Fq) * nsm * 16 * 1024));
+    for (int th : {32, 128}) for (int bps : {1, 2, 4}) {  // inversion latency (1 warp per SM) and throughput
+        int blocks = nsm * bps;
+        char nm[64];
+        snprintf(nm, 64, "fq_inv_safegcd_chain1_%dthr", th);
+        run(nm, [&](Res* d) { k_fqinv<1><<<blocks, th>>>(d, din, dout, 50); }, 50.0, blocks, th, nsm);
+        snprintf(nm, 64, "fq_inv_safegcd_chain2_%dthr", th);
+        run(nm, [&](Res* d) { k_fqinv<2><<<blocks, th>>>(d, din, dout, 50); }, 100.0, blocks, th, nsm);
+    }
     {   // long modmul runs: 256 threads x 4 CTAs/SM, two chains
         int blocks = nsm * 4, th = 256;
         for (int itl : {20000, 80000}) {
