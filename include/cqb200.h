@@ -279,8 +279,10 @@ CQB_API int cqb_msm_set_window_bits(int c);
 /* number of point-range parts a large device-resident MSM is cut into (the sort phase of part p+1 runs on a second stream
  * under the bucket accumulation of part p); 0 = automatic, 1 = no pipelining, at most 8. Results do not depend on it. */
 CQB_API int cqb_msm_set_parts(int parts);
-/* bucket accumulation variant: 0 = automatic (batched affine additions — the reference's batch_add,
- * arithmetic/curves/src/derive/curve.rs:4-141 — for large MSMs, XYZZ mixed additions below), 1 = XYZZ, 2 = batched affine;
+/* bucket accumulation variant: 0 = automatic, 1 = XYZZ mixed additions, 2 = batched affine additions (the reference's batch_add,
+ * arithmetic/curves/src/derive/curve.rs:4-141, as a kernel: Montgomery's trick over the streams of a thread, one safegcd
+ * inversion per step). Measured on B200 the affine variant is SLOWER (2^24: 44-56 ms against 32 ms), so
+ * automatic means XYZZ; the variant stays selectable and parity-tested (tests/test_gpu_affine_acc.py).
  * affine_seg_log: entries per accumulation stream = 2^affine_seg_log (0 = automatic). Results do not depend on either. */
 CQB_API int cqb_msm_set_accumulator(int mode, int affine_seg_log);
 

@@ -5,13 +5,23 @@
 #include <algorithm>
 #include <map>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "internal.h"
 
 namespace cqb {
 
-static Ctx g_ctx;
-Ctx& ctx() { return g_ctx; }
+static Ctx g_ctxs[MAX_DEVICES];
+static int g_nslots = 0;                 // initialised slots: 1 after cqb_init, n after cqb_init_multi(n)
+static thread_local int tl_slot = 0;
+int cur_slot() { return tl_slot; }
+void bind_slot(int slot) {
+    tl_slot = slot;
+    if (g_ctxs[slot].inited) cudaSetDevice(g_ctxs[slot].device);
+}
+Ctx& ctx() { return g_ctxs[tl_slot]; }
+#define g_ctx (ctx())
 static std::recursive_mutex g_mu;
 static thread_local char g_errbuf[512];
 
@@ -67,13 +77,22 @@ void Pinned::release() {
     cap = 0;
 }
 
-struct BaseSet { void* d; size_t n; bool owned; void* table; int table_c; };
+// a registered base set lives on one slot; a SHARDED set (cqb_bases_register_sharded) is a parent whose children hold
+// contiguous point ranges on the slots of cqb_init_multi
+struct BaseSet {
+    void* d; size_t n; bool owned; void* table; int table_c;
+    int slot = 0;
+    std::vector<cqb_bases_t> shards;   // children (empty for a plain set)
+    std::vector<size_t> shard_start;   // first point of each child
+};
 static std::map<cqb_bases_t, BaseSet> g_bases;
 static cqb_bases_t g_next_handle = 1;
-static Scratch g_scalars, g_idx, g_io, g_tmp_bases, g_out;
-static Pinned g_out_host;
-static cudaStream_t g_copy_stream = nullptr;  // H2D of part p+1 overlaps the kernels of part p (host-pointer MSM)
-static cudaEvent_t g_copy_ev[4];
+static PerDevice<Scratch> g_scalars, g_idx, g_tmp_bases, g_out;
+static Scratch g_io;
+static PerDevice<Pinned> g_out_host;
+struct CopyStream { cudaStream_t s = nullptr; cudaEvent_t ev[4]; };  // H2D of part p+1 overlaps the kernels of part p (host-pointer MSM)
+static PerDevice<CopyStream> g_copy;
+static PerDevice<Pinned> g_stage;  // pinned staging ring for pageable host scalars
 
 static int require_init() {
     if (!g_ctx.inited) return fail(CQB_E_NO_DEVICE, "cqb_init() has not been called or no CUDA device is available (there is no CPU fallback)");
@@ -81,11 +100,11 @@ static int require_init() {
 }
 
 static int fetch_result(uint64_t out_xy[8], int* is_inf) {
-    CQB_TRY(g_out_host.ensure(128));
-    CQB_CUDA(cudaMemcpyAsync(g_out_host.p, g_out.p, 80, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CQB_TRY(g_out_host->ensure(128));
+    CQB_CUDA(cudaMemcpyAsync(g_out_host->p, g_out->p, 80, cudaMemcpyDeviceToHost, g_ctx.stream));
     CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
-    memcpy(out_xy, g_out_host.p, 64);
-    if (is_inf) *is_inf = (int)((uint32_t*)g_out_host.p)[16];
+    memcpy(out_xy, g_out_host->p, 64);
+    if (is_inf) *is_inf = (int)((uint32_t*)g_out_host->p)[16];
     return 0;
 }
 
@@ -121,7 +140,7 @@ int cqb_init(int device) {
     g_ctx.own_stream = true;
     g_ctx.inited = true;
     g_ctx.launches = 0;
-    CQB_TRY(g_out.ensure(256));
+    CQB_TRY(g_out->ensure(256));
     return 0;
 }
 
@@ -135,8 +154,8 @@ void cqb_shutdown(void) {
         if (kv.second.table) cudaFree(kv.second.table);
     }
     g_bases.clear();
-    g_scalars.release(); g_idx.release(); g_io.release(); g_tmp_bases.release(); g_out.release();
-    g_out_host.release();
+    g_scalars->release(); g_idx->release(); g_io.release(); g_tmp_bases->release(); g_out->release();
+    g_out_host->release();
     ntt_release_all();
     msm_release_all();
     gen_release_all();
@@ -145,10 +164,10 @@ void cqb_shutdown(void) {
     poly_release_all();
     products_release_all();
     evalh_release_all();
-    if (g_copy_stream) {
-        for (auto& e : g_copy_ev) cudaEventDestroy(e);
-        cudaStreamDestroy(g_copy_stream);
-        g_copy_stream = nullptr;
+    if (g_copy->s) {
+        for (auto& e : g_copy->ev) cudaEventDestroy(e);
+        cudaStreamDestroy(g_copy->s);
+        g_copy->s = nullptr;
     }
     if (g_ctx.own_stream && g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
     g_ctx.stream = nullptr;
@@ -259,8 +278,8 @@ static int find_bases(cqb_bases_t h, size_t offset, size_t n, BaseSet** out) {
 // (its bucket count is sized for the whole set), else the windowed layout on the plain bases
 static int dispatch_msm(BaseSet* bs, size_t offset, const void* d_scalars, const uint32_t* d_idx, size_t n) {
     if (bs->table && n * 8 >= bs->n)
-        return msm_run_precomputed(bs->table, bs->n, bs->table_c, offset, d_scalars, d_idx, n, g_out.p);
-    return msm_run(bs->d, offset, d_scalars, d_idx, n, g_out.p);
+        return msm_run_precomputed(bs->table, bs->n, bs->table_c, offset, d_scalars, d_idx, n, g_out->p);
+    return msm_run(bs->d, offset, d_scalars, d_idx, n, g_out->p);
 }
 
 int cqb_bases_precompute(cqb_bases_t h, int window_bits) {
@@ -317,7 +336,7 @@ int cqb_msm_bn254_g1(cqb_bases_t b, size_t offset, const uint64_t* scalars, size
     if (!out_xy || (!scalars && n)) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1: NULL argument");
     BaseSet* bs = nullptr;
     CQB_TRY(find_bases(b, offset, n, &bs));
-    CQB_TRY(g_scalars.ensure(n * 32 + 32));
+    CQB_TRY(g_scalars->ensure(n * 32 + 32));
     // Large MSM from PINNED host memory: cut into parts; the H2D copy of part p+1 (copy stream) overlaps the kernels of
     // part p (compute stream). Pageable memory cannot overlap (the copy is staged synchronously), so it takes the plain path.
 #ifndef CQB_HOST_PARTS
@@ -331,46 +350,46 @@ int cqb_msm_bn254_g1(cqb_bases_t b, size_t offset, const uint64_t* scalars, size
         else cudaGetLastError();
     }
     if (pinned) {
-        if (!g_copy_stream) {
-            CQB_CUDA(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
-            for (auto& e : g_copy_ev) CQB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        if (!g_copy->s) {
+            CQB_CUDA(cudaStreamCreateWithFlags(&g_copy->s, cudaStreamNonBlocking));
+            for (auto& e : g_copy->ev) CQB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
         size_t bounds[PARTS + 1];
         msm_part_bounds(n, PARTS, true, bounds);  // the same split msm_run* makes (small first part: its copy is the exposed one)
         bool use_table = bs->table && n * 8 >= bs->n;
         for (int p = 0; p < PARTS; p++) {
             size_t lo = bounds[p], cnt = bounds[p + 1] - lo;
-            if (cnt) CQB_CUDA(cudaMemcpyAsync((char*)g_scalars.p + lo * 32, scalars + lo * 4, cnt * 32, cudaMemcpyHostToDevice, g_copy_stream));
-            CQB_CUDA(cudaEventRecord(g_copy_ev[p], g_copy_stream));
+            if (cnt) CQB_CUDA(cudaMemcpyAsync((char*)g_scalars->p + lo * 32, scalars + lo * 4, cnt * 32, cudaMemcpyHostToDevice, g_copy->s));
+            CQB_CUDA(cudaEventRecord(g_copy->ev[p], g_copy->s));
         }
         // the sort of part p waits for its copy; the accumulation of part p-1 runs meanwhile on the main stream
-        if (use_table) CQB_TRY(msm_run_precomputed(bs->table, bs->n, bs->table_c, offset, g_scalars.p, nullptr, n, g_out.p, 1, PARTS, g_copy_ev));
-        else CQB_TRY(msm_run(bs->d, offset, g_scalars.p, nullptr, n, g_out.p, PARTS, g_copy_ev));
+        if (use_table) CQB_TRY(msm_run_precomputed(bs->table, bs->n, bs->table_c, offset, g_scalars->p, nullptr, n, g_out->p, 1, PARTS, g_copy->ev));
+        else CQB_TRY(msm_run(bs->d, offset, g_scalars->p, nullptr, n, g_out->p, PARTS, g_copy->ev));
         return fetch_result(out_xy, is_inf);
     }
-    if (n) CQB_CUDA(cudaMemcpyAsync(g_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, g_ctx.stream));
-    CQB_TRY(dispatch_msm(bs, offset, g_scalars.p, nullptr, n));
+    if (n) CQB_CUDA(cudaMemcpyAsync(g_scalars->p, scalars, n * 32, cudaMemcpyHostToDevice, g_ctx.stream));
+    CQB_TRY(dispatch_msm(bs, offset, g_scalars->p, nullptr, n));
     return fetch_result(out_xy, is_inf);
 }
 
 // B MSMs over the same base range in one pass (commit_lagrange of all advice columns, the h pieces, ...)
 static int msm_batch_common(BaseSet* bs, size_t offset, const void* d_scalars, size_t n, int batch, uint64_t* out_xy, int* is_inf) {
-    CQB_TRY(g_out.ensure((size_t)batch * 80 + 80));
-    CQB_TRY(g_out_host.ensure((size_t)batch * 80 + 80));
+    CQB_TRY(g_out->ensure((size_t)batch * 80 + 80));
+    CQB_TRY(g_out_host->ensure((size_t)batch * 80 + 80));
     if (bs->table && n * 8 >= bs->n && batch > 1) {
-        CQB_TRY(msm_run_precomputed(bs->table, bs->n, bs->table_c, offset, d_scalars, nullptr, n, g_out.p, batch));
+        CQB_TRY(msm_run_precomputed(bs->table, bs->n, bs->table_c, offset, d_scalars, nullptr, n, g_out->p, batch));
     } else {
         for (int b = 0; b < batch; b++) {  // no table for this set: one MSM after the other (same results)
             const char* sc = (const char*)d_scalars + (size_t)b * n * 32;
-            if (bs->table && n * 8 >= bs->n) CQB_TRY(msm_run_precomputed(bs->table, bs->n, bs->table_c, offset, sc, nullptr, n, (char*)g_out.p + (size_t)b * 80));
-            else CQB_TRY(msm_run(bs->d, offset, sc, nullptr, n, (char*)g_out.p + (size_t)b * 80));
+            if (bs->table && n * 8 >= bs->n) CQB_TRY(msm_run_precomputed(bs->table, bs->n, bs->table_c, offset, sc, nullptr, n, (char*)g_out->p + (size_t)b * 80));
+            else CQB_TRY(msm_run(bs->d, offset, sc, nullptr, n, (char*)g_out->p + (size_t)b * 80));
         }
     }
-    CQB_CUDA(cudaMemcpyAsync(g_out_host.p, g_out.p, (size_t)batch * 80, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CQB_CUDA(cudaMemcpyAsync(g_out_host->p, g_out->p, (size_t)batch * 80, cudaMemcpyDeviceToHost, g_ctx.stream));
     CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
     for (int b = 0; b < batch; b++) {
-        memcpy(out_xy + 8 * b, (char*)g_out_host.p + (size_t)b * 80, 64);
-        if (is_inf) is_inf[b] = (int)((uint32_t*)((char*)g_out_host.p + (size_t)b * 80))[16];
+        memcpy(out_xy + 8 * b, (char*)g_out_host->p + (size_t)b * 80, 64);
+        if (is_inf) is_inf[b] = (int)((uint32_t*)((char*)g_out_host->p + (size_t)b * 80))[16];
     }
     return 0;
 }
@@ -388,22 +407,22 @@ int cqb_msm_bn254_g1_batch(cqb_bases_t h, size_t offset, const uint64_t* scalars
     if (!out_xy || (!scalars && n) || batch < 1 || batch > 64) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1_batch: bad argument (1 <= batch <= 64)");
     BaseSet* bs = nullptr;
     CQB_TRY(find_bases(h, offset, n, &bs));
-    CQB_TRY(g_scalars.ensure((size_t)batch * n * 32 + 32));
-    if (n) CQB_CUDA(cudaMemcpyAsync(g_scalars.p, scalars, (size_t)batch * n * 32, cudaMemcpyHostToDevice, g_ctx.stream));
-    return msm_batch_common(bs, offset, g_scalars.p, n, batch, out_xy, is_inf);
+    CQB_TRY(g_scalars->ensure((size_t)batch * n * 32 + 32));
+    if (n) CQB_CUDA(cudaMemcpyAsync(g_scalars->p, scalars, (size_t)batch * n * 32, cudaMemcpyHostToDevice, g_ctx.stream));
+    return msm_batch_common(bs, offset, g_scalars->p, n, batch, out_xy, is_inf);
 }
 
 int cqb_msm_bn254_g1_host(const uint64_t* affine_xy, const uint64_t* scalars, size_t n, uint64_t out_xy[8], int* is_inf) {
     LOCK;
     CQB_TRY(require_init());
     if (!out_xy || ((!scalars || !affine_xy) && n)) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1_host: NULL argument");
-    CQB_TRY(g_tmp_bases.ensure(n * 64 + 64));
-    CQB_TRY(g_scalars.ensure(n * 32 + 32));
+    CQB_TRY(g_tmp_bases->ensure(n * 64 + 64));
+    CQB_TRY(g_scalars->ensure(n * 32 + 32));
     if (n) {
-        CQB_CUDA(cudaMemcpyAsync(g_tmp_bases.p, affine_xy, n * 64, cudaMemcpyHostToDevice, g_ctx.stream));
-        CQB_CUDA(cudaMemcpyAsync(g_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, g_ctx.stream));
+        CQB_CUDA(cudaMemcpyAsync(g_tmp_bases->p, affine_xy, n * 64, cudaMemcpyHostToDevice, g_ctx.stream));
+        CQB_CUDA(cudaMemcpyAsync(g_scalars->p, scalars, n * 32, cudaMemcpyHostToDevice, g_ctx.stream));
     }
-    CQB_TRY(msm_run(g_tmp_bases.p, 0, g_scalars.p, nullptr, n, g_out.p));
+    CQB_TRY(msm_run(g_tmp_bases->p, 0, g_scalars->p, nullptr, n, g_out->p));
     return fetch_result(out_xy, is_inf);
 }
 
@@ -415,13 +434,13 @@ int cqb_msm_bn254_g1_sparse(cqb_bases_t b, const uint32_t* idx, const uint64_t* 
     if (it == g_bases.end()) return fail(CQB_E_BAD_ARG, "unknown bases handle %llu", (unsigned long long)b);
     for (size_t j = 0; j < m; j++)  // the reference would panic on an out-of-range table index (slice indexing)
         if (idx[j] >= it->second.n) return fail(CQB_E_BAD_ARG, "sparse index %u out of range (%zu bases)", idx[j], it->second.n);
-    CQB_TRY(g_scalars.ensure(m * 32 + 32));
-    CQB_TRY(g_idx.ensure(m * 4 + 4));
+    CQB_TRY(g_scalars->ensure(m * 32 + 32));
+    CQB_TRY(g_idx->ensure(m * 4 + 4));
     if (m) {
-        CQB_CUDA(cudaMemcpyAsync(g_scalars.p, scalars, m * 32, cudaMemcpyHostToDevice, g_ctx.stream));
-        CQB_CUDA(cudaMemcpyAsync(g_idx.p, idx, m * 4, cudaMemcpyHostToDevice, g_ctx.stream));
+        CQB_CUDA(cudaMemcpyAsync(g_scalars->p, scalars, m * 32, cudaMemcpyHostToDevice, g_ctx.stream));
+        CQB_CUDA(cudaMemcpyAsync(g_idx->p, idx, m * 4, cudaMemcpyHostToDevice, g_ctx.stream));
     }
-    CQB_TRY(dispatch_msm(&it->second, 0, g_scalars.p, g_idx.as<uint32_t>(), m));
+    CQB_TRY(dispatch_msm(&it->second, 0, g_scalars->p, g_idx->as<uint32_t>(), m));
     return fetch_result(out_xy, is_inf);
 }
 
@@ -429,9 +448,9 @@ int cqb_g1_sum_affine(const uint64_t* affine_xy, size_t n, uint64_t out_xy[8], i
     LOCK;
     CQB_TRY(require_init());
     if (!out_xy || (!affine_xy && n)) return fail(CQB_E_BAD_ARG, "cqb_g1_sum_affine: NULL argument");
-    CQB_TRY(g_tmp_bases.ensure(n * 64 + 64));
-    if (n) CQB_CUDA(cudaMemcpyAsync(g_tmp_bases.p, affine_xy, n * 64, cudaMemcpyHostToDevice, g_ctx.stream));
-    CQB_TRY(g1_sum_affine_run(g_tmp_bases.p, n, g_out.p));
+    CQB_TRY(g_tmp_bases->ensure(n * 64 + 64));
+    if (n) CQB_CUDA(cudaMemcpyAsync(g_tmp_bases->p, affine_xy, n * 64, cudaMemcpyHostToDevice, g_ctx.stream));
+    CQB_TRY(g1_sum_affine_run(g_tmp_bases->p, n, g_out->p));
     return fetch_result(out_xy, is_inf);
 }
 
@@ -769,11 +788,11 @@ int cqb_eval_polynomial_dev(const void* d_coeffs, size_t n, const uint64_t point
     LOCK;
     CQB_TRY(require_init());
     if ((!d_coeffs && n) || !point || !out) return fail(CQB_E_BAD_ARG, "cqb_eval_polynomial_dev: NULL argument");
-    CQB_TRY(eval_polynomial_run(d_coeffs, n, point, g_out.p));
-    CQB_TRY(g_out_host.ensure(128));
-    CQB_CUDA(cudaMemcpyAsync(g_out_host.p, g_out.p, 32, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CQB_TRY(eval_polynomial_run(d_coeffs, n, point, g_out->p));
+    CQB_TRY(g_out_host->ensure(128));
+    CQB_CUDA(cudaMemcpyAsync(g_out_host->p, g_out->p, 32, cudaMemcpyDeviceToHost, g_ctx.stream));
     CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
-    memcpy(out, g_out_host.p, 32);
+    memcpy(out, g_out_host->p, 32);
     return 0;
 }
 int cqb_kate_division_dev(const void* d_a, size_t n, const uint64_t b[4], void* d_q) {

@@ -12,6 +12,23 @@
 
 namespace cqb {
 
+// One context per DEVICE SLOT. A process drives one GPU (cqb_init(device): slot 0 only — the one-process-per-GPU form the
+// benchmark launches under torchrun) or several (cqb_init_multi(n): slot i = device i; MSMs over a sharded base set fan out
+// to one host thread per slot, the reference's own decomposition across threads, arithmetic.rs:137-153). Every host thread
+// works on the slot it is bound to (thread-local); ctx() and every PerDevice<> object resolve through it, so the launchers
+// below the ABI are written once and never mention a device.
+constexpr int MAX_DEVICES = 16;
+int cur_slot();
+void bind_slot(int slot);  // also cudaSetDevice()s the slot's device when the slot is initialised
+
+template <class T>
+struct PerDevice {
+    T v[MAX_DEVICES];
+    T* operator->() { return &v[cur_slot()]; }
+    T& get() { return v[cur_slot()]; }
+    T& at(int slot) { return v[slot]; }
+};
+
 struct Ctx {
     int device = -1;
     int sm_count = 148;

@@ -524,12 +524,12 @@ __device__ __noinline__ Fq aff_mul(Fq a, Fq b) { return fp_mul<FqP>(a, b); }
 __device__ __noinline__ Fq aff_inv(Fq a) { return fp_inv_safegcd<FqP>(a); }
 
 template <int AFF_K, bool SMEM>
-__global__ void __launch_bounds__(AFF_THREADS, SMEM ? (AFF_K <= 9 ? 3 : 2) : 4) msm_accumulate_affine_kernel(const uint4* __restrict__ bases, const uint32_t* __restrict__ sorted,
+__global__ void __launch_bounds__(AFF_THREADS, SMEM ? 2 : 4) msm_accumulate_affine_kernel(const uint4* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                                                const uint32_t* __restrict__ offs, const uint32_t* __restrict__ nxt,
                                                                                MsmShape s, int seg_log, uint32_t cpw, uint32_t tpw,
                                                                                uint4* __restrict__ baff, uint4* __restrict__ head,
                                                                                uint4* __restrict__ tail, uint4* __restrict__ prefix,
-                                                                               uint32_t* __restrict__ cur, uint4* __restrict__ acc_scratch, int fake_inv) {
+                                                                               uint32_t* __restrict__ cur, uint4* __restrict__ acc_scratch) {
     extern __shared__ uint4 aff_smem[];
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nthreads = (size_t)s.nsets * tpw;
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(AFF_THREADS, SMEM ? (AFF_K <= 9 ? 3 : 2) : 4) 
         }
         if (kinds == 0) continue;
         // ---- one inversion for the whole step --------------------------------------------------------------------------------
-        Fq inv = ((kinds & 0xaaaaaaaaaaaaaaaaull) && !fake_inv) ? aff_inv(run) : run;  // no ADD / DBL in this step: nothing to invert
+        Fq inv = (kinds & 0xaaaaaaaaaaaaaaaaull) ? aff_inv(run) : run;  // no ADD / DBL in this step: nothing to invert
         // ---- backward: peel the inverses off, finish the additions -------------------------------------------------------------
 #pragma unroll 1
         for (int k = nact - 1; k >= 0; k--) {
@@ -970,13 +970,25 @@ __global__ void __launch_bounds__(128) msm_precompute_row_kernel(const uint4* __
 // -------------------------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------------------------
-static Scratch g_hist, g_sorted, g_buckets, g_partials, g_chunks, g_pre_tmp, g_aff;
+static PerDevice<Scratch> g_hist, g_sorted, g_buckets, g_partials, g_chunks, g_pre_tmp, g_aff;
 
 // Second stream (high priority) for the sort phases (count / scan / scatter) of part p+1 of a large MSM, which overlap the
 // bucket accumulation of part p on the main stream: the sort is atomics/latency bound, the accumulation multiplier bound.
 constexpr int MSM_MAX_PARTS = 8;
-static cudaStream_t g_sort_stream = nullptr;
-static cudaEvent_t g_ev_start = nullptr, g_ev_sorted[MSM_MAX_PARTS];
+struct ProfSpan { int phase; cudaEvent_t a, b; };
+struct MsmDev {  // per device slot (context.h): streams, events and profiling spans of the MSMs running on that device
+    cudaStream_t sort_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_sorted[MSM_MAX_PARTS];
+    std::vector<ProfSpan> spans;
+    size_t spans_used = 0;
+    bool aff_attr_set = false;
+};
+static PerDevice<MsmDev> g_dev;
+#define g_sort_stream (g_dev->sort_stream)
+#define g_ev_start (g_dev->ev_start)
+#define g_ev_sorted (g_dev->ev_sorted)
+#define g_spans (g_dev->spans)
+#define g_spans_used (g_dev->spans_used)
 static int ensure_sort_stream() {
     if (g_sort_stream) return 0;
     int lo = 0, hi = 0;
@@ -991,9 +1003,6 @@ static int ensure_sort_stream() {
 // runs on; msm_phase_ms sums the spans of each phase (a pipelined MSM has one span per phase and part). No host sync
 // until the times are read.
 static bool g_prof = false;
-struct ProfSpan { int phase; cudaEvent_t a, b; };
-static std::vector<ProfSpan> g_spans;
-static size_t g_spans_used = 0;
 void msm_set_profiling(bool on) { g_prof = on; }
 static int prof_begin(int phase, cudaStream_t st) {
     if (!g_prof) return -1;
@@ -1026,13 +1035,13 @@ int msm_phase_ms(float* ms, int cap) {
 }
 
 void msm_release_all() {
-    g_hist.release();
-    g_sorted.release();
-    g_buckets.release();
-    g_partials.release();
-    g_chunks.release();
-    g_pre_tmp.release();
-    g_aff.release();
+    g_hist->release();
+    g_sorted->release();
+    g_buckets->release();
+    g_partials->release();
+    g_chunks->release();
+    g_pre_tmp->release();
+    g_aff->release();
     for (auto& sp : g_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     g_spans.clear();
     g_spans_used = 0;
@@ -1070,7 +1079,7 @@ int msm_precompute_table(const void* d_bases, size_t n, int c, void* d_table) {
     int nwin = msm_windows_for(c);
     CQB_CUDA(cudaMemcpyAsync(d_table, d_bases, n * 64, cudaMemcpyDeviceToDevice, st));
     const size_t CHUNK = (size_t)1 << 22;
-    CQB_TRY(g_pre_tmp.ensure(std::min(n, CHUNK) * 160));
+    CQB_TRY(g_pre_tmp->ensure(std::min(n, CHUNK) * 160));
     for (int w = 1; w < nwin; w++) {
         const char* prev = (const char*)d_table + (size_t)(w - 1) * n * 64;
         char* next = (char*)d_table + (size_t)w * n * 64;
@@ -1078,7 +1087,7 @@ int msm_precompute_table(const void* d_bases, size_t n, int c, void* d_table) {
             size_t m = std::min(CHUNK, n - off);
             size_t threads = (m + PRE_RUN - 1) / PRE_RUN;
             msm_precompute_row_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>((const uint4*)(prev + off * 64), (uint4*)(next + off * 64), m, c,
-                                                                                          g_pre_tmp.as<uint4>());
+                                                                                          g_pre_tmp->as<uint4>());
             CQB_LAUNCHED();
         }
     }
@@ -1126,20 +1135,20 @@ static int plan_parts(const MsmShape& s, int nparts, PartPlan* pl) {
     pl->ntiles = (s.nb + 1 + SCAN_TILE - 1) / SCAN_TILE;
     pl->part_hist_words = pl->hist_words * 3 + 2 * (size_t)pl->ntiles + 8;
     pl->nbuckets = (size_t)s.nsets * s.nb;
-    CQB_TRY(g_hist.ensure((size_t)nparts * pl->part_hist_words * 4));
-    CQB_TRY(g_sorted.ensure((size_t)nparts * s.nsets * s.list_cap * 4));
-    CQB_TRY(g_buckets.ensure((size_t)nparts * pl->nbuckets * 128));
+    CQB_TRY(g_hist->ensure((size_t)nparts * pl->part_hist_words * 4));
+    CQB_TRY(g_sorted->ensure((size_t)nparts * s.nsets * s.list_cap * 4));
+    CQB_TRY(g_buckets->ensure((size_t)nparts * pl->nbuckets * 128));
     return 0;
 }
 static PartBuf part_buf(const MsmShape& s, const PartPlan& pl, int part) {
     PartBuf b;
-    b.hist = g_hist.as<uint32_t>() + (size_t)part * pl.part_hist_words;
+    b.hist = g_hist->as<uint32_t>() + (size_t)part * pl.part_hist_words;
     b.offs = b.hist + pl.hist_words;
     b.cursor = b.offs + pl.hist_words;
     b.tile_sums = b.cursor + pl.hist_words;
     b.nonempty = b.tile_sums + 2 * (size_t)pl.ntiles;  // one word (of the 8 spare ones): occupied buckets of this part
-    b.sorted = g_sorted.as<uint32_t>() + (size_t)part * s.nsets * s.list_cap;
-    b.buckets = g_buckets.as<uint4>() + (size_t)part * pl.nbuckets * 8;
+    b.sorted = g_sorted->as<uint32_t>() + (size_t)part * s.nsets * s.list_cap;
+    b.buckets = g_buckets->as<uint4>() + (size_t)part * pl.nbuckets * 8;
     return b;
 }
 
@@ -1190,7 +1199,7 @@ static int msm_sort_phase(const void* d_scalars, const uint32_t* d_idx, size_t n
     return 0;
 }
 
-// bucket accumulation variant: 0 = automatic (batched affine for large MSMs), 1 = XYZZ mixed additions, 2 = batched affine
+// bucket accumulation variant: 0 = automatic (= XYZZ: the batched-affine kernel measured slower on B200), 1 = XYZZ mixed additions, 2 = batched affine
 static int g_acc_mode = 0;
 void msm_set_accumulator(int mode) { g_acc_mode = mode; }
 static int g_aff_seg_log = 0;  // experiments: entries per stream = 2^g_aff_seg_log (0 = automatic)
@@ -1200,13 +1209,12 @@ void msm_set_affine_segment(int seg_log) { g_aff_seg_log = seg_log; }
 static int g_aff_variant = 0;  // experiments: 0 = accumulators in shared memory, K = 14 | 1 = global scratch, K = 14 | 2 = global scratch, K = 28
 void msm_set_affine_variant(int v) { g_aff_variant = v; }
 static int msm_acc_phase_affine(const void* d_bases, size_t n, const MsmShape& s, const PartPlan& pl, const PartBuf& b, cudaStream_t st) {
-    static bool attr_set = false;
-    const int K = g_aff_variant == 2 ? 28 : g_aff_variant == 3 ? 9 : 14;
-    const bool in_smem = g_aff_variant == 0 || g_aff_variant == 3;
+    bool& attr_set = g_dev->aff_attr_set;
+    const int K = g_aff_variant == 2 ? 28 : 14;
+    const bool in_smem = g_aff_variant == 0;
     const size_t smem = in_smem ? (size_t)K * 64 * AFF_THREADS : 0;
     if (!attr_set) {
         CQB_CUDA(cudaFuncSetAttribute(msm_accumulate_affine_kernel<14, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 14 * 64 * AFF_THREADS));
-        CQB_CUDA(cudaFuncSetAttribute(msm_accumulate_affine_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 64 * AFF_THREADS));
         CQB_CUDA(cudaFuncSetAttribute(msm_merge_big_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MERGE_BIG_AFF_THREADS * 128));
         attr_set = true;
     }
@@ -1222,16 +1230,16 @@ static int msm_acc_phase_affine(const void* d_bases, size_t n, const MsmShape& s
     const size_t nsub = (size_t)s.nsets * cpw, nthreads = (size_t)s.nsets * tpw;
     const uint32_t big_cap = (uint32_t)(s.nsets * (cpw / MERGE_LONG + 2));
     // head, tail: 64 B per sub-chunk; baff: 64 B per bucket; parked products: 32 B per stream; current bucket: 4 B per stream
-    const size_t head_b = nsub * 64, baff_b = pl.nbuckets * 64, pre_b = nthreads * K * 32, cur_b = nthreads * K * 4;
+    const size_t head_b = nsub * 64, baff_b = pl.nbuckets * 64, pre_b = nthreads * K * 32, cur_b = (nthreads * K * 4 + 15) / 16 * 16;
     const size_t acc_b = in_smem ? 0 : nthreads * K * 64;
-    CQB_TRY(g_aff.ensure(2 * head_b + baff_b + pre_b + acc_b + cur_b + 16 + (size_t)big_cap * 8));
-    uint4* head = g_aff.as<uint4>();
+    CQB_TRY(g_aff->ensure(2 * head_b + baff_b + pre_b + acc_b + cur_b + 16 + (size_t)big_cap * 8));
+    uint4* head = g_aff->as<uint4>();
     uint4* tail = head + nsub * 4;
     uint4* baff = tail + nsub * 4;
     uint4* prefix = baff + pl.nbuckets * 4;
     uint4* accs = prefix + nthreads * K * 2;
     uint32_t* cur = (uint32_t*)(accs + acc_b / 16);
-    uint32_t* big_count = cur + nthreads * K;
+    uint32_t* big_count = cur + cur_b / 4;
     uint2* big_list = (uint2*)(big_count + 4);
     CQB_CUDA(cudaMemsetAsync(b.buckets, 0, pl.nbuckets * 128, st));
     CQB_CUDA(cudaMemsetAsync(big_count, 0, 16, st));
@@ -1241,10 +1249,9 @@ static int msm_acc_phase_affine(const void* d_bases, size_t n, const MsmShape& s
     const unsigned grid = (unsigned)((nthreads + AFF_THREADS - 1) / AFF_THREADS);
 #define AFF_LAUNCH(KK, SM)                                                                                                              \
     msm_accumulate_affine_kernel<KK, SM><<<grid, AFF_THREADS, smem, st>>>((const uint4*)d_bases, b.sorted, b.offs, b.hist, s, seg_log, cpw, tpw, \
-                                                                         baff, head, tail, prefix, cur, accs, getenv("CQB_AFF_FAKEINV") ? 1 : 0)
+                                                                         baff, head, tail, prefix, cur, accs)
     if (g_aff_variant == 0) AFF_LAUNCH(14, true);
     else if (g_aff_variant == 1) AFF_LAUNCH(14, false);
-    else if (g_aff_variant == 3) AFF_LAUNCH(9, true);
     else AFF_LAUNCH(28, false);
 #undef AFF_LAUNCH
     CQB_LAUNCHED();
@@ -1268,7 +1275,7 @@ static int msm_acc_phase(const void* d_bases, size_t n, const MsmShape& s, const
     size_t entries = (size_t)n * s.nwin;
     // batched affine: the sorted entries must leave bit 31 free for the first-of-bucket mark
     const bool idx_fits = s.single ? ((size_t)s.nwin * s.table_n < ((size_t)1 << 30)) : true;
-    if (idx_fits && (g_acc_mode == 2 || (g_acc_mode == 0 && entries >= ((size_t)1 << 24)))) return msm_acc_phase_affine(d_bases, n, s, pl, b, st);
+    if (idx_fits && g_acc_mode == 2) return msm_acc_phase_affine(d_bases, n, s, pl, b, st);  // measured slower than XYZZ: opt-in only
     int seg_log = 8;
     while (seg_log > 6 && (entries >> seg_log) < 1000000) seg_log--;
     while (seg_log > 4 && (entries >> seg_log) < 150000) seg_log--;
@@ -1276,8 +1283,8 @@ static int msm_acc_phase(const void* d_bases, size_t n, const MsmShape& s, const
     uint32_t cpw = (uint32_t)((list_len + ((size_t)1 << seg_log) - 1) >> seg_log);  // chunks per set (upper bound)
     size_t nchunks = (size_t)s.nsets * cpw;
     uint32_t big_cap = (uint32_t)(s.nsets * (cpw / MERGE_LONG + 2));
-    CQB_TRY(g_chunks.ensure(nchunks * 256 + 16 + (size_t)big_cap * 8));
-    uint4* head = g_chunks.as<uint4>();
+    CQB_TRY(g_chunks->ensure(nchunks * 256 + 16 + (size_t)big_cap * 8));
+    uint4* head = g_chunks->as<uint4>();
     uint4* tail = head + nchunks * 8;
     uint32_t* big_count = (uint32_t*)(tail + nchunks * 8);
     uint2* big_list = (uint2*)(big_count + 4);
@@ -1315,17 +1322,17 @@ static int msm_finish(const MsmShape& s, int nparts, void* d_out) {  // nparts i
     tpw = std::max<uint32_t>(tpw, (uint32_t)RED_CTA);    // pad: threads with t * ch >= nb idle
     uint32_t cps = (tpw + RED_CTA - 1) / RED_CTA;  // CTA partials per set
     uint32_t lvl1 = (cps + 2047) / 2048;           // tree-sum levels over them
-    CQB_TRY(g_partials.ensure(((size_t)s.nsets * (cps + lvl1 + 1) + 1) * 128));
-    uint4* partials = g_partials.as<uint4>();
+    CQB_TRY(g_partials->ensure(((size_t)s.nsets * (cps + lvl1 + 1) + 1) * 128));
+    uint4* partials = g_partials->as<uint4>();
     uint4* sums1 = partials + (size_t)s.nsets * cps * 8;
     uint4* wins = sums1 + (size_t)s.nsets * lvl1 * 8;
     int h = prof_begin(5, st);
     if (nparts > 1) {
-        msm_fold_parts_kernel<<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>(g_buckets.as<uint4>(), nbuckets, nparts);
+        msm_fold_parts_kernel<<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>(g_buckets->as<uint4>(), nbuckets, nparts);
         CQB_LAUNCHED();
         nparts = 1;
     }
-    msm_reduce_kernel<<<(unsigned)(s.nsets * cps), RED_CTA, 0, st>>>(g_buckets.as<uint4>(), s, tpw, ch, nparts, nbuckets * 8, partials);
+    msm_reduce_kernel<<<(unsigned)(s.nsets * cps), RED_CTA, 0, st>>>(g_buckets->as<uint4>(), s, tpw, ch, nparts, nbuckets * 8, partials);
     CQB_LAUNCHED();
     prof_end(h, st);
     h = prof_begin(6, st);
