@@ -34,9 +34,33 @@ os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "SHA2-CQ prove ms; BN254 MSM Mpts/s @2^24; Fr NTT Gelem/s @2^24; 1/2/4/8 GPU"
 UNIT = "Mpts/s (BN254 G1 MSM @2^24)"
-MAD32_PER_POINT = 21760           # 16 windows x 10 modmul x 136 MAD32
-INT_PEAK_TMAD32 = 8.51            # measured: profiles/r01_int_pipe_calibration.md (carry-chained IMAD.WIDE.U32.X)
+MAD32_PER_POINT = 21760           # SURVEY.md §8(d), the PINNED algorithm: 16 windows x 10 modmul x 136 MAD32
+MAD32_PER_XYZZ_ADD = 1232         # what the kernel executes per bucket addition: 6 mul x 136 + 2 sqr x 108 + one fused a*b-c*d x 200
 SEED_BASES, SEED_SCALARS, SEED_NTT = 0xC0FFEE, 0x5EED0001, 0x5EED0002
+
+
+def int_peak():
+    """integer-multiplier roofline denominator (T MAD32/s): profiles/INT_PEAK.json — the IMAD.WIDE issue limit (32 per clk per SM)
+    at the clock measured under load, calibrated with >= 30 ms probes (MEASURED_PEAKS.json holds no integer figure)"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "INT_PEAK.json")))
+        return float(d["peak_tmad32"]), "profiles/INT_PEAK.json: " + d["peak_basis"][:140]
+    except Exception:
+        return 148 * 32 * 1.965e9 / 1e12, "148 SMs x 32 IMAD.WIDE/clk/SM x 1.965 GHz (profiles/INT_PEAK.json missing)"
+
+
+def golden_point(log_n):
+    """the N=1 result of the seeded benchmark MSM, committed under tests/golden/ (checked against the CPU oracle by
+    tests/test_gpu_bigsize_oracle.py::test_msm_2p24_full_vs_oracle, same seeds): every run at every N must reproduce it"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_points.json")))
+        return d.get(str(log_n))
+    except Exception:
+        return None
+
+
+def point_hex(aff):
+    return {"x": "0x" + "".join(f"{int(v):016x}" for v in aff[3::-1]), "y": "0x" + "".join(f"{int(v):016x}" for v in aff[7:3:-1])}
 
 
 def measured_peaks():
@@ -93,16 +117,19 @@ def run_reference(args):
 
     O.build()
     threads = O.hw_threads()
-    # size the sample so that one step is a few seconds
-    probe_n = 1 << 14
+    # each step is a bounded sample of the 2^log_n workload, sized so that the whole --steps/--warmup run ends in about three minutes;
+    # with few enough steps (<= ~10 on a 16-core host) the sample IS the full workload
+    t_start = time.perf_counter()
+    probe_n = 1 << 16
     sc = O.synth_scalars(SEED_SCALARS, probe_n)
     bs = O.synth_bases(SEED_BASES, probe_n, threads)
     t = time.perf_counter()
     O.best_multiexp(sc, bs, threads)
     dt = max(time.perf_counter() - t, 1e-4)
-    rate = probe_n / dt
+    rate = probe_n / dt * 1.15  # larger inputs run faster per point (c = ceil(ln chunk) grows)
+    per_step_budget = 170.0 / max(1, args.steps + args.warmup)
     log_s = 16
-    while log_s < args.ref_max_log and (1 << (log_s + 1)) / rate < 4.0:
+    while log_s < min(args.log_n, args.ref_max_log) and (1 << (log_s + 1)) / rate <= per_step_budget:
         log_s += 1
     n = 1 << log_s
     sc = O.synth_scalars(SEED_SCALARS, n)
@@ -111,17 +138,36 @@ def run_reference(args):
         O.best_multiexp(sc, bs, threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.best_multiexp(sc, bs, threads)
+        _, aff = O.best_multiexp(sc, bs, threads)
     dt = (time.perf_counter() - t0) / args.steps
     val = n / dt / 1e6
+    full = None
+    if log_s == args.log_n:
+        full = {"log_n": args.log_n, "seconds": dt, "mpts": val, "point": point_hex(aff), "matches_golden": None}
+    elif time.perf_counter() - t_start < 200.0 and (1 << args.log_n) / (val * 1e6) < 60.0:
+        # one run at the full size, outside the timed steps, so that the like-for-like ratio is on record
+        nf = 1 << args.log_n
+        scf = O.synth_scalars(SEED_SCALARS, nf)
+        bsf = O.synth_bases(SEED_BASES, nf, threads)
+        t1 = time.perf_counter()
+        _, aff = O.best_multiexp(scf, bsf, threads)
+        df = time.perf_counter() - t1
+        full = {"log_n": args.log_n, "seconds": df, "mpts": nf / df / 1e6, "point": point_hex(aff), "matches_golden": None}
+    if full is not None:
+        g = golden_point(args.log_n)
+        full["matches_golden"] = None if g is None else bool(g == full["point"])
+    workload = f"BN254 G1 MSM 2^{args.log_n} uniform scalars x distinct points (BASELINE.json configs[1])"
+    sample = (f"the full 2^{args.log_n} workload per step" if log_s == args.log_n else
+              f"first 2^{log_s} points of the 2^{args.log_n} workload per step (bounded so that {args.steps}+{args.warmup} steps end within minutes)")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64 limbs (256-bit modular integer)", "data": "synthetic",
-        "config": {"workload": f"BN254 G1 MSM, uniform scalars x distinct points, bounded sample 2^{log_s} of the 2^{args.log_n} workload",
+        "config": {"workload": workload, "sample": sample,
                    "algorithm": "best_multiexp: c=ceil(ln chunk) unsigned windows, len/threads chunks (arithmetic.rs:13-159)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"2^{log_s} points per step, {args.steps} steps; C restatement of the reference (Rust toolchain absent)"},
+                         "sample": sample + f"; {args.steps} steps; C restatement of the reference (Rust toolchain absent)"},
+        "full_size_check": full,
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -142,7 +188,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-prove", action="store_true")
     ap.add_argument("--prove-k", type=lambda v: [int(x) for x in v.split(",")], default=[16, 20])
-    ap.add_argument("--ref-max-log", type=int, default=22)
+    ap.add_argument("--ref-max-log", type=int, default=26)
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--no-precompute", action="store_true", help="windowed layout on the plain bases (no per-SRS table)")
     args = ap.parse_args()
@@ -238,10 +284,28 @@ def main():
     ph_avg /= max(1, len(acc_ms))
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
     result_e2e = step_e2e().copy()
+    # the same call from PAGEABLE host memory (what a Rust Vec<Fr> is): the library stages it through pinned buffers with host
+    # threads, part by part, under the kernels of the previous part
+    scal_pageable = np.empty((per, 4), np.uint64)
+    L.check(lib.cqb_memcpy_d2h(scal_pageable.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(scal_t.data_ptr()), per * 32))
+
+    def step_pageable():
+        return msm.msm_host_ptr(scal_pageable.ctypes.data, per).to_affine()
+
+    ms_pageable = timed(step_pageable, max(3, args.steps // 2), 3)
+    result_pageable = step_pageable().copy()
     if sampler:
         sampler.stop_flag = True
         sampler.join()
     assert np.array_equal(result_dev, result_e2e), "device-resident and host-pointer paths disagree"
+    assert np.array_equal(result_dev, result_pageable), "pinned and pageable host-pointer paths disagree"
+    # parity carried by the line itself: the point this run computed, and whether it is the committed N=1 result
+    golden = golden_point(args.log_n) if not args.window_bits else golden_point(args.log_n)
+    parity = {"point": point_hex(result_dev), "golden": "tests/golden/bench_points.json" if golden else None,
+              "matches_golden": None if golden is None else bool(golden == point_hex(result_dev)),
+              "paths_agree": ["device-resident", "host pinned", "host pageable"]}
+    if golden is not None:
+        assert parity["matches_golden"], f"MSM result {parity['point']} differs from the committed N=1 point {golden} (n_gpus={world})"
 
     # windows per point actually executed: 254/c + 1 with the c the library picked (20 for the table layout at >= 2^22)
     c_tab = lib.cqb_bases_precomputed_window_bits(h.value)
@@ -250,7 +314,13 @@ def main():
     value = n_total / (ms_dev * 1e-3) / 1e6
     e2e = n_total / (ms_e2e * 1e-3) / 1e6
     t_acc = float(np.mean(acc_ms)) if acc_ms else float("nan")
-    achieved = per * MAD32_PER_POINT / (t_acc * 1e-3) / 1e12
+    peak, peak_src = int_peak()
+    executed = per * nwin_eff * MAD32_PER_XYZZ_ADD / (t_acc * 1e-3) / 1e12       # T MAD32/s the kernel really issues
+    pinned_alg = per * MAD32_PER_POINT / (t_acc * 1e-3) / 1e12                   # the same time read on SURVEY's pinned count
+    ncu_traffic = None
+    if world == 1 and args.log_n == 24 and not args.no_precompute:
+        ncu_traffic = {"bytes": 29.66e9, "source": "profiles/r01b_ncu_msm_accumulate_raw.csv (one ncu --set full capture of this launch: "
+                                                    "29.47 GB read + 0.18 GB written); not re-measured by this run"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -262,24 +332,32 @@ def main():
                    "layout": "windowed" if args.no_precompute else "single bucket set over the per-SRS precomputed table (built once at SRS registration)"},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": per * 32 * world,
                 "d2h_bytes_per_step": 80 * world, "note": "scalars in pinned host memory per step; SRS bases resident in HBM"},
+        "e2e_pageable": {"value": n_total / (ms_pageable * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_pageable,
+                         "note": "the same call with the scalars in pageable host memory (a Rust Vec<Fr>): staged through pinned buffers by "
+                                 "8 host threads per part, overlapped with the previous part's kernels"},
+        "parity": parity,
         "gpu_launches": int(launches) * args.steps,
-        "roofline": {"bound": "int", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": INT_PEAK_TMAD32,
-                     "unit": "TMAD32/s", "frac": achieved / INT_PEAK_TMAD32, "traffic": 29.66e9 if (world == 1 and args.log_n == 24 and not args.no_precompute) else None,
-                     "kernel_ms": t_acc, "algorithmic_mad32_per_point": MAD32_PER_POINT,
-                     # what the kernel really executes: windows_per_point bucket additions x (6 mul x 136 + 2 sqr x 108 + one
-                     # fused a*b-c*d x 200) MAD32 — the fraction of the multiplier peak actually in use (< 1 by construction)
-                     "executed_mad32_per_point": nwin_eff * 1232,
-                     "executed_frac": per * nwin_eff * 1232 / (t_acc * 1e-3) / 1e12 / INT_PEAK_TMAD32,
-                     "peak_source": "measured on this pool's B200: profiles/r01_int_pipe_calibration.md (MEASURED_PEAKS.json has no integer figure)",
-                     "whole_msm_frac": n_total / world * MAD32_PER_POINT / (ms_dev * 1e-3) / 1e12 / INT_PEAK_TMAD32},
+        "roofline": {"bound": "int", "kernel": "msm_accumulate_kernel", "achieved": executed, "peak": peak,
+                     "unit": "TMAD32/s", "frac": executed / peak,
+                     "traffic": ncu_traffic["bytes"] if ncu_traffic else None, "traffic_source": ncu_traffic["source"] if ncu_traffic else None,
+                     "kernel_ms": t_acc,
+                     # achieved = EXECUTED multiply-accumulates: windows_per_point bucket additions x (6 mul x 136 + 2 sqr x 108 + one
+                     # fused a*b-c*d x 200) MAD32, over the kernel's CUDA-event time; peak = IMAD.WIDE issue limit (< 1 by construction)
+                     "executed_mad32_per_point": nwin_eff * MAD32_PER_XYZZ_ADD,
+                     "peak_source": peak_src,
+                     "whole_msm_frac": n_total / world * nwin_eff * MAD32_PER_XYZZ_ADD / (ms_dev * 1e-3) / 1e12 / peak,
+                     # the same kernel time read against the algorithm SURVEY.md 8(d) pinned for grading (16 windows x 10 modmul x 136):
+                     # above 1 because the kernel does less work than that algorithm (13 windows, cheaper squarings, one fused reduction)
+                     "vs_pinned_algorithm": {"mad32_per_point": MAD32_PER_POINT, "achieved": pinned_alg, "frac": pinned_alg / peak,
+                                             "whole_msm_frac": n_total / world * MAD32_PER_POINT / (ms_dev * 1e-3) / 1e12 / peak,
+                                             "vs_nominal_18p6T": n_total / world * MAD32_PER_POINT / (ms_dev * 1e-3) / 1e12 / 18.6}},
         # the same kernel against the HBM roofline, in the canonical schema: it is NOT bandwidth-bound (frac << 1 by design)
         "roofline_hbm": {"bound": "hbm", "kernel": "msm_accumulate_kernel",
                          "achieved": per * nwin_eff * 68 / (t_acc * 1e-3) / 1e9, "peak": measured_peaks().get("hbm_gbs", 6650.0),
                          "unit": "GB/s", "frac": per * nwin_eff * 68 / (t_acc * 1e-3) / 1e9 / measured_peaks().get("hbm_gbs", 6650.0),
-                         "traffic": 29.66e9 if (world == 1 and args.log_n == 24 and not args.no_precompute) else None,
+                         "traffic": ncu_traffic["bytes"] if ncu_traffic else None, "traffic_source": ncu_traffic["source"] if ncu_traffic else None,
                          "algorithmic_bytes_per_launch": per * nwin_eff * 68,
-                         "note": "68 B per bucket addition (64 B affine point + 4 B sorted index) x windows per point; traffic = dram read+write "
-                                 "of one ncu --set full capture of this launch (profiles/r01b_ncu_msm_accumulate_raw.csv: 29.47 GB read + 0.18 GB written)",
+                         "note": "68 B per bucket addition (64 B affine point + 4 B sorted index) x windows per point",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in measured_peaks() else "fallback 6650 GB/s"},
         "msm_phase_ms": {k: float(v) for k, v in zip(["count", "scan", "scatter", "accumulate", "merge", "reduce", "window_sum", "final"], ph_avg)},
     }
@@ -317,8 +395,8 @@ def main():
                        "e2e_value": n / (ms_ntt_e2e * 1e-3) / 1e9, "e2e_ms": ms_ntt_e2e,
                        "roofline_hbm": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                                         "algorithmic_bytes_per_elem": 64},
-                       "roofline_int": {"bound": "int", "achieved": int_t, "peak": INT_PEAK_TMAD32, "unit": "TMAD32/s",
-                                        "frac": int_t / INT_PEAK_TMAD32}}
+                       "roofline_int": {"bound": "int", "achieved": int_t, "peak": int_peak()[0], "unit": "TMAD32/s",
+                                        "frac": int_t / int_peak()[0]}}
         del a_t
 
     # ---- N > 1: the distributed four-step NTT (sharded.ShardedNTT), 2^ntt_log_n elements block-distributed over the ranks in
@@ -346,14 +424,24 @@ def main():
             exchange += ", each group's exchange overlapped with the next group's transform"
         else:
             sn._groups = 0
-        del ref_out
+        # parity: this rank's block of the distributed transform must have the limbs of the single-GPU transform of the WHOLE
+        # vector (every rank regenerates the seeded input and transforms it alone: 2^24 elements are 512 MiB and 3.7 ms)
+        full_t = torch.empty(n * 32, dtype=torch.uint8, device=dev)
+        L.check(lib.cqb_synth_scalars_dev(SEED_NTT, 0, n, ctypes.c_void_p(full_t.data_ptr())))
+        L.check(lib.cqb_ntt_bn254_fr_dev(ctypes.c_void_p(full_t.data_ptr()), L.p64(sn._limbs(sn.omega)), k))
+        blk_ok = torch.tensor([1 if torch.equal(ref_out, full_t[rank * per_ntt * 32:(rank + 1) * per_ntt * 32]) else 0], device=dev)
+        dist.all_reduce(blk_ok, op=dist.ReduceOp.MIN)
+        ntt_parity = bool(int(blk_ok.item()) == 1)
+        assert ntt_parity, "distributed NTT block differs from the single-GPU transform"
+        del ref_out, full_t
         ms_ntt = timed(lambda: sn.forward(x_t), args.steps, args.warmup)
         int_t = (n / 2) * k * 136 / (ms_ntt * 1e-3) / 1e12
         line["ntt"] = {"metric": f"Fr NTT Gelem/s @2^{k}", "value": n / (ms_ntt * 1e-3) / 1e9, "ms": ms_ntt, "n_gpus": world, "scaling": "strong",
                        "algorithm": "distributed four-step: transpose, " + exchange + ", two batched local transforms with the "
                                     "gather / twiddle / transposed store fused in; block-distributed natural order in and out",
-                       "roofline_int": {"bound": "int", "achieved": int_t, "peak": INT_PEAK_TMAD32 * world, "unit": "TMAD32/s",
-                                        "frac": int_t / (INT_PEAK_TMAD32 * world)}}
+                       "parity": {"every_rank_block_equals_single_gpu_transform": ntt_parity, "overlap_variant_equals_plain": bool(int(same.item()) == 1)},
+                       "roofline_int": {"bound": "int", "achieved": int_t, "peak": int_peak()[0] * world, "unit": "TMAD32/s",
+                                        "frac": int_t / (int_peak()[0] * world)}}
         del x_t
 
     # ---- "SHA2-CQ prove ms": the synthetic CQ-prover-shaped op list of SURVEY.md §8(d) (no SHA circuit exists in the

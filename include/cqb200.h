@@ -50,6 +50,14 @@ CQB_API int cqb_device_count(void);
 /* run all subsequent work on the caller's CUDA stream (cudaStream_t), e.g. torch.cuda.current_stream().cuda_stream;
  * NULL restores the library's own stream */
 CQB_API int cqb_set_stream(void* cuda_stream);
+/* ONE process, SEVERAL GPUs (SURVEY.md 8(b) `cqb_init(int n_devices)`; cqb_init(device) above keeps the one-process-per-GPU form
+ * bench.py is launched in): devices 0 .. n_devices-1, device 0 primary (NTTs, polynomial helpers and plain base sets live there).
+ * A base set registered with cqb_bases_register_sharded is split by contiguous point range over the devices — the
+ * decomposition best_multiexp makes across threads, halo2_proofs/src/arithmetic.rs:137-153 — and every MSM over it runs on
+ * all of them: one host thread per device, the partial points gathered on device 0 with peer copies and folded there
+ * (arithmetic.rs:153). No torch, no NCCL on this path. */
+CQB_API int cqb_init_multi(int n_devices);
+CQB_API int cqb_active_devices(void);
 CQB_API int cqb_sync(void);
 CQB_API unsigned long long cqb_launch_count(void); /* kernels launched by this library so far (bench.py's gpu_launches) */
 
@@ -57,6 +65,7 @@ CQB_API unsigned long long cqb_launch_count(void); /* kernels launched by this l
  *      and TableSRS { g1, g1_lagrange, g_lagrange_opening_at_0 } (:42-47) as MSM operands ------------------------- */
 CQB_API int cqb_bases_register(const uint64_t* affine_xy, size_t n, cqb_bases_t* out);        /* host -> device copy */
 CQB_API int cqb_bases_register_device(const void* d_affine_xy, size_t n, cqb_bases_t* out);  /* adopt device memory, no copy */
+CQB_API int cqb_bases_register_sharded(const uint64_t* affine_xy, size_t n, cqb_bases_t* out); /* split over the devices of cqb_init_multi */
 CQB_API int cqb_bases_free(cqb_bases_t h);
 CQB_API size_t cqb_bases_len(cqb_bases_t h);
 /* points [offset, offset + n) of a registered set back to the host (ParamsKZG::write_custom, poly/kzg/commitment.rs:366-380)
@@ -78,6 +87,14 @@ CQB_API int cqb_bases_precomputed_window_bits(cqb_bases_t h); /* c of the table,
 CQB_API int cqb_msm_bn254_g1(cqb_bases_t b, size_t offset, const uint64_t* scalars, size_t n, uint64_t out_xy[8], int* is_inf);
 /* same, scalars already in device memory (bench "value": inputs resident in HBM) */
 CQB_API int cqb_msm_bn254_g1_dev(cqb_bases_t b, size_t offset, const void* d_scalars, size_t n, uint64_t out_xy[8], int* is_inf);
+/* sharded base set, scalars already resident: d_scalars[i] points, on shard i's device, at the scalars of that shard's point
+ * range intersected with [offset, offset + n) (shard ranges: n / devices points each, the first n % devices one more) */
+CQB_API int cqb_msm_bn254_g1_multi_dev(cqb_bases_t b, size_t offset, const void* const* d_scalars, size_t n, uint64_t out_xy[8], int* is_inf);
+/* device memory on the device of slot `slot` (cqb_init_multi) for callers without a CUDA binding of their own */
+CQB_API int cqb_dev_alloc_on(int slot, size_t bytes, void** d_out);
+CQB_API int cqb_dev_free_on(int slot, void* d);
+CQB_API int cqb_memcpy_h2d_on(int slot, void* d_dst, const void* h_src, size_t bytes);
+CQB_API int cqb_synth_scalars_dev_on(int slot, uint64_t seed, size_t start, size_t n, void* d_out);
 /* `batch` MSMs over the same base range in one pass: scalars = batch contiguous vectors of n scalars, out_xy = batch x 8
  * limbs, is_inf = batch flags. What the prover's commitment loops are (`advice.iter().map(|poly| params.commit_lagrange(poly))`
  * plonk/prover.rs:356-360; the h pieces vanishing/prover.rs:101-105): with a precomputed table every MSM gets its own bucket

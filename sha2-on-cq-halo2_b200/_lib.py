@@ -22,6 +22,14 @@ SYMBOLS = [
     ("cqb_last_error", ctypes.c_char_p, []),
     ("cqb_device_count", _int, []),
     ("cqb_set_stream", _int, [_vp]),
+    ("cqb_init_multi", _int, [_int]),
+    ("cqb_active_devices", _int, []),
+    ("cqb_bases_register_sharded", _int, [u64p, _sz, u64p]),
+    ("cqb_msm_bn254_g1_multi_dev", _int, [_u64, _sz, ctypes.POINTER(_vp), _sz, u64p, _ip]),
+    ("cqb_dev_alloc_on", _int, [_int, _sz, ctypes.POINTER(_vp)]),
+    ("cqb_dev_free_on", _int, [_int, _vp]),
+    ("cqb_memcpy_h2d_on", _int, [_int, _vp, _vp, _sz]),
+    ("cqb_synth_scalars_dev_on", _int, [_int, _u64, _sz, _sz, _vp]),
     ("cqb_sync", _int, []),
     ("cqb_launch_count", ctypes.c_ulonglong, []),
     ("cqb_bases_register", _int, [u64p, _sz, u64p]),

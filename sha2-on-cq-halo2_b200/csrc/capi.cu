@@ -123,56 +123,108 @@ int cqb_device_count(void) {
     return n;
 }
 
-int cqb_init(int device) {
-    LOCK;
-    if (g_ctx.inited && g_ctx.device == device) return 0;
-    int n = cqb_device_count();
-    if (n <= 0) return fail(CQB_E_NO_DEVICE, "no CUDA device visible (there is no CPU fallback)");
-    if (device < 0 || device >= n) return fail(CQB_E_BAD_ARG, "device %d out of range (%d visible)", device, n);
-    if (g_ctx.inited) cqb_shutdown();
+// bring up one slot on one device (the caller holds the lock and has bound the slot)
+static int init_slot(int slot, int device) {
+    tl_slot = slot;
+    Ctx& c = g_ctxs[slot];
     CQB_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     CQB_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(CQB_E_NO_DEVICE, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
-    g_ctx.device = device;
-    g_ctx.sm_count = prop.multiProcessorCount;
-    CQB_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
-    g_ctx.own_stream = true;
-    g_ctx.inited = true;
-    g_ctx.launches = 0;
+    c.device = device;
+    c.sm_count = prop.multiProcessorCount;
+    CQB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    c.own_stream = true;
+    c.inited = true;
+    c.launches = 0;
     CQB_TRY(g_out->ensure(256));
     return 0;
 }
 
+int cqb_init(int device) {
+    LOCK;
+    tl_slot = 0;
+    if (g_nslots == 1 && g_ctxs[0].inited && g_ctxs[0].device == device) return 0;
+    int n = cqb_device_count();
+    if (n <= 0) return fail(CQB_E_NO_DEVICE, "no CUDA device visible (there is no CPU fallback)");
+    if (device < 0 || device >= n) return fail(CQB_E_BAD_ARG, "device %d out of range (%d visible)", device, n);
+    if (g_nslots) cqb_shutdown();
+    CQB_TRY(init_slot(0, device));
+    g_nslots = 1;
+    return 0;
+}
+
+// SURVEY.md section 8(b) `cqb_init(int n_devices)`: ONE process drives devices 0 .. n_devices-1 (slot i = device i). Slot 0 is
+// the primary device: every single-device entry point (NTT, polynomial helpers, plain base sets) runs there; base sets
+// registered with cqb_bases_register_sharded are split by point range over all slots and their MSMs run on all of them.
+int cqb_init_multi(int n_devices) {
+    LOCK;
+    tl_slot = 0;
+    int n = cqb_device_count();
+    if (n <= 0) return fail(CQB_E_NO_DEVICE, "no CUDA device visible (there is no CPU fallback)");
+    if (n_devices < 1 || n_devices > n || n_devices > MAX_DEVICES) return fail(CQB_E_BAD_ARG, "cqb_init_multi(%d): %d devices visible, at most %d supported", n_devices, n, MAX_DEVICES);
+    if (g_nslots == n_devices && g_ctxs[0].inited && g_ctxs[0].device == 0) return 0;
+    if (g_nslots) cqb_shutdown();
+    for (int i = 0; i < n_devices; i++) {
+        int rc = init_slot(i, i);
+        if (rc) { std::string msg = g_ctxs[i].last_error; g_nslots = i; cqb_shutdown(); tl_slot = 0; g_ctxs[0].last_error = msg; return rc; }
+    }
+    g_nslots = n_devices;
+    // peer access from the primary device to the others (the partial results travel with cudaMemcpyPeerAsync either way)
+    bind_slot(0);
+    for (int i = 1; i < n_devices; i++) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, 0, i) == cudaSuccess && can) { if (cudaDeviceEnablePeerAccess(i, 0) != cudaSuccess) cudaGetLastError(); }
+        else cudaGetLastError();
+    }
+    return 0;
+}
+
+int cqb_active_devices(void) { return g_nslots; }
+
 void cqb_shutdown(void) {
     LOCK;
-    if (!g_ctx.inited) return;
-    cudaSetDevice(g_ctx.device);
-    cudaDeviceSynchronize();
-    for (auto& kv : g_bases) {
-        if (kv.second.owned) cudaFree(kv.second.d);
-        if (kv.second.table) cudaFree(kv.second.table);
+    if (!g_nslots && !g_ctxs[0].inited) return;
+    for (int slot = MAX_DEVICES - 1; slot >= 0; slot--) {
+        Ctx& c = g_ctxs[slot];
+        if (!c.inited) continue;
+        tl_slot = slot;
+        cudaSetDevice(c.device);
+        cudaDeviceSynchronize();
+        for (auto it = g_bases.begin(); it != g_bases.end();) {
+            if (it->second.slot == slot) {
+                if (it->second.owned && it->second.d) cudaFree(it->second.d);
+                if (it->second.table) cudaFree(it->second.table);
+                it = g_bases.erase(it);
+            } else ++it;
+        }
+        g_scalars->release(); g_idx->release(); g_tmp_bases->release(); g_out->release();
+        g_out_host->release();
+        g_stage->release();
+        msm_release_all();
+        if (slot == 0) {
+            g_io.release();
+            ntt_release_all();
+            gen_release_all();
+            srs_release_all();
+            ecntt_release_all();
+            poly_release_all();
+            products_release_all();
+            evalh_release_all();
+        }
+        if (g_copy->s) {
+            for (auto& e : g_copy->ev) cudaEventDestroy(e);
+            cudaStreamDestroy(g_copy->s);
+            g_copy->s = nullptr;
+        }
+        if (c.own_stream && c.stream) cudaStreamDestroy(c.stream);
+        c.stream = nullptr;
+        c.own_stream = false;
+        c.inited = false;
     }
     g_bases.clear();
-    g_scalars->release(); g_idx->release(); g_io.release(); g_tmp_bases->release(); g_out->release();
-    g_out_host->release();
-    ntt_release_all();
-    msm_release_all();
-    gen_release_all();
-    srs_release_all();
-    ecntt_release_all();
-    poly_release_all();
-    products_release_all();
-    evalh_release_all();
-    if (g_copy->s) {
-        for (auto& e : g_copy->ev) cudaEventDestroy(e);
-        cudaStreamDestroy(g_copy->s);
-        g_copy->s = nullptr;
-    }
-    if (g_ctx.own_stream && g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
-    g_ctx.stream = nullptr;
-    g_ctx.own_stream = false;
-    g_ctx.inited = false;
+    g_nslots = 0;
+    tl_slot = 0;
 }
 
 const char* cqb_last_error(void) { return g_ctx.last_error.c_str(); }
@@ -201,7 +253,11 @@ int cqb_sync(void) {
     return 0;
 }
 
-unsigned long long cqb_launch_count(void) { return g_ctx.launches; }
+unsigned long long cqb_launch_count(void) {
+    unsigned long long t = 0;
+    for (int i = 0; i < MAX_DEVICES; i++) t += g_ctxs[i].launches;
+    return t;
+}
 
 // ---- bases ------------------------------------------------------------------------------------------------------
 int cqb_bases_register(const uint64_t* affine_xy, size_t n, cqb_bases_t* out) {
@@ -226,14 +282,62 @@ int cqb_bases_register_device(const void* d_affine_xy, size_t n, cqb_bases_t* ou
     *out = h;
     return 0;
 }
+// Split n points by contiguous range over the slots of cqb_init_multi (balanced: the first n % slots shards hold one point more),
+// upload every shard to its device; `out` addresses the whole set: MSMs over it run on all devices (cqb_msm_bn254_g1,
+// cqb_msm_bn254_g1_multi_dev). With one slot this is cqb_bases_register.
+int cqb_bases_register_sharded(const uint64_t* affine_xy, size_t n, cqb_bases_t* out) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!out || (!affine_xy && n)) return fail(CQB_E_BAD_ARG, "cqb_bases_register_sharded: NULL argument");
+    if (g_nslots <= 1) return cqb_bases_register(affine_xy, n, out);
+    BaseSet parent{nullptr, n, false, nullptr, 0};
+    const size_t base = n / g_nslots, rem = n % g_nslots;
+    size_t start = 0;
+    int rc = 0;
+    for (int i = 0; i < g_nslots && rc == 0; i++) {
+        const size_t cnt = base + ((size_t)i < rem ? 1 : 0);
+        bind_slot(i);
+        void* d = nullptr;
+        if (cudaMalloc(&d, cnt ? cnt * 64 : 64) != cudaSuccess) { cudaGetLastError(); rc = fail(CQB_E_OOM, "cudaMalloc(%zu) for a bases shard on device %d failed", cnt * 64, ctx().device); break; }
+        cudaError_t e = cnt ? cudaMemcpyAsync(d, affine_xy + start * 8, cnt * 64, cudaMemcpyHostToDevice, g_ctx.stream) : cudaSuccess;
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx.stream);
+        if (e != cudaSuccess) { cudaFree(d); rc = fail(CQB_E_CUDA, "upload of a bases shard to device %d failed: %s", ctx().device, cudaGetErrorString(e)); break; }
+        cqb_bases_t h = g_next_handle++;
+        BaseSet child{d, cnt, true, nullptr, 0};
+        child.slot = i;
+        g_bases[h] = child;
+        parent.shards.push_back(h);
+        parent.shard_start.push_back(start);
+        start += cnt;
+    }
+    std::string msg = ctx().last_error;
+    bind_slot(0);
+    if (rc) {
+        for (cqb_bases_t h : parent.shards) cqb_bases_free(h);
+        g_ctxs[0].last_error = msg;
+        return rc;
+    }
+    cqb_bases_t h = g_next_handle++;
+    g_bases[h] = parent;
+    *out = h;
+    return 0;
+}
 int cqb_bases_free(cqb_bases_t h) {
     LOCK;
     auto it = g_bases.find(h);
     if (it == g_bases.end()) return fail(CQB_E_BAD_ARG, "unknown bases handle %llu", (unsigned long long)h);
+    if (!it->second.shards.empty()) {
+        std::vector<cqb_bases_t> kids = it->second.shards;
+        g_bases.erase(it);
+        for (cqb_bases_t k : kids) cqb_bases_free(k);
+        return 0;
+    }
+    bind_slot(it->second.slot);
     cudaStreamSynchronize(g_ctx.stream);
     if (it->second.owned) cudaFree(it->second.d);
     if (it->second.table) cudaFree(it->second.table);
     g_bases.erase(it);
+    bind_slot(0);
     return 0;
 }
 int cqb_bases_download(cqb_bases_t h, size_t offset, size_t n, uint64_t* affine_xy_out) {
@@ -242,6 +346,20 @@ int cqb_bases_download(cqb_bases_t h, size_t offset, size_t n, uint64_t* affine_
     auto it = g_bases.find(h);
     if (it == g_bases.end()) return fail(CQB_E_BAD_ARG, "unknown bases handle %llu", (unsigned long long)h);
     if (!affine_xy_out && n) return fail(CQB_E_BAD_ARG, "cqb_bases_download: NULL argument");
+    if (!it->second.shards.empty()) {
+        const BaseSet& ps = it->second;
+        if (offset > ps.n || n > ps.n - offset) return fail(CQB_E_LEN_MISMATCH, "download of %zu points at offset %zu exceeds the %zu registered bases", n, offset, ps.n);
+        for (size_t i = 0; i < ps.shards.size(); i++) {
+            const BaseSet& ch = g_bases[ps.shards[i]];
+            const size_t lo = std::max(offset, ps.shard_start[i]), hi = std::min(offset + n, ps.shard_start[i] + ch.n);
+            if (hi <= lo) continue;
+            bind_slot(ch.slot);
+            cudaError_t e = cudaMemcpy(affine_xy_out + (lo - offset) * 8, (const char*)ch.d + (lo - ps.shard_start[i]) * 64, (hi - lo) * 64, cudaMemcpyDeviceToHost);
+            bind_slot(0);
+            if (e != cudaSuccess) return fail(CQB_E_CUDA, "download from a bases shard failed: %s", cudaGetErrorString(e));
+        }
+        return 0;
+    }
     if (offset > it->second.n || n > it->second.n - offset) return fail(CQB_E_LEN_MISMATCH, "download of %zu points at offset %zu exceeds the %zu registered bases", n, offset, it->second.n);
     if (n) CQB_CUDA(cudaMemcpyAsync(affine_xy_out, (const char*)it->second.d + offset * 64, n * 64, cudaMemcpyDeviceToHost, g_ctx.stream));
     CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
@@ -253,6 +371,7 @@ int cqb_bases_copy_dev(cqb_bases_t h, size_t offset, size_t n, void* d_affine_xy
     auto it = g_bases.find(h);
     if (it == g_bases.end()) return fail(CQB_E_BAD_ARG, "unknown bases handle %llu", (unsigned long long)h);
     if (!d_affine_xy_out && n) return fail(CQB_E_BAD_ARG, "cqb_bases_copy_dev: NULL argument");
+    if (!it->second.shards.empty()) return fail(CQB_E_BAD_ARG, "cqb_bases_copy_dev: not available for a sharded base set (use cqb_bases_download)");
     if (offset > it->second.n || n > it->second.n - offset) return fail(CQB_E_LEN_MISMATCH, "copy of %zu points at offset %zu exceeds the %zu registered bases", n, offset, it->second.n);
     if (n) CQB_CUDA(cudaMemcpyAsync(d_affine_xy_out, (const char*)it->second.d + offset * 64, n * 64, cudaMemcpyDeviceToDevice, g_ctx.stream));
     return 0;
@@ -289,6 +408,16 @@ int cqb_bases_precompute(cqb_bases_t h, int window_bits) {
     if (it == g_bases.end()) return fail(CQB_E_BAD_ARG, "unknown bases handle %llu", (unsigned long long)h);
     BaseSet& bs = it->second;
     if (bs.n == 0) return 0;
+    if (!bs.shards.empty()) {  // every shard builds the table of its own point range, on its own device
+        int c = window_bits ? window_bits : msm_precompute_window_bits((bs.n + bs.shards.size() - 1) / bs.shards.size());
+        for (cqb_bases_t k : bs.shards) {
+            bind_slot(g_bases[k].slot);
+            int rc = cqb_bases_precompute(k, c);
+            if (rc) { std::string msg = ctx().last_error; bind_slot(0); g_ctxs[0].last_error = msg; return rc; }
+        }
+        bind_slot(0);
+        return 0;
+    }
     int c = window_bits ? window_bits : msm_precompute_window_bits(bs.n);
     if (c < 8 || c > 23) return fail(CQB_E_BAD_ARG, "precompute window bits must be 8..23 (got %d)", c);
     if (bs.table && bs.table_c == c) return 0;
@@ -310,6 +439,7 @@ int cqb_bases_precompute(cqb_bases_t h, int window_bits) {
 int cqb_bases_precomputed_window_bits(cqb_bases_t h) {
     LOCK;
     auto it = g_bases.find(h);
+    if (it != g_bases.end() && !it->second.shards.empty()) return cqb_bases_precomputed_window_bits(it->second.shards[0]);
     return (it == g_bases.end() || !it->second.table) ? 0 : it->second.table_c;
 }
 int cqb_bases_drop_precomputed(cqb_bases_t h) {
@@ -320,14 +450,163 @@ int cqb_bases_drop_precomputed(cqb_bases_t h) {
     return 0;
 }
 
+// ---- host-pointer scalars -> device, pipelined with the MSM ----------------------------------------------------------
+// A large MSM from host memory is cut into point-range parts; the transfer of part p+1 overlaps the kernels of part p.
+//   pinned memory   : one cudaMemcpyAsync per part on the copy stream.
+//   pageable memory : (what a Rust Vec<Fr> is) the driver would stage such a copy synchronously at a few GB/s, so COPY_THREADS
+//                     host threads first move the part into a pinned staging buffer (grow-only, one per device slot) and the
+//                     asynchronous copy starts from there; the staging of part p+1 runs while the GPU works on part p.
+constexpr int COPY_THREADS = 8;
+struct HostFeeder : MsmFeeder {
+    const uint64_t* src;
+    bool pinned;
+    int feed(int part, size_t lo, size_t cnt, cudaEvent_t* ready_out) override {
+        const char* from = (const char*)(src + lo * 4);
+        if (!pinned && cnt) {
+            char* stage = (char*)g_stage->p + lo * 32;
+            const size_t bytes = cnt * 32, per = (bytes / COPY_THREADS + 4095) & ~(size_t)4095;
+            std::vector<std::thread> th;
+            for (int t = 1; t < COPY_THREADS; t++) {
+                const size_t a = std::min(bytes, (size_t)t * per), b = std::min(bytes, (size_t)(t + 1) * per);
+                if (b > a) th.emplace_back([=] { memcpy(stage + a, from + a, b - a); });
+            }
+            memcpy(stage, from, std::min(bytes, per));
+            for (auto& t : th) t.join();
+            from = stage;
+        }
+        if (cnt) CQB_CUDA(cudaMemcpyAsync((char*)g_scalars->p + lo * 32, from, cnt * 32, cudaMemcpyHostToDevice, g_copy->s));
+        CQB_CUDA(cudaEventRecord(g_copy->ev[part & 3], g_copy->s));
+        *ready_out = g_copy->ev[part & 3];
+        return 0;
+    }
+};
+
+#ifndef CQB_HOST_PARTS
+#define CQB_HOST_PARTS 3
+#endif
+static int g_pageable_parts = 4;
+
+// queues `sum scalars[i] * bases[offset + i]` from HOST scalars on the current slot; the result lands in g_out (80 bytes)
+static int msm_host_enqueue(BaseSet* bs, size_t offset, const uint64_t* scalars, size_t n) {
+    CQB_TRY(g_scalars->ensure(n * 32 + 32));
+    bool pinned = false;
+    const bool large = n >= ((size_t)1 << 21);
+    if (large) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, scalars) == cudaSuccess) pinned = (attr.type == cudaMemoryTypeHost);
+        else cudaGetLastError();
+    }
+    bool staged = large && !pinned && g_pageable_parts > 1 && g_stage->ensure(n * 32) == 0;
+    if (large && (pinned || staged)) {
+        if (!g_copy->s) {
+            CQB_CUDA(cudaStreamCreateWithFlags(&g_copy->s, cudaStreamNonBlocking));
+            for (auto& e : g_copy->ev) CQB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        HostFeeder feeder;
+        feeder.src = scalars;
+        feeder.pinned = pinned;
+        const int parts = pinned ? CQB_HOST_PARTS : g_pageable_parts;  // at most 4: the feeder cycles through 4 events
+        const bool use_table = bs->table && n * 8 >= bs->n;
+        if (use_table) return msm_run_precomputed(bs->table, bs->n, bs->table_c, offset, g_scalars->p, nullptr, n, g_out->p, 1, parts, nullptr, &feeder);
+        return msm_run(bs->d, offset, g_scalars->p, nullptr, n, g_out->p, parts, nullptr, &feeder);
+    }
+    if (n) CQB_CUDA(cudaMemcpyAsync(g_scalars->p, scalars, n * 32, cudaMemcpyHostToDevice, g_ctx.stream));
+    return dispatch_msm(bs, offset, g_scalars->p, nullptr, n);
+}
+
+// ---- MSM over a SHARDED base set: one host thread per device slot (the reference's decomposition across threads,
+// arithmetic.rs:137-153), partial points gathered on the primary device with peer copies and folded there -----------------
+static PerDevice<cudaEvent_t> g_part_done;
+static int msm_sharded(BaseSet* parent, size_t offset, const uint64_t* h_scalars, const void* const* d_scalars_per_shard, size_t n,
+                       uint64_t out_xy[8], int* is_inf) {
+    const int ns = (int)parent->shards.size();
+    std::vector<int> rc(ns, 0);
+    std::vector<std::string> msg(ns);
+    std::vector<char> active(ns, 0);
+    bind_slot(0);
+    CQB_TRY(g_tmp_bases->ensure((size_t)ns * 64 + 64));
+    CQB_CUDA(cudaMemsetAsync(g_tmp_bases->p, 0, (size_t)ns * 64, g_ctx.stream));  // shards without points contribute the identity
+    CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    void* gather = g_tmp_bases->p;
+    const int dev0 = g_ctxs[0].device;
+    std::vector<std::thread> th;
+    for (int i = 0; i < ns; i++) {
+        BaseSet* child = &g_bases[parent->shards[i]];
+        const size_t c_lo = parent->shard_start[i], c_hi = c_lo + child->n;
+        const size_t lo = std::max(offset, c_lo), hi = std::min(offset + n, c_hi);
+        if (hi <= lo) continue;
+        active[i] = 1;
+        auto work = [=, &rc, &msg]() {
+            bind_slot(child->slot);
+            int r;
+            if (h_scalars) r = msm_host_enqueue(child, lo - c_lo, h_scalars + (lo - offset) * 4, hi - lo);
+            else r = dispatch_msm(child, lo - c_lo, d_scalars_per_shard[i], nullptr, hi - lo);
+            if (r == 0) {
+                cudaEvent_t& ev = g_part_done.get();
+                cudaError_t e = cudaSuccess;
+                if (!ev) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+                if (e == cudaSuccess) e = cudaMemcpyPeerAsync((char*)gather + (size_t)i * 64, dev0, g_out->p, ctx().device, 64, ctx().stream);
+                if (e == cudaSuccess) e = cudaEventRecord(ev, ctx().stream);
+                if (e != cudaSuccess) r = fail(CQB_E_CUDA, "gather of the partial point from device %d failed: %s", ctx().device, cudaGetErrorString(e));
+            }
+            rc[i] = r;
+            if (r) msg[i] = ctx().last_error;
+        };
+        if (child->slot == 0) continue;  // the primary device's shard is queued by this thread below
+        th.emplace_back(work);
+    }
+    // slot 0's own shard on the calling thread
+    for (int i = 0; i < ns; i++) {
+        BaseSet* child = &g_bases[parent->shards[i]];
+        if (!active[i] || child->slot != 0) continue;
+        const size_t c_lo = parent->shard_start[i];
+        const size_t lo = std::max(offset, c_lo), hi = std::min(offset + n, c_lo + child->n);
+        int r;
+        if (h_scalars) r = msm_host_enqueue(child, lo - c_lo, h_scalars + (lo - offset) * 4, hi - lo);
+        else r = dispatch_msm(child, lo - c_lo, d_scalars_per_shard[i], nullptr, hi - lo);
+        if (r == 0) {
+            cudaError_t e = cudaMemcpyAsync((char*)gather + (size_t)i * 64, g_out->p, 64, cudaMemcpyDeviceToDevice, g_ctx.stream);
+            if (e != cudaSuccess) r = fail(CQB_E_CUDA, "gather of the primary device's partial failed: %s", cudaGetErrorString(e));
+        }
+        rc[i] = r;
+        if (r) msg[i] = ctx().last_error;
+    }
+    for (auto& t : th) t.join();
+    bind_slot(0);
+    for (int i = 0; i < ns; i++)
+        if (rc[i]) { g_ctxs[0].last_error = msg[i]; return rc[i]; }
+    for (int i = 0; i < ns; i++) {
+        BaseSet* child = &g_bases[parent->shards[i]];
+        if (active[i] && child->slot != 0) CQB_CUDA(cudaStreamWaitEvent(g_ctx.stream, g_part_done.at(child->slot), 0));
+    }
+    CQB_TRY(g1_sum_affine_run(gather, ns, g_out->p));
+    return fetch_result(out_xy, is_inf);
+}
+
 int cqb_msm_bn254_g1_dev(cqb_bases_t b, size_t offset, const void* d_scalars, size_t n, uint64_t out_xy[8], int* is_inf) {
     LOCK;
     CQB_TRY(require_init());
     if (!out_xy || (!d_scalars && n)) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1_dev: NULL argument");
     BaseSet* bs = nullptr;
     CQB_TRY(find_bases(b, offset, n, &bs));
+    if (!bs->shards.empty()) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1_dev: sharded base set; use cqb_msm_bn254_g1_multi_dev (one scalar pointer per device)");
     CQB_TRY(dispatch_msm(bs, offset, d_scalars, nullptr, n));
     return fetch_result(out_xy, is_inf);
+}
+
+// device-resident scalars of a sharded set: d_scalars[i] holds, on shard i's device, the scalars of that shard's point range
+// intersected with [offset, offset + n)
+int cqb_msm_bn254_g1_multi_dev(cqb_bases_t b, size_t offset, const void* const* d_scalars, size_t n, uint64_t out_xy[8], int* is_inf) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!out_xy || (!d_scalars && n)) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1_multi_dev: NULL argument");
+    BaseSet* bs = nullptr;
+    CQB_TRY(find_bases(b, offset, n, &bs));
+    if (bs->shards.empty()) {
+        CQB_TRY(dispatch_msm(bs, offset, d_scalars[0], nullptr, n));
+        return fetch_result(out_xy, is_inf);
+    }
+    return msm_sharded(bs, offset, nullptr, d_scalars, n, out_xy, is_inf);
 }
 
 int cqb_msm_bn254_g1(cqb_bases_t b, size_t offset, const uint64_t* scalars, size_t n, uint64_t out_xy[8], int* is_inf) {
@@ -336,39 +615,8 @@ int cqb_msm_bn254_g1(cqb_bases_t b, size_t offset, const uint64_t* scalars, size
     if (!out_xy || (!scalars && n)) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1: NULL argument");
     BaseSet* bs = nullptr;
     CQB_TRY(find_bases(b, offset, n, &bs));
-    CQB_TRY(g_scalars->ensure(n * 32 + 32));
-    // Large MSM from PINNED host memory: cut into parts; the H2D copy of part p+1 (copy stream) overlaps the kernels of
-    // part p (compute stream). Pageable memory cannot overlap (the copy is staged synchronously), so it takes the plain path.
-#ifndef CQB_HOST_PARTS
-#define CQB_HOST_PARTS 3
-#endif
-    const int PARTS = CQB_HOST_PARTS;
-    bool pinned = false;
-    if (n >= ((size_t)1 << 21)) {
-        cudaPointerAttributes attr;
-        if (cudaPointerGetAttributes(&attr, scalars) == cudaSuccess) pinned = (attr.type == cudaMemoryTypeHost);
-        else cudaGetLastError();
-    }
-    if (pinned) {
-        if (!g_copy->s) {
-            CQB_CUDA(cudaStreamCreateWithFlags(&g_copy->s, cudaStreamNonBlocking));
-            for (auto& e : g_copy->ev) CQB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        }
-        size_t bounds[PARTS + 1];
-        msm_part_bounds(n, PARTS, true, bounds);  // the same split msm_run* makes (small first part: its copy is the exposed one)
-        bool use_table = bs->table && n * 8 >= bs->n;
-        for (int p = 0; p < PARTS; p++) {
-            size_t lo = bounds[p], cnt = bounds[p + 1] - lo;
-            if (cnt) CQB_CUDA(cudaMemcpyAsync((char*)g_scalars->p + lo * 32, scalars + lo * 4, cnt * 32, cudaMemcpyHostToDevice, g_copy->s));
-            CQB_CUDA(cudaEventRecord(g_copy->ev[p], g_copy->s));
-        }
-        // the sort of part p waits for its copy; the accumulation of part p-1 runs meanwhile on the main stream
-        if (use_table) CQB_TRY(msm_run_precomputed(bs->table, bs->n, bs->table_c, offset, g_scalars->p, nullptr, n, g_out->p, 1, PARTS, g_copy->ev));
-        else CQB_TRY(msm_run(bs->d, offset, g_scalars->p, nullptr, n, g_out->p, PARTS, g_copy->ev));
-        return fetch_result(out_xy, is_inf);
-    }
-    if (n) CQB_CUDA(cudaMemcpyAsync(g_scalars->p, scalars, n * 32, cudaMemcpyHostToDevice, g_ctx.stream));
-    CQB_TRY(dispatch_msm(bs, offset, g_scalars->p, nullptr, n));
+    if (!bs->shards.empty()) return msm_sharded(bs, offset, scalars, nullptr, n, out_xy, is_inf);
+    CQB_TRY(msm_host_enqueue(bs, offset, scalars, n));
     return fetch_result(out_xy, is_inf);
 }
 
@@ -719,6 +967,19 @@ int cqb_synth_scalars_dev(uint64_t seed, size_t start, size_t n, void* d_out) {
     if (!d_out && n) return fail(CQB_E_BAD_ARG, "cqb_synth_scalars_dev: NULL argument");
     return synth_scalars_run(seed, start, n, d_out);
 }
+int cqb_synth_scalars_dev_on(int slot, uint64_t seed, size_t start, size_t n, void* d_out) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (slot < 0 || slot >= g_nslots) return fail(CQB_E_BAD_ARG, "device slot %d out of range (%d active)", slot, g_nslots);
+    if (!d_out && n) return fail(CQB_E_BAD_ARG, "cqb_synth_scalars_dev_on: NULL argument");
+    bind_slot(slot);
+    int rc = synth_scalars_run(seed, start, n, d_out);  // a plain kernel on the slot's stream, no per-device scratch
+    if (rc == 0 && cudaStreamSynchronize(ctx().stream) != cudaSuccess) rc = fail(CQB_E_CUDA, "synth scalars on slot %d failed", slot);
+    std::string msg = ctx().last_error;
+    bind_slot(0);
+    if (rc) g_ctxs[0].last_error = msg;
+    return rc;
+}
 int cqb_synth_bases_dev(uint64_t seed, size_t start, size_t n, void* d_out) {
     LOCK;
     CQB_TRY(require_init());
@@ -955,6 +1216,40 @@ int cqb_msm_phase_ms(float* ms, int cap) {
     return msm_phase_ms(ms, cap);
 }
 
+static int check_slot(int slot) {
+    if (slot < 0 || slot >= g_nslots) return fail(CQB_E_BAD_ARG, "device slot %d out of range (%d active)", slot, g_nslots);
+    return 0;
+}
+int cqb_dev_alloc_on(int slot, size_t bytes, void** d_out) {
+    LOCK;
+    CQB_TRY(require_init());
+    CQB_TRY(check_slot(slot));
+    if (!d_out) return fail(CQB_E_BAD_ARG, "cqb_dev_alloc_on: NULL argument");
+    bind_slot(slot);
+    cudaError_t e = cudaMalloc(d_out, bytes ? bytes : 64);
+    bind_slot(0);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(CQB_E_OOM, "cudaMalloc(%zu) on slot %d failed", bytes, slot); }
+    return 0;
+}
+int cqb_dev_free_on(int slot, void* d) {
+    LOCK;
+    CQB_TRY(check_slot(slot));
+    bind_slot(slot);
+    cudaDeviceSynchronize();
+    cudaError_t e = cudaFree(d);
+    bind_slot(0);
+    if (e != cudaSuccess) return fail(CQB_E_CUDA, "cudaFree on slot %d failed: %s", slot, cudaGetErrorString(e));
+    return 0;
+}
+int cqb_memcpy_h2d_on(int slot, void* d_dst, const void* h_src, size_t bytes) {
+    LOCK;
+    CQB_TRY(check_slot(slot));
+    bind_slot(slot);
+    cudaError_t e = cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice);
+    bind_slot(0);
+    if (e != cudaSuccess) return fail(CQB_E_CUDA, "cudaMemcpy to slot %d failed: %s", slot, cudaGetErrorString(e));
+    return 0;
+}
 int cqb_msm_set_window_bits(int c) {
     LOCK;
     if (c != 0 && (c < 2 || c > 16)) return fail(CQB_E_BAD_ARG, "window bits must be 0 (auto) or 2..16");

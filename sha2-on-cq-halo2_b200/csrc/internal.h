@@ -43,13 +43,20 @@ Fr fr_from_u64x4(const uint64_t* p);
 // windowed layout; d_bases = element 0 of the base set, point id = idx ? idx[i] : offset + i
 // nparts: 0 = automatic (large MSMs are cut into point-range parts whose sort phase overlaps the previous part's bucket
 // accumulation on a second stream); ready[p] (optional, with nparts > 0): event the sort of part p waits for (H2D of its scalars)
+// feeder (optional, with nparts > 0, instead of ready): called on the enqueuing thread right before part p's sort is queued; starts
+// the transfer of the scalars [lo, lo + cnt) and returns the event their sort must wait for
+struct MsmFeeder {
+    virtual int feed(int part, size_t lo, size_t cnt, cudaEvent_t* ready_out) = 0;
+    virtual ~MsmFeeder() {}
+};
 int msm_run(const void* d_bases, size_t offset, const void* d_scalars, const uint32_t* d_idx, size_t n, void* d_out_xy_flag, int nparts = 0,
-            const cudaEvent_t* ready = nullptr);
+            const cudaEvent_t* ready = nullptr, MsmFeeder* feeder = nullptr);
 // single bucket set over a precomputed table (row w = 2^(c w) * bases), table_n points per row
 // batch > 1: d_scalars holds `batch` contiguous vectors of n scalars, d_out receives batch x 80 B; each MSM gets its own
 // bucket set, all kernels run once for the whole batch (the latency-bound tails are shared)
 int msm_run_precomputed(const void* d_table, size_t table_n, int c, size_t offset, const void* d_scalars, const uint32_t* d_idx,
-                        size_t n, void* d_out_xy_flag, int batch = 1, int nparts = 0, const cudaEvent_t* ready = nullptr);
+                        size_t n, void* d_out_xy_flag, int batch = 1, int nparts = 0, const cudaEvent_t* ready = nullptr,
+                        MsmFeeder* feeder = nullptr);
 void msm_set_parts(int p);
 void msm_set_accumulator(int mode);     // 0 auto | 1 XYZZ mixed additions | 2 batched affine
 void msm_set_affine_segment(int seg_log);

@@ -1393,13 +1393,22 @@ void msm_part_bounds(size_t n, int nparts, bool small_first, size_t* bounds) {
     bounds[nparts] = n;
 }
 
-// `ready[p]` (optional): event the sort of part p must wait for (the H2D copy of its scalars)
+static int msm_empty_out(void* d_out) {
+    static const uint32_t zero_pt[20] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0};
+    CQB_CUDA(cudaMemcpyAsync(d_out, zero_pt, sizeof(zero_pt), cudaMemcpyHostToDevice, ctx().stream));
+    return 0;
+}
+
+// `ready[p]` (optional): event the sort of part p must wait for (the H2D copy of its scalars). `feeder` (optional, instead of
+// ready): called on the enqueuing host thread right before part p's sort is queued; it starts the transfer of the part's
+// scalars and hands back the event to wait for. Its host-side work (staging pageable memory into pinned buffers) overlaps
+// the kernels of the parts already queued: the accumulation of part p-1 is queued before the feeder of part p+1 runs.
 static int msm_run_shape(const void* d_bases, const void* d_scalars, const uint32_t* d_idx, size_t n, MsmShape s, int nparts,
-                         const cudaEvent_t* ready, void* d_out) {
+                         const cudaEvent_t* ready, MsmFeeder* feeder, void* d_out) {
     cudaStream_t st = ctx().stream;
     g_spans_used = 0;
     if (nparts > MSM_MAX_PARTS) nparts = MSM_MAX_PARTS;
-    if (nparts <= 1 && !ready) {
+    if (nparts <= 1 && !ready && !feeder) {
         PartPlan pl;
         CQB_TRY(plan_parts(s, 1, &pl));
         PartBuf b = part_buf(s, pl, 0);
@@ -1407,8 +1416,9 @@ static int msm_run_shape(const void* d_bases, const void* d_scalars, const uint3
         CQB_TRY(msm_acc_phase(d_bases, n, s, pl, b, st));
         return msm_finish(s, 1, d_out);
     }
+    if (nparts < 1) nparts = 1;
     size_t bounds[MSM_MAX_PARTS + 1];
-    msm_part_bounds(n, nparts, ready != nullptr, bounds);
+    msm_part_bounds(n, nparts, ready != nullptr || feeder != nullptr, bounds);
     size_t per = 0;
     for (int p = 0; p < nparts; p++) per = std::max(per, bounds[p + 1] - bounds[p]);
     // per-part list capacity
@@ -1420,50 +1430,54 @@ static int msm_run_shape(const void* d_bases, const void* d_scalars, const uint3
     CQB_CUDA(cudaEventRecord(g_ev_start, st));  // the sort stream starts after everything already queued on the main stream
     CQB_CUDA(cudaStreamWaitEvent(g_sort_stream, g_ev_start, 0));
     int used = 0;  // parts that hold points (bucket arrays of the others are never touched and must not be summed)
+    size_t prev_lo = 0, prev_cnt = 0;
+    auto queue_acc = [&](int slot, size_t lo, size_t cnt) -> int {
+        MsmShape sp = s;
+        sp.offset = offset0 + (uint32_t)lo;
+        PartBuf b = part_buf(s, pl, slot);
+        CQB_CUDA(cudaStreamWaitEvent(st, g_ev_sorted[slot], 0));
+        return msm_acc_phase(d_bases, cnt, sp, pl, b, st);
+    };
     for (int p = 0; p < nparts; p++) {
         size_t lo = bounds[p], cnt = bounds[p + 1] - lo;
-        if (ready) CQB_CUDA(cudaStreamWaitEvent(g_sort_stream, ready[p], 0));
+        if (feeder) {
+            cudaEvent_t ev = nullptr;
+            CQB_TRY(feeder->feed(p, lo, cnt, &ev));
+            if (ev) CQB_CUDA(cudaStreamWaitEvent(g_sort_stream, ev, 0));
+        } else if (ready) {
+            CQB_CUDA(cudaStreamWaitEvent(g_sort_stream, ready[p], 0));
+        }
         if (cnt == 0) continue;
         MsmShape sp = s;
         sp.offset = offset0 + (uint32_t)lo;
         PartBuf b = part_buf(s, pl, used);
         CQB_TRY(msm_sort_phase((const char*)d_scalars + lo * 32, d_idx ? d_idx + lo : nullptr, cnt, sp, pl, b, g_sort_stream));
         CQB_CUDA(cudaEventRecord(g_ev_sorted[used], g_sort_stream));
+        if (used > 0) CQB_TRY(queue_acc(used - 1, prev_lo, prev_cnt));  // the previous part's accumulation, under this part's sort
+        prev_lo = lo;
+        prev_cnt = cnt;
         used++;
     }
-    used = 0;
-    for (int p = 0; p < nparts; p++) {
-        size_t lo = bounds[p], cnt = bounds[p + 1] - lo;
-        if (cnt == 0) continue;
-        MsmShape sp = s;
-        sp.offset = offset0 + (uint32_t)lo;
-        PartBuf b = part_buf(s, pl, used);
-        CQB_CUDA(cudaStreamWaitEvent(st, g_ev_sorted[used], 0));
-        CQB_TRY(msm_acc_phase(d_bases, cnt, sp, pl, b, st));
-        used++;
-    }
+    if (used > 0) CQB_TRY(queue_acc(used - 1, prev_lo, prev_cnt));
+    if (used == 0) return msm_empty_out(d_out);
     return msm_finish(s, used, d_out);
 }
 
-static int msm_empty(void* d_out) {
-    static const uint32_t zero_pt[20] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0};
-    CQB_CUDA(cudaMemcpyAsync(d_out, zero_pt, sizeof(zero_pt), cudaMemcpyHostToDevice, ctx().stream));
-    return 0;
-}
+static int msm_empty(void* d_out) { return msm_empty_out(d_out); }
 
 // windowed layout: sum_i scalars[i] * bases[idx ? idx[i] : offset + i]
 int msm_run(const void* d_bases, size_t offset, const void* d_scalars, const uint32_t* d_idx, size_t n, void* d_out, int nparts,
-            const cudaEvent_t* ready) {
+            const cudaEvent_t* ready, MsmFeeder* feeder) {
     if (n == 0) return msm_empty(d_out);  // best_multiexp of empty slices returns the identity
     if (n > ((size_t)1 << 30)) return fail(CQB_E_BAD_SIZE, "MSM of %zu points exceeds the supported 2^30", n);
     MsmShape s = windowed_shape(n);
     s.offset = (uint32_t)offset;
-    return msm_run_shape(d_bases, d_scalars, d_idx, n, s, nparts > 0 ? nparts : auto_parts(n, s, d_idx), ready, d_out);
+    return msm_run_shape(d_bases, d_scalars, d_idx, n, s, nparts > 0 ? nparts : auto_parts(n, s, d_idx), ready, feeder, d_out);
 }
 
 // single-set layout over a precomputed table of `table_n` points per row built with window bits c
 int msm_run_precomputed(const void* d_table, size_t table_n, int c, size_t offset, const void* d_scalars, const uint32_t* d_idx, size_t n,
-                        void* d_out, int batch, int nparts, const cudaEvent_t* ready) {
+                        void* d_out, int batch, int nparts, const cudaEvent_t* ready, MsmFeeder* feeder) {
     if (n == 0) {
         for (int b = 0; b < batch; b++) CQB_TRY(msm_empty((char*)d_out + (size_t)b * 80));
         return 0;
@@ -1480,7 +1494,7 @@ int msm_run_precomputed(const void* d_table, size_t table_n, int c, size_t offse
     s.list_cap = n * (size_t)s.nwin;
     if (s.list_cap >= ((size_t)1 << 32) || (size_t)s.nwin * table_n >= ((size_t)1 << 31))
         return fail(CQB_E_BAD_SIZE, "precomputed MSM: %zu x %d entries exceed the 32-bit index range", n, s.nwin);
-    return msm_run_shape(d_table, d_scalars, d_idx, n, s, nparts > 0 ? nparts : auto_parts(n, s, d_idx), ready, d_out);
+    return msm_run_shape(d_table, d_scalars, d_idx, n, s, nparts > 0 ? nparts : auto_parts(n, s, d_idx), ready, feeder, d_out);
 }
 
 int g1_sum_affine_run(const void* d_points, size_t n, void* d_out) {
