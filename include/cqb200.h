@@ -87,6 +87,10 @@ CQB_API int cqb_bases_precomputed_window_bits(cqb_bases_t h); /* c of the table,
 CQB_API int cqb_msm_bn254_g1(cqb_bases_t b, size_t offset, const uint64_t* scalars, size_t n, uint64_t out_xy[8], int* is_inf);
 /* same, scalars already in device memory (bench "value": inputs resident in HBM) */
 CQB_API int cqb_msm_bn254_g1_dev(cqb_bases_t b, size_t offset, const void* d_scalars, size_t n, uint64_t out_xy[8], int* is_inf);
+/* the same two calls with the result left on the device (80 bytes at d_out_xy_flag: affine x||y, then a uint32 identity flag),
+ * queued on the library's stream and NOT waited for: a multi-process caller all-gathers its partial straight from there */
+CQB_API int cqb_msm_bn254_g1_dev_to(cqb_bases_t b, size_t offset, const void* d_scalars, size_t n, void* d_out_xy_flag);
+CQB_API int cqb_msm_bn254_g1_to(cqb_bases_t b, size_t offset, const uint64_t* scalars, size_t n, void* d_out_xy_flag);
 /* sharded base set, scalars already resident: d_scalars[i] points, on shard i's device, at the scalars of that shard's point
  * range intersected with [offset, offset + n) (shard ranges: n / devices points each, the first n % devices one more) */
 CQB_API int cqb_msm_bn254_g1_multi_dev(cqb_bases_t b, size_t offset, const void* const* d_scalars, size_t n, uint64_t out_xy[8], int* is_inf);
@@ -110,6 +114,7 @@ CQB_API int cqb_msm_bn254_g1_sparse(cqb_bases_t b, const uint32_t* idx, const ui
 /* sum of n affine points (host): the final fold of per-GPU partial results of a point-range-sharded MSM — the
  * multi-GPU analogue of results.iter().fold(identity, |a, b| a + b), arithmetic.rs:153 */
 CQB_API int cqb_g1_sum_affine(const uint64_t* affine_xy, size_t n, uint64_t out_xy[8], int* is_inf);
+CQB_API int cqb_g1_sum_affine_dev(const void* d_affine_xy, size_t n, uint64_t out_xy[8], int* is_inf); /* the partials already on the device (all-gather output) */
 
 /* ---- NTT: replaces best_fft::<Fr> (halo2_proofs/src/arithmetic.rs:171-234) and its EvaluationDomain wrappers ---- */
 /* in place, natural order in and out: a[k] <- sum_j a[j] omega^(jk); n = 1 << log_n (arithmetic.rs:184) */

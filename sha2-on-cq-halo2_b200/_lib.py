@@ -48,6 +48,9 @@ SYMBOLS = [
     ("cqb_msm_bn254_g1_host", _int, [u64p, u64p, _sz, u64p, _ip]),
     ("cqb_msm_bn254_g1_sparse", _int, [_u64, u32p, u64p, _sz, u64p, _ip]),
     ("cqb_g1_sum_affine", _int, [u64p, _sz, u64p, _ip]),
+    ("cqb_g1_sum_affine_dev", _int, [_vp, _sz, u64p, _ip]),
+    ("cqb_msm_bn254_g1_dev_to", _int, [_u64, _sz, _vp, _sz, _vp]),
+    ("cqb_msm_bn254_g1_to", _int, [_u64, _sz, u64p, _sz, _vp]),
     ("cqb_ntt_bn254_fr", _int, [u64p, u64p, _u32]),
     ("cqb_ntt_bn254_fr_dev", _int, [_vp, u64p, _u32]),
     ("cqb_ntt_bn254_fr_batch_dev", _int, [_vp, u64p, _u32, _u32]),

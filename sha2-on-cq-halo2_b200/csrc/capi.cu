@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <map>
+#include <condition_variable>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -90,7 +91,7 @@ static cqb_bases_t g_next_handle = 1;
 static PerDevice<Scratch> g_scalars, g_idx, g_tmp_bases, g_out;
 static Scratch g_io;
 static PerDevice<Pinned> g_out_host;
-struct CopyStream { cudaStream_t s = nullptr; cudaEvent_t ev[4]; };  // H2D of part p+1 overlaps the kernels of part p (host-pointer MSM)
+struct CopyStream { cudaStream_t s = nullptr; cudaEvent_t ev[8]; };  // H2D of part p+1 overlaps the kernels of part p (host-pointer MSM)
 static PerDevice<CopyStream> g_copy;
 static PerDevice<Pinned> g_stage;  // pinned staging ring for pageable host scalars
 
@@ -395,10 +396,11 @@ static int find_bases(cqb_bases_t h, size_t offset, size_t n, BaseSet** out) {
 
 // picks the layout: the precomputed single-set table when it exists and the MSM covers a good part of the set
 // (its bucket count is sized for the whole set), else the windowed layout on the plain bases
-static int dispatch_msm(BaseSet* bs, size_t offset, const void* d_scalars, const uint32_t* d_idx, size_t n) {
+static int dispatch_msm(BaseSet* bs, size_t offset, const void* d_scalars, const uint32_t* d_idx, size_t n, void* d_out = nullptr) {
+    if (!d_out) d_out = g_out->p;
     if (bs->table && n * 8 >= bs->n)
-        return msm_run_precomputed(bs->table, bs->n, bs->table_c, offset, d_scalars, d_idx, n, g_out->p);
-    return msm_run(bs->d, offset, d_scalars, d_idx, n, g_out->p);
+        return msm_run_precomputed(bs->table, bs->n, bs->table_c, offset, d_scalars, d_idx, n, d_out);
+    return msm_run(bs->d, offset, d_scalars, d_idx, n, d_out);
 }
 
 int cqb_bases_precompute(cqb_bases_t h, int window_bits) {
@@ -456,38 +458,80 @@ int cqb_bases_drop_precomputed(cqb_bases_t h) {
 //   pageable memory : (what a Rust Vec<Fr> is) the driver would stage such a copy synchronously at a few GB/s, so COPY_THREADS
 //                     host threads first move the part into a pinned staging buffer (grow-only, one per device slot) and the
 //                     asynchronous copy starts from there; the staging of part p+1 runs while the GPU works on part p.
-constexpr int COPY_THREADS = 8;
+constexpr int COPY_THREADS = 12;
 struct HostFeeder : MsmFeeder {
-    const uint64_t* src;
-    bool pinned;
-    int feed(int part, size_t lo, size_t cnt, cudaEvent_t* ready_out) override {
-        const char* from = (const char*)(src + lo * 4);
-        if (!pinned && cnt) {
-            char* stage = (char*)g_stage->p + lo * 32;
-            const size_t bytes = cnt * 32, per = (bytes / COPY_THREADS + 4095) & ~(size_t)4095;
-            std::vector<std::thread> th;
-            for (int t = 1; t < COPY_THREADS; t++) {
-                const size_t a = std::min(bytes, (size_t)t * per), b = std::min(bytes, (size_t)(t + 1) * per);
-                if (b > a) th.emplace_back([=] { memcpy(stage + a, from + a, b - a); });
+    const uint64_t* src = nullptr;
+    bool pinned = true;
+    // pageable source: a coordinator thread stages part after part at full memcpy speed from the moment the call starts,
+    // independently of how far the enqueuing thread has got; feed() only waits for the part it is about to queue
+    std::thread coordinator;
+    std::mutex mu;
+    std::condition_variable cv;
+    int staged = 0;   // parts whose copy has been issued and whose event has been recorded
+    int rc = 0;
+    std::string err;
+    cudaEvent_t* evs = nullptr;
+
+    void start_staging(size_t n, int parts) {
+        const int slot = cur_slot();
+        char* stage0 = (char*)g_stage->p;
+        char* dev0 = (char*)g_scalars->p;
+        cudaStream_t cs = g_copy->s;
+        evs = g_copy->ev;
+        coordinator = std::thread([=] {
+            bind_slot(slot);
+            size_t bounds[9];
+            msm_part_bounds(n, parts, true, bounds);
+            for (int p = 0; p < parts; p++) {
+                const size_t lo = bounds[p], cnt = bounds[p + 1] - lo;
+                const char* from = (const char*)(src + lo * 4);
+                char* stage = stage0 + lo * 32;
+                const size_t bytes = cnt * 32, per = (bytes / COPY_THREADS + 4095) & ~(size_t)4095;
+                std::vector<std::thread> th;
+                for (int t = 1; t < COPY_THREADS && per; t++) {
+                    const size_t a = std::min(bytes, (size_t)t * per), b = std::min(bytes, (size_t)(t + 1) * per);
+                    if (b > a) th.emplace_back([=] { memcpy(stage + a, from + a, b - a); });
+                }
+                if (bytes) memcpy(stage, from, per ? std::min(bytes, per) : bytes);
+                for (auto& t : th) t.join();
+                cudaError_t e = cnt ? cudaMemcpyAsync(dev0 + lo * 32, stage, bytes, cudaMemcpyHostToDevice, cs) : cudaSuccess;
+                if (e == cudaSuccess) e = cudaEventRecord(evs[p & 7], cs);
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (e != cudaSuccess) { rc = CQB_E_CUDA; err = std::string("staged copy of host scalars failed: ") + cudaGetErrorString(e); }
+                    staged = p + 1;
+                }
+                cv.notify_all();
+                if (e != cudaSuccess) return;
             }
-            memcpy(stage, from, std::min(bytes, per));
-            for (auto& t : th) t.join();
-            from = stage;
+        });
+    }
+    int feed(int part, size_t lo, size_t cnt, cudaEvent_t* ready_out) override {
+        if (pinned) {
+            if (cnt) CQB_CUDA(cudaMemcpyAsync((char*)g_scalars->p + lo * 32, src + lo * 4, cnt * 32, cudaMemcpyHostToDevice, g_copy->s));
+            CQB_CUDA(cudaEventRecord(g_copy->ev[part & 7], g_copy->s));
+            *ready_out = g_copy->ev[part & 7];
+            return 0;
         }
-        if (cnt) CQB_CUDA(cudaMemcpyAsync((char*)g_scalars->p + lo * 32, from, cnt * 32, cudaMemcpyHostToDevice, g_copy->s));
-        CQB_CUDA(cudaEventRecord(g_copy->ev[part & 3], g_copy->s));
-        *ready_out = g_copy->ev[part & 3];
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return staged > part || rc != 0; });
+        if (rc) return fail(rc, "%s", err.c_str());
+        *ready_out = evs[part & 7];
         return 0;
+    }
+    ~HostFeeder() override {
+        if (coordinator.joinable()) coordinator.join();
     }
 };
 
 #ifndef CQB_HOST_PARTS
 #define CQB_HOST_PARTS 3
 #endif
-static int g_pageable_parts = 4;
+static int g_pageable_parts = 4;  // cqb_msm_set_parts overrides (<= 8: the feeder cycles through 8 events)
 
 // queues `sum scalars[i] * bases[offset + i]` from HOST scalars on the current slot; the result lands in g_out (80 bytes)
-static int msm_host_enqueue(BaseSet* bs, size_t offset, const uint64_t* scalars, size_t n) {
+static int msm_host_enqueue(BaseSet* bs, size_t offset, const uint64_t* scalars, size_t n, void* d_out = nullptr) {
+    if (!d_out) d_out = g_out->p;
     CQB_TRY(g_scalars->ensure(n * 32 + 32));
     bool pinned = false;
     const bool large = n >= ((size_t)1 << 21);
@@ -505,13 +549,15 @@ static int msm_host_enqueue(BaseSet* bs, size_t offset, const uint64_t* scalars,
         HostFeeder feeder;
         feeder.src = scalars;
         feeder.pinned = pinned;
-        const int parts = pinned ? CQB_HOST_PARTS : g_pageable_parts;  // at most 4: the feeder cycles through 4 events
+        static const int env_parts = getenv("CQB_PAGEABLE_PARTS") ? std::max(2, std::min(8, atoi(getenv("CQB_PAGEABLE_PARTS")))) : 0;  // experiments
+        const int parts = pinned ? CQB_HOST_PARTS : (env_parts ? env_parts : g_pageable_parts);
+        if (!pinned) feeder.start_staging(n, parts);
         const bool use_table = bs->table && n * 8 >= bs->n;
-        if (use_table) return msm_run_precomputed(bs->table, bs->n, bs->table_c, offset, g_scalars->p, nullptr, n, g_out->p, 1, parts, nullptr, &feeder);
-        return msm_run(bs->d, offset, g_scalars->p, nullptr, n, g_out->p, parts, nullptr, &feeder);
+        if (use_table) return msm_run_precomputed(bs->table, bs->n, bs->table_c, offset, g_scalars->p, nullptr, n, d_out, 1, parts, nullptr, &feeder);
+        return msm_run(bs->d, offset, g_scalars->p, nullptr, n, d_out, parts, nullptr, &feeder);
     }
     if (n) CQB_CUDA(cudaMemcpyAsync(g_scalars->p, scalars, n * 32, cudaMemcpyHostToDevice, g_ctx.stream));
-    return dispatch_msm(bs, offset, g_scalars->p, nullptr, n);
+    return dispatch_msm(bs, offset, g_scalars->p, nullptr, n, d_out);
 }
 
 // ---- MSM over a SHARDED base set: one host thread per device slot (the reference's decomposition across threads,
@@ -592,6 +638,27 @@ int cqb_msm_bn254_g1_dev(cqb_bases_t b, size_t offset, const void* d_scalars, si
     if (!bs->shards.empty()) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1_dev: sharded base set; use cqb_msm_bn254_g1_multi_dev (one scalar pointer per device)");
     CQB_TRY(dispatch_msm(bs, offset, d_scalars, nullptr, n));
     return fetch_result(out_xy, is_inf);
+}
+
+// The same two MSMs with the result LEFT ON THE DEVICE (64 B affine x||y + 16 B identity flag at d_out_xy_flag), queued on the
+// library's stream and not waited for: a multi-process caller all-gathers the partial straight from there (sharded.py).
+int cqb_msm_bn254_g1_dev_to(cqb_bases_t b, size_t offset, const void* d_scalars, size_t n, void* d_out_xy_flag) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!d_out_xy_flag || (!d_scalars && n)) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1_dev_to: NULL argument");
+    BaseSet* bs = nullptr;
+    CQB_TRY(find_bases(b, offset, n, &bs));
+    if (!bs->shards.empty()) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1_dev_to: sharded base set");
+    return dispatch_msm(bs, offset, d_scalars, nullptr, n, d_out_xy_flag);
+}
+int cqb_msm_bn254_g1_to(cqb_bases_t b, size_t offset, const uint64_t* scalars, size_t n, void* d_out_xy_flag) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!d_out_xy_flag || (!scalars && n)) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1_to: NULL argument");
+    BaseSet* bs = nullptr;
+    CQB_TRY(find_bases(b, offset, n, &bs));
+    if (!bs->shards.empty()) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1_to: sharded base set");
+    return msm_host_enqueue(bs, offset, scalars, n, d_out_xy_flag);
 }
 
 // device-resident scalars of a sharded set: d_scalars[i] holds, on shard i's device, the scalars of that shard's point range
@@ -699,6 +766,14 @@ int cqb_g1_sum_affine(const uint64_t* affine_xy, size_t n, uint64_t out_xy[8], i
     CQB_TRY(g_tmp_bases->ensure(n * 64 + 64));
     if (n) CQB_CUDA(cudaMemcpyAsync(g_tmp_bases->p, affine_xy, n * 64, cudaMemcpyHostToDevice, g_ctx.stream));
     CQB_TRY(g1_sum_affine_run(g_tmp_bases->p, n, g_out->p));
+    return fetch_result(out_xy, is_inf);
+}
+
+int cqb_g1_sum_affine_dev(const void* d_affine_xy, size_t n, uint64_t out_xy[8], int* is_inf) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!out_xy || (!d_affine_xy && n)) return fail(CQB_E_BAD_ARG, "cqb_g1_sum_affine_dev: NULL argument");
+    CQB_TRY(g1_sum_affine_run(d_affine_xy, n, g_out->p));
     return fetch_result(out_xy, is_inf);
 }
 

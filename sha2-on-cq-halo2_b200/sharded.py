@@ -61,12 +61,27 @@ class CudaBackend:
                                                    ctypes.byref(self._inf)))
         return self._out.copy(), self._inf.value
 
+    def msm_dev_to(self, device_ptr, m, out_device_ptr):
+        """result left on the device (80 B), not waited for"""
+        _lib.check(_lib.lib().cqb_msm_bn254_g1_dev_to(self.handle, 0, ctypes.c_void_p(device_ptr), m, ctypes.c_void_p(out_device_ptr)))
+
+    def msm_host_ptr_to(self, host_ptr, m, out_device_ptr):
+        _lib.check(_lib.lib().cqb_msm_bn254_g1_to(self.handle, 0, ctypes.cast(ctypes.c_void_p(host_ptr), _lib.u64p), m,
+                                                  ctypes.c_void_p(out_device_ptr)))
+
     def msm_sparse(self, idx, scalars):
         idx = np.ascontiguousarray(idx, dtype=np.uint32)
         scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
         _lib.check(_lib.lib().cqb_msm_bn254_g1_sparse(self.handle, idx.ctypes.data_as(_lib.u32p), _lib.p64(scalars), idx.shape[0],
                                                       _lib.p64(self._out), ctypes.byref(self._inf)))
         return self._out.copy(), self._inf.value
+
+    def sum_affine_dev(self, device_ptr, count):
+        """fold `count` affine points that already sit in device memory (the all-gather's output): no host bounce"""
+        out = np.zeros(8, np.uint64)
+        inf = ctypes.c_int(0)
+        _lib.check(_lib.lib().cqb_g1_sum_affine_dev(ctypes.c_void_p(device_ptr), count, _lib.p64(out), ctypes.byref(inf)))
+        return out, inf.value
 
     def sum_affine(self, points):
         points = np.ascontiguousarray(points, dtype=np.uint64)
@@ -88,6 +103,7 @@ class ShardedMSM:
             self._torch = torch
             self._in = torch.zeros(8, dtype=torch.int64, device=device)
             self._out = torch.zeros(8 * world, dtype=torch.int64, device=device)
+            self._raw = torch.zeros(10, dtype=torch.int64, device=device)  # 80-byte device result of the *_to calls
 
     def fold(self, partial_affine):
         """all-gather the per-rank affine partials and add them up: arithmetic.rs:153 across GPUs. The identity is the
@@ -99,6 +115,10 @@ class ShardedMSM:
         torch = self._torch
         self._in.copy_(torch.from_numpy(np.ascontiguousarray(partial_affine).view(np.int64)))
         dist.all_gather_into_tensor(self._out, self._in, group=self.group)
+        if self._out.is_cuda and hasattr(self.backend, "sum_affine_dev"):
+            # the library's kernels run on torch's current stream (cqb_set_stream), so the fold is ordered after the all-gather
+            out, inf = self.backend.sum_affine_dev(self._out.data_ptr(), self.world)
+            return G1(out, inf)
         parts = self._out.cpu().numpy().view(np.uint64).reshape(self.world, 8)
         out, inf = self.backend.sum_affine(np.ascontiguousarray(parts))
         return G1(out, inf)
@@ -115,11 +135,28 @@ class ShardedMSM:
         partial, _ = self.backend.msm_sparse((idx[keep] - shard_start).astype(np.uint32), np.ascontiguousarray(scalars)[keep])
         return self.fold(partial)
 
+    def _fold_device(self):
+        """the rank's partial is in self._raw on the device: all-gather its 64 point bytes and fold, one read-back in all"""
+        import torch.distributed as dist
+
+        dist.all_gather_into_tensor(self._out, self._raw[:8], group=self.group)
+        out, inf = self.backend.sum_affine_dev(self._out.data_ptr(), self.world)
+        return G1(out, inf)
+
+    def _device_path(self):
+        return self.world > 1 and self._out.is_cuda and hasattr(self.backend, "msm_dev_to")
+
     def msm_dev(self, device_ptr, m):
+        if self._device_path():
+            self.backend.msm_dev_to(device_ptr, m, self._raw.data_ptr())
+            return self._fold_device()
         partial, _ = self.backend.msm_dev(device_ptr, m)
         return self.fold(partial)
 
     def msm_host_ptr(self, host_ptr, m):
+        if self._device_path():
+            self.backend.msm_host_ptr_to(host_ptr, m, self._raw.data_ptr())
+            return self._fold_device()
         partial, _ = self.backend.msm_host_ptr(host_ptr, m)
         return self.fold(partial)
 

@@ -164,6 +164,15 @@ def _full_msm_vs_oracle(env, oracle, log_n, host_paths):
         bs = _d2h(L, lib, d_b, (n, 8))
         _, exp = oracle.best_multiexp(sc, bs, oracle.hw_threads())
         del bs
+        # the point bench.py asserts at every GPU count (tests/golden/bench_points.json) is this oracle result
+        import json
+        import os
+
+        gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bench_points.json"))).get(str(log_n))
+        if gold is not None:  # x, y as the 256-bit integers the in-memory G1Affine limbs spell (Montgomery form)
+            ex = sum(int(v) << (64 * i) for i, v in enumerate(exp[:4]))
+            ey = sum(int(v) << (64 * i) for i, v in enumerate(exp[4:]))
+            assert (int(gold["x"], 16), int(gold["y"], 16)) == (ex, ey), "committed bench point differs from the oracle"
         h = ctypes.c_uint64(0)
         L.check(lib.cqb_bases_register_device(d_b, n, ctypes.byref(h)))
         try:
