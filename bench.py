@@ -175,6 +175,76 @@ def run_reference(args):
     return 0
 
 
+def in_process_leg(args, world, L, lib, stream, torch):
+    """One process, `world` devices, C ABI only: cqb_init_multi -> cqb_bases_register_sharded (+ per-shard tables) ->
+    cqb_msm_bn254_g1 from pinned host scalars (e2e) and cqb_msm_bn254_g1_multi_dev with resident scalars (value). Timed with CUDA
+    events on device 0's stream: the fold there waits for every device's partial, so the span covers the slowest device."""
+    n = 1 << args.log_n
+    L.check(lib.cqb_init_multi(world))
+    L.check(lib.cqb_set_stream(ctypes.c_void_p(stream.cuda_stream)))
+    # the seeded workload: generated on device 0, brought to the host once (setup, not timed)
+    d = ctypes.c_void_p()
+    bases_h = np.empty((n, 8), np.uint64)
+    L.check(lib.cqb_dev_alloc(n * 64, ctypes.byref(d)))
+    L.check(lib.cqb_synth_bases_dev(SEED_BASES, 0, n, d))
+    L.check(lib.cqb_memcpy_d2h(bases_h.ctypes.data_as(ctypes.c_void_p), d, n * 64))
+    hp = ctypes.c_void_p()
+    L.check(lib.cqb_host_alloc_pinned(n * 32, ctypes.byref(hp)))
+    L.check(lib.cqb_synth_scalars_dev(SEED_SCALARS, 0, n, d))
+    L.check(lib.cqb_memcpy_d2h(hp, d, n * 32))
+    L.check(lib.cqb_dev_free(d))
+    h = ctypes.c_uint64(0)
+    L.check(lib.cqb_bases_register_sharded(L.p64(bases_h), n, ctypes.byref(h)))
+    del bases_h
+    if not args.no_precompute:
+        L.check(lib.cqb_bases_precompute(h.value, args.window_bits))
+    out, inf = np.zeros(8, np.uint64), ctypes.c_int(0)
+    # resident scalars: shard i's range on device i
+    ptrs = (ctypes.c_void_p * world)()
+    base, rem = divmod(n, world)
+    for i in range(world):
+        s0, c0 = i * base + min(i, rem), base + (1 if i < rem else 0)
+        p = ctypes.c_void_p()
+        L.check(lib.cqb_dev_alloc_on(i, c0 * 32, ctypes.byref(p)))
+        L.check(lib.cqb_synth_scalars_dev_on(i, SEED_SCALARS, s0, c0, p))
+        ptrs[i] = p.value
+
+    def run_e2e():
+        L.check(lib.cqb_msm_bn254_g1(h.value, 0, ctypes.cast(hp, L.u64p), n, L.p64(out), ctypes.byref(inf)))
+
+    def run_dev():
+        L.check(lib.cqb_msm_bn254_g1_multi_dev(h.value, 0, ptrs, n, L.p64(out), ctypes.byref(inf)))
+
+    def timed_local(fn):
+        for _ in range(args.warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps
+
+    ms_dev = timed_local(run_dev)
+    pt_dev = point_hex(out.copy())
+    ms_e2e = timed_local(run_e2e)
+    pt_e2e = point_hex(out.copy())
+    golden = golden_point(args.log_n)
+    res = {"n_devices": world, "api": "cqb_init_multi + cqb_bases_register_sharded + cqb_msm_bn254_g1[_multi_dev] (one process, one host thread per "
+                                       "device, partials gathered with cudaMemcpyPeerAsync and folded on device 0)",
+           "value": n / (ms_dev * 1e-3) / 1e6, "ms_per_step": ms_dev, "e2e": {"value": n / (ms_e2e * 1e-3) / 1e6, "ms_per_step": ms_e2e,
+                                                                            "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 80},
+           "unit": UNIT, "point": pt_dev, "paths_agree": bool(pt_dev == pt_e2e),
+           "matches_golden": None if golden is None else bool(golden == pt_dev and golden == pt_e2e)}
+    for i in range(world):
+        L.check(lib.cqb_dev_free_on(i, ctypes.c_void_p(ptrs[i])))
+    L.check(lib.cqb_host_free_pinned(hp))
+    L.check(lib.cqb_bases_free(h.value))
+    return res
+
+
 # ---------------------------------------------------------------------------------------------------------------- ours
 def main():
     ap = argparse.ArgumentParser()
@@ -187,6 +257,7 @@ def main():
     ap.add_argument("--no-ntt", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-prove", action="store_true")
+    ap.add_argument("--no-in-process", action="store_true", help="skip the one-process-N-devices leg (cqb_init_multi) at N > 1")
     ap.add_argument("--prove-k", type=lambda v: [int(x) for x in v.split(",")], default=[16, 20])
     ap.add_argument("--ref-max-log", type=int, default=26)
     ap.add_argument("--window-bits", type=int, default=0)
@@ -443,6 +514,18 @@ def main():
                        "roofline_int": {"bound": "int", "achieved": int_t, "peak": int_peak()[0] * world, "unit": "TMAD32/s",
                                         "frac": int_t / (int_peak()[0] * world)}}
         del x_t
+
+    # ---- N > 1: the same sharded MSM driven by ONE process through the C ABI alone (cqb_init_multi: what a single-process Rust prover
+    #      binds — no torch, no NCCL on the path). Rank 0 runs it while the other ranks wait at a barrier; it re-initialises rank 0's
+    #      library state, so it is the last GPU leg of this process. ---------------------------------------------------------------
+    if world > 1 and not args.no_in_process:
+        dist.barrier()
+        if rank == 0:
+            try:
+                line["in_process"] = in_process_leg(args, world, L, lib, stream, torch)
+            except Exception as exc:  # reported, never fatal for the main line
+                line["in_process"] = {"error": repr(exc)[:300]}
+        dist.barrier()
 
     # ---- "SHA2-CQ prove ms": the synthetic CQ-prover-shaped op list of SURVEY.md §8(d) (no SHA circuit exists in the
     #      reference, F1), host-pointer C-ABI calls, N=1 only -------------------------------------------------------

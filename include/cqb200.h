@@ -226,6 +226,9 @@ CQB_API int cqb_lookup_h_dev(void* d_values, const void* d_table_value, const vo
 CQB_API int cqb_fr_compress_dev(const void* const* d_cols, uint32_t ncols, const uint32_t* d_idx, size_t n, const uint64_t theta[4], void* d_out);
 CQB_API int cqb_fr_inv_shifted_dev(const void* d_in, size_t n, size_t usable, const uint64_t shift[4], void* d_out);
 CQB_API int cqb_fr_mul_dev(const void* d_a, const void* d_b, size_t n, void* d_out);
+/* d_acc[i] = d_acc[i] * a + d_x[i]: one Horner step over whole polynomials. h(X) = sum_i h_i(X) x^(n i) (plonk/vanishing/prover.rs:131-135)
+ * and the GWC batches sum_i v^i p_i(X) (poly/kzg/multiopen/gwc/prover.rs:62-77) are folds of it. */
+CQB_API int cqb_fr_axpy_dev(void* d_acc, const uint64_t a[4], const void* d_x, size_t n);
 CQB_API int cqb_msm_bn254_g1_sparse_dev(cqb_bases_t b, const uint32_t* d_idx, const void* d_scalars, size_t m, uint64_t out_xy[8], int* is_inf);
 /* Exclusive running product, the serial z-loop of the grand-product arguments (plonk/permutation/prover.rs:157-163):
  * d_out[0] = init, d_out[i] = init * d_in[0] * ... * d_in[i-1] for i < n. d_out may alias d_in. */

@@ -6,7 +6,7 @@ kzg (ParamsKZG.commit / commit_lagrange, TableSRS), cq (CQ prover commit calls),
 the GPUs of one box). Import name: `sha2_on_cq_halo2_b200` via the repo-root shim `cqb200.py`.
 """
 from . import _lib  # noqa: F401
-from . import arithmetic, cq, domain, evaluation, fields, kzg, lookup, permutation  # noqa: F401
+from . import arithmetic, cq, domain, evaluation, fields, kzg, lookup, permutation, prover  # noqa: F401
 from .arithmetic import G1, best_fft, best_multiexp, eval_polynomial, kate_division  # noqa: F401
 from .domain import EvaluationDomain  # noqa: F401
 from .kzg import DeviceBases, ParamsKZG, TableSRS  # noqa: F401

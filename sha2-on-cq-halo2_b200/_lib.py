@@ -89,6 +89,7 @@ SYMBOLS = [
     ("cqb_fr_compress_dev", _int, [_vp, _u32, _vp, _sz, u64p, _vp]),
     ("cqb_fr_inv_shifted_dev", _int, [_vp, _sz, _sz, u64p, _vp]),
     ("cqb_fr_mul_dev", _int, [_vp, _vp, _sz, _vp]),
+    ("cqb_fr_axpy_dev", _int, [_vp, u64p, _vp, _sz]),
     ("cqb_msm_bn254_g1_sparse_dev", _int, [_u64, _vp, _vp, _sz, u64p, _ip]),
     ("cqb_permutation_product_dev", _int, [_vp, _vp, _u32, _u32, u64p, u64p, u64p, u64p, u64p, u64p, _vp]),
     ("cqb_dev_alloc", _int, [_sz, ctypes.POINTER(_vp)]),

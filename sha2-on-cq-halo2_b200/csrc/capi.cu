@@ -458,7 +458,7 @@ int cqb_bases_drop_precomputed(cqb_bases_t h) {
 //   pageable memory : (what a Rust Vec<Fr> is) the driver would stage such a copy synchronously at a few GB/s, so COPY_THREADS
 //                     host threads first move the part into a pinned staging buffer (grow-only, one per device slot) and the
 //                     asynchronous copy starts from there; the staging of part p+1 runs while the GPU works on part p.
-constexpr int COPY_THREADS = 12;
+constexpr int COPY_THREADS = 16;
 struct HostFeeder : MsmFeeder {
     const uint64_t* src = nullptr;
     bool pinned = true;
@@ -482,19 +482,24 @@ struct HostFeeder : MsmFeeder {
             bind_slot(slot);
             size_t bounds[9];
             msm_part_bounds(n, parts, true, bounds);
+            const int nthreads = std::max(2, std::min(COPY_THREADS, (int)std::thread::hardware_concurrency() - 2));
+            const size_t CHUNK = (size_t)16 << 20;  // staged and sent chunk by chunk: the H2D of a chunk runs under the staging of the next
             for (int p = 0; p < parts; p++) {
                 const size_t lo = bounds[p], cnt = bounds[p + 1] - lo;
-                const char* from = (const char*)(src + lo * 4);
-                char* stage = stage0 + lo * 32;
-                const size_t bytes = cnt * 32, per = (bytes / COPY_THREADS + 4095) & ~(size_t)4095;
-                std::vector<std::thread> th;
-                for (int t = 1; t < COPY_THREADS && per; t++) {
-                    const size_t a = std::min(bytes, (size_t)t * per), b = std::min(bytes, (size_t)(t + 1) * per);
-                    if (b > a) th.emplace_back([=] { memcpy(stage + a, from + a, b - a); });
+                cudaError_t e = cudaSuccess;
+                for (size_t off = 0; off < cnt * 32 && e == cudaSuccess; off += CHUNK) {
+                    const char* from = (const char*)(src + lo * 4) + off;
+                    char* stage = stage0 + lo * 32 + off;
+                    const size_t bytes = std::min(CHUNK, cnt * 32 - off), per = (bytes / nthreads + 4095) & ~(size_t)4095;
+                    std::vector<std::thread> th;
+                    for (int t = 1; t < nthreads; t++) {
+                        const size_t a = std::min(bytes, (size_t)t * per), b = std::min(bytes, (size_t)(t + 1) * per);
+                        if (b > a) th.emplace_back([=] { memcpy(stage + a, from + a, b - a); });
+                    }
+                    memcpy(stage, from, std::min(bytes, per));
+                    for (auto& t : th) t.join();
+                    e = cudaMemcpyAsync(dev0 + lo * 32 + off, stage, bytes, cudaMemcpyHostToDevice, cs);
                 }
-                if (bytes) memcpy(stage, from, per ? std::min(bytes, per) : bytes);
-                for (auto& t : th) t.join();
-                cudaError_t e = cnt ? cudaMemcpyAsync(dev0 + lo * 32, stage, bytes, cudaMemcpyHostToDevice, cs) : cudaSuccess;
                 if (e == cudaSuccess) e = cudaEventRecord(evs[p & 7], cs);
                 {
                     std::lock_guard<std::mutex> lk(mu);
@@ -1174,6 +1179,12 @@ int cqb_fr_mul_dev(const void* d_a, const void* d_b, size_t n, void* d_out) {
     CQB_TRY(require_init());
     if ((!d_a || !d_b || !d_out) && n) return fail(CQB_E_BAD_ARG, "cqb_fr_mul_dev: NULL argument");
     return fr_mul_run(d_a, d_b, n, d_out);
+}
+int cqb_fr_axpy_dev(void* d_acc, const uint64_t a[4], const void* d_x, size_t n) {
+    LOCK;
+    CQB_TRY(require_init());
+    if ((!d_acc || !d_x || !a) && n) return fail(CQB_E_BAD_ARG, "cqb_fr_axpy_dev: NULL argument");
+    return fr_axpy_run(d_acc, a, d_x, n);
 }
 int cqb_msm_bn254_g1_sparse_dev(cqb_bases_t b, const uint32_t* d_idx, const void* d_scalars, size_t m, uint64_t out_xy[8], int* is_inf) {
     LOCK;

@@ -106,6 +106,7 @@ int permutation_product_run(const void* const* d_columns, const void* const* d_p
 int fr_compress_run(const void* const* d_cols, uint32_t ncols, const uint32_t* d_idx, size_t n, const uint64_t theta[4], void* d_out);
 int fr_inv_shifted_run(const void* d_in, size_t n, size_t usable, const uint64_t shift[4], void* d_out);
 int fr_mul_run(const void* d_a, const void* d_b, size_t n, void* d_out);
+int fr_axpy_run(void* d_acc, const uint64_t a[4], const void* d_x, size_t n);
 int lookup_product_run(const void* d_compressed_input, const void* d_compressed_table, const void* d_permuted_input, const void* d_permuted_table,
                        uint32_t k, const uint64_t beta[4], const uint64_t gamma[4], void* d_z);
 void products_release_all();

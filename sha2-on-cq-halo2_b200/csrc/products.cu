@@ -229,6 +229,21 @@ __global__ void __launch_bounds__(256) fr_mul_kernel(const uint4* a, const uint4
     q_st(out, i, fp_mul<FrP>(q_ld(a, i), q_ld(b, i)));
 }
 
+// acc[i] = acc[i] * a + x[i]: one Horner step over whole polynomials — h(X) = sum_i h_i(X) x^(n i) (vanishing/prover.rs:131-135) and
+// the GWC batches sum_i v^i p_i(X) (poly/kzg/multiopen/gwc/prover.rs:62-77) are folds of it
+__global__ void __launch_bounds__(256) fr_axpy_kernel(uint4* acc, Fr a, const uint4* x, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    q_st(acc, i, fp_add<FrP>(fp_mul<FrP>(q_ld(acc, i), a), q_ld(x, i)));
+}
+int fr_axpy_run(void* d_acc, const uint64_t a[4], const void* d_x, size_t n) {
+    if (n == 0) return 0;
+    fr_axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx().stream>>>((uint4*)d_acc, fr_from_u64x4(a), (const uint4*)d_x, n);
+    CQB_LAUNCHED();
+    CQB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int fr_compress_run(const void* const* d_cols, uint32_t ncols, const uint32_t* d_idx, size_t n, const uint64_t theta[4], void* d_out) {
     if (ncols == 0 || ncols > CQ_MAX_COLS) return fail(CQB_E_BAD_ARG, "compress: 1..%d columns (got %u)", CQ_MAX_COLS, ncols);
     if (n == 0) return 0;

@@ -29,6 +29,10 @@ class Blake2bWrite:
         self.common_point(affine_limbs, oracle)
         self.proof += oracle.g1_to_bytes(affine_limbs)  # compressed encoding, derive/curve.rs:635-646
 
+    def write_scalar(self, scalar_int):  # :204-208: common_scalar, then the canonical 32-byte repr goes to the proof
+        self.common_scalar(scalar_int)
+        self.proof += int(scalar_int).to_bytes(32, "little")
+
     def squeeze_challenge_scalar(self):  # :208-215 + Challenge255::new (:297-309): from_bytes_wide of the 64-byte digest
         self.state.update(bytes([PREFIX_CHALLENGE]))
         digest = self.state.copy().digest()
