@@ -483,23 +483,32 @@ struct HostFeeder : MsmFeeder {
             size_t bounds[9];
             msm_part_bounds(n, parts, true, bounds);
             const int nthreads = std::max(2, std::min(COPY_THREADS, (int)std::thread::hardware_concurrency() - 2));
-            const size_t CHUNK = (size_t)16 << 20;  // staged and sent chunk by chunk: the H2D of a chunk runs under the staging of the next
             for (int p = 0; p < parts; p++) {
                 const size_t lo = bounds[p], cnt = bounds[p + 1] - lo;
-                cudaError_t e = cudaSuccess;
-                for (size_t off = 0; off < cnt * 32 && e == cudaSuccess; off += CHUNK) {
-                    const char* from = (const char*)(src + lo * 4) + off;
-                    char* stage = stage0 + lo * 32 + off;
-                    const size_t bytes = std::min(CHUNK, cnt * 32 - off), per = (bytes / nthreads + 4095) & ~(size_t)4095;
-                    std::vector<std::thread> th;
-                    for (int t = 1; t < nthreads; t++) {
-                        const size_t a = std::min(bytes, (size_t)t * per), b = std::min(bytes, (size_t)(t + 1) * per);
-                        if (b > a) th.emplace_back([=] { memcpy(stage + a, from + a, b - a); });
+                const char* from = (const char*)(src + lo * 4);
+                char* stage = stage0 + lo * 32;
+                char* dev = dev0 + lo * 32;
+                const size_t bytes = cnt * 32, per = (bytes / nthreads + 4095) & ~(size_t)4095;
+                // every copier thread stages its slice in four pieces and queues the H2D of a piece as soon as it is staged: the DMA of
+                // the first pieces runs under the staging of the later ones
+                std::vector<cudaError_t> errs(nthreads, cudaSuccess);
+                auto slice = [&](int t) {
+                    if (t) bind_slot(slot);
+                    const size_t a = std::min(bytes, (size_t)t * per), b = std::min(bytes, (size_t)(t + 1) * per);
+                    const size_t piece = ((b - a) / 4 + 4095) & ~(size_t)4095;
+                    for (size_t o = a; o < b && piece; o += piece) {
+                        const size_t len = std::min(piece, b - o);
+                        memcpy(stage + o, from + o, len);
+                        cudaError_t e2 = cudaMemcpyAsync(dev + o, stage + o, len, cudaMemcpyHostToDevice, cs);
+                        if (e2 != cudaSuccess) { errs[t] = e2; return; }
                     }
-                    memcpy(stage, from, std::min(bytes, per));
-                    for (auto& t : th) t.join();
-                    e = cudaMemcpyAsync(dev0 + lo * 32 + off, stage, bytes, cudaMemcpyHostToDevice, cs);
-                }
+                };
+                std::vector<std::thread> th;
+                for (int t = 1; t < nthreads && per; t++) th.emplace_back(slice, t);
+                if (bytes) { if (per) slice(0); else { memcpy(stage, from, bytes); errs[0] = cudaMemcpyAsync(dev, stage, bytes, cudaMemcpyHostToDevice, cs); } }
+                for (auto& t : th) t.join();
+                cudaError_t e = cudaSuccess;
+                for (cudaError_t e2 : errs) if (e2 != cudaSuccess) e = e2;
                 if (e == cudaSuccess) e = cudaEventRecord(evs[p & 7], cs);
                 {
                     std::lock_guard<std::mutex> lk(mu);

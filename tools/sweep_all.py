@@ -20,7 +20,7 @@ torch.cuda.set_stream(stream)
 L.check(lib.cqb_set_stream(ctypes.c_void_p(stream.cuda_stream)))
 HBM = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(
     os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
-INT_PEAK = 8.51
+INT_PEAK = 9.306  # profiles/INT_PEAK.json
 max_log = int(sys.argv[1]) if len(sys.argv) > 1 else 26
 
 
