@@ -109,6 +109,10 @@ CQB_API int cqb_msm_bn254_g1_batch_dev(cqb_bases_t b, size_t offset, const void*
 CQB_API int cqb_msm_bn254_g1_host(const uint64_t* affine_xy, const uint64_t* scalars, size_t n, uint64_t out_xy[8], int* is_inf);
 /* sparse MSM sum_j scalars[j] * bases[idx[j]]: replaces the serial scalar-mul loops of the CQ prover for m(X), A(X),
  * Q_A(X), A_0(X) (plonk/static_lookup/prover.rs:167-170, 245-257) */
+/* MSMKZG::eval (poly/kzg/msm.rs:65-70): projective bases (E::G1 = Jacobian x, y, z Montgomery limbs, 96 B each; z = 0 is the
+ * identity) are normalised with Curve::batch_normalize (arithmetic/curves/src/derive/curve.rs:362-397) on the device, then multiplied */
+CQB_API int cqb_g1_batch_normalize(const uint64_t* jacobian_xyz, size_t n, uint64_t* affine_xy_out);
+CQB_API int cqb_msm_bn254_g1_jacobian(const uint64_t* jacobian_xyz, const uint64_t* scalars, size_t n, uint64_t out_xy[8], int* is_inf);
 CQB_API int cqb_msm_bn254_g1_sparse(cqb_bases_t b, const uint32_t* idx, const uint64_t* scalars, size_t m, uint64_t out_xy[8],
                             int* is_inf);
 /* sum of n affine points (host): the final fold of per-GPU partial results of a point-range-sharded MSM — the
@@ -282,6 +286,17 @@ CQB_API int cqb_permutation_h_dev(void* d_values, uint64_t size, int32_t rot_sca
                                   const void* const* d_perm_cosets, uint32_t ncols, const void* d_l0, const void* d_l_last,
                                   const void* d_l_active_row, const uint64_t beta[4], const uint64_t gamma[4], const uint64_t y[4],
                                   const uint64_t extended_omega[4]);
+
+/* ---- G2 (keygen-time, primary device). G2Affine = 128 bytes x.c0 || x.c1 || y.c0 || y.c1 (Fq Montgomery limbs, the reference's raw
+ *      layout, arithmetic/curves/src/bn256/fq2.rs + derive/curve.rs SerdeObject); identity = zeros.
+ *   cqb_g2_powers     : out[i] = [s^i] G2, i < count — ParamsKZG's s_g2 = out[1] (poly/kzg/commitment.rs:265-266, 337-338) and the table
+ *                       SRS's G2 powers (:94-104, 114-141).
+ *   cqb_msm_bn254_g2  : best_multiexp::<G2Affine> — the CQ table commitment t (plonk/static_lookup.rs:146); zv = [s^N]G2 - G2 (:137)
+ *                       is the same call with scalars (1, r - 1).
+ *   cqb_g2_generator_mul_dev: out[i] = [scalars[i]] G2 with device-resident scalars and output. */
+CQB_API int cqb_g2_powers(const uint64_t s[4], size_t count, uint64_t* g2_affine_out);
+CQB_API int cqb_msm_bn254_g2(const uint64_t* g2_affine, const uint64_t* scalars, size_t n, uint64_t out_xy[16], int* is_inf);
+CQB_API int cqb_g2_generator_mul_dev(const void* d_scalars, size_t n, void* d_out_affine);
 
 /* ---- plain device memory helpers so non-CUDA hosts (ctypes, the Rust shim) need no CUDA binding of their own ---- */
 CQB_API int cqb_dev_alloc(size_t bytes, void** d_out);

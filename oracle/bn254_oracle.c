@@ -283,6 +283,171 @@ static int g1a_is_on_curve(const g1a* p) {
 }
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Fq2 = Fq[u]/(u^2 + 1) — arithmetic/curves/src/bn256/fq2.rs:161-307 — and G2 — derive/curve.rs (new_curve_impl!) instantiated
+ * bn256/curve.rs:36-48 over Fq2 with G2_GENERATOR_X / _Y (:100-129) and b = G2_B = 3/(9+u) (:85-98). The same generic formulas
+ * as G1 above (the macro is generic in the base field), restated over fq2.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct { fe c0, c1; } fe2;
+static fe2 fq2_zero(void) { fe2 r; r.c0 = fq_zero(); r.c1 = fq_zero(); return r; }
+static fe2 fq2_one(void) { fe2 r; r.c0 = fq_one(); r.c1 = fq_zero(); return r; }
+static int fq2_is_zero(fe2 a) { return fq_is_zero(a.c0) & fq_is_zero(a.c1); }
+static int fq2_eq(fe2 a, fe2 b) { return fq_eq(a.c0, b.c0) & fq_eq(a.c1, b.c1); }
+static fe2 fq2_add(fe2 a, fe2 b) { fe2 r; r.c0 = fq_add(a.c0, b.c0); r.c1 = fq_add(a.c1, b.c1); return r; }  /* fq2.rs:195-200 */
+static fe2 fq2_sub(fe2 a, fe2 b) { fe2 r; r.c0 = fq_sub(a.c0, b.c0); r.c1 = fq_sub(a.c1, b.c1); return r; }  /* :202-207 */
+static fe2 fq2_neg(fe2 a) { fe2 r; r.c0 = fq_neg(a.c0); r.c1 = fq_neg(a.c1); return r; }                      /* :221-226 */
+static fe2 fq2_mul(fe2 a, fe2 b) { /* :161-170 */
+    fe t1 = fq_mul(a.c0, b.c0);
+    fe t0 = fq_add(a.c0, a.c1);
+    fe t2 = fq_mul(a.c1, b.c1);
+    fe s = fq_add(b.c0, b.c1);
+    fe2 r;
+    r.c0 = fq_sub(t1, t2);
+    t1 = fq_add(t1, t2);
+    t0 = fq_mul(t0, s);
+    r.c1 = fq_sub(t0, t1);
+    return r;
+}
+static fe2 fq2_square(fe2 a) { /* :172-181 */
+    fe ab = fq_mul(a.c0, a.c1);
+    fe c0c1 = fq_add(a.c0, a.c1);
+    fe c0 = fq_add(fq_neg(a.c1), a.c0);
+    c0 = fq_mul(c0, c0c1);
+    c0 = fq_sub(c0, ab);
+    fe2 r;
+    r.c1 = fq_add(ab, ab);
+    r.c0 = fq_add(c0, ab);
+    return r;
+}
+static fe2 fq2_invert(fe2 a) { /* :290-307; 0 -> 0 (unwrap_or(zero) at the call sites) */
+    fe t = fq_add(fq_square(a.c0), fq_square(a.c1));
+    t = fq_invert(t);
+    fe2 r;
+    r.c0 = fq_mul(a.c0, t);
+    r.c1 = fq_neg(fq_mul(a.c1, t));
+    return r;
+}
+typedef struct { fe2 x, y; } g2a;    /* affine, 128 bytes: x.c0 x.c1 y.c0 y.c1; identity = zeros */
+typedef struct { fe2 x, y, z; } g2j; /* Jacobian; identity z = 0 */
+static g2j g2j_identity(void) { g2j p; p.x = fq2_zero(); p.y = fq2_zero(); p.z = fq2_zero(); return p; }
+static g2a g2a_identity(void) { g2a p; p.x = fq2_zero(); p.y = fq2_zero(); return p; }
+static int g2j_is_identity(const g2j* p) { return fq2_is_zero(p->z); }
+static int g2a_is_identity(const g2a* p) { return fq2_is_zero(p->x) & fq2_is_zero(p->y); }
+static g2a g2a_generator(void) { /* bn256/curve.rs:100-129 */
+    g2a g;
+    g.x.c0 = fq_from_raw(0x46debd5cd992f6edULL, 0x674322d4f75edaddULL, 0x426a00665e5c4479ULL, 0x1800deef121f1e76ULL);
+    g.x.c1 = fq_from_raw(0x97e485b7aef312c2ULL, 0xf1aa493335a9e712ULL, 0x7260bfb731fb5d25ULL, 0x198e9393920d483aULL);
+    g.y.c0 = fq_from_raw(0x4ce6cc0166fa7daaULL, 0xe3d1e7690c43d37bULL, 0x4aab71808dcb408fULL, 0x12c85ea5db8c6debULL);
+    g.y.c1 = fq_from_raw(0x55acdadcd122975bULL, 0xbc4b313370b38ef3ULL, 0xec9e99ad690c3395ULL, 0x090689d0585ff075ULL);
+    return g;
+}
+static fe2 g2_b(void) { /* bn256/curve.rs:85-98 */
+    fe2 b;
+    b.c0 = fq_from_raw(0x3267e6dc24a138e5ULL, 0xb5b4c5e559dbefa3ULL, 0x81be18991be06ac3ULL, 0x2b149d40ceb8aaaeULL);
+    b.c1 = fq_from_raw(0xe4a2bd0685c315d2ULL, 0xa74fa084e52d1852ULL, 0xcd2cafadeed8fdf4ULL, 0x009713b03af0fed4ULL);
+    return b;
+}
+static g2j g2a_to_curve(const g2a* p) { g2j r; r.x = p->x; r.y = p->y; r.z = g2a_is_identity(p) ? fq2_zero() : fq2_one(); return r; }
+static g2a g2a_neg(const g2a* p) { g2a r; r.x = p->x; r.y = fq2_neg(p->y); return r; }
+static g2j g2j_double(const g2j* p) { /* derive/curve.rs:422-447 */
+    fe2 a = fq2_square(p->x);
+    fe2 b = fq2_square(p->y);
+    fe2 c = fq2_square(b);
+    fe2 d = fq2_square(fq2_add(p->x, b));
+    d = fq2_sub(fq2_sub(d, a), c);
+    d = fq2_add(d, d);
+    fe2 e = fq2_add(fq2_add(a, a), a);
+    fe2 f = fq2_square(e);
+    fe2 z3 = fq2_mul(p->z, p->y);
+    z3 = fq2_add(z3, z3);
+    fe2 x3 = fq2_sub(f, fq2_add(d, d));
+    c = fq2_add(c, c);
+    c = fq2_add(c, c);
+    c = fq2_add(c, c);
+    fe2 y3 = fq2_sub(fq2_mul(e, fq2_sub(d, x3)), c);
+    g2j r; r.x = x3; r.y = y3; r.z = z3;
+    if (g2j_is_identity(p)) return g2j_identity();
+    return r;
+}
+static g2j g2j_add(const g2j* s, const g2j* rhs) { /* :809-851 */
+    if (g2j_is_identity(s)) return *rhs;
+    if (g2j_is_identity(rhs)) return *s;
+    fe2 z1z1 = fq2_square(s->z);
+    fe2 z2z2 = fq2_square(rhs->z);
+    fe2 u1 = fq2_mul(s->x, z2z2);
+    fe2 u2 = fq2_mul(rhs->x, z1z1);
+    fe2 s1 = fq2_mul(fq2_mul(s->y, z2z2), rhs->z);
+    fe2 s2 = fq2_mul(fq2_mul(rhs->y, z1z1), s->z);
+    if (fq2_eq(u1, u2)) {
+        if (fq2_eq(s1, s2)) return g2j_double(s);
+        return g2j_identity();
+    }
+    fe2 h = fq2_sub(u2, u1);
+    fe2 i = fq2_square(fq2_add(h, h));
+    fe2 j = fq2_mul(h, i);
+    fe2 r = fq2_sub(s2, s1);
+    r = fq2_add(r, r);
+    fe2 v = fq2_mul(u1, i);
+    fe2 x3 = fq2_sub(fq2_sub(fq2_sub(fq2_square(r), j), v), v);
+    s1 = fq2_mul(s1, j);
+    s1 = fq2_add(s1, s1);
+    fe2 y3 = fq2_sub(fq2_mul(r, fq2_sub(v, x3)), s1);
+    fe2 z3 = fq2_sub(fq2_sub(fq2_square(fq2_add(s->z, rhs->z)), z1z1), z2z2);
+    z3 = fq2_mul(z3, h);
+    g2j o; o.x = x3; o.y = y3; o.z = z3;
+    return o;
+}
+static g2j g2j_madd(const g2j* s, const g2a* rhs) { /* :853-893 */
+    if (g2j_is_identity(s)) return g2a_to_curve(rhs);
+    if (g2a_is_identity(rhs)) return *s;
+    fe2 z1z1 = fq2_square(s->z);
+    fe2 u2 = fq2_mul(rhs->x, z1z1);
+    fe2 s2 = fq2_mul(fq2_mul(rhs->y, z1z1), s->z);
+    if (fq2_eq(s->x, u2)) {
+        if (fq2_eq(s->y, s2)) return g2j_double(s);
+        return g2j_identity();
+    }
+    fe2 h = fq2_sub(u2, s->x);
+    fe2 hh = fq2_square(h);
+    fe2 i = fq2_add(hh, hh);
+    i = fq2_add(i, i);
+    fe2 j = fq2_mul(h, i);
+    fe2 r = fq2_sub(s2, s->y);
+    r = fq2_add(r, r);
+    fe2 v = fq2_mul(s->x, i);
+    fe2 x3 = fq2_sub(fq2_sub(fq2_sub(fq2_square(r), j), v), v);
+    j = fq2_mul(s->y, j);
+    j = fq2_add(j, j);
+    fe2 y3 = fq2_sub(fq2_mul(r, fq2_sub(v, x3)), j);
+    fe2 z3 = fq2_sub(fq2_sub(fq2_square(fq2_add(s->z, h)), z1z1), hh);
+    g2j o; o.x = x3; o.y = y3; o.z = z3;
+    return o;
+}
+static g2a g2j_to_affine(const g2j* p) { /* :399-412 */
+    fe2 zinv = fq2_invert(p->z);
+    fe2 zinv2 = fq2_square(zinv);
+    fe2 x = fq2_mul(p->x, zinv2);
+    fe2 y = fq2_mul(p->y, fq2_mul(zinv2, zinv));
+    if (fq2_is_zero(zinv)) return g2a_identity();
+    g2a r; r.x = x; r.y = y;
+    return r;
+}
+static g2j g2a_mul(const g2a* p, fe scalar) { /* :1019-1040 */
+    uint8_t repr[32];
+    fr_to_repr(scalar, repr);
+    g2j acc = g2j_identity();
+    for (int byte = 31; byte >= 0; byte--)
+        for (int i = 7; i >= 0; i--) {
+            acc = g2j_double(&acc);
+            if ((repr[byte] >> i) & 1) acc = g2j_madd(&acc, p);
+        }
+    return acc;
+}
+static int g2a_is_on_curve(const g2a* p) {
+    if (g2a_is_identity(p)) return 1;
+    return fq2_eq(fq2_square(p->y), fq2_add(fq2_mul(fq2_square(p->x), p->x), g2_b()));
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
  * MSM — halo2_proofs/src/arithmetic.rs:13-159
  * ------------------------------------------------------------------------------------------------------------------ */
 /* arithmetic.rs:24-42 get_at */
@@ -1068,4 +1233,41 @@ API void oracle_lookup_h(uint64_t* values, size_t size, int32_t rot_scale, const
         v[idx] = fr_add(fr_mul(v[idx], y), fr_mul(a_minus_s, l0[idx]));                                              /* :516 */
         v[idx] = fr_add(fr_mul(v[idx], y), fr_mul(fr_mul(a_minus_s, fr_sub(a[idx], a[r_prev])), l_active[idx]));     /* :521-525 */
     }
+}
+
+/* ---- G2 (keygen-time pieces of the path: [s]G2, the table SRS's G2 powers, the G2 table commitment) --------------------------- */
+API void oracle_g2_generator(uint64_t* out_aff) { g2a g = g2a_generator(); memcpy(out_aff, &g, 128); }
+API int oracle_g2_is_on_curve(const uint64_t* a) { g2a x; memcpy(&x, a, 128); return g2a_is_on_curve(&x); }
+API void oracle_g2_mul_a(const uint64_t* a, const uint64_t* s, uint64_t* out_aff) {
+    g2a x; fe k; memcpy(&x, a, 128); memcpy(&k, s, 32);
+    g2j r = g2a_mul(&x, k); g2a o = g2j_to_affine(&r); memcpy(out_aff, &o, 128);
+}
+API void oracle_g2_add_aa(const uint64_t* a, const uint64_t* b, uint64_t* out_aff) {
+    g2a x, y; memcpy(&x, a, 128); memcpy(&y, b, 128);
+    g2j xj = g2a_to_curve(&x); g2j r = g2j_madd(&xj, &y); g2a o = g2j_to_affine(&r); memcpy(out_aff, &o, 128);
+}
+API void oracle_g2_neg_a(const uint64_t* a, uint64_t* out_aff) { g2a x; memcpy(&x, a, 128); g2a r = g2a_neg(&x); memcpy(out_aff, &r, 128); }
+/* poly/kzg/commitment.rs:94-104 (TableSRS) / :265 (ParamsKZG s_g2): out[i] = [s^i] G2, i < count, affine */
+API void oracle_g2_powers(const uint64_t* s_, size_t count, uint64_t* out_aff) {
+    fe s; memcpy(&s, s_, 32);
+    g2a gen = g2a_generator();
+    fe cur = fr_one();
+    for (size_t i = 0; i < count; i++) {
+        g2j r = g2a_mul(&gen, cur);
+        g2a o = g2j_to_affine(&r);
+        memcpy(out_aff + 16 * i, &o, 128);
+        cur = fr_mul(cur, s);
+    }
+}
+/* best_multiexp::<G2Affine> (plonk/static_lookup.rs:146): only the affine normal form of the sum is canonical, so the oracle adds
+ * the scalar multiples one by one */
+API void oracle_g2_msm(const uint64_t* bases_aff, const uint64_t* scalars, size_t n, uint64_t* out_aff) {
+    g2j acc = g2j_identity();
+    for (size_t i = 0; i < n; i++) {
+        g2a b; fe k; memcpy(&b, bases_aff + 16 * i, 128); memcpy(&k, scalars + 4 * i, 32);
+        g2j t = g2a_mul(&b, k);
+        acc = g2j_add(&acc, &t);
+    }
+    g2a o = g2j_to_affine(&acc);
+    memcpy(out_aff, &o, 128);
 }

@@ -409,3 +409,47 @@ def lookup_h(values, rot_scale, table_value, product, permuted_input, permuted_t
     lib().oracle_lookup_h(_p(v), ctypes.c_size_t(v.shape[0]), ctypes.c_int32(rot_scale), *[_p(x) for x in arrs], _p(_c(beta, 4)), _p(_c(gamma, 4)),
                           _p(_c(y, 4)))
     return v
+
+
+# ---- G2 (affine (16,) uint64: x.c0 x.c1 y.c0 y.c1, Montgomery limbs; identity = zeros) ----------------------------------------
+def g2_generator():
+    out = np.zeros(16, np.uint64)
+    lib().oracle_g2_generator(_p(out))
+    return out
+
+
+def g2_is_on_curve(a):
+    lib().oracle_g2_is_on_curve.restype = ctypes.c_int
+    return bool(lib().oracle_g2_is_on_curve(_p(_c(a, 16))))
+
+
+def g2_mul_a(a, s):
+    out = np.zeros(16, np.uint64)
+    lib().oracle_g2_mul_a(_p(_c(a, 16)), _p(_c(s, 4)), _p(out))
+    return out
+
+
+def g2_add_aa(a, b):
+    out = np.zeros(16, np.uint64)
+    lib().oracle_g2_add_aa(_p(_c(a, 16)), _p(_c(b, 16)), _p(out))
+    return out
+
+
+def g2_neg_a(a):
+    out = np.zeros(16, np.uint64)
+    lib().oracle_g2_neg_a(_p(_c(a, 16)), _p(out))
+    return out
+
+
+def g2_powers(s, count):
+    out = np.zeros((count, 16), np.uint64)
+    lib().oracle_g2_powers(_p(_c(s, 4)), ctypes.c_size_t(count), _p(out))
+    return out
+
+
+def g2_msm(bases, scalars):
+    bases, scalars = _c(bases, 16), _c(scalars, 4)
+    assert bases.shape[0] == scalars.shape[0]
+    out = np.zeros(16, np.uint64)
+    lib().oracle_g2_msm(_p(bases), _p(scalars), ctypes.c_size_t(bases.shape[0]), _p(out))
+    return out

@@ -142,3 +142,71 @@ def dft(a, omega):
         out[k + n // 2] = (even[k] - t) % R_MOD
         w = w * omega % R_MOD
     return out
+
+
+# ---- Fq2 = Fq[u]/(u^2 + 1) and G2: an independent big-integer model (tuples (c0, c1); affine points ((x0,x1),(y0,y1)) or None) ----
+G2_GEN = ((0x1800deef121f1e76426a00665e5c4479674322d4f75edadd46debd5cd992f6ed, 0x198e9393920d483a7260bfb731fb5d25f1aa493335a9e71297e485b7aef312c2),
+          (0x12c85ea5db8c6deb4aab71808dcb408fe3d1e7690c43d37b4ce6cc0166fa7daa, 0x090689d0585ff075ec9e99ad690c3395bc4b313370b38ef355acdadcd122975b))
+
+
+def fq2_add(a, b):
+    return ((a[0] + b[0]) % Q_MOD, (a[1] + b[1]) % Q_MOD)
+
+
+def fq2_sub(a, b):
+    return ((a[0] - b[0]) % Q_MOD, (a[1] - b[1]) % Q_MOD)
+
+
+def fq2_mul(a, b):
+    return ((a[0] * b[0] - a[1] * b[1]) % Q_MOD, (a[0] * b[1] + a[1] * b[0]) % Q_MOD)
+
+
+def fq2_inv(a):
+    t = pow(a[0] * a[0] + a[1] * a[1], -1, Q_MOD)
+    return (a[0] * t % Q_MOD, -a[1] * t % Q_MOD)
+
+
+G2_B = fq2_mul((3, 0), fq2_inv((9, 1)))  # 3 / (9 + u), bn256/curve.rs:85-98
+
+
+def g2_add(P, Q):
+    if P is None:
+        return Q
+    if Q is None:
+        return P
+    (x1, y1), (x2, y2) = P, Q
+    if x1 == x2:
+        if fq2_add(y1, y2) == (0, 0):
+            return None
+        lam = fq2_mul(fq2_mul((3, 0), fq2_mul(x1, x1)), fq2_inv(fq2_add(y1, y1)))
+    else:
+        lam = fq2_mul(fq2_sub(y2, y1), fq2_inv(fq2_sub(x2, x1)))
+    x3 = fq2_sub(fq2_sub(fq2_mul(lam, lam), x1), x2)
+    y3 = fq2_sub(fq2_mul(lam, fq2_sub(x1, x3)), y1)
+    return (x3, y3)
+
+
+def g2_mul(P, k):
+    k %= R_MOD
+    acc, add = None, P
+    while k:
+        if k & 1:
+            acc = g2_add(acc, add)
+        add = g2_add(add, add)
+        k >>= 1
+    return acc
+
+
+def g2_on_curve(P):
+    if P is None:
+        return True
+    x, y = P
+    return fq2_mul(y, y) == fq2_add(fq2_mul(fq2_mul(x, x), x), G2_B)
+
+
+def g2_affine_to_ints(limbs16):
+    a = np.asarray(limbs16, dtype=np.uint64).reshape(4, 4)
+    v = [from_mont(limbs_to_int(r), Q_MOD) for r in a]
+    if not any(limbs_to_int(r) for r in a):
+        return None
+    return ((v[0], v[1]), (v[2], v[3]))

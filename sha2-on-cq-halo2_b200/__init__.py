@@ -9,4 +9,4 @@ from . import _lib  # noqa: F401
 from . import arithmetic, cq, domain, evaluation, fields, kzg, lookup, permutation, prover  # noqa: F401
 from .arithmetic import G1, best_fft, best_multiexp, eval_polynomial, kate_division  # noqa: F401
 from .domain import EvaluationDomain  # noqa: F401
-from .kzg import DeviceBases, ParamsKZG, TableSRS  # noqa: F401
+from .kzg import MSMKZG, DeviceBases, ParamsKZG, TableSRS, batch_normalize  # noqa: F401

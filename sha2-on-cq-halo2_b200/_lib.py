@@ -46,6 +46,8 @@ SYMBOLS = [
     ("cqb_msm_bn254_g1_batch", _int, [_u64, _sz, u64p, _sz, _int, u64p, _ip]),
     ("cqb_msm_bn254_g1_batch_dev", _int, [_u64, _sz, _vp, _sz, _int, u64p, _ip]),
     ("cqb_msm_bn254_g1_host", _int, [u64p, u64p, _sz, u64p, _ip]),
+    ("cqb_g1_batch_normalize", _int, [u64p, _sz, u64p]),
+    ("cqb_msm_bn254_g1_jacobian", _int, [u64p, u64p, _sz, u64p, _ip]),
     ("cqb_msm_bn254_g1_sparse", _int, [_u64, u32p, u64p, _sz, u64p, _ip]),
     ("cqb_g1_sum_affine", _int, [u64p, _sz, u64p, _ip]),
     ("cqb_g1_sum_affine_dev", _int, [_vp, _sz, u64p, _ip]),
@@ -92,6 +94,9 @@ SYMBOLS = [
     ("cqb_fr_axpy_dev", _int, [_vp, u64p, _vp, _sz]),
     ("cqb_msm_bn254_g1_sparse_dev", _int, [_u64, _vp, _vp, _sz, u64p, _ip]),
     ("cqb_permutation_product_dev", _int, [_vp, _vp, _u32, _u32, u64p, u64p, u64p, u64p, u64p, u64p, _vp]),
+    ("cqb_g2_powers", _int, [u64p, _sz, u64p]),
+    ("cqb_msm_bn254_g2", _int, [u64p, u64p, _sz, u64p, _ip]),
+    ("cqb_g2_generator_mul_dev", _int, [_vp, _sz, _vp]),
     ("cqb_dev_alloc", _int, [_sz, ctypes.POINTER(_vp)]),
     ("cqb_dev_free", _int, [_vp]),
     ("cqb_memcpy_h2d", _int, [_vp, _vp, _sz]),

@@ -64,6 +64,7 @@ class StaticTableValues:
             "srs_g1 must be a device-resident SRS with at least `size` powers"
         self.size = size
         self.value_index_mapping = {bytes(v): i for i, v in enumerate(values)}
+        self._values = values.copy()
         k = size.bit_length() - 1
         lib = _lib.lib()
         dom = EvaluationDomain(2, k)
@@ -78,6 +79,31 @@ class StaticTableValues:
         _lib.check(lib.cqb_sync())
         self._dev_alloc = d_vals
         self.qs = DeviceBases.adopt(d_qs.value, size, precompute=False)
+
+    def commit(self, srs_g1_len, srs_g2, circuit_domain):
+        """reference plonk/static_lookup.rs:127-160 StaticTableValues::commit -> StaticCommittedTable { zv, t, x_b0_bound, size }:
+        zv = [s^N]G2 - G2 (:137); t = best_multiexp::<G2Affine>(ifft(table values), srs_g2) (:139-146) — the values are taken in the
+        order of value_index_mapping.keys(), a BTreeMap, i.e. SORTED by canonical value (derive/field.rs:128-141), as the reference
+        does; x_b0_bound = srs_g2[srs_g1_len - 1 - (circuit_domain - 2)] (:149). srs_g2: (>= N + 1, 16) uint64 G2Affine array."""
+        from . import _lib
+        from .domain import EvaluationDomain
+        from .fields import fr_from_limbs, fr_to_limbs
+
+        srs_g2 = np.ascontiguousarray(srs_g2, dtype=np.uint64)
+        N = self.size
+        assert srs_g2.ndim == 2 and srs_g2.shape[1] == 16 and srs_g2.shape[0] > N, "srs_g2 must hold the powers 0..N"
+        lib = _lib.lib()
+        out = np.zeros(16, np.uint64)
+        inf = ctypes.c_int(0)
+        pm = np.stack([fr_to_limbs(1), fr_to_limbs(R_MOD - 1)])
+        _lib.check(lib.cqb_msm_bn254_g2(_lib.p64(np.ascontiguousarray(srs_g2[[N, 0]])), _lib.p64(pm), 2, _lib.p64(out), ctypes.byref(inf)))
+        zv = out.copy()
+        order = sorted(range(N), key=lambda i: fr_from_limbs(self._values[i]))
+        coeffs = np.ascontiguousarray(self._values[order])
+        dom = EvaluationDomain(2, N.bit_length() - 1)
+        EvaluationDomain.ifft(coeffs, dom.omega_inv, dom.k, dom.ifft_divisor)
+        _lib.check(lib.cqb_msm_bn254_g2(_lib.p64(np.ascontiguousarray(srs_g2[:N])), _lib.p64(coeffs), N, _lib.p64(out), ctypes.byref(inf)))
+        return {"zv": zv, "t": out.copy(), "x_b0_bound": srs_g2[srs_g1_len - 1 - (circuit_domain - 2)].copy(), "size": srs_g1_len}
 
     def free(self):
         from . import _lib

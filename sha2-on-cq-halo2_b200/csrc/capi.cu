@@ -212,6 +212,7 @@ void cqb_shutdown(void) {
             poly_release_all();
             products_release_all();
             evalh_release_all();
+            g2_release_all();
         }
         if (g_copy->s) {
             for (auto& e : g_copy->ev) cudaEventDestroy(e);
@@ -429,7 +430,15 @@ int cqb_bases_precompute(cqb_bases_t h, int window_bits) {
     size_t bytes = (size_t)nwin * bs.n * 64;
     size_t free_b = 0, total_b = 0;
     CQB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    if (bytes > free_b / 2) return fail(CQB_E_OOM, "precomputed table needs %zu bytes, only %zu free", bytes, free_b);
+    // Memory plan: the table may take what is free minus the working set an MSM over this set needs afterwards —
+    // the bucket-sorted list (nwin x n x 4 B), the scalars (n x 32 B), histograms / bucket arrays / chunk partials (< 2 GiB) — and a
+    // reserve of 1/16 of the device for the caller's polynomials. With window_bits = 0 (automatic) a set whose table does not fit simply
+    // stays on the windowed layout (16 windows instead of 13: ~20 % slower, results identical); an explicit window size fails loudly.
+    const size_t need_after = bs.n * ((size_t)nwin * 4 + 32) + ((size_t)2 << 30) + total_b / 16;
+    if (bytes + need_after > free_b) {
+        if (window_bits == 0) return 0;
+        return fail(CQB_E_OOM, "precomputed table needs %zu bytes (+ %zu of MSM working set), only %zu free", bytes, need_after, free_b);
+    }
     if (cudaMalloc(&bs.table, bytes) != cudaSuccess) { cudaGetLastError(); bs.table = nullptr; return fail(CQB_E_OOM, "cudaMalloc(%zu) for the precomputed table failed", bytes); }
     bs.table_c = c;
     int rc = msm_precompute_table(bs.d, bs.n, c, bs.table);
@@ -751,6 +760,36 @@ int cqb_msm_bn254_g1_host(const uint64_t* affine_xy, const uint64_t* scalars, si
         CQB_CUDA(cudaMemcpyAsync(g_tmp_bases->p, affine_xy, n * 64, cudaMemcpyHostToDevice, g_ctx.stream));
         CQB_CUDA(cudaMemcpyAsync(g_scalars->p, scalars, n * 32, cudaMemcpyHostToDevice, g_ctx.stream));
     }
+    CQB_TRY(msm_run(g_tmp_bases->p, 0, g_scalars->p, nullptr, n, g_out->p));
+    return fetch_result(out_xy, is_inf);
+}
+
+// MSMKZG::eval (poly/kzg/msm.rs:65-70): the bases are PROJECTIVE (E::G1, Jacobian x, y, z; 96 B each): batch_normalize
+// (derive/curve.rs:362-397) on the device, then the MSM. Verifier-side and small; one-shot like cqb_msm_bn254_g1_host.
+int cqb_g1_batch_normalize(const uint64_t* jacobian_xyz, size_t n, uint64_t* affine_xy_out) {
+    LOCK;
+    CQB_TRY(require_init());
+    if ((!jacobian_xyz || !affine_xy_out) && n) return fail(CQB_E_BAD_ARG, "cqb_g1_batch_normalize: NULL argument");
+    CQB_TRY(g_tmp_bases->ensure(n * 160 + 64));
+    char* d_jac = (char*)g_tmp_bases->p + n * 64;
+    if (n) CQB_CUDA(cudaMemcpyAsync(d_jac, jacobian_xyz, n * 96, cudaMemcpyHostToDevice, g_ctx.stream));
+    CQB_TRY(g1_batch_normalize_run(d_jac, n, g_tmp_bases->p));
+    if (n) CQB_CUDA(cudaMemcpyAsync(affine_xy_out, g_tmp_bases->p, n * 64, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return 0;
+}
+int cqb_msm_bn254_g1_jacobian(const uint64_t* jacobian_xyz, const uint64_t* scalars, size_t n, uint64_t out_xy[8], int* is_inf) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!out_xy || ((!scalars || !jacobian_xyz) && n)) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1_jacobian: NULL argument");
+    CQB_TRY(g_tmp_bases->ensure(n * 160 + 64));
+    CQB_TRY(g_scalars->ensure(n * 32 + 32));
+    char* d_jac = (char*)g_tmp_bases->p + n * 64;
+    if (n) {
+        CQB_CUDA(cudaMemcpyAsync(d_jac, jacobian_xyz, n * 96, cudaMemcpyHostToDevice, g_ctx.stream));
+        CQB_CUDA(cudaMemcpyAsync(g_scalars->p, scalars, n * 32, cudaMemcpyHostToDevice, g_ctx.stream));
+    }
+    CQB_TRY(g1_batch_normalize_run(d_jac, n, g_tmp_bases->p));
     CQB_TRY(msm_run(g_tmp_bases->p, 0, g_scalars->p, nullptr, n, g_out->p));
     return fetch_result(out_xy, is_inf);
 }
@@ -1345,6 +1384,47 @@ int cqb_memcpy_h2d_on(int slot, void* d_dst, const void* h_src, size_t bytes) {
     if (e != cudaSuccess) return fail(CQB_E_CUDA, "cudaMemcpy to slot %d failed: %s", slot, cudaGetErrorString(e));
     return 0;
 }
+// ---- G2: the verifier-side half of the SRS and the CQ table commitment (keygen-time, primary device) ----------------------
+int cqb_g2_generator_mul_dev(const void* d_scalars, size_t n, void* d_out_affine) {
+    LOCK;
+    CQB_TRY(require_init());
+    if ((!d_scalars || !d_out_affine) && n) return fail(CQB_E_BAD_ARG, "cqb_g2_generator_mul_dev: NULL argument");
+    return g2_mul_run(nullptr, d_scalars, n, d_out_affine);
+}
+int cqb_g2_powers(const uint64_t s[4], size_t count, uint64_t* g2_affine_out) {
+    LOCK;
+    CQB_TRY(require_init());
+    if ((!s || !g2_affine_out) && count) return fail(CQB_E_BAD_ARG, "cqb_g2_powers: NULL argument");
+    if (count == 0) return 0;
+    CQB_TRY(g_io.ensure(count * 32 + count * 128));
+    void* d_pw = g_io.p;
+    void* d_out = (char*)g_io.p + count * 32;
+    CQB_TRY(fr_powers_run(s, count, d_pw));
+    CQB_TRY(g2_mul_run(nullptr, d_pw, count, d_out));
+    CQB_CUDA(cudaMemcpyAsync(g2_affine_out, d_out, count * 128, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return 0;
+}
+int cqb_msm_bn254_g2(const uint64_t* g2_affine, const uint64_t* scalars, size_t n, uint64_t out_xy[16], int* is_inf) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (!out_xy || ((!g2_affine || !scalars) && n)) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g2: NULL argument");
+    CQB_TRY(g_io.ensure(n * 160 + 256));
+    char* d_b = (char*)g_io.p + 256;
+    char* d_s = d_b + n * 128;
+    if (n) {
+        CQB_CUDA(cudaMemcpyAsync(d_b, g2_affine, n * 128, cudaMemcpyHostToDevice, g_ctx.stream));
+        CQB_CUDA(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, g_ctx.stream));
+    }
+    CQB_TRY(g2_msm_run(d_b, d_s, n, g_io.p));
+    CQB_TRY(g_out_host->ensure(256));
+    CQB_CUDA(cudaMemcpyAsync(g_out_host->p, g_io.p, 144, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    memcpy(out_xy, g_out_host->p, 128);
+    if (is_inf) *is_inf = (int)((uint32_t*)g_out_host->p)[32];
+    return 0;
+}
+
 int cqb_msm_set_window_bits(int c) {
     LOCK;
     if (c != 0 && (c < 2 || c > 16)) return fail(CQB_E_BAD_ARG, "window bits must be 0 (auto) or 2..16");

@@ -67,6 +67,7 @@ int msm_precompute_window_bits(size_t n);
 int msm_windows_for(int c);
 int msm_precompute_table(const void* d_bases, size_t n, int c, void* d_table);
 int g1_sum_affine_run(const void* d_points, size_t n, void* d_out_xy_flag);
+int g1_batch_normalize_run(const void* d_jacobian, size_t n, void* d_affine);
 void msm_release_all();
 void msm_set_window_bits(int c);
 void msm_set_profiling(bool on);
@@ -117,6 +118,11 @@ int fr_batch_invert_run(void* d_a, size_t n);
 int g1_generator_mul_run(const void* d_scalars, size_t n, void* d_out);
 int srs_setup_run(uint32_t k, const uint64_t s_limbs[4], void* d_g, void* d_g_lagrange, void* d_opening_at_0);
 void srs_release_all();
+
+// ---- g2.cu ----
+int g2_mul_run(const void* d_bases_or_null, const void* d_scalars, size_t n, void* d_out_affine);  // affine 128 B each
+int g2_msm_run(const void* d_bases, const void* d_scalars, size_t n, void* d_out_affine_flag);       // 128 B affine + uint32 identity flag
+void g2_release_all();
 
 // ---- gen.cu ----
 int synth_scalars_run(uint64_t seed, size_t start, size_t n, void* d_out);

@@ -967,6 +967,41 @@ __global__ void __launch_bounds__(128) msm_precompute_row_kernel(const uint4* __
     }
 }
 
+// ---- Curve::batch_normalize (arithmetic/curves/src/derive/curve.rs:362-397): Jacobian (x, y, z) -> affine (x / z^2, y / z^3),
+// identities (z = 0) -> (0, 0). MSMKZG::eval (poly/kzg/msm.rs:65-70) normalises its projective bases this way before
+// best_multiexp. One thread per run of NORM_RUN points: prefix products of the z's, ONE inversion (safegcd), back substitution.
+constexpr int NORM_RUN = 16;
+__global__ void __launch_bounds__(128) g1_batch_normalize_kernel(const uint4* __restrict__ jac, size_t n, uint4* __restrict__ aff) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t p0 = t * NORM_RUN;
+    if (p0 >= n) return;
+    const int cnt = (int)((n - p0 < (size_t)NORM_RUN) ? (n - p0) : (size_t)NORM_RUN);
+    Fq pre[NORM_RUN];
+    Fq acc = Fq::one();
+#pragma unroll 1
+    for (int j = 0; j < cnt; j++) {
+        pre[j] = acc;
+        const Fq z = ld_fq(jac + (p0 + j) * 6 + 4);
+        if (!z.is_zero()) acc = fp_mul<FqP>(acc, z);
+    }
+    acc = fp_inv_safegcd<FqP>(acc);
+#pragma unroll 1
+    for (int j = cnt - 1; j >= 0; j--) {
+        const uint4* src = jac + (p0 + j) * 6;
+        const Fq z = ld_fq(src + 4);
+        Fq ax = Fq::zero(), ay = Fq::zero();
+        if (!z.is_zero()) {
+            const Fq zi = fp_mul<FqP>(pre[j], acc);  // 1 / z
+            acc = fp_mul<FqP>(acc, z);
+            const Fq zi2 = fp_sqr<FqP>(zi);
+            ax = fp_mul<FqP>(ld_fq(src), zi2);
+            ay = fp_mul<FqP>(ld_fq(src + 2), fp_mul<FqP>(zi2, zi));
+        }
+        st_fq(aff + (p0 + j) * 4, ax);
+        st_fq(aff + (p0 + j) * 4 + 2, ay);
+    }
+}
+
 // -------------------------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------------------------
@@ -1067,7 +1102,9 @@ int msm_precompute_window_bits(size_t n) {
     double best = 1e300;
     int best_c = 12;
     for (int c = 10; c <= 20; c++) {  // beyond 2^19 buckets the scatter's open write streams thrash L2
-        double cost = msm_windows_for(c) * (double)n * 10.0 + (double)((size_t)1 << (c - 1)) * 130.0;  // measured: tools/sweep_msm.py
+        // measured (tools/sweep_msm.py, r02): 0.149 ns per bucket addition, bucket reduction 0.18 ms + 0.9 ns per bucket (2^21 points:
+        // c = 20 5.78 ms, c = 17 5.99 ms — the 130 of round 1 kept c = 17 there and cost the 8-GPU run two extra windows)
+        double cost = msm_windows_for(c) * (double)n * 10.0 + (double)((size_t)1 << (c - 1)) * 60.0;
         if (cost < best) { best = cost; best_c = c; }
     }
     return best_c;
@@ -1495,6 +1532,15 @@ int msm_run_precomputed(const void* d_table, size_t table_n, int c, size_t offse
     if (s.list_cap >= ((size_t)1 << 32) || (size_t)s.nwin * table_n >= ((size_t)1 << 31))
         return fail(CQB_E_BAD_SIZE, "precomputed MSM: %zu x %d entries exceed the 32-bit index range", n, s.nwin);
     return msm_run_shape(d_table, d_scalars, d_idx, n, s, nparts > 0 ? nparts : auto_parts(n, s, d_idx), ready, feeder, d_out);
+}
+
+int g1_batch_normalize_run(const void* d_jacobian, size_t n, void* d_affine) {
+    if (n == 0) return 0;
+    const size_t threads = (n + NORM_RUN - 1) / NORM_RUN;
+    g1_batch_normalize_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx().stream>>>((const uint4*)d_jacobian, n, (uint4*)d_affine);
+    CQB_LAUNCHED();
+    CQB_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int g1_sum_affine_run(const void* d_points, size_t n, void* d_out) {

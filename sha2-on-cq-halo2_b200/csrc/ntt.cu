@@ -115,15 +115,6 @@ __global__ void __launch_bounds__(256, NTT_MIN_CTAS) ntt_pass_kernel(const __gri
     const uint32_t T = 1u << (a.r + a.q);
     uint4* slo = sm;
     uint4* shi = sm + T;
-    // the pass's twiddles, staged once per CTA: stage t of this pass uses w^((jlow | low << s0) << (L-1-s0-t)) with low < 2^t the
-    // row bits below t and jlow the CTA's column bits, i.e. 2^qt (2^r - 1) distinct values per CTA (qt = 0 in the first pass, whose
-    // twiddles depend on the row bits only). Entry (t, low, c) sits at ((2^t - 1 + low) << qt) | c. Fetching them up front, all
-    // independent and in flight together with the tile load, replaces three dependent L2 round trips per radix-4 step (the
-    // long-scoreboard stall ncu showed at 73-76 % multiplier activity) by shared-memory reads.
-    const uint32_t qt = a.first ? 0u : (uint32_t)a.q;
-    const uint32_t ntw = ((1u << a.r) - 1u) << qt;
-    uint4* wlo = sm + 2 * T;
-    uint4* whi = wlo + ntw;
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;
     const uint32_t blk = blockIdx.x;
     const size_t boff = (size_t)blockIdx.y << a.L;  // batched transforms: member blockIdx.y of gridDim.y independent vectors
@@ -135,13 +126,6 @@ __global__ void __launch_bounds__(256, NTT_MIN_CTAS) ntt_pass_kernel(const __gri
         hi = blk >> (a.s0 - a.q);
     }
     // ---- load ----------------------------------------------------------------------------------------------------
-    for (uint32_t e = tid; e < ntw; e += nthr) {
-        const uint32_t c = e & ((1u << qt) - 1u), rp = (e >> qt) + 1u;       // rp = 2^t + low
-        const uint32_t t = 31u - (uint32_t)__clz(rp), low = rp - (1u << t);
-        const uint32_t jlow = a.first ? 0u : (c | (lo << a.q));
-        const Fr w = ldg_fr(a.tw, (size_t)((jlow | (low << a.s0)) << (a.L - 1 - a.s0 - (int)t)));
-        sm_st(wlo, whi, e, w);
-    }
     for (uint32_t e = tid; e < T; e += nthr) {
         uint32_t row = e >> a.q, col = e & qmask;
         Fr v;
@@ -180,15 +164,16 @@ __global__ void __launch_bounds__(256, NTT_MIN_CTAS) ntt_pass_kernel(const __gri
         const bool first_step = a.first && t == 0;
         for (uint32_t qd = tid; qd < (T >> 2); qd += nthr) {
             const uint32_t c = qd & qmask, rq = qd >> a.q;
+            const uint32_t jlow = a.first ? 0u : (c | (lo << a.q));
             const uint32_t r00 = ((rq >> t) << (t + 2)) | (rq & ((1u << t) - 1u));
             const uint32_t r01 = r00 | (1u << t), r10 = r00 | (2u << t), r11 = r00 | (3u << t);
             const uint32_t e00 = (r00 << a.q) | c, e01 = (r01 << a.q) | c, e10 = (r10 << a.q) | c, e11 = (r11 << a.q) | c;
             const uint32_t low_t = r00 & ((1u << t) - 1u);
-            const uint32_t cw = a.first ? 0u : c;
-            const uint32_t tw0 = ((((1u << t) - 1u) + low_t) << qt) | cw;                      // stage t (same for both pairs)
-            const uint32_t tw1a = ((((2u << t) - 1u) + low_t) << qt) | cw;                     // stage t+1, rows r00 / r10
-            const uint32_t tw1b = ((((2u << t) - 1u) + (low_t | (1u << t))) << qt) | cw;       // stage t+1, rows r01 / r11
-            const Fr w1b = sm_ld(wlo, whi, tw1b);
+            const int s = a.s0 + t;
+            const uint32_t tw0 = (jlow | (low_t << a.s0)) << (a.L - 1 - s);              // stage t (same for both pairs)
+            const uint32_t tw1a = (jlow | (low_t << a.s0)) << (a.L - 2 - s);              // stage t+1, rows r00 / r10
+            const uint32_t tw1b = (jlow | ((low_t | (1u << t)) << a.s0)) << (a.L - 2 - s);  // stage t+1, rows r01 / r11
+            const Fr w1b = ldg_fr(a.tw, tw1b);
             if (first_step) {  // tw0 == tw1a == 0 on every lane
                 Fr x00 = sm_ld(slo, shi, e00), x01 = sm_ld(slo, shi, e01), x10 = sm_ld(slo, shi, e10), x11 = sm_ld(slo, shi, e11);
                 butterfly_1(x00, x01);
@@ -197,7 +182,7 @@ __global__ void __launch_bounds__(256, NTT_MIN_CTAS) ntt_pass_kernel(const __gri
                 butterfly_w(x01, x11, w1b);
                 sm_st(slo, shi, e00, x00); sm_st(slo, shi, e01, x01); sm_st(slo, shi, e10, x10); sm_st(slo, shi, e11, x11);
             } else {
-                const Fr w0 = sm_ld(wlo, whi, tw0), w1a = sm_ld(wlo, whi, tw1a);
+                const Fr w0 = ldg_fr(a.tw, tw0), w1a = ldg_fr(a.tw, tw1a);
                 Fr x00 = sm_ld(slo, shi, e00), x01 = sm_ld(slo, shi, e01), x10 = sm_ld(slo, shi, e10), x11 = sm_ld(slo, shi, e11);
                 butterfly_w(x00, x01, w0);
                 butterfly_w(x10, x11, w0);
@@ -212,13 +197,15 @@ __global__ void __launch_bounds__(256, NTT_MIN_CTAS) ntt_pass_kernel(const __gri
         const bool first_stage = a.first && t == 0;  // a one-stage first pass (tiny transforms): every twiddle is 1
         for (uint32_t b = tid; b < (T >> 1); b += nthr) {
             const uint32_t c = b & qmask, rb = b >> a.q;
+            const uint32_t jlow = a.first ? 0u : (c | (lo << a.q));
             const uint32_t r0 = ((rb >> t) << (t + 1)) | (rb & ((1u << t) - 1u));
             const uint32_t r1 = r0 | (1u << t);
             const uint32_t e0 = (r0 << a.q) | c, e1 = (r1 << a.q) | c;
-            const uint32_t twi = ((((1u << t) - 1u) + (r0 & ((1u << t) - 1u))) << qt) | (a.first ? 0u : c);
+            const int s = a.s0 + t;
+            const uint32_t twi = (jlow | ((r0 & ((1u << t) - 1u)) << a.s0)) << (a.L - 1 - s);
             Fr x = sm_ld(slo, shi, e0), y = sm_ld(slo, shi, e1);
             if (first_stage) butterfly_1(x, y);
-            else butterfly_w(x, y, sm_ld(wlo, whi, twi));
+            else butterfly_w(x, y, ldg_fr(a.tw, twi));
             sm_st(slo, shi, e0, x); sm_st(slo, shi, e1, y);
         }
         __syncthreads();
@@ -439,8 +426,7 @@ int ntt_run(const void* d_src, void* d_dst, uint32_t L, const uint64_t omega[4],
         unsigned grid = (unsigned)(n >> (a.r + a.q));
         int threads = T >> 2;
         if (threads < 1) threads = 1;
-        const size_t ntw = (((size_t)1 << a.r) - 1) << (p == 0 ? 0 : a.q);  // staged twiddles of the pass
-        ntt_pass_kernel<<<dim3(grid, batch), threads, ((size_t)T + ntw) * 32, st>>>(a);
+        ntt_pass_kernel<<<dim3(grid, batch), threads, (size_t)T * 32, st>>>(a);
         CQB_LAUNCHED();
         CQB_CUDA(cudaGetLastError());
         s0 += a.r;

@@ -111,7 +111,9 @@ class ParamsKZG:
         self.k, self.n = k, n
         self.g = DeviceBases.adopt(d.value, n, precompute)
         self.g_lagrange = DeviceBases.adopt(d.value + n * 64, n, precompute)
-        self.g2 = self.s_g2 = None
+        # g2 = G2 generator, s_g2 = [s]G2 (:265-266): the first two G2 powers, as the 128-byte raw blobs write() emits
+        p2 = g2_powers(s, 2)
+        self.g2, self.s_g2 = p2[0].tobytes(), p2[1].tobytes()
         self._dev_alloc = d
         return self
 
@@ -178,6 +180,50 @@ class ParamsKZG:
             self._dev_alloc = None
 
 
+def g2_powers(s, count):
+    """[s^i] G2 for i < count as a (count, 16) uint64 G2Affine array (poly/kzg/commitment.rs:94-104, 114-141; 265-266 for i = 1)"""
+    out = np.zeros((count, 16), np.uint64)
+    _lib.check(_lib.lib().cqb_g2_powers(_lib.p64(_lib.fr_limbs(s)), count, _lib.p64(out)))
+    return out
+
+
+class MSMKZG:
+    """reference poly/kzg/msm.rs:12-80: a multiscalar multiplication collected term by term with PROJECTIVE bases (E::G1); eval()
+    normalises them (Curve::batch_normalize) and calls best_multiexp — here one device call does both."""
+
+    def __init__(self):
+        self.scalars, self.bases = [], []  # (4,) uint64 Fr ; (12,) uint64 Jacobian x, y, z
+
+    def append_term(self, scalar, point_jacobian):  # :41-44
+        self.scalars.append(np.asarray(scalar, dtype=np.uint64).reshape(4))
+        self.bases.append(np.asarray(point_jacobian, dtype=np.uint64).reshape(12))
+
+    def add_msm(self, other):  # :46-49
+        self.scalars.extend(other.scalars)
+        self.bases.extend(other.bases)
+
+    def eval(self):  # :65-70
+        n = len(self.scalars)
+        sc = np.ascontiguousarray(np.stack(self.scalars)) if n else np.zeros((0, 4), np.uint64)
+        bs = np.ascontiguousarray(np.stack(self.bases)) if n else np.zeros((0, 12), np.uint64)
+        out = np.zeros(8, np.uint64)
+        inf = ctypes.c_int(0)
+        _lib.check(_lib.lib().cqb_msm_bn254_g1_jacobian(_lib.p64(bs), _lib.p64(sc), n, _lib.p64(out), ctypes.byref(inf)))
+        return G1(out, inf.value)
+
+    def check(self):  # :60-62
+        return self.eval().is_identity
+
+
+def batch_normalize(points_jacobian):
+    """Curve::batch_normalize (arithmetic/curves/src/derive/curve.rs:362-397): (n, 12) Jacobian -> (n, 8) affine, identities -> zeros"""
+    p = np.ascontiguousarray(points_jacobian, dtype=np.uint64)
+    assert p.ndim == 2 and p.shape[1] == 12
+    out = np.zeros((p.shape[0], 8), np.uint64)
+    _lib.check(_lib.lib().cqb_g1_batch_normalize(_lib.p64(p), p.shape[0], _lib.p64(out)))
+    return out
+
+
 class TableSRS:
     """reference commitment.rs:42-47 (G1 parts): g1, g1_lagrange, g_lagrange_opening_at_0, device resident"""
 
@@ -189,8 +235,9 @@ class TableSRS:
         self._dev_alloc = None
 
     @classmethod
-    def setup_from_toxic_waste(cls, max_g1_power, s, precompute=None):
-        """reference commitment.rs:73-178 (G1 parts; the G2 powers are verifier/keygen-side): generated on the device"""
+    def setup_from_toxic_waste(cls, max_g1_power, s, precompute=None, max_g2_power=None):
+        """reference commitment.rs:73-178: generated on the device. max_g2_power: also build g2 = [s^i]G2, i <= max_g2_power (:94-104),
+        as a host (count, 16) uint64 array — keygen / verifier-side data (StaticTableValues.commit reads it)"""
         g1_len = max_g1_power + 1
         assert g1_len & (g1_len - 1) == 0, "assert!(is_pow_2(g1_len))"  # commitment.rs:77
         log_len = g1_len.bit_length() - 1
@@ -205,6 +252,7 @@ class TableSRS:
         self.g1 = DeviceBases.adopt(d.value, g1_len, precompute)
         self.g1_lagrange = DeviceBases.adopt(d.value + g1_len * 64, g1_len, precompute)
         self.g_lagrange_opening_at_0 = DeviceBases.adopt(d.value + 2 * g1_len * 64, g1_len, precompute)
+        self.g2 = g2_powers(s, max_g2_power + 1) if max_g2_power is not None else None
         self._dev_alloc = d
         return self
 

@@ -215,3 +215,37 @@ def test_msm_2p23_full_vs_oracle(env, oracle):
 def test_msm_2p26_full_vs_oracle(env, oracle):
     """top of the sweep (about a minute of CPU for the oracle)"""
     _full_msm_vs_oracle(env, oracle, 26, host_paths=False)
+
+
+@pytest.mark.slow
+def test_commit_identity_at_k26_both_srs_vectors(env, oracle):
+    """BASELINE.json configs[4]'s "largest k": ParamsKZG at k = 26 generated on the device (g and g_lagrange: 8 GiB), BOTH per-SRS
+    tables resident (2 x 52 GiB at c = 20 — DESIGN.md section 2's memory plan), and the reference's own commitment identity
+    (poly/kzg/commitment.rs:570-593 test_commit_lagrange): commit(lagrange_to_coeff(a)) == commit_lagrange(a), on 2^26 points."""
+    cq, L, lib = env
+    k = 26
+    n = 1 << k
+    s = oracle.synth_scalars(0x26, 1)[0]
+    params = cq.ParamsKZG.setup_from_toxic_waste(k, s, precompute=True)
+    dv = Dev(L, lib)
+    try:
+        assert lib.cqb_bases_precomputed_window_bits(params.g.handle) >= 16, "the table of g did not fit"
+        assert lib.cqb_bases_precomputed_window_bits(params.g_lagrange.handle) >= 16, "the table of g_lagrange did not fit"
+        d_a = dv.alloc(n * 32)
+        L.check(lib.cqb_synth_scalars_dev(0x2626, 0, n, d_a))
+        c_lagrange = _msm_dev(L, lib, params.g_lagrange.handle, d_a, n)
+        dom = cq.EvaluationDomain(1, k)
+        L.check(lib.cqb_intt_bn254_fr_dev(d_a, L.p64(dom.omega_inv), L.p64(dom.ifft_divisor), k))
+        c_coeff = _msm_dev(L, lib, params.g.handle, d_a, n)
+        assert c_lagrange.any() and np.array_equal(c_coeff, c_lagrange)
+        # anchor to the oracle on a prefix: the first 2^16 coefficients against the first 2^16 powers of the SRS
+        m = 1 << 16
+        sc = _d2h(L, lib, d_a, (m, 4))
+        g_host = np.zeros((m, 8), np.uint64)
+        L.check(lib.cqb_bases_download(params.g.handle, 0, m, L.p64(g_host)))
+        _, exp = oracle.best_multiexp(sc, g_host, oracle.hw_threads())
+        # a short commitment falls below 1/8 of the set and takes the windowed layout on the same resident bases
+        assert np.array_equal(_msm_dev(L, lib, params.g.handle, d_a, m), exp)
+    finally:
+        dv.free()
+        params.free()

@@ -440,3 +440,35 @@ def test_msm_parts_do_not_change_result(cq, oracle, parts):
         finally:
             cq._lib.check(lib.cqb_msm_set_parts(0))
         dev.free()
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 17, 100, 1000, 5000])
+def test_msmkzg_eval_and_batch_normalize_parity(cq, oracle, n):
+    """poly/kzg/msm.rs:65-70 MSMKZG::eval: Jacobian bases -> batch_normalize (derive/curve.rs:362-397) -> best_multiexp"""
+    rng = np.random.default_rng(40 + n)
+    aff = oracle.synth_bases(0xE7A1 + n, max(n, 1), 2)[:n]
+    sc = oracle.synth_scalars(0xE7A2 + n, max(n, 1))[:n]
+    # non-trivial z: scale every point by a random scalar in Jacobian form (g1_mul_a returns Jacobian), keep the multiplier's inverse in the scalar
+    jac = np.zeros((n, 12), np.uint64)
+    for i in range(n):
+        jac[i] = oracle.g1_mul_a(aff[i], oracle.synth_scalars(0xE7A3 + i, 1)[0])
+    if n >= 17:
+        jac[3] = 0                     # identity (z = 0)
+        jac[5, 8:] = 0                 # z = 0 with junk x, y: still the identity
+        sc[7] = 0
+    exp_aff = oracle.g1_batch_normalize(jac) if n else np.zeros((0, 8), np.uint64)
+    assert np.array_equal(cq.batch_normalize(jac), exp_aff)
+    m = cq.MSMKZG()
+    for i in range(n):
+        m.append_term(sc[i], jac[i])
+    got = m.eval()
+    if n:
+        _, exp = oracle.best_multiexp(sc, exp_aff, 4)
+    else:
+        exp = np.zeros(8, np.uint64)
+    assert np.array_equal(got.to_affine(), exp)
+    # check(): sum s_i P_i + (-sum) == identity
+    if n >= 2:
+        tot = oracle.g1_mul_a(got.to_affine(), P.int_to_limbs(P.to_mont(P.R_MOD - 1, P.R_MOD))) if got.to_affine().any() else np.zeros(12, np.uint64)
+        m.append_term(P.int_to_limbs(P.to_mont(1, P.R_MOD)), tot)
+        assert m.check()

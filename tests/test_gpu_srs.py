@@ -225,3 +225,57 @@ def test_eval_polynomial_and_kate_division(cq, oracle, n):
     assert q.shape == (n - 1, 4)
     if n > 1:
         assert np.array_equal(q, oracle.kate_division(a, x))
+
+
+def test_g2_powers_and_table_commit_parity(cq, oracle):
+    """The G2 half of the SRS and the CQ table commitment: [s^i]G2 (poly/kzg/commitment.rs:94-104, 265-266) and StaticTableValues::commit
+    (plonk/static_lookup.rs:127-160: zv, t = G2 multiexp over the SORTED table values' coefficients, x_b0_bound) vs the oracle"""
+    N, k_circ = 64, 5
+    s = oracle.synth_scalars(0x62, 1)[0]
+    srs = cq.TableSRS.setup_from_toxic_waste(N - 1, s, precompute=False, max_g2_power=N)
+    exp_g2 = oracle.g2_powers(s, N + 1)
+    assert np.array_equal(srs.g2, exp_g2)
+    assert np.array_equal(srs.g2[0], oracle.g2_generator())
+    # G2 multiexp with edge scalars / an identity base
+    sc = oracle.synth_scalars(0x63, N)
+    sc[0] = 0
+    sc[1] = P.int_to_limbs(P.to_mont(P.R_MOD - 1, P.R_MOD))
+    bases = exp_g2[:N].copy()
+    bases[2] = 0
+    out = np.zeros(16, np.uint64)
+    inf = ctypes.c_int(0)
+    L = cq._lib
+    L.check(L.lib().cqb_msm_bn254_g2(L.p64(bases), L.p64(sc), N, L.p64(out), ctypes.byref(inf)))
+    assert np.array_equal(out, oracle.g2_msm(bases, sc)) and inf.value == 0
+    L.check(L.lib().cqb_msm_bn254_g2(L.p64(bases), L.p64(np.zeros((N, 4), np.uint64)), N, L.p64(out), ctypes.byref(inf)))
+    assert inf.value == 1 and not out.any()
+    # table commitment
+    rng = np.random.default_rng(4)
+    vals = P.fr_array_from_ints([int(v) for v in rng.choice(1 << 40, N, replace=False)])
+    table = cq.cq.StaticTableValues(vals, srs.g1)
+    ct = table.commit(N, srs.g2, 1 << k_circ)
+    assert np.array_equal(ct["zv"], oracle.g2_add_aa(exp_g2[N], oracle.g2_neg_a(exp_g2[0])))
+    order = sorted(range(N), key=lambda i: P.fr_array_to_ints(vals[i:i + 1])[0])
+    od = oracle.domain_new(2, 6)
+    coeffs = oracle.lagrange_to_coeff(od, np.ascontiguousarray(vals[order]))
+    assert np.array_equal(ct["t"], oracle.g2_msm(exp_g2[:N], coeffs))
+    assert np.array_equal(ct["x_b0_bound"], exp_g2[N - 1 - ((1 << k_circ) - 2)]) and ct["size"] == N
+    table.free()
+    srs.free()
+    # ParamsKZG: g2 / s_g2 come with the setup now, so the params can be written and read back without external blobs
+    import io
+
+    params = cq.ParamsKZG.setup_from_toxic_waste(5, s, precompute=False)
+    assert params.g2 == exp_g2[0].tobytes() and params.s_g2 == exp_g2[1].tobytes()
+    buf = io.BytesIO()
+    params.write(buf)
+    back = cq.ParamsKZG.read(io.BytesIO(buf.getvalue()), precompute=False)
+    assert back.k == 5 and back.s_g2 == params.s_g2
+    buf2 = io.BytesIO()
+    back.write(buf2)                     # read -> write round trip of host-built params (ADVICE r01)
+    assert buf2.getvalue() == buf.getvalue()
+    back.downsize(4)                     # and downsize on params that came from a file
+    fresh = cq.ParamsKZG.setup_from_toxic_waste(4, s, precompute=False)
+    assert np.array_equal(back.g_lagrange.to_host(), fresh.g_lagrange.to_host())
+    for p_ in (params, back, fresh):
+        p_.free()
