@@ -107,6 +107,10 @@ CQB_API int cqb_msm_bn254_g1_batch(cqb_bases_t b, size_t offset, const uint64_t*
 CQB_API int cqb_msm_bn254_g1_batch_dev(cqb_bases_t b, size_t offset, const void* d_scalars, size_t n, int batch, uint64_t* out_xy, int* is_inf);
 /* one-shot: bases and scalars both on the host (exact best_multiexp(&[Fr], &[G1Affine]) shape) */
 CQB_API int cqb_msm_bn254_g1_host(const uint64_t* affine_xy, const uint64_t* scalars, size_t n, uint64_t out_xy[8], int* is_inf);
+/* cqb_msm_bn254_g1_host keeps large host base slices resident after their first use (key: pointer, length, fingerprint of the points;
+ * an SRS slice is immutable for the life of its params): the commit loops of a prover stop re-sending 64 B per point per call. Budget in
+ * bytes of device memory (default 1/8 of the device; 0 turns the cache off, as does CQB_HOST_BASES_CACHE=0 in the environment). */
+CQB_API int cqb_set_host_bases_cache(long long budget_bytes);
 /* sparse MSM sum_j scalars[j] * bases[idx[j]]: replaces the serial scalar-mul loops of the CQ prover for m(X), A(X),
  * Q_A(X), A_0(X) (plonk/static_lookup/prover.rs:167-170, 245-257) */
 /* MSMKZG::eval (poly/kzg/msm.rs:65-70): projective bases (E::G1 = Jacobian x, y, z Montgomery limbs, 96 B each; z = 0 is the

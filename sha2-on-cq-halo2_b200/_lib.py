@@ -48,6 +48,7 @@ SYMBOLS = [
     ("cqb_msm_bn254_g1_host", _int, [u64p, u64p, _sz, u64p, _ip]),
     ("cqb_g1_batch_normalize", _int, [u64p, _sz, u64p]),
     ("cqb_msm_bn254_g1_jacobian", _int, [u64p, u64p, _sz, u64p, _ip]),
+    ("cqb_set_host_bases_cache", _int, [ctypes.c_longlong]),
     ("cqb_msm_bn254_g1_sparse", _int, [_u64, u32p, u64p, _sz, u64p, _ip]),
     ("cqb_g1_sum_affine", _int, [u64p, _sz, u64p, _ip]),
     ("cqb_g1_sum_affine_dev", _int, [_vp, _sz, u64p, _ip]),

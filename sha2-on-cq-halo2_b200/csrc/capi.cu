@@ -87,6 +87,11 @@ struct BaseSet {
     std::vector<size_t> shard_start;   // first point of each child
 };
 static std::map<cqb_bases_t, BaseSet> g_bases;
+// resident copies of host base slices seen by cqb_msm_bn254_g1_host (see there)
+struct HostBasesEntry { const void* ptr; size_t n; uint64_t fp; cqb_bases_t h; unsigned uses; unsigned long long last; size_t bytes; };
+static std::vector<HostBasesEntry> g_hb_cache;
+static unsigned long long g_hb_clock = 0;
+static long long g_hb_budget = -1;  // -1: not decided yet
 static cqb_bases_t g_next_handle = 1;
 static PerDevice<Scratch> g_scalars, g_idx, g_tmp_bases, g_out;
 static Scratch g_io;
@@ -225,6 +230,7 @@ void cqb_shutdown(void) {
         c.inited = false;
     }
     g_bases.clear();
+    g_hb_cache.clear();
     g_nslots = 0;
     tl_slot = 0;
 }
@@ -750,10 +756,84 @@ int cqb_msm_bn254_g1_batch(cqb_bases_t h, size_t offset, const uint64_t* scalars
     return msm_batch_common(bs, offset, g_scalars->p, n, batch, out_xy, is_inf);
 }
 
+// ---- the generic best_multiexp(&[Fr], &[G1Affine]) call (arithmetic.rs:132): bases arrive as a host slice on EVERY call -------------
+// A prover calls it in loops over the SAME slice (params.g, params.g_lagrange: `commit` per advice column, per h piece, per opening
+// witness), and 64 B per point of upload dwarf the 32 B of scalars (1 GiB per call at 2^24). Large host slices are therefore kept
+// resident after their first use, keyed by (pointer, length, fingerprint): the fingerprint hashes 4096 spread points plus the first and
+// last 64 of the slice (~0.1 ms) — an SRS slice is immutable for the life of the
+// params, and any edit that keeps all of those points is not a case this call path has. From the second use on the slice is served by
+// a registered set (no upload), from the third by its precomputed table. CQB_HOST_BASES_CACHE=0 (environment) or
+// cqb_set_host_bases_cache(0) turns the cache off; its budget is a byte count (default 1/8 of the device), least recently used out first.
+constexpr size_t HB_MIN_POINTS = (size_t)1 << 14;
+
+static uint64_t hb_fingerprint(const uint64_t* p, size_t n) {
+    uint64_t h = 0xcbf29ce484222325ull ^ n;
+    auto mix = [&](size_t i) {
+        for (int k = 0; k < 8; k++) { h ^= p[i * 8 + k]; h *= 0x100000001b3ull; h ^= h >> 29; }
+    };
+    if (n <= 8192) { for (size_t i = 0; i < n; i++) mix(i); return h; }
+    for (size_t i = 0; i < 64; i++) { mix(i); mix(n - 1 - i); }
+    const size_t step = n / 4096;
+    for (size_t i = 0; i < 4096; i++) mix(i * step + (i % step));
+    return h;
+}
+static void hb_evict_until(size_t need) {
+    size_t used = 0;
+    for (auto& e : g_hb_cache) used += e.bytes;
+    while (!g_hb_cache.empty() && (long long)(used + need) > g_hb_budget) {
+        size_t v = 0;
+        for (size_t i = 1; i < g_hb_cache.size(); i++) if (g_hb_cache[i].last < g_hb_cache[v].last) v = i;
+        used -= g_hb_cache[v].bytes;
+        cqb_bases_free(g_hb_cache[v].h);
+        g_hb_cache.erase(g_hb_cache.begin() + v);
+    }
+}
+
+int cqb_set_host_bases_cache(long long budget_bytes) {
+    LOCK;
+    g_hb_budget = budget_bytes < 0 ? -1 : budget_bytes;
+    if (g_hb_budget >= 0) hb_evict_until(0);
+    return 0;
+}
+
 int cqb_msm_bn254_g1_host(const uint64_t* affine_xy, const uint64_t* scalars, size_t n, uint64_t out_xy[8], int* is_inf) {
     LOCK;
     CQB_TRY(require_init());
     if (!out_xy || ((!scalars || !affine_xy) && n)) return fail(CQB_E_BAD_ARG, "cqb_msm_bn254_g1_host: NULL argument");
+    if (g_hb_budget < 0) {
+        const char* e = getenv("CQB_HOST_BASES_CACHE");
+        size_t free_b = 0, total_b = 0;
+        if (e) g_hb_budget = atoll(e);
+        else g_hb_budget = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess ? (long long)(total_b / 8) : 0;
+    }
+    if (n >= HB_MIN_POINTS && g_hb_budget > 0 && (long long)(n * 64) <= g_hb_budget) {
+        const uint64_t fp = hb_fingerprint(affine_xy, n);
+        HostBasesEntry* hit = nullptr;
+        for (auto& e : g_hb_cache) if (e.ptr == affine_xy && e.n == n && e.fp == fp) { hit = &e; break; }
+        if (!hit) {
+            // a stale entry for the same pointer (freed and reallocated slice) goes first
+            for (size_t i = 0; i < g_hb_cache.size();) {
+                if (g_hb_cache[i].ptr == affine_xy) { cqb_bases_free(g_hb_cache[i].h); g_hb_cache.erase(g_hb_cache.begin() + i); } else i++;
+            }
+            hb_evict_until(n * 64);
+            cqb_bases_t h = 0;
+            if (cqb_bases_register(affine_xy, n, &h) == 0) {
+                g_hb_cache.push_back(HostBasesEntry{affine_xy, n, fp, h, 0, 0, n * 64});
+                hit = &g_hb_cache.back();
+            }
+        }
+        if (hit) {
+            hit->uses++;
+            hit->last = ++g_hb_clock;
+            if (hit->uses == 3 && n >= ((size_t)1 << 16)) {  // third use of the same slice: worth a table (memory-aware, may decline)
+                const size_t before = hit->bytes;
+                if (cqb_bases_precompute(hit->h, 0) == 0 && cqb_bases_precomputed_window_bits(hit->h) > 0)
+                    hit->bytes = before + (size_t)msm_windows_for(cqb_bases_precomputed_window_bits(hit->h)) * n * 64;
+            }
+            const cqb_bases_t h = hit->h;
+            return cqb_msm_bn254_g1(h, 0, scalars, n, out_xy, is_inf);
+        }
+    }
     CQB_TRY(g_tmp_bases->ensure(n * 64 + 64));
     CQB_TRY(g_scalars->ensure(n * 32 + 32));
     if (n) {

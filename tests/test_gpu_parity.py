@@ -472,3 +472,29 @@ def test_msmkzg_eval_and_batch_normalize_parity(cq, oracle, n):
         tot = oracle.g1_mul_a(got.to_affine(), P.int_to_limbs(P.to_mont(P.R_MOD - 1, P.R_MOD))) if got.to_affine().any() else np.zeros(12, np.uint64)
         m.append_term(P.int_to_limbs(P.to_mont(1, P.R_MOD)), tot)
         assert m.check()
+
+
+def test_generic_best_multiexp_keeps_host_bases_resident(cq, oracle):
+    """arithmetic.rs:132 called in a loop over the SAME bases slice (what `commit` does per column): the second call is served by the
+    resident copy, the third by its table; a different slice at the same address (or edited points) is a different fingerprint. Results
+    never change."""
+    lib = cq._lib.lib()
+    n = (1 << 16) + 77
+    bases = oracle.synth_bases(0xCAC4E, n, 4)
+    out0 = lib.cqb_launch_count()
+    for rep in range(4):
+        sc = oracle.synth_scalars(0xCAC5 + rep, n)
+        _, exp = oracle.best_multiexp(sc, bases, 8)
+        assert np.array_equal(cq.best_multiexp(sc, bases).to_affine(), exp), rep
+    # the same buffer refilled with other points: must not be served from the cache
+    bases[:] = oracle.synth_bases(0xCAC4F, n, 4)
+    sc = oracle.synth_scalars(0xCAD0, n)
+    _, exp = oracle.best_multiexp(sc, bases, 8)
+    assert np.array_equal(cq.best_multiexp(sc, bases).to_affine(), exp)
+    # cache off: same results
+    cq._lib.check(lib.cqb_set_host_bases_cache(0))
+    try:
+        assert np.array_equal(cq.best_multiexp(sc, bases).to_affine(), exp)
+    finally:
+        cq._lib.check(lib.cqb_set_host_bases_cache(-1))
+    assert lib.cqb_launch_count() > out0
