@@ -259,6 +259,7 @@ def main():
     ap.add_argument("--no-prove", action="store_true")
     ap.add_argument("--no-in-process", action="store_true", help="skip the one-process-N-devices leg (cqb_init_multi) at N > 1")
     ap.add_argument("--prove-k", type=lambda v: [int(x) for x in v.split(",")], default=[16, 20])
+    ap.add_argument("--prove-real-k", type=lambda v: [int(x) for x in v.split(",") if x], default=[14, 16])
     ap.add_argument("--ref-max-log", type=int, default=26)
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--no-precompute", action="store_true", help="windowed layout on the plain bases (no per-SRS table)")
@@ -533,6 +534,15 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import prove_workload
 
+        import prove_real
+
+        # a REAL proof (complete create_proof through the Blake2b transcript, checked: the quotient identity must hold at x)
+        line["prove_real_ms"] = [prove_real.run(cqb200, k, log_table=16, n_advice=8, reps=3) for k in args.prove_real_k]
+        line["prove_real_note"] = ("complete create_proof (sha2_on_cq_halo2_b200.prover: commit phase, evaluate_h, vanishing pieces, evaluations, GWC "
+                                   "openings) of a CQ-lookup circuit: 8 advice columns, one static lookup of (a0, a1) in two 2^16-row tables, permutation "
+                                   "over all columns; timed from the witness upload to the last opening witness; every proof checked against the "
+                                   "verifier's quotient identity. The reference has no SHA circuit (SURVEY F1); witness synthesis and hashing are CPU work "
+                                   "outside the path.")
         line["prove_ms"] = [prove_workload.run(cqb200, k, reps=2) for k in args.prove_k]
         line["prove_ms_resident"] = [prove_workload.run(cqb200, k, reps=2, resident=True) for k in args.prove_k]
         line["prove_ms_note"] = ("synthetic CQ-prover-shaped op list of SURVEY 8(d): 8 advice columns, one CQ lookup over a 2^16-row table. "

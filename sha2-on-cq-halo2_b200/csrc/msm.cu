@@ -677,6 +677,8 @@ __global__ void __launch_bounds__(128) msm_fold_parts_kernel(uint4* __restrict__
 }
 
 // the kernels from here to the precompute kernel are latency-bound chains of XYZZ operations: compact code (ec.cuh FqCall)
+// (round 2 re-check: inlined multiplications INSIDE the one non-inlined point addition / doubling of each kernel, 65 KB of code, are
+// slower again — bucket reduction 0.19 -> 0.32 ms at 2^16, 0.64 -> 0.76 ms at 2^24 — so the call form stays)
 typedef FqCall TailMul;
 // one copy of each point operation per kernel as well (a g1_add is still ~1.2k instructions around its 13 multiplier calls)
 __device__ __noinline__ G1Xyzz tail_add_fn(G1Xyzz a, G1Xyzz b) { g1_add<TailMul>(a, b); return a; }

@@ -56,6 +56,21 @@ def _commit(bases, d_ptr, count):
     return out
 
 
+def _commit_batch(bases, d_ptr, count, batch):
+    """`batch` commitments over vectors stored back to back (plonk/prover.rs:356-360 commits every advice column in a loop; the h pieces
+    likewise, vanishing/prover.rs:101-105): one launch sequence for all of them"""
+    outs = []
+    done = 0
+    while done < batch:
+        b = min(64, batch - done)
+        out = np.zeros((b, 8), np.uint64)
+        inf = (ctypes.c_int * b)()
+        _lib.check(_lib.lib().cqb_msm_bn254_g1_batch_dev(bases.handle, 0, _vp(d_ptr + done * count * 32), count, b, _lib.p64(out), inf))
+        outs.extend(out[i].copy() for i in range(b))
+        done += b
+    return outs
+
+
 def _eval(d_poly, n, point):
     out = np.zeros(4, np.uint64)
     _lib.check(_lib.lib().cqb_eval_polynomial_dev(_vp(d_poly), n, _lib.p64(fr_to_limbs(point)), _lib.p64(out)))
@@ -156,9 +171,10 @@ def create_proof(pk, advice_lagrange, lookups_m_sparse, rng, transcript):
             return d_e
 
         transcript.common_scalar(pk.vk_transcript_repr)                                   # prover.rs:85
-        d_adv = [ar.upload(a) for a in advice_lagrange]
-        for d in d_adv:                                                                    # :356-374 advice commitments
-            transcript.write_point(_commit(params.g_lagrange, d, n))
+        d_adv0 = ar.upload(np.concatenate([np.ascontiguousarray(a, dtype=np.uint64).reshape(n, 4) for a in advice_lagrange]))
+        d_adv = [d_adv0 + i * n * 32 for i in range(len(advice_lagrange))]
+        for pt in _commit_batch(params.g_lagrange, d_adv0, n, len(d_adv)):                 # :356-374 advice commitments
+            transcript.write_point(pt)
         theta = info["theta"] = transcript.squeeze_challenge_scalar()                      # :472
         # static lookups, first phase: f and m (static_lookup/prover.rs:51-184)
         d_f = []
@@ -212,8 +228,8 @@ def create_proof(pk, advice_lagrange, lookups_m_sparse, rng, transcript):
                                                    _lib.p64(dom.g_coset), _lib.p64(dom.g_coset_inv), _lib.p64(dom.t_evaluations),
                                                    dom.t_evaluations.shape[0]))
         npieces = dom.quotient_poly_degree
-        for i in range(npieces):
-            transcript.write_point(_commit(params.g, d_h + i * n * 32, n))
+        for pt in _commit_batch(params.g, d_h, n, npieces):
+            transcript.write_point(pt)
         x = info["x"] = transcript.squeeze_challenge_scalar()                              # prover.rs:627
         xn = pow(x, n, R_MOD)
         evals = info["evals"] = {}
@@ -289,6 +305,55 @@ def create_proof(pk, advice_lagrange, lookups_m_sparse, rng, transcript):
             transcript.write_point(_commit(params.g, d_wit, n - 1))
         for cld in clds:
             cld.free()
+        info["table_sizes"] = [lk.tables[0].size for lk in pk.static_lookups]
         return info
     finally:
         ar.free()
+
+
+def expected_h_eval(pk, info):
+    """What plonk/verifier.rs computes from the evaluations in the proof: the value h(x) must have for the quotient identity
+    h(X) (X^n - 1) = sum of the constraint terms folded with y to hold at x — the permutation terms (plonk/permutation/verifier.rs, the
+    same expressions as evaluation.rs:376-452) and the static-lookup terms (evaluation.rs:533-548; B(x) = B_0(x) x + B(0) with B(0) from
+    the sumcheck identity n B(0) = N A(0), static_lookup/prover.rs:315-325). Plain integer arithmetic: used by bench.py and the tests to
+    check a finished proof without a pairing."""
+    n, bf, omega = pk.n, pk.blinding_factors, pk.domain._omega
+    x, y, beta, gamma = info["x"], info["y"], info["beta"], info["gamma"]
+    e = info["evals"]
+    xn = pow(x, n, R_MOD)
+    inv = lambda a: pow(a % R_MOD, -1, R_MOD)  # noqa: E731
+
+    def lag_at(i):
+        wi = pow(omega, i, R_MOD)
+        return (xn - 1) * inv(n) % R_MOD * wi % R_MOD * inv(x - wi) % R_MOD
+
+    l0, l_last = lag_at(0), lag_at(n - bf - 1)
+    l_blind = sum(lag_at(i) for i in range(n - bf, n)) % R_MOD
+    l_act = (1 - (l_last + l_blind)) % R_MOD
+    adv_at = {}
+    for (c, rot), v in zip(pk.advice_queries, e["advice"]):
+        adv_at[(c, rot)] = v
+    exp = 0
+    zs = e["z"]
+    if zs:
+        exp = (exp * y + l0 * (1 - zs[0][0])) % R_MOD
+        exp = (exp * y + l_last * (zs[-1][0] * zs[-1][0] - zs[-1][0])) % R_MOD
+        for i in range(1, len(zs)):
+            exp = (exp * y + l0 * (zs[i][0] - zs[i - 1][2])) % R_MOD
+        chunk_len = pk.cs_degree - 2
+        cur = beta * x % R_MOD
+        for s_, (z_x, z_wx, _) in enumerate(zs):
+            cols = pk.permutation_columns[s_ * chunk_len:(s_ + 1) * chunk_len]
+            sig = e["sigma"][s_ * chunk_len:(s_ + 1) * chunk_len]
+            left, right = z_wx, z_x
+            for c, sg in zip(cols, sig):
+                a = adv_at[(c, 0)]
+                left = left * (a + beta * sg + gamma) % R_MOD
+                right = right * (a + cur + gamma) % R_MOD
+                cur = cur * permutation.FR_DELTA % R_MOD
+            exp = (exp * y + (left - right) * l_act) % R_MOD
+    for (b0_x, f_x, a_at_zero), N in zip(e["static_lookups"], info["table_sizes"]):
+        b_at_zero = (a_at_zero * N + (bf + 1) * inv(beta)) % R_MOD * inv(n) % R_MOD
+        b_x = (b0_x * x + b_at_zero) % R_MOD
+        exp = (exp * y + (b_x * (f_x * l_act + beta) - 1)) % R_MOD
+    return exp * inv(xn - 1) % R_MOD

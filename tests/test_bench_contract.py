@@ -39,7 +39,7 @@ def test_reference_arm_other_ranks_stay_silent():
 
 @pytest.mark.gpu
 def test_product_arm_line_has_roofline_e2e_and_cpu_baseline():
-    lines = _run(["--log-n", "20", "--ntt-log-n", "20", "--steps", "3", "--warmup", "3", "--prove-k", "12"])
+    lines = _run(["--log-n", "20", "--ntt-log-n", "20", "--steps", "3", "--warmup", "3", "--prove-k", "12", "--prove-real-k", "10"])
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert BASE_KEYS <= set(d) and "impl" not in d
@@ -53,3 +53,4 @@ def test_product_arm_line_has_roofline_e2e_and_cpu_baseline():
     assert d["gpu_launches"] > 0 and d["cpu_baseline"]["gpu_matches_cpu_on_sample"] is True
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert d["ntt"]["value"] > 0 and d["prove_ms"][0]["ms_per_proof"] > 0 and d["prove_ms_resident"][0]["ms_per_proof"] > 0
+    assert d["prove_real_ms"][0]["quotient_identity_holds"] is True and d["prove_real_ms"][0]["ms_per_proof"] > 0

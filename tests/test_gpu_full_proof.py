@@ -54,8 +54,11 @@ class Transcript(Blake2bWrite):
         super().write_point(np.ascontiguousarray(affine_limbs, dtype=np.uint64), self._o)
 
 
-@pytest.mark.parametrize("k,N", [(3, 16), (6, 64), (9, 128), (12, 1024)])
-def test_full_proof_bytes_and_verification(cq, oracle, k, N):
+@pytest.mark.parametrize("k,N,A", [(3, 16, 2), (6, 64, 2), (7, 32, 5), (9, 128, 3), (12, 1024, 2)])
+def test_full_proof_bytes_and_verification(cq, oracle, k, N, A):
+    """A advice columns: columns 0 and 1 carry the looked-up tuple, the others repeat them (so that the permutation can tie cells of
+    different columns together); cs_degree 4 => column sets of two, i.e. ceil(A / 2) permutation product polynomials chained through
+    their last rows (permutation/prover.rs:82-166, the omega^last openings of :320-340)"""
     O = oracle
     from sha2_on_cq_halo2_b200 import prover as PR
 
@@ -72,10 +75,12 @@ def test_full_proof_bytes_and_verification(cq, oracle, k, N):
     tvals = [[int(v) + (j << 40) for v in rng.choice(1 << 30, N, replace=False)] for j in range(2)]
     rows = [int(v) for v in rng.integers(0, N, usable)]
     adv = [[tv[r] for r in rows] + [int(v) for v in rng.integers(0, 1 << 50, n - usable)] for tv in tvals]
+    for j in range(2, A):
+        adv.append(adv[j % 2][:usable] + [int(v) for v in rng.integers(0, 1 << 50, n - usable)])
     omega = P.omega_for(k)
     delta = cq.permutation.FR_DELTA
     # sigma: identity permutation with a few cycles between equal cells (rows using the same table row hold equal values)
-    sig = [[pow(delta, j, R) * pow(omega, i, R) % R for i in range(n)] for j in range(2)]
+    sig = [[pow(delta, j, R) * pow(omega, i, R) % R for i in range(n)] for j in range(A)]
     seen = {}
     for i, r in enumerate(rows):
         if r in seen and len(seen) % 3 == 0:
@@ -83,9 +88,14 @@ def test_full_proof_bytes_and_verification(cq, oracle, k, N):
             for j in range(2):
                 sig[j][i0], sig[j][i] = sig[j][i], sig[j][i0]
         seen.setdefault(r, i)
+    for j in range(2, A):  # cross-column cycles: cell (j, i) holds the value of cell (j % 2, i) on the usable rows
+        for i in range(j, usable, 4):
+            sig[j][i], sig[j % 2][i] = sig[j % 2][i], sig[j][i]
+    chunk_len = cs_degree - 2
+    nsets = (A + chunk_len - 1) // chunk_len
     vk_repr = 0x1234ABCD + k
     rnd_poly = O.synth_scalars(0x4444 + k, n)
-    blind_rows = [O.synth_scalars(0xB11D + k, bf)]
+    blind_rows = [O.synth_scalars(0xB11D + k + 97 * s_, bf) for s_ in range(nsets)]
     b0_bound = np.ascontiguousarray(t_g1_big[Nt - (n - 1):])
     m = {}
     for r in rows:
@@ -97,7 +107,7 @@ def test_full_proof_bytes_and_verification(cq, oracle, k, N):
     en = 1 << ek
     th = 4
     ext_omega_limbs = odom.f("extended_omega")
-    advice_queries = [(0, 0), (1, 0)]
+    advice_queries = [(j, 0) for j in range(A)]
     x_rot = lambda x, rot: x * pow(omega, rot, R) % R if rot >= 0 else x * pow(pow(omega, -1, R), -rot, R) % R  # noqa: E731
 
     def lagrange_basis(rows_set):
@@ -115,15 +125,19 @@ def test_full_proof_bytes_and_verification(cq, oracle, k, N):
         for a in adv_l:
             t.write_point(O.best_multiexp(a, g_lagrange, th)[1])
         theta = info["theta"] = t.squeeze_challenge_scalar()
-        f_int = [(a0 * theta + a1) % R for a0, a1 in zip(*adv)]
+        f_int = [(a0 * theta + a1) % R for a0, a1 in zip(adv[0], adv[1])]
         t.write_point(O.best_multiexp(F(f_int), g_lagrange, th)[1])
         t.write_point(O.sparse_commit(t_lag, idx, mult))
         beta = info["beta"] = t.squeeze_challenge_scalar()
         gamma = info["gamma"] = t.squeeze_challenge_scalar()
-        z, _ = O.permutation_product(adv_l, [F(sg) for sg in sig], L1(beta), L1(gamma), L1(omega), L1(1), L1(1))
-        z[n - bf:] = blind_rows[0]
-        t.write_point(O.best_multiexp(z, g_lagrange, th)[1])
-        z_poly = O.lagrange_to_coeff(odom, z, th)
+        z_polys, dw, last_z = [], L1(1), L1(1)
+        for s_ in range(nsets):                                                    # permutation/prover.rs:82-186
+            sl = slice(s_ * chunk_len, (s_ + 1) * chunk_len)
+            z, dw = O.permutation_product(adv_l[sl], [F(sg) for sg in sig[sl]], L1(beta), L1(gamma), L1(omega), dw, last_z)
+            z[n - bf:] = blind_rows[s_]
+            last_z = z[n - bf - 1].copy()
+            t.write_point(O.best_multiexp(z, g_lagrange, th)[1])
+            z_polys.append(O.lagrange_to_coeff(odom, z, th))
         # commit_log_derivatives (static_lookup/prover.rs:187-342), the reference's per-index loop
         qs_host = [O.cq_table_qs(F(v), t_g1, th) for v in tvals]
         a_acc = qa_acc = a0_acc = None
@@ -160,8 +174,8 @@ def test_full_proof_bytes_and_verification(cq, oracle, k, N):
         one = L1(1)
         l_act = np.stack([O.fr_op("sub", one, O.fr_op("add", a, b)) for a, b in zip(l_last, l_blind)])
         h = np.zeros((en, 4), np.uint64)
-        h = O.permutation_h(h, 1 << (ek - k), -(bf + 1), cs_degree - 2, [O.coeff_to_extended(odom, z_poly, th)], adv_coset, sig_coset, l0, l_last, l_act,
-                            L1(beta), L1(gamma), L1(y), ext_omega_limbs)
+        h = O.permutation_h(h, 1 << (ek - k), -(bf + 1), chunk_len, [O.coeff_to_extended(odom, zp, th) for zp in z_polys], adv_coset, sig_coset, l0,
+                            l_last, l_act, L1(beta), L1(gamma), L1(y), ext_omega_limbs)
         h = O.cq_lookup_h(h, O.coeff_to_extended(odom, b_poly, th), O.coeff_to_extended(odom, f_poly, th), l_act, L1(beta), L1(y))
         h_coeff = O.extended_to_coeff(odom, O.divide_by_vanishing_poly(odom, h), th)
         pieces = [np.ascontiguousarray(h_coeff[i * n:(i + 1) * n]) for i in range(cs_degree - 1)]
@@ -182,16 +196,24 @@ def test_full_proof_bytes_and_verification(cq, oracle, k, N):
         sigma_evals = [ev(p, x) for p in sig_poly]
         for e in sigma_evals:
             t.write_scalar(e)
-        x_next = x_rot(x, 1)
-        z_cur, z_next = ev(z_poly, x), ev(z_poly, x_next)
-        t.write_scalar(z_cur)
-        t.write_scalar(z_next)
+        x_next, x_last = x_rot(x, 1), x_rot(x, -(bf + 1))
+        z_evals = []
+        for s_, zp in enumerate(z_polys):                                          # permutation/prover.rs:244-288
+            ze = [ev(zp, x), ev(zp, x_next), ev(zp, x_last) if s_ + 1 < nsets else None]
+            for e_ in ze:
+                if e_ is not None:
+                    t.write_scalar(e_)
+            z_evals.append(tuple(ze))
         b0_eval, f_eval = ev(b0_poly, x), ev(f_poly, x)
         for e in (b0_eval, f_eval, a_at_zero):
             t.write_scalar(e)
         h_eval = info["h_eval"] = ev(h_x_poly, x)
         queries = [(x_rot(x, rot), adv_poly[c], e) for (c, rot), e in zip(advice_queries, adv_evals)]
-        queries += [(x, z_poly, z_cur), (x_next, z_poly, z_next), (x, b0_poly, b0_eval), (x, f_poly, f_eval)]
+        for zp, ze in zip(z_polys, z_evals):                                       # permutation/prover.rs:304-340
+            queries += [(x, zp, ze[0]), (x_next, zp, ze[1])]
+        for zp, ze in list(zip(z_polys, z_evals))[::-1][1:]:
+            queries.append((x_last, zp, ze[2]))
+        queries += [(x, b0_poly, b0_eval), (x, f_poly, f_eval)]
         queries += [(x, p, e) for p, e in zip(sig_poly, sigma_evals)]
         queries += [(x, h_x_poly, h_eval), (x, rnd_poly, random_eval)]
         v = info["v"] = t.squeeze_challenge_scalar()
@@ -212,7 +234,7 @@ def test_full_proof_bytes_and_verification(cq, oracle, k, N):
             batch[0] = (batch[0] - eb) % R
             wit = O.kate_division(F(batch), L1(zpt))
             t.write_point(O.best_multiexp(np.ascontiguousarray(wit), g[: n - 1], th)[1])
-        info["evals"] = dict(advice=adv_evals, random=random_eval, sigma=sigma_evals, z=(z_cur, z_next), lk=(b0_eval, f_eval, a_at_zero))
+        info["evals"] = dict(advice=adv_evals, random=random_eval, sigma=sigma_evals, z=z_evals, lk=(b0_eval, f_eval, a_at_zero))
         return t, info
 
     # ------------------------------------------------------------------------------------------------- device prover
@@ -222,10 +244,11 @@ def test_full_proof_bytes_and_verification(cq, oracle, k, N):
         tables = [cq.cq.StaticTableValues(F(v), tsrs.g1) for v in tvals]
         bound = cq.DeviceBases(b0_bound)
         lk = PR.StaticLookup([0, 1], tsrs, tables, bound)
-        pk = PR.ProvingKey(params, k, cs_degree, bf, [0, 1], [F(sg) for sg in sig], advice_queries, [lk], vk_transcript_repr=vk_repr)
+        pk = PR.ProvingKey(params, k, cs_degree, bf, list(range(A)), [F(sg) for sg in sig], advice_queries, [lk], vk_transcript_repr=vk_repr)
         t = Transcript(O)
         try:
             info = PR.create_proof(pk, [F(c) for c in adv], [(idx, mult)], {"permutation_blinds": blind_rows, "random_poly": rnd_poly}, t)
+            info["expected_h"] = PR.expected_h_eval(pk, info)   # the verifier's side of the quotient identity, from the product module
         finally:
             pk.free()
             for tb in tables:
@@ -239,8 +262,9 @@ def test_full_proof_bytes_and_verification(cq, oracle, k, N):
     t_d, info_d = device_prover()
     for name in ("theta", "beta", "gamma", "y", "x", "v", "h_eval"):
         assert info_d[name] == info_o[name], name
-    npoints = 2 + 2 + 1 + 5 + 1 + (cs_degree - 1) + 2
-    nscalars = 2 + 1 + 2 + 2 + 3
+    npts_open = 2 + (1 if nsets > 1 else 0)                                    # distinct opening points: x, omega x, omega^last x
+    npoints = A + 2 + nsets + 5 + 1 + (cs_degree - 1) + npts_open
+    nscalars = A + 1 + A + (3 * nsets - 1) + 3
     assert len(t_o.proof) == 32 * (npoints + nscalars)
     assert bytes(t_d.proof) == bytes(t_o.proof), "proof bytes differ"
 
@@ -253,40 +277,66 @@ def test_full_proof_bytes_and_verification(cq, oracle, k, N):
     l0_x, l_last_x = lag_at(0), lag_at(n - bf - 1)
     l_blind_x = sum(lag_at(i) for i in range(n - bf, n)) % R
     l_act_x = (1 - (l_last_x + l_blind_x)) % R
-    a_x, sg_x, (z_x, z_wx) = e["advice"], e["sigma"], e["z"]
+    a_x, sg_x, zs = e["advice"], e["sigma"], e["z"]
     b0_x, f_x, a_at_zero = e["lk"]
     exp = 0
-    exp = (exp * y + l0_x * (1 - z_x)) % R
-    exp = (exp * y + l_last_x * (z_x * z_x - z_x)) % R
-    left, right, cur = z_wx, z_x, beta * x % R
-    for j in range(2):
-        left = left * (a_x[j] + beta * sg_x[j] + gamma) % R
-        right = right * (a_x[j] + cur + gamma) % R
-        cur = cur * delta % R
-    exp = (exp * y + (left - right) * l_act_x) % R
+    exp = (exp * y + l0_x * (1 - zs[0][0])) % R                                  # plonk/permutation/verifier.rs expressions
+    exp = (exp * y + l_last_x * (zs[-1][0] * zs[-1][0] - zs[-1][0])) % R
+    for i in range(1, nsets):
+        exp = (exp * y + l0_x * (zs[i][0] - zs[i - 1][2])) % R
+    cur = beta * x % R
+    for s_ in range(nsets):
+        left, right = zs[s_][1], zs[s_][0]
+        for j in range(s_ * chunk_len, min(A, (s_ + 1) * chunk_len)):
+            left = left * (a_x[j] + beta * sg_x[j] + gamma) % R
+            right = right * (a_x[j] + cur + gamma) % R
+            cur = cur * delta % R
+        exp = (exp * y + (left - right) * l_act_x) % R
     b_at_zero = (a_at_zero * N + (bf + 1) * inv(beta)) % R * inv(n) % R       # the sumcheck identity n B(0) = N A(0), solved for B(0)
     b_x = (b0_x * x + b_at_zero) % R
     exp = (exp * y + (b_x * (f_x * l_act_x + beta) - 1)) % R
     h_x_expected = exp * inv((xn - 1) % R) % R
     assert h_x_expected == info_d["h_eval"], "the quotient identity fails at x"
+    assert info_d["expected_h"] == h_x_expected, "prover.expected_h_eval disagrees with the verifier restated here"
     # GWC openings with the toxic s: sum_i v^i C_i - [sum_i v^i e_i] G == [s - z] W
     pts = [P.g1_affine_to_ints(p.reshape(1, 8))[0] for p in t_d.points]
-    adv_cm, f_cm, z_cm = pts[0:2], pts[2], pts[4]
-    b0_cm, rnd_cm = pts[8], pts[10]
-    h_cms = pts[11:11 + cs_degree - 1]
-    wit = pts[11 + cs_degree - 1:]
+    adv_cm, f_cm = pts[0:A], pts[A]
+    z_cm = pts[A + 2:A + 2 + nsets]
+    o = A + 2 + nsets
+    b0_cm, rnd_cm = pts[o + 3], pts[o + 5]
+    h_cms = pts[o + 6:o + 6 + cs_degree - 1]
+    wit = pts[o + 6 + cs_degree - 1:]
     sigma_cm = [P.g1_affine_to_ints(O.best_multiexp(F(sg), g_lagrange, th)[1].reshape(1, 8))[0] for sg in sig]  # the vk's permutation commitments
     h_cm = None
     for hc in h_cms[::-1]:
         h_cm = P.g1_add(P.g1_mul(h_cm, xn) if h_cm is not None else None, hc)
-    x_next = x_rot(x, 1)
-    q_at_x = [(adv_cm[0], a_x[0]), (adv_cm[1], a_x[1]), (z_cm, z_x), (b0_cm, b0_x), (f_cm, f_x), (sigma_cm[0], sg_x[0]), (sigma_cm[1], sg_x[1]),
-              (h_cm, h_x_expected), (rnd_cm, e["random"])]
-    q_at_next = [(z_cm, z_wx)]
-    assert len(wit) == 2
-    for zpt, qs, w in ((x, q_at_x, wit[0]), (x_next, q_at_next, wit[1])):
+    x_next, x_last = x_rot(x, 1), x_rot(x, -(bf + 1))
+    q_at_x = [(adv_cm[j], a_x[j]) for j in range(A)] + [(z_cm[s_], zs[s_][0]) for s_ in range(nsets)]
+    q_at_x += [(b0_cm, b0_x), (f_cm, f_x)] + [(sigma_cm[j], sg_x[j]) for j in range(A)] + [(h_cm, h_x_expected), (rnd_cm, e["random"])]
+    q_at_next = [(z_cm[s_], zs[s_][1]) for s_ in range(nsets)]
+    q_at_last = [(z_cm[s_], zs[s_][2]) for s_ in range(nsets - 2, -1, -1)]
+    groups = [(x, q_at_x), (x_next, q_at_next)] + ([(x_last, q_at_last)] if nsets > 1 else [])
+    assert len(wit) == len(groups)
+    # the order of the queries INSIDE the point set of x follows the prover's chain (advice, then per set z at x, ...): rebuild it
+    # from the interleaved chain instead of the grouped lists above
+    chain = [(x, adv_cm[j], a_x[j]) for j in range(A)]
+    for s_ in range(nsets):
+        chain += [(x, z_cm[s_], zs[s_][0]), (x_next, z_cm[s_], zs[s_][1])]
+    for s_ in range(nsets - 2, -1, -1):
+        chain.append((x_last, z_cm[s_], zs[s_][2]))
+    chain += [(x, b0_cm, b0_x), (x, f_cm, f_x)] + [(x, sigma_cm[j], sg_x[j]) for j in range(A)] + [(x, h_cm, h_x_expected), (x, rnd_cm, e["random"])]
+    sets_v = []
+    for q in chain:
+        for ps in sets_v:
+            if ps[0] == q[0]:
+                ps[1].append(q)
+                break
+        else:
+            sets_v.append((q[0], [q]))
+    assert [z_ for z_, _ in sets_v] == [z_ for z_, _ in groups]
+    for (zpt, qs), w in zip(sets_v, wit):
         c_acc, e_acc, pw = None, 0, 1
-        for cm, ev_ in qs:
+        for _, cm, ev_ in qs:
             c_acc = P.g1_add(c_acc, P.g1_mul(cm, pw))
             e_acc = (e_acc + pw * ev_) % R
             pw = pw * v % R
