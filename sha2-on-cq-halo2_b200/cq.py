@@ -78,7 +78,7 @@ class StaticTableValues:
         _lib.check(lib.cqb_cq_table_qs_dev(d_vals, k, ctypes.c_void_p(srs_g1._device_ptr), d_qs))
         _lib.check(lib.cqb_sync())
         self._dev_alloc = d_vals
-        self.qs = DeviceBases.adopt(d_qs.value, size, precompute=False)
+        self.qs = DeviceBases.adopt(d_qs.value, size)  # table by default from 2^10 rows on: Q_A is a short sparse MSM over it every proof
 
     def commit(self, srs_g1_len, srs_g2, circuit_domain):
         """reference plonk/static_lookup.rs:127-160 StaticTableValues::commit -> StaticCommittedTable { zv, t, x_b0_bound, size }:
@@ -171,13 +171,23 @@ def commit_log_derivatives_dev(params, table_srs, tables, b0_bound_bases, k, bli
     # (:230-233); the sum over the support is linear, so Q_A = sum_k theta^(K-1-k) * MSM(table_k.qs, a) — K sparse MSMs and a
     # K-term combination instead of |supp| x K scalar multiplications and affine conversions.
     a_cm = sparse(table_srs.g1_lagrange)
-    parts = [sparse(t.qs) for t in tables]
     if K == 1:
-        qa_cm = parts[0]
+        qa_cm = sparse(tables[0].qs)
     else:
-        pts = np.stack([p.to_affine() for p in parts])
-        pw = np.stack([fr_to_limbs(pow(theta, K - 1 - j, R_MOD)) for j in range(K)])
-        _lib.check(lib.cqb_msm_bn254_g1_host(_lib.p64(pts), _lib.p64(pw), K, _lib.p64(out), ctypes.byref(inf)))
+        # the theta powers go into the scalars (a copy of a in the d_tv scratch, which is free once a exists), the K partial points are
+        # added on the device: no K-term windowed MSM (whose window combination alone is ~254 dependent doublings)
+        parts = []
+        for j, t in enumerate(tables):
+            pw = pow(theta, K - 1 - j, R_MOD)
+            if pw == 1:
+                parts.append(sparse(t.qs).to_affine())
+                continue
+            _lib.check(lib.cqb_memcpy_d2d(vp(d_tv), vp(d_a), m * 32))
+            _lib.check(lib.cqb_fr_scale_dev(vp(d_tv), m, _lib.p64(fr_to_limbs(pw))))
+            _lib.check(lib.cqb_msm_bn254_g1_sparse_dev(t.qs.handle, vp(d_idx), vp(d_tv), m, _lib.p64(out), ctypes.byref(inf)))
+            parts.append(out.copy())
+        pts = np.ascontiguousarray(np.stack(parts))
+        _lib.check(lib.cqb_g1_sum_affine(_lib.p64(pts), K, _lib.p64(out), ctypes.byref(inf)))
         qa_cm = G1(out.copy(), inf.value)
     a0_cm = sparse(table_srs.g_lagrange_opening_at_0)
     # :261-276 bs = 1/(f_i + beta) on the usable rows, 1/beta on the blinding rows; ifft

@@ -9,6 +9,12 @@ from . import _lib
 from .arithmetic import G1, _as_fr, _as_g1
 
 
+# Sets from this size on get their per-SRS table by default: without one an MSM ends in the ~254 dependent doublings of the window
+# combination (1.8 ms on one thread), which is most of the time of a commitment at circuit sizes k <= 16; the table of a small set is
+# built in microseconds and costs (254/c + 1) x n x 64 bytes
+PRECOMPUTE_MIN_POINTS = 1 << 10
+
+
 class DeviceBases:
     """A device-resident Vec<G1Affine>"""
 
@@ -22,7 +28,7 @@ class DeviceBases:
         self.handle = h.value
         self._device_ptr = device_ptr
         if precompute is None:
-            precompute = n >= (1 << 16)
+            precompute = n >= PRECOMPUTE_MIN_POINTS
         if precompute and n:
             self.precompute(window_bits)
         return self
@@ -35,14 +41,14 @@ class DeviceBases:
 
     def __init__(self, affine, precompute=None, window_bits=0):
         """precompute: build the resident 2^(c w) P_i table (cqb_bases_precompute) so that MSMs over this set use one
-        bucket set with wider windows. None = automatically for sets of >= 2^16 points."""
+        bucket set with wider windows. None = automatically for sets of >= PRECOMPUTE_MIN_POINTS points."""
         affine = _as_g1(affine)
         self.n = affine.shape[0]
         h = ctypes.c_uint64(0)
         _lib.check(_lib.lib().cqb_bases_register(_lib.p64(affine), self.n, ctypes.byref(h)))
         self.handle = h.value
         if precompute is None:
-            precompute = self.n >= (1 << 16)
+            precompute = self.n >= PRECOMPUTE_MIN_POINTS
         if precompute and self.n:
             self.precompute(window_bits)
 

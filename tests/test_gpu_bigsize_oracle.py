@@ -244,7 +244,7 @@ def test_commit_identity_at_k26_both_srs_vectors(env, oracle):
         g_host = np.zeros((m, 8), np.uint64)
         L.check(lib.cqb_bases_download(params.g.handle, 0, m, L.p64(g_host)))
         _, exp = oracle.best_multiexp(sc, g_host, oracle.hw_threads())
-        # a short commitment falls below 1/8 of the set and takes the windowed layout on the same resident bases
+        # a short commitment (2^16 of the 2^26 points) over the same resident table
         assert np.array_equal(_msm_dev(L, lib, params.g.handle, d_a, m), exp)
     finally:
         dv.free()

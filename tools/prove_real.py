@@ -78,7 +78,7 @@ def build_circuit(cq, k, log_table, n_advice, seed=1):
     s = fr_to_limbs(int(rng.integers(1, 1 << 62)) * 0x9E3779B97F4A7C15 % R_MOD)
     params = cq.ParamsKZG.setup_from_toxic_waste(k, s)
     Nt = max(N, n)
-    tsrs = cq.TableSRS.setup_from_toxic_waste(N - 1, s, precompute=False)
+    tsrs = cq.TableSRS.setup_from_toxic_waste(N - 1, s)
     big = tsrs if Nt == N else cq.TableSRS.setup_from_toxic_waste(Nt - 1, s, precompute=False)
     # b0_g1_bound = the last n - 1 powers of the length-Nt table SRS (my_test.rs:205, static_lookup.rs:149)
     bound_host = big.g1.to_host()[Nt - (n - 1):]
