@@ -126,7 +126,7 @@ class CommittedLogDerivative:
             self._alloc = None
 
 
-def commit_log_derivatives_dev(params, table_srs, tables, b0_bound_bases, k, blinding_factors, d_f, idx, multiplicities, beta, theta):
+def commit_log_derivatives_dev(params, table_srs, tables, b0_bound_bases, k, blinding_factors, d_f, idx, multiplicities, beta, theta, alloc=None):
     """Committed::commit_log_derivatives (static_lookup/prover.rs:187-342) with every vector resident in HBM.
 
     params: ParamsKZG; table_srs: TableSRS (the table_config of :213-216); tables: the lookup's StaticTableValues (same size,
@@ -144,10 +144,15 @@ def commit_log_derivatives_dev(params, table_srs, tables, b0_bound_bases, k, bli
     idx = np.ascontiguousarray(idx, dtype=np.uint32)
     mult = np.ascontiguousarray(multiplicities, dtype=np.uint64).reshape(m, 4)
     # one allocation: b (n) | b0 (n) | f coeff (n) | a (m) | tv (m) | mult (m) | idx (m u32)
-    alloc = ctypes.c_void_p()
-    _lib.check(lib.cqb_dev_alloc(3 * n * 32 + 3 * max(m, 1) * 32 + max(m, 1) * 4 + 64, ctypes.byref(alloc)))
-    d_b, d_b0, d_fc = alloc.value, alloc.value + n * 32, alloc.value + 2 * n * 32
-    d_a = alloc.value + 3 * n * 32
+    nbytes = 3 * n * 32 + 3 * max(m, 1) * 32 + max(m, 1) * 4 + 64
+    if alloc is not None:  # the caller's arena (a proof's pooled working memory): nothing to free here
+        base, owned = alloc(nbytes), None
+    else:
+        owned = ctypes.c_void_p()
+        _lib.check(lib.cqb_dev_alloc(nbytes, ctypes.byref(owned)))
+        base = owned.value
+    d_b, d_b0, d_fc = base, base + n * 32, base + 2 * n * 32
+    d_a = base + 3 * n * 32
     d_tv, d_mult = d_a + max(m, 1) * 32, d_a + 2 * max(m, 1) * 32
     d_idx = d_a + 3 * max(m, 1) * 32
     vp = ctypes.c_void_p
@@ -215,4 +220,4 @@ def commit_log_derivatives_dev(params, table_srs, tables, b0_bound_bases, k, bli
     _lib.check(lib.cqb_memcpy_d2d(vp(d_fc), vp(d_f), n * 32))
     _lib.check(lib.cqb_intt_bn254_fr_dev(vp(d_fc), _lib.p64(dom.omega_inv), _lib.p64(dom.ifft_divisor), k))
     _lib.check(lib.cqb_sync())
-    return CommittedLogDerivative(alloc, d_b, d_b0, d_fc, a_at_zero, a_cm, qa_cm, a0_cm, b0_cm, p_cm)
+    return CommittedLogDerivative(owned, d_b, d_b0, d_fc, a_at_zero, a_cm, qa_cm, a0_cm, b0_cm, p_cm)

@@ -46,6 +46,12 @@ struct G1 {
     bool operator==(const G1& o) const { return affine == o.affine; }
 };
 
+/// bn256 G2Affine in the reference's raw layout: x.c0, x.c1, y.c0, y.c1 (Fq Montgomery limbs, 128 bytes); identity = zeros
+struct G2Affine {
+    uint64_t l[16];
+    bool operator==(const G2Affine& o) const { return std::memcmp(l, o.l, 128) == 0; }
+};
+
 namespace detail {
 inline void check(int rc, const char* what) {
     if (rc != 0) throw std::logic_error(std::string(what) + ": libcqb200 error " + std::to_string(rc) + ": " + cqb_last_error());
@@ -287,6 +293,13 @@ inline F delta() { return raw(0x870e56bbe533e9a2ULL, 0x5b5f898e5e963f25ULL, 0x64
 /// reference poly/kzg/commitment.rs:42-47, 73-178 (G1 parts; the G2 powers are keygen / verifier side): device resident
 class TableSRS {
   public:
+    /// reference signature (:73): also the G2 powers [s^i]G2, i <= max_g2_power (:94-104, 114-141) — keygen / verifier-side data
+    static TableSRS setup_from_toxic_waste(size_t max_g1_power, size_t max_g2_power, const Fr& s) {
+        TableSRS t = setup_from_toxic_waste(max_g1_power, s);
+        t.g2_.resize(max_g2_power + 1);
+        detail::check(cqb_g2_powers(s.l, max_g2_power + 1, (uint64_t*)t.g2_.data()), "TableSRS g2 powers");
+        return t;
+    }
     static TableSRS setup_from_toxic_waste(size_t max_g1_power, const Fr& s) {
         size_t len = max_g1_power + 1;
         if (len & (len - 1)) throw std::logic_error("assertion failed: is_pow_2(g1_len)");  // :77
@@ -305,6 +318,7 @@ class TableSRS {
     TableSRS& operator=(TableSRS&& o) noexcept {
         release();
         len_ = o.len_; dev_ = o.dev_; g1_ = o.g1_; g1_lagrange_ = o.g1_lagrange_; opening_at_0_ = o.opening_at_0_;
+        g2_ = std::move(o.g2_);
         o.dev_ = nullptr; o.g1_ = o.g1_lagrange_ = o.opening_at_0_ = 0;
         return *this;
     }
@@ -314,6 +328,7 @@ class TableSRS {
     cqb_bases_t g1() const { return g1_; }
     cqb_bases_t g1_lagrange() const { return g1_lagrange_; }
     cqb_bases_t g_lagrange_opening_at_0() const { return opening_at_0_; }
+    const std::vector<G2Affine>& g2() const { return g2_; }
     std::vector<G1Affine> download(int which) const {  // 0: g1, 1: g1_lagrange, 2: g_lagrange_opening_at_0
         std::vector<G1Affine> v(len_);
         detail::check(cqb_memcpy_d2h(v.data(), (char*)dev_ + (size_t)which * len_ * 64, len_ * 64), "d2h");
@@ -330,13 +345,20 @@ class TableSRS {
     size_t len_ = 0;
     void* dev_ = nullptr;
     cqb_bases_t g1_ = 0, g1_lagrange_ = 0, opening_at_0_ = 0;
+    std::vector<G2Affine> g2_;
+};
+
+/// reference plonk/static_lookup.rs:162-168
+struct StaticCommittedTable {
+    G2Affine zv, t, x_b0_bound;
+    size_t size;
 };
 
 /// reference plonk/static_lookup.rs:69-126: a table's values and its cached quotient commitments qs (FK on the device
 /// instead of the reference's N kate_divisions + N MSMs, ":107 TODO: THIS SHOULD BE DONE WITH FK METHOD")
 class StaticTableValues {
   public:
-    StaticTableValues(const std::vector<Fr>& values, const TableSRS& srs) : size_(values.size()) {
+    StaticTableValues(const std::vector<Fr>& values, const TableSRS& srs) : size_(values.size()), values_(values) {
         if (size_ == 0 || (size_ & (size_ - 1))) throw std::logic_error("assertion failed: is_pow_2(size)");  // :80
         if (srs.len() < size_) throw std::logic_error("srs_g1 shorter than the table");
         for (size_t i = 0; i < size_; i++) {
@@ -362,6 +384,35 @@ class StaticTableValues {
         if (qs_) cqb_bases_free(qs_);
         if (dev_) cqb_dev_free(dev_);
     }
+    /// reference plonk/static_lookup.rs:127-160: zv = [s^N]G2 - G2, t = best_multiexp::<G2Affine>(ifft(values), srs_g2) with the values
+    /// in the order of value_index_mapping.keys() — a BTreeMap, i.e. SORTED by canonical value (derive/field.rs:128-141), as the
+    /// reference does — and x_b0_bound = srs_g2[srs_g1_len - 1 - (circuit_domain - 2)]
+    StaticCommittedTable commit(size_t srs_g1_len, const std::vector<G2Affine>& srs_g2, size_t circuit_domain) const {
+        if (srs_g2.size() <= size_) throw std::logic_error("srs_g2 must hold the powers 0..N");
+        std::vector<size_t> order(size_);
+        for (size_t i = 0; i < size_; i++) order[i] = i;
+        std::vector<detail::F> canon(size_);
+        for (size_t i = 0; i < size_; i++) canon[i] = cqb::fp_from_mont<cqb::FrP>(detail::to_f(values_[i]));
+        std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+            for (int w = 7; w >= 0; w--) if (canon[a].l[w] != canon[b].l[w]) return canon[a].l[w] < canon[b].l[w];
+            return false;
+        });
+        std::vector<Fr> coeffs(size_);
+        for (size_t i = 0; i < size_; i++) coeffs[i] = values_[order[i]];
+        uint32_t k = 0;
+        while (((size_t)1 << k) < size_) k++;
+        EvaluationDomain dom(2, k);
+        EvaluationDomain::ifft(coeffs, dom.get_omega_inv(), k, dom.ifft_divisor());
+        StaticCommittedTable r;
+        int inf = 0;
+        G2Affine two[2] = {srs_g2[size_], srs_g2[0]};
+        Fr pm[2] = {fr_one(), detail::from_f(cqb::fp_neg<cqb::FrP>(detail::F::one()))};
+        detail::check(cqb_msm_bn254_g2(two[0].l, pm[0].l, 2, r.zv.l, &inf), "zv");
+        detail::check(cqb_msm_bn254_g2(srs_g2[0].l, coeffs[0].l, size_, r.t.l, &inf), "table commitment");
+        r.x_b0_bound = srs_g2[srs_g1_len - 1 - (circuit_domain - 2)];
+        r.size = srs_g1_len;
+        return r;
+    }
     size_t size() const { return size_; }
     const void* values_dev() const { return d_values_; }
     cqb_bases_t qs() const { return qs_; }
@@ -374,6 +425,7 @@ class StaticTableValues {
 
   private:
     size_t size_;
+    std::vector<Fr> values_;
     void* dev_ = nullptr;
     void* d_values_ = nullptr;
     void* d_qs_ = nullptr;
@@ -532,7 +584,7 @@ inline CommittedLogDerivative commit_log_derivatives(const Committed& c, const P
         std::vector<Fr> pw(K);
         F acc = F::one();
         for (size_t j = K; j-- > 0;) { pw[j] = from_f(acc); acc = mul(acc, to_f(theta)); }
-        r.qa_cm = best_multiexp(pw, parts);
+        r.qa_cm = best_multiexp(pw, parts);  // K terms; the Python mirror folds theta^j into the scalars instead (cq.py)
     }
     r.a0_cm = sparse(table_config.g_lagrange_opening_at_0());                                              // :252
     const size_t usable_rows = n - (blinding_factors + 1);                                                 // :259-260
@@ -559,5 +611,33 @@ inline CommittedLogDerivative commit_log_derivatives(const Committed& c, const P
     return r;
 }
 }  // namespace static_lookup
+
+/// reference poly/kzg/msm.rs:12-80: scalars and PROJECTIVE bases collected term by term; eval() = batch_normalize + best_multiexp
+struct G1Jacobian { uint64_t x[4], y[4], z[4]; };
+class MSMKZG {
+  public:
+    void append_term(const Fr& scalar, const G1Jacobian& point) { scalars_.push_back(scalar); bases_.push_back(point); }  // :41-44
+    void add_msm(const MSMKZG& other) {                                                                                    // :46-49
+        scalars_.insert(scalars_.end(), other.scalars_.begin(), other.scalars_.end());
+        bases_.insert(bases_.end(), other.bases_.begin(), other.bases_.end());
+    }
+    void scale(const Fr& factor) {                                                                                         // :51-58
+        for (auto& sc : scalars_) sc = detail::from_f(detail::mul(detail::to_f(sc), detail::to_f(factor)));
+    }
+    G1 eval() const {                                                                                                      // :65-70
+        uint64_t out[8];
+        int inf = 0;
+        detail::check(cqb_msm_bn254_g1_jacobian(bases_.empty() ? nullptr : bases_[0].x, scalars_.empty() ? nullptr : scalars_[0].l,
+                                                scalars_.size(), out, &inf), "MSMKZG::eval");
+        return detail::fetch_point(out, inf);
+    }
+    bool check() const { return eval().identity; }                                                                      // :60-62
+    const std::vector<Fr>& scalars() const { return scalars_; }
+    const std::vector<G1Jacobian>& bases() const { return bases_; }
+
+  private:
+    std::vector<Fr> scalars_;
+    std::vector<G1Jacobian> bases_;
+};
 
 }  // namespace halo2_b200

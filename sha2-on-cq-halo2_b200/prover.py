@@ -25,14 +25,23 @@ def _vp(p):
 
 
 class _Arena:
-    """device buffers of one object, freed together"""
+    """Device buffers of one object, released together. With a pool (one device allocation kept by the proving key and reused by
+    every proof) an allocation is a pointer bump: cudaMalloc / cudaFree cost ~0.4-1 ms each and a proof makes ~40 of them — at
+    circuit sizes that was most of the time of a proof (profiles/r02_summary.md)."""
 
-    def __init__(self):
+    def __init__(self, pool=None, pool_bytes=0):
         self.ptrs = []
+        self.pool, self.pool_bytes, self.used = pool, pool_bytes, 0
 
     def alloc(self, nbytes):
+        nbytes = max(nbytes, 64)
+        if self.pool is not None:
+            start = (self.used + 255) & ~255
+            if start + nbytes <= self.pool_bytes:
+                self.used = start + nbytes
+                return self.pool + start
         d = ctypes.c_void_p()
-        _lib.check(_lib.lib().cqb_dev_alloc(max(nbytes, 64), ctypes.byref(d)))
+        _lib.check(_lib.lib().cqb_dev_alloc(nbytes, ctypes.byref(d)))
         self.ptrs.append(d)
         return d.value
 
@@ -44,9 +53,12 @@ class _Arena:
         return d
 
     def free(self):
+        if self.pool is not None:
+            _lib.check(_lib.lib().cqb_sync())  # the pool is reused by the next proof: everything queued on it must have finished
         for d in self.ptrs:
             _lib.check(_lib.lib().cqb_dev_free(d))
         self.ptrs = []
+        self.used = 0
 
 
 def _commit(bases, d_ptr, count):
@@ -100,6 +112,7 @@ class ProvingKey:
         self.advice_queries = list(advice_queries)            # (column, rotation) in cs.advice_queries order
         self.static_lookups = list(static_lookups)
         self.vk_transcript_repr = vk_transcript_repr
+        self._pool, self._pool_bytes = None, 0
         self._arena = ar = _Arena()
         n, en = self.n, dom.extended_len()
 
@@ -139,8 +152,29 @@ class ProvingKey:
         w = self.domain._omega
         return x * pow(w, rot, R_MOD) % R_MOD if rot >= 0 else x * pow(pow(w, -1, R_MOD), -rot, R_MOD) % R_MOD
 
+    def proof_pool(self, n_advice):
+        """the working memory of one create_proof, allocated once and reused: every polynomial a proof holds in HBM at the same time"""
+        n, en = self.n, self.domain.extended_len()
+        chunk = self.cs_degree - 2
+        nsets = (len(self.permutation_columns) + chunk - 1) // chunk if self.permutation_columns else 0
+        L = len(self.static_lookups)
+        # n-sized: advice (Lagrange + coefficients), f, z (Lagrange + coefficients), the CQ argument's b / b0 / f / a / t / m, random
+        # poly, h(X), batch, witness; extended: z, advice, b, f cosets and the quotient
+        elems = n * (2 * n_advice + 2 * nsets + 8 * L + 6) + en * (nsets + n_advice + 2 * L + 1)
+        need = elems * 32 + (1 << 20)
+        if need > self._pool_bytes:
+            if self._pool is not None:
+                _lib.check(_lib.lib().cqb_dev_free(_vp(self._pool)))
+            d = ctypes.c_void_p()
+            _lib.check(_lib.lib().cqb_dev_alloc(need, ctypes.byref(d)))
+            self._pool, self._pool_bytes = d.value, need
+        return self._pool, self._pool_bytes
+
     def free(self):
         self._arena.free()
+        if self._pool is not None:
+            _lib.check(_lib.lib().cqb_dev_free(_vp(self._pool)))
+            self._pool, self._pool_bytes = None, 0
 
 
 def create_proof(pk, advice_lagrange, lookups_m_sparse, rng, transcript):
@@ -155,7 +189,7 @@ def create_proof(pk, advice_lagrange, lookups_m_sparse, rng, transcript):
     lib = _lib.lib()
     dom, params = pk.domain, pk.params
     k, n, en, bf = pk.k, pk.n, pk.domain.extended_len(), pk.blinding_factors
-    ar = _Arena()
+    ar = _Arena(*pk.proof_pool(len(advice_lagrange)))
     info = {}
     try:
         def to_coeff(d_lagrange):
@@ -184,8 +218,8 @@ def create_proof(pk, advice_lagrange, lookups_m_sparse, rng, transcript):
             _lib.check(lib.cqb_fr_compress_dev(ptrs, len(lk.input_columns), None, n, _lib.p64(fr_to_limbs(theta)), _vp(d)))  # :108-121
             d_f.append(d)
             transcript.write_point(_commit(params.g_lagrange, d, n))                       # f_cm :165, :174
-            m_sparse = {int(i): mult[j] for j, i in enumerate(idx)}
-            transcript.write_point(cq.commit_m(lk.table_srs, m_sparse).to_affine())        # m_cm :167-175
+            # m_cm (:167-175): one sparse MSM over the support, handed over as the (index, multiplicity) arrays in key order
+            transcript.write_point(lk.table_srs.g1_lagrange.msm_sparse(idx, mult).to_affine())
         beta = info["beta"] = transcript.squeeze_challenge_scalar()                        # :529
         gamma = info["gamma"] = transcript.squeeze_challenge_scalar()                      # :532
         # permutation argument (permutation/prover.rs:46-200)
@@ -204,7 +238,7 @@ def create_proof(pk, advice_lagrange, lookups_m_sparse, rng, transcript):
         # static lookups, second phase (static_lookup/prover.rs:187-342)
         clds = []
         for lk, d, (idx, mult) in zip(pk.static_lookups, d_f, lookups_m_sparse):
-            cld = cq.commit_log_derivatives_dev(params, lk.table_srs, lk.tables, lk.b0_g1_bound, k, bf, d, idx, mult, beta, theta)
+            cld = cq.commit_log_derivatives_dev(params, lk.table_srs, lk.tables, lk.b0_g1_bound, k, bf, d, idx, mult, beta, theta, alloc=ar.alloc)
             clds.append(cld)
             for pt in (cld.a_cm, cld.qa_cm, cld.a0_cm, cld.b0_cm, cld.p_cm):               # :301-313
                 transcript.write_point(pt.to_affine())

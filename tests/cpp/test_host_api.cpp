@@ -23,6 +23,11 @@ void oracle_fr_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out); 
 void oracle_g1_mul_a(const uint64_t* a, const uint64_t* s, uint64_t* out_jac);
 void oracle_g1_add_jj(const uint64_t* a, const uint64_t* b, uint64_t* out_jac);
 void oracle_g1_to_affine(const uint64_t* a_jac, uint64_t* out_aff);
+void oracle_g2_powers(const uint64_t* s, size_t count, uint64_t* out_aff);
+void oracle_g2_msm(const uint64_t* bases_aff, const uint64_t* scalars, size_t n, uint64_t* out_aff);
+void oracle_g2_add_aa(const uint64_t* a, const uint64_t* b, uint64_t* out_aff);
+void oracle_g2_neg_a(const uint64_t* a, uint64_t* out_aff);
+void oracle_g1_batch_normalize(const uint64_t* p, uint64_t* q, size_t n);
 void oracle_permutation_product(const uint64_t* const* columns, const uint64_t* const* perms, uint32_t ncols, size_t n, const uint64_t* beta,
                                 const uint64_t* gamma, const uint64_t* omega, uint64_t* deltaomega_io, const uint64_t* last_z, uint64_t* z_out);
 }
@@ -239,8 +244,68 @@ static void test_static_lookup_commit() {
     printf("test_static_lookup_commit ok\n");
 }
 
+// poly/kzg/msm.rs:65-70 MSMKZG::eval over projective bases, and check()
+static void test_msmkzg_eval() {
+    const size_t n = 300;
+    std::vector<Fr> sc(n), mult(n);
+    std::vector<G1Affine> aff(n);
+    oracle_synth_scalars(0xE7B1, 0, n, (uint64_t*)sc.data());
+    oracle_synth_scalars(0xE7B2, 0, n, (uint64_t*)mult.data());
+    oracle_synth_bases(0xE7B3, n, 2, (uint64_t*)aff.data());
+    std::vector<G1Jacobian> jac(n);
+    for (size_t i = 0; i < n; i++) oracle_g1_mul_a((const uint64_t*)&aff[i], mult[i].l, (uint64_t*)&jac[i]);  // non-trivial z
+    memset(&jac[3], 0, sizeof(G1Jacobian));                                                                      // an identity term
+    std::vector<G1Affine> norm(n);
+    oracle_g1_batch_normalize((const uint64_t*)jac.data(), (uint64_t*)norm.data(), n);
+    uint64_t jexp[12], aexp[8];
+    oracle_best_multiexp((const uint64_t*)sc.data(), (const uint64_t*)norm.data(), n, 4, jexp, aexp);
+    MSMKZG m;
+    for (size_t i = 0; i < n; i++) m.append_term(sc[i], jac[i]);
+    G1 got = m.eval();
+    ASSERT(memcmp(&got.affine, aexp, 64) == 0);
+    ASSERT(!m.check());
+    MSMKZG empty;
+    ASSERT(empty.check());
+}
+
+// poly/kzg/commitment.rs:94-141 (G2 powers of the table SRS) and plonk/static_lookup.rs:127-160 (StaticTableValues::commit)
+static void test_table_commit_g2() {
+    const size_t N = 32, circuit_domain = 16;
+    Fr s;
+    oracle_synth_scalars(0x62A, 0, 1, s.l);
+    TableSRS srs = TableSRS::setup_from_toxic_waste(N - 1, N, s);
+    std::vector<G2Affine> exp_g2(N + 1);
+    oracle_g2_powers(s.l, N + 1, (uint64_t*)exp_g2.data());
+    ASSERT(srs.g2().size() == N + 1);
+    for (size_t i = 0; i <= N; i++) ASSERT(srs.g2()[i] == exp_g2[i]);
+    std::vector<Fr> values(N);
+    for (size_t i = 0; i < N; i++) values[i] = fr_from_u64(1000003ull * (i * 7919 % N) + 17);  // distinct, not sorted
+    StaticTableValues table(values, srs);
+    StaticCommittedTable ct = table.commit(N, srs.g2(), circuit_domain);
+    G2Affine neg0, zv;
+    oracle_g2_neg_a(exp_g2[0].l, neg0.l);
+    oracle_g2_add_aa(exp_g2[N].l, neg0.l, zv.l);
+    ASSERT(ct.zv == zv);
+    std::vector<Fr> sorted = values;  // small positive integers: canonical order = integer order = order of i*7919 % N
+    std::sort(sorted.begin(), sorted.end(), [](const Fr& a, const Fr& b) {
+        Fr ca, cb;
+        oracle_fr_op(7, a.l, a.l, ca.l);  // from_mont: canonical limbs
+        oracle_fr_op(7, b.l, b.l, cb.l);
+        for (int w = 3; w >= 0; w--) if (ca.l[w] != cb.l[w]) return ca.l[w] < cb.l[w];
+        return false;
+    });
+    EvaluationDomain dom(2, 5);
+    oracle_ifft((uint64_t*)sorted.data(), dom.get_omega_inv().l, 5, dom.ifft_divisor().l, 2);
+    G2Affine t;
+    oracle_g2_msm((const uint64_t*)exp_g2.data(), (const uint64_t*)sorted.data(), N, t.l);
+    ASSERT(ct.t == t);
+    ASSERT(ct.x_b0_bound == exp_g2[N - 1 - (circuit_domain - 2)] && ct.size == N);
+}
+
 int main() {
     init(0);
+    test_msmkzg_eval();
+    test_table_commit_g2();
     test_commit_lagrange();
     test_best_multiexp();
     test_permutation_commit();
