@@ -206,6 +206,8 @@ CQB_API int cqb_cq_table_qs_dev(const void* d_table_coeffs, uint32_t log_n, cons
 CQB_API int cqb_g1_generator_mul_dev(const void* d_scalars, size_t n, void* d_out);
 /* eval_polynomial (halo2_proofs/src/arithmetic.rs:304-329): out = sum_i coeffs[i] point^i, coefficients device-resident */
 CQB_API int cqb_eval_polynomial_dev(const void* d_coeffs, size_t n, const uint64_t point[4], uint64_t out[4]);
+/* count polynomials of n coefficients each, evaluated at points[i] (count x 4 limbs), one read-back for all (plonk/prover.rs:629-719) */
+CQB_API int cqb_eval_polynomials_dev(const void* const* d_coeffs, size_t n, const uint64_t* points, uint32_t count, uint64_t* out);
 /* kate_division (arithmetic.rs:351-387): d_q[0..n-1) = (a(X) - a(b)) / (X - b); as used by the multiopen provers
  * (poly/kzg/multiopen/gwc/prover.rs:80-86) and the CQ table preprocessing; d_q must not alias d_a */
 CQB_API int cqb_kate_division_dev(const void* d_a, size_t n, const uint64_t b[4], void* d_q);

@@ -84,6 +84,7 @@ SYMBOLS = [
     ("cqb_permutation_h_dev", _int, [_vp, _u64, ctypes.c_int32, ctypes.c_int32, _u32, _vp, _u32, _vp, _vp, _u32, _vp, _vp, _vp, u64p, u64p,
                                      u64p, u64p]),
     ("cqb_eval_polynomial_dev", _int, [_vp, _sz, u64p, u64p]),
+    ("cqb_eval_polynomials_dev", _int, [_vp, _sz, u64p, _u32, u64p]),
     ("cqb_kate_division_dev", _int, [_vp, _sz, u64p, _vp]),
     ("cqb_fr_powers_dev", _int, [u64p, _sz, _vp]),
     ("cqb_fr_prefix_product_dev", _int, [_vp, _sz, u64p, _vp]),

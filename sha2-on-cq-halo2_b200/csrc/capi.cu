@@ -1266,6 +1266,24 @@ int cqb_eval_polynomial_dev(const void* d_coeffs, size_t n, const uint64_t point
     memcpy(out, g_out_host->p, 32);
     return 0;
 }
+// `count` evaluations queued back to back, ONE read-back: create_proof evaluates every queried polynomial at x, omega x, ... between two
+// challenges (plonk/prover.rs:629-719), and a 32-byte synchronous read per evaluation costs more than the evaluation at circuit sizes
+int cqb_eval_polynomials_dev(const void* const* d_coeffs, size_t n, const uint64_t* points, uint32_t count, uint64_t* out) {
+    LOCK;
+    CQB_TRY(require_init());
+    if (count == 0) return 0;
+    if (!d_coeffs || !points || !out) return fail(CQB_E_BAD_ARG, "cqb_eval_polynomials_dev: NULL argument");
+    CQB_TRY(g_out->ensure((size_t)count * 32 + 256));
+    CQB_TRY(g_out_host->ensure((size_t)count * 32 + 256));
+    for (uint32_t i = 0; i < count; i++) {
+        if (!d_coeffs[i] && n) return fail(CQB_E_BAD_ARG, "cqb_eval_polynomials_dev: NULL polynomial %u", i);
+        CQB_TRY(eval_polynomial_run(d_coeffs[i], n, points + 4 * i, (char*)g_out->p + (size_t)i * 32));
+    }
+    CQB_CUDA(cudaMemcpyAsync(g_out_host->p, g_out->p, (size_t)count * 32, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    memcpy(out, g_out_host->p, (size_t)count * 32);
+    return 0;
+}
 int cqb_kate_division_dev(const void* d_a, size_t n, const uint64_t b[4], void* d_q) {
     LOCK;
     CQB_TRY(require_init());

@@ -89,6 +89,18 @@ def _eval(d_poly, n, point):
     return fr_from_limbs(out)
 
 
+def _eval_many(queries, n):
+    """[(device polynomial, point)] -> evaluations, one device read-back for all of them"""
+    if not queries:
+        return []
+    cnt = len(queries)
+    ptrs = (ctypes.c_void_p * cnt)(*[_vp(p) for p, _ in queries])
+    pts = np.ascontiguousarray(np.stack([fr_to_limbs(x) for _, x in queries]))
+    out = np.zeros((cnt, 4), np.uint64)
+    _lib.check(_lib.lib().cqb_eval_polynomials_dev(ptrs, n, _lib.p64(pts), cnt, _lib.p64(out)))
+    return [fr_from_limbs(out[i]) for i in range(cnt)]
+
+
 class StaticLookup:
     """one lookup_static of the constraint system: the advice columns whose theta-compression is looked up, the tables it is
     looked up in (plonk/static_lookup.rs:69-126) and the table SRS (poly/kzg/commitment.rs:42-47)"""
@@ -226,13 +238,15 @@ def create_proof(pk, advice_lagrange, lookups_m_sparse, rng, transcript):
         chunk_len = pk.cs_degree - 2
         ncols = len(pk.permutation_columns)
         nsets = (ncols + chunk_len - 1) // chunk_len if ncols else 0
-        d_z = [ar.alloc(n * 32) for _ in range(nsets)]
+        d_z0 = ar.alloc(max(nsets, 1) * n * 32)                                          # the z's back to back: committed in one batch
+        d_z = [d_z0 + i * n * 32 for i in range(nsets)]
         z_poly, z_coset = [], []
         if nsets:
             permutation.commit_dev([d_adv[c] for c in pk.permutation_columns], pk.sigma_lagrange, k, pk.cs_degree, bf, beta, gamma, dom._omega,
                                    rng["permutation_blinds"], d_z)
+            for pt in _commit_batch(params.g_lagrange, d_z0, n, nsets):                    # :166-186
+                transcript.write_point(pt)
             for d in d_z:
-                transcript.write_point(_commit(params.g_lagrange, d, n))                   # :166-186
                 z_poly.append(to_coeff(d))                                                 # :168
             z_coset = [to_extended(d) for d in z_poly]                                     # :171
         # static lookups, second phase (static_lookup/prover.rs:187-342)
@@ -267,36 +281,55 @@ def create_proof(pk, advice_lagrange, lookups_m_sparse, rng, transcript):
         x = info["x"] = transcript.squeeze_challenge_scalar()                              # prover.rs:627
         xn = pow(x, n, R_MOD)
         evals = info["evals"] = {}
-        adv_evals = [_eval(adv_poly[c], n, pk.rotate_omega(x, rot)) for c, rot in pk.advice_queries]   # :652-670
-        for e in adv_evals:
-            transcript.write_scalar(e)
-        # vanishing evaluate (vanishing/prover.rs:123-157): h(X) = sum_i h_i(X) xn^i by Horner over the pieces; random_eval
-        d_hx = ar.alloc(n * 32)
+        # every evaluation the proof carries (and h(x), which it does not) is queued at once and read back together; they are written
+        # to the transcript in the reference's order: advice :652-670, random_eval (vanishing/prover.rs:123-157), the sigma polys
+        # (permutation/prover.rs:229-241), z at x / omega x / omega^last x (:244-288), b0, f, A(0) (static_lookup/prover.rs:346-375)
+        d_hx = ar.alloc(n * 32)                                                            # h(X) = sum_i h_i(X) xn^i, Horner over the pieces
         _lib.check(lib.cqb_memcpy_d2d(_vp(d_hx), _vp(d_h + (npieces - 1) * n * 32), n * 32))
         for i in range(npieces - 2, -1, -1):
             _lib.check(lib.cqb_fr_axpy_dev(_vp(d_hx), _lib.p64(fr_to_limbs(xn)), _vp(d_h + i * n * 32), n))
-        random_eval = _eval(d_rnd, n, x)
+        x_next, x_last = pk.rotate_omega(x, 1), pk.rotate_omega(x, -(bf + 1))
+        ev_q = [(adv_poly[c], pk.rotate_omega(x, rot)) for c, rot in pk.advice_queries]
+        ev_q.append((d_rnd, x))
+        ev_q += [(p, x) for p in pk.sigma_polys]
+        for s_, zp in enumerate(z_poly):
+            ev_q += [(zp, x), (zp, x_next)] + ([(zp, x_last)] if s_ + 1 < nsets else [])
+        for cld in clds:
+            ev_q += [(cld.d_b0, x), (cld.d_f, x)]
+        ev_q.append((d_hx, x))
+        ev = _eval_many(ev_q, n)
+        pos = 0
+        adv_evals = ev[pos:pos + len(pk.advice_queries)]
+        pos += len(pk.advice_queries)
+        for e in adv_evals:
+            transcript.write_scalar(e)
+        random_eval = ev[pos]
+        pos += 1
         transcript.write_scalar(random_eval)
-        sigma_evals = [_eval(p, n, x) for p in pk.sigma_polys]                             # permutation/prover.rs:229-241
+        sigma_evals = ev[pos:pos + len(pk.sigma_polys)]
+        pos += len(pk.sigma_polys)
         for e in sigma_evals:
             transcript.write_scalar(e)
-        x_next, x_last = pk.rotate_omega(x, 1), pk.rotate_omega(x, -(bf + 1))
         z_evals = []
-        for s, zp in enumerate(z_poly):                                                    # permutation/prover.rs:244-288
-            e_cur, e_next = _eval(zp, n, x), _eval(zp, n, x_next)
+        for s_ in range(len(z_poly)):
+            e_cur, e_next = ev[pos], ev[pos + 1]
+            pos += 2
             transcript.write_scalar(e_cur)
             transcript.write_scalar(e_next)
             e_last = None
-            if s + 1 < nsets:
-                e_last = _eval(zp, n, x_last)
+            if s_ + 1 < nsets:
+                e_last = ev[pos]
+                pos += 1
                 transcript.write_scalar(e_last)
             z_evals.append((e_cur, e_next, e_last))
         lk_evals = []
-        for cld in clds:                                                                   # static_lookup/prover.rs:346-375
-            b0_eval, f_eval = _eval(cld.d_b0, n, x), _eval(cld.d_f, n, x)
+        for cld in clds:
+            b0_eval, f_eval = ev[pos], ev[pos + 1]
+            pos += 2
             for e in (b0_eval, f_eval, cld.a_at_zero):
                 transcript.write_scalar(e)
             lk_evals.append((b0_eval, f_eval, cld.a_at_zero))
+        h_eval_batched = ev[pos]
         evals.update(advice=adv_evals, random=random_eval, sigma=sigma_evals, z=z_evals, static_lookups=lk_evals)
         # the queries, in the order prover.rs:718-774 chains them: (point, polynomial, evaluation)
         queries = [(pk.rotate_omega(x, rot), adv_poly[c], e) for (c, rot), e in zip(pk.advice_queries, adv_evals)]
@@ -307,7 +340,7 @@ def create_proof(pk, advice_lagrange, lookups_m_sparse, rng, transcript):
         for cld, (b0_eval, f_eval, _) in zip(clds, lk_evals):                              # static_lookup open :378-400
             queries += [(x, cld.d_b0, b0_eval), (x, cld.d_f, f_eval)]
         queries += [(x, p, e) for p, e in zip(pk.sigma_polys, sigma_evals)]                # pk.permutation.open :220-227
-        h_eval = info["h_eval"] = _eval(d_hx, n, x)
+        h_eval = info["h_eval"] = h_eval_batched
         queries += [(x, d_hx, h_eval), (x, d_rnd, random_eval)]                            # vanishing open :160-173
         # GWC multi-open (poly/kzg/multiopen/gwc/prover.rs:42-86)
         v = info["v"] = transcript.squeeze_challenge_scalar()
@@ -320,10 +353,11 @@ def create_proof(pk, advice_lagrange, lookups_m_sparse, rng, transcript):
             else:
                 point_sets.append((q[0], [q]))
         info["point_sets"] = [(z, [(e) for _, _, e in qs]) for z, qs in point_sets]
-        d_batch, d_wit = ar.alloc(n * 32), ar.alloc(n * 32)
+        d_batch = ar.alloc(n * 32)
+        d_wit0 = ar.upload(np.zeros((len(point_sets) * n, 4), np.uint64))                  # witness polynomials, n - 1 coefficients each + a zero
         tmp = np.zeros(4, np.uint64)
         v_l = fr_to_limbs(v)
-        for z, qs in point_sets:
+        for j, (z, qs) in enumerate(point_sets):
             # poly_batch = sum_i v^i p_i by Horner from the last query; eval_batch likewise
             _lib.check(lib.cqb_memcpy_d2d(_vp(d_batch), _vp(qs[-1][1]), n * 32))
             eval_batch = qs[-1][2]
@@ -335,8 +369,9 @@ def create_proof(pk, advice_lagrange, lookups_m_sparse, rng, transcript):
             _lib.check(lib.cqb_sync())
             c0 = fr_to_limbs((fr_from_limbs(tmp) - eval_batch) % R_MOD)
             _lib.check(lib.cqb_memcpy_h2d(_vp(d_batch), c0.ctypes.data_as(ctypes.c_void_p), 32))
-            _lib.check(lib.cqb_kate_division_dev(_vp(d_batch), n, _lib.p64(fr_to_limbs(z)), _vp(d_wit)))   # arithmetic.rs:351-387
-            transcript.write_point(_commit(params.g, d_wit, n - 1))
+            _lib.check(lib.cqb_kate_division_dev(_vp(d_batch), n, _lib.p64(fr_to_limbs(z)), _vp(d_wit0 + j * n * 32)))   # arithmetic.rs:351-387
+        for pt in _commit_batch(params.g, d_wit0, n, len(point_sets)):                     # gwc/prover.rs:79-84, all witnesses in one batch
+            transcript.write_point(pt)
         for cld in clds:
             cld.free()
         info["table_sizes"] = [lk.tables[0].size for lk in pk.static_lookups]
