@@ -280,8 +280,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")  # host-side waits that must not occupy the GPUs
     L = cqb200._lib
     lib = L.init(local_rank)
     stream = torch.cuda.Stream(device=local_rank)  # a real (non-NULL) stream handle shared by torch events and the library
@@ -520,13 +522,15 @@ def main():
     #      binds — no torch, no NCCL on the path). Rank 0 runs it while the other ranks wait at a barrier; it re-initialises rank 0's
     #      library state, so it is the last GPU leg of this process. ---------------------------------------------------------------
     if world > 1 and not args.no_in_process:
-        dist.barrier()
+        barrier()
         if rank == 0:
             try:
                 line["in_process"] = in_process_leg(args, world, L, lib, stream, torch)
             except Exception as exc:  # reported, never fatal for the main line
                 line["in_process"] = {"error": repr(exc)[:300]}
-        dist.barrier()
+        # the other ranks wait on the HOST (gloo): an NCCL barrier would leave its kernel spinning on their GPUs — the very GPUs rank 0's
+        # in-process MSM is running on — and time-slice it to half speed
+        dist.barrier(group=cpu_group)
 
     # ---- "SHA2-CQ prove ms": the synthetic CQ-prover-shaped op list of SURVEY.md §8(d) (no SHA circuit exists in the
     #      reference, F1), host-pointer C-ABI calls, N=1 only -------------------------------------------------------
