@@ -499,7 +499,9 @@ struct HostFeeder : MsmFeeder {
             bind_slot(slot);
             size_t bounds[9];
             msm_part_bounds(n, parts, true, bounds);
-            const int nthreads = std::max(2, std::min(COPY_THREADS, (int)std::thread::hardware_concurrency() - 2));
+            // copier threads: the host's cores are shared by every rank of a one-process-per-GPU job (torchrun sets LOCAL_WORLD_SIZE)
+            static const int ranks_on_host = std::max(1, getenv("LOCAL_WORLD_SIZE") ? atoi(getenv("LOCAL_WORLD_SIZE")) : 1);
+            const int nthreads = std::max(2, std::min(COPY_THREADS, ((int)std::thread::hardware_concurrency() - 2) / ranks_on_host));
             for (int p = 0; p < parts; p++) {
                 const size_t lo = bounds[p], cnt = bounds[p + 1] - lo;
                 const char* from = (const char*)(src + lo * 4);
@@ -581,7 +583,9 @@ static int msm_host_enqueue(BaseSet* bs, size_t offset, const uint64_t* scalars,
         feeder.src = scalars;
         feeder.pinned = pinned;
         static const int env_parts = getenv("CQB_PAGEABLE_PARTS") ? std::max(2, std::min(8, atoi(getenv("CQB_PAGEABLE_PARTS")))) : 0;  // experiments
-        const int parts = pinned ? CQB_HOST_PARTS : (env_parts ? env_parts : g_pageable_parts);
+        // below 2^22 points a part's fixed cost (~0.5 ms of launches and tails) outweighs what a third part hides of the copy
+        const int small = n < ((size_t)1 << 22);
+        const int parts = pinned ? (small ? 2 : CQB_HOST_PARTS) : (env_parts ? env_parts : (small ? 3 : g_pageable_parts));
         if (!pinned) feeder.start_staging(n, parts);
         const bool use_table = bs->table != nullptr;
         if (use_table) return msm_run_precomputed(bs->table, bs->n, bs->table_c, offset, g_scalars->p, nullptr, n, d_out, 1, parts, nullptr, &feeder);

@@ -153,6 +153,11 @@ class EvaluationDomain {
     const Fr& get_omega_inv() const { return omega_inv_; }
     const Fr& get_extended_omega() const { return extended_omega_; }
     const Fr& ifft_divisor() const { return ifft_divisor_; }
+    const Fr& get_extended_omega_inv() const { return extended_omega_inv_; }
+    const Fr& extended_ifft_divisor() const { return extended_ifft_divisor_; }
+    const Fr& g_coset() const { return g_coset_; }
+    const Fr& g_coset_inv() const { return g_coset_inv_; }
+    const std::vector<Fr>& t_evaluations() const { return t_evaluations_; }
 
     /// domain.rs:366-374
     static void ifft(std::vector<Fr>& a, const Fr& omega_inv, uint32_t log_n, const Fr& divisor) {

@@ -64,29 +64,20 @@ def _fr_array_fast(ints):
     return out
 
 
-def build_circuit(cq, k, log_table, n_advice, seed=1):
-    """proving key + witness of the lookup circuit; everything that keygen would prepare (SRS, tables with their cached quotients,
-    sigma polynomials) is resident on the device when this returns"""
-    from sha2_on_cq_halo2_b200 import prover as PR
-    from sha2_on_cq_halo2_b200.permutation import FR_DELTA
+def circuit_arrays(k, log_table, n_advice, seed=1):
+    """the circuit as plain host arrays (no device, no library): toxic s, table values, advice witness, sigma columns, the lookup's
+    m_sparse in key order, the rng draws"""
     from sha2_on_cq_halo2_b200.fields import FR_ROOT_OF_UNITY, FR_S, fr_to_limbs
+    from sha2_on_cq_halo2_b200.permutation import FR_DELTA
 
     n, N, A = 1 << k, 1 << log_table, n_advice
     cs_degree, bf = 4, 5
     usable = n - (bf + 1)
     rng = np.random.default_rng(seed)
     s = fr_to_limbs(int(rng.integers(1, 1 << 62)) * 0x9E3779B97F4A7C15 % R_MOD)
-    params = cq.ParamsKZG.setup_from_toxic_waste(k, s)
-    Nt = max(N, n)
-    tsrs = cq.TableSRS.setup_from_toxic_waste(N - 1, s)
-    big = tsrs if Nt == N else cq.TableSRS.setup_from_toxic_waste(Nt - 1, s, precompute=False)
-    # b0_g1_bound = the last n - 1 powers of the length-Nt table SRS (my_test.rs:205, static_lookup.rs:149)
-    bound_host = big.g1.to_host()[Nt - (n - 1):]
-    bound = cq.DeviceBases(np.ascontiguousarray(bound_host))
     # spread-table-like values: distinct 30-bit values, second table offset (sha/src/tables.rs generates (x, f(x)) tuples)
     t0 = rng.choice(1 << 30, N, replace=False).astype(np.int64)
     tvals = [[int(v) for v in t0], [int(v) + (1 << 40) for v in rng.permutation(t0)]]
-    tables = [cq.cq.StaticTableValues(_fr_array_fast(v), tsrs.g1) for v in tvals]
     rows = rng.integers(0, N, usable)
     adv = [[tv[r] for r in rows] + [int(v) for v in rng.integers(0, 1 << 50, n - usable)] for tv in tvals]
     for j in range(2, A):
@@ -105,16 +96,35 @@ def build_circuit(cq, k, log_table, n_advice, seed=1):
     for r in rows:
         m[int(r)] = m.get(int(r), 0) + 1
     idx = np.array(sorted(m), dtype=np.uint32)
-    mult = _fr_array_fast([m[int(i)] for i in idx])
-    lk = PR.StaticLookup([0, 1], tsrs, tables, bound)
-    pk = PR.ProvingKey(params, k, cs_degree, bf, list(range(A)), [_fr_array_fast(sg) for sg in sig], [(j, 0) for j in range(A)], [lk],
-                       vk_transcript_repr=0xC0DE + k)
-    witness = [_fr_array_fast(c) for c in adv]
     nsets = (A + cs_degree - 3) // (cs_degree - 2)
-    rnd = {"permutation_blinds": [_fr_array_fast([int(v) for v in rng.integers(1, 1 << 62, bf)]) for _ in range(nsets)],
-           "random_poly": _fr_array_fast([int(v) for v in rng.integers(1, 1 << 62, n)])}
+    return {"k": k, "N": N, "A": A, "cs_degree": cs_degree, "bf": bf, "s": s, "vk_repr": 0xC0DE + k,
+            "tables": [_fr_array_fast(v) for v in tvals], "advice": [_fr_array_fast(c) for c in adv], "sigma": [_fr_array_fast(sg) for sg in sig],
+            "idx": idx, "mult": _fr_array_fast([m[int(i)] for i in idx]),
+            "permutation_blinds": [_fr_array_fast([int(v) for v in rng.integers(1, 1 << 62, bf)]) for _ in range(nsets)],
+            "random_poly": _fr_array_fast([int(v) for v in rng.integers(1, 1 << 62, n)])}
+
+
+def build_circuit(cq, k, log_table, n_advice, seed=1):
+    """proving key + witness of the lookup circuit; everything that keygen would prepare (SRS, tables with their cached quotients,
+    sigma polynomials) is resident on the device when this returns"""
+    from sha2_on_cq_halo2_b200 import prover as PR
+
+    c = circuit_arrays(k, log_table, n_advice, seed)
+    n, N, A = 1 << k, c["N"], c["A"]
+    params = cq.ParamsKZG.setup_from_toxic_waste(k, c["s"])
+    Nt = max(N, n)
+    tsrs = cq.TableSRS.setup_from_toxic_waste(N - 1, c["s"])
+    big = tsrs if Nt == N else cq.TableSRS.setup_from_toxic_waste(Nt - 1, c["s"], precompute=False)
+    # b0_g1_bound = the last n - 1 powers of the length-Nt table SRS (my_test.rs:205, static_lookup.rs:149)
+    bound_host = big.g1.to_host()[Nt - (n - 1):]
+    bound = cq.DeviceBases(np.ascontiguousarray(bound_host))
+    tables = [cq.cq.StaticTableValues(v, tsrs.g1) for v in c["tables"]]
+    lk = PR.StaticLookup([0, 1], tsrs, tables, bound)
+    pk = PR.ProvingKey(params, k, c["cs_degree"], c["bf"], list(range(A)), c["sigma"], [(j, 0) for j in range(A)], [lk],
+                       vk_transcript_repr=c["vk_repr"])
+    rnd = {"permutation_blinds": c["permutation_blinds"], "random_poly": c["random_poly"]}
     keep = (params, tsrs, big, bound, tables)
-    return pk, witness, (idx, mult), rnd, keep
+    return pk, c["advice"], (c["idx"], c["mult"]), rnd, keep
 
 
 def run(cq, k, log_table=16, n_advice=8, reps=3):
