@@ -1,4 +1,6 @@
-//! Rust side of the drop-in boundary (SOURCE ONLY — not compiled in this repository's image, see Cargo.toml).
+//! Rust side of the drop-in boundary — a SOURCE SKETCH: never compiled (no Rust toolchain in this repository's image, see Cargo.toml);
+//! `mod generic` below holds `unimplemented!()` placeholders where the reference's own generic bodies stay. What is tested is the C ABI
+//! these declarations bind (tests/cpp/*.cpp, tests/test_abi.py).
 //!
 //! `best_multiexp` / `best_fft` keep the reference's signatures (halo2_proofs/src/arithmetic.rs:132,171). For the two
 //! instantiations on the prover's hot path — `C = bn256::G1Affine` and `G = bn256::Fr` — they call libcqb200.so; every
@@ -56,6 +58,19 @@ extern "C" {
     pub fn cqb_fr_mul_dev(d_a: *const c_void, d_b: *const c_void, n: usize, d_out: *mut c_void) -> c_int;
     pub fn cqb_msm_bn254_g1_sparse_dev(b: cqb_bases_t, d_idx: *const u32, d_scalars: *const c_void, m: usize, out_xy: *mut u64,
                                        is_inf: *mut c_int) -> c_int;
+    // round 2: one process, several GPUs (cqb_init_multi), MSMKZG::eval, the G2 side, batched evaluations
+    pub fn cqb_init_multi(n_devices: c_int) -> c_int;
+    pub fn cqb_active_devices() -> c_int;
+    pub fn cqb_bases_register_sharded(affine_xy: *const u64, n: usize, out: *mut cqb_bases_t) -> c_int;
+    pub fn cqb_msm_bn254_g1_multi_dev(b: cqb_bases_t, offset: usize, d_scalars: *const *const c_void, n: usize, out_xy: *mut u64,
+                                      is_inf: *mut c_int) -> c_int;
+    pub fn cqb_set_host_bases_cache(budget_bytes: i64) -> c_int;
+    pub fn cqb_msm_bn254_g1_jacobian(jacobian_xyz: *const u64, scalars: *const u64, n: usize, out_xy: *mut u64, is_inf: *mut c_int) -> c_int;
+    pub fn cqb_g1_batch_normalize(jacobian_xyz: *const u64, n: usize, affine_xy_out: *mut u64) -> c_int;
+    pub fn cqb_g2_powers(s: *const u64, count: usize, g2_affine_out: *mut u64) -> c_int;
+    pub fn cqb_msm_bn254_g2(g2_affine: *const u64, scalars: *const u64, n: usize, out_xy: *mut u64, is_inf: *mut c_int) -> c_int;
+    pub fn cqb_eval_polynomials_dev(d_coeffs: *const *const c_void, n: usize, points: *const u64, count: u32, out: *mut u64) -> c_int;
+    pub fn cqb_fr_axpy_dev(d_acc: *mut c_void, a: *const u64, d_x: *const c_void, n: usize) -> c_int;
     pub fn cqb_dev_alloc(bytes: usize, d_out: *mut *mut c_void) -> c_int;
     pub fn cqb_dev_free(d: *mut c_void) -> c_int;
     pub fn cqb_memcpy_h2d(d_dst: *mut c_void, h_src: *const c_void, bytes: usize) -> c_int;
