@@ -53,4 +53,40 @@ a = O.synth_scalars(9, 1000)
 x = O.synth_scalars(10, 1)[0]
 assert np.array_equal(cqb200.eval_polynomial(a, x), O.eval_polynomial(a, x))
 assert np.array_equal(cqb200.kate_division(a, x), O.kate_division(a, x))
+# ---- round 2 kernels: batched-affine accumulation (+ mark / merge), batch_normalize, G2, axpy / batched evaluation, a complete proof
+for seg in (3, 5):
+    L.check(lib.cqb_msm_set_accumulator(2, seg))
+    n = 3000
+    sc, bs = O.synth_scalars(20 + seg, n), O.synth_bases(21 + seg, n, 2)
+    bs[5] = 0
+    bs[7] = bs[6]; sc[7] = sc[6]
+    assert np.array_equal(cqb200.best_multiexp(sc, bs).to_affine(), O.best_multiexp(sc, bs, 2)[1])
+    dev = cqb200.DeviceBases(bs, precompute=True, window_bits=11)
+    assert np.array_equal(dev.msm(sc).to_affine(), O.best_multiexp(sc, bs, 2)[1])
+    sk = sc.copy(); sk[:] = sk[0]
+    assert np.array_equal(dev.msm(sk).to_affine(), O.best_multiexp(sk, bs, 2)[1])
+    dev.free()
+L.check(lib.cqb_msm_set_accumulator(0, 0))
+jac = np.stack([O.g1_mul_a(b, O.synth_scalars(30 + i, 1)[0]) for i, b in enumerate(O.synth_bases(31, 40, 1))])
+jac[3] = 0
+assert np.array_equal(cqb200.batch_normalize(jac), O.g1_batch_normalize(jac))
+msm = cqb200.MSMKZG()
+scj = O.synth_scalars(32, 40)
+for i in range(40):
+    msm.append_term(scj[i], jac[i])
+assert np.array_equal(msm.eval().to_affine(), O.best_multiexp(scj, O.g1_batch_normalize(jac), 2)[1])
+g2 = cqb200.kzg.g2_powers(s, 9)
+assert np.array_equal(g2, O.g2_powers(s, 9))
+o16, inf = np.zeros(16, np.uint64), ctypes.c_int(0)
+sc2 = O.synth_scalars(33, 9)
+L.check(lib.cqb_msm_bn254_g2(L.p64(g2), L.p64(sc2), 9, L.p64(o16), ctypes.byref(inf)))
+assert np.array_equal(o16, O.g2_msm(g2, sc2))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+import prove_real
+from sha2_on_cq_halo2_b200 import prover as PR
+
+pk, witness, m_sparse, rnd, keep = prove_real.build_circuit(cqb200, 6, 5, 3)
+info = PR.create_proof(pk, witness, [m_sparse], rnd, prove_real.Blake2bTranscript())
+assert PR.expected_h_eval(pk, info) == info["h_eval"]
+pk.free()
 print("sanitize_small: all ok; launches", lib.cqb_launch_count())
