@@ -13,8 +13,10 @@ arithmetic.rs:137-153): each rank owns n/N resident SRS points + scalars, comput
 value  : Mpts/s with scalars and bases already resident in HBM (device-pointer C-ABI call)
 e2e    : Mpts/s through the host-pointer C-ABI call a halo2 caller would make (scalars in pinned host memory, H2D inside
          the timed region, 64 B result read back); bases resident (the SRS is uploaded once per proving key)
-roofline: msm_accumulate_kernel, integer pipe: 21,760 MAD32 per point over its CUDA-event duration,
-         against the IMAD.WIDE peak calibrated on this pool's B200 (profiles/r01_int_pipe_calibration.md)
+roofline: the bucket-accumulation phase (the affine tree's level kernels + the XYZZ tail; msm_accumulate_kernel alone below 40
+         entries per bucket), integer pipe: the MAD32 it EXECUTES per point over its CUDA-event duration against the IMAD.WIDE issue
+         limit calibrated on this pool's B200 (profiles/INT_PEAK.json); the same time is also read on the round-1 XYZZ formula and on
+         SURVEY.md §8d's pinned 21,760 MAD32 per point
 """
 import argparse
 import ctypes
@@ -34,8 +36,19 @@ os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "SHA2-CQ prove ms; BN254 MSM Mpts/s @2^24; Fr NTT Gelem/s @2^24; 1/2/4/8 GPU"
 UNIT = "Mpts/s (BN254 G1 MSM @2^24)"
+TREE_TRAFFIC_2P24 = 83.9e9        # DRAM bytes of the accumulation phase of one 2^24 step, profiles/r02_launches_bench_2p24.csv
 MAD32_PER_POINT = 21760           # SURVEY.md §8(d), the PINNED algorithm: 16 windows x 10 modmul x 136 MAD32
 MAD32_PER_XYZZ_ADD = 1232         # what the kernel executes per bucket addition: 6 mul x 136 + 2 sqr x 108 + one fused a*b-c*d x 200
+# affine-tree pair addition: 5 mul x 136 + 1 sqr x 108 = 788, minus the two multiplications the first pair of a thread skips (2 x 136 / 16),
+# plus the inversion pass's share (3 mul per thread of 16 pairs; the safegcd itself runs on the ALU pipe)
+MAD32_PER_AFFINE_ADD = 788 - 2 * 136 / 16 + 3 * 136 / 16
+
+
+def mad32_per_entry(levels):
+    """executed MAD32 per bucket-list entry: 1 - 2^-levels of the additions are affine pair additions, the rest XYZZ"""
+    if levels <= 0:
+        return float(MAD32_PER_XYZZ_ADD)
+    return (1 - 2.0 ** -levels) * MAD32_PER_AFFINE_ADD + 2.0 ** -levels * MAD32_PER_XYZZ_ADD
 SEED_BASES, SEED_SCALARS, SEED_NTT = 0xC0FFEE, 0x5EED0001, 0x5EED0002
 
 
@@ -356,6 +369,7 @@ def main():
         acc_ms.append(phases[3])
         ph_avg += np.array([phases[i] for i in range(8)])
     ph_avg /= max(1, len(acc_ms))
+    tree_levels = int(lib.cqb_msm_last_tree_levels())  # of the device-resident call just profiled
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
     result_e2e = step_e2e().copy()
     # the same call from PAGEABLE host memory (what a Rust Vec<Fr> is): the library stages it through pinned buffers with host
@@ -389,12 +403,23 @@ def main():
     e2e = n_total / (ms_e2e * 1e-3) / 1e6
     t_acc = float(np.mean(acc_ms)) if acc_ms else float("nan")
     peak, peak_src = int_peak()
-    executed = per * nwin_eff * MAD32_PER_XYZZ_ADD / (t_acc * 1e-3) / 1e12       # T MAD32/s the kernel really issues
+    per_entry = mad32_per_entry(tree_levels)
+    acc_kernels = ("msm_accumulate_kernel" if tree_levels == 0 else
+                   f"accumulation phase: {tree_levels} levels of aft_level_kernel (forward + backward) and aft_invert_kernel, then "
+                   f"msm_accumulate_kernel<DIRECT> over the remaining 1/{1 << tree_levels} of the list")
+    executed = per * nwin_eff * per_entry / (t_acc * 1e-3) / 1e12                 # T MAD32/s the phase really issues
+    xyzz_alg = per * nwin_eff * MAD32_PER_XYZZ_ADD / (t_acc * 1e-3) / 1e12        # the same time read on the round-1 (XYZZ) formula
     pinned_alg = per * MAD32_PER_POINT / (t_acc * 1e-3) / 1e12                   # the same time read on SURVEY's pinned count
     ncu_traffic = None
     if world == 1 and args.log_n == 24 and not args.no_precompute:
-        ncu_traffic = {"bytes": 29.66e9, "source": "profiles/r01b_ncu_msm_accumulate_raw.csv (one ncu --set full capture of this launch: "
-                                                    "29.47 GB read + 0.18 GB written); not re-measured by this run"}
+        ncu_traffic = ({"bytes": 29.66e9, "source": "profiles/r01b_ncu_msm_accumulate_raw.csv (one ncu --set full capture of this launch: "
+                                                     "29.47 GB read + 0.18 GB written); not re-measured by this run"} if tree_levels == 0 else
+                       {"bytes": TREE_TRAFFIC_2P24, "source": "profiles/r02_launches_bench_2p24.csv (dram__bytes_read.sum + dram__bytes_write.sum "
+                                                               "summed over the accumulation-phase kernels of one step); not re-measured by this run"})
+    # algorithmic bytes per entry: XYZZ 68 B (64 B point + 4 B index); tree: per level-l pair 64 B (x of both operands) + 32 B parked product
+    # written, then 128 B (both points) + 32 B read and 64 B written = 320 B, i.e. 320 / 2^l per entry, + 8 B of index reads at level 1,
+    # + the XYZZ tail's 64 B per remaining point
+    alg_bytes_entry = 68.0 if tree_levels == 0 else 320.0 * (1 - 2.0 ** -tree_levels) + 8 + 64.0 * 2.0 ** -tree_levels
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -411,27 +436,32 @@ def main():
                                  "8 host threads per part, overlapped with the previous part's kernels"},
         "parity": parity,
         "gpu_launches": int(launches) * args.steps,
-        "roofline": {"bound": "int", "kernel": "msm_accumulate_kernel", "achieved": executed, "peak": peak,
+        "roofline": {"bound": "int", "kernel": acc_kernels, "achieved": executed, "peak": peak,
                      "unit": "TMAD32/s", "frac": executed / peak,
                      "traffic": ncu_traffic["bytes"] if ncu_traffic else None, "traffic_source": ncu_traffic["source"] if ncu_traffic else None,
                      "kernel_ms": t_acc,
                      # achieved = EXECUTED multiply-accumulates: windows_per_point bucket additions x (6 mul x 136 + 2 sqr x 108 + one
                      # fused a*b-c*d x 200) MAD32, over the kernel's CUDA-event time; peak = IMAD.WIDE issue limit (< 1 by construction)
-                     "executed_mad32_per_point": nwin_eff * MAD32_PER_XYZZ_ADD,
+                     "executed_mad32_per_point": nwin_eff * per_entry, "affine_tree_levels": tree_levels,
                      "peak_source": peak_src,
-                     "whole_msm_frac": n_total / world * nwin_eff * MAD32_PER_XYZZ_ADD / (ms_dev * 1e-3) / 1e12 / peak,
+                     "whole_msm_frac": n_total / world * nwin_eff * per_entry / (ms_dev * 1e-3) / 1e12 / peak,
+                     # the same time read on the XYZZ formula of round 1 (1,232 MAD32 per addition): what the kernel of that round would
+                     # have had to issue to finish in this time — above its 0.90 ceiling when the tree is on, which is the point of it
+                     "vs_xyzz_formula": {"mad32_per_point": nwin_eff * MAD32_PER_XYZZ_ADD, "achieved": xyzz_alg, "frac": xyzz_alg / peak},
                      # the same kernel time read against the algorithm SURVEY.md 8(d) pinned for grading (16 windows x 10 modmul x 136):
                      # above 1 because the kernel does less work than that algorithm (13 windows, cheaper squarings, one fused reduction)
                      "vs_pinned_algorithm": {"mad32_per_point": MAD32_PER_POINT, "achieved": pinned_alg, "frac": pinned_alg / peak,
                                              "whole_msm_frac": n_total / world * MAD32_PER_POINT / (ms_dev * 1e-3) / 1e12 / peak,
                                              "vs_nominal_18p6T": n_total / world * MAD32_PER_POINT / (ms_dev * 1e-3) / 1e12 / 18.6}},
         # the same kernel against the HBM roofline, in the canonical schema: it is NOT bandwidth-bound (frac << 1 by design)
-        "roofline_hbm": {"bound": "hbm", "kernel": "msm_accumulate_kernel",
-                         "achieved": per * nwin_eff * 68 / (t_acc * 1e-3) / 1e9, "peak": measured_peaks().get("hbm_gbs", 6650.0),
-                         "unit": "GB/s", "frac": per * nwin_eff * 68 / (t_acc * 1e-3) / 1e9 / measured_peaks().get("hbm_gbs", 6650.0),
+        "roofline_hbm": {"bound": "hbm", "kernel": acc_kernels,
+                         "achieved": per * nwin_eff * alg_bytes_entry / (t_acc * 1e-3) / 1e9, "peak": measured_peaks().get("hbm_gbs", 6650.0),
+                         "unit": "GB/s", "frac": per * nwin_eff * alg_bytes_entry / (t_acc * 1e-3) / 1e9 / measured_peaks().get("hbm_gbs", 6650.0),
                          "traffic": ncu_traffic["bytes"] if ncu_traffic else None, "traffic_source": ncu_traffic["source"] if ncu_traffic else None,
-                         "algorithmic_bytes_per_launch": per * nwin_eff * 68,
-                         "note": "68 B per bucket addition (64 B affine point + 4 B sorted index) x windows per point",
+                         "algorithmic_bytes_per_launch": per * nwin_eff * alg_bytes_entry,
+                         "note": ("68 B per bucket addition (64 B affine point + 4 B sorted index) x windows per point" if tree_levels == 0 else
+                                  "affine tree: 320 B per pair addition (forward 64 + 32, backward 128 + 32 + 64) over the levels, 8 B of index reads "
+                                  "per entry, 64 B per point of the XYZZ tail — the tree trades multiplier work for HBM traffic"),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in measured_peaks() else "fallback 6650 GB/s"},
         "msm_phase_ms": {k: float(v) for k, v in zip(["count", "scan", "scatter", "accumulate", "merge", "reduce", "window_sum", "final"], ph_avg)},
     }

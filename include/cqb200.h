@@ -325,12 +325,22 @@ CQB_API int cqb_msm_set_window_bits(int c);
 /* number of point-range parts a large device-resident MSM is cut into (the sort phase of part p+1 runs on a second stream
  * under the bucket accumulation of part p); 0 = automatic, 1 = no pipelining, at most 8. Results do not depend on it. */
 CQB_API int cqb_msm_set_parts(int parts);
-/* bucket accumulation variant: 0 = automatic, 1 = XYZZ mixed additions, 2 = batched affine additions (the reference's batch_add,
- * arithmetic/curves/src/derive/curve.rs:4-141, as a kernel: Montgomery's trick over the streams of a thread, one safegcd
- * inversion per step). Measured on B200 the affine variant is SLOWER (2^24: 44-56 ms against 32 ms), so
- * automatic means XYZZ; the variant stays selectable and parity-tested (tests/test_gpu_affine_acc.py).
- * affine_seg_log: entries per accumulation stream = 2^affine_seg_log (0 = automatic). Results do not depend on either. */
+/* bucket accumulation variant (the CPU form of 2 and 3 is the reference's batch_add, arithmetic/curves/src/derive/curve.rs:4-141):
+ *   0 = automatic: the affine tree (3) for MSMs over a precomputed table with >= 40 entries per bucket, its depth chosen from the
+ *       bucket length; XYZZ otherwise
+ *   1 = XYZZ mixed additions (1,232 MAD32 each)
+ *   2 = batched affine additions as per-thread streams with one safegcd inversion per step: measured SLOWER than XYZZ on B200
+ *       (2^24: 44-56 ms against 32 ms); kept selectable and parity-tested (tests/test_gpu_affine_acc.py)
+ *   3 = the affine tree with the depth of cqb_msm_set_tree_levels: every bucket's run of the sorted list is padded to a multiple of
+ *       2^levels entries, so that each level is ONE batch of independent pair additions (788 MAD32 each) over the whole list —
+ *       forward pass (denominators, running products), one lane-parallel inversion pass, backward pass — and only 1 / 2^levels of
+ *       the additions stay XYZZ. Measured 2^24: accumulation 28.1 ms against 32.0 ms (tests/test_gpu_affine_tree.py).
+ * affine_seg_log: variant 2 only, entries per stream = 2^affine_seg_log (0 = automatic). Results do not depend on any of these. */
 CQB_API int cqb_msm_set_accumulator(int mode, int affine_seg_log);
+/* depth of the affine tree when variant 3 is forced: 1..6, default 4 */
+CQB_API int cqb_msm_set_tree_levels(int levels);
+/* tree depth the most recent MSM's accumulation ran with (its largest part); 0 = XYZZ mixed additions only */
+CQB_API int cqb_msm_last_tree_levels(void);
 
 #ifdef __cplusplus
 }

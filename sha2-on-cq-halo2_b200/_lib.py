@@ -109,6 +109,8 @@ SYMBOLS = [
     ("cqb_msm_set_window_bits", _int, [_int]),
     ("cqb_msm_set_parts", _int, [_int]),
     ("cqb_msm_set_accumulator", _int, [_int, _int]),
+    ("cqb_msm_set_tree_levels", _int, [_int]),
+    ("cqb_msm_last_tree_levels", _int, []),
     ("cqb_msm_set_profiling", _int, [_int]),
     ("cqb_msm_phase_ms", _int, [ctypes.POINTER(ctypes.c_float), _int]),
 ]

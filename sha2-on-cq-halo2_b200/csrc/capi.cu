@@ -139,6 +139,14 @@ static int init_slot(int slot, int device) {
     if (prop.major < 10) return fail(CQB_E_NO_DEVICE, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
     c.device = device;
     c.sm_count = prop.multiProcessorCount;
+    if (const char* v = getenv("CQB_L2_FETCH")) {  // experiment: DRAM -> L2 fetch granularity (32 / 64 / 128 B)
+        size_t before = 0, after = 0;
+        cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(v));
+        cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "cqb: L2 fetch granularity %zu -> %zu (%s)\n", before, after, cudaGetErrorString(e));
+        cudaGetLastError();
+    }
     CQB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     c.own_stream = true;
     c.inited = true;
@@ -439,10 +447,15 @@ int cqb_bases_precompute(cqb_bases_t h, int window_bits) {
     size_t free_b = 0, total_b = 0;
     CQB_CUDA(cudaMemGetInfo(&free_b, &total_b));
     // Memory plan: the table may take what is free minus the working set an MSM over this set needs afterwards —
-    // the bucket-sorted list (nwin x n x 4 B), the scalars (n x 32 B), histograms / bucket arrays / chunk partials (< 2 GiB) — and a
+    // the bucket-sorted list (nwin x n x 4 B), the affine tree's scratch (72 B per list entry of one part, at most ~16 GiB), the scalars
+    // (n x 32 B), histograms / bucket arrays / chunk partials (< 2 GiB) — and a
     // reserve of 1/16 of the device for the caller's polynomials. With window_bits = 0 (automatic) a set whose table does not fit simply
     // stays on the windowed layout (16 windows instead of 13: ~20 % slower, results identical); an explicit window size fails loudly.
-    const size_t need_after = bs.n * ((size_t)nwin * 4 + 32) + ((size_t)2 << 30) + total_b / 16;
+    const size_t need_after = bs.n * 32 + msm_working_set_bytes(bs.n, nwin) + total_b / 16;
+    if (bytes + need_after > free_b) {  // the grow-only working buffers of earlier, larger calls go first
+        msm_release_scratch();
+        CQB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    }
     if (bytes + need_after > free_b) {
         if (window_bits == 0) return 0;
         return fail(CQB_E_OOM, "precomputed table needs %zu bytes (+ %zu of MSM working set), only %zu free", bytes, need_after, free_b);
@@ -585,7 +598,10 @@ static int msm_host_enqueue(BaseSet* bs, size_t offset, const uint64_t* scalars,
         static const int env_parts = getenv("CQB_PAGEABLE_PARTS") ? std::max(2, std::min(8, atoi(getenv("CQB_PAGEABLE_PARTS")))) : 0;  // experiments
         // below 2^22 points a part's fixed cost (~0.5 ms of launches and tails) outweighs what a third part hides of the copy
         const int small = n < ((size_t)1 << 22);
-        const int parts = pinned ? (small ? 2 : CQB_HOST_PARTS) : (env_parts ? env_parts : (small ? 3 : g_pageable_parts));
+        int parts = pinned ? (small ? 2 : CQB_HOST_PARTS) : (env_parts ? env_parts : (small ? 3 : g_pageable_parts));
+        // beyond 2^24 points: more parts, so that the largest one (11/16 of the points split over parts - 2, msm_part_bounds) stays near 2^24
+        // and the affine tree's scratch near 16 GiB
+        if (n > ((size_t)1 << 24)) parts = std::min(8, std::max(parts, 2 + (int)((n / 16 * 11 + ((size_t)1 << 24) - 1) >> 24)));
         if (!pinned) feeder.start_staging(n, parts);
         const bool use_table = bs->table != nullptr;
         if (use_table) return msm_run_precomputed(bs->table, bs->n, bs->table_c, offset, g_scalars->p, nullptr, n, d_out, 1, parts, nullptr, &feeder);
@@ -1538,10 +1554,19 @@ int cqb_msm_set_window_bits(int c) {
 
 int cqb_msm_set_accumulator(int mode, int affine_seg_log) {
     LOCK;
-    if (mode < 0 || mode > 2 || affine_seg_log < 0 || affine_seg_log > 10) return fail(CQB_E_BAD_ARG, "cqb_msm_set_accumulator: mode 0..2, segment log 0..10");
+    if (mode < 0 || mode > 3 || affine_seg_log < 0 || affine_seg_log > 10) return fail(CQB_E_BAD_ARG, "cqb_msm_set_accumulator: mode 0..3, segment log 0..10");
     msm_set_accumulator(mode);
     msm_set_affine_segment(affine_seg_log);
     if (const char* v = getenv("CQB_AFF_VARIANT")) msm_set_affine_variant(atoi(v));
+    if (const char* v = getenv("CQB_TREE_LEVELS")) msm_set_tree_levels(atoi(v));
+    if (const char* v = getenv("CQB_TREE_CFG")) msm_set_tree_config(atoi(v), strchr(v, ',') ? atoi(strchr(v, ',') + 1) : 0);
+    return 0;
+}
+int cqb_msm_last_tree_levels(void) { return msm_last_tree_levels(); }
+int cqb_msm_set_tree_levels(int levels) {
+    LOCK;
+    if (levels < 1 || levels > 6) return fail(CQB_E_BAD_ARG, "cqb_msm_set_tree_levels: 1..6");
+    msm_set_tree_levels(levels);
     return 0;
 }
 int cqb_msm_set_parts(int parts) {

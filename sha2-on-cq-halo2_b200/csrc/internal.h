@@ -58,7 +58,10 @@ int msm_run_precomputed(const void* d_table, size_t table_n, int c, size_t offse
                         size_t n, void* d_out_xy_flag, int batch = 1, int nparts = 0, const cudaEvent_t* ready = nullptr,
                         MsmFeeder* feeder = nullptr);
 void msm_set_parts(int p);
-void msm_set_accumulator(int mode);     // 0 auto | 1 XYZZ mixed additions | 2 batched affine
+void msm_set_accumulator(int mode);     // 0 auto | 1 XYZZ mixed additions | 2 batched affine streams | 3 affine tree
+void msm_set_tree_levels(int levels);
+int msm_last_tree_levels();
+void msm_set_tree_config(int cfg, int dbg);  // experiments
 void msm_set_affine_segment(int seg_log);
 void msm_set_affine_variant(int v);
 // bounds[0..nparts]: the point ranges the parts of an MSM cover (small_first: host-pointer MSMs, see msm.cu)
@@ -69,6 +72,8 @@ int msm_precompute_table(const void* d_bases, size_t n, int c, void* d_table);
 int g1_sum_affine_run(const void* d_points, size_t n, void* d_out_xy_flag);
 int g1_batch_normalize_run(const void* d_jacobian, size_t n, void* d_affine);
 void msm_release_all();
+void msm_release_scratch();                              // grow-only working buffers of the current device
+size_t msm_working_set_bytes(size_t n, int nwin);         // what an MSM over a table of n x nwin points allocates besides its scalars
 void msm_set_window_bits(int c);
 void msm_set_profiling(bool on);
 int msm_phase_ms(float* ms, int cap);

@@ -45,6 +45,21 @@ __device__ __forceinline__ Fq ldg_fq(const uint4* p) {
     r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
     return r;
 }
+// Random reads of 64 B table records: by default a missing sector pulls its whole 128 B line from DRAM (126.7 B per read measured,
+// tools/ubench_gather.cu), the other half of which is a neighbouring point nobody asked for; the L2::64B prefetch-size qualifier
+// halves that (63.7 B per read) — the gather-heavy kernels are DRAM-bound otherwise.
+__device__ __forceinline__ uint4 ldg_u4_64(const uint4* p) {
+    uint4 r;
+    asm("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ Fq ldg_fq_64(const uint4* p) {
+    uint4 a = ldg_u4_64(p), b = ldg_u4_64(p + 1);
+    Fq r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
 __device__ __forceinline__ void st_fq(uint4* p, const Fq& v) {
     p[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
     p[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
@@ -84,7 +99,8 @@ struct MsmShape {
     uint32_t stride;  // nb + 2 : per-set stride of the histogram / offset arrays
     uint32_t table_n; // single set: points per window row of the precomputed table
     uint32_t offset;  // first base of this MSM inside the registered set
-    size_t list_cap;  // capacity of one set's sorted list: n (windowed) or n * nwin (single set)
+    size_t list_cap;  // capacity of one set's sorted list: n (windowed) or n * nwin (single set), plus the padding below
+    int pad_log;      // affine-tree accumulation: every bucket's run in the sorted list is padded to a multiple of 2^pad_log entries
 };
 
 __device__ __forceinline__ Fr load_scalar_canonical(const uint4* scalars, size_t i) {
@@ -173,8 +189,14 @@ __device__ __forceinline__ uint32_t block_excl_suffix_min_1024(uint32_t v, uint3
 }
 
 // (2a) exclusive scan, one CTA per bucket set (windowed layout: nb <= 32768)
+// Padded layout (s.pad_log > 0, affine-tree accumulation): bucket d's run starts at a multiple of 2^pad_log and its unused
+// slots are filled with AFT_PAD here; cursor[] = entry positions (what the scatter advances, cursor[nb+1] = padded total),
+// offs[] = the same in units of 2^pad_log entries (what the accumulation over the tree's outputs and the merge kernels read).
+constexpr uint32_t AFT_PAD = 0xffffffffu;
+__device__ __forceinline__ uint32_t pad_up(uint32_t v, int pad_log) { return (v + ((1u << pad_log) - 1u)) & ~((1u << pad_log) - 1u); }
 __global__ void __launch_bounds__(1024) msm_scan_kernel(uint32_t* __restrict__ hist, uint32_t* __restrict__ offs,
-                                                        uint32_t* __restrict__ cursor, MsmShape s, uint32_t* __restrict__ nonempty) {
+                                                        uint32_t* __restrict__ cursor, MsmShape s, uint32_t* __restrict__ nonempty,
+                                                        uint32_t* __restrict__ sorted) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry_s;
     const int w = blockIdx.x;
@@ -188,7 +210,8 @@ __global__ void __launch_bounds__(1024) msm_scan_kernel(uint32_t* __restrict__ h
     for (uint32_t base = 1; base <= s.nb + 1; base += 1024) {
         last_base = base;
         uint32_t d = base + tid;
-        uint32_t v = (d <= s.nb) ? h[d] : 0u;
+        const uint32_t raw = (d <= s.nb) ? h[d] : 0u;
+        uint32_t v = pad_up(raw, s.pad_log);
         uint32_t x = v;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -208,7 +231,8 @@ __global__ void __launch_bounds__(1024) msm_scan_kernel(uint32_t* __restrict__ h
         }
         __syncthreads();
         uint32_t excl = carry_s + (wid ? warp_sums[wid - 1] : 0u) + (x - v);
-        if (d <= s.nb + 1) { o[d] = excl; cu[d] = excl; }
+        if (d <= s.nb + 1) { o[d] = excl >> s.pad_log; cu[d] = excl; }
+        for (uint32_t j = raw; j < v; j++) sorted[(size_t)w * s.list_cap + excl + j] = AFT_PAD;
         __syncthreads();
         if (tid == 1023) carry_s = excl + v;
         __syncthreads();
@@ -262,14 +286,14 @@ __device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* w
     return excl;
 }
 __global__ void __launch_bounds__(1024) scan_tile_sums_kernel(const uint32_t* __restrict__ hist, uint32_t nb, uint32_t* __restrict__ tile_sums,
-                                                              uint32_t ntiles) {
+                                                              uint32_t ntiles, int pad_log) {
     __shared__ uint32_t ws[32];
     uint32_t base = 1 + blockIdx.x * SCAN_TILE + threadIdx.x * 8;
     uint32_t v = 0, first = NO_BUCKET;
 #pragma unroll
     for (int j = 7; j >= 0; j--) {
         uint32_t d = base + j;
-        if (d <= nb) { uint32_t c = hist[d]; v += c; if (c) first = d; }
+        if (d <= nb) { uint32_t c = hist[d]; v += pad_up(c, pad_log); if (c) first = d; }
     }
     uint32_t total;
     (void)block_excl_scan_1024(v, ws, &total);
@@ -313,7 +337,7 @@ __global__ void __launch_bounds__(1024) scan_tile_offsets_kernel(uint32_t* __res
 }
 __global__ void __launch_bounds__(1024) scan_apply_kernel(uint32_t* __restrict__ hist, uint32_t nb, const uint32_t* __restrict__ tile_sums,
                                                           uint32_t ntiles, uint32_t* __restrict__ offs, uint32_t* __restrict__ cursor,
-                                                          uint32_t* __restrict__ nonempty) {
+                                                          uint32_t* __restrict__ nonempty, int pad_log, uint32_t* __restrict__ sorted) {
     __shared__ uint32_t ws[32];
     uint32_t base = 1 + blockIdx.x * SCAN_TILE + threadIdx.x * 8;
     uint32_t vals[8], v = 0, first = NO_BUCKET;
@@ -321,7 +345,7 @@ __global__ void __launch_bounds__(1024) scan_apply_kernel(uint32_t* __restrict__
     for (int j = 7; j >= 0; j--) {
         uint32_t d = base + j;
         vals[j] = (d <= nb) ? hist[d] : 0u;
-        v += vals[j];
+        v += pad_up(vals[j], pad_log);
         if (vals[j]) first = d;
     }
     uint32_t excl = block_excl_scan_1024(v, ws, nullptr) + tile_sums[blockIdx.x];
@@ -329,8 +353,10 @@ __global__ void __launch_bounds__(1024) scan_apply_kernel(uint32_t* __restrict__
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         uint32_t d = base + j;
-        if (d <= nb + 1) { offs[d] = excl; cursor[d] = excl; }
-        excl += vals[j];
+        if (d <= nb + 1) { offs[d] = excl >> pad_log; cursor[d] = excl; }
+        const uint32_t padded = pad_up(vals[j], pad_log);
+        for (uint32_t q = vals[j]; q < padded; q++) sorted[excl + q] = AFT_PAD;
+        excl += padded;
     }
     uint32_t mine = 0;
 #pragma unroll
@@ -421,7 +447,8 @@ __device__ __forceinline__ uint32_t bucket_of_pos(const uint32_t* __restrict__ o
 // buckets are occupied (no host round trip): DENSE steps to the next bucket id (almost every id is occupied — uniform
 // scalars; this loop shape is 2.6 % faster there, 32.2 vs 33.0 ms at 2^24), SPARSE (< 1/4 of the ids occupied) follows the
 // nxt table so that a step costs the same however many empty ids lie in between.
-template <bool SPARSE>
+// DIRECT: the list is the identity map over `bases` (the affine tree's outputs, one point per 2^pad_log entries): no entry load.
+template <bool SPARSE, bool DIRECT = false>
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint4* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                              const uint32_t* __restrict__ offs, const uint32_t* __restrict__ nxt,
                                                              const uint32_t* __restrict__ nonempty, MsmShape s, int seg_log, uint32_t cpw,
@@ -455,9 +482,13 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint4* __rest
                 bound = o[d + 1];
             }
         }
-        uint32_t e = __ldg(lst + pos);
+        uint32_t e = DIRECT ? (pos << 1) : __ldg(lst + pos);
         const uint4* bp = bases + (size_t)(e >> 1) * 4;
+#ifdef CQB_XYZZ_GATHER_DEFAULT
         Fq x = ldg_fq(bp), y = ldg_fq(bp + 2);
+#else
+        Fq x = DIRECT ? ldg_fq(bp) : ldg_fq_64(bp), y = DIRECT ? ldg_fq(bp + 2) : ldg_fq_64(bp + 2);
+#endif
         if (x.is_zero() && y.is_zero()) continue;  // identity base contributes nothing (reference curve.rs:857-858)
         if (e & 1u) y = fp_neg<FqP>(y);
         g1_madd(acc, x, y);
@@ -465,6 +496,273 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint4* __rest
     if (is_first) st_xyzz(head + gid * 8, acc);
     else st_xyzz(tail + gid * 8, acc);
 }
+
+// (4'') AFFINE-TREE bucket accumulation. The bucket-sorted list is laid out with every bucket's run padded to a multiple of
+// S = 2^pad_log entries (AFT_PAD sentinels = identity), so that at every level l = 1..pad_log the pair (2p, 2p+1) of the
+// level's input list lies inside ONE bucket and all pair additions of a level are independent: level l is one launch of the
+// kernel below over the whole list, 218 M -> 109 M -> ... points, and after pad_log levels one affine point per S entries is
+// left; those (1/S of the additions) go through the XYZZ chunk kernel (DIRECT) and the usual merge. An affine addition costs
+// 5M + 1S = 788 MAD32 against 1,232 for the XYZZ mixed addition because its field inversion is shared: Montgomery's trick
+// over the AFT_T pairs of a thread (running products parked in shared memory), then over the AFT_THREADS threads of the CTA
+// (ONE warp inverts: lane l owns the totals of threads l, l+32, ... and runs the branch-free safegcd of fp.cuh once), i.e.
+// one inversion instruction stream per AFT_T * AFT_THREADS additions; the other CTA of the SM computes meanwhile. The backward
+// pass re-reads the points (L2; level 1 gathers them from the table again), finishes the additions and writes 64 B per pair,
+// coalesced. Exceptional pairs (reference batch_add, arithmetic/curves/src/derive/curve.rs:4-141, and the mixed addition's
+// branches :866-871): an identity operand (sentinel, identity base, an earlier P + (-P)) passes the other one through, P + P
+// joins the batch as a doubling (denominator 2y, numerator 3x^2), P + (-P) gives the identity. Identity = (0, 0).
+// the two operands of a pair: pointers to their 64 B records (nullptr = sentinel) and sign flags
+struct AftPair {
+    const uint4 *pa, *pb;
+    uint32_t na, nb;
+};
+template <bool GATHER>
+__device__ __forceinline__ uint2 aft_entry(const uint32_t* __restrict__ sorted, size_t p, bool valid) {
+    if (GATHER && valid) return __ldg((const uint2*)sorted + p);
+    return make_uint2(AFT_PAD, AFT_PAD);
+}
+template <bool GATHER>
+__device__ __forceinline__ AftPair aft_pair(const uint4* __restrict__ pts, uint2 e, size_t p, bool valid) {
+    AftPair q;
+    if (GATHER) {
+        q.pa = e.x == AFT_PAD ? nullptr : pts + (size_t)(e.x >> 1) * 4;
+        q.pb = e.y == AFT_PAD ? nullptr : pts + (size_t)(e.y >> 1) * 4;
+        q.na = e.x & 1u;
+        q.nb = e.y & 1u;
+    } else {
+        q.pa = valid ? pts + p * 8 : nullptr;
+        q.pb = valid ? q.pa + 4 : nullptr;
+        q.na = q.nb = 0;
+    }
+    return q;
+}
+constexpr int AFT_NT = 128;
+#ifndef AFT_FWD_BATCH
+#define AFT_FWD_BATCH 4
+#endif
+__device__ __noinline__ Fq aft_mul(Fq a, Fq b) { return fp_mul<FqP>(a, b); }
+#define AFT_P(i) (tile + (size_t)(i) * AFT_NT + threadIdx.x)
+// forward: thread g owns the T pairs tile + i * AFT_NT + tid; the running product of their denominators after pair p is parked in
+// pf[p] (32 B, coalesced), the thread's total in tot[g], the pair kinds (2 bits each: 0 add, 1 double, 2 pass an operand through,
+// 3 P + (-P)) in kinds[g]. Loads run one pair (entries: two pairs) ahead of the arithmetic.
+template <bool GATHER, int T>
+__device__ __forceinline__ void aft_forward_tile(const uint4* __restrict__ pts, const uint32_t* __restrict__ sorted, size_t npairs, size_t tile_idx,
+                                                 uint4* __restrict__ pf, uint4* __restrict__ tot, uint32_t* __restrict__ kinds_out) {
+    const size_t tile = tile_idx * (AFT_NT * T);
+    if (tile >= npairs) return;
+    Fq r = Fq::one();
+    uint32_t kinds = 0;
+    constexpr int B = AFT_FWD_BATCH;  // pairs whose gathers are in flight together (the kernel is bound by their latency, not by its one multiplication per pair)
+    uint2 e[B];
+#pragma unroll
+    for (int b = 0; b < B; b++) e[b] = aft_entry<GATHER>(sorted, AFT_P(b), AFT_P(b) < npairs);
+#pragma unroll 1
+    for (int i0 = 0; i0 < T; i0 += B) {
+        AftPair q[B];
+        Fq xa[B], xb[B];
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            q[b] = aft_pair<GATHER>(pts, e[b], AFT_P(i0 + b), AFT_P(i0 + b) < npairs);
+            xa[b] = q[b].pa ? (GATHER ? ldg_fq_64(q[b].pa) : ldg_fq(q[b].pa)) : Fq::zero();
+            xb[b] = q[b].pb ? (GATHER ? ldg_fq_64(q[b].pb) : ldg_fq(q[b].pb)) : Fq::zero();
+        }
+#pragma unroll
+        for (int b = 0; b < B; b++) e[b] = aft_entry<GATHER>(sorted, AFT_P(i0 + B + b), i0 + B + b < T && AFT_P(i0 + B + b) < npairs);
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            const int i = i0 + b;
+            uint32_t kind = 2;
+            bool ida = !q[b].pa, idb = !q[b].pb;
+            if (q[b].pa && xa[b].is_zero()) ida = ldg_fq(q[b].pa + 2).is_zero();
+            if (q[b].pb && xb[b].is_zero()) idb = ldg_fq(q[b].pb + 2).is_zero();
+            if (!(ida || idb)) {
+                Fq d;
+                if (xa[b] == xb[b]) {
+                    Fq ya = ldg_fq(q[b].pa + 2), yb = ldg_fq(q[b].pb + 2);
+                    if (q[b].na) ya = fp_neg<FqP>(ya);
+                    if (q[b].nb) yb = fp_neg<FqP>(yb);
+                    if (ya == yb) { kind = 1; d = fp_dbl<FqP>(ya); }
+                    else kind = 3;
+                } else {
+                    kind = 0;
+                    d = fp_sub<FqP>(xb[b], xa[b]);
+                }
+                if (kind < 2) r = aft_mul(r, d);
+            }
+            kinds |= kind << (2 * i);
+            if (AFT_P(i) < npairs) st_fq(pf + AFT_P(i) * 2, r);
+        }
+    }
+    const size_t g = tile_idx * AFT_NT + threadIdx.x;
+    st_fq(tot + g * 2, r);
+    kinds_out[g] = kinds;
+}
+// inversion of the thread totals [first, first + count) in place (count is clipped to what the forward tiles wrote): thread j owns the
+// totals first + j, first + j + stride, ... (coalesced), Montgomery's trick over them (running products in tp), ONE branch-free safegcd
+// inversion per thread — every lane inverts its own value
+__global__ void __launch_bounds__(128) aft_invert_kernel(uint4* __restrict__ tot, uint4* __restrict__ tp, const uint32_t* __restrict__ total_entries,
+                                                         int level, int pairs_per_cta, size_t first, size_t count, int group, int dbg) {
+    const size_t npairs = (size_t)(*total_entries) >> level;
+    const size_t written = (npairs + pairs_per_cta - 1) / pairs_per_cta * AFT_NT;  // totals the forward tiles wrote
+    if (first >= written) return;
+    const size_t m = min(count, written - first);
+    const size_t stride = (m + group - 1) / group;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= stride) return;
+    tot += first * 2;
+    tp += first * 2;
+    Fq acc = ld_fq(tot + j * 2);
+    st_fq(tp + j * 2, acc);
+    int cnt = 1;
+#pragma unroll 1
+    for (size_t k = j + stride; k < m; k += stride, cnt++) {
+        acc = fp_mul<FqP>(acc, ld_fq(tot + k * 2));
+        st_fq(tp + k * 2, acc);
+    }
+    Fq inv = dbg ? acc : fp_inv_safegcd<FqP>(acc);  // dbg: timing experiments only (wrong results)
+#pragma unroll 1
+    for (int c = cnt - 1; c >= 1; c--) {
+        const size_t k = j + (size_t)c * stride;
+        const Fq v = ld_fq(tot + k * 2);
+        st_fq(tot + k * 2, fp_mul<FqP>(inv, ld_fq(tp + (k - stride) * 2)));
+        inv = fp_mul<FqP>(inv, v);
+    }
+    st_fq(tot + j * 2, inv);
+}
+// Raw 64 B records of a pair's two operands as this lane received them from the loads. GATHER: the four lanes 4j .. 4j+3 read the
+// record of one owner lane TOGETHER (16 B each, one coalesced 64 B request per record; a thread reading its own record issues four
+// 16 B requests that reach the L2 as two sector requests — random L2 misses are limited to ~47 G requests/s on B200 whatever their
+// size, tools/ubench_gather.cu: 2.80 ms -> 1.40 ms for 2^26 random 64 B reads), round k serves the owners 8k .. 8k+7; aft_exchange
+// hands the quarters to their owners through shared memory. Sequential levels read their own records (already coalesced per line).
+struct AftRaw { uint4 a[4], b[4]; };
+template <bool GATHER>
+__device__ __forceinline__ void aft_load_raw(AftRaw& w, const AftPair& q) {
+    if (GATHER) {
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int owner = (lane >> 2) + 8 * k;
+            const uint4* pa = (const uint4*)__shfl_sync(0xffffffffu, (unsigned long long)q.pa, owner);
+            const uint4* pb = (const uint4*)__shfl_sync(0xffffffffu, (unsigned long long)q.pb, owner);
+            w.a[k] = pa ? ldg_u4_64(pa + (lane & 3)) : make_uint4(0, 0, 0, 0);
+            w.b[k] = pb ? ldg_u4_64(pb + (lane & 3)) : make_uint4(0, 0, 0, 0);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            w.a[k] = q.pa ? __ldg(q.pa + k) : make_uint4(0, 0, 0, 0);
+            w.b[k] = q.pb ? __ldg(q.pb + k) : make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+__device__ __forceinline__ Fq fq_of(const uint4& lo, const uint4& hi) {
+    Fq r;
+    r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
+    r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+    return r;
+}
+// xch: this warp's 32 x 64 B exchange buffer (quarter-major: [quarter][owner lane], conflict-free 16 B accesses)
+template <bool GATHER>
+__device__ __forceinline__ void aft_exchange(const AftRaw& w, uint4* xch, Fq& xa, Fq& ya, Fq& xb, Fq& yb) {
+    if (GATHER) {
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int k = 0; k < 4; k++) xch[(lane & 3) * 32 + (lane >> 2) + 8 * k] = w.a[k];
+        __syncwarp();
+        xa = fq_of(xch[lane], xch[32 + lane]);
+        ya = fq_of(xch[64 + lane], xch[96 + lane]);
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; k++) xch[(lane & 3) * 32 + (lane >> 2) + 8 * k] = w.b[k];
+        __syncwarp();
+        xb = fq_of(xch[lane], xch[32 + lane]);
+        yb = fq_of(xch[64 + lane], xch[96 + lane]);
+        __syncwarp();
+    } else {
+        xa = fq_of(w.a[0], w.a[1]); ya = fq_of(w.a[2], w.a[3]);
+        xb = fq_of(w.b[0], w.b[1]); yb = fq_of(w.b[2], w.b[3]);
+    }
+}
+// backward: peel the inverses off, finish the additions (points of pair i-1 and entries of pair i-2 in flight), 64 B per pair out.
+// All 32 lanes of a warp run every iteration (the cooperative loads need them); lanes past the end of the list carry null pairs.
+template <bool GATHER, int T>
+__device__ __forceinline__ void aft_backward_tile(const uint4* __restrict__ pts, const uint32_t* __restrict__ sorted, size_t npairs, size_t tile_idx,
+                                                  const uint4* __restrict__ pf, const uint4* __restrict__ tot,
+                                                  const uint32_t* __restrict__ kinds_in, uint4* __restrict__ out, uint4* xch_all) {
+    const size_t tile = tile_idx * (AFT_NT * T);
+    if (tile >= npairs) return;
+    uint4* xch = xch_all + (threadIdx.x >> 5) * 128;
+    const size_t g = tile_idx * AFT_NT + threadIdx.x;
+    Fq inv = ld_fq(tot + g * 2);
+    const uint32_t kinds = kinds_in[g];
+    AftPair nq = aft_pair<GATHER>(pts, aft_entry<GATHER>(sorted, AFT_P(T - 1), AFT_P(T - 1) < npairs), AFT_P(T - 1), AFT_P(T - 1) < npairs);
+    AftRaw raw;
+    aft_load_raw<GATHER>(raw, nq);
+    uint2 ne = aft_entry<GATHER>(sorted, AFT_P(T > 1 ? T - 2 : 0), T > 1 && AFT_P(T - 2) < npairs);
+    Fq npre = (T > 1 && AFT_P(T - 1) < npairs) ? ld_fq(pf + AFT_P(T - 2) * 2) : Fq::one();
+#pragma unroll 1
+    for (int i = T - 1; i >= 0; i--) {
+        const AftPair q = nq;
+        Fq xa, ya, xb, yb;
+        aft_exchange<GATHER>(raw, xch, xa, ya, xb, yb);
+        const Fq pre = npre;
+        if (i > 0) {
+            nq = aft_pair<GATHER>(pts, ne, AFT_P(i - 1), AFT_P(i - 1) < npairs);
+            aft_load_raw<GATHER>(raw, nq);
+            ne = aft_entry<GATHER>(sorted, AFT_P(i > 1 ? i - 2 : 0), i > 1 && AFT_P(i - 2) < npairs);
+            npre = (i > 1 && AFT_P(i - 1) < npairs) ? ld_fq(pf + AFT_P(i - 2) * 2) : Fq::one();
+        }
+        const size_t p = AFT_P(i);
+        if (p < npairs) {
+            const uint32_t kind = (kinds >> (2 * i)) & 3u;
+            if (GATHER) {
+                if (q.na) ya = fp_neg<FqP>(ya);  // fp_neg(0) = 0: the identity stays (0, 0)
+                if (q.nb) yb = fp_neg<FqP>(yb);
+            }
+            Fq ox, oy;
+            if (kind >= 2) {
+                if (kind == 3) { ox = Fq::zero(); oy = Fq::zero(); }
+                else if (xa.is_zero() && ya.is_zero()) { ox = xb; oy = yb; }
+                else { ox = xa; oy = ya; }
+            } else {
+                Fq d, num;
+                if (kind == 0) { d = fp_sub<FqP>(xb, xa); num = fp_sub<FqP>(yb, ya); }
+                else {
+                    d = fp_dbl<FqP>(ya);
+                    const Fq xx = fp_sqr<FqP>(xa);
+                    num = fp_add<FqP>(fp_dbl<FqP>(xx), xx);
+                }
+                Fq dinv = inv;
+                if (i > 0) {
+                    dinv = fp_mul<FqP>(inv, pre);
+                    inv = fp_mul<FqP>(inv, d);
+                }
+                const Fq lam = fp_mul<FqP>(num, dinv);
+                ox = fp_sub<FqP>(fp_sub<FqP>(fp_sqr<FqP>(lam), xa), xb);
+                oy = fp_sub<FqP>(fp_mul<FqP>(lam, fp_sub<FqP>(xa, ox)), ya);
+            }
+            st_fq(out + p * 4, ox);
+            st_fq(out + p * 4 + 2, oy);
+        }
+    }
+}
+// One launch = the backward pass over the tiles [bwd0, bwd0 + nbwd) and the forward pass over [fwd0, fwd0 + nfwd) of a level, CTAs of the
+// two roles interleaved (even / odd blockIdx): the forward pass is bound by its gathers (one multiplication per pair), the backward
+// pass by the multiplier pipe, so a later slab's forward pass runs in the shadow of an earlier slab's backward pass.
+template <bool GATHER, int T>
+__global__ void __launch_bounds__(AFT_NT) aft_level_kernel(const uint4* __restrict__ pts, const uint32_t* __restrict__ sorted,
+                                                          const uint32_t* __restrict__ total_entries, int level, unsigned fwd0, unsigned nfwd,
+                                                          unsigned bwd0, unsigned nbwd, uint4* __restrict__ pf, uint4* __restrict__ tot,
+                                                          uint32_t* __restrict__ kinds, uint4* __restrict__ out) {
+    __shared__ uint4 xch[GATHER ? (AFT_NT / 32) * 128 : 1];
+    const size_t npairs = (size_t)(*total_entries) >> level;
+    const unsigned idx = blockIdx.x >> 1;
+    if ((blockIdx.x & 1u) == 0) {
+        if (idx < nbwd) aft_backward_tile<GATHER, T>(pts, sorted, npairs, (size_t)bwd0 + idx, pf, tot, kinds, out, xch);
+    } else {
+        if (idx < nfwd) aft_forward_tile<GATHER, T>(pts, sorted, npairs, (size_t)fwd0 + idx, pf, tot, kinds);
+    }
+}
+#undef AFT_P
 
 // (4') BATCHED-AFFINE bucket accumulation (the CPU form is the reference's batch_add, arithmetic/curves/src/derive/curve.rs:4-141).
 // An affine addition needs one field inversion; shared by a batch through Montgomery's trick it costs 5M + 1S = 788 MAD32
@@ -1071,6 +1369,26 @@ int msm_phase_ms(float* ms, int cap) {
     return k;
 }
 
+// the grow-only working buffers of the current device (a following MSM reallocates what it needs)
+void msm_release_scratch() {
+    cudaStreamSynchronize(ctx().stream);
+    if (g_sort_stream) cudaStreamSynchronize(g_sort_stream);
+    g_hist->release();
+    g_sorted->release();
+    g_buckets->release();
+    g_partials->release();
+    g_chunks->release();
+    g_pre_tmp->release();
+    g_aff->release();
+}
+// working set of one MSM of n points over a single-set table with nwin windows, beyond the scalars: sorted list, tree scratch (parts
+// are capped at TREE_PART_ENTRIES entries), histograms / bucket arrays / chunk partials
+constexpr size_t TREE_PART_ENTRIES = (size_t)232 << 20;  // 2^24 points x 13 windows + padding
+size_t msm_working_set_bytes(size_t n, int nwin) {
+    const size_t entries = n * (size_t)nwin, part = std::min(entries, TREE_PART_ENTRIES);
+    return entries * 4 + part * 72 + ((size_t)2 << 30);
+}
+
 void msm_release_all() {
     g_hist->release();
     g_sorted->release();
@@ -1152,6 +1470,7 @@ static MsmShape windowed_shape(size_t n) {
     s.stride = s.nb + 2;
     s.table_n = 0;
     s.offset = 0;
+    s.pad_log = 0;
     s.list_cap = n;
     return s;
 }
@@ -1160,6 +1479,28 @@ static MsmShape windowed_shape(size_t n) {
 // / offsets / sorted list / bucket array; its SORT phase (count, scan, scatter) may run on the sort stream while the
 // ACCUMULATE phase (accumulate, merge) of the previous part runs on the main stream. msm_finish adds the parts' bucket
 // arrays while it reduces them. For a host-pointer MSM the sort of part p additionally waits for the H2D copy of part p.
+// capacity of one set's sorted list: the entries plus, in the padded layout, up to 2^pad_log - 1 sentinels per bucket
+static size_t padded_cap(size_t entries, const MsmShape& s) {
+    if (s.pad_log <= 0) return entries;
+    const size_t m = ((size_t)1 << s.pad_log) - 1;
+    return (entries + (size_t)s.nb * m + m) & ~m;
+}
+// accumulation variant: 0 = automatic, 1 = XYZZ mixed additions, 2 = batched affine streams (measured slower), 3 = affine tree
+static int g_acc_mode = 0;
+void msm_set_accumulator(int mode) { g_acc_mode = mode; }
+static int g_tree_levels = 4;  // experiments: levels of the affine tree (entries per padded run = 2^levels)
+void msm_set_tree_levels(int l) { g_tree_levels = l < 1 ? 1 : (l > 6 ? 6 : l); }
+// levels of the affine tree for an MSM (or a part of one) of n points over shape s; 0 = plain XYZZ accumulation. Measured on B200
+// (profiles/r02_affine_tree.md): the tree pays from ~40 entries per bucket on (2^21 points at c = 20: 5.53 vs 5.73 ms; 2^24: 34.0 vs
+// 37.9 ms), deeper trees as the buckets get longer; below that the padding and the extra launches cost more than the cheaper additions.
+static int tree_pad_log(size_t n, const MsmShape& s) {
+    if (g_acc_mode == 1 || g_acc_mode == 2) return 0;
+    if (!s.single || s.nsets != 1) return 0;
+    const size_t per_bucket = n * (size_t)s.nwin / s.nb;
+    if (g_acc_mode == 3) return per_bucket >= ((size_t)4 << g_tree_levels) ? g_tree_levels : 0;
+    return per_bucket >= 256 ? 4 : per_bucket >= 128 ? 3 : per_bucket >= 40 ? 2 : 0;
+}
+
 struct PartBuf {
     uint32_t *hist, *offs, *cursor, *tile_sums, *nonempty;
     uint32_t* sorted;
@@ -1206,15 +1547,16 @@ static int msm_sort_phase(const void* d_scalars, const uint32_t* d_idx, size_t n
     if (s.single && s.nb > 32768) {
         for (int k = 0; k < s.nsets; k++) {  // one tiled scan per bucket set
             const size_t o = (size_t)k * s.stride;
-            scan_tile_sums_kernel<<<pl.ntiles, 1024, 0, st>>>(b.hist + o, s.nb, b.tile_sums, pl.ntiles);
+            scan_tile_sums_kernel<<<pl.ntiles, 1024, 0, st>>>(b.hist + o, s.nb, b.tile_sums, pl.ntiles, s.pad_log);
             CQB_LAUNCHED();
             scan_tile_offsets_kernel<<<1, 1024, 0, st>>>(b.tile_sums, pl.ntiles);
             CQB_LAUNCHED();
-            scan_apply_kernel<<<pl.ntiles, 1024, 0, st>>>(b.hist + o, s.nb, b.tile_sums, pl.ntiles, b.offs + o, b.cursor + o, b.nonempty);
+            scan_apply_kernel<<<pl.ntiles, 1024, 0, st>>>(b.hist + o, s.nb, b.tile_sums, pl.ntiles, b.offs + o, b.cursor + o, b.nonempty, s.pad_log,
+                                                          b.sorted + (size_t)k * s.list_cap);
             CQB_LAUNCHED();
         }
     } else {
-        msm_scan_kernel<<<s.nsets, 1024, 0, st>>>(b.hist, b.offs, b.cursor, s, b.nonempty);
+        msm_scan_kernel<<<s.nsets, 1024, 0, st>>>(b.hist, b.offs, b.cursor, s, b.nonempty, b.sorted);
         CQB_LAUNCHED();
     }
     prof_end(h, st);
@@ -1238,9 +1580,6 @@ static int msm_sort_phase(const void* d_scalars, const uint32_t* d_idx, size_t n
     return 0;
 }
 
-// bucket accumulation variant: 0 = automatic (= XYZZ: the batched-affine kernel measured slower on B200), 1 = XYZZ mixed additions, 2 = batched affine
-static int g_acc_mode = 0;
-void msm_set_accumulator(int mode) { g_acc_mode = mode; }
 static int g_aff_seg_log = 0;  // experiments: entries per stream = 2^g_aff_seg_log (0 = automatic)
 void msm_set_affine_segment(int seg_log) { g_aff_seg_log = seg_log; }
 
@@ -1307,10 +1646,106 @@ static int msm_acc_phase_affine(const void* d_bases, size_t n, const MsmShape& s
     return 0;
 }
 
+// affine-tree accumulation (kernel comment above): pad_log levels of pair additions, then the XYZZ chunk kernel over the
+// remaining 1 / 2^pad_log of the list; the XYZZ bucket array comes out as msm_acc_phase leaves it
+// scratch of the affine tree: level outputs (cap/2 + cap/4 points), parked products (32 B per level-1 pair), thread totals and
+// their running products (the forward kernel's threads own >= 8 pairs each), kinds
+static size_t tree_scratch_bytes(const MsmShape& s) {
+    const size_t cap = s.list_cap, thr = cap / 2 / 8 + 2 * AFT_NT;
+    return (cap / 2 + cap / 4) * 64 + (cap / 2) * 32 + thr * (32 + 32 + 4) + 64;
+}
+static int g_last_tree_levels = 0;  // tree depth the most recent MSM ran with (its largest part); 0 = XYZZ
+int msm_last_tree_levels() { return g_last_tree_levels; }
+static int g_tree_slabs = 0;  // experiments: slabs per level (0 = automatic)
+static int g_tree_cfg = 0, g_tree_dbg = 0;  // experiments: pairs per thread; dbg = skip the inversion (timing only)
+void msm_set_tree_config(int cfg, int dbg) { g_tree_cfg = cfg % 10; g_tree_slabs = cfg / 10; g_tree_dbg = dbg; }
+template <int T>
+static int tree_level_launch(const uint4* in, const uint32_t* sorted, const uint32_t* total, int level, size_t pairs_ub, uint4* pf, uint4* tot,
+                             uint4* tp, uint32_t* kinds, uint4* out, cudaStream_t st) {
+    const size_t per_cta = (size_t)AFT_NT * T;
+    const unsigned tiles = (unsigned)((pairs_ub + per_cta - 1) / per_cta);
+    // slabs: the forward pass of slab s+1 shares a launch with the backward pass of slab s (their inversion in between)
+    unsigned slabs = g_tree_slabs > 0 ? (unsigned)g_tree_slabs : (tiles >= 16000u ? 2u : 1u);  // measured: 2 slabs 28.1 ms, 1: 28.7, 4: 28.7, 8: 29.3 (2^24)
+    const unsigned per_slab = (tiles + slabs - 1) / slabs;
+    slabs = (tiles + per_slab - 1) / per_slab;
+    const int group = 32;
+    auto launch = [&](unsigned f0, unsigned nf, unsigned b0, unsigned nb) {
+        const unsigned grid = 2 * std::max(nf, nb);
+        if (sorted) aft_level_kernel<true, T><<<grid, AFT_NT, 0, st>>>(in, sorted, total, level, f0, nf, b0, nb, pf, tot, kinds, out);
+        else aft_level_kernel<false, T><<<grid, AFT_NT, 0, st>>>(in, nullptr, total, level, f0, nf, b0, nb, pf, tot, kinds, out);
+        CQB_LAUNCHED();
+    };
+    auto count_of = [&](unsigned sidx) { return std::min(per_slab, tiles - sidx * per_slab); };
+    for (unsigned sidx = 0; sidx <= slabs; sidx++) {
+        const unsigned nf = sidx < slabs ? count_of(sidx) : 0, nb = sidx > 0 ? count_of(sidx - 1) : 0;
+        launch(sidx * per_slab, nf, sidx ? (sidx - 1) * per_slab : 0, nb);
+        if (nf) {
+            const size_t cnt = (size_t)nf * AFT_NT, inv_threads = (cnt + group - 1) / group;
+            aft_invert_kernel<<<(unsigned)((inv_threads + 127) / 128), 128, 0, st>>>(tot, tp, total, level, (int)per_cta, (size_t)sidx * per_slab * AFT_NT,
+                                                                                     cnt, group, g_tree_dbg);
+            CQB_LAUNCHED();
+        }
+    }
+    return 0;
+}
+static int msm_acc_phase_tree(const void* d_bases, size_t n, const MsmShape& s, const PartPlan& pl, const PartBuf& b, cudaStream_t st) {
+    (void)n;
+    const size_t cap = s.list_cap;  // padded capacity, a multiple of 2^pad_log
+    CQB_TRY(g_aff->ensure(tree_scratch_bytes(s)));
+    uint4* bufA = g_aff->as<uint4>();        // levels 1, 3, ...: cap / 2 points
+    uint4* bufB = bufA + (cap / 2) * 4;      // levels 2, 4, ...: cap / 4 points
+    uint4* pf = bufB + (cap / 4) * 4;        // parked running products: 32 B per pair
+    const size_t thr = cap / 2 / 8 + 2 * AFT_NT;
+    uint4* tot = pf + (cap / 2) * 2;
+    uint4* tp = tot + thr * 2;
+    uint32_t* kinds = (uint32_t*)(tp + thr * 2);
+    const uint32_t* total = b.cursor + (size_t)s.nb + 1;  // padded entry total of this part (never advanced by the scatter)
+    int h = prof_begin(3, st);
+    const uint4* in = (const uint4*)d_bases;
+    for (int level = 1; level <= s.pad_log; level++) {
+        uint4* out = (level & 1) ? bufA : bufB;
+        const size_t pairs_ub = cap >> level;
+        const uint32_t* srt = level == 1 ? b.sorted : nullptr;
+        if (g_tree_cfg == 1) CQB_TRY(tree_level_launch<8>(in, srt, total, level, pairs_ub, pf, tot, tp, kinds, out, st));
+        else CQB_TRY(tree_level_launch<16>(in, srt, total, level, pairs_ub, pf, tot, tp, kinds, out, st));
+        in = out;
+    }
+    // the remaining list: cap >> pad_log points, bucket d owns [offs[d], offs[d+1])
+    const size_t entries = cap >> s.pad_log;
+    int seg_log = 6;
+    while (seg_log > 3 && (entries >> seg_log) < 300000) seg_log--;
+    uint32_t cpw = (uint32_t)((entries + ((size_t)1 << seg_log) - 1) >> seg_log);
+    size_t nchunks = cpw;
+    uint32_t big_cap = (uint32_t)(cpw / MERGE_LONG + 2);
+    CQB_TRY(g_chunks->ensure(nchunks * 256 + 16 + (size_t)big_cap * 8));
+    uint4* head = g_chunks->as<uint4>();
+    uint4* tail = head + nchunks * 8;
+    uint32_t* big_count = (uint32_t*)(tail + nchunks * 8);
+    uint2* big_list = (uint2*)(big_count + 4);
+    CQB_CUDA(cudaMemsetAsync(b.buckets, 0, pl.nbuckets * 128, st));
+    CQB_CUDA(cudaMemsetAsync(big_count, 0, 16, st));
+    const unsigned acc_grid = (unsigned)((nchunks + 127) / 128);
+    msm_accumulate_kernel<false, true><<<acc_grid, 128, 0, st>>>(in, nullptr, b.offs, b.hist, b.nonempty, s, seg_log, cpw, b.buckets, head, tail);
+    CQB_LAUNCHED();
+    msm_accumulate_kernel<true, true><<<acc_grid, 128, 0, st>>>(in, nullptr, b.offs, b.hist, b.nonempty, s, seg_log, cpw, b.buckets, head, tail);
+    CQB_LAUNCHED();
+    prof_end(h, st);
+    h = prof_begin(4, st);
+    msm_merge_kernel<<<(unsigned)((pl.nbuckets + 127) / 128), 128, 0, st>>>(b.offs, s, seg_log, cpw, b.buckets, head, tail, big_count, big_list,
+                                                                             big_cap);
+    CQB_LAUNCHED();
+    msm_merge_big_kernel<<<big_cap, 128, 0, st>>>(b.offs, s, seg_log, cpw, b.buckets, head, tail, big_count, big_list);
+    CQB_LAUNCHED();
+    prof_end(h, st);
+    CQB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 static int msm_acc_phase(const void* d_bases, size_t n, const MsmShape& s, const PartPlan& pl, const PartBuf& b, cudaStream_t st) {
     // chunking of the bucket-sorted lists: 16..256 entries per chunk thread. One wave is 148 SMs x 4 CTAs x 128 threads = 76k
     // chunks; with fewer than ~10 waves the last, partly filled wave shows (2^22: 213k chunks of 256 = 2.8 waves -> 10.9 ms, 852k
     // chunks of 64 -> 10.3 ms), so the chunks shrink to 64 entries until there are ~1M of them, and further only to keep >= 150k.
+    if (s.pad_log > 0) return msm_acc_phase_tree(d_bases, n, s, pl, b, st);
     size_t entries = (size_t)n * s.nwin;
     // batched affine: the sorted entries must leave bit 31 free for the first-of-bucket mark
     const bool idx_fits = s.single ? ((size_t)s.nwin * s.table_n < ((size_t)1 << 30)) : true;
@@ -1406,7 +1841,12 @@ static int auto_parts(size_t n, const MsmShape& s, const uint32_t* d_idx) {
     // slow them by about the time the sort would have taken alone (2^24: 39.5 / 39.3 / 41.1 / 42.1 ms; re-measured with the
     // geometric part sizes and the bucket-array fold: 38.0 / 38.6 / 38.7 / 40.1 ms). Parts are used only where there is a copy
     // to hide (host-pointer MSM from pinned memory).
-    (void)n;
+    // the affine tree's scratch is 64 B per list entry: very large MSMs are cut into parts of at most 2^24 x 13 entries so that it stays
+    // ~15 GB (2^26: 4 parts; the parts' sorts run under the previous part's accumulation)
+    if (tree_pad_log(n, s) > 0) {
+        const size_t entries = n * (size_t)s.nwin;
+        return (int)std::min<size_t>(MSM_MAX_PARTS, (entries + TREE_PART_ENTRIES - 1) / TREE_PART_ENTRIES);
+    }
     return 1;
 }
 
@@ -1448,6 +1888,11 @@ static int msm_run_shape(const void* d_bases, const void* d_scalars, const uint3
     g_spans_used = 0;
     if (nparts > MSM_MAX_PARTS) nparts = MSM_MAX_PARTS;
     if (nparts <= 1 && !ready && !feeder) {
+        if (s.pad_log > 0 && g_aff->ensure(tree_scratch_bytes(s)) != 0) {  // no room for the tree's scratch: XYZZ accumulation
+            s.pad_log = 0;
+            s.list_cap = s.single ? n * (size_t)s.nwin : n;
+        }
+        g_last_tree_levels = s.pad_log;
         PartPlan pl;
         CQB_TRY(plan_parts(s, 1, &pl));
         PartBuf b = part_buf(s, pl, 0);
@@ -1460,8 +1905,15 @@ static int msm_run_shape(const void* d_bases, const void* d_scalars, const uint3
     msm_part_bounds(n, nparts, ready != nullptr || feeder != nullptr, bounds);
     size_t per = 0;
     for (int p = 0; p < nparts; p++) per = std::max(per, bounds[p + 1] - bounds[p]);
-    // per-part list capacity
-    s.list_cap = s.single ? per * (size_t)s.nwin : per;
+    // per-part list capacity; each part picks its own tree depth from its size (the padded capacity is that of the largest part)
+    s.pad_log = tree_pad_log(per, s);
+    s.list_cap = padded_cap(s.single ? per * (size_t)s.nwin : per, s);
+    if (s.pad_log > 0 && g_aff->ensure(tree_scratch_bytes(s)) != 0) {
+        s.pad_log = 0;
+        s.list_cap = s.single ? per * (size_t)s.nwin : per;
+    }
+    const bool tree_ok = s.pad_log > 0;
+    g_last_tree_levels = s.pad_log;
     PartPlan pl;
     CQB_TRY(plan_parts(s, nparts, &pl));
     CQB_TRY(ensure_sort_stream());
@@ -1473,6 +1925,7 @@ static int msm_run_shape(const void* d_bases, const void* d_scalars, const uint3
     auto queue_acc = [&](int slot, size_t lo, size_t cnt) -> int {
         MsmShape sp = s;
         sp.offset = offset0 + (uint32_t)lo;
+        sp.pad_log = tree_ok ? tree_pad_log(cnt, s) : 0;
         PartBuf b = part_buf(s, pl, slot);
         CQB_CUDA(cudaStreamWaitEvent(st, g_ev_sorted[slot], 0));
         return msm_acc_phase(d_bases, cnt, sp, pl, b, st);
@@ -1489,6 +1942,7 @@ static int msm_run_shape(const void* d_bases, const void* d_scalars, const uint3
         if (cnt == 0) continue;
         MsmShape sp = s;
         sp.offset = offset0 + (uint32_t)lo;
+        sp.pad_log = tree_ok ? tree_pad_log(cnt, s) : 0;
         PartBuf b = part_buf(s, pl, used);
         CQB_TRY(msm_sort_phase((const char*)d_scalars + lo * 32, d_idx ? d_idx + lo : nullptr, cnt, sp, pl, b, g_sort_stream));
         CQB_CUDA(cudaEventRecord(g_ev_sorted[used], g_sort_stream));
@@ -1530,8 +1984,9 @@ int msm_run_precomputed(const void* d_table, size_t table_n, int c, size_t offse
     s.stride = s.nb + 2;
     s.table_n = (uint32_t)table_n;
     s.offset = (uint32_t)offset;
-    s.list_cap = n * (size_t)s.nwin;
-    if (s.list_cap >= ((size_t)1 << 32) || (size_t)s.nwin * table_n >= ((size_t)1 << 31))
+    s.pad_log = tree_pad_log(n, s);
+    s.list_cap = padded_cap(n * (size_t)s.nwin, s);
+    if (s.list_cap >= ((size_t)1 << 32) || (size_t)s.nwin * table_n >= ((size_t)1 << 31) - 1)
         return fail(CQB_E_BAD_SIZE, "precomputed MSM: %zu x %d entries exceed the 32-bit index range", n, s.nwin);
     return msm_run_shape(d_table, d_scalars, d_idx, n, s, nparts > 0 ? nparts : auto_parts(n, s, d_idx), ready, feeder, d_out);
 }
