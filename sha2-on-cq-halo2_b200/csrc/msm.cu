@@ -546,11 +546,11 @@ __device__ __noinline__ Fq aft_mul(Fq a, Fq b) { return fp_mul<FqP>(a, b); }
 // 3 P + (-P)) in kinds[g]. Loads run one pair (entries: two pairs) ahead of the arithmetic.
 template <bool GATHER, int T>
 __device__ __forceinline__ void aft_forward_tile(const uint4* __restrict__ pts, const uint32_t* __restrict__ sorted, size_t npairs, size_t tile_idx,
-                                                 uint4* __restrict__ pf, uint4* __restrict__ tot, uint32_t* __restrict__ kinds_out) {
+                                                 uint4* __restrict__ pf, uint4* __restrict__ tot, uint64_t* __restrict__ kinds_out) {
     const size_t tile = tile_idx * (AFT_NT * T);
     if (tile >= npairs) return;
     Fq r = Fq::one();
-    uint32_t kinds = 0;
+    uint64_t kinds = 0;
     constexpr int B = AFT_FWD_BATCH;  // pairs whose gathers are in flight together (the kernel is bound by their latency, not by its one multiplication per pair)
     uint2 e[B];
 #pragma unroll
@@ -588,7 +588,7 @@ __device__ __forceinline__ void aft_forward_tile(const uint4* __restrict__ pts, 
                 }
                 if (kind < 2) r = aft_mul(r, d);
             }
-            kinds |= kind << (2 * i);
+            kinds |= (uint64_t)kind << (2 * i);
             if (AFT_P(i) < npairs) st_fq(pf + AFT_P(i) * 2, r);
         }
     }
@@ -687,13 +687,13 @@ __device__ __forceinline__ void aft_exchange(const AftRaw& w, uint4* xch, Fq& xa
 template <bool GATHER, int T>
 __device__ __forceinline__ void aft_backward_tile(const uint4* __restrict__ pts, const uint32_t* __restrict__ sorted, size_t npairs, size_t tile_idx,
                                                   const uint4* __restrict__ pf, const uint4* __restrict__ tot,
-                                                  const uint32_t* __restrict__ kinds_in, uint4* __restrict__ out, uint4* xch_all) {
+                                                  const uint64_t* __restrict__ kinds_in, uint4* __restrict__ out, uint4* xch_all) {
     const size_t tile = tile_idx * (AFT_NT * T);
     if (tile >= npairs) return;
     uint4* xch = xch_all + (threadIdx.x >> 5) * 128;
     const size_t g = tile_idx * AFT_NT + threadIdx.x;
     Fq inv = ld_fq(tot + g * 2);
-    const uint32_t kinds = kinds_in[g];
+    const uint64_t kinds = kinds_in[g];
     AftPair nq = aft_pair<GATHER>(pts, aft_entry<GATHER>(sorted, AFT_P(T - 1), AFT_P(T - 1) < npairs), AFT_P(T - 1), AFT_P(T - 1) < npairs);
     AftRaw raw;
     aft_load_raw<GATHER>(raw, nq);
@@ -713,7 +713,7 @@ __device__ __forceinline__ void aft_backward_tile(const uint4* __restrict__ pts,
         }
         const size_t p = AFT_P(i);
         if (p < npairs) {
-            const uint32_t kind = (kinds >> (2 * i)) & 3u;
+            const uint32_t kind = (uint32_t)(kinds >> (2 * i)) & 3u;
             if (GATHER) {
                 if (q.na) ya = fp_neg<FqP>(ya);  // fp_neg(0) = 0: the identity stays (0, 0)
                 if (q.nb) yb = fp_neg<FqP>(yb);
@@ -752,7 +752,7 @@ template <bool GATHER, int T>
 __global__ void __launch_bounds__(AFT_NT) aft_level_kernel(const uint4* __restrict__ pts, const uint32_t* __restrict__ sorted,
                                                           const uint32_t* __restrict__ total_entries, int level, unsigned fwd0, unsigned nfwd,
                                                           unsigned bwd0, unsigned nbwd, uint4* __restrict__ pf, uint4* __restrict__ tot,
-                                                          uint32_t* __restrict__ kinds, uint4* __restrict__ out) {
+                                                          uint64_t* __restrict__ kinds, uint4* __restrict__ out) {
     __shared__ uint4 xch[GATHER ? (AFT_NT / 32) * 128 : 1];
     const size_t npairs = (size_t)(*total_entries) >> level;
     const unsigned idx = blockIdx.x >> 1;
@@ -1498,6 +1498,9 @@ static int tree_pad_log(size_t n, const MsmShape& s) {
     if (!s.single || s.nsets != 1) return 0;
     const size_t per_bucket = n * (size_t)s.nwin / s.nb;
     if (g_acc_mode == 3) return per_bucket >= ((size_t)4 << g_tree_levels) ? g_tree_levels : 0;
+    // ... and from ~24 M list entries on: below that the levels are too short to fill the machine (2^20 points at c = 17, 15.7 M entries:
+    // 3.48 ms with the tree against 3.28 ms without)
+    if (n * (size_t)s.nwin < ((size_t)24 << 20)) return 0;
     return per_bucket >= 256 ? 4 : per_bucket >= 128 ? 3 : per_bucket >= 40 ? 2 : 0;
 }
 
@@ -1652,7 +1655,7 @@ static int msm_acc_phase_affine(const void* d_bases, size_t n, const MsmShape& s
 // their running products (the forward kernel's threads own >= 8 pairs each), kinds
 static size_t tree_scratch_bytes(const MsmShape& s) {
     const size_t cap = s.list_cap, thr = cap / 2 / 8 + 2 * AFT_NT;
-    return (cap / 2 + cap / 4) * 64 + (cap / 2) * 32 + thr * (32 + 32 + 4) + 64;
+    return (cap / 2 + cap / 4) * 64 + (cap / 2) * 32 + thr * (32 + 32 + 8) + 64;
 }
 static int g_last_tree_levels = 0;  // tree depth the most recent MSM ran with (its largest part); 0 = XYZZ
 int msm_last_tree_levels() { return g_last_tree_levels; }
@@ -1661,11 +1664,11 @@ static int g_tree_cfg = 0, g_tree_dbg = 0;  // experiments: pairs per thread; db
 void msm_set_tree_config(int cfg, int dbg) { g_tree_cfg = cfg % 10; g_tree_slabs = cfg / 10; g_tree_dbg = dbg; }
 template <int T>
 static int tree_level_launch(const uint4* in, const uint32_t* sorted, const uint32_t* total, int level, size_t pairs_ub, uint4* pf, uint4* tot,
-                             uint4* tp, uint32_t* kinds, uint4* out, cudaStream_t st) {
+                             uint4* tp, uint64_t* kinds, uint4* out, cudaStream_t st) {
     const size_t per_cta = (size_t)AFT_NT * T;
     const unsigned tiles = (unsigned)((pairs_ub + per_cta - 1) / per_cta);
     // slabs: the forward pass of slab s+1 shares a launch with the backward pass of slab s (their inversion in between)
-    unsigned slabs = g_tree_slabs > 0 ? (unsigned)g_tree_slabs : (tiles >= 16000u ? 2u : 1u);  // measured: 2 slabs 28.1 ms, 1: 28.7, 4: 28.7, 8: 29.3 (2^24)
+    unsigned slabs = g_tree_slabs > 0 ? (unsigned)g_tree_slabs : ((size_t)tiles * T >= 256000u ? 2u : 1u);  // measured: 2 slabs 28.1 ms, 1: 28.7, 4: 28.7, 8: 29.3 (2^24)
     const unsigned per_slab = (tiles + slabs - 1) / slabs;
     slabs = (tiles + per_slab - 1) / per_slab;
     const int group = 32;
@@ -1698,7 +1701,7 @@ static int msm_acc_phase_tree(const void* d_bases, size_t n, const MsmShape& s, 
     const size_t thr = cap / 2 / 8 + 2 * AFT_NT;
     uint4* tot = pf + (cap / 2) * 2;
     uint4* tp = tot + thr * 2;
-    uint32_t* kinds = (uint32_t*)(tp + thr * 2);
+    uint64_t* kinds = (uint64_t*)(tp + thr * 2);
     const uint32_t* total = b.cursor + (size_t)s.nb + 1;  // padded entry total of this part (never advanced by the scatter)
     int h = prof_begin(3, st);
     const uint4* in = (const uint4*)d_bases;
@@ -1706,8 +1709,9 @@ static int msm_acc_phase_tree(const void* d_bases, size_t n, const MsmShape& s, 
         uint4* out = (level & 1) ? bufA : bufB;
         const size_t pairs_ub = cap >> level;
         const uint32_t* srt = level == 1 ? b.sorted : nullptr;
-        if (g_tree_cfg == 1) CQB_TRY(tree_level_launch<8>(in, srt, total, level, pairs_ub, pf, tot, tp, kinds, out, st));
-        else CQB_TRY(tree_level_launch<16>(in, srt, total, level, pairs_ub, pf, tot, tp, kinds, out, st));
+        if (g_tree_cfg == 2) CQB_TRY(tree_level_launch<8>(in, srt, total, level, pairs_ub, pf, tot, tp, kinds, out, st));
+        else if (g_tree_cfg == 1) CQB_TRY(tree_level_launch<16>(in, srt, total, level, pairs_ub, pf, tot, tp, kinds, out, st));
+        else CQB_TRY(tree_level_launch<32>(in, srt, total, level, pairs_ub, pf, tot, tp, kinds, out, st));
         in = out;
     }
     // the remaining list: cap >> pad_log points, bucket d owns [offs[d], offs[d+1])
