@@ -182,6 +182,16 @@ def _full_msm_vs_oracle(env, oracle, log_n, host_paths):
             assert lib.cqb_bases_precomputed_window_bits(h.value) >= 16
             got_t = _msm_dev(L, lib, h.value, d_s, n)
             assert np.array_equal(got_t, exp), "table layout differs from the oracle"
+            # at these sizes the automatic choice is the affine tree (>= 40 entries per bucket): that is the path just checked ...
+            assert lib.cqb_msm_last_tree_levels() >= 2, "the affine-tree accumulation was expected here"
+            # ... and the XYZZ accumulation it replaces gives the same point
+            L.check(lib.cqb_msm_set_accumulator(1, 0))
+            try:
+                got_x = _msm_dev(L, lib, h.value, d_s, n)
+                assert lib.cqb_msm_last_tree_levels() == 0
+            finally:
+                L.check(lib.cqb_msm_set_accumulator(0, 0))
+            assert np.array_equal(got_x, exp), "table layout with XYZZ accumulation differs from the oracle"
             if host_paths:
                 out = np.zeros(8, np.uint64)
                 inf = ctypes.c_int(0)
