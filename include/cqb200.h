@@ -339,6 +339,11 @@ CQB_API int cqb_msm_set_parts(int parts);
 CQB_API int cqb_msm_set_accumulator(int mode, int affine_seg_log);
 /* depth of the affine tree when variant 3 is forced: 1..6, default 4 */
 CQB_API int cqb_msm_set_tree_levels(int levels);
+/* sorting of the digits into bucket order: 0 = automatic = 1 = the one-thread-per-scalar scatter; 2 = the partitioned sort (tile-local sort by
+ * the top 9 bits of the bucket id in shared memory, then per-bin count and placement) whenever the shape allows (window bits 11..22, one
+ * bucket set). Measured slower on B200 (2^24: 6.2 ms against 4.5 ms, profiles/r02_partitioned_sort.md); selectable and parity-tested.
+ * Results do not depend on it. */
+CQB_API int cqb_msm_set_sort_mode(int mode);
 /* tree depth the most recent MSM's accumulation ran with (its largest part); 0 = XYZZ mixed additions only */
 CQB_API int cqb_msm_last_tree_levels(void);
 

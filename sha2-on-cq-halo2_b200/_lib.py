@@ -110,6 +110,7 @@ SYMBOLS = [
     ("cqb_msm_set_parts", _int, [_int]),
     ("cqb_msm_set_accumulator", _int, [_int, _int]),
     ("cqb_msm_set_tree_levels", _int, [_int]),
+    ("cqb_msm_set_sort_mode", _int, [_int]),
     ("cqb_msm_last_tree_levels", _int, []),
     ("cqb_msm_set_profiling", _int, [_int]),
     ("cqb_msm_phase_ms", _int, [ctypes.POINTER(ctypes.c_float), _int]),

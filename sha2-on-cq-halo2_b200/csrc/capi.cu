@@ -1559,7 +1559,14 @@ int cqb_msm_set_accumulator(int mode, int affine_seg_log) {
     msm_set_affine_segment(affine_seg_log);
     if (const char* v = getenv("CQB_AFF_VARIANT")) msm_set_affine_variant(atoi(v));
     if (const char* v = getenv("CQB_TREE_LEVELS")) msm_set_tree_levels(atoi(v));
+    if (const char* v = getenv("CQB_SORT")) msm_set_sort_mode(atoi(v));
     if (const char* v = getenv("CQB_TREE_CFG")) msm_set_tree_config(atoi(v), strchr(v, ',') ? atoi(strchr(v, ',') + 1) : 0);
+    return 0;
+}
+int cqb_msm_set_sort_mode(int mode) {
+    LOCK;
+    if (mode < 0 || mode > 2) return fail(CQB_E_BAD_ARG, "cqb_msm_set_sort_mode: 0..2");
+    msm_set_sort_mode(mode);
     return 0;
 }
 int cqb_msm_last_tree_levels(void) { return msm_last_tree_levels(); }

@@ -59,6 +59,7 @@ int msm_run_precomputed(const void* d_table, size_t table_n, int c, size_t offse
                         MsmFeeder* feeder = nullptr);
 void msm_set_parts(int p);
 void msm_set_accumulator(int mode);     // 0 auto | 1 XYZZ mixed additions | 2 batched affine streams | 3 affine tree
+void msm_set_sort_mode(int m);           // 0 auto | 1 one-thread-per-scalar scatter | 2 partitioned sort whenever the shape allows
 void msm_set_tree_levels(int levels);
 int msm_last_tree_levels();
 void msm_set_tree_config(int cfg, int dbg);  // experiments

@@ -427,6 +427,168 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint4* __restric
     }
 }
 
+// (3') PARTITIONED SORT for one large bucket set (single-set layout, c >= 11) — an experiment that did NOT pay (see use_part_sort): kept
+// selectable and parity-tested (tests/test_gpu_partitioned_sort.py). The one-thread-per-scalar
+// scatter above issues one L2 atomic and one scattered 4 B store per list entry (218 M of each at 2^24: 1.17 ms count + 3.34 ms
+// scatter). Here the bucket id (c - 1 bits) is split into 9 coarse + F fine bits:
+//   msm_part_kernel      a CTA takes a TILE of 256 x spt scalars, derives their digits and sorts the tile's entries by COARSE bin in
+//                        shared memory (histogram, scan, placement: shared-memory atomics only), then writes them out coalesced as
+//                        (fine id, entry) pairs, with the tile's 513 bin offsets beside them;
+//   msm_part_bin_kernel  work item = (coarse bin, chunk of tiles): reads that bin's segment of every tile of the chunk, counts the fine
+//                        ids in shared memory and adds the non-zero counts to the global histogram (COUNT), or — after the same scans
+//                        as before — reserves its share of every bucket with one global atomic per bucket and places the entries
+//                        (PLACE); all stores of a bin land in that bin's ~1.7 MB window of the list.
+// Global atomics drop from 2 per entry to ~2 per (work item, bucket); the order inside a bucket is as arbitrary as before.
+constexpr int PS_THREADS = 256;
+constexpr int PS_COARSE_LOG = 9;
+constexpr int PS_COARSE = 1 << PS_COARSE_LOG;
+constexpr int PS_TAB = PS_COARSE + 2;  // uint16 offsets per tile: 513 used, padded to an even count
+static inline int part_spt(int nwin) { return nwin <= 16 ? 3 : 2; }  // scalars per thread: 256 x spt x nwin <= 12288 entries per tile
+// slot reservation in a shared-memory counter array, warp-aggregated when lanes share a key (hot buckets would serialise otherwise);
+// key 0 = no entry. Returns the slot (COUNT_ONLY: nothing).
+template <bool WANT_SLOT>
+__device__ __forceinline__ uint32_t smem_reserve(uint32_t* counters, uint32_t key) {  // counters[key - 1]
+    const uint32_t lane = threadIdx.x & 31u;
+    const int mode = warp_key_mode(key);
+    uint32_t slot = 0;
+    if (mode == 0) return 0;
+    if (mode == 2) {
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
+        uint32_t base = 0;
+        if (key && lane == leader) base = atomicAdd(counters + (key - 1), (uint32_t)__popc(peers));
+        if (WANT_SLOT) slot = __shfl_sync(0xffffffffu, base, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+    } else if (key) {
+        slot = atomicAdd(counters + (key - 1), 1u);
+    }
+    return slot;
+}
+__global__ void __launch_bounds__(PS_THREADS, 2) msm_part_kernel(const uint4* __restrict__ scalars, const uint32_t* __restrict__ idx, size_t n,
+                                                                 MsmShape s, int spt, int fine_bits, uint2* __restrict__ local,
+                                                                 uint16_t* __restrict__ tab) {
+    extern __shared__ uint4 ps_sm[];
+    uint32_t* hist = (uint32_t*)ps_sm;         // [512] counts, then running cursors
+    uint32_t* offs = hist + PS_COARSE;         // [513] exclusive offsets
+    uint2* ent = (uint2*)(offs + PS_COARSE + 4);  // [cap] the tile's entries in coarse-bin order (1028 words before it: 8 B aligned)
+    const uint32_t cap = (uint32_t)(PS_THREADS * spt * s.nwin);
+    const size_t tile = blockIdx.x, first = tile * (size_t)(PS_THREADS * spt);
+    for (int b = threadIdx.x; b < PS_COARSE; b += PS_THREADS) hist[b] = 0;
+    __syncthreads();
+    Fr k[3];
+    uint32_t pid[3];
+    bool act[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const size_t i = first + (size_t)j * PS_THREADS + threadIdx.x;
+        act[j] = j < spt && i < n;
+        k[j] = act[j] ? load_scalar_canonical(scalars, i) : Fr::zero();
+        pid[j] = act[j] ? (idx ? __ldg(idx + i) : (uint32_t)i + s.offset) : 0u;
+    }
+    const uint32_t fine_mask = (1u << fine_bits) - 1u;
+    // pass 1: coarse histogram
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        if (j >= spt) break;
+        uint32_t carry = 0;
+        for (int w = 0; w < s.nwin; w++) {
+            uint32_t d = window_bits(k[j].l, w, s.c) + carry;
+            carry = 0;
+            if (d > s.nb) { d = (1u << s.c) - d; carry = 1; }
+            const uint32_t key = (act[j] && d) ? ((d - 1u) >> fine_bits) + 1u : 0u;
+            smem_reserve<false>(hist, key);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {  // exclusive scan of the 512 counts: 16 per lane + a warp scan
+        const int lane = threadIdx.x;
+        uint32_t v[16], sum = 0;
+#pragma unroll
+        for (int q = 0; q < 16; q++) { v[q] = hist[lane * 16 + q]; sum += v[q]; }
+        uint32_t x = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
+            if (lane >= off) x += y;
+        }
+        uint32_t run = x - sum;
+#pragma unroll
+        for (int q = 0; q < 16; q++) { offs[lane * 16 + q] = run; hist[lane * 16 + q] = run; run += v[q]; }
+        if (lane == 31) offs[PS_COARSE] = run;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b <= PS_COARSE; b += PS_THREADS) tab[tile * PS_TAB + b] = (uint16_t)offs[b];
+    // pass 2: placement in shared memory
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        if (j >= spt) break;
+        uint32_t carry = 0;
+        for (int w = 0; w < s.nwin; w++) {
+            uint32_t d = window_bits(k[j].l, w, s.c) + carry;
+            carry = 0;
+            uint32_t neg = 0;
+            if (d > s.nb) { d = (1u << s.c) - d; carry = 1; neg = 1; }
+            const bool has = act[j] && d;
+            const uint32_t key = has ? ((d - 1u) >> fine_bits) + 1u : 0u;
+            const uint32_t slot = smem_reserve<true>(hist, key);
+            if (has) ent[slot] = make_uint2((d - 1u) & fine_mask, ((pid[j] + (uint32_t)w * s.table_n) << 1) | neg);
+        }
+    }
+    __syncthreads();
+    const uint32_t total = offs[PS_COARSE];
+    uint2* dst = local + tile * (size_t)cap;
+    for (uint32_t e = threadIdx.x; e < total; e += PS_THREADS) dst[e] = ent[e];
+}
+template <bool PLACE>
+__global__ void __launch_bounds__(PS_THREADS) msm_part_bin_kernel(const uint2* __restrict__ local, const uint16_t* __restrict__ tab, uint32_t ntiles,
+                                                                  uint32_t cap, int fine_bits, uint32_t tiles_per_chunk,
+                                                                  uint32_t* __restrict__ counters /* hist (COUNT) or cursor (PLACE), by bucket id */,
+                                                                  uint32_t* __restrict__ sorted) {
+    extern __shared__ uint4 ps_sm[];
+    uint32_t* fh = (uint32_t*)ps_sm;            // [2^F] counts, then running cursors
+    uint32_t* base = fh + ((size_t)1 << fine_bits);  // [2^F] PLACE: reserved start of this work item's share of every bucket
+    const uint32_t bin = blockIdx.y, nfine = 1u << fine_bits;
+    const uint32_t t0 = blockIdx.x * tiles_per_chunk, t1 = min(t0 + tiles_per_chunk, ntiles);
+    for (uint32_t f = threadIdx.x; f < nfine; f += PS_THREADS) fh[f] = 0;
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    // every lane walks the segment of ITS OWN tile (32 tiles per warp step): the 32 offset reads and then the 32 entry reads of a step are
+    // independent — one tile per warp at a time was a chain of dependent loads per 19-entry segment and ran 8x slower
+    for (uint32_t tb = t0 + warp * 32; tb < t1; tb += PS_THREADS) {
+        const uint32_t t = tb + lane;
+        uint32_t a = 0, e = 0;
+        if (t < t1) { a = tab[(size_t)t * PS_TAB + bin]; e = tab[(size_t)t * PS_TAB + bin + 1]; }
+        const uint2* seg = local + (size_t)t * cap + a;
+        const uint32_t len = e - a, maxlen = __reduce_max_sync(0xffffffffu, len);
+        for (uint32_t q = 0; q < maxlen; q++) smem_reserve<false>(fh, q < len ? __ldg(&seg[q].x) + 1u : 0u);
+    }
+    __syncthreads();
+    const uint32_t bucket0 = 1u + (bin << fine_bits);  // bucket id of fine id 0
+    if (!PLACE) {
+        for (uint32_t f = threadIdx.x; f < nfine; f += PS_THREADS)
+            if (fh[f]) atomicAdd(counters + bucket0 + f, fh[f]);
+        return;
+    }
+    for (uint32_t f = threadIdx.x; f < nfine; f += PS_THREADS) {
+        const uint32_t c = fh[f];
+        base[f] = c ? atomicAdd(counters + bucket0 + f, c) : 0u;
+        fh[f] = 0;
+    }
+    __syncthreads();
+    for (uint32_t tb = t0 + warp * 32; tb < t1; tb += PS_THREADS) {
+        const uint32_t t = tb + lane;
+        uint32_t a = 0, e = 0;
+        if (t < t1) { a = tab[(size_t)t * PS_TAB + bin]; e = tab[(size_t)t * PS_TAB + bin + 1]; }
+        const uint2* seg = local + (size_t)t * cap + a;
+        const uint32_t len = e - a, maxlen = __reduce_max_sync(0xffffffffu, len);
+        for (uint32_t q = 0; q < maxlen; q++) {
+            uint2 x = make_uint2(0, 0);
+            if (q < len) x = __ldg(seg + q);
+            const uint32_t slot = smem_reserve<true>(fh, q < len ? x.x + 1u : 0u);
+            if (q < len) sorted[base[x.x] + slot] = x.y;
+        }
+    }
+}
+
 // the largest d in [lo, hi] with o[d] <= pos
 __device__ __forceinline__ uint32_t bucket_of_pos(const uint32_t* __restrict__ o, uint32_t lo, uint32_t hi, uint32_t pos) {
     while (lo < hi) {
@@ -1305,7 +1467,7 @@ __global__ void __launch_bounds__(128) g1_batch_normalize_kernel(const uint4* __
 // -------------------------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------------------------
-static PerDevice<Scratch> g_hist, g_sorted, g_buckets, g_partials, g_chunks, g_pre_tmp, g_aff;
+static PerDevice<Scratch> g_hist, g_sorted, g_buckets, g_partials, g_chunks, g_pre_tmp, g_aff, g_part;
 
 // Second stream (high priority) for the sort phases (count / scan / scatter) of part p+1 of a large MSM, which overlap the
 // bucket accumulation of part p on the main stream: the sort is atomics/latency bound, the accumulation multiplier bound.
@@ -1380,6 +1542,7 @@ void msm_release_scratch() {
     g_chunks->release();
     g_pre_tmp->release();
     g_aff->release();
+    g_part->release();
 }
 // working set of one MSM of n points over a single-set table with nwin windows, beyond the scalars: sorted list, tree scratch (parts
 // are capped at TREE_PART_ENTRIES entries), histograms / bucket arrays / chunk partials
@@ -1397,6 +1560,7 @@ void msm_release_all() {
     g_chunks->release();
     g_pre_tmp->release();
     g_aff->release();
+    g_part->release();
     for (auto& sp : g_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     g_spans.clear();
     g_spans_used = 0;
@@ -1535,11 +1699,74 @@ static PartBuf part_buf(const MsmShape& s, const PartPlan& pl, int part) {
     return b;
 }
 
+// partitioned sort (kernel comment above): tile pass, per-bin count, the usual scans, per-bin placement
+static int g_sort_mode = 0;  // experiments / tests: 0 = automatic, 1 = one-thread-per-scalar scatter, 2 = partitioned whenever the shape allows
+void msm_set_sort_mode(int m) { g_sort_mode = m; }
+static bool use_part_sort(size_t n, const MsmShape& s) {
+    if (g_sort_mode == 1 || !s.single || s.nsets != 1 || s.c < PS_COARSE_LOG + 2 || s.c > 22) return false;
+    (void)n;
+    return g_sort_mode == 2;  // measured SLOWER than the scatter (2^24: 2.1 + 1.0 + 3.1 ms against 1.17 + 3.34 ms, profiles/r02_partitioned_sort.md): opt-in only
+}
+static size_t part_scratch_bytes(size_t n, const MsmShape& s) {
+    const int spt = part_spt(s.nwin);
+    const size_t ntiles = (n + (size_t)PS_THREADS * spt - 1) / ((size_t)PS_THREADS * spt);
+    return ntiles * ((size_t)PS_THREADS * spt * s.nwin * 8 + PS_TAB * 2) + 64;
+}
+static int msm_sort_phase_partitioned(const void* d_scalars, const uint32_t* d_idx, size_t n, const MsmShape& s, const PartPlan& pl, const PartBuf& b,
+                                      cudaStream_t st) {
+    const int spt = part_spt(s.nwin), fine_bits = s.c - 1 - PS_COARSE_LOG;
+    const uint32_t cap = (uint32_t)(PS_THREADS * spt * s.nwin);
+    const size_t ntiles = (n + (size_t)PS_THREADS * spt - 1) / ((size_t)PS_THREADS * spt);
+    CQB_TRY(g_part->ensure(part_scratch_bytes(n, s)));
+    uint2* local = g_part->as<uint2>();
+    uint16_t* tab = (uint16_t*)(local + ntiles * cap);
+    const size_t smem1 = 1028 * 4 + (size_t)cap * 8, smem2 = ((size_t)2 << fine_bits) * 4;
+    static bool attr[MAX_DEVICES] = {};
+    if (!attr[cur_slot()]) {
+        CQB_CUDA(cudaFuncSetAttribute(msm_part_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1028 * 4 + 12288 * 8));
+        CQB_CUDA(cudaFuncSetAttribute(msm_part_bin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CQB_CUDA(cudaFuncSetAttribute(msm_part_bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr[cur_slot()] = true;
+    }
+    // work items per coarse bin: chunks of tiles holding ~8 k entries of the bin when the digits are uniform
+    const uint32_t per_tile = std::max<uint32_t>(1u, cap / PS_COARSE);
+    uint32_t tiles_per_chunk = std::max<uint32_t>(32u, 8192u / per_tile);
+    uint32_t chunks = (uint32_t)((ntiles + tiles_per_chunk - 1) / tiles_per_chunk);
+    if (chunks > 128u) { chunks = 128u; tiles_per_chunk = (uint32_t)((ntiles + chunks - 1) / chunks); chunks = (uint32_t)((ntiles + tiles_per_chunk - 1) / tiles_per_chunk); }
+    const dim3 grid2(chunks, PS_COARSE);
+    int h = prof_begin(0, st);
+    msm_part_kernel<<<(unsigned)ntiles, PS_THREADS, smem1, st>>>((const uint4*)d_scalars, d_idx, n, s, spt, fine_bits, local, tab);
+    CQB_LAUNCHED();
+    msm_part_bin_kernel<false><<<grid2, PS_THREADS, smem2, st>>>(local, tab, (uint32_t)ntiles, cap, fine_bits, tiles_per_chunk, b.hist, nullptr);
+    CQB_LAUNCHED();
+    prof_end(h, st);
+    h = prof_begin(1, st);
+    if (s.nb > 32768) {
+        scan_tile_sums_kernel<<<pl.ntiles, 1024, 0, st>>>(b.hist, s.nb, b.tile_sums, pl.ntiles, s.pad_log);
+        CQB_LAUNCHED();
+        scan_tile_offsets_kernel<<<1, 1024, 0, st>>>(b.tile_sums, pl.ntiles);
+        CQB_LAUNCHED();
+        scan_apply_kernel<<<pl.ntiles, 1024, 0, st>>>(b.hist, s.nb, b.tile_sums, pl.ntiles, b.offs, b.cursor, b.nonempty, s.pad_log, b.sorted);
+        CQB_LAUNCHED();
+    } else {
+        msm_scan_kernel<<<1, 1024, 0, st>>>(b.hist, b.offs, b.cursor, s, b.nonempty, b.sorted);
+        CQB_LAUNCHED();
+    }
+    prof_end(h, st);
+    h = prof_begin(2, st);
+    msm_part_bin_kernel<true><<<grid2, PS_THREADS, smem2, st>>>(local, tab, (uint32_t)ntiles, cap, fine_bits, tiles_per_chunk, b.cursor, b.sorted);
+    CQB_LAUNCHED();
+    prof_end(h, st);
+    CQB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // d_bases: windowed layout -> element 0 of the registered set (pid = offset + i); single-set layout -> the table base.
 static int msm_sort_phase(const void* d_scalars, const uint32_t* d_idx, size_t n, const MsmShape& s, const PartPlan& pl, const PartBuf& b,
                           cudaStream_t st) {
     CQB_CUDA(cudaMemsetAsync(b.hist, 0, pl.hist_words * 4, st));
     CQB_CUDA(cudaMemsetAsync(b.nonempty, 0, 4, st));
+    if (use_part_sort(n, s)) return msm_sort_phase_partitioned(d_scalars, d_idx, n, s, pl, b, st);
     int h = prof_begin(0, st);
     unsigned gN = (unsigned)((n + 255) / 256);
     const dim3 gridN(gN, s.single ? (unsigned)s.nsets : 1u);
