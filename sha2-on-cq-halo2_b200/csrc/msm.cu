@@ -563,11 +563,10 @@ __global__ void __launch_bounds__(PS_THREADS) msm_part_bin_kernel(const uint2* _
     }
     __syncthreads();
     const uint32_t bucket0 = 1u + (bin << fine_bits);  // bucket id of fine id 0
-    if (!PLACE) {
+    if constexpr (!PLACE) {
         for (uint32_t f = threadIdx.x; f < nfine; f += PS_THREADS)
             if (fh[f]) atomicAdd(counters + bucket0 + f, fh[f]);
-        return;
-    }
+    } else {
     for (uint32_t f = threadIdx.x; f < nfine; f += PS_THREADS) {
         const uint32_t c = fh[f];
         base[f] = c ? atomicAdd(counters + bucket0 + f, c) : 0u;
@@ -586,6 +585,7 @@ __global__ void __launch_bounds__(PS_THREADS) msm_part_bin_kernel(const uint2* _
             const uint32_t slot = smem_reserve<true>(fh, q < len ? x.x + 1u : 0u);
             if (q < len) sorted[base[x.x] + slot] = x.y;
         }
+    }
     }
 }
 
