@@ -281,7 +281,11 @@ int cqb_bases_register(const uint64_t* affine_xy, size_t n, cqb_bases_t* out) {
     CQB_TRY(require_init());
     if (!out || (!affine_xy && n)) return fail(CQB_E_BAD_ARG, "cqb_bases_register: NULL argument");
     void* d = nullptr;
-    if (cudaMalloc(&d, n ? n * 64 : 64) != cudaSuccess) return fail(CQB_E_OOM, "cudaMalloc(%zu) for bases failed", n * 64);
+    if (cudaMalloc(&d, n ? n * 64 : 64) != cudaSuccess) {
+        cudaGetLastError();
+        msm_release_scratch();
+        if (cudaMalloc(&d, n ? n * 64 : 64) != cudaSuccess) { cudaGetLastError(); return fail(CQB_E_OOM, "cudaMalloc(%zu) for bases failed", n * 64); }
+    }
     if (n) CQB_CUDA(cudaMemcpyAsync(d, affine_xy, n * 64, cudaMemcpyHostToDevice, g_ctx.stream));
     CQB_CUDA(cudaStreamSynchronize(g_ctx.stream));
     cqb_bases_t h = g_next_handle++;
@@ -1412,7 +1416,11 @@ int cqb_dev_alloc(size_t bytes, void** d_out) {
     if (!d_out) return fail(CQB_E_BAD_ARG, "cqb_dev_alloc: NULL argument");
     if (cudaMalloc(d_out, bytes ? bytes : 32) != cudaSuccess) {
         cudaGetLastError();
-        return fail(CQB_E_OOM, "cudaMalloc(%zu) failed", bytes);
+        msm_release_scratch();  // the MSM's grow-only working buffers (up to ~20 GB after a 2^24+ MSM) make room; the next MSM reallocates
+        if (cudaMalloc(d_out, bytes ? bytes : 32) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(CQB_E_OOM, "cudaMalloc(%zu) failed", bytes);
+        }
     }
     return 0;
 }
@@ -1481,6 +1489,11 @@ int cqb_dev_alloc_on(int slot, size_t bytes, void** d_out) {
     if (!d_out) return fail(CQB_E_BAD_ARG, "cqb_dev_alloc_on: NULL argument");
     bind_slot(slot);
     cudaError_t e = cudaMalloc(d_out, bytes ? bytes : 64);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        msm_release_scratch();
+        e = cudaMalloc(d_out, bytes ? bytes : 64);
+    }
     bind_slot(0);
     if (e != cudaSuccess) { cudaGetLastError(); return fail(CQB_E_OOM, "cudaMalloc(%zu) on slot %d failed", bytes, slot); }
     return 0;
