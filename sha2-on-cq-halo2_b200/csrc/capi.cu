@@ -1573,7 +1573,7 @@ int cqb_msm_set_accumulator(int mode, int affine_seg_log) {
     if (const char* v = getenv("CQB_AFF_VARIANT")) msm_set_affine_variant(atoi(v));
     if (const char* v = getenv("CQB_TREE_LEVELS")) msm_set_tree_levels(atoi(v));
     if (const char* v = getenv("CQB_SORT")) msm_set_sort_mode(atoi(v));
-    if (const char* v = getenv("CQB_TREE_CFG")) msm_set_tree_config(atoi(v), strchr(v, ',') ? atoi(strchr(v, ',') + 1) : 0);
+    if (const char* v = getenv("CQB_TREE_SLABS")) msm_set_tree_slabs(atoi(v));
     return 0;
 }
 int cqb_msm_set_sort_mode(int mode) {

@@ -62,7 +62,7 @@ void msm_set_accumulator(int mode);     // 0 auto | 1 XYZZ mixed additions | 2 b
 void msm_set_sort_mode(int m);           // 0 auto | 1 one-thread-per-scalar scatter | 2 partitioned sort whenever the shape allows
 void msm_set_tree_levels(int levels);
 int msm_last_tree_levels();
-void msm_set_tree_config(int cfg, int dbg);  // experiments
+void msm_set_tree_slabs(int slabs);          // experiments: slabs per level of the affine tree (0 = automatic)
 void msm_set_affine_segment(int seg_log);
 void msm_set_affine_variant(int v);
 // bounds[0..nparts]: the point ranges the parts of an MSM cover (small_first: host-pointer MSMs, see msm.cu)
