@@ -136,3 +136,42 @@ def test_tree_host_pointer_parts(cq, oracle, tree):
     finally:
         cq._lib.check(lib.cqb_msm_set_parts(0))
         dev.free()
+
+
+@pytest.mark.parametrize("kind", ["all_equal", "few_values", "small", "negative_small"])
+def test_tree_automatic_choice_on_skewed_scalars(cq, oracle, kind):
+    """2^21 points: the automatic choice (no forcing) takes the tree from 24 M list entries on, whatever the digits look like — a handful of
+    giant buckets (the long-bucket merge behind the tree), or most windows empty"""
+    lib = cq._lib.lib()
+    cq._lib.check(lib.cqb_msm_set_accumulator(0, 0))
+    n = 1 << 21
+    bases = oracle.synth_bases(7001, n, 8)
+    sc = oracle.synth_scalars(7002, n)
+    rng = np.random.default_rng(11)
+    if kind == "all_equal":
+        sc[:] = sc[0]
+    elif kind == "few_values":
+        sc = sc[rng.integers(0, 7, n)]
+    elif kind == "small":                                    # 16-bit values: every window but the lowest is empty
+        small = P.fr_array_from_ints(list(range(1 << 16)))
+        sc = small[rng.integers(0, 1 << 16, n)]
+    elif kind == "negative_small":
+        sc[:] = oracle.synth_scalars(7003, 1)[0]
+        sc[::2] = L(P.to_mont(P.R_MOD - 5, P.R_MOD))
+    import ctypes
+
+    Lb = cq._lib
+    dev = cq.DeviceBases(bases, precompute=True)
+    d_s = ctypes.c_void_p()
+    Lb.check(lib.cqb_dev_alloc(n * 32, ctypes.byref(d_s)))
+    try:
+        _, exp = oracle.best_multiexp(sc, bases, oracle.hw_threads())
+        sc = np.ascontiguousarray(sc)
+        Lb.check(lib.cqb_memcpy_h2d(d_s, sc.ctypes.data_as(ctypes.c_void_p), n * 32))
+        out, inf = np.zeros(8, np.uint64), ctypes.c_int(0)
+        Lb.check(lib.cqb_msm_bn254_g1_dev(dev.handle, 0, d_s, n, Lb.p64(out), ctypes.byref(inf)))  # device-resident scalars: one part
+        assert lib.cqb_msm_last_tree_levels() >= 2
+        assert np.array_equal(out, exp)
+    finally:
+        Lb.check(lib.cqb_dev_free(d_s))
+        dev.free()
