@@ -60,8 +60,13 @@ for lg in range(16, max_log + 1, 2):
     res["msm_windowed"].append({"log_n": lg, "ms": round(ms_w, 4), "mpts": round(n / ms_w / 1e3, 2)})
     L.check(lib.cqb_bases_precompute(h.value, 0))
     ms = timed(run, reps)
-    res["msm_uniform"].append({"log_n": lg, "ms": round(ms, 4), "mpts": round(n / ms / 1e3, 2),
-                               "int_roofline_frac": round(n * 21760 / (ms * 1e-3) / 1e12 / INT_PEAK, 3)})
+    # whole-MSM reading: the MAD32 the accumulation EXECUTES per point (bench.py mad32_per_entry) and, beside it, SURVEY's pinned 21,760
+    lv = int(lib.cqb_msm_last_tree_levels())
+    nwin = 254 // int(lib.cqb_bases_precomputed_window_bits(h.value)) + 1
+    per_entry = 1232.0 if lv == 0 else (1 - 2.0 ** -lv) * 796.5 + 2.0 ** -lv * 1232
+    res["msm_uniform"].append({"log_n": lg, "ms": round(ms, 4), "mpts": round(n / ms / 1e3, 2), "affine_tree_levels": lv,
+                               "int_executed_frac": round(n * nwin * per_entry / (ms * 1e-3) / 1e12 / INT_PEAK, 3),
+                               "int_pinned_algorithm_frac": round(n * 21760 / (ms * 1e-3) / 1e12 / INT_PEAK, 3)})
     if lg == 22:  # skewed scalar distributions, same bases
         rng = np.random.default_rng(7)
         full = np.zeros((n, 4), np.uint64)
