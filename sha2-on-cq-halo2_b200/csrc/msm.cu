@@ -861,7 +861,7 @@ __device__ __forceinline__ void aft_backward_tile(const uint4* __restrict__ pts,
     aft_load_raw<GATHER>(raw, nq);
     uint2 ne = aft_entry<GATHER>(sorted, AFT_P(T > 1 ? T - 2 : 0), T > 1 && AFT_P(T - 2) < npairs);
     Fq npre = (T > 1 && AFT_P(T - 1) < npairs) ? ld_fq(pf + AFT_P(T - 2) * 2) : Fq::one();
-#pragma unroll 1
+#pragma unroll 1  // unrolled by 2: 144-150 registers, 3 CTAs per SM, 30.0 ms against 27.7 ms for the phase at 2^24
     for (int i = T - 1; i >= 0; i--) {
         const AftPair q = nq;
         Fq xa, ya, xb, yb;
@@ -911,7 +911,9 @@ __device__ __forceinline__ void aft_backward_tile(const uint4* __restrict__ pts,
 // two roles interleaved (even / odd blockIdx): the forward pass is bound by its gathers (one multiplication per pair), the backward
 // pass by the multiplier pipe, so a later slab's forward pass runs in the shadow of an earlier slab's backward pass.
 template <bool GATHER, int T>
-__global__ void __launch_bounds__(AFT_NT) aft_level_kernel(const uint4* __restrict__ pts, const uint32_t* __restrict__ sorted,
+// 4 CTAs per SM (<= 128 registers, no spills): 27.7 ms for the phase at 2^24; left to the compiler 28.2 ms (124 registers + a spill), forced to 5
+// CTAs (96 registers, 300-500 B of spills) 30.5 ms
+__global__ void __launch_bounds__(AFT_NT, 4) aft_level_kernel(const uint4* __restrict__ pts, const uint32_t* __restrict__ sorted,
                                                           const uint32_t* __restrict__ total_entries, int level, unsigned fwd0, unsigned nfwd,
                                                           unsigned bwd0, unsigned nbwd, uint4* __restrict__ pf, uint4* __restrict__ tot,
                                                           uint64_t* __restrict__ kinds, uint4* __restrict__ out) {
