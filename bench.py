@@ -36,7 +36,7 @@ os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "SHA2-CQ prove ms; BN254 MSM Mpts/s @2^24; Fr NTT Gelem/s @2^24; 1/2/4/8 GPU"
 UNIT = "Mpts/s (BN254 G1 MSM @2^24)"
-TREE_TRAFFIC_2P24 = 83.9e9        # DRAM bytes of the accumulation phase of one 2^24 step, profiles/r02_launches_bench_2p24.csv
+TREE_TRAFFIC_2P24 = 82.7e9        # DRAM bytes of the accumulation phase of one 2^24 step, profiles/r02_launches_bench_2p24.csv
 MAD32_PER_POINT = 21760           # SURVEY.md §8(d), the PINNED algorithm: 16 windows x 10 modmul x 136 MAD32
 MAD32_PER_XYZZ_ADD = 1232         # what the kernel executes per bucket addition: 6 mul x 136 + 2 sqr x 108 + one fused a*b-c*d x 200
 # affine-tree pair addition: 5 mul x 136 + 1 sqr x 108 = 788, minus the two multiplications the first pair of a thread skips (2 x 136 / 16),
