@@ -54,3 +54,19 @@ def test_product_arm_line_has_roofline_e2e_and_cpu_baseline():
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert d["ntt"]["value"] > 0 and d["prove_ms"][0]["ms_per_proof"] > 0 and d["prove_ms_resident"][0]["ms_per_proof"] > 0
     assert d["prove_real_ms"][0]["quotient_identity_holds"] is True and d["prove_real_ms"][0]["ms_per_proof"] > 0
+
+
+def test_executed_work_model_of_the_accumulation():
+    """bench.py's MAD32-per-entry model: XYZZ alone at depth 0, the affine share growing with the tree depth"""
+    sys.path.insert(0, ROOT) if ROOT not in sys.path else None
+    import importlib
+
+    bench = importlib.import_module("bench")
+    assert bench.mad32_per_entry(0) == 1232 == 6 * 136 + 2 * 108 + 200
+    assert abs(bench.MAD32_PER_AFFINE_ADD - (5 * 136 + 108 - 17 + 25.5)) < 1e-9
+    prev = 1232.0
+    for levels in range(1, 7):
+        cur = bench.mad32_per_entry(levels)
+        assert bench.MAD32_PER_AFFINE_ADD < cur < prev
+        prev = cur
+    assert abs(13 * bench.mad32_per_entry(4) - 10708.34375) < 1e-6
