@@ -661,17 +661,21 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint4* __rest
 
 // (4'') AFFINE-TREE bucket accumulation. The bucket-sorted list is laid out with every bucket's run padded to a multiple of
 // S = 2^pad_log entries (AFT_PAD sentinels = identity), so that at every level l = 1..pad_log the pair (2p, 2p+1) of the
-// level's input list lies inside ONE bucket and all pair additions of a level are independent: level l is one launch of the
-// kernel below over the whole list, 218 M -> 109 M -> ... points, and after pad_log levels one affine point per S entries is
-// left; those (1/S of the additions) go through the XYZZ chunk kernel (DIRECT) and the usual merge. An affine addition costs
-// 5M + 1S = 788 MAD32 against 1,232 for the XYZZ mixed addition because its field inversion is shared: Montgomery's trick
-// over the AFT_T pairs of a thread (running products parked in shared memory), then over the AFT_THREADS threads of the CTA
-// (ONE warp inverts: lane l owns the totals of threads l, l+32, ... and runs the branch-free safegcd of fp.cuh once), i.e.
-// one inversion instruction stream per AFT_T * AFT_THREADS additions; the other CTA of the SM computes meanwhile. The backward
-// pass re-reads the points (L2; level 1 gathers them from the table again), finishes the additions and writes 64 B per pair,
-// coalesced. Exceptional pairs (reference batch_add, arithmetic/curves/src/derive/curve.rs:4-141, and the mixed addition's
-// branches :866-871): an identity operand (sentinel, identity base, an earlier P + (-P)) passes the other one through, P + P
-// joins the batch as a doubling (denominator 2y, numerator 3x^2), P + (-P) gives the identity. Identity = (0, 0).
+// level's input list lies inside ONE bucket and all pair additions of a level are independent: a level is a pass over the whole
+// list, 218 M -> 109 M -> ... points at 2^24, and after pad_log levels one affine point per S entries is left; those (1/S of the
+// additions) go through the XYZZ chunk kernel (DIRECT) and the usual merge. An affine addition costs 5M + 1S = 788 MAD32 against
+// 1,232 for the XYZZ mixed addition because its field inversion is shared by Montgomery's trick, in three launches per level:
+//   forward  (aft_forward_tile)   a thread owns T = 32 pairs (interleaved over the CTA for coalescing): denominators x2 - x1, their
+//                                 running product parked per pair (32 B), the thread's total, 2 kind bits per pair;
+//   invert   (aft_invert_kernel)  Montgomery's trick once more over 32 thread totals per thread and ONE branch-free safegcd inversion
+//                                 (fp.cuh) per thread: every lane inverts its own value, 32 x 32 x 32 additions per inversion stream;
+//   backward (aft_backward_tile)  peels the inverses off, lambda, x3, y3; 64 B per pair out, coalesced. Level 1 gathers its points
+//                                 from the table (four lanes per 64 B record, L2::64B loads), the other levels read the previous
+//                                 level's output.
+// aft_level_kernel runs the backward role of one slab of tiles and the forward role of the next in one launch. Exceptional pairs
+// (reference batch_add, arithmetic/curves/src/derive/curve.rs:4-141, and the mixed addition's branches :866-871): an identity operand
+// (sentinel, identity base, an earlier P + (-P)) passes the other one through, P + P joins the batch as a doubling (denominator 2y,
+// numerator 3x^2), P + (-P) gives the identity. Identity = (0, 0). Measurements and the variants that lost: profiles/r02_affine_tree.md.
 // the two operands of a pair: pointers to their 64 B records (nullptr = sentinel) and sign flags
 struct AftPair {
     const uint4 *pa, *pb;
