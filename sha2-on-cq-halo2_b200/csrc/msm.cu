@@ -912,11 +912,12 @@ __device__ __forceinline__ void aft_backward_tile(const uint4* __restrict__ pts,
     }
 }
 // One launch = the backward pass over the tiles [bwd0, bwd0 + nbwd) and the forward pass over [fwd0, fwd0 + nfwd) of a level, CTAs of the
-// two roles interleaved (even / odd blockIdx): the forward pass is bound by its gathers (one multiplication per pair), the backward
-// pass by the multiplier pipe, so a later slab's forward pass runs in the shadow of an earlier slab's backward pass.
-template <bool GATHER, int T>
+// two roles interleaved (even / odd blockIdx). The forward pass is bound by its gathers (one multiplication per pair), the backward pass
+// by the multiplier pipe; interleaving a later slab's forward pass with an earlier slab's backward pass buys 0.6 ms of the 28 at 2^24 with
+// two slabs and nothing beyond (both roles are limited by the same 16 warps per SM; profiles/r02_affine_tree.md).
 // 4 CTAs per SM (<= 128 registers, no spills): 27.7 ms for the phase at 2^24; left to the compiler 28.2 ms (124 registers + a spill), forced to 5
-// CTAs (96 registers, 300-500 B of spills) 30.5 ms
+// CTAs (96 registers, 300-500 B of spills) 30.5 ms.
+template <bool GATHER, int T>
 __global__ void __launch_bounds__(AFT_NT, 4) aft_level_kernel(const uint4* __restrict__ pts, const uint32_t* __restrict__ sorted,
                                                           const uint32_t* __restrict__ total_entries, int level, unsigned fwd0, unsigned nfwd,
                                                           unsigned bwd0, unsigned nbwd, uint4* __restrict__ pf, uint4* __restrict__ tot,
